@@ -1,0 +1,1174 @@
+/*
+ * dsim_api.cu — the C ABI of include/dsim.h: state ownership, host<->HBM conversion, step driver.
+ *
+ * Mirrors what `run` (src/cli.rs:123-156) holds between steps: State {families, t, p, patches}
+ * (lib.rs:292-318), the `storage` map returned by `step`, and the `nearby_cache`.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "dsim_kernels.h"
+#include "dsim_math.h"
+#include "dsim_reach.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf { /* one cudaMalloc'd array */
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char buf_[512];                                                                              \
+            std::snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(h, DSIM_ERR_CUDA, buf_);                                                         \
+        }                                                                                                \
+    } while (0)
+
+} // namespace
+
+struct dsim_handle {
+    dsim_params p;
+    dsim_options opt;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    LaunchGeom geom;
+    uint32_t n_nodes = 0, n_eco = 0;
+    std::vector<uint32_t> eco_off_h; /* [n+1] */
+    uint64_t n_near = 0, n_reach = 0, n_reach_padded = 0;
+
+    std::vector<void *> allocs; /* everything to cudaFree */
+    ReachTable rt;
+    PatchState ps;
+    FamCore fam[2];
+    FamHeavy hv;
+    StepScratch sc;
+    DevCtl *ctl = nullptr;
+    DevCtl *ctl_h = nullptr; /* pinned mirror */
+    double *mem_table_d = nullptr;
+    ModelConst mc;
+    std::vector<void *> fam_allocs; /* family-capacity dependent arrays */
+    uint64_t cap = 0, hs_cap = 0;
+    uint32_t hcap = 0, acap = 0;
+    uint32_t parity = 0;
+    bool mid_step = false;
+    uint32_t steps_since_check = 0;
+    uint64_t n_known = 0; /* families at the last host check */
+
+#if !defined(DSIM_EMU)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+#endif
+    bool graphs_valid = false;
+    bool profiling = false;
+    cudaEvent_t ev[DSIM_K_COUNT + 1] = {};
+    double k_ms[DSIM_K_COUNT] = {};
+    uint64_t k_launches[DSIM_K_COUNT] = {};
+    uint64_t total_launches = 0;
+
+    /* host snapshot for the getters */
+    bool snap_valid = false;
+    std::vector<uint64_t> s_id, s_culture;
+    std::vector<double> s_stored, s_lh;
+    std::vector<uint32_t> s_loc, s_size, s_till_adult, s_till_mut, s_misc, s_hs, s_hist_len;
+    std::vector<uint16_t> s_a_eco;
+    std::vector<double> s_a_val;
+    std::vector<uint32_t> s_a_n;
+
+    std::vector<uint32_t> storage_nodes; /* nodes named by dsim_set_storage */
+    std::string err;
+};
+
+namespace {
+
+int fail(dsim_handle *h, int code, const char *msg) {
+    if (h)
+        h->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+template <typename T> int dev_alloc(dsim_handle *h, T **out, size_t count, std::vector<void *> &list, bool zero = true) {
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    if (zero) CK(cudaMemsetAsync(p, 0, bytes, h->stream));
+    list.push_back(p);
+    *out = (T *)p;
+    return DSIM_OK;
+}
+
+template <typename T> int upload(dsim_handle *h, T *dst, const T *src, size_t count) {
+    if (count) CK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return DSIM_OK;
+}
+template <typename T> int download(dsim_handle *h, T *dst, const T *src, size_t count) {
+    if (count) CK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    return DSIM_OK;
+}
+
+int sync_ctl(dsim_handle *h) { /* device -> pinned host mirror */
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+int push_ctl(dsim_handle *h) {
+    CK(cudaMemcpyAsync(h->ctl, h->ctl_h, sizeof(DevCtl), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+void free_list(std::vector<void *> &l) {
+    for (void *p : l) cudaFree(p);
+    l.clear();
+}
+
+void destroy_graphs(dsim_handle *h) {
+#if !defined(DSIM_EMU)
+    for (int k = 0; k < 2; ++k)
+        if (h->gexec[k]) {
+            cudaGraphExecDestroy(h->gexec[k]);
+            h->gexec[k] = nullptr;
+        }
+#endif
+    h->graphs_valid = false;
+}
+
+StepArgs make_args(dsim_handle *h, uint32_t parity) {
+    StepArgs a;
+    a.cur = h->fam[parity];
+    a.next = h->fam[parity ^ 1u];
+    a.hv = h->hv;
+    a.ps = h->ps;
+    a.rt = h->rt;
+    a.sc = h->sc;
+    a.ctl = h->ctl;
+    a.mc = h->mc;
+    a.parity = parity;
+    return a;
+}
+
+/* family-capacity dependent allocations; preserves the contents of the first `keep` families / slots */
+int alloc_families(dsim_handle *h, uint64_t new_cap) {
+    if (new_cap > 0xFFFFFF00ull) return fail(h, DSIM_ERR_CAPACITY, "family capacity exceeds 2^32");
+    new_cap = (new_cap + 255) & ~(uint64_t)255;
+    std::vector<void *> fresh;
+    FamCore nf[2];
+    FamHeavy nh = h->hv;
+    StepScratch ns;
+    std::memset(&ns, 0, sizeof ns);
+    const uint64_t old_cap = h->cap, old_hs = h->hs_cap;
+    const uint64_t hs_cap = new_cap;
+    int rc;
+#define A(ptr, count)                                     \
+    if ((rc = dev_alloc(h, &(ptr), (count), fresh)) != 0) { \
+        free_list(fresh);                                 \
+        return rc;                                        \
+    }
+    for (int b = 0; b < 2; ++b) {
+        A(nf[b].id, new_cap) A(nf[b].culture, new_cap) A(nf[b].stored, new_cap) A(nf[b].last_harvest, new_cap)
+        A(nf[b].loc, new_cap) A(nf[b].size, new_cap) A(nf[b].till_adult, new_cap) A(nf[b].till_mut, new_cap)
+        A(nf[b].misc, new_cap) A(nf[b].hs, new_cap)
+    }
+    A(nh.hist_cnt, hs_cap) A(nh.hist_patch, hs_cap * h->hcap) A(nh.hist_harv, hs_cap * h->hcap)
+    A(nh.a_eco, hs_cap * h->acap) A(nh.a_cnt, hs_cap * h->acap) A(nh.a_val, hs_cap * h->acap)
+    A(nh.decay, hs_cap) A(nh.parent, hs_cap) A(nh.birth_index, hs_cap)
+    nh.hcap = h->hcap;
+    nh.acap = h->acap;
+    A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8)
+    A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
+    A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
+    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap)
+    A(ns.x_idx, new_cap) A(ns.x_tidx, new_cap) A(ns.x_size, new_cap) A(ns.x_band, new_cap)
+    A(ns.x_bcnt, new_cap) A(ns.x_btot, new_cap)
+    A(ns.x_key, new_cap) A(ns.x_fid, new_cap) A(ns.x_tfid, new_cap) A(ns.x_cult, new_cap) A(ns.x_bcult, new_cap)
+    A(ns.x_stored, new_cap) A(ns.x_contrib, new_cap) A(ns.x_lh, new_cap) A(ns.x_beff, new_cap) A(ns.x_bcoef, new_cap)
+    A(ns.x_balive, new_cap)
+    uint64_t *new_band_cult;
+    uint32_t *new_band_size;
+    A(new_band_cult, 2 * new_cap) A(new_band_size, 2 * new_cap)
+#undef A
+    /* a_eco: all slots free */
+    if (cudaMemsetAsync(nh.a_eco, 0xFF, hs_cap * h->acap * sizeof(uint16_t), h->stream) != cudaSuccess) {
+        free_list(fresh);
+        return fail(h, DSIM_ERR_CUDA, "cudaMemsetAsync failed");
+    }
+    if (old_cap) { /* grow: carry the live state over */
+#define CP(dst, src, count, T) \
+    if (cudaMemcpyAsync((dst), (src), (size_t)(count) * sizeof(T), cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) { \
+        free_list(fresh);      \
+        return fail(h, DSIM_ERR_CUDA, "device copy failed while growing"); \
+    }
+        for (int b = 0; b < 2; ++b) {
+            CP(nf[b].id, h->fam[b].id, old_cap, uint64_t) CP(nf[b].culture, h->fam[b].culture, old_cap, uint64_t)
+            CP(nf[b].stored, h->fam[b].stored, old_cap, double) CP(nf[b].last_harvest, h->fam[b].last_harvest, old_cap, double)
+            CP(nf[b].loc, h->fam[b].loc, old_cap, uint32_t) CP(nf[b].size, h->fam[b].size, old_cap, uint32_t)
+            CP(nf[b].till_adult, h->fam[b].till_adult, old_cap, uint32_t) CP(nf[b].till_mut, h->fam[b].till_mut, old_cap, uint32_t)
+            CP(nf[b].misc, h->fam[b].misc, old_cap, uint32_t) CP(nf[b].hs, h->fam[b].hs, old_cap, uint32_t)
+        }
+        CP(nh.hist_cnt, h->hv.hist_cnt, old_hs, uint32_t) CP(nh.hist_patch, h->hv.hist_patch, old_hs * h->hcap, uint32_t)
+        CP(nh.hist_harv, h->hv.hist_harv, old_hs * h->hcap, double) CP(nh.a_eco, h->hv.a_eco, old_hs * h->acap, uint16_t)
+        CP(nh.a_cnt, h->hv.a_cnt, old_hs * h->acap, uint32_t) CP(nh.a_val, h->hv.a_val, old_hs * h->acap, double)
+        CP(nh.decay, h->hv.decay, old_hs, uint32_t) CP(nh.parent, h->hv.parent, old_hs, uint64_t)
+        CP(nh.birth_index, h->hv.birth_index, old_hs, uint16_t)
+        CP(ns.free_hs, h->sc.free_hs, old_hs, uint32_t)
+        CP(ns.occ[0], h->sc.occ[0], old_cap, uint32_t) CP(ns.occ[1], h->sc.occ[1], old_cap, uint32_t)
+        /* band cultures: [0, old_cap) written by k_patch, [old_cap, 2 old_cap) uploaded by dsim_set_storage; the
+         * views hold absolute offsets, so both halves keep their positions */
+        CP(new_band_cult, h->ps.band_cult, 2 * old_cap, uint64_t) CP(new_band_size, h->ps.band_size, 2 * old_cap, uint32_t)
+#undef CP
+    }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        free_list(fresh);
+        return fail(h, DSIM_ERR_CUDA, "synchronize failed while allocating families");
+    }
+    free_list(h->fam_allocs);
+    h->fam_allocs.swap(fresh);
+    h->fam[0] = nf[0];
+    h->fam[1] = nf[1];
+    h->hv = nh;
+    h->sc = ns;
+    h->ps.band_cult = new_band_cult;
+    h->ps.band_size = new_band_size;
+    h->cap = new_cap;
+    h->hs_cap = hs_cap;
+    destroy_graphs(h);
+    return DSIM_OK;
+}
+
+int ensure_capacity(dsim_handle *h, uint64_t n_now) {
+    if (n_now * 10 <= h->cap * 7) return DSIM_OK;
+    uint64_t want = std::max<uint64_t>(2 * n_now + 1024, h->cap);
+    if (want == h->cap) return DSIM_OK;
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    rc = alloc_families(h, want);
+    if (rc) return rc;
+    h->ctl_h->cap = (uint32_t)h->cap;
+    h->ctl_h->hs_cap = (uint32_t)h->hs_cap;
+    return push_ctl(h);
+}
+
+#if !defined(DSIM_EMU)
+int build_graphs(dsim_handle *h) {
+    for (uint32_t par = 0; par < 2; ++par) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const StepArgs a = make_args(h, par);
+        for (int k = 0; k < DSIM_K_COUNT; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        CK(cudaStreamEndCapture(h->stream, &g));
+        CK(cudaGraphInstantiate(&h->gexec[par], g, 0));
+        CK(cudaGraphDestroy(g));
+    }
+    h->graphs_valid = true;
+    return DSIM_OK;
+}
+#endif
+
+int launch_range(dsim_handle *h, int k0, int k1) { /* kernels [k0, k1) of one step, plain launches */
+    const StepArgs a = make_args(h, h->parity);
+    for (int k = k0; k < k1; ++k) {
+        if (h->profiling) CK(cudaEventRecord(h->ev[k], h->stream));
+        dsim_launch_kernel(k, a, h->geom, h->stream);
+        h->k_launches[k] += 1;
+        h->total_launches += 1;
+    }
+    if (h->profiling) {
+        CK(cudaEventRecord(h->ev[k1], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int k = k0; k < k1; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+            h->k_ms[k] += ms;
+        }
+    }
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+int launch_step(dsim_handle *h) {
+#if !defined(DSIM_EMU)
+    if (h->opt.use_graphs && !h->profiling) {
+        if (!h->graphs_valid) {
+            int rc = build_graphs(h);
+            if (rc) return rc;
+        }
+        CK(cudaGraphLaunch(h->gexec[h->parity], h->stream));
+        for (int k = 0; k < DSIM_K_COUNT; ++k) h->k_launches[k] += 1;
+        h->total_launches += DSIM_K_COUNT;
+        h->parity ^= 1u;
+        return DSIM_OK;
+    }
+#endif
+    int rc = launch_range(h, 0, DSIM_K_COUNT);
+    if (rc) return rc;
+    h->parity ^= 1u;
+    return DSIM_OK;
+}
+
+uint32_t compute_acap(double minimum) {
+    /* number of `* 0.95` applications that take the largest reachable value (1.0, the fixed point of
+     * v -> 0.95 v + 0.05) down to the floor; a slot is live for at most that many applications */
+    double v = 1.0;
+    uint32_t k = 0;
+    while (v != minimum && k < DSIM_N_ECOREGIONS) {
+        v = dsim_adapt_decay(v, minimum);
+        ++k;
+    }
+    uint32_t acap = k + 2;
+    if (acap > DSIM_N_ECOREGIONS) acap = DSIM_N_ECOREGIONS;
+    return (acap + 3u) & ~3u;
+}
+
+/* refresh the list of "occupied last step" nodes and the census from the current family buffer */
+int recensus(dsim_handle *h) {
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    const uint32_t prev = h->parity ^ 1u;
+    h->ctl_h->n_occ[prev] = 0;
+    rc = push_ctl(h);
+    if (rc) return rc;
+    dsim_launch_census(h->ps, h->fam[h->parity], h->ctl_h->n_cur[h->parity], h->n_nodes, h->sc.occ[prev], h->ctl, prev,
+                       h->geom, h->stream);
+    h->total_launches += 3;
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+int take_snapshot(dsim_handle *h);
+
+} // namespace
+
+/* kernels used only by the getters / setters ----------------------------------------------------- */
+__global__ void k_pack_adaptation(FamHeavy hv, const uint32_t *hs_of, uint32_t n, double minimum, uint16_t *out_eco,
+                                  double *out_val, uint32_t *out_n) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n; i += nth) {
+        const uint32_t hs = hs_of[i];
+        const uint32_t d = hv.decay[hs];
+        uint32_t m = 0;
+        for (uint32_t k = 0; k < hv.acap; ++k) {
+            const uint32_t e = hv.a_eco[(size_t)hs * hv.acap + k];
+            if (e == DSIM_ECO_EMPTY) continue;
+            double v = hv.a_val[(size_t)hs * hv.acap + k];
+            for (uint32_t r = d - hv.a_cnt[(size_t)hs * hv.acap + k]; r > 0u && v != minimum; --r) v = dsim_adapt_decay(v, minimum);
+            if (v == minimum) continue;
+            out_eco[(size_t)i * hv.acap + m] = (uint16_t)e;
+            out_val[(size_t)i * hv.acap + m] = v;
+            ++m;
+        }
+        out_n[i] = m;
+    }
+}
+
+__global__ void k_pack_history(FamHeavy hv, const uint32_t *hs_of, const uint64_t *off, uint32_t n, uint32_t *out_patch,
+                               double *out_harv) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = gw; i < n; i += nw) {
+        const uint32_t hs = hs_of[i];
+        const uint32_t cnt = hv.hist_cnt[hs];
+        const uint32_t len = cnt < hv.hcap ? cnt : hv.hcap;
+        for (uint32_t k = lane; k < len; k += 32u) { /* chronological k: newest-first index len-1-k */
+            const uint32_t pos = (cnt - 1u - (len - 1u - k)) % hv.hcap;
+            out_patch[off[i] + k] = hv.hist_patch[(size_t)hs * hv.hcap + pos];
+            out_harv[off[i] + k] = hv.hist_harv[(size_t)hs * hv.hcap + pos];
+        }
+    }
+}
+
+__global__ void k_pack_storage(PatchState ps, const uint32_t *nodes, const uint64_t *off, uint32_t n, uint32_t *out_node,
+                               uint64_t *out_cult, uint64_t *out_size, uint32_t *out_nb) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t k = tid; k < n; k += nth) {
+        const uint32_t p = nodes[k];
+        const PatchView v = ps.view[p];
+        if (out_nb) out_nb[k] = v.nb;
+        if (off)
+            for (uint32_t b = 0; b < v.nb; ++b) {
+                out_node[off[k] + b] = p;
+                out_cult[off[k] + b] = ps.band_cult[v.stor_off + b];
+                out_size[off[k] + b] = ps.band_size[v.stor_off + b];
+            }
+    }
+}
+
+__global__ void k_apply_storage(PatchState ps, const uint32_t *nodes, const uint32_t *first, const uint32_t *count, uint32_t n,
+                                uint32_t base, uint32_t *occ, DevCtl *ctl, uint32_t prev) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t k = tid; k < n; k += nth) {
+        const uint32_t p = nodes[k];
+        ps.view[p].nb = count[k];
+        ps.view[p].stor_off = base + first[k];
+        ps.view[p].cult0 = ps.band_cult[base + first[k]];
+        /* make sure the node is on the "occupied last step" list so that the next step clears it */
+        if (ps.view[p].pop == 0u) occ[atomicAdd(&ctl->n_occ[prev], 1u)] = p;
+    }
+}
+
+__global__ void k_clear_storage(PatchState ps, uint32_t n_nodes) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t p = tid; p < n_nodes; p += nth) ps.view[p].nb = 0u;
+}
+
+namespace {
+
+int take_snapshot(dsim_handle *h) {
+    if (h->snap_valid) return DSIM_OK;
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    const uint32_t buf = h->mid_step ? (h->parity ^ 1u) : h->parity;
+    const uint32_t n = h->mid_step ? h->ctl_h->n_next : h->ctl_h->n_cur[h->parity];
+    const FamCore &f = h->fam[buf];
+    h->s_id.resize(n); h->s_culture.resize(n); h->s_stored.resize(n); h->s_lh.resize(n);
+    h->s_loc.resize(n); h->s_size.resize(n); h->s_till_adult.resize(n); h->s_till_mut.resize(n);
+    h->s_misc.resize(n); h->s_hs.resize(n); h->s_hist_len.resize(n); h->s_a_n.resize(n);
+    h->s_a_eco.resize((size_t)n * h->acap); h->s_a_val.resize((size_t)n * h->acap);
+    if ((rc = download(h, h->s_id.data(), f.id, n))) return rc;
+    if ((rc = download(h, h->s_culture.data(), f.culture, n))) return rc;
+    if ((rc = download(h, h->s_stored.data(), f.stored, n))) return rc;
+    if ((rc = download(h, h->s_lh.data(), f.last_harvest, n))) return rc;
+    if ((rc = download(h, h->s_loc.data(), f.loc, n))) return rc;
+    if ((rc = download(h, h->s_size.data(), f.size, n))) return rc;
+    if ((rc = download(h, h->s_till_adult.data(), f.till_adult, n))) return rc;
+    if ((rc = download(h, h->s_till_mut.data(), f.till_mut, n))) return rc;
+    if ((rc = download(h, h->s_misc.data(), f.misc, n))) return rc;
+    if ((rc = download(h, h->s_hs.data(), f.hs, n))) return rc;
+    /* adaptation, replayed to the current decay count */
+    std::vector<void *> tmp;
+    uint16_t *d_eco;
+    double *d_val;
+    uint32_t *d_n;
+    if ((rc = dev_alloc(h, &d_eco, (size_t)n * h->acap, tmp, false)) || (rc = dev_alloc(h, &d_val, (size_t)n * h->acap, tmp, false)) ||
+        (rc = dev_alloc(h, &d_n, n, tmp, false))) {
+        free_list(tmp);
+        return rc;
+    }
+    if (n) {
+        DSIM_LAUNCH(k_pack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint32_t *)f.hs, n, h->p.minimum_adaptation,
+                    d_eco, d_val, d_n);
+        h->total_launches += 1;
+    }
+    rc = download(h, h->s_a_eco.data(), d_eco, (size_t)n * h->acap);
+    if (!rc) rc = download(h, h->s_a_val.data(), d_val, (size_t)n * h->acap);
+    if (!rc) rc = download(h, h->s_a_n.data(), d_n, n);
+    /* history lengths */
+    std::vector<uint32_t> cnt(h->hs_cap);
+    if (!rc) rc = download(h, cnt.data(), h->hv.hist_cnt, h->hs_cap);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
+    free_list(tmp);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; ++i) h->s_hist_len[i] = std::min(cnt[h->s_hs[i]], h->hcap);
+    h->snap_valid = true;
+    return DSIM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int dsim_abi_version(void) { return DSIM_ABI_VERSION; }
+
+void dsim_default_params(dsim_params *p) { /* src/parameters.rs:22-54 */
+    std::memset(p, 0, sizeof *p);
+    p->resource_recovery_per_season = 0.10;
+    p->culture_mutation_rate = 6e-3;
+    p->culture_dimensionality = 20;
+    p->cooperation_threshold = 6;
+    p->maximum_resources_one_adult_can_harvest = 1e50;
+    p->evidence_needed = 0.1;
+    p->payoff_std = 0.1;
+    p->minimum_adaptation = 0.5;
+    p->fight_deadliness = 1u << 31;
+    p->enemy_discount = std::pow(0.5, 0.2);
+    p->season_length_in_years = 1. / 6.;
+    p->cooperation_inclusive = 0;
+}
+
+void dsim_default_options(dsim_options *o) {
+    std::memset(o, 0, sizeof *o);
+    o->use_graphs = 1;
+}
+
+const char *dsim_last_error(const dsim_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void dsim_destroy(dsim_handle *h) {
+    if (!h) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    destroy_graphs(h);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    free_list(h->fam_allocs);
+    free_list(h->allocs);
+    if (h->ctl_h) cudaFreeHost(h->ctl_h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const dsim_options *opt, dsim_handle **out) {
+    if (!p || !g || !out || !g->eco_off || !g->eco_id || !g->edge_off || !g->edge_dst || !g->edge_sec)
+        return fail(nullptr, DSIM_ERR_INVALID, "null argument");
+    if (g->n_nodes == 0 || g->n_nodes > 0xFFFFFF00u) return fail(nullptr, DSIM_ERR_INVALID, "bad node count");
+    if (!(p->season_length_in_years > 0.0)) return fail(nullptr, DSIM_ERR_INVALID, "season length must be positive");
+    if (!(p->minimum_adaptation >= 0.0)) return fail(nullptr, DSIM_ERR_INVALID, "minimum_adaptation must be >= 0");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+        return fail(nullptr, DSIM_ERR_NO_DEVICE, "no CUDA device: the step loop has no CPU fallback");
+    dsim_options o;
+    if (opt)
+        o = *opt;
+    else
+        dsim_default_options(&o);
+    if ((int)o.device >= n_dev) return fail(nullptr, DSIM_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaSetDevice((int)o.device) != cudaSuccess || cudaGetDeviceProperties(&prop, (int)o.device) != cudaSuccess)
+        return fail(nullptr, DSIM_ERR_NO_DEVICE, "cannot select the CUDA device");
+    if (prop.major != 10)
+        return fail(nullptr, DSIM_ERR_NO_DEVICE, "the kernels are built for sm_100a (B200) only");
+
+    const uint32_t n = g->n_nodes;
+    const uint64_t n_eco = g->eco_off[n], n_edge = g->edge_off[n];
+    if (n_eco > 0xFFFFFF00ull) return fail(nullptr, DSIM_ERR_INVALID, "too many ecoregion entries");
+    for (uint32_t v = 0; v < n; ++v) {
+        if (g->eco_off[v + 1] < g->eco_off[v] || g->edge_off[v + 1] < g->edge_off[v])
+            return fail(nullptr, DSIM_ERR_INVALID, "CSR offsets must not decrease");
+        for (uint64_t k = g->eco_off[v]; k < g->eco_off[v + 1]; ++k) {
+            if (g->eco_id[k] >= DSIM_N_ECOREGIONS) return fail(nullptr, DSIM_ERR_INVALID, "ecoregion id out of range");
+            if (k > g->eco_off[v] && g->eco_id[k] <= g->eco_id[k - 1])
+                return fail(nullptr, DSIM_ERR_INVALID, "ecoregion ids must ascend within a node");
+        }
+    }
+    for (uint64_t e = 0; e < n_edge; ++e)
+        if (g->edge_dst[e] >= n) return fail(nullptr, DSIM_ERR_INVALID, "edge target out of range");
+
+    dsim_handle *h = new dsim_handle;
+    h->p = *p;
+    h->opt = o;
+    h->seed = seed;
+    h->n_nodes = n;
+    h->n_eco = (uint32_t)n_eco;
+    h->geom.n_sm = (uint32_t)std::max(1, prop.multiProcessorCount);
+    std::memset(&h->rt, 0, sizeof h->rt);
+    std::memset(&h->ps, 0, sizeof h->ps);
+    std::memset(&h->hv, 0, sizeof h->hv);
+    std::memset(&h->sc, 0, sizeof h->sc);
+    std::memset(h->fam, 0, sizeof h->fam);
+    int rc = DSIM_OK;
+#define TRY(expr)                     \
+    if ((rc = (expr)) != DSIM_OK) {   \
+        g_create_error = h->err;      \
+        dsim_destroy(h);              \
+        return rc;                    \
+    }
+#define TRYCUDA(call)                                                                     \
+    if ((call) != cudaSuccess) {                                                          \
+        g_create_error = std::string(#call) + " failed: " + cudaGetErrorString(cudaGetLastError()); \
+        dsim_destroy(h);                                                                  \
+        return DSIM_ERR_CUDA;                                                             \
+    }
+    TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
+    TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
+    std::memset(h->ctl_h, 0, sizeof(DevCtl));
+    TRY(dev_alloc(h, &h->ctl, 1, h->allocs));
+
+    /* reach table (replaces bounded_dijkstra per family per step and the nearby_cache) */
+    {
+        HostReach hr;
+        std::string err;
+        rc = dsim_build_reach(g, &hr, &err);
+        if (rc != DSIM_OK) {
+            g_create_error = err;
+            dsim_destroy(h);
+            return rc;
+        }
+        h->n_near = hr.near_dst.size();
+        h->n_reach = hr.n_reach;
+        h->n_reach_padded = hr.dst.size();
+        uint32_t *off, *dst, *near_off, *near_dst;
+        double *cost;
+        uint16_t *nidx;
+        TRY(dev_alloc(h, &off, hr.off.size(), h->allocs, false));
+        TRY(dev_alloc(h, &dst, hr.dst.size(), h->allocs, false));
+        TRY(dev_alloc(h, &cost, hr.cost.size(), h->allocs, false));
+        TRY(dev_alloc(h, &nidx, hr.nidx.size(), h->allocs, false));
+        TRY(dev_alloc(h, &near_off, hr.near_off.size(), h->allocs, false));
+        TRY(dev_alloc(h, &near_dst, hr.near_dst.size(), h->allocs, false));
+        TRY(upload(h, off, hr.off.data(), hr.off.size()));
+        TRY(upload(h, dst, hr.dst.data(), hr.dst.size()));
+        TRY(upload(h, cost, hr.cost.data(), hr.cost.size()));
+        TRY(upload(h, nidx, hr.nidx.data(), hr.nidx.size()));
+        TRY(upload(h, near_off, hr.near_off.data(), hr.near_off.size()));
+        TRY(upload(h, near_dst, hr.near_dst.data(), hr.near_dst.size()));
+        TRYCUDA(cudaStreamSynchronize(h->stream));
+        h->rt.off = off; h->rt.dst = dst; h->rt.cost = cost; h->rt.nidx = nidx;
+        h->rt.near_off = near_off; h->rt.near_dst = near_dst;
+    }
+    /* patches */
+    {
+        h->eco_off_h.resize((size_t)n + 1);
+        for (uint32_t v = 0; v <= n; ++v) h->eco_off_h[v] = (uint32_t)g->eco_off[v];
+        std::vector<uint16_t> eco16(n_eco);
+        for (uint64_t k = 0; k < n_eco; ++k) eco16[k] = (uint16_t)g->eco_id[k];
+        uint32_t *eco_off;
+        uint16_t *eco_id;
+        double *mx;
+        TRY(dev_alloc(h, &h->ps.view, n, h->allocs));
+        TRY(dev_alloc(h, &h->ps.cnt, n, h->allocs));
+        TRY(dev_alloc(h, &h->ps.seg, n, h->allocs));
+        TRY(dev_alloc(h, &eco_off, (size_t)n + 1, h->allocs, false));
+        TRY(dev_alloc(h, &eco_id, n_eco, h->allocs, false));
+        TRY(dev_alloc(h, &h->ps.res, n_eco, h->allocs));
+        TRY(dev_alloc(h, &mx, n_eco, h->allocs));
+        TRY(upload(h, eco_off, h->eco_off_h.data(), (size_t)n + 1));
+        TRY(upload(h, eco_id, eco16.data(), n_eco));
+        TRYCUDA(cudaStreamSynchronize(h->stream));
+        h->ps.eco_off = eco_off;
+        h->ps.eco_id = eco_id;
+        h->ps.max_res = mx;
+    }
+    /* model constants */
+    {
+        ModelConst &mc = h->mc;
+        std::memset(&mc, 0, sizeof mc);
+        mc.recovery = p->resource_recovery_per_season;
+        mc.season = p->season_length_in_years;
+        mc.cap_harvest = p->maximum_resources_one_adult_can_harvest;
+        mc.min_adapt = p->minimum_adaptation;
+        mc.log1m_rate = dsim_log(1. - p->culture_mutation_rate);
+        mc.threshold = p->cooperation_threshold;
+        mc.inclusive = p->cooperation_inclusive;
+        mc.deadliness = p->fight_deadliness;
+        mc.adult_reset = dsim_f64_as_u32(15. / mc.season) + 1u;                    /* lib.rs:535,1878 */
+        mc.grow_reset = dsim_f64_as_u32((2.85 - 1.35) / (1. - 0.488) / mc.season); /* lib.rs:1910,1916 */
+        mc.n_nodes = n;
+        mc.k0 = (uint32_t)seed;
+        mc.k1 = (uint32_t)(seed >> 32);
+        /* memory after n decays, lib.rs:847-864; examined while memory >= f64::EPSILON */
+        std::vector<double> mem;
+        const double decay = std::pow(0.5, mc.season / 2.0);
+        double memory = 1.0;
+        while (!(memory < std::numeric_limits<double>::epsilon()) && mem.size() < (1u << 20)) {
+            mem.push_back(memory);
+            memory *= decay;
+        }
+        mc.n_mem = (uint32_t)mem.size();
+        TRY(dev_alloc(h, &h->mem_table_d, mem.size(), h->allocs, false));
+        TRY(upload(h, h->mem_table_d, mem.data(), mem.size()));
+        TRYCUDA(cudaStreamSynchronize(h->stream));
+        mc.mem_table = h->mem_table_d;
+        uint32_t hcap = o.history_capacity ? o.history_capacity : std::max(mc.n_mem, mc.adult_reset + 1u);
+        h->hcap = (hcap + 3u) & ~3u;
+        h->acap = compute_acap(mc.min_adapt);
+    }
+    TRY(alloc_families(h, o.family_capacity ? o.family_capacity : 1024));
+    h->ctl_h->cap = (uint32_t)h->cap;
+    h->ctl_h->hs_cap = (uint32_t)h->hs_cap;
+    TRY(push_ctl(h));
+    dsim_launch_init_views(h->ps, n, h->mc.recovery, h->geom, h->stream);
+    h->total_launches += 1;
+    TRYCUDA(cudaStreamSynchronize(h->stream));
+#undef TRY
+#undef TRYCUDA
+    *out = h;
+    return DSIM_OK;
+}
+
+int dsim_sync(dsim_handle *h) {
+    if (!h) return DSIM_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_set_patches(dsim_handle *h, const double *res, const double *max_res) {
+    if (!h || !res || !max_res) return DSIM_ERR_INVALID;
+    int rc;
+    if ((rc = upload(h, h->ps.res, res, h->n_eco))) return rc;
+    if ((rc = upload(h, const_cast<double *>(h->ps.max_res), max_res, h->n_eco))) return rc;
+    dsim_launch_init_views(h->ps, h->n_nodes, h->mc.recovery, h->geom, h->stream);
+    h->total_launches += 1;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_get_patches(dsim_handle *h, double *res, double *max_res) {
+    if (!h) return DSIM_ERR_INVALID;
+    int rc;
+    if (res && (rc = download(h, res, h->ps.res, h->n_eco))) return rc;
+    if (max_res && (rc = download(h, max_res, h->ps.max_res, h->n_eco))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_set_families(dsim_handle *h, const dsim_families *f) {
+    if (!h || !f) return DSIM_ERR_INVALID;
+    const uint64_t n = f->n;
+    if (n && (!f->id || !f->culture || !f->location || !f->size || !f->stored)) return fail(h, DSIM_ERR_INVALID, "missing family array");
+    if (n > 0xFFFFFF00ull) return fail(h, DSIM_ERR_CAPACITY, "too many families");
+    for (uint64_t i = 0; i < n; ++i) {
+        if (f->location[i] >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "family location out of range");
+        if (i > 0 && f->id[i] <= f->id[i - 1]) return fail(h, DSIM_ERR_INVALID, "family ids must ascend");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    int rc;
+    uint64_t want = h->opt.family_capacity ? std::max<uint64_t>(h->opt.family_capacity, n + n / 4 + 256) : 2 * n + 1024;
+    if (want > h->cap) {
+        free_list(h->fam_allocs); /* nothing to preserve */
+        h->cap = h->hs_cap = 0;
+        if ((rc = alloc_families(h, want))) return rc;
+    }
+    const uint32_t hcap = h->hcap, acap = h->acap;
+    std::vector<uint32_t> misc(n), hs(n), till_adult(n), till_mut(n), hist_cnt(n);
+    std::vector<double> lh(n);
+    std::vector<uint64_t> parent(n);
+    std::vector<uint16_t> birth(n);
+    std::vector<uint32_t> hp((size_t)n * hcap, 0);
+    std::vector<double> hh((size_t)n * hcap, 0.0);
+    std::vector<uint16_t> a_eco((size_t)n * acap, (uint16_t)DSIM_ECO_EMPTY);
+    std::vector<uint32_t> a_cnt((size_t)n * acap, 0);
+    std::vector<double> a_val((size_t)n * acap, 0.0);
+    for (uint64_t i = 0; i < n; ++i) {
+        const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
+        misc[i] = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
+        hs[i] = (uint32_t)i;
+        till_adult[i] = f->till_adult ? f->till_adult[i] : 0;
+        till_mut[i] = (clock && f->till_mutation) ? f->till_mutation[i] : 0;
+        lh[i] = f->last_harvest ? f->last_harvest[i] : 0.0;
+        parent[i] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
+        birth[i] = f->birth_index ? f->birth_index[i] : 0;
+        if (f->hist_off) {
+            const uint64_t a = f->hist_off[i], b = f->hist_off[i + 1];
+            const uint64_t keep = std::min<uint64_t>(b - a, hcap);
+            for (uint64_t k = 0; k < keep; ++k) {
+                const uint32_t q = f->hist_patch[b - keep + k];
+                if (q >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "history node out of range");
+                hp[i * hcap + k] = q;
+                hh[i * hcap + k] = f->hist_harvest[b - keep + k];
+            }
+            hist_cnt[i] = (uint32_t)keep;
+        }
+        if (f->adapt_off) {
+            uint32_t m = 0;
+            for (uint64_t k = f->adapt_off[i]; k < f->adapt_off[i + 1]; ++k) {
+                if (f->adapt_eco[k] >= DSIM_N_ECOREGIONS) return fail(h, DSIM_ERR_INVALID, "adaptation ecoregion out of range");
+                if (f->adapt_val[k] == h->p.minimum_adaptation) continue;
+                if (m >= acap) return fail(h, DSIM_ERR_CAPACITY, "more adapted ecoregions than adaptation slots");
+                a_eco[i * acap + m] = (uint16_t)f->adapt_eco[k];
+                a_val[i * acap + m] = f->adapt_val[k];
+                ++m;
+            }
+        }
+    }
+    h->parity = 0;
+    h->mid_step = false;
+    h->snap_valid = false;
+    const FamCore &c = h->fam[0];
+    if ((rc = upload(h, c.id, f->id, n)) || (rc = upload(h, c.culture, f->culture, n)) || (rc = upload(h, c.stored, f->stored, n)) ||
+        (rc = upload(h, c.last_harvest, lh.data(), n)) || (rc = upload(h, c.loc, f->location, n)) || (rc = upload(h, c.size, f->size, n)) ||
+        (rc = upload(h, c.till_adult, till_adult.data(), n)) || (rc = upload(h, c.till_mut, till_mut.data(), n)) ||
+        (rc = upload(h, c.misc, misc.data(), n)) || (rc = upload(h, c.hs, hs.data(), n)) ||
+        (rc = upload(h, h->hv.hist_cnt, hist_cnt.data(), n)) || (rc = upload(h, h->hv.hist_patch, hp.data(), (size_t)n * hcap)) ||
+        (rc = upload(h, h->hv.hist_harv, hh.data(), (size_t)n * hcap)) || (rc = upload(h, h->hv.a_eco, a_eco.data(), (size_t)n * acap)) ||
+        (rc = upload(h, h->hv.a_cnt, a_cnt.data(), (size_t)n * acap)) || (rc = upload(h, h->hv.a_val, a_val.data(), (size_t)n * acap)) ||
+        (rc = upload(h, h->hv.parent, parent.data(), n)) || (rc = upload(h, h->hv.birth_index, birth.data(), n)))
+        return rc;
+    CK(cudaMemsetAsync(h->hv.decay, 0, h->hs_cap * sizeof(uint32_t), h->stream));
+    if ((rc = sync_ctl(h))) return rc;
+    DevCtl &ctl = *h->ctl_h;
+    const uint32_t t_keep = ctl.t;
+    std::memset(&ctl, 0, sizeof ctl);
+    ctl.t = t_keep;
+    ctl.n_cur[0] = (uint32_t)n;
+    ctl.hs_hwm = (uint32_t)n;
+    ctl.next_id = n ? f->id[n - 1] + 1 : 0;
+    ctl.cap = (uint32_t)h->cap;
+    ctl.hs_cap = (uint32_t)h->hs_cap;
+    if ((rc = push_ctl(h))) return rc;
+    h->n_known = n;
+    h->steps_since_check = 0;
+    if ((rc = recensus(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *n_adapt) {
+    if (!h) return DSIM_ERR_INVALID;
+    int rc = take_snapshot(h);
+    if (rc) return rc;
+    uint64_t nh = 0, na = 0;
+    for (size_t i = 0; i < h->s_id.size(); ++i) {
+        nh += h->s_hist_len[i];
+        na += h->s_a_n[i];
+    }
+    if (n) *n = h->s_id.size();
+    if (n_hist) *n_hist = nh;
+    if (n_adapt) *n_adapt = na;
+    return DSIM_OK;
+}
+
+int dsim_get_families(dsim_handle *h, dsim_families *f) {
+    if (!h || !f) return DSIM_ERR_INVALID;
+    int rc = take_snapshot(h);
+    if (rc) return rc;
+    const size_t n = h->s_id.size();
+    f->n = n;
+    std::vector<uint64_t> parent;
+    std::vector<uint16_t> birth;
+    if (f->parent_id || f->birth_index) {
+        parent.resize(h->hs_cap);
+        birth.resize(h->hs_cap);
+        if ((rc = download(h, parent.data(), h->hv.parent, h->hs_cap)) || (rc = download(h, birth.data(), h->hv.birth_index, h->hs_cap)))
+            return rc;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    std::vector<uint64_t> hoff(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+        if (f->id) f->id[i] = h->s_id[i];
+        if (f->parent_id) f->parent_id[i] = parent[h->s_hs[i]];
+        if (f->birth_index) f->birth_index[i] = birth[h->s_hs[i]];
+        if (f->culture) f->culture[i] = h->s_culture[i];
+        if (f->location) f->location[i] = h->s_loc[i];
+        if (f->size) f->size[i] = h->s_size[i];
+        if (f->stored) f->stored[i] = h->s_stored[i];
+        if (f->last_harvest) f->last_harvest[i] = h->s_lh[i];
+        if (f->till_adult) f->till_adult[i] = h->s_till_adult[i];
+        const bool clock = (h->s_misc[i] & DSIM_MISC_CLOCK) != 0;
+        if (f->till_mutation) f->till_mutation[i] = clock ? h->s_till_mut[i] : 0;
+        if (f->has_mutation_clock) f->has_mutation_clock[i] = clock ? 1 : 0;
+        if (f->n_offspring) f->n_offspring[i] = (uint16_t)(h->s_misc[i] & 0xFFFFu);
+        hoff[i + 1] = hoff[i] + h->s_hist_len[i];
+    }
+    if (f->hist_off) {
+        std::copy(hoff.begin(), hoff.end(), f->hist_off);
+        if (hoff[n] && (f->hist_patch || f->hist_harvest)) {
+            std::vector<void *> tmp;
+            uint64_t *d_off;
+            uint32_t *d_hs, *d_patch;
+            double *d_harv;
+            if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_hs, n, tmp, false)) ||
+                (rc = dev_alloc(h, &d_patch, hoff[n], tmp, false)) || (rc = dev_alloc(h, &d_harv, hoff[n], tmp, false)) ||
+                (rc = upload(h, d_off, hoff.data(), n + 1)) || (rc = upload(h, d_hs, h->s_hs.data(), n))) {
+                free_list(tmp);
+                return rc;
+            }
+            DSIM_LAUNCH(k_pack_history, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint32_t *)d_hs, (const uint64_t *)d_off,
+                        (uint32_t)n, d_patch, d_harv);
+            h->total_launches += 1;
+            if (f->hist_patch) rc = download(h, f->hist_patch, d_patch, hoff[n]);
+            if (!rc && f->hist_harvest) rc = download(h, f->hist_harvest, d_harv, hoff[n]);
+            if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in get_families");
+            free_list(tmp);
+            if (rc) return rc;
+        }
+    }
+    if (f->adapt_off) {
+        uint64_t na = 0;
+        std::vector<std::pair<uint32_t, double>> row;
+        for (size_t i = 0; i < n; ++i) {
+            f->adapt_off[i] = na;
+            row.clear();
+            for (uint32_t k = 0; k < h->s_a_n[i]; ++k) row.push_back({h->s_a_eco[i * h->acap + k], h->s_a_val[i * h->acap + k]});
+            std::sort(row.begin(), row.end());
+            for (const auto &ev : row) {
+                if (f->adapt_eco) f->adapt_eco[na] = ev.first;
+                if (f->adapt_val) f->adapt_val[na] = ev.second;
+                ++na;
+            }
+        }
+        f->adapt_off[n] = na;
+    }
+    return DSIM_OK;
+}
+
+int dsim_set_time(dsim_handle *h, uint64_t t) {
+    if (!h) return DSIM_ERR_INVALID;
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    h->ctl_h->t = (uint32_t)t;
+    return push_ctl(h);
+}
+
+int dsim_get_time(dsim_handle *h, uint64_t *t) {
+    if (!h || !t) return DSIM_ERR_INVALID;
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    *t = h->ctl_h->t;
+    return DSIM_OK;
+}
+
+static int collect_storage(dsim_handle *h, std::vector<uint32_t> &node, std::vector<uint64_t> &cult, std::vector<uint64_t> &size) {
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    /* the nodes visited by part 2 of the last step are the "occupied last step" list of the next one */
+    const uint32_t prev = h->parity ^ 1u;
+    const uint32_t n = h->ctl_h->n_occ[prev];
+    node.clear(); cult.clear(); size.clear();
+    if (n == 0) return DSIM_OK;
+    std::vector<void *> tmp;
+    uint32_t *d_nb, *d_node;
+    uint64_t *d_off, *d_cult, *d_size;
+    if ((rc = dev_alloc(h, &d_nb, n, tmp, false))) { free_list(tmp); return rc; }
+    DSIM_LAUNCH(k_pack_storage, h->geom.n_sm * 4, 256, 0, h->stream, h->ps, (const uint32_t *)h->sc.occ[prev], (const uint64_t *)nullptr, n,
+                (uint32_t *)nullptr, (uint64_t *)nullptr, (uint64_t *)nullptr, d_nb);
+    std::vector<uint32_t> nb(n);
+    rc = download(h, nb.data(), d_nb, n);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in storage");
+    if (rc) { free_list(tmp); return rc; }
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint32_t k = 0; k < n; ++k) off[k + 1] = off[k] + nb[k];
+    const uint64_t total = off[n];
+    if (total) {
+        if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_node, total, tmp, false)) ||
+            (rc = dev_alloc(h, &d_cult, total, tmp, false)) || (rc = dev_alloc(h, &d_size, total, tmp, false)) ||
+            (rc = upload(h, d_off, off.data(), n + 1))) { free_list(tmp); return rc; }
+        DSIM_LAUNCH(k_pack_storage, h->geom.n_sm * 4, 256, 0, h->stream, h->ps, (const uint32_t *)h->sc.occ[prev], (const uint64_t *)d_off, n,
+                    d_node, d_cult, d_size, (uint32_t *)nullptr);
+        node.resize(total); cult.resize(total); size.resize(total);
+        rc = download(h, node.data(), d_node, total);
+        if (!rc) rc = download(h, cult.data(), d_cult, total);
+        if (!rc) rc = download(h, size.data(), d_size, total);
+        if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in storage");
+    }
+    h->total_launches += 2;
+    free_list(tmp);
+    if (rc) return rc;
+    /* map semantics of lib.rs:628-632: a later band with the same culture overwrites; sort by (node, culture) */
+    std::vector<uint64_t> order(total);
+    for (uint64_t k = 0; k < total; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+        return node[a] != node[b] ? node[a] < node[b] : cult[a] < cult[b];
+    });
+    std::vector<uint32_t> n2;
+    std::vector<uint64_t> c2, s2;
+    for (uint64_t r = 0; r < total; ++r) {
+        const uint64_t k = order[r];
+        if (!n2.empty() && n2.back() == node[k] && c2.back() == cult[k]) {
+            s2.back() = size[k];
+            continue;
+        }
+        n2.push_back(node[k]); c2.push_back(cult[k]); s2.push_back(size[k]);
+    }
+    node.swap(n2); cult.swap(c2); size.swap(s2);
+    return DSIM_OK;
+}
+
+int dsim_storage_count(dsim_handle *h, uint64_t *n) {
+    if (!h || !n) return DSIM_ERR_INVALID;
+    std::vector<uint32_t> node;
+    std::vector<uint64_t> cult, size;
+    int rc = collect_storage(h, node, cult, size);
+    if (rc) return rc;
+    *n = node.size();
+    return DSIM_OK;
+}
+
+int dsim_get_storage(dsim_handle *h, uint32_t *node, uint64_t *culture, uint64_t *size) {
+    if (!h) return DSIM_ERR_INVALID;
+    std::vector<uint32_t> nd;
+    std::vector<uint64_t> cu, sz;
+    int rc = collect_storage(h, nd, cu, sz);
+    if (rc) return rc;
+    if (node) std::copy(nd.begin(), nd.end(), node);
+    if (culture) std::copy(cu.begin(), cu.end(), culture);
+    if (size) std::copy(sz.begin(), sz.end(), size);
+    return DSIM_OK;
+}
+
+int dsim_set_storage(dsim_handle *h, uint64_t n, const uint32_t *node, const uint64_t *culture, const uint64_t *size) {
+    if (!h || (n && (!node || !culture))) return DSIM_ERR_INVALID;
+    if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "set_storage between the two parts of a step");
+    if (n > h->cap) return fail(h, DSIM_ERR_CAPACITY, "more storage entries than family capacity");
+    for (uint64_t i = 0; i < n; ++i)
+        if (node[i] >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "storage node out of range");
+    /* group by node, keeping insertion order within a node; a repeated (node, culture) overwrites */
+    std::vector<uint64_t> order(n);
+    for (uint64_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return node[a] < node[b]; });
+    std::vector<uint32_t> nodes, first, count, sizes;
+    std::vector<uint64_t> cults;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint64_t i = order[r];
+        if (nodes.empty() || nodes.back() != node[i]) {
+            nodes.push_back(node[i]);
+            first.push_back((uint32_t)cults.size());
+            count.push_back(0);
+        }
+        bool dup = false;
+        for (uint32_t k = first.back(); k < cults.size(); ++k)
+            if (cults[k] == culture[i]) {
+                sizes[k] = (uint32_t)(size ? size[i] : 0);
+                dup = true;
+            }
+        if (dup) continue;
+        cults.push_back(culture[i]);
+        sizes.push_back((uint32_t)(size ? size[i] : 0));
+        count.back() += 1;
+    }
+    int rc;
+    /* previous-step node list = census nodes (rebuilt) + storage-only nodes */
+    if ((rc = recensus(h))) return rc;
+    DSIM_LAUNCH(k_clear_storage, h->geom.n_sm * 4, 256, 0, h->stream, h->ps, h->n_nodes);
+    h->total_launches += 1;
+    const uint32_t base = (uint32_t)h->cap;
+    if (!nodes.empty()) {
+        std::vector<void *> tmp;
+        uint32_t *d_nodes, *d_first, *d_count;
+        if ((rc = dev_alloc(h, &d_nodes, nodes.size(), tmp, false)) || (rc = dev_alloc(h, &d_first, nodes.size(), tmp, false)) ||
+            (rc = dev_alloc(h, &d_count, nodes.size(), tmp, false)) || (rc = upload(h, d_nodes, nodes.data(), nodes.size())) ||
+            (rc = upload(h, d_first, first.data(), nodes.size())) || (rc = upload(h, d_count, count.data(), nodes.size())) ||
+            (rc = upload(h, h->ps.band_cult + base, cults.data(), cults.size())) ||
+            (rc = upload(h, h->ps.band_size + base, sizes.data(), sizes.size()))) {
+            free_list(tmp);
+            return rc;
+        }
+        const uint32_t prev = h->parity ^ 1u;
+        DSIM_LAUNCH(k_apply_storage, h->geom.n_sm * 4, 256, 0, h->stream, h->ps, (const uint32_t *)d_nodes, (const uint32_t *)d_first,
+                    (const uint32_t *)d_count, (uint32_t)nodes.size(), base, h->sc.occ[prev], h->ctl, prev);
+        h->total_launches += 1;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in set_storage");
+        free_list(tmp);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+static int host_check(dsim_handle *h) { /* read the live count, grow if the buffers are getting full */
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    h->steps_since_check = 0;
+    h->n_known = h->ctl_h->n_cur[h->parity];
+    if (h->ctl_h->errors & DSIM_MODEL_CAPACITY) return fail(h, DSIM_ERR_CAPACITY, "family capacity exceeded during a batch of steps");
+    return ensure_capacity(h, h->n_known);
+}
+
+int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
+    if (!h) return DSIM_ERR_INVALID;
+    if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "dsim_step between the two parts of a step");
+    int rc;
+    h->snap_valid = false;
+    uint64_t births0 = 0, deaths0 = 0, updates0 = 0;
+    if (stats) {
+        if ((rc = sync_ctl(h))) return rc;
+        births0 = h->ctl_h->births; deaths0 = h->ctl_h->deaths; updates0 = h->ctl_h->updates;
+    }
+    for (uint32_t s = 0; s < n_steps; ++s) {
+        if (h->steps_since_check >= 8 || h->n_known * 10 > h->cap * 7)
+            if ((rc = host_check(h))) return rc;
+        if ((rc = launch_step(h))) return rc;
+        h->steps_since_check += 1;
+    }
+    if (!stats) return DSIM_OK;
+    if ((rc = host_check(h))) return rc;
+    const DevCtl &c = *h->ctl_h;
+    std::memset(stats, 0, sizeof *stats);
+    stats->t = c.t;
+    stats->live_families = c.n_cur[h->parity];
+    stats->births = c.births - births0;
+    stats->deaths = c.deaths - deaths0;
+    stats->family_updates = c.updates - updates0;
+    stats->occupied_patches = c.n_occ[h->parity ^ 1u];
+    stats->model_errors = c.errors;
+    if (c.errors & ~(uint32_t)DSIM_MODEL_CAPACITY) {
+        h->err = "a model assertion of the reference failed (see dsim_step_stats.model_errors)";
+        return DSIM_ERR_MODEL;
+    }
+    return DSIM_OK;
+}
+
+int dsim_step_part(dsim_handle *h, int part) {
+    if (!h) return DSIM_ERR_INVALID;
+    int rc;
+    h->snap_valid = false;
+    if (part == 1) {
+        if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "part 1 twice");
+        if ((rc = host_check(h))) return rc;
+        if ((rc = launch_range(h, DSIM_K_LIFECYCLE, DSIM_K_SEGMENTS))) return rc;
+        h->mid_step = true;
+    } else if (part == 2) {
+        if (!h->mid_step) return fail(h, DSIM_ERR_INVALID, "part 2 without part 1");
+        if ((rc = launch_range(h, DSIM_K_SEGMENTS, DSIM_K_COUNT))) return rc;
+        h->mid_step = false;
+        h->parity ^= 1u;
+        h->steps_since_check += 1;
+    } else {
+        return DSIM_ERR_INVALID;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach) {
+    if (!h) return DSIM_ERR_INVALID;
+    if (n_nearby) *n_nearby = h->n_near;
+    if (n_reach) *n_reach = h->n_reach;
+    return DSIM_OK;
+}
+
+int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst, uint64_t *reach_off, uint32_t *reach_dst,
+                   double *reach_cost) {
+    if (!h) return DSIM_ERR_INVALID;
+    const uint32_t n = h->n_nodes;
+    std::vector<uint32_t> off(n + 1), noff(n + 1), dst(h->n_reach_padded);
+    std::vector<double> cost(h->n_reach_padded);
+    int rc;
+    if ((rc = download(h, off.data(), h->rt.off, n + 1)) || (rc = download(h, noff.data(), h->rt.near_off, n + 1)) ||
+        (rc = download(h, dst.data(), h->rt.dst, h->n_reach_padded)) || (rc = download(h, cost.data(), h->rt.cost, h->n_reach_padded)))
+        return rc;
+    if (near_dst && (rc = download(h, near_dst, h->rt.near_dst, h->n_near))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    uint64_t w = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        if (near_off) near_off[v] = noff[v];
+        if (reach_off) reach_off[v] = w;
+        for (uint32_t e = off[v]; e < off[v + 1]; ++e) {
+            if (dst[e] == 0xFFFFFFFFu) break; /* row padding */
+            if (reach_dst) reach_dst[w] = dst[e];
+            if (reach_cost) reach_cost[w] = cost[e];
+            ++w;
+        }
+    }
+    if (near_off) near_off[n] = noff[n];
+    if (reach_off) reach_off[n] = w;
+    return DSIM_OK;
+}
+
+int dsim_profile_enable(dsim_handle *h, int on) {
+    if (!h) return DSIM_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    h->profiling = on != 0;
+    return DSIM_OK;
+}
+
+int dsim_profile_read(dsim_handle *h, dsim_kernel_times *out, int reset) {
+    if (!h || !out) return DSIM_ERR_INVALID;
+    out->n = DSIM_K_COUNT;
+    for (int k = 0; k < DSIM_K_COUNT; ++k) {
+        out->name[k] = dsim_kernel_names[k];
+        out->ms[k] = h->k_ms[k];
+        out->launches[k] = h->k_launches[k];
+        if (reset) {
+            h->k_ms[k] = 0.0;
+            h->k_launches[k] = 0;
+        }
+    }
+    return DSIM_OK;
+}
+
+int dsim_launch_count(dsim_handle *h, uint64_t *n) {
+    if (!h || !n) return DSIM_ERR_INVALID;
+    *n = h->total_launches;
+    return DSIM_OK;
+}
+
+} /* extern "C" */

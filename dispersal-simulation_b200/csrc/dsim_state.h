@@ -1,0 +1,121 @@
+/*
+ * dsim_state.h — HBM layout of the simulation state.
+ *
+ * Families (lib.rs:178-229) are split into
+ *   - a 56-byte CORE record, structure-of-arrays, kept in the reference's vector order and
+ *     double-buffered: part 1 of the step reads buffer `cur` and writes the survivors (compacted,
+ *     lib.rs:541) and the children (appended, lib.rs:551) into buffer `next`;
+ *   - HEAVY per-family state that never moves (history ring, sparse adaptation slots, lineage),
+ *     addressed through the `hs` (heavy slot) column of the core record.
+ * Patches (lib.rs:142-152) keep their resources in the ecoregion CSR of the graph plus one 32-byte
+ * VIEW record per node that holds everything the move decision gathers for a candidate patch.
+ */
+#ifndef DSIM_STATE_H
+#define DSIM_STATE_H
+
+#include <stdint.h>
+
+#define DSIM_NIDX_NONE 0xFFFFu   /* reach entry that is not in the 2-hop `nearby` list */
+#define DSIM_ECO_EMPTY 0xFFFFu   /* free adaptation slot */
+#define DSIM_MISC_CLOCK 0x10000u /* misc bit 16: seasons_till_next_mutation is Some(..) */
+
+struct FamCore {            /* one column per field, index = position in the family vector */
+    uint64_t *id;           /* birth-order id; keys every random draw of the family              */
+    uint64_t *culture;      /* Culture.in_memory[0]                                             */
+    double *stored;         /* stored_resources                                                 */
+    double *last_harvest;
+    uint32_t *loc;          /* location (node id)                                               */
+    uint32_t *size;         /* effective_size                                                   */
+    uint32_t *till_adult;   /* seasons_till_next_adult                                          */
+    uint32_t *till_mut;     /* seasons_till_next_mutation (valid iff misc & DSIM_MISC_CLOCK)    */
+    uint32_t *misc;         /* bits 0..15 number_offspring, bit 16 mutation clock present       */
+    uint32_t *hs;           /* heavy slot                                                       */
+};
+
+struct FamHeavy {           /* index = heavy slot */
+    uint32_t *hist_cnt;     /* pushes so far; entry n (0 = newest) sits at ring position (cnt-1-n) % hcap */
+    uint32_t *hist_patch;   /* [slot * hcap + pos] */
+    double *hist_harv;      /* [slot * hcap + pos] */
+    uint16_t *a_eco;        /* [slot * acap + k] ecoregion of adaptation slot k or DSIM_ECO_EMPTY  */
+    uint32_t *a_cnt;        /* [slot * acap + k] decay count at which a_val was current           */
+    double *a_val;          /* [slot * acap + k]                                                  */
+    uint32_t *decay;        /* number of `adaptation * 0.95` applications so far (lib.rs:1953)    */
+    uint64_t *parent;       /* lineage (descendence, lib.rs:227,1880)                             */
+    uint16_t *birth_index;
+    uint32_t hcap, acap;
+};
+
+struct __align__(16) PatchView { /* what decide_on_moving gathers per candidate (lib.rs:1034-1062) */
+    double quality;         /* expected_harvest: sum_e(res + max * recovery), lib.rs:989-994       */
+    uint32_t pop;           /* census cc[node], lib.rs:522-525                                    */
+    uint32_t nb;            /* number of band cultures stored for the node (storage[node].len())   */
+    uint64_t cult0;         /* first of them, inline                                              */
+    uint32_t stor_off;      /* the others: band_cult[stor_off + 1 ... stor_off + nb - 1]          */
+    uint32_t pad_;
+};
+
+struct PatchState {
+    PatchView *view;        /* [P]                                                                */
+    uint32_t *cnt;          /* [P] arrivals during part 1 (counting sort histogram), 0 between steps */
+    uint32_t *seg;          /* [P] start of the node's segment in `members`                        */
+    const uint32_t *eco_off;/* [P+1]                                                              */
+    const uint16_t *eco_id; /* [n_eco]                                                            */
+    double *res;            /* [n_eco] Patch.resources[eco].0                                      */
+    const double *max_res;  /* [n_eco] Patch.resources[eco].1                                      */
+    uint64_t *band_cult;    /* [cap] storage' cultures, segment-aligned                            */
+    uint32_t *band_size;    /* [cap] storage' sizes                                                */
+};
+
+struct ReachTable {          /* replaces bounded_dijkstra per family per step (lib.rs:843)         */
+    const uint32_t *off;     /* [P+1] rows padded to multiples of 8 entries                        */
+    const uint32_t *dst;     /* ascending; padding = 0xFFFFFFFF                                     */
+    const double *cost;      /* OYR                                                                */
+    const uint16_t *nidx;    /* index in the node's nearby list or DSIM_NIDX_NONE                  */
+    const uint32_t *near_off;/* [P+1] 2-hop lists (lib.rs:1158-1178), ascending                    */
+    const uint32_t *near_dst;
+};
+
+struct StepScratch {
+    uint32_t *alive_bits;   /* [cap/32] bit i: family i survives `retain` (lib.rs:541)             */
+    uint32_t *split_bits;   /* [cap/32] bit i: family i procreates (lib.rs:1870)                    */
+    uint32_t *blk_alive;    /* [cap/256] per-256 counts, then exclusive offsets                    */
+    uint32_t *blk_split;
+    uint32_t *dead_hs;      /* [cap] heavy slots vacated this step                                 */
+    uint32_t *free_hs;      /* [hcap_slots] free stack                                             */
+    uint32_t *fslot;        /* [cap] arrival rank of family j at its new node                      */
+    uint32_t *members;      /* [cap] family positions grouped by node                              */
+    uint32_t *occ[2];       /* [cap] occupied nodes of this / the previous step                    */
+    /* patch-kernel spill arrays for nodes with more families than fit in shared memory, indexed
+     * by segment position */
+    uint32_t *x_idx, *x_tidx, *x_size, *x_band, *x_bcnt, *x_btot;
+    uint64_t *x_key, *x_fid, *x_tfid, *x_cult, *x_bcult;
+    double *x_stored, *x_contrib, *x_lh, *x_beff, *x_bcoef;
+    uint8_t *x_balive;
+};
+
+struct DevCtl {              /* one instance in device memory */
+    uint32_t n_cur[2];       /* families in buffer 0 / 1                                           */
+    uint32_t n_occ[2];       /* occupied nodes recorded in occ[0] / occ[1]                          */
+    uint32_t n_alive, n_children, n_dead, n_next;
+    uint32_t child_pos_base; /* = n_alive                                                         */
+    uint32_t seg_cursor;
+    uint32_t free_top, hs_hwm;
+    uint32_t t;              /* State.t                                                            */
+    uint32_t errors;
+    uint32_t cap, hs_cap;
+    uint64_t child_id_base, next_id;
+    uint64_t births, deaths, updates;
+};
+
+struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed by value          */
+    double recovery, season, cap_harvest, min_adapt, log1m_rate;
+    uint32_t threshold, inclusive, deadliness;
+    uint32_t adult_reset;    /* (15 / season) as u32 + 1, lib.rs:535,1878                          */
+    uint32_t grow_reset;     /* (YEARS_BETWEEN_ADULTS / season) as u32, lib.rs:1910-1916            */
+    uint32_t n_mem;          /* history entries the memory loop can still sample (lib.rs:856)       */
+    uint32_t n_nodes;
+    uint32_t k0, k1;         /* Philox key = seed                                                  */
+    const double *mem_table; /* [n_mem] memory after n decays (lib.rs:847-864)                      */
+};
+
+#endif
