@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — family-updates/s of the B200 step loop (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPUs
+
+A "step" is one season (`step`, lib.rs:477-496) over every live family.  At N=1 the workload is
+BASELINE.json configs[1]: a 1155x1732 hex grid (2.0M patches) with 100k families whose histories
+are pre-filled (the steady-state regime of the memory loop, lib.rs:854-866).
+`value` = family-updates / device-seconds with the state resident in HBM; `e2e` = the same metric
+through the C ABI from host buffers (upload of the state, per-step stats read-back, download of the
+families and patches, all inside the timed region).
+
+The reference itself cannot be built (Rust, not compilable at this revision, no toolchain): the
+reference arm and `cpu_baseline` time the C++ oracle port in its reference-shaped mode (one bounded
+Dijkstra per family per decision, dense 304-entry adaptation vectors) with OpenMP on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "dispersal-simulation_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+import dsim_b200 as D  # noqa: E402
+
+CONFIGS = {
+    # name: (W, H, families, n_occupied, hist_fill)
+    "c1": (100, 100, 1000, 0, 0),            # reference CPU-runnable case
+    "c2": (1155, 1732, 100_000, 0, 625),     # Americas-scale grid, 1 GPU (the metric's configuration)
+    "c3": (1155, 1732, 1_000_000, 0, 625),   # Americas-scale grid, 1M families
+    "c4": (2582, 3873, 10_000_000, 1_250_000, 64),  # stress: dense co-residence
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def build_workload(cfg, seed, synth):
+    W, H, n_fam, n_occ, hist_fill = cfg
+    t0 = time.time()
+    g, res, mx = D.synth_grid(W, H, seed, lib=synth)
+    fam = D.synth_families(W, H, n_fam, seed, n_occupied=n_occ, hist_fill=hist_fill, lib=synth)
+    log(f"[bench] workload {W}x{H} patches={g.n_nodes} edges={len(g.edge_dst)} families={n_fam} "
+        f"hist_fill={hist_fill} built in {time.time() - t0:.1f}s")
+    return g, res, mx, fam
+
+
+def load_oracle():
+    subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(REPO, "oracle", "liboracle.so"))
+    lib.oracle_set_mode.argtypes = [C.c_void_p, C.c_int]
+    return lib
+
+
+def cpu_reference_rate(g, res, mx, fam, seed, budget_s, max_steps, warm_steps=0):
+    """family-updates/s of the oracle port in reference-shaped mode on all host cores."""
+    lib = load_oracle()
+    s = D.Sim(lib, g, seed=seed, prefix="oracle_")
+    lib.oracle_set_mode(s.h, 0)
+    s.set_patches(res, mx)
+    s.set_families(fam)
+    for _ in range(warm_steps):
+        s.step(1, allow_model_errors=True)
+    updates, t_total, steps = 0, 0.0, 0
+    per_step = []
+    while steps < max_steps and (steps == 0 or t_total + (t_total / steps) < budget_s):
+        t0 = time.perf_counter()
+        st = s.step(1, allow_model_errors=True)
+        dt = time.perf_counter() - t0
+        t_total += dt
+        per_step.append(dt)
+        updates += st.family_updates
+        steps += 1
+    s.close()
+    cores = len(os.sched_getaffinity(0))
+    omp = os.environ.get("OMP_NUM_THREADS")
+    if omp:
+        cores = min(cores, int(omp))
+    return updates / t_total, cores, steps, t_total, per_step
+
+
+def run_reference(args, cfg_name, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    synth = D.load_synth()
+    g, res, mx, fam = build_workload(cfg, args.seed, synth)
+    rate, cores, steps, t_total, per_step = cpu_reference_rate(g, res, mx, fam, args.sim_seed, args.cpu_seconds * max(1, args.steps),
+                                                               max_steps=args.warmup + args.steps, warm_steps=0)
+    # first `warmup` steps are part of the sample only if the budget allowed nothing else
+    timed = per_step[args.warmup:] if len(per_step) > args.warmup else per_step
+    ms = 1000.0 * sum(timed) / len(timed)
+    line = {
+        "impl": "reference", "metric": "family-updates/sec/GPU", "value": rate, "unit": "family-updates/s",
+        "n_gpus": args.gpus, "steps": len(timed), "warmup": min(args.warmup, len(per_step) - len(timed)),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{cfg_name}: {cfg[0]}x{cfg[1]} hex grid, {cfg[2]} families, hist_fill {cfg[4]}",
+                   "note": "CPU arm: C++ port of the reference algorithm (reference-shaped: Dijkstra per family per "
+                           "decision), OpenMP"},
+        "cpu_baseline": {"value": rate, "unit": "family-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of the same workload ({t_total:.1f} s)"},
+        "e2e": {"value": rate, "unit": "family-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def algorithmic_bytes(sim, fam_hist_len, mem_table, rho_src):
+    """Algorithmic HBM bytes per family-update of k_move, SURVEY.md §8d's formula restricted to part 1
+    (DESIGN.md §5): core record read + write (2 x 56), history append (16), the n_h remembered entries
+    that are sampled (16 each), and per sensed candidate the reach entry (dest u32 + cost f64 = 12) plus
+    what is gathered about the candidate patch (census, quality, band cultures: one 32-byte view); the
+    candidate terms are shared by the rho families that start the step on the same patch."""
+    near_off, _, reach_off, _, _ = sim.get_reach()
+    n = len(near_off) - 1
+    K = float(near_off[n]) / n          # sensed candidates per patch (2-hop list)
+    R = float(reach_off[n]) / n         # reach-row entries per patch (for reference; not in the formula)
+    n_h = float(np.sum(mem_table[:min(fam_hist_len, len(mem_table))]))
+    b = 2 * 56 + 16 + n_h * 16 + K * (12 + 32) / max(rho_src, 1.0)
+    return b, {"K": K, "R": R, "n_h": n_h, "rho": rho_src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--seed", type=int, default=1, help="workload seed")
+    ap.add_argument("--sim-seed", type=int, default=7, help="Philox key of the simulation")
+    ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU sample budget in seconds (total for b200 arm, per step for reference arm)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=20)
+    args = ap.parse_args()
+    cfg_name = args.config or "c2"
+    cfg = CONFIGS[cfg_name]
+
+    if args.impl == "reference":
+        if args.cpu_seconds is None:
+            args.cpu_seconds = 8.0
+        return run_reference(args, cfg_name, cfg)
+    if args.cpu_seconds is None:
+        args.cpu_seconds = 20.0
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the step loop has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = D.load()
+    synth = D.load_synth()
+    # N > 1: every rank advances its own replica of the workload (different seeds).  The band-partitioned
+    # multi-GPU step is not built yet; see DESIGN.md §8.
+    g, res, mx, fam = build_workload(cfg, args.seed + rank, synth)
+    opt = D.Options()
+    lib.dsim_default_options(C.byref(opt))
+    opt.device = local_rank
+    opt.use_graphs = 0 if args.no_graphs else 1
+    t0 = time.time()
+    sim = D.Sim(lib, g, seed=args.sim_seed, options=opt)
+    log(f"[bench] rank {rank}: handle + reach table in {time.time() - t0:.1f}s")
+    sim.set_patches(res, mx)
+    sim.set_families(fam)
+
+    launches0 = sim.launch_count()
+    barrier()
+    sim.step(args.warmup, want_stats=True, allow_model_errors=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches1 = sim.launch_count()
+    st, dev_ms = sim.step_timed(args.steps)
+    barrier()
+    clocks = sampler.stop()
+    launches2 = sim.launch_count()
+    t = torch.tensor([dev_ms, float(st.family_updates)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms_all, updates_all = float(tmax[0]), float(tsum[1])
+    else:
+        dev_ms_all, updates_all = dev_ms, float(st.family_updates)
+    value = updates_all / (dev_ms_all * 1e-3)
+    log(f"[bench] rank {rank}: {args.steps} steps in {dev_ms:.2f} ms, live {st.live_families}, "
+        f"births {st.births}, deaths {st.deaths}, errors {st.model_errors}")
+
+    # ---- per-kernel device times (separate pass: event pairs around every launch serialise the step) ----
+    roofline, kernels = None, {}
+    fam_live = st.live_families
+    occ = max(1, st.occupied_patches)
+    if args.profile_steps > 0:
+        sim.profile_enable(True)
+        sim.profile_read(reset=True)
+        stp = sim.step(args.profile_steps, allow_model_errors=True)
+        prof = sim.profile_read(reset=True)
+        sim.profile_enable(False)
+        total_ms = sum(v[0] for v in prof.values()) or 1.0
+        kernels = {k: {"ms_per_launch": v[0] / max(1, v[1]), "share": v[0] / total_ms} for k, v in prof.items()}
+        top = max(prof, key=lambda k: prof[k][0])
+        peak, peak_src = measured_peak_gbs()
+        upd_per_launch = stp.family_updates / args.profile_steps
+        mem_table = 0.5 ** (np.arange(626) / 12.0)
+        b_move, parts = algorithmic_bytes(sim, cfg[4] + args.warmup + args.steps, mem_table, fam_live / occ)
+        if top == "k_move":
+            bytes_per_launch = b_move * upd_per_launch
+        else:  # k_patch and the small kernels: core r/w + adaptation slots + patch state
+            bytes_per_launch = (152 + 90 / max(fam_live / occ, 1.0)) * upd_per_launch
+        dur_s = kernels[top]["ms_per_launch"] * 1e-3
+        achieved = bytes_per_launch / dur_s / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_family_update": b_move if top == "k_move" else None, "terms": parts}
+
+    # ---- end to end through the C ABI from host buffers -----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_steps_e2e = max(1, min(args.steps, 50))
+        barrier()
+        t0 = time.perf_counter()
+        sim2 = sim  # same handle: re-upload the initial state, run, download
+        sim2.set_patches(res, mx)
+        sim2.set_families(fam)
+        upd = 0
+        for _ in range(n_steps_e2e):
+            s1 = sim2.step(1, allow_model_errors=True)      # stats read-back every step (cli.rs:138 extinction check)
+            upd += s1.family_updates
+        out = sim2.get_families(history=False, adaptation=False)
+        r_out, _ = sim2.get_patches()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = (res.nbytes + mx.nbytes + sum(getattr(fam, n).nbytes for n, _ in D._FAM_FIELDS) + fam.hist_patch.nbytes
+               + fam.hist_harvest.nbytes + fam.hist_off.nbytes)
+        d2h = sum(getattr(out, n).nbytes for n, _ in D._FAM_FIELDS) + r_out.nbytes + n_steps_e2e * C.sizeof(D.StepStats)
+        tt = torch.tensor([dt, float(upd)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            dt_all, upd_all = float(a[0]), float(b[1])
+        else:
+            dt_all, upd_all = dt, float(upd)
+        e2e = {"value": upd_all / dt_all, "unit": "family-updates/s", "h2d_bytes_per_step": h2d / n_steps_e2e,
+               "d2h_bytes_per_step": d2h / n_steps_e2e, "steps": n_steps_e2e,
+               "what": "dsim_set_patches + dsim_set_families from host arrays, steps with per-step stats read-back, "
+                       "dsim_get_families (core columns) + dsim_get_patches, wall clock"}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, steps_cpu, t_cpu, _ = cpu_reference_rate(g, res, mx, fam, args.sim_seed, args.cpu_seconds, max_steps=20)
+        cpu = {"value": rate, "unit": "family-updates/s", "cores": cores, "kind": "port",
+               "sample": f"first {steps_cpu} steps of the same workload, oracle in reference-shaped mode "
+                         f"(Dijkstra per family per decision), {t_cpu:.1f} s"}
+
+    if rank == 0:
+        W, H, n_fam, n_occ, hist_fill = cfg
+        line = {
+            "metric": "family-updates/sec/GPU", "value": value, "unit": "family-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg_name}: {W}x{H} hex grid ({W * H} patches), {n_fam} families per GPU, "
+                                   f"hist_fill {hist_fill}, seed {args.seed}",
+                       "l2": "working set (reach table 3.7 GB + views 64 MB + histories) exceeds the 126 MB L2; no flush",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (band partition not built yet)",
+                       "cuda_graphs": not args.no_graphs,
+                       "live_families_end": int(fam_live)},
+            "per_gpu_value": value / world,
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches2 - launches1),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

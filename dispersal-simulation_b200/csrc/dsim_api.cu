@@ -71,6 +71,8 @@ struct dsim_handle {
     bool graphs_valid = false;
     bool profiling = false;
     cudaEvent_t ev[DSIM_K_COUNT + 1] = {};
+    cudaEvent_t tev[2] = {};
+    uint64_t timed_births0 = 0, timed_deaths0 = 0, timed_updates0 = 0;
     double k_ms[DSIM_K_COUNT] = {};
     uint64_t k_launches[DSIM_K_COUNT] = {};
     uint64_t total_launches = 0;
@@ -508,6 +510,8 @@ void dsim_destroy(dsim_handle *h) {
     destroy_graphs(h);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : h->tev)
+        if (e) cudaEventDestroy(e);
     free_list(h->fam_allocs);
     free_list(h->allocs);
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
@@ -578,6 +582,7 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
+    for (auto &e : h->tev) TRYCUDA(cudaEventCreate(&e));
     TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
     std::memset(h->ctl_h, 0, sizeof(DevCtl));
     TRY(dev_alloc(h, &h->ctl, 1, h->allocs));
@@ -796,6 +801,7 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
     if ((rc = push_ctl(h))) return rc;
     h->n_known = n;
     h->steps_since_check = 0;
+    h->timed_births0 = h->timed_deaths0 = h->timed_updates0 = 0;
     if ((rc = recensus(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
@@ -1084,6 +1090,30 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
         return DSIM_ERR_MODEL;
     }
     return DSIM_OK;
+}
+
+int dsim_step_timed(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats, double *device_ms) {
+    if (!h || !stats || !device_ms) return DSIM_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->tev[0], h->stream));
+    /* enqueue without the final read-back, then close the timed region on the device */
+    int rc = dsim_step(h, n_steps, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->tev[1], h->stream));
+    CK(cudaEventSynchronize(h->tev[1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]));
+    *device_ms = ms;
+    /* dsim_step(.., stats) reports deltas from its own start; recompute them over the timed call */
+    const uint64_t b0 = h->timed_births0, d0 = h->timed_deaths0, u0 = h->timed_updates0;
+    rc = dsim_step(h, 0, stats);
+    stats->births = h->ctl_h->births - b0;
+    stats->deaths = h->ctl_h->deaths - d0;
+    stats->family_updates = h->ctl_h->updates - u0;
+    h->timed_births0 = h->ctl_h->births;
+    h->timed_deaths0 = h->ctl_h->deaths;
+    h->timed_updates0 = h->ctl_h->updates;
+    return rc;
 }
 
 int dsim_step_part(dsim_handle *h, int part) {

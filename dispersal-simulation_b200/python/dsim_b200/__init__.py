@@ -276,6 +276,7 @@ class Sim:
             "profile_enable": (C.c_int, [vp, C.c_int]),
             "profile_read": (C.c_int, [vp, C.POINTER(KernelTimes), C.c_int]),
             "launch_count": (C.c_int, [vp, u64p]),
+            "step_timed": (C.c_int, [vp, C.c_uint32, C.POINTER(StepStats), f64p]),
         }.items():
             if hasattr(self.lib, self.prefix + name):
                 fn = self._f(name)
@@ -377,6 +378,12 @@ class Sim:
             return st
         self._check(self._f("step")(self.h, n_steps, None), allow_model_errors)
         return None
+
+    def step_timed(self, n_steps: int):
+        """n_steps steps timed with CUDA events on the library's stream -> (stats, device milliseconds)."""
+        st, ms = StepStats(), C.c_double()
+        self._check(self._f("step_timed")(self.h, n_steps, C.byref(st), C.byref(ms)))
+        return st, ms.value
 
     def sync(self):
         self._check(self._f("sync")(self.h))

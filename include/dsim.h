@@ -178,6 +178,9 @@ int dsim_set_storage(dsim_handle *h, uint64_t n, const uint32_t *node, const uin
  * returns after enqueueing when stats == NULL, otherwise waits and fills *stats. */
 int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats);
 int dsim_sync(dsim_handle *h);
+/* As dsim_step with stats, and *device_ms receives the time between two CUDA events recorded on the
+ * internal stream immediately before the first and after the last kernel of the n_steps steps. */
+int dsim_step_timed(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats, double *device_ms);
 
 /* Debugging aid for the parity tests: part 1 = update_each_family_step (lib.rs:511-552),
  * part 2 = distribute_each_patch_resources_step (lib.rs:591-655) + t += 1. */

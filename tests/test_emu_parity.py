@@ -1,0 +1,79 @@
+"""The CUDA kernels, compiled for the CPU by the test-only fiber emulator (tests/emu), against the
+oracle.  This is how the kernels are debugged in a container without a GPU; the GPU tests
+(test_gpu_parity.py) run the same scenarios through the real library on a B200."""
+import pytest
+
+import parity_cases as pc
+
+
+def test_reach_table(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 16, 20, 10, hist_cap=96)
+    pc.check_reach(o, d)
+
+
+def test_reach_table_ragged(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 16, 20, 10, hist_cap=96, graph_edit=pc.sparse_edges_graph)
+    pc.check_reach(o, d)
+
+
+def test_small_grid_by_parts(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 20, 30, 150, hist_cap=96)
+    pc.run_lockstep(o, d, 12, hist_cap=96)
+
+
+def test_growth_and_splits(oracle, emu, synth):
+    def peaceful(p):
+        p.cooperation_threshold = 65      # everyone cooperates: population grows, families split
+    o, d = pc.build_pair(oracle, emu, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96)
+    trace = pc.run_lockstep(o, d, 45, by_parts=False, hist_cap=96, check_every=3)
+    f = o.get_families(history=False, adaptation=False)
+    assert (f.parent_id != pc.D.NO_PARENT).sum() > 5, "scenario must exercise splits"
+    assert trace[-1] > 100
+
+
+def test_dense_coresidence_spill_path(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2500, n_occupied=6, hist_cap=96)
+    f = o.get_families(history=False, adaptation=False)
+    import numpy as np
+    assert np.unique(f.location, return_counts=True)[1].max() > 64, "scenario must exceed the shared-memory path"
+    pc.run_lockstep(o, d, 3, hist_cap=96)
+
+
+def test_prefilled_history_exact_capacity(oracle, emu, synth):
+    # default history capacity (every entry the memory loop can sample); oracle history is unbounded
+    o, d = pc.build_pair(oracle, emu, synth, 24, 30, 60, hist_fill=700)
+    cap = d.get_families().hist_off[1] - d.get_families().hist_off[0]
+    assert cap >= 625
+    pc.run_lockstep(o, d, 4, hist_cap=int(cap))
+
+
+def test_two_ecoregions_per_patch(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 200, hist_cap=96, graph_edit=pc.two_ecoregion_graph)
+    pc.run_lockstep(o, d, 8, hist_cap=96)
+
+
+def test_ragged_graph(oracle, emu, synth):
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 200, hist_cap=96, graph_edit=pc.sparse_edges_graph)
+    pc.run_lockstep(o, d, 8, hist_cap=96)
+
+
+def test_parameter_variants(oracle, emu, synth):
+    def edit(p):
+        p.cooperation_inclusive = 1
+        p.cooperation_threshold = 3
+        p.maximum_resources_one_adult_can_harvest = 0.25   # plotting/plot.py:259 treats this as typical
+        p.fight_deadliness = 1 << 30
+        p.culture_mutation_rate = 0.2                      # exercise the mutation clock hitting zero
+        p.minimum_adaptation = 0.3
+        p.resource_recovery_per_season = 0.05
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 250, params_edit=edit, hist_cap=96)
+    pc.run_lockstep(o, d, 10, hist_cap=96)
+
+
+def test_extinction_and_empty(oracle, emu, synth):
+    def starve(p):
+        p.maximum_resources_one_adult_can_harvest = 1e-6
+    o, d = pc.build_pair(oracle, emu, synth, 12, 12, 40, params_edit=starve, hist_cap=96)
+    trace = pc.run_lockstep(o, d, 40, by_parts=False, hist_cap=96, check_every=5)
+    assert trace[-1] == 0, "everyone starves (extinction check of src/cli.rs:138)"
+    pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)   # stepping an empty world is a no-op
