@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=20)
+    ap.add_argument("--flags", type=int, default=0, help="dsim_options.flags (kernel variants, see include/dsim.h)")
     args = ap.parse_args()
     cfg_name = args.config or "c2"
     cfg = CONFIGS[cfg_name]
@@ -244,6 +245,7 @@ def main():
     lib.dsim_default_options(C.byref(opt))
     opt.device = local_rank
     opt.use_graphs = 0 if args.no_graphs else 1
+    opt.flags = args.flags
     t0 = time.time()
     sim = D.Sim(lib, g, seed=args.sim_seed, options=opt)
     log(f"[bench] rank {rank}: handle + reach table in {time.time() - t0:.1f}s")

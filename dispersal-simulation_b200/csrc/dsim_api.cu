@@ -46,6 +46,7 @@ struct dsim_handle {
     uint32_t n_nodes = 0, n_eco = 0;
     std::vector<uint32_t> eco_off_h; /* [n+1] */
     uint64_t n_near = 0, n_reach = 0, n_reach_padded = 0;
+    uint32_t max_row = 0;
 
     std::vector<void *> allocs; /* everything to cudaFree */
     ReachTable rt;
@@ -55,7 +56,7 @@ struct dsim_handle {
     StepScratch sc;
     DevCtl *ctl = nullptr;
     DevCtl *ctl_h = nullptr; /* pinned mirror */
-    double *mem_table_d = nullptr;
+    uint32_t *mem_thr_d = nullptr;
     ModelConst mc;
     std::vector<void *> fam_allocs; /* family-capacity dependent arrays */
     uint64_t cap = 0, hs_cap = 0;
@@ -157,6 +158,8 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     a.ctl = h->ctl;
     a.mc = h->mc;
     a.parity = parity;
+    a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
+    a.children_inline = (h->opt.flags & DSIM_OPT_MOVE_COOPERATIVE) ? 1u : 0u;
     return a;
 }
 
@@ -190,7 +193,8 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
     A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8)
     A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
     A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
-    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap)
+    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_small, new_cap) A(ns.plist_big, new_cap)
+    A(ns.child_task, new_cap)
     A(ns.x_idx, new_cap) A(ns.x_tidx, new_cap) A(ns.x_size, new_cap) A(ns.x_band, new_cap)
     A(ns.x_bcnt, new_cap) A(ns.x_btot, new_cap)
     A(ns.x_key, new_cap) A(ns.x_fid, new_cap) A(ns.x_tfid, new_cap) A(ns.x_cult, new_cap) A(ns.x_bcult, new_cap)
@@ -561,7 +565,9 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     h->seed = seed;
     h->n_nodes = n;
     h->n_eco = (uint32_t)n_eco;
+    std::memset(&h->geom, 0, sizeof h->geom);
     h->geom.n_sm = (uint32_t)std::max(1, prop.multiProcessorCount);
+    h->geom.force_global_rows = (o.flags & DSIM_OPT_ROWS_IN_PLACE) ? 1u : 0u;
     std::memset(&h->rt, 0, sizeof h->rt);
     std::memset(&h->ps, 0, sizeof h->ps);
     std::memset(&h->hv, 0, sizeof h->hv);
@@ -600,23 +606,31 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         h->n_near = hr.near_dst.size();
         h->n_reach = hr.n_reach;
         h->n_reach_padded = hr.dst.size();
-        uint32_t *off, *dst, *near_off, *near_dst;
+        h->max_row = 0;
+        for (uint32_t v = 0; v < n; ++v) h->max_row = std::max(h->max_row, hr.hdr[v].len);
+        RowHdr *hdr;
+        uint8_t *hash;
+        uint32_t *dst, *near_off, *near_dst;
         double *cost;
         uint16_t *nidx;
-        TRY(dev_alloc(h, &off, hr.off.size(), h->allocs, false));
-        TRY(dev_alloc(h, &dst, hr.dst.size(), h->allocs, false));
-        TRY(dev_alloc(h, &cost, hr.cost.size(), h->allocs, false));
-        TRY(dev_alloc(h, &nidx, hr.nidx.size(), h->allocs, false));
+        static_assert(sizeof(RowHdr) == sizeof(HostRowHdr), "row header layouts must agree");
+        TRY(dev_alloc(h, &hdr, hr.hdr.size(), h->allocs, false));
+        TRY(dev_alloc(h, &dst, hr.dst.size() + 8, h->allocs, false));
+        TRY(dev_alloc(h, &cost, hr.cost.size() + 8, h->allocs, false));
+        TRY(dev_alloc(h, &nidx, hr.nidx.size() + 8, h->allocs, false));
+        TRY(dev_alloc(h, &hash, hr.hash.size(), h->allocs, false));
+        TRY(upload(h, hash, hr.hash.data(), hr.hash.size()));
         TRY(dev_alloc(h, &near_off, hr.near_off.size(), h->allocs, false));
         TRY(dev_alloc(h, &near_dst, hr.near_dst.size(), h->allocs, false));
-        TRY(upload(h, off, hr.off.data(), hr.off.size()));
+        TRY(upload(h, (HostRowHdr *)hdr, hr.hdr.data(), hr.hdr.size()));
         TRY(upload(h, dst, hr.dst.data(), hr.dst.size()));
         TRY(upload(h, cost, hr.cost.data(), hr.cost.size()));
         TRY(upload(h, nidx, hr.nidx.data(), hr.nidx.size()));
         TRY(upload(h, near_off, hr.near_off.data(), hr.near_off.size()));
         TRY(upload(h, near_dst, hr.near_dst.data(), hr.near_dst.size()));
         TRYCUDA(cudaStreamSynchronize(h->stream));
-        h->rt.off = off; h->rt.dst = dst; h->rt.cost = cost; h->rt.nidx = nidx;
+        h->rt.hash = hash;
+        h->rt.hdr = hdr; h->rt.dst = dst; h->rt.cost = cost; h->rt.nidx = nidx;
         h->rt.near_off = near_off; h->rt.near_dst = near_dst;
     }
     /* patches */
@@ -668,10 +682,21 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
             memory *= decay;
         }
         mc.n_mem = (uint32_t)mem.size();
-        TRY(dev_alloc(h, &h->mem_table_d, mem.size(), h->allocs, false));
-        TRY(upload(h, h->mem_table_d, mem.data(), mem.size()));
+        /* entry n is kept iff draw * 2^-32 < memory_n (lib.rs:859)  <=>  draw <= ceil(memory_n * 2^32) - 1 */
+        std::vector<uint32_t> thr(mem.size());
+        for (size_t k = 0; k < mem.size(); ++k) {
+            const double x = std::ceil(mem[k] * 4294967296.0) - 1.0;
+            thr[k] = x >= 4294967295.0 ? 4294967295u : (x <= 0.0 ? 0u : (uint32_t)x);
+        }
+        TRY(dev_alloc(h, &h->mem_thr_d, thr.size(), h->allocs, false));
+        TRY(upload(h, h->mem_thr_d, thr.data(), thr.size()));
         TRYCUDA(cudaStreamSynchronize(h->stream));
-        mc.mem_table = h->mem_table_d;
+        mc.mem_thr = h->mem_thr_d;
+        if (dsim_configure_kernels(&h->geom, h->max_row, mc.n_mem) != 0) {
+            g_create_error = "cannot configure the shared-memory size of k_move";
+            dsim_destroy(h);
+            return DSIM_ERR_CUDA;
+        }
         uint32_t hcap = o.history_capacity ? o.history_capacity : std::max(mc.n_mem, mc.adult_reset + 1u);
         h->hcap = (hcap + 3u) & ~3u;
         h->acap = compute_acap(mc.min_adapt);
@@ -1149,22 +1174,27 @@ int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst, uint6
                    double *reach_cost) {
     if (!h) return DSIM_ERR_INVALID;
     const uint32_t n = h->n_nodes;
-    std::vector<uint32_t> off(n + 1), noff(n + 1), dst(h->n_reach_padded);
+    std::vector<HostRowHdr> hdr(n);
+    std::vector<uint32_t> noff(n + 1), dst(h->n_reach_padded);
     std::vector<double> cost(h->n_reach_padded);
     int rc;
-    if ((rc = download(h, off.data(), h->rt.off, n + 1)) || (rc = download(h, noff.data(), h->rt.near_off, n + 1)) ||
+    if ((rc = download(h, hdr.data(), (const HostRowHdr *)h->rt.hdr, n)) || (rc = download(h, noff.data(), h->rt.near_off, n + 1)) ||
         (rc = download(h, dst.data(), h->rt.dst, h->n_reach_padded)) || (rc = download(h, cost.data(), h->rt.cost, h->n_reach_padded)))
         return rc;
     if (near_dst && (rc = download(h, near_dst, h->rt.near_dst, h->n_near))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     uint64_t w = 0;
+    std::vector<std::pair<uint32_t, double>> row;
     for (uint32_t v = 0; v < n; ++v) {
         if (near_off) near_off[v] = noff[v];
         if (reach_off) reach_off[v] = w;
-        for (uint32_t e = off[v]; e < off[v + 1]; ++e) {
-            if (dst[e] == 0xFFFFFFFFu) break; /* row padding */
-            if (reach_dst) reach_dst[w] = dst[e];
-            if (reach_cost) reach_cost[w] = cost[e];
+        row.clear(); /* merge the sensed-first layout back into one ascending list */
+        for (uint32_t e = hdr[v].start; e < hdr[v].start + hdr[v].len; ++e)
+            if (dst[e] != 0xFFFFFFFFu) row.push_back({dst[e], cost[e]});
+        std::sort(row.begin(), row.end());
+        for (const auto &qc : row) {
+            if (reach_dst) reach_dst[w] = qc.first;
+            if (reach_cost) reach_cost[w] = qc.second;
             ++w;
         }
     }

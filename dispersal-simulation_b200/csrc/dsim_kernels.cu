@@ -26,10 +26,15 @@
 #include "dsim_kernels.h"
 #include "dsim_math.h"
 
+#include <cstring>
+
 #define LIFE_BLOCK 256
-#define MOVE_THREADS 256
+#ifndef MOVE_THREADS
+#define MOVE_THREADS 128
+#endif
 #define PATCH_WARPS 4
 #define PATCH_M 64 /* families per node handled in shared memory; larger nodes spill to HBM scratch */
+#define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by one thread each */
 
 __device__ __forceinline__ dsim_stream stream_of(const ModelConst &mc) {
     dsim_stream s;
@@ -38,10 +43,15 @@ __device__ __forceinline__ dsim_stream stream_of(const ModelConst &mc) {
     return s;
 }
 
-/* resource_uncertainty (lib.rs:1317) for candidate `i` of family `fid`: two draws per Philox block */
-__device__ __forceinline__ double noise_draw(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t i) {
-    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_NOISE, i >> 1);
+/* resource_uncertainty (lib.rs:1317) for candidate `i` of family `fid`: two draws per Philox block;
+ * index i uses block i>>1 and words (x,y) if i is even, (z,w) otherwise. */
+__device__ __forceinline__ uint32_t noise_block(uint32_t i) { return i >> 1; }
+__device__ __forceinline__ double noise_pick(const dsim_u4 &o, uint32_t i) {
     return (i & 1u) ? dsim_u53(o.z, o.w) : dsim_u53(o.x, o.y);
+}
+__device__ __forceinline__ double noise_draw(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t i) {
+    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_NOISE, noise_block(i));
+    return noise_pick(o, i);
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -160,6 +170,8 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
         ctl->n_cur[a.parity ^ 1u] = n_alive + n_children;
         ctl->n_occ[a.parity] = 0;
         ctl->seg_cursor = 0;
+        ctl->n_small = 0;
+        ctl->n_big = 0;
         ctl->births += n_children;
         ctl->deaths += n - n_alive;
         ctl->updates += n;
@@ -171,38 +183,153 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
     }
 }
 
+/* ---- asynchronous bulk copies global -> shared (TMA, 1-D) with an mbarrier ------------------------ */
+#if defined(DSIM_EMU)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 /* ------------------------------------------------------------------------------------------ *
  * part 1c: move + split
+ *
+ * One warp per CHUNK of 32 consecutive families (= one word of the survivor / split bitmaps).  Lane L
+ * loads the record of family 32c+L (coalesced), its reach-row header and history length; new positions
+ * and children's ranks are popcounts of the bitmap word plus the per-256 offsets of k_control.  The
+ * surviving families are then decided 32/G at a time, each by a GROUP of G lanes; the groups of a warp
+ * run in lockstep (every collective is executed by the full warp, every loop runs while any group
+ * needs it), so that one instruction stream and one memory round trip serve 32/G families.  Each
+ * group stages its family's reach row in shared memory with TMA bulk copies.
+ * Selected with DSIM_OPT_MOVE_COOPERATIVE; the default is the thread-per-family kernel further down.
  * ------------------------------------------------------------------------------------------ */
 struct Choice { /* best_location state, lib.rs:911-916 */
     uint32_t target;
     double max_gain, t_cost, m;
 };
 
-/* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in
- * lane order: a candidate is accepted iff g > m with m as left by the previous acceptance. */
-__device__ __forceinline__ void accept_scan(Choice &ch, bool valid, double g, double gain, double cost, uint32_t q,
-                                            uint32_t lane) {
-    uint32_t cursor = 0;
-    for (;;) {
-        const uint32_t mask = __ballot_sync(DSIM_FULL, valid && lane >= cursor && g > ch.m);
-        if (mask == 0u) break;
-        const int L = __ffs((int)mask) - 1;
-        const double gain_l = __shfl_sync(DSIM_FULL, gain, L);
-        const double cost_l = __shfl_sync(DSIM_FULL, cost, L);
-        const uint32_t q_l = __shfl_sync(DSIM_FULL, q, L);
-        ch.target = q_l;
-        ch.max_gain = dsim_oyr_max(ch.max_gain, gain_l);
-        ch.t_cost = cost_l;
-        ch.m = ch.max_gain - ch.t_cost;
-        cursor = (uint32_t)L + 1u;
+#define MOVE_ROUND 32u   /* candidates evaluated per round and group */
+#define MOVE_RING 128u   /* capacity of a group's ring of kept history indices */
+#define DSIM_NEG_INF (dsim_bits_to_f64(0xFFF0000000000000ull))
+
+struct GroupSmem { /* carved out of dynamic shared memory, one per group */
+    double *cost;     /* [row_cap] staged reach row */
+    uint32_t *dst;    /* [row_cap] */
+    uint16_t *nidx;   /* [row_cap] */
+    double *c_g;      /* [MOVE_ROUND] candidates of the current round: noised net gain (-inf = no candidate) */
+    double *c_gain;   /* [MOVE_ROUND] expected harvest */
+    double *c_cost;   /* [MOVE_ROUND] travel cost */
+    uint32_t *c_q;    /* [MOVE_ROUND] node */
+    uint16_t *ring;   /* [MOVE_RING] kept history indices awaiting evaluation */
+    uint64_t *bar;    /* mbarrier of the row staging */
+    uint32_t phase;
+};
+
+__host__ __device__ __forceinline__ uint32_t move_smem_per_group(uint32_t row_cap) {
+    return row_cap * 14u + MOVE_ROUND * 28u + MOVE_RING * 2u + 16u;
+}
+__host__ __device__ __forceinline__ uint32_t move_smem_table(uint32_t n_mem) { return ((n_mem * 4u) + 15u) & ~15u; }
+
+/* A family's reach row as the kernel sees it: staged in shared memory or in place in HBM.
+ * Layout: [n_sensed entries that are also in the 2-hop list, ascending dst][the other reachable
+ * nodes, ascending dst][padding]. */
+struct Row {
+    const uint32_t *dst;
+    const double *cost;
+    const uint16_t *nidx;
+    uint32_t len, n_sensed;
+};
+
+/* Stage a reach row (group leader issues, every lane of the group waits).  Rows start at multiples
+ * of 8 entries and are padded to multiples of 8, so every column start is 16-byte aligned and every
+ * copy size a multiple of 16 bytes, as cp.async.bulk requires.  The caller guarantees (by a
+ * __syncwarp) that no lane still reads the buffers. */
+template <bool STAGED>
+__device__ __forceinline__ Row stage_row(const ReachTable &rt, bool on, uint32_t start, uint32_t len, uint32_t n_sensed,
+                                         GroupSmem &gs, bool leader) {
+    Row row;
+    row.len = on ? len : 0u;
+    row.n_sensed = on ? n_sensed : 0u;
+    if (STAGED) {
+        if (on && len > 0u) {
+            if (leader) {
+                const uint32_t ns8 = (n_sensed + 7u) & ~7u;
+                mbar_expect_tx(gs.bar, len * 12u + ns8 * 2u);
+                bulk_g2s(gs.cost, rt.cost + start, len * 8u, gs.bar);
+                bulk_g2s(gs.dst, rt.dst + start, len * 4u, gs.bar);
+                if (ns8) bulk_g2s(gs.nidx, rt.nidx + start, ns8 * 2u, gs.bar);
+            }
+            mbar_wait(gs.bar, gs.phase);
+            gs.phase ^= 1u;
+        }
+        __syncwarp();
+        row.dst = gs.dst;
+        row.cost = gs.cost;
+        row.nidx = gs.nidx;
+    } else {
+        row.dst = rt.dst + start;
+        row.cost = rt.cost + start;
+        row.nidx = rt.nidx + start;
     }
+    return row;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *v, uint32_t lo, uint32_t hi, uint32_t q) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (v[mid] < q)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+/* travel cost look-up in a reach row (replaces travel_costs.get(), lib.rs:869): both sorted segments */
+__device__ __forceinline__ bool reach_lookup(const Row &row, uint32_t q, double *cost) {
+    uint32_t k = lower_bound_u32(row.dst, 0u, row.n_sensed, q);
+    if (k < row.n_sensed && row.dst[k] == q) {
+        *cost = row.cost[k];
+        return true;
+    }
+    k = lower_bound_u32(row.dst, row.n_sensed, row.len, q);
+    if (k < row.len && row.dst[k] == q) {
+        *cost = row.cost[k];
+        return true;
+    }
+    return false;
 }
 
 /* destination_quality, lib.rs:1034-1062 (has_enemies lib.rs:996-1017, expected_harvest 989-994) */
-__device__ __forceinline__ double dest_quality(const StepArgs &a, uint32_t q, uint64_t culture, uint32_t size,
+__device__ __forceinline__ double view_quality(const StepArgs &a, const PatchView &v, uint64_t culture, uint32_t size,
                                                bool same_patch) {
-    const PatchView v = a.ps.view[q];
     bool enemy = false;
     if (v.nb > 0u) {
         enemy = !dsim_will_cooperate(culture, v.cult0, a.mc.threshold, a.mc.inclusive);
@@ -214,119 +341,643 @@ __device__ __forceinline__ double dest_quality(const StepArgs &a, uint32_t q, ui
     return v.quality / (double)pop_at_destination;
 }
 
-/* travel cost look-up in the reach row [r0, r1) (replaces travel_costs.get(), lib.rs:869) */
-__device__ __forceinline__ bool reach_lookup(const ReachTable &rt, uint32_t r0, uint32_t r1, uint32_t q, double *cost) {
-    uint32_t lo = r0, hi = r1;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (rt.dst[mid] < q)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    if (lo < r1 && rt.dst[lo] == q) {
-        *cost = rt.cost[lo];
-        return true;
-    }
-    return false;
-}
+template <int G> struct Lanes { /* position of a lane in its group */
+    uint32_t lane, gl, goff, gbits;
+    __device__ __forceinline__ explicit Lanes(uint32_t l) : lane(l), gl(l % G), goff(l - l % G), gbits(G == 32 ? 0xffffffffu : ((1u << G) - 1u)) {}
+    /* ballot restricted to my group (bit k = lane k of the group); executed by the full warp */
+    __device__ __forceinline__ uint32_t ballot(bool pred) const { return (__ballot_sync(DSIM_FULL, pred) >> goff) & gbits; }
+};
 
-/* The remembered-patch part of decide_on_moving (lib.rs:854-867): history entry n (0 = newest) is
- * kept with probability memory_n; kept entries with a travel cost become candidates whose expected
- * harvest is the remembered per-capita harvest.  With `virt`, entry 0 is (v0_patch, v0_harv) and
- * entry n >= 1 is ring entry n-1 (a child inheriting its parent's history, lib.rs:1882-1885). */
-__device__ __forceinline__ void history_pass(const StepArgs &a, uint32_t step, uint32_t lane, uint64_t fid, uint32_t r0,
-                                             uint32_t r1, uint32_t n_sensed, uint32_t hs, uint32_t ring_cnt, uint32_t nh,
-                                             bool virt, uint32_t v0_patch, double v0_harv, Choice &ch) {
-    const uint32_t hcap = a.hv.hcap;
-    const size_t hbase = (size_t)hs * hcap;
-    for (uint32_t n0 = 0; n0 < nh; n0 += 128u) {
-        /* memory draws: entry n uses Philox block (n>>7)*32 + (n&31), word (n>>5)&3 */
-        const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, (n0 >> 7) * 32u + lane);
-#pragma unroll
-        for (uint32_t w = 0; w < 4u; ++w) {
-            const uint32_t nb0 = n0 + 32u * w;
-            if (nb0 >= nh) break;
-            const uint32_t n = nb0 + lane;
-            bool keep = false;
-            if (n < nh) keep = ((double)dsim_word(o, w) * (1.0 / 4294967296.0)) < a.mc.mem_table[n];
-            if (!__any_sync(DSIM_FULL, keep)) continue;
-            bool cand = false;
-            double g = 0.0, gain = 0.0, cost = 0.0;
-            uint32_t q = 0;
-            if (keep) {
-                if (virt && n == 0u) {
-                    q = v0_patch;
-                    gain = v0_harv;
-                } else {
-                    const uint32_t nn = virt ? n - 1u : n;
-                    const uint32_t pos = (ring_cnt - 1u - nn) % hcap;
-                    q = a.hv.hist_patch[hbase + pos];
-                    gain = a.hv.hist_harv[hbase + pos];
-                }
-                if (reach_lookup(a.rt, r0, r1, q, &cost)) {
-                    const double u = noise_draw(a.mc, step, fid, n_sensed + n);
-                    g = gain * u - cost;
-                    cand = true;
-                }
+/* Ordered acceptance scan of lib.rs:918-927 over the first `ncand` candidates of the group's round
+ * buffer (c_g/c_gain/c_cost/c_q), in candidate order: a candidate is accepted iff g > m with m as left
+ * by the previous acceptance.  Full-warp lockstep; `ch` is replicated in the lanes of a group. */
+template <int G>
+__device__ __forceinline__ void accept_round(const Lanes<G> &ln, const GroupSmem &gs, bool on, uint32_t ncand, Choice &ch) {
+    for (uint32_t sub = 0; __any_sync(DSIM_FULL, on && sub < ncand); sub += (uint32_t)G) {
+        const uint32_t e = sub + ln.gl;
+        const double g = (on && e < ncand) ? gs.c_g[e] : DSIM_NEG_INF;
+        uint32_t cursor = 0;
+        for (;;) {
+            const uint32_t all = __ballot_sync(DSIM_FULL, ln.gl >= cursor && g > ch.m);
+            if (all == 0u) break;
+            const uint32_t mine = (all >> ln.goff) & ln.gbits;
+            if (mine != 0u) {
+                const uint32_t L = (uint32_t)__ffs((int)mine) - 1u;
+                const uint32_t ea = sub + L;
+                ch.target = gs.c_q[ea];
+                ch.max_gain = dsim_oyr_max(ch.max_gain, gs.c_gain[ea]);
+                ch.t_cost = gs.c_cost[ea];
+                ch.m = ch.max_gain - ch.t_cost;
+                cursor = L + 1u;
+            } else {
+                cursor = (uint32_t)G;
             }
-            accept_scan(ch, cand, g, gain, cost, q, lane);
         }
     }
 }
 
-/* number of set bits of a 256-family bitmap group that precede family i, plus the group's offset;
- * *flag receives bit i.  Warp-uniform i. */
-__device__ __forceinline__ uint32_t rank_before(const uint32_t *bits, const uint32_t *blk_off, uint32_t i, uint32_t lane,
-                                                bool *flag) {
-    const uint32_t wi = (i >> 5) & 7u;
-    uint32_t word = 0, v = 0;
-    if (lane < 8u) {
-        word = bits[(i >> 8) * 8u + lane];
-        if (lane < wi)
-            v = (uint32_t)__popc(word);
-        else if (lane == wi)
-            v = (uint32_t)__popc(word & ((1u << (i & 31u)) - 1u));
+struct HistSource { /* where history entry n (0 = newest) of the deciding family comes from */
+    uint32_t hs, ring_cnt;
+    bool virt;          /* entry 0 is (v0_patch, v0_harv), entry n >= 1 is ring entry n-1 (lib.rs:1882-1885) */
+    uint32_t v0_patch;
+    double v0_harv;
+};
+
+/* evaluate up to G kept history entries (the oldest `k` of the group's ring) as candidates */
+template <int G>
+__device__ __forceinline__ void history_flush(const StepArgs &a, const Lanes<G> &ln, GroupSmem &gs, uint32_t step, bool on,
+                                              uint64_t fid, const Row &row, uint32_t n_sensed, const HistSource &hsrc,
+                                              uint32_t head, uint32_t k, Choice &ch) {
+    if (on && ln.gl < k) {
+        const uint32_t n = gs.ring[(head + ln.gl) % MOVE_RING];
+        uint32_t q;
+        double gain, cost = 0.0, g = DSIM_NEG_INF;
+        if (hsrc.virt && n == 0u) {
+            q = hsrc.v0_patch;
+            gain = hsrc.v0_harv;
+        } else {
+            const uint32_t nn = hsrc.virt ? n - 1u : n;
+            const uint32_t pos = (hsrc.ring_cnt - 1u - nn) % a.hv.hcap;
+            const size_t at = (size_t)hsrc.hs * a.hv.hcap + pos;
+            q = a.hv.hist_patch[at];
+            gain = a.hv.hist_harv[at];
+        }
+        if (reach_lookup(row, q, &cost)) g = gain * noise_draw(a.mc, step, fid, n_sensed + n) - cost;
+        gs.c_g[ln.gl] = g;
+        gs.c_gain[ln.gl] = gain;
+        gs.c_cost[ln.gl] = cost;
+        gs.c_q[ln.gl] = q;
     }
-    const uint32_t myword = __shfl_sync(DSIM_FULL, word, (int)wi);
-    v += __shfl_xor_sync(DSIM_FULL, v, 4);
-    v += __shfl_xor_sync(DSIM_FULL, v, 2);
-    v += __shfl_xor_sync(DSIM_FULL, v, 1);
-    v = __shfl_sync(DSIM_FULL, v, 0);
-    *flag = ((myword >> (i & 31u)) & 1u) != 0u;
-    return blk_off[i >> 8] + v;
+    __syncwarp();
+    accept_round<G>(ln, gs, on, k, ch);
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(MOVE_THREADS) k_move(StepArgs a) {
+/* The remembered-patch part of decide_on_moving (lib.rs:854-867): history entry n is kept with
+ * probability memory_n (keyed 32-bit draw against an integer threshold: no memory access); kept
+ * entries with a travel cost become candidates whose expected harvest is the remembered per-capita
+ * harvest.  Per iteration a group examines 4G consecutive entries (one Philox block of four draws per
+ * lane), appends the indices of the kept ones, in order, to its ring and evaluates them G at a time. */
+template <int G>
+__device__ __forceinline__ void history_pass(const StepArgs &a, const Lanes<G> &ln, GroupSmem &gs, uint32_t step, bool on,
+                                             uint64_t fid, const Row &row, uint32_t n_sensed, uint32_t nh, const HistSource &hsrc,
+                                             const uint32_t *thr, Choice &ch) {
+    uint32_t head = 0, tail = 0;
+    for (uint32_t nb = 0; __any_sync(DSIM_FULL, on && nb < nh); nb += 4u * (uint32_t)G) {
+        const uint32_t n4 = nb + 4u * ln.gl;
+        uint32_t flags = 0;
+        if (on && n4 < nh) {
+            /* memory draws: entry n uses Philox block n>>2, word n&3 */
+            const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, n4 >> 2);
+#pragma unroll
+            for (uint32_t w = 0; w < 4u; ++w)
+                if (n4 + w < nh && dsim_word(o, w) <= thr[n4 + w]) flags |= 1u << w; /* draw * 2^-32 < memory_n, lib.rs:859 */
+        }
+        /* exclusive prefix sum of the per-lane counts inside the group */
+        const uint32_t c = (uint32_t)__popc(flags);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(DSIM_FULL, incl, (unsigned)d, G);
+            if ((int)ln.gl >= d) incl += up;
+        }
+        const uint32_t total = __shfl_sync(DSIM_FULL, incl, G - 1, G);
+        uint32_t at = tail + incl - c;
+#pragma unroll
+        for (uint32_t w = 0; w < 4u; ++w)
+            if (flags & (1u << w)) gs.ring[(at++) % MOVE_RING] = (uint16_t)(n4 + w);
+        tail += total;
+        __syncwarp();
+        while (__any_sync(DSIM_FULL, on && tail - head >= (uint32_t)G)) {
+            const bool go = on && tail - head >= (uint32_t)G;
+            history_flush<G>(a, ln, gs, step, go, fid, row, n_sensed, hsrc, head, (uint32_t)G, ch);
+            if (go) head += (uint32_t)G;
+        }
+    }
+    if (__any_sync(DSIM_FULL, on && tail > head)) {
+        const bool go = on && tail > head;
+        history_flush<G>(a, ln, gs, step, go, fid, row, n_sensed, hsrc, head, tail - head, ch);
+    }
+}
+
+#ifndef MOVE_MIN_BLOCKS
+#define MOVE_MIN_BLOCKS 4
+#endif
+#ifndef MOVE_GROUP
+#define MOVE_GROUP 16
+#endif
+
+template <bool STAGED, int G>
+__global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs a, uint32_t row_cap) {
+    constexpr uint32_t NG = 32 / G;          /* families decided concurrently by a warp */
+    constexpr uint32_t KP = MOVE_ROUND / G;  /* candidates per lane and round */
+    DSIM_DYN_SMEM(smem_raw);
     DevCtl *ctl = a.ctl;
     const uint32_t n = ctl->n_cur[a.parity];
     const uint32_t step = ctl->t;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const Lanes<G> ln(lane);
+    const uint32_t grp = lane / G;
+    const bool leader = ln.gl == 0u;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
+    const uint32_t lt = (1u << lane) - 1u;
 
-    for (uint32_t i = gwarp; i < n; i += nwarps) {
-        bool alive, split;
-        const uint32_t newpos = rank_before(a.sc.alive_bits, a.sc.blk_alive, i, lane, &alive);
-        const uint32_t crank = rank_before(a.sc.split_bits, a.sc.blk_split, i, lane, &split);
-        if (!alive) { /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
-            if (lane == 0) a.sc.dead_hs[i - newpos] = a.cur.hs[i];
+    /* dynamic shared memory: [keep thresholds, n_mem x u32][one GroupSmem area per group] */
+    uint32_t *thr = (uint32_t *)smem_raw;
+    for (uint32_t k = threadIdx.x; k < a.mc.n_mem; k += blockDim.x) thr[k] = a.mc.mem_thr[k];
+    GroupSmem gs;
+    {
+        unsigned char *base = smem_raw + move_smem_table(a.mc.n_mem) + (size_t)(wib * NG + grp) * move_smem_per_group(row_cap);
+        gs.cost = (double *)base;
+        base += (size_t)row_cap * 8u;
+        gs.c_g = (double *)base;
+        gs.c_gain = gs.c_g + MOVE_ROUND;
+        gs.c_cost = gs.c_gain + MOVE_ROUND;
+        base += MOVE_ROUND * 24u;
+        gs.bar = (uint64_t *)base;
+        base += 16u;
+        gs.dst = (uint32_t *)base;
+        base += (size_t)row_cap * 4u;
+        gs.c_q = (uint32_t *)base;
+        base += MOVE_ROUND * 4u;
+        gs.nidx = (uint16_t *)base;
+        base += (size_t)row_cap * 2u;
+        gs.ring = (uint16_t *)base;
+        gs.phase = 0u;
+        if (STAGED && leader) mbar_init(gs.bar, 1u);
+    }
+    __syncthreads();
+
+    const uint32_t nchunks = (n + 31u) >> 5;
+    for (uint32_t c = gwarp; c < nchunks; c += nwarps) {
+        const uint32_t i = (c << 5) + lane;
+        const bool in = i < n;
+        /* ---- ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) ------------------- */
+        const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
+        uint32_t va = 0, vs = 0;
+        if (lane < (c & 7u)) {
+            va = (uint32_t)__popc(a.sc.alive_bits[(c & ~7u) + lane]);
+            vs = (uint32_t)__popc(a.sc.split_bits[(c & ~7u) + lane]);
+        }
+        va += __shfl_xor_sync(DSIM_FULL, va, 4);
+        vs += __shfl_xor_sync(DSIM_FULL, vs, 4);
+        va += __shfl_xor_sync(DSIM_FULL, va, 2);
+        vs += __shfl_xor_sync(DSIM_FULL, vs, 2);
+        va += __shfl_xor_sync(DSIM_FULL, va, 1);
+        vs += __shfl_xor_sync(DSIM_FULL, vs, 1);
+        va = __shfl_sync(DSIM_FULL, va, 0);
+        vs = __shfl_sync(DSIM_FULL, vs, 0);
+        const uint32_t my_newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
+        const uint32_t my_crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
+        const bool my_alive = ((alive_mask >> lane) & 1u) != 0u && my_newpos < cap;
+
+        /* ---- my family's record ------------------------------------------------------------- */
+        uint64_t m_id = 0, m_culture = 0;
+        double m_stored = 0.0, m_lh = 0.0;
+        uint32_t m_loc = 0, m_size = 0, m_till_adult = 0, m_till_mut = 0, m_misc = 0, m_hs = 0;
+        uint32_t m_start = 0, m_len = 0, m_nsensed = 0, m_nnear = 0, m_hist_cnt = 0;
+        if (in) {
+            m_hs = a.cur.hs[i];
+            if (my_alive) {
+                m_loc = a.cur.loc[i];
+                m_id = a.cur.id[i];
+                m_culture = a.cur.culture[i];
+                m_stored = a.cur.stored[i];
+                m_lh = a.cur.last_harvest[i];
+                m_size = a.cur.size[i];
+                m_till_adult = a.cur.till_adult[i];
+                m_till_mut = a.cur.till_mut[i];
+                m_misc = a.cur.misc[i];
+                const RowHdr hd = a.rt.hdr[m_loc];
+                m_start = hd.start;
+                m_len = hd.len;
+                m_nsensed = hd.n_sensed;
+                m_nnear = hd.n_near;
+                m_hist_cnt = a.hv.hist_cnt[m_hs];
+            } else if (!((alive_mask >> lane) & 1u)) {
+                a.sc.dead_hs[i - my_newpos] = m_hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
+            }
+        }
+
+        /* ---- the chunk's survivors, NG at a time ------------------------------------------------ */
+        uint32_t todo = __ballot_sync(DSIM_FULL, my_alive);
+        while (todo) {
+            /* group g takes the g-th remaining survivor */
+            int myj = -1;
+#pragma unroll
+            for (uint32_t g = 0; g < NG; ++g) {
+                int j = -1;
+                if (todo) {
+                    j = __ffs((int)todo) - 1;
+                    todo &= todo - 1u;
+                }
+                if (g == grp) myj = j;
+            }
+            const bool on = myj >= 0;
+            const int src = on ? myj : 0;
+            const uint64_t fid = __shfl_sync(DSIM_FULL, m_id, src);
+            const uint64_t culture = __shfl_sync(DSIM_FULL, m_culture, src);
+            double stored = __shfl_sync(DSIM_FULL, m_stored, src);
+            const double last_harvest = __shfl_sync(DSIM_FULL, m_lh, src);
+            const uint32_t loc = __shfl_sync(DSIM_FULL, m_loc, src);
+            uint32_t size = __shfl_sync(DSIM_FULL, m_size, src);
+            const uint32_t hs = __shfl_sync(DSIM_FULL, m_hs, src);
+            const uint32_t r_start = __shfl_sync(DSIM_FULL, m_start, src);
+            const uint32_t r_len = __shfl_sync(DSIM_FULL, m_len, src);
+            const uint32_t r_nsensed = __shfl_sync(DSIM_FULL, m_nsensed, src);
+            const uint32_t n_near = __shfl_sync(DSIM_FULL, m_nnear, src);
+            const uint32_t hist_cnt = __shfl_sync(DSIM_FULL, m_hist_cnt, src);
+            const uint32_t newpos = __shfl_sync(DSIM_FULL, my_newpos, src);
+            const uint32_t crank = __shfl_sync(DSIM_FULL, my_crank, src);
+            const uint32_t misc_in = __shfl_sync(DSIM_FULL, m_misc, src);
+            const uint32_t till_adult = __shfl_sync(DSIM_FULL, m_till_adult, src);
+            const uint32_t till_mut = __shfl_sync(DSIM_FULL, m_till_mut, src);
+            const bool split = on && ((split_mask >> src) & 1u) != 0u;
+
+            const Row row = stage_row<STAGED>(a.rt, on, r_start, r_len, r_nsensed, gs, leader);
+
+            /* ---- decide_on_moving, lib.rs:830-889 -------------------------------------------- */
+            Choice ch;
+            ch.target = loc;
+            ch.max_gain = 0.0;
+            ch.t_cost = 0.0;
+            ch.m = 0.0;
+            /* sensed patches: the leading entries of the row, in ascending node order; their noise index
+             * is their position in the 2-hop list.  MOVE_ROUND per round: a lane holds KP entries G apart,
+             * and gathers all their views before using any. */
+            for (uint32_t base = 0; __any_sync(DSIM_FULL, on && base < row.n_sensed); base += MOVE_ROUND) {
+                uint32_t q[KP];
+                PatchView pv[KP];
+                bool ok[KP];
+#pragma unroll
+                for (uint32_t k = 0; k < KP; ++k) {
+                    const uint32_t e = base + k * (uint32_t)G + ln.gl;
+                    ok[k] = on && e < row.n_sensed;
+                    q[k] = 0;
+                    if (ok[k]) {
+                        q[k] = row.dst[e];
+                        pv[k] = a.ps.view[q[k]];
+                    }
+                }
+                double gain[KP], cost[KP], u[KP];
+                uint32_t ni[KP];
+#pragma unroll
+                for (uint32_t k = 0; k < KP; ++k) {
+                    const uint32_t e = base + k * (uint32_t)G + ln.gl;
+                    gain[k] = 0.0;
+                    cost[k] = 0.0;
+                    ni[k] = 0;
+                    u[k] = 0.0;
+                    if (ok[k]) {
+                        ni[k] = row.nidx[e];
+                        cost[k] = row.cost[e];
+                        gain[k] = view_quality(a, pv[k], culture, size, q[k] == loc);
+                    }
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < KP; ++k)
+                    if (ok[k]) u[k] = noise_draw(a.mc, step, fid, ni[k]);
+#pragma unroll
+                for (uint32_t k = 0; k < KP; ++k) {
+                    const uint32_t e = k * (uint32_t)G + ln.gl;
+                    if (ok[k]) {
+                        gs.c_g[e] = gain[k] * u[k] - cost[k];
+                        gs.c_gain[e] = gain[k];
+                        gs.c_cost[e] = cost[k];
+                        gs.c_q[e] = q[k];
+                    }
+                }
+                __syncwarp();
+                const uint32_t left = (on && base < row.n_sensed) ? row.n_sensed - base : 0u;
+                accept_round<G>(ln, gs, on, left < MOVE_ROUND ? left : MOVE_ROUND, ch);
+                __syncwarp();
+            }
+            const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
+            const uint32_t nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
+            HistSource hsrc;
+            hsrc.hs = hs;
+            hsrc.ring_cnt = hist_cnt;
+            hsrc.virt = false;
+            hsrc.v0_patch = 0u;
+            hsrc.v0_harv = 0.0;
+            history_pass<G>(a, ln, gs, step, on, fid, row, n_near, on ? nh : 0u, hsrc, thr, ch);
+
+            /* ---- move bookkeeping, lib.rs:1826-1833 ------------------------------------------ */
+            const double harv0 = last_harvest / (double)size; /* pushed to the history */
+            stored = stored + last_harvest;
+            const uint32_t newloc = ch.target;
+            stored = stored - ch.t_cost;
+            uint32_t misc = misc_in;
+
+            /* ---- maybe_procreate + the child's move, lib.rs:1840-1855, 1869-1897 --------------- */
+            if (__any_sync(DSIM_FULL, split)) {
+                const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
+                double take = 0.0;
+                if (split) {
+                    misc = (misc & ~0xFFFFu) | n_off;
+                    take = stored * 2.0 / (double)size;
+                    stored = stored - take;
+                    size -= 2u;
+                }
+                uint64_t cid = 0;
+                uint32_t cpos = 0, chs = 0;
+                RowHdr chd;
+                chd.start = chd.len = chd.n_sensed = chd.n_near = 0u;
+                uint32_t nl0 = 0, nl1 = 0;
+                if (split) {
+                    cid = ctl->child_id_base + crank;
+                    cpos = ctl->child_pos_base + crank;
+                    const uint32_t ft = ctl->free_top;
+                    chs = (crank < ft) ? a.sc.free_hs[ft - 1u - crank] : ctl->hs_hwm + (crank - ft);
+                    chd = a.rt.hdr[newloc];
+                    nl0 = a.rt.near_off[loc];
+                    nl1 = a.rt.near_off[loc + 1];
+                }
+                Choice cc;
+                cc.target = newloc;
+                cc.max_gain = 0.0;
+                cc.t_cost = 0.0;
+                cc.m = 0.0;
+                /* the parent's row is no longer needed: reuse the buffers for the child's row */
+                __syncwarp();
+                const Row crow = stage_row<STAGED>(a.rt, split, chd.start, chd.len, chd.n_sensed, gs, leader);
+                /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
+                const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
+                for (uint32_t base = first; __any_sync(DSIM_FULL, split && base < nl1); base += MOVE_ROUND) {
+#pragma unroll
+                    for (uint32_t k = 0; k < KP; ++k) {
+                        const uint32_t e = k * (uint32_t)G + ln.gl;
+                        const uint32_t jj = base + e;
+                        if (split && jj < nl1) {
+                            const uint32_t q = a.rt.near_dst[jj];
+                            double cost = 0.0, gain = 0.0, g = DSIM_NEG_INF;
+                            if (reach_lookup(crow, q, &cost)) {
+                                gain = view_quality(a, a.ps.view[q], culture, 2u, q == newloc);
+                                g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
+                            }
+                            gs.c_g[e] = g;
+                            gs.c_gain[e] = gain;
+                            gs.c_cost[e] = cost;
+                            gs.c_q[e] = q;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t left = (split && base < nl1) ? nl1 - base : 0u;
+                    accept_round<G>(ln, gs, split, left < MOVE_ROUND ? left : MOVE_ROUND, cc);
+                    __syncwarp();
+                }
+                /* child history = newest min(len, time_to_grow_adult) entries incl. the one just pushed */
+                uint32_t child_len = hist_valid + 1u;
+                if (child_len > a.mc.adult_reset) child_len = a.mc.adult_reset;
+                if (child_len > hcap) child_len = hcap;
+                const uint32_t nhc = child_len < a.mc.n_mem ? child_len : a.mc.n_mem;
+                HistSource csrc;
+                csrc.hs = hs;
+                csrc.ring_cnt = hist_cnt;
+                csrc.virt = true;
+                csrc.v0_patch = loc;
+                csrc.v0_harv = harv0;
+                history_pass<G>(a, ln, gs, step, split, cid, crow, nl1 - first, split ? nhc : 0u, csrc, thr, cc);
+
+                if (split) {
+                    if (cpos < cap && chs < ctl->hs_cap) {
+                        const size_t pb = (size_t)hs * hcap, cb = (size_t)chs * hcap;
+                        for (uint32_t k = ln.gl; k < child_len; k += (uint32_t)G) { /* chronological index k */
+                            const uint32_t nn = child_len - 1u - k;                /* newest-first index      */
+                            uint32_t hp;
+                            double hh;
+                            if (nn == 0u) {
+                                hp = loc;
+                                hh = harv0;
+                            } else {
+                                const uint32_t pos = (hist_cnt - 1u - (nn - 1u)) % hcap;
+                                hp = a.hv.hist_patch[pb + pos];
+                                hh = a.hv.hist_harv[pb + pos];
+                            }
+                            a.hv.hist_patch[cb + k] = hp;
+                            a.hv.hist_harv[cb + k] = hh;
+                        }
+                        for (uint32_t k = ln.gl; k < acap; k += (uint32_t)G) { /* adaptation: family.adaptation, lib.rs:1893 */
+                            a.hv.a_eco[(size_t)chs * acap + k] = a.hv.a_eco[(size_t)hs * acap + k];
+                            a.hv.a_cnt[(size_t)chs * acap + k] = a.hv.a_cnt[(size_t)hs * acap + k];
+                            a.hv.a_val[(size_t)chs * acap + k] = a.hv.a_val[(size_t)hs * acap + k];
+                        }
+                        if (leader) {
+                            a.hv.hist_cnt[chs] = child_len;
+                            a.hv.decay[chs] = a.hv.decay[hs];
+                            a.hv.parent[chs] = fid;
+                            a.hv.birth_index[chs] = (uint16_t)n_off;
+                            a.next.id[cpos] = cid;
+                            a.next.culture[cpos] = culture;
+                            a.next.stored[cpos] = take - cc.t_cost; /* descendant.stored_resources -= cost */
+                            a.next.last_harvest[cpos] = 0.0;
+                            a.next.loc[cpos] = cc.target;
+                            a.next.size[cpos] = 2u;
+                            a.next.till_adult[cpos] = a.mc.adult_reset;
+                            a.next.till_mut[cpos] = 0u;
+                            a.next.misc[cpos] = 0u;
+                            a.next.hs[cpos] = chs;
+                            const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
+                            if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = cc.target;
+                            a.sc.fslot[cpos] = slot;
+                        }
+                    } else if (leader) {
+                        atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+                    }
+                }
+            }
+            /* every lane of the group has read the family's history by now (the child copied it above):
+             * the leader pushes the new entry and stores the compacted record */
+            __syncwarp();
+            if (on && leader) {
+                /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
+                const uint32_t pos = hist_cnt % hcap;
+                a.hv.hist_patch[(size_t)hs * hcap + pos] = loc;
+                a.hv.hist_harv[(size_t)hs * hcap + pos] = harv0;
+                a.hv.hist_cnt[hs] = hist_cnt + 1u;
+                a.next.id[newpos] = fid;
+                a.next.culture[newpos] = culture;
+                a.next.stored[newpos] = stored;
+                a.next.last_harvest[newpos] = 0.0;
+                a.next.loc[newpos] = newloc;
+                a.next.size[newpos] = size;
+                a.next.till_adult[newpos] = till_adult;
+                a.next.till_mut[newpos] = till_mut;
+                a.next.misc[newpos] = misc;
+                a.next.hs[newpos] = hs;
+                const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
+                if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = newloc;
+                a.sc.fslot[newpos] = slot;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * part 1c (default): move, one THREAD per family.
+ *
+ * Measured on B200 (profiles/): with one warp — or a group of 8/16 lanes — per family the kernel is
+ * bound by the latency of its own instruction stream (shuffles, ballots, shared-memory round trips,
+ * work replicated in every lane) long before HBM; 32 independent families per warp need ~half the
+ * warp-instructions per family and no collectives at all.  Lane L of a warp owns family 32c+L, so the
+ * 56-byte records are still read and written coalesced; a family's reach row is a contiguous,
+ * 16-byte-aligned run that its thread streams with 8/16-byte loads (every sector is used in full).
+ * Families that split leave a ChildTask; k_children moves the children afterwards.
+ * ------------------------------------------------------------------------------------------ */
+#ifndef TPF_THREADS
+#define TPF_THREADS 128
+#endif
+#ifndef TPF_MIN_BLOCKS
+#define TPF_MIN_BLOCKS 4
+#endif
+#define TPF_KEPT 32 /* kept history entries buffered per thread before they are evaluated */
+
+struct RowPtr { /* a reach row in place (HBM / L1) */
+    const uint32_t *dst;
+    const double *cost;
+    const uint16_t *nidx;
+    const uint8_t *hash; /* the row's 256-slot index, or nullptr for rows longer than DSIM_ROW_HASH_MAX */
+    uint32_t len, n_sensed;
+};
+
+__device__ __forceinline__ RowPtr row_of(const ReachTable &rt, uint32_t node, const RowHdr &hd) {
+    RowPtr row;
+    row.dst = rt.dst + hd.start;
+    row.cost = rt.cost + hd.start;
+    row.nidx = rt.nidx + hd.start;
+    row.hash = hd.len <= DSIM_ROW_HASH_MAX ? rt.hash + (size_t)node * 256u : nullptr;
+    row.len = hd.len;
+    row.n_sensed = hd.n_sensed;
+    return row;
+}
+
+__device__ __forceinline__ uint32_t row_hash_slot(uint32_t q) { return (q * 2654435761u) >> 24; }
+
+/* position of node q in the row, or 0xFFFFFFFF (replaces travel_costs.get(), lib.rs:869) */
+__device__ __forceinline__ uint32_t row_find(const RowPtr &row, uint32_t q) {
+    if (row.hash != nullptr) {
+        uint32_t h = row_hash_slot(q);
+        for (;;) {
+            const uint32_t k = row.hash[h];
+            if (k == 0xFFu) return 0xFFFFFFFFu;
+            if (row.dst[k] == q) return k;
+            h = (h + 1u) & 255u;
+        }
+    }
+    uint32_t k = lower_bound_u32(row.dst, 0u, row.n_sensed, q);
+    if (k < row.n_sensed && row.dst[k] == q) return k;
+    k = lower_bound_u32(row.dst, row.n_sensed, row.len, q);
+    if (k < row.len && row.dst[k] == q) return k;
+    return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ void accept_one(Choice &ch, double g, double gain, double cost, uint32_t q) {
+    if (g > ch.m) { /* lib.rs:921-926 */
+        ch.target = q;
+        ch.max_gain = dsim_oyr_max(ch.max_gain, gain);
+        ch.t_cost = cost;
+        ch.m = ch.max_gain - ch.t_cost;
+    }
+}
+
+/* evaluate the buffered kept history entries kept[0..cnt) (ascending n) as candidates.  The memory
+ * accesses are issued stage by stage for all entries (ring entry -> hash slot -> row entry -> cost),
+ * so the dependent round trips are paid once per stage, not once per entry. */
+__device__ __forceinline__ void tpf_flush(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
+                                          uint32_t hs, uint32_t ring_cnt, const uint16_t *kept, uint32_t cnt, Choice &ch) {
+    uint32_t kq[TPF_KEPT], kidx[TPF_KEPT];
+    double kgain[TPF_KEPT], kcost[TPF_KEPT];
+    const size_t hbase = (size_t)hs * a.hv.hcap;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t pos = (ring_cnt - 1u - kept[k]) % a.hv.hcap;
+        kq[k] = a.hv.hist_patch[hbase + pos];
+        kgain[k] = a.hv.hist_harv[hbase + pos];
+    }
+    if (row.hash != nullptr) {
+        for (uint32_t k = 0; k < cnt; ++k) kidx[k] = row.hash[row_hash_slot(kq[k])]; /* first probe of every entry */
+        for (uint32_t k = 0; k < cnt; ++k) {
+            uint32_t idx = kidx[k];
+            if (idx != 0xFFu && row.dst[idx] != kq[k]) idx = row_find(row, kq[k]); /* collision: walk the probe sequence */
+            kidx[k] = idx == 0xFFu ? 0xFFFFFFFFu : idx;
+        }
+    } else {
+        for (uint32_t k = 0; k < cnt; ++k) kidx[k] = row_find(row, kq[k]);
+    }
+    for (uint32_t k = 0; k < cnt; ++k) kcost[k] = kidx[k] != 0xFFFFFFFFu ? row.cost[kidx[k]] : 0.0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        if (kidx[k] == 0xFFFFFFFFu) continue; /* no travel cost from here: lib.rs:869 */
+        const double g = kgain[k] * noise_draw(a.mc, step, fid, n_sensed + kept[k]) - kcost[k];
+        accept_one(ch, g, kgain[k], kcost[k], kq[k]);
+    }
+}
+
+/* The remembered-patch part of decide_on_moving (lib.rs:854-867) for one thread: history entry n is
+ * kept iff its keyed 32-bit draw is <= thr[n] (i.e. draw * 2^-32 < memory_n); kept entries with a
+ * travel cost are candidates whose expected harvest is the remembered per-capita harvest. */
+__device__ __forceinline__ void tpf_history(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
+                                            uint32_t hs, uint32_t ring_cnt, uint32_t nh, const uint32_t *thr, Choice &ch) {
+    uint16_t kept[TPF_KEPT];
+    uint32_t cnt = 0;
+    for (uint32_t n8 = 0; n8 < nh; n8 += 8u) { /* two independent Philox blocks per iteration (entry n: block n>>2, word n&3) */
+        const dsim_u4 o0 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, n8 >> 2);
+        const dsim_u4 o1 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, (n8 >> 2) + 1u);
+#pragma unroll
+        for (uint32_t w = 0; w < 4u; ++w)
+            if (n8 + w < nh && dsim_word(o0, w) <= thr[n8 + w]) kept[cnt++] = (uint16_t)(n8 + w);
+#pragma unroll
+        for (uint32_t w = 0; w < 4u; ++w)
+            if (n8 + 4u + w < nh && dsim_word(o1, w) <= thr[n8 + 4u + w]) kept[cnt++] = (uint16_t)(n8 + 4u + w);
+        if (cnt > TPF_KEPT - 8u) {
+            tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
+            cnt = 0;
+        }
+    }
+    if (cnt) tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
+}
+
+__global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepArgs a) {
+    DSIM_DYN_SMEM(smem_raw);
+    DevCtl *ctl = a.ctl;
+    const uint32_t n = ctl->n_cur[a.parity];
+    const uint32_t step = ctl->t;
+    const uint32_t cap = ctl->cap;
+    const uint32_t hcap = a.hv.hcap;
+    uint32_t *thr = (uint32_t *)smem_raw; /* keep thresholds: read with a warp-uniform index (broadcast) */
+    for (uint32_t k = threadIdx.x; k < a.mc.n_mem; k += blockDim.x) thr[k] = a.mc.mem_thr[k];
+    __syncthreads();
+
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
+        /* ---- ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) ------------------- */
+        const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
+        uint32_t va = 0, vs = 0;
+        for (uint32_t w = c & ~7u; w < c; ++w) { /* warp-uniform addresses */
+            va += (uint32_t)__popc(a.sc.alive_bits[w]);
+            vs += (uint32_t)__popc(a.sc.split_bits[w]);
+        }
+        const uint32_t newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
+        const uint32_t hs = a.cur.hs[i];
+        if (!((alive_mask >> (i & 31u)) & 1u)) { /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
+            a.sc.dead_hs[i - newpos] = hs;
             continue;
         }
         if (newpos >= cap) continue; /* capacity error already flagged by k_control */
+        const bool split = ((split_mask >> (i & 31u)) & 1u) != 0u;
 
+        const uint32_t loc = a.cur.loc[i];
         const uint64_t fid = a.cur.id[i];
         const uint64_t culture = a.cur.culture[i];
         double stored = a.cur.stored[i];
         const double last_harvest = a.cur.last_harvest[i];
-        const uint32_t loc = a.cur.loc[i];
         uint32_t size = a.cur.size[i];
-        const uint32_t till_adult = a.cur.till_adult[i];
-        const uint32_t till_mut = a.cur.till_mut[i];
         uint32_t misc = a.cur.misc[i];
-        const uint32_t hs = a.cur.hs[i];
+        const RowHdr hd = a.rt.hdr[loc];
+        const uint32_t hist_cnt = a.hv.hist_cnt[hs];
+        const RowPtr row = row_of(a.rt, loc, hd);
 
         /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------ */
         Choice ch;
@@ -334,151 +985,221 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(StepArgs a) {
         ch.max_gain = 0.0;
         ch.t_cost = 0.0;
         ch.m = 0.0;
-        const uint32_t r0 = a.rt.off[loc], r1 = a.rt.off[loc + 1];
-        const uint32_t n_near = a.rt.near_off[loc + 1] - a.rt.near_off[loc];
-        /* sensed patches: the entries of the reach row that are in the 2-hop list, in ascending
-         * node order; their noise index is their position in that list */
-        for (uint32_t base = r0; base < r1; base += 32u) {
-            const uint32_t e = base + lane;
-            bool cand = false;
-            double g = 0.0, gain = 0.0, cost = 0.0;
-            uint32_t q = 0;
-            if (e < r1) {
-                const uint32_t nidx = a.rt.nidx[e];
-                if (nidx != DSIM_NIDX_NONE) {
-                    q = a.rt.dst[e];
-                    cost = a.rt.cost[e];
-                    gain = dest_quality(a, q, culture, size, q == loc);
-                    g = gain * noise_draw(a.mc, step, fid, nidx) - cost;
-                    cand = true;
+        /* sensed patches: the leading entries of the row in ascending node order, four per iteration:
+         * the four views are gathered together, the node ids of the next four are requested one
+         * iteration ahead, and entries 2k, 2k+1 share one Philox block when their noise indices do.
+         * Rows are padded to multiples of 8 entries, so the 16-byte loads never leave the row. */
+        {
+            uint4 q_next = make_uint4(0u, 0u, 0u, 0u);
+            if (row.n_sensed > 0u) q_next = *reinterpret_cast<const uint4 *>(row.dst);
+            for (uint32_t e = 0; e < row.n_sensed; e += 4u) {
+                const uint4 q4 = q_next;
+                const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
+                const uint32_t m = row.n_sensed - e < 4u ? row.n_sensed - e : 4u;
+                PatchView pv[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; ++k)
+                    if (k < m) pv[k] = a.ps.view[q[k]];
+                if (e + 4u < row.n_sensed) q_next = *reinterpret_cast<const uint4 *>(row.dst + e + 4u);
+                const double2 c01 = *reinterpret_cast<const double2 *>(row.cost + e);
+                const double2 c23 = *reinterpret_cast<const double2 *>(row.cost + e + 2u);
+                const uint2 nn = *reinterpret_cast<const uint2 *>(row.nidx + e);
+                const double cost[4] = {c01.x, c01.y, c23.x, c23.y};
+                const uint32_t ni[4] = {nn.x & 0xFFFFu, nn.x >> 16, nn.y & 0xFFFFu, nn.y >> 16};
+                double u[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; k += 2u) {
+                    if (k < m) {
+                        const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, noise_block(ni[k]));
+                        u[k] = noise_pick(o, ni[k]);
+                        if (k + 1u < m)
+                            u[k + 1] = (noise_block(ni[k + 1]) == noise_block(ni[k])) ? noise_pick(o, ni[k + 1])
+                                                                                       : noise_draw(a.mc, step, fid, ni[k + 1]);
+                    }
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; ++k) {
+                    if (k < m) {
+                        const double gain = view_quality(a, pv[k], culture, size, q[k] == loc);
+                        accept_one(ch, gain * u[k] - cost[k], gain, cost[k], q[k]);
+                    }
                 }
             }
-            accept_scan(ch, cand, g, gain, cost, q, lane);
         }
-        const uint32_t hist_cnt = a.hv.hist_cnt[hs];
         const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
         const uint32_t nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
-        history_pass(a, step, lane, fid, r0, r1, n_near, hs, hist_cnt, nh, false, 0u, 0.0, ch);
+        tpf_history(a, step, fid, row, hd.n_near, hs, hist_cnt, nh, thr, ch);
 
         /* ---- move bookkeeping, lib.rs:1826-1833 ---------------------------------------------- */
-        const double harv0 = last_harvest / (double)size; /* pushed to the history */
+        const double harv0 = last_harvest / (double)size;
         stored = stored + last_harvest;
         const uint32_t newloc = ch.target;
         stored = stored - ch.t_cost;
-
-        /* ---- maybe_procreate + the child's move, lib.rs:1840-1855, 1869-1897 ------------------- */
-        if (split) {
-            uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
-            misc = (misc & ~0xFFFFu) | n_off;
-            const double take = stored * 2.0 / (double)size;
-            stored = stored - take;
-            size -= 2u;
-            const uint64_t cid = ctl->child_id_base + crank;
-            const uint32_t cpos = ctl->child_pos_base + crank;
-            const uint32_t ft = ctl->free_top;
-            const uint32_t chs = (crank < ft) ? a.sc.free_hs[ft - 1u - crank] : ctl->hs_hwm + (crank - ft);
-
-            Choice cc;
-            cc.target = newloc;
-            cc.max_gain = 0.0;
-            cc.t_cost = 0.0;
-            cc.m = 0.0;
-            const uint32_t c0 = a.rt.off[newloc], c1 = a.rt.off[newloc + 1];
-            /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
-            const uint32_t nl0 = a.rt.near_off[loc], nl1 = a.rt.near_off[loc + 1];
-            const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
-            for (uint32_t base = first; base < nl1; base += 32u) {
-                const uint32_t j = base + lane;
-                bool cand = false;
-                double g = 0.0, gain = 0.0, cost = 0.0;
-                uint32_t q = 0;
-                if (j < nl1) {
-                    q = a.rt.near_dst[j];
-                    if (reach_lookup(a.rt, c0, c1, q, &cost)) {
-                        gain = dest_quality(a, q, culture, 2u, q == newloc);
-                        g = gain * noise_draw(a.mc, step, cid, j - first) - cost;
-                        cand = true;
-                    }
-                }
-                accept_scan(cc, cand, g, gain, cost, q, lane);
-            }
-            /* child history = newest min(len, time_to_grow_adult) entries incl. the one just pushed */
-            uint32_t child_len = hist_valid + 1u;
-            if (child_len > a.mc.adult_reset) child_len = a.mc.adult_reset;
-            if (child_len > hcap) child_len = hcap;
-            const uint32_t nhc = child_len < a.mc.n_mem ? child_len : a.mc.n_mem;
-            history_pass(a, step, lane, cid, c0, c1, nl1 - first, hs, hist_cnt, nhc, true, loc, harv0, cc);
-
-            if (cpos < cap && chs < ctl->hs_cap) {
-                const size_t pb = (size_t)hs * hcap, cb = (size_t)chs * hcap;
-                for (uint32_t k = lane; k < child_len; k += 32u) { /* chronological index k */
-                    const uint32_t nn = child_len - 1u - k;        /* newest-first index      */
-                    uint32_t hp;
-                    double hh;
-                    if (nn == 0u) {
-                        hp = loc;
-                        hh = harv0;
-                    } else {
-                        const uint32_t pos = (hist_cnt - 1u - (nn - 1u)) % hcap;
-                        hp = a.hv.hist_patch[pb + pos];
-                        hh = a.hv.hist_harv[pb + pos];
-                    }
-                    a.hv.hist_patch[cb + k] = hp;
-                    a.hv.hist_harv[cb + k] = hh;
-                }
-                for (uint32_t k = lane; k < acap; k += 32u) { /* adaptation: family.adaptation, lib.rs:1893 */
-                    a.hv.a_eco[(size_t)chs * acap + k] = a.hv.a_eco[(size_t)hs * acap + k];
-                    a.hv.a_cnt[(size_t)chs * acap + k] = a.hv.a_cnt[(size_t)hs * acap + k];
-                    a.hv.a_val[(size_t)chs * acap + k] = a.hv.a_val[(size_t)hs * acap + k];
-                }
-                if (lane == 0) {
-                    a.hv.hist_cnt[chs] = child_len;
-                    a.hv.decay[chs] = a.hv.decay[hs];
-                    a.hv.parent[chs] = fid;
-                    a.hv.birth_index[chs] = (uint16_t)n_off;
-                    a.next.id[cpos] = cid;
-                    a.next.culture[cpos] = culture;
-                    a.next.stored[cpos] = take - cc.t_cost; /* descendant.stored_resources -= cost */
-                    a.next.last_harvest[cpos] = 0.0;
-                    a.next.loc[cpos] = cc.target;
-                    a.next.size[cpos] = 2u;
-                    a.next.till_adult[cpos] = a.mc.adult_reset;
-                    a.next.till_mut[cpos] = 0u;
-                    a.next.misc[cpos] = 0u;
-                    a.next.hs[cpos] = chs;
-                    const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
-                    if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = cc.target;
-                    a.sc.fslot[cpos] = slot;
-                }
-            } else if (lane == 0) {
-                atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
-            }
-            __syncwarp();
-        }
-
-        /* every lane has read the family's record and history by now; without this barrier lane 0
-         * could bump hist_cnt / overwrite the oldest ring entry under a slower lane */
-        __syncwarp();
-        if (lane == 0) {
+        {
             /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
             const uint32_t pos = hist_cnt % hcap;
             a.hv.hist_patch[(size_t)hs * hcap + pos] = loc;
             a.hv.hist_harv[(size_t)hs * hcap + pos] = harv0;
             a.hv.hist_cnt[hs] = hist_cnt + 1u;
-            a.next.id[newpos] = fid;
-            a.next.culture[newpos] = culture;
-            a.next.stored[newpos] = stored;
-            a.next.last_harvest[newpos] = 0.0;
-            a.next.loc[newpos] = newloc;
-            a.next.size[newpos] = size;
-            a.next.till_adult[newpos] = till_adult;
-            a.next.till_mut[newpos] = till_mut;
-            a.next.misc[newpos] = misc;
-            a.next.hs[newpos] = hs;
-            const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-            if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = newloc;
-            a.sc.fslot[newpos] = slot;
         }
+        /* ---- maybe_procreate, lib.rs:1869-1897: the child moves in k_children ------------------- */
+        if (split) {
+            const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
+            const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
+            misc = (misc & ~0xFFFFu) | n_off;
+            const double take = stored * 2.0 / (double)size;
+            stored = stored - take;
+            size -= 2u;
+            ChildTask t;
+            t.parent_id = fid;
+            t.culture = culture;
+            t.take = take;
+            t.old_loc = loc;
+            t.new_loc = newloc;
+            t.parent_hs = hs;
+            t.hist_cnt = hist_cnt + 1u;
+            t.n_off = n_off;
+            t.pad_ = 0u;
+            a.sc.child_task[crank] = t;
+        }
+        a.next.id[newpos] = fid;
+        a.next.culture[newpos] = culture;
+        a.next.stored[newpos] = stored;
+        a.next.last_harvest[newpos] = 0.0;
+        a.next.loc[newpos] = newloc;
+        a.next.size[newpos] = size;
+        a.next.till_adult[newpos] = a.cur.till_adult[i];
+        a.next.till_mut[newpos] = a.cur.till_mut[i];
+        a.next.misc[newpos] = misc;
+        a.next.hs[newpos] = hs;
+        const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
+        if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = newloc;
+        a.sc.fslot[newpos] = slot;
+    }
+}
+
+/* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in
+ * lane order: a candidate is accepted iff g > m with m as left by the previous acceptance. */
+__device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double g, double gain, double cost, uint32_t q,
+                                                 uint32_t lane) {
+    uint32_t cursor = 0;
+    for (;;) {
+        const uint32_t mask = __ballot_sync(DSIM_FULL, valid && lane >= cursor && g > ch.m);
+        if (mask == 0u) break;
+        const int L = __ffs((int)mask) - 1;
+        ch.target = __shfl_sync(DSIM_FULL, q, L);
+        ch.max_gain = dsim_oyr_max(ch.max_gain, __shfl_sync(DSIM_FULL, gain, L));
+        ch.t_cost = __shfl_sync(DSIM_FULL, cost, L);
+        ch.m = ch.max_gain - ch.t_cost;
+        cursor = (uint32_t)L + 1u;
+    }
+}
+
+/* part 1d: the children of this step (lib.rs:1840-1855, 1877-1895), one WARP per child: there are few
+ * of them (about 1 % of the families), so the kernel is latency-bound and the candidates are spread
+ * over the lanes. */
+__global__ void __launch_bounds__(128) k_children(StepArgs a) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t step = ctl->t;
+    const uint32_t n_children = a.children_inline ? 0u : ctl->n_children;
+    const uint32_t cap = ctl->cap;
+    const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+
+    for (uint32_t r = gwarp; r < n_children; r += nwarps) {
+        const ChildTask t = a.sc.child_task[r];
+        const uint64_t cid = ctl->child_id_base + r;
+        const uint32_t cpos = ctl->child_pos_base + r;
+        const uint32_t ft = ctl->free_top;
+        const uint32_t chs = (r < ft) ? a.sc.free_hs[ft - 1u - r] : ctl->hs_hwm + (r - ft);
+        if (cpos >= cap || chs >= ctl->hs_cap) {
+            if (lane == 0) atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+            continue;
+        }
+        const RowHdr hd = a.rt.hdr[t.new_loc];
+        const RowPtr row = row_of(a.rt, t.new_loc, hd);
+        Choice cc;
+        cc.target = t.new_loc;
+        cc.max_gain = 0.0;
+        cc.t_cost = 0.0;
+        cc.m = 0.0;
+        /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
+        const uint32_t nl0 = a.rt.near_off[t.old_loc], nl1 = a.rt.near_off[t.old_loc + 1];
+        const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
+        for (uint32_t base = first; base < nl1; base += 32u) {
+            const uint32_t jj = base + lane;
+            bool cand = false;
+            double g = 0.0, gain = 0.0, cost = 0.0;
+            uint32_t q = 0;
+            if (jj < nl1) {
+                q = a.rt.near_dst[jj];
+                const uint32_t k = row_find(row, q);
+                if (k != 0xFFFFFFFFu) {
+                    cost = row.cost[k];
+                    gain = view_quality(a, a.ps.view[q], t.culture, 2u, q == t.new_loc);
+                    g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
+                    cand = true;
+                }
+            }
+            accept_scan_warp(cc, cand, g, gain, cost, q, lane);
+        }
+        /* history = the parent's newest min(len, time_to_grow_adult) entries, the one pushed this step included */
+        const uint32_t valid = t.hist_cnt < hcap ? t.hist_cnt : hcap;
+        const uint32_t child_len = valid < a.mc.adult_reset ? valid : a.mc.adult_reset;
+        const uint32_t nhc = child_len < a.mc.n_mem ? child_len : a.mc.n_mem;
+        const size_t pb = (size_t)t.parent_hs * hcap, cb = (size_t)chs * hcap;
+        for (uint32_t base = 0; base < nhc; base += 32u) {
+            const uint32_t n = base + lane;
+            bool cand = false;
+            double g = 0.0, gain = 0.0, cost = 0.0;
+            uint32_t q = 0;
+            if (n < nhc) {
+                const dsim_u4 o = dsim_draw(stream_of(a.mc), step, cid, DSIM_P_MEM, n >> 2); /* entry n: block n>>2, word n&3 */
+                if (dsim_word(o, n & 3u) <= a.mc.mem_thr[n]) {
+                    const uint32_t pos = (t.hist_cnt - 1u - n) % hcap;
+                    q = a.hv.hist_patch[pb + pos];
+                    gain = a.hv.hist_harv[pb + pos];
+                    const uint32_t k = row_find(row, q);
+                    if (k != 0xFFFFFFFFu) {
+                        cost = row.cost[k];
+                        g = gain * noise_draw(a.mc, step, cid, (nl1 - first) + n) - cost;
+                        cand = true;
+                    }
+                }
+            }
+            accept_scan_warp(cc, cand, g, gain, cost, q, lane);
+        }
+        for (uint32_t k = lane; k < child_len; k += 32u) { /* chronological index k = newest-first index child_len-1-k */
+            const uint32_t pos = (t.hist_cnt - 1u - (child_len - 1u - k)) % hcap;
+            a.hv.hist_patch[cb + k] = a.hv.hist_patch[pb + pos];
+            a.hv.hist_harv[cb + k] = a.hv.hist_harv[pb + pos];
+        }
+        for (uint32_t k = lane; k < acap; k += 32u) { /* adaptation: family.adaptation, lib.rs:1893 */
+            a.hv.a_eco[(size_t)chs * acap + k] = a.hv.a_eco[(size_t)t.parent_hs * acap + k];
+            a.hv.a_cnt[(size_t)chs * acap + k] = a.hv.a_cnt[(size_t)t.parent_hs * acap + k];
+            a.hv.a_val[(size_t)chs * acap + k] = a.hv.a_val[(size_t)t.parent_hs * acap + k];
+        }
+        if (lane == 0) {
+            a.hv.hist_cnt[chs] = child_len;
+            a.hv.decay[chs] = a.hv.decay[t.parent_hs];
+            a.hv.parent[chs] = t.parent_id;
+            a.hv.birth_index[chs] = (uint16_t)t.n_off;
+            a.next.id[cpos] = cid;
+            a.next.culture[cpos] = t.culture;
+            a.next.stored[cpos] = t.take - cc.t_cost; /* descendant.stored_resources -= cost */
+            a.next.last_harvest[cpos] = 0.0;
+            a.next.loc[cpos] = cc.target;
+            a.next.size[cpos] = 2u;
+            a.next.till_adult[cpos] = a.mc.adult_reset;
+            a.next.till_mut[cpos] = 0u;
+            a.next.misc[cpos] = 0u;
+            a.next.hs[cpos] = chs;
+            const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
+            if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = cc.target;
+            a.sc.fslot[cpos] = slot;
+        }
+        __syncwarp();
     }
 }
 
@@ -491,7 +1212,13 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
     const uint32_t n_occ = ctl->n_occ[a.parity];
     for (uint32_t k = tid; k < n_occ; k += nth) {
         const uint32_t p = a.sc.occ[a.parity][k];
-        a.ps.seg[p] = atomicAdd(&ctl->seg_cursor, a.ps.cnt[p]);
+        const uint32_t c = a.ps.cnt[p];
+        a.ps.seg[p] = atomicAdd(&ctl->seg_cursor, c);
+        /* sparsely occupied nodes go to the thread-per-node kernel, crowded ones to the warp-per-node kernel */
+        if (c <= a.small_max)
+            a.sc.plist_small[atomicAdd(&ctl->n_small, 1u)] = p;
+        else
+            a.sc.plist_big[atomicAdd(&ctl->n_big, 1u)] = p;
     }
     /* heavy slots vacated this step go onto the free stack, above what the children did not pop */
     const uint32_t ft = ctl->free_top, births = ctl->n_children, dead = ctl->n_dead;
@@ -582,14 +1309,13 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
     const uint32_t step = ctl->t;
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t gwarp = blockIdx.x * PATCH_WARPS + wib, nwarps = gridDim.x * PATCH_WARPS;
-    const uint32_t n_occ = ctl->n_occ[a.parity];
+    const uint32_t n_big = ctl->n_big;
     const dsim_stream rs = stream_of(a.mc);
-    const double season = a.mc.season, minimum_unused = a.mc.min_adapt;
-    (void)minimum_unused;
+    const double season = a.mc.season;
     uint32_t errors = 0;
 
-    for (uint32_t vw = gwarp; vw < n_occ; vw += nwarps) {
-        const uint32_t p = a.sc.occ[a.parity][vw];
+    for (uint32_t vw = gwarp; vw < n_big; vw += nwarps) {
+        const uint32_t p = a.sc.plist_big[vw];
         const uint32_t n = a.ps.cnt[p];
         const uint32_t s0 = a.ps.seg[p];
         PatchMem M;
@@ -846,6 +1572,194 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
     if (errors) atomicOr(&ctl->errors, errors);
 }
 
+/* ------------------------------------------------------------------------------------------ *
+ * part 2c': one THREAD per sparsely occupied node (at most PATCH_SMALL_MAX families).
+ * Same rules as k_patch; with one to a handful of families per node (the common case on the
+ * continental grid) a warp per node would leave 30 lanes idle, so 32 nodes share a warp instead.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) k_patch_small(StepArgs a) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t step = ctl->t;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const uint32_t n_small = ctl->n_small;
+    const dsim_stream rs = stream_of(a.mc);
+    const double season = a.mc.season;
+    uint32_t errors = 0;
+
+    for (uint32_t v = tid; v < n_small; v += nth) {
+        const uint32_t p = a.sc.plist_small[v];
+        const uint32_t n = a.ps.cnt[p];
+        const uint32_t s0 = a.ps.seg[p];
+        uint32_t idx[PATCH_SMALL_MAX], size[PATCH_SMALL_MAX], band[PATCH_SMALL_MAX];
+        uint64_t fid[PATCH_SMALL_MAX], key[PATCH_SMALL_MAX], cult[PATCH_SMALL_MAX];
+        double stored[PATCH_SMALL_MAX], contrib[PATCH_SMALL_MAX], lh[PATCH_SMALL_MAX];
+        uint64_t bcult[PATCH_SMALL_MAX];
+        uint32_t btot[PATCH_SMALL_MAX];
+        double beff[PATCH_SMALL_MAX], bcoef[PATCH_SMALL_MAX];
+
+        /* shuffle (lib.rs:1376): insertion sort by (keyed random number, id) */
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t i = a.sc.members[s0 + j];
+            const uint64_t id = a.next.id[i];
+            const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
+            const uint64_t k = ((uint64_t)o.y << 32) | o.x;
+            uint32_t r = j;
+            while (r > 0u && (key[r - 1] > k || (key[r - 1] == k && fid[r - 1] > id))) {
+                key[r] = key[r - 1];
+                fid[r] = fid[r - 1];
+                idx[r] = idx[r - 1];
+                --r;
+            }
+            key[r] = k;
+            fid[r] = id;
+            idx[r] = i;
+        }
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint32_t i = idx[r];
+            cult[r] = a.next.culture[i];
+            size[r] = a.next.size[i];
+            stored[r] = a.next.stored[i];
+        }
+        /* cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 */
+        uint32_t nb = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            int joined = -1;
+            for (uint32_t B = 0; B < nb && joined < 0; ++B) {
+                bool any_hostile = false;
+                for (uint32_t j = 0; j < i; ++j) {
+                    if (band[j] != B || dsim_will_cooperate(cult[i], cult[j], a.mc.threshold, a.mc.inclusive)) continue;
+                    any_hostile = true;
+                    const uint32_t reduction = size[i] < size[j] ? size[i] : size[j];
+                    const dsim_u4 o = dsim_draw(rs, step, fid[i], DSIM_P_FIGHT, j);
+                    if (o.x < a.mc.deadliness) {
+                        size[j] -= reduction;
+                        if (size[j] == 0u) {
+                            stored[i] = stored[i] + stored[j];
+                            stored[j] = 0.0;
+                        }
+                    }
+                    if (o.y < a.mc.deadliness) size[i] -= reduction;
+                }
+                if (!any_hostile) joined = (int)B;
+            }
+            band[i] = joined < 0 ? nb++ : (uint32_t)joined;
+        }
+        /* band culture = culture of a random member; empty bands are dropped, lib.rs:1400-1416 */
+        uint32_t nb_alive = 0;
+        uint64_t cult0 = 0;
+        for (uint32_t B = 0; B < nb; ++B) {
+            uint32_t cnt = 0, tot = 0;
+            for (uint32_t j = 0; j < n; ++j)
+                if (band[j] == B) {
+                    cnt += 1u;
+                    tot += size[j];
+                }
+            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
+            const uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)cnt);
+            uint64_t c = 0;
+            uint32_t seen = 0;
+            for (uint32_t j = 0; j < n; ++j)
+                if (band[j] == B) {
+                    if (seen == pick) {
+                        c = cult[j];
+                        break;
+                    }
+                    ++seen;
+                }
+            bcult[B] = c;
+            btot[B] = tot;
+            if (tot > 0u) { /* storage', lib.rs:622-633 */
+                if (nb_alive == 0u) cult0 = c;
+                a.ps.band_cult[s0 + nb_alive] = c;
+                a.ps.band_size[s0 + nb_alive] = tot;
+                ++nb_alive;
+            }
+        }
+        /* adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 */
+        for (uint32_t r = 0; r < n; ++r) {
+            if (btot[band[r]] == 0u) continue;
+            const uint32_t i = idx[r];
+            uint64_t c = bcult[band[r]];
+            uint32_t misc = a.next.misc[i];
+            uint32_t clock = a.next.till_mut[i];
+            const dsim_u4 o = dsim_draw(rs, step, fid[r], DSIM_P_MUT, 0u);
+            if (!(misc & DSIM_MISC_CLOCK)) {
+                misc |= DSIM_MISC_CLOCK;
+                clock = dsim_time_till_next_mutation(dsim_u53(o.x, o.y), a.mc.log1m_rate);
+            }
+            if (clock == 0u) {
+                c ^= (uint64_t)1 << (o.z >> 26);
+                const dsim_u4 o2 = dsim_draw(rs, step, fid[r], DSIM_P_MUT, 1u);
+                clock = dsim_time_till_next_mutation(dsim_u53(o2.x, o2.y), a.mc.log1m_rate);
+            } else {
+                clock -= 1u;
+            }
+            cult[r] = c;
+            a.next.misc[i] = misc;
+            a.next.till_mut[i] = clock;
+        }
+        /* exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 */
+        const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
+        double quality = 0.0;
+        for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t eco = a.ps.eco_id[e];
+            for (uint32_t B = 0; B < nb; ++B) beff[B] = 0.0;
+            for (uint32_t r = 0; r < n; ++r) {
+                if (btot[band[r]] == 0u) continue;
+                contrib[r] = (double)size[r] * adapt_touch(a, a.next.hs[idx[r]], eco, &errors);
+                beff[band[r]] = beff[band[r]] + contrib[r];
+            }
+            double total_squared = 1.0;
+            for (uint32_t B = 0; B < nb; ++B)
+                if (btot[B] > 0u) total_squared = total_squared + beff[B] * beff[B];
+            double res = a.ps.res[e];
+            const double mx = a.ps.max_res[e];
+            for (uint32_t B = 0; B < nb; ++B) {
+                if (btot[B] == 0u) continue;
+                const double eff = beff[B];
+                if (!(eff > 0.0)) errors |= DSIM_MODEL_EFFORT_NOT_POSITIVE;
+                const double harvest = dsim_oyr_min(res * (eff * eff) / total_squared, a.mc.cap_harvest * season * eff);
+                if (!(harvest > 0.0)) errors |= DSIM_MODEL_HARVEST_NOT_POSITIVE;
+                const double coefficient = dsim_oyr_min(harvest / eff, 2.5);
+                if (!(coefficient > 0.0)) errors |= DSIM_MODEL_COEFF_NOT_POSITIVE;
+                bcoef[B] = coefficient;
+                res = res - coefficient * eff;
+                if (!(res >= 0.0)) errors |= DSIM_MODEL_RESOURCES_NEGATIVE;
+            }
+            for (uint32_t r = 0; r < n; ++r)
+                if (btot[band[r]] > 0u) lh[r] = bcoef[band[r]] * season * contrib[r];
+            if (res < mx) {
+                const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_REGROW, e - e0);
+                res = dsim_oyr_min(mx, mx * a.mc.recovery * (2.0 * dsim_u53(o.x, o.y)) + res);
+            }
+            a.ps.res[e] = res;
+            quality = quality + (res + mx * a.mc.recovery);
+        }
+        /* write back */
+        uint32_t pop = 0;
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint32_t i = idx[r];
+            a.next.size[i] = size[r];
+            a.next.stored[i] = stored[r];
+            if (btot[band[r]] > 0u) {
+                a.next.culture[i] = cult[r];
+                if (e1 > e0) a.next.last_harvest[i] = lh[r];
+            }
+            pop += size[r];
+        }
+        PatchView pv;
+        pv.quality = quality;
+        pv.pop = pop;
+        pv.nb = nb_alive;
+        pv.cult0 = cult0;
+        pv.stor_off = s0;
+        pv.pad_ = 0;
+        a.ps.view[p] = pv;
+        a.ps.cnt[p] = 0u;
+    }
+    if (errors) atomicOr(&ctl->errors, errors);
+}
+
 __global__ void k_advance(StepArgs a) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     DevCtl *ctl = a.ctl;
@@ -902,10 +1816,28 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     switch (which) {
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
     case DSIM_K_CONTROL: DSIM_LAUNCH(k_control, 1, CTL_THREADS, 0, s, a); break;
-    case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, 8), MOVE_THREADS, 0, s, a); break;
+    case DSIM_K_MOVE: {
+        if (!a.children_inline) { /* default: one thread per family */
+            DSIM_LAUNCH(k_move_tpf, grid_for(g, 2 * TPF_MIN_BLOCKS), TPF_THREADS, move_smem_table(a.mc.n_mem), s, a);
+            break;
+        }
+        /* cooperative variant: rows up to g.row_cap entries are staged in shared memory by TMA; longer
+         * rows (or g.row_cap == 0) are read in place */
+        const uint32_t groups = (MOVE_THREADS / 32) * (32 / MOVE_GROUP);
+        if (g.row_cap > 0u) {
+            const uint32_t smem = move_smem_table(a.mc.n_mem) + groups * move_smem_per_group(g.row_cap);
+            DSIM_LAUNCH((k_move<true, MOVE_GROUP>), grid_for(g, g.move_blocks_per_sm), MOVE_THREADS, smem, s, a, g.row_cap);
+        } else {
+            const uint32_t smem = move_smem_table(a.mc.n_mem) + groups * move_smem_per_group(0u);
+            DSIM_LAUNCH((k_move<false, MOVE_GROUP>), grid_for(g, 4), MOVE_THREADS, smem, s, a, 0u);
+        }
+        break;
+    }
+    case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
-    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, 8), PATCH_WARPS * 32, 0, s, a); break;
+    case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 4), 128, 0, s, a); break;
+    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, 4), PATCH_WARPS * 32, 0, s, a); break;
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;
     }
@@ -920,4 +1852,33 @@ void dsim_launch_census(const PatchState &ps, const FamCore &f, uint32_t n, uint
     DSIM_LAUNCH(k_clear_census, grid_for(g, 4), 256, 0, s, ps, n_nodes);
     DSIM_LAUNCH(k_census, grid_for(g, 4), 256, 0, s, ps, f, n, occ, ctl, parity);
     DSIM_LAUNCH(k_reset_cnt, grid_for(g, 4), 256, 0, s, ps, (const uint32_t *)occ, (const DevCtl *)ctl, parity);
+}
+
+int dsim_configure_kernels(LaunchGeom *g, uint32_t max_row, uint32_t n_mem) {
+    /* shared-memory budget of k_move: keep-threshold table + one row buffer, candidate round and ring
+     * per group; stage rows when at least one block fits on an SM */
+    g->row_cap = 0u;
+    g->move_blocks_per_sm = 4u;
+    const uint32_t row_cap = (max_row + 7u) & ~7u;
+    const uint32_t groups = (MOVE_THREADS / 32) * (32 / MOVE_GROUP);
+    uint32_t smem = move_smem_table(n_mem) + groups * move_smem_per_group(0u);
+    if (row_cap != 0u && !g->force_global_rows) {
+        const uint32_t staged = move_smem_table(n_mem) + groups * move_smem_per_group(row_cap);
+        if (staged <= 200u * 1024u) {
+            smem = staged;
+            g->row_cap = row_cap;
+        }
+    }
+#if !defined(DSIM_EMU)
+    if (smem > 48u * 1024u) {
+        cudaError_t e = g->row_cap ? cudaFuncSetAttribute(k_move<true, MOVE_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(k_move<false, MOVE_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+#endif
+    uint32_t per_sm = (220u * 1024u) / (smem + 1024u);
+    if (per_sm > 8u) per_sm = 8u;
+    if (per_sm < 1u) per_sm = 1u;
+    g->move_blocks_per_sm = per_sm;
+    return 0;
 }

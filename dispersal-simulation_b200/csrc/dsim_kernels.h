@@ -17,25 +17,35 @@ struct StepArgs {
     DevCtl *ctl;
     ModelConst mc;
     uint32_t parity;   /* index of `cur` (0/1); also selects occ[parity] / n_occ[parity] */
+    uint32_t children_inline; /* 1: the (cooperative) move kernel also moves the children; 0: k_children does */
+    uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
 };
 
 struct LaunchGeom {
-    uint32_t n_sm; /* grids are multiples of the SM count (148 on B200); kernels are grid-stride */
+    uint32_t n_sm;               /* grids are multiples of the SM count (148 on B200); kernels are grid-stride */
+    uint32_t row_cap;            /* reach-row capacity of k_move's shared-memory staging; 0 = read rows in place */
+    uint32_t move_blocks_per_sm;
+    uint32_t force_global_rows;  /* test knob: never stage */
 };
+
+/* choose the k_move variant for a reach table whose longest (padded) row has max_row entries */
+int dsim_configure_kernels(LaunchGeom *g, uint32_t max_row, uint32_t n_mem);
 
 enum {
     DSIM_K_LIFECYCLE = 0,
     DSIM_K_CONTROL,
     DSIM_K_MOVE,
+    DSIM_K_CHILDREN,
     DSIM_K_SEGMENTS,
     DSIM_K_SCATTER,
+    DSIM_K_PATCH_SMALL,
     DSIM_K_PATCH,
     DSIM_K_ADVANCE,
     DSIM_K_COUNT
 };
 
-static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_control", "k_move",  "k_segments",
-                                                            "k_scatter",   "k_patch",   "k_advance"};
+static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_control", "k_move",  "k_children", "k_segments",
+                                                            "k_scatter",   "k_patch_small", "k_patch", "k_advance"};
 
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s);
 void dsim_launch_init_views(const PatchState &ps, uint32_t n_nodes, double recovery, const LaunchGeom &g, cudaStream_t s);

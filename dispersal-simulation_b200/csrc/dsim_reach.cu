@@ -124,7 +124,7 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
     const uint32_t kChunk = 2048;
     const uint32_t n_chunks = (n + kChunk - 1) / kChunk;
     struct Chunk {
-        std::vector<uint32_t> r_len, n_len, r_dst, n_dst;
+        std::vector<uint32_t> r_len, n_len, r_dst, n_dst, r_sensed;
         std::vector<double> r_cost;
         std::vector<uint16_t> r_nidx;
     };
@@ -150,12 +150,19 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
                 ch.r_len.push_back((uint32_t)row.size());
                 ch.n_len.push_back((uint32_t)near.size());
                 for (uint32_t q : near) ch.n_dst.push_back(q);
-                for (const auto &qc : row) {
-                    ch.r_dst.push_back(qc.first);
-                    ch.r_cost.push_back(qc.second);
-                    const auto it = std::lower_bound(near.begin(), near.end(), qc.first);
-                    ch.r_nidx.push_back((it != near.end() && *it == qc.first) ? (uint16_t)(it - near.begin()) : (uint16_t)0xFFFFu);
-                }
+                /* sensed entries (also in the nearby list) first, then the rest; both ascending */
+                uint32_t n_sensed = 0;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (const auto &qc : row) {
+                        const auto it = std::lower_bound(near.begin(), near.end(), qc.first);
+                        const bool sensed = (it != near.end() && *it == qc.first);
+                        if (sensed != (pass == 0)) continue;
+                        ch.r_dst.push_back(qc.first);
+                        ch.r_cost.push_back(qc.second);
+                        ch.r_nidx.push_back(sensed ? (uint16_t)(it - near.begin()) : (uint16_t)0xFFFFu);
+                        n_sensed += sensed ? 1u : 0u;
+                    }
+                ch.r_sensed.push_back(n_sensed);
             }
         }
     }
@@ -164,15 +171,17 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
         return DSIM_ERR_INVALID;
     }
     /* offsets: reach rows padded to multiples of 8 entries (16-byte aligned starts for every column) */
-    out->off.assign((size_t)n + 1, 0);
+    out->hdr.assign((size_t)n, HostRowHdr{0, 0, 0, 0});
     out->near_off.assign((size_t)n + 1, 0);
     uint64_t ro = 0, no = 0, n_reach = 0;
     for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint32_t v0 = c * kChunk;
         for (size_t k = 0; k < chunks[c].r_len.size(); ++k) {
-            out->off[v0 + k] = (uint32_t)ro;
+            const uint32_t padded = (chunks[c].r_len[k] + 7u) & ~7u;
+            if (ro > 0xFFFFFFF0ull) break;
+            out->hdr[v0 + k] = HostRowHdr{(uint32_t)ro, padded, chunks[c].r_sensed[k], chunks[c].n_len[k]};
             out->near_off[v0 + k] = (uint32_t)no;
-            ro += (chunks[c].r_len[k] + 7u) & ~7u;
+            ro += padded;
             no += chunks[c].n_len[k];
             n_reach += chunks[c].r_len[k];
         }
@@ -181,7 +190,6 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
         if (err) *err = "reach table exceeds 2^32 entries";
         return DSIM_ERR_CAPACITY;
     }
-    out->off[n] = (uint32_t)ro;
     out->near_off[n] = (uint32_t)no;
     out->n_reach = n_reach;
     out->dst.assign(ro, 0xFFFFFFFFu);
@@ -194,12 +202,27 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
         const uint32_t v0 = (uint32_t)c * kChunk;
         size_t rp = 0, np = 0;
         for (size_t k = 0; k < ch.r_len.size(); ++k) {
-            std::copy(ch.r_dst.begin() + rp, ch.r_dst.begin() + rp + ch.r_len[k], out->dst.begin() + out->off[v0 + k]);
-            std::copy(ch.r_cost.begin() + rp, ch.r_cost.begin() + rp + ch.r_len[k], out->cost.begin() + out->off[v0 + k]);
-            std::copy(ch.r_nidx.begin() + rp, ch.r_nidx.begin() + rp + ch.r_len[k], out->nidx.begin() + out->off[v0 + k]);
+            std::copy(ch.r_dst.begin() + rp, ch.r_dst.begin() + rp + ch.r_len[k], out->dst.begin() + out->hdr[v0 + k].start);
+            std::copy(ch.r_cost.begin() + rp, ch.r_cost.begin() + rp + ch.r_len[k], out->cost.begin() + out->hdr[v0 + k].start);
+            std::copy(ch.r_nidx.begin() + rp, ch.r_nidx.begin() + rp + ch.r_len[k], out->nidx.begin() + out->hdr[v0 + k].start);
             std::copy(ch.n_dst.begin() + np, ch.n_dst.begin() + np + ch.n_len[k], out->near_dst.begin() + out->near_off[v0 + k]);
             rp += ch.r_len[k];
             np += ch.n_len[k];
+        }
+    }
+    /* per-row hash: entry index by destination node, for the travel-cost look-ups of remembered patches */
+    out->hash.assign((size_t)n * 256u, (uint8_t)0xFF);
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < (long)n; ++v) {
+        const HostRowHdr &hd = out->hdr[v];
+        if (hd.len > DSIM_ROW_HASH_MAX) continue;
+        uint8_t *tbl = out->hash.data() + (size_t)v * 256u;
+        for (uint32_t k = 0; k < hd.len; ++k) {
+            const uint32_t q = out->dst[hd.start + k];
+            if (q == 0xFFFFFFFFu) continue;
+            uint32_t h = dsim_row_hash(q);
+            while (tbl[h] != 0xFF) h = (h + 1u) & 255u;
+            tbl[h] = (uint8_t)k;
         }
     }
     return DSIM_OK;

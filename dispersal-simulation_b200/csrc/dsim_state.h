@@ -15,6 +15,7 @@
 
 #include <stdint.h>
 
+#define DSIM_ROW_HASH_MAX 192u
 #define DSIM_NIDX_NONE 0xFFFFu   /* reach entry that is not in the 2-hop `nearby` list */
 #define DSIM_ECO_EMPTY 0xFFFFu   /* free adaptation slot */
 #define DSIM_MISC_CLOCK 0x10000u /* misc bit 16: seasons_till_next_mutation is Some(..) */
@@ -66,13 +67,31 @@ struct PatchState {
     uint32_t *band_size;    /* [cap] storage' sizes                                                */
 };
 
+struct __align__(16) RowHdr { /* one per node: where its reach row lives */
+    uint32_t start;          /* first entry, a multiple of 8                                       */
+    uint32_t len;            /* entries incl. padding (multiple of 8)                               */
+    uint32_t n_sensed;       /* leading entries that are also in the 2-hop `nearby` list            */
+    uint32_t n_near;         /* length of the node's nearby list (lib.rs:1158-1178)                 */
+};
+
 struct ReachTable {          /* replaces bounded_dijkstra per family per step (lib.rs:843)         */
-    const uint32_t *off;     /* [P+1] rows padded to multiples of 8 entries                        */
-    const uint32_t *dst;     /* ascending; padding = 0xFFFFFFFF                                     */
+    const RowHdr *hdr;       /* [P]                                                                */
+    /* row = [sensed entries, ascending dst][other reachable nodes, ascending dst][padding 0xFFFFFFFF] */
+    const uint32_t *dst;
     const double *cost;      /* OYR                                                                */
-    const uint16_t *nidx;    /* index in the node's nearby list or DSIM_NIDX_NONE                  */
+    const uint16_t *nidx;    /* sensed entries: index in the node's nearby list                    */
+    const uint8_t *hash;     /* [P * 256] per-row open-addressing index (entry position by node, 0xFF = empty) for
+                                rows of at most DSIM_ROW_HASH_MAX entries; longer rows are binary-searched      */
     const uint32_t *near_off;/* [P+1] 2-hop lists (lib.rs:1158-1178), ascending                    */
     const uint32_t *near_dst;
+};
+
+struct ChildTask { /* what k_children needs about a family that split (lib.rs:1869-1897) */
+    uint64_t parent_id, culture;
+    double take;             /* resources_they_take */
+    uint32_t old_loc, new_loc, parent_hs;
+    uint32_t hist_cnt;       /* parent's history pushes incl. this step's */
+    uint32_t n_off, pad_;    /* the ":<k>" of lib.rs:1880 */
 };
 
 struct StepScratch {
@@ -85,6 +104,9 @@ struct StepScratch {
     uint32_t *fslot;        /* [cap] arrival rank of family j at its new node                      */
     uint32_t *members;      /* [cap] family positions grouped by node                              */
     uint32_t *occ[2];       /* [cap] occupied nodes of this / the previous step                    */
+    uint32_t *plist_small;  /* [cap] occupied nodes with few families (thread-per-node kernel)       */
+    uint32_t *plist_big;    /* [cap] the others (warp-per-node kernel)                              */
+    ChildTask *child_task;  /* [cap] indexed by child rank                                          */
     /* patch-kernel spill arrays for nodes with more families than fit in shared memory, indexed
      * by segment position */
     uint32_t *x_idx, *x_tidx, *x_size, *x_band, *x_bcnt, *x_btot;
@@ -99,6 +121,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t n_alive, n_children, n_dead, n_next;
     uint32_t child_pos_base; /* = n_alive                                                         */
     uint32_t seg_cursor;
+    uint32_t n_small, n_big; /* lengths of plist_small / plist_big                                  */
     uint32_t free_top, hs_hwm;
     uint32_t t;              /* State.t                                                            */
     uint32_t errors;
@@ -115,7 +138,8 @@ struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed
     uint32_t n_mem;          /* history entries the memory loop can still sample (lib.rs:856)       */
     uint32_t n_nodes;
     uint32_t k0, k1;         /* Philox key = seed                                                  */
-    const double *mem_table; /* [n_mem] memory after n decays (lib.rs:847-864)                      */
+    const uint32_t *mem_thr; /* [n_mem] history entry n is kept iff its 32-bit draw <= mem_thr[n], i.e. iff
+                                draw * 2^-32 < memory after n decays (lib.rs:847-864)                */
 };
 
 #endif

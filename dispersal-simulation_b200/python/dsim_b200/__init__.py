@@ -19,10 +19,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.normpath(os.path.join(_HERE, "..", ".."))
 REPO_ROOT = os.path.normpath(os.path.join(PKG_ROOT, ".."))
-LIB_PATH = os.path.join(PKG_ROOT, "libdsim_b200.so")
+LIB_PATH = os.environ.get("DSIM_B200_LIB") or os.path.join(PKG_ROOT, "libdsim_b200.so")  # env: developer A/B builds
 SYNTH_LIB_PATH = os.path.join(PKG_ROOT, "libdsim_synth.so")
 
 N_ECOREGIONS = 304
+OPT_ROWS_IN_PLACE = 0x1
+OPT_PATCH_WARP_ONLY = 0x2
+OPT_MOVE_COOPERATIVE = 0x4
 NO_PARENT = 2**64 - 1
 
 u8p = C.POINTER(C.c_uint8)
@@ -84,7 +87,7 @@ class Options(C.Structure):
         ("history_capacity", C.c_uint32),
         ("device", C.c_uint32),
         ("use_graphs", C.c_uint32),
-        ("reserved_", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 

@@ -362,9 +362,10 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
 
     auto consider = [&](uint32_t q, double gain, double l_cost, uint32_t noise_index) {
         /* lib.rs:918-927.  CANON noise index: position in `known_destinations` for sensed patches,
-         * n_known + n for the n-th newest history entry; two draws per Philox block. */
+         * n_known + n for the n-th newest history entry; two draws per Philox block: index i uses
+         * block i>>1, words (0,1) if i is even, else (2,3). */
         h.rng.draw(h.t, family.id, P_NOISE, noise_index >> 1, out);
-        const double u = (noise_index & 1) ? u53(out[2], out[3]) : u53(out[0], out[1]);
+        const double u = (noise_index & 1u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
         const double g = gain * u - l_cost;
         if (g > m) {
             target = q;
@@ -386,10 +387,10 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
     for (auto it = family.history.rbegin(); it != family.history.rend(); ++it, ++n) {
         if (n >= h.mem_table.size()) break; /* memory < f64::EPSILON from here on, lib.rs:856 */
         const double memory = h.mem_table[n];
-        /* CANON: 32-bit uniform for the memory draws, four per Philox block; entry n uses block
-         * (n>>7)*32 + (n&31), word (n>>5)&3 */
-        h.rng.draw(h.t, family.id, P_MEM, (uint32_t)((n >> 7) * 32 + (n & 31)), out);
-        const double u = (double)out[(n >> 5) & 3] * (1.0 / 4294967296.0);
+        /* CANON: 32-bit uniform for the memory draws, four per Philox block: entry n uses block n>>2,
+         * word n&3 */
+        h.rng.draw(h.t, family.id, P_MEM, (uint32_t)(n >> 2), out);
+        const double u = (double)out[n & 3] * (1.0 / 4294967296.0);
         if (!(u < memory)) continue;
         double c;
         if (!cost_of(it->first, &c)) continue;

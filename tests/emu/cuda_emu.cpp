@@ -151,12 +151,21 @@ static unsigned long long finish_collective(WarpState &w, unsigned mask) {
         if (!((mask >> l) & 1u)) continue;
         LaneSlot &s = w.lane[l];
         int src = (int)l;
-        switch (op) {
-        case OP_SHFL: src = s.arg & 31; break;
-        case OP_SHFL_UP: src = (int)l - s.arg; if (src < 0) src = (int)l; break;
-        case OP_SHFL_DOWN: src = (int)l + s.arg; if (src > 31) src = (int)l; break;
-        case OP_SHFL_XOR: src = (int)l ^ s.arg; break;
-        default: break;
+        {
+            /* CUDA semantics with a segment width w (power of two): lanes are grouped in segments of
+             * w; a source outside the caller's segment returns the caller's own value (up/down/xor)
+             * or wraps inside the segment (indexed) */
+            const int operand = s.arg & 0xFFFF;
+            int w = (s.arg >> 16) & 0xFFFF;
+            if (w <= 0 || w > 32) w = 32;
+            const int seg = ((int)l / w) * w;
+            switch (op) {
+            case OP_SHFL: src = seg + (operand % w); break;
+            case OP_SHFL_UP: src = (int)l - operand; if (src < seg) src = (int)l; break;
+            case OP_SHFL_DOWN: src = (int)l + operand; if (src >= seg + w) src = (int)l; break;
+            case OP_SHFL_XOR: src = (int)l ^ operand; if (src < seg || src >= seg + w) src = (int)l; break;
+            default: break;
+            }
         }
         switch (op) {
         case OP_SHFL: case OP_SHFL_UP: case OP_SHFL_DOWN: case OP_SHFL_XOR:

@@ -81,21 +81,18 @@ template <typename T> static inline T emu_unpack(unsigned long long u) {
     std::memcpy(&v, &u, sizeof(T));
     return v;
 }
+/* `arg` packs the shuffle operand (low 16 bits) and the segment width (high 16 bits) */
 template <typename T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
-    (void)width;
-    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL, mask, emu_pack(v), src));
+    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL, mask, emu_pack(v), (src & 0xFFFF) | (width << 16)));
 }
 template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
-    (void)width;
-    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_UP, mask, emu_pack(v), (int)d));
+    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_UP, mask, emu_pack(v), (int)(d & 0xFFFF) | (width << 16)));
 }
 template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
-    (void)width;
-    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_DOWN, mask, emu_pack(v), (int)d));
+    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_DOWN, mask, emu_pack(v), (int)(d & 0xFFFF) | (width << 16)));
 }
 template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
-    (void)width;
-    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_XOR, mask, emu_pack(v), lanemask));
+    return emu_unpack<T>(emu::warp_collective(emu::OP_SHFL_XOR, mask, emu_pack(v), (lanemask & 0xFFFF) | (width << 16)));
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return (unsigned)emu::warp_collective(emu::OP_BALLOT, mask, pred ? 1 : 0, 0);

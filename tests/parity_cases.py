@@ -15,7 +15,7 @@ from helpers import D
 
 
 def build_pair(oracle_lib, dev_lib, synth, W, H, n_fam, seed=1, sim_seed=7, n_occupied=0, hist_fill=0,
-               params_edit=None, hist_cap=0, graph_edit=None, dev_prefix="dsim_", use_graphs=1):
+               params_edit=None, hist_cap=0, graph_edit=None, dev_prefix="dsim_", use_graphs=1, flags=0):
     g, res, mx = D.synth_grid(W, H, seed, lib=synth)
     if graph_edit is not None:
         g, res, mx = graph_edit(g, res, mx)
@@ -28,6 +28,7 @@ def build_pair(oracle_lib, dev_lib, synth, W, H, n_fam, seed=1, sim_seed=7, n_oc
     getattr(dev_lib, dev_prefix + "default_options")(opt)
     opt.history_capacity = hist_cap
     opt.use_graphs = use_graphs
+    opt.flags = flags
     d = D.Sim(dev_lib, g, params=p, seed=sim_seed, options=opt, prefix=dev_prefix)
     for s in (o, d):
         s.set_patches(res, mx)

@@ -77,3 +77,16 @@ def test_extinction_and_empty(oracle, emu, synth):
     trace = pc.run_lockstep(o, d, 40, by_parts=False, hist_cap=96, check_every=5)
     assert trace[-1] == 0, "everyone starves (extinction check of src/cli.rs:138)"
     pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)   # stepping an empty world is a no-op
+
+
+@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_COOPERATIVE, pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE, pc.D.OPT_PATCH_WARP_ONLY,
+                                   pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE | pc.D.OPT_PATCH_WARP_ONLY])
+def test_kernel_variants(oracle, emu, synth, flags):
+    """The group-cooperative k_move (TMA-staged rows, or rows read in place) and k_patch (warp per node) for every node."""
+    o, d = pc.build_pair(oracle, emu, synth, 24, 30, 400, hist_fill=40, hist_cap=96, flags=flags)
+    pc.run_lockstep(o, d, 6, hist_cap=96)
+
+    def peaceful(p):
+        p.cooperation_threshold = 65
+    o, d = pc.build_pair(oracle, emu, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96, flags=flags)
+    pc.run_lockstep(o, d, 40, by_parts=False, hist_cap=96, check_every=4)
