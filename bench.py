@@ -56,52 +56,46 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML by a thread DURING the timed region."""
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.gpu, self.stop_flag, self.th = gpu_index, False, None
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def _loop(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                     "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+            legacy = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                      "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+            bits = {k: getattr(N, v, getattr(N, legacy[k], 0)) for k, v in names.items()}
+            get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = get(h)
+                for k, b in bits.items():
+                    if b and (r & b):
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report no samples rather than fail the bench
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        import threading
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.sm:
+            out["sm_mhz"] = statistics.median(self.sm)
         return out
 
 
@@ -306,7 +300,7 @@ def main():
     # ---- end to end through the C ABI from host buffers -----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        n_steps_e2e = max(1, min(args.steps, 50))
+        n_steps_e2e = max(1, args.steps)
         barrier()
         t0 = time.perf_counter()
         sim2 = sim  # same handle: re-upload the initial state, run, download

@@ -41,7 +41,8 @@ struct dsim_handle {
     dsim_params p;
     dsim_options opt;
     uint64_t seed = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     LaunchGeom geom;
     uint32_t n_nodes = 0, n_eco = 0;
     std::vector<uint32_t> eco_off_h; /* [n+1] */
@@ -267,11 +268,20 @@ int ensure_capacity(dsim_handle *h, uint64_t n_now) {
 
 #if !defined(DSIM_EMU)
 int build_graphs(dsim_handle *h) {
+    /* one graph per buffer parity.  k_patch_small and k_patch work on disjoint sets of nodes, so they are
+     * captured on two branches (fork/join through events on a second stream) and run concurrently. */
     for (uint32_t par = 0; par < 2; ++par) {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const StepArgs a = make_args(h, par);
-        for (int k = 0; k < DSIM_K_COUNT; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        for (int k = 0; k < DSIM_K_PATCH_SMALL; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        dsim_launch_kernel(DSIM_K_PATCH_SMALL, a, h->geom, h->stream);
+        dsim_launch_kernel(DSIM_K_PATCH, a, h->geom, h->stream2);
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        for (int k = DSIM_K_PATCH + 1; k < DSIM_K_COUNT; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
         CK(cudaStreamEndCapture(h->stream, &g));
         CK(cudaGraphInstantiate(&h->gexec[par], g, 0));
         CK(cudaGraphDestroy(g));
@@ -374,6 +384,48 @@ __global__ void k_pack_adaptation(FamHeavy hv, const uint32_t *hs_of, uint32_t n
             ++m;
         }
         out_n[i] = m;
+    }
+}
+
+/* dsim_set_families: history CSR (oldest first) -> ring, newest min(len, hcap) entries at positions 0.. */
+__global__ void k_unpack_history(FamHeavy hv, const uint64_t *off, const uint32_t *patch, const double *harv, uint32_t n,
+                                 uint32_t n_nodes, uint32_t *bad) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = gw; i < n; i += nw) {
+        const uint64_t a = off[i], b = off[i + 1];
+        const uint32_t keep = (b - a) < hv.hcap ? (uint32_t)(b - a) : hv.hcap;
+        for (uint32_t k = lane; k < keep; k += 32u) {
+            const uint32_t q = patch[b - keep + k];
+            if (q >= n_nodes) atomicOr(bad, 1u);
+            hv.hist_patch[(size_t)i * hv.hcap + k] = q;
+            hv.hist_harv[(size_t)i * hv.hcap + k] = harv[b - keep + k];
+        }
+        if (lane == 0) hv.hist_cnt[i] = keep;
+    }
+}
+
+/* dsim_set_families: sparse adaptation CSR -> slots (entries at the floor are not stored) */
+__global__ void k_unpack_adaptation(FamHeavy hv, const uint64_t *off, const uint32_t *eco, const double *val, uint32_t n,
+                                    double minimum, uint32_t *bad) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n; i += nth) {
+        uint32_t m = 0;
+        for (uint64_t k = off[i]; k < off[i + 1]; ++k) {
+            if (eco[k] >= DSIM_N_ECOREGIONS) {
+                atomicOr(bad, 2u);
+                continue;
+            }
+            if (val[k] == minimum) continue;
+            if (m >= hv.acap) {
+                atomicOr(bad, 4u);
+                break;
+            }
+            hv.a_eco[(size_t)i * hv.acap + m] = (uint16_t)eco[k];
+            hv.a_cnt[(size_t)i * hv.acap + m] = 0u;
+            hv.a_val[(size_t)i * hv.acap + m] = val[k];
+            ++m;
+        }
     }
 }
 
@@ -519,6 +571,9 @@ void dsim_destroy(dsim_handle *h) {
     free_list(h->fam_allocs);
     free_list(h->allocs);
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->join_ev) cudaEventDestroy(h->join_ev);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -587,6 +642,9 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         return DSIM_ERR_CUDA;                                                             \
     }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
     for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
     for (auto &e : h->tev) TRYCUDA(cudaEventCreate(&e));
     TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
@@ -757,16 +815,11 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
         h->cap = h->hs_cap = 0;
         if ((rc = alloc_families(h, want))) return rc;
     }
-    const uint32_t hcap = h->hcap, acap = h->acap;
-    std::vector<uint32_t> misc(n), hs(n), till_adult(n), till_mut(n), hist_cnt(n);
+    const uint32_t acap = h->acap;
+    std::vector<uint32_t> misc(n), hs(n), till_adult(n), till_mut(n);
     std::vector<double> lh(n);
     std::vector<uint64_t> parent(n);
     std::vector<uint16_t> birth(n);
-    std::vector<uint32_t> hp((size_t)n * hcap, 0);
-    std::vector<double> hh((size_t)n * hcap, 0.0);
-    std::vector<uint16_t> a_eco((size_t)n * acap, (uint16_t)DSIM_ECO_EMPTY);
-    std::vector<uint32_t> a_cnt((size_t)n * acap, 0);
-    std::vector<double> a_val((size_t)n * acap, 0.0);
     for (uint64_t i = 0; i < n; ++i) {
         const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
         misc[i] = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
@@ -776,28 +829,6 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
         lh[i] = f->last_harvest ? f->last_harvest[i] : 0.0;
         parent[i] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
         birth[i] = f->birth_index ? f->birth_index[i] : 0;
-        if (f->hist_off) {
-            const uint64_t a = f->hist_off[i], b = f->hist_off[i + 1];
-            const uint64_t keep = std::min<uint64_t>(b - a, hcap);
-            for (uint64_t k = 0; k < keep; ++k) {
-                const uint32_t q = f->hist_patch[b - keep + k];
-                if (q >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "history node out of range");
-                hp[i * hcap + k] = q;
-                hh[i * hcap + k] = f->hist_harvest[b - keep + k];
-            }
-            hist_cnt[i] = (uint32_t)keep;
-        }
-        if (f->adapt_off) {
-            uint32_t m = 0;
-            for (uint64_t k = f->adapt_off[i]; k < f->adapt_off[i + 1]; ++k) {
-                if (f->adapt_eco[k] >= DSIM_N_ECOREGIONS) return fail(h, DSIM_ERR_INVALID, "adaptation ecoregion out of range");
-                if (f->adapt_val[k] == h->p.minimum_adaptation) continue;
-                if (m >= acap) return fail(h, DSIM_ERR_CAPACITY, "more adapted ecoregions than adaptation slots");
-                a_eco[i * acap + m] = (uint16_t)f->adapt_eco[k];
-                a_val[i * acap + m] = f->adapt_val[k];
-                ++m;
-            }
-        }
     }
     h->parity = 0;
     h->mid_step = false;
@@ -807,11 +838,43 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
         (rc = upload(h, c.last_harvest, lh.data(), n)) || (rc = upload(h, c.loc, f->location, n)) || (rc = upload(h, c.size, f->size, n)) ||
         (rc = upload(h, c.till_adult, till_adult.data(), n)) || (rc = upload(h, c.till_mut, till_mut.data(), n)) ||
         (rc = upload(h, c.misc, misc.data(), n)) || (rc = upload(h, c.hs, hs.data(), n)) ||
-        (rc = upload(h, h->hv.hist_cnt, hist_cnt.data(), n)) || (rc = upload(h, h->hv.hist_patch, hp.data(), (size_t)n * hcap)) ||
-        (rc = upload(h, h->hv.hist_harv, hh.data(), (size_t)n * hcap)) || (rc = upload(h, h->hv.a_eco, a_eco.data(), (size_t)n * acap)) ||
-        (rc = upload(h, h->hv.a_cnt, a_cnt.data(), (size_t)n * acap)) || (rc = upload(h, h->hv.a_val, a_val.data(), (size_t)n * acap)) ||
         (rc = upload(h, h->hv.parent, parent.data(), n)) || (rc = upload(h, h->hv.birth_index, birth.data(), n)))
         return rc;
+    CK(cudaMemsetAsync(h->hv.hist_cnt, 0, h->hs_cap * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->hv.a_eco, 0xFF, h->hs_cap * acap * sizeof(uint16_t), h->stream));
+    {
+        /* history and adaptation travel as the caller's CSR arrays and are unpacked on the device */
+        std::vector<void *> tmp;
+        uint32_t *d_bad = nullptr;
+        uint32_t bad = 0;
+        if ((rc = dev_alloc(h, &d_bad, 1, tmp))) { free_list(tmp); return rc; }
+        const uint64_t nh = f->hist_off ? f->hist_off[n] : 0, na = f->adapt_off ? f->adapt_off[n] : 0;
+        if (n && nh) {
+            uint64_t *d_off; uint32_t *d_patch; double *d_harv;
+            if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_patch, nh, tmp, false)) ||
+                (rc = dev_alloc(h, &d_harv, nh, tmp, false)) || (rc = upload(h, d_off, f->hist_off, n + 1)) ||
+                (rc = upload(h, d_patch, f->hist_patch, nh)) || (rc = upload(h, d_harv, f->hist_harvest, nh))) { free_list(tmp); return rc; }
+            DSIM_LAUNCH(k_unpack_history, h->geom.n_sm * 8, 256, 0, h->stream, h->hv, (const uint64_t *)d_off, (const uint32_t *)d_patch,
+                        (const double *)d_harv, (uint32_t)n, h->n_nodes, d_bad);
+            h->total_launches += 1;
+        }
+        if (n && na) {
+            uint64_t *d_off; uint32_t *d_eco; double *d_val;
+            if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_eco, na, tmp, false)) ||
+                (rc = dev_alloc(h, &d_val, na, tmp, false)) || (rc = upload(h, d_off, f->adapt_off, n + 1)) ||
+                (rc = upload(h, d_eco, f->adapt_eco, na)) || (rc = upload(h, d_val, f->adapt_val, na))) { free_list(tmp); return rc; }
+            DSIM_LAUNCH(k_unpack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint64_t *)d_off, (const uint32_t *)d_eco,
+                        (const double *)d_val, (uint32_t)n, h->p.minimum_adaptation, d_bad);
+            h->total_launches += 1;
+        }
+        rc = download(h, &bad, d_bad, 1);
+        if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in set_families");
+        free_list(tmp);
+        if (rc) return rc;
+        if (bad & 1u) return fail(h, DSIM_ERR_INVALID, "history node out of range");
+        if (bad & 2u) return fail(h, DSIM_ERR_INVALID, "adaptation ecoregion out of range");
+        if (bad & 4u) return fail(h, DSIM_ERR_CAPACITY, "more adapted ecoregions than adaptation slots");
+    }
     CK(cudaMemsetAsync(h->hv.decay, 0, h->hs_cap * sizeof(uint32_t), h->stream));
     if ((rc = sync_ctl(h))) return rc;
     DevCtl &ctl = *h->ctl_h;

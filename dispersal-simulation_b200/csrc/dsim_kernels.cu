@@ -255,7 +255,8 @@ struct GroupSmem { /* carved out of dynamic shared memory, one per group */
 __host__ __device__ __forceinline__ uint32_t move_smem_per_group(uint32_t row_cap) {
     return row_cap * 14u + MOVE_ROUND * 28u + MOVE_RING * 2u + 16u;
 }
-__host__ __device__ __forceinline__ uint32_t move_smem_table(uint32_t n_mem) { return ((n_mem * 4u) + 15u) & ~15u; }
+/* keep-threshold table in shared memory, padded with zeros to a multiple of 8 entries */
+__host__ __device__ __forceinline__ uint32_t move_smem_table(uint32_t n_mem) { return ((n_mem + 7u) & ~7u) * 4u; }
 
 /* A family's reach row as the kernel sees it: staged in shared memory or in place in HBM.
  * Layout: [n_sensed entries that are also in the 2-hop list, ascending dst][the other reachable
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
 
     /* dynamic shared memory: [keep thresholds, n_mem x u32][one GroupSmem area per group] */
     uint32_t *thr = (uint32_t *)smem_raw;
-    for (uint32_t k = threadIdx.x; k < a.mc.n_mem; k += blockDim.x) thr[k] = a.mc.mem_thr[k];
+    for (uint32_t k = threadIdx.x; k < ((a.mc.n_mem + 7u) & ~7u); k += blockDim.x) thr[k] = k < a.mc.n_mem ? a.mc.mem_thr[k] : 0u;
     GroupSmem gs;
     {
         unsigned char *base = smem_raw + move_smem_table(a.mc.n_mem) + (size_t)(wib * NG + grp) * move_smem_per_group(row_cap);
@@ -925,12 +926,16 @@ __device__ __forceinline__ void tpf_history(const StepArgs &a, uint32_t step, ui
     for (uint32_t n8 = 0; n8 < nh; n8 += 8u) { /* two independent Philox blocks per iteration (entry n: block n>>2, word n&3) */
         const dsim_u4 o0 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, n8 >> 2);
         const dsim_u4 o1 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, (n8 >> 2) + 1u);
-#pragma unroll
-        for (uint32_t w = 0; w < 4u; ++w)
-            if (n8 + w < nh && dsim_word(o0, w) <= thr[n8 + w]) kept[cnt++] = (uint16_t)(n8 + w);
-#pragma unroll
-        for (uint32_t w = 0; w < 4u; ++w)
-            if (n8 + 4u + w < nh && dsim_word(o1, w) <= thr[n8 + 4u + w]) kept[cnt++] = (uint16_t)(n8 + 4u + w);
+        /* the table is padded to a multiple of 8 entries; the index is warp-uniform (broadcast) */
+        const uint4 t0 = *reinterpret_cast<const uint4 *>(thr + n8), t1 = *reinterpret_cast<const uint4 *>(thr + n8 + 4u);
+        uint32_t mask = (o0.x <= t0.x ? 1u : 0u) | (o0.y <= t0.y ? 2u : 0u) | (o0.z <= t0.z ? 4u : 0u) | (o0.w <= t0.w ? 8u : 0u) |
+                        (o1.x <= t1.x ? 16u : 0u) | (o1.y <= t1.y ? 32u : 0u) | (o1.z <= t1.z ? 64u : 0u) | (o1.w <= t1.w ? 128u : 0u);
+        if (nh - n8 < 8u) mask &= (1u << (nh - n8)) - 1u;
+        if (mask == 0u) continue; /* the common case beyond the first few dozen entries */
+        while (mask) {
+            kept[cnt++] = (uint16_t)(n8 + (uint32_t)__ffs((int)mask) - 1u);
+            mask &= mask - 1u;
+        }
         if (cnt > TPF_KEPT - 8u) {
             tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
             cnt = 0;
@@ -947,7 +952,7 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap;
     uint32_t *thr = (uint32_t *)smem_raw; /* keep thresholds: read with a warp-uniform index (broadcast) */
-    for (uint32_t k = threadIdx.x; k < a.mc.n_mem; k += blockDim.x) thr[k] = a.mc.mem_thr[k];
+    for (uint32_t k = threadIdx.x; k < ((a.mc.n_mem + 7u) & ~7u); k += blockDim.x) thr[k] = k < a.mc.n_mem ? a.mc.mem_thr[k] : 0u;
     __syncthreads();
 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
