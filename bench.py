@@ -232,19 +232,30 @@ def main():
 
     lib = D.load()
     synth = D.load_synth()
-    # N > 1: every rank advances its own replica of the workload (different seeds).  The band-partitioned
-    # multi-GPU step is not built yet; see DESIGN.md §8.
-    g, res, mx, fam = build_workload(cfg, args.seed + rank, synth)
+    # N > 1: weak scaling — 100k x N families on the same Americas-scale grid, split into N latitude bands of
+    # about equal family counts; halo views and migrating families travel over NCCL.
+    if world > 1:
+        cfg = (cfg[0], cfg[1], cfg[2] * world, cfg[3], cfg[4])
+    g, res, mx, fam = build_workload(cfg, args.seed, synth)
     opt = D.Options()
     lib.dsim_default_options(C.byref(opt))
     opt.device = local_rank
     opt.use_graphs = 0 if args.no_graphs else 1
     opt.flags = args.flags
+    if world > 1:
+        opt.family_capacity = 4 * cfg[2] // world + 65536
     t0 = time.time()
     sim = D.Sim(lib, g, seed=args.sim_seed, options=opt)
     log(f"[bench] rank {rank}: handle + reach table in {time.time() - t0:.1f}s")
+    if world > 1:
+        bounds = D.mg_band_bounds(fam.location, g.n_nodes, world, sim.mg_halo_width())
+        sim.mg_configure(rank, world, bounds)
     sim.set_patches(res, mx)
     sim.set_families(fam)
+    if world > 1:
+        uid = [D.mg_unique_id(lib) if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim.mg_init_nccl(uid[0])     # communicator + initial halo exchange
 
     launches0 = sim.launch_count()
     barrier()
@@ -274,7 +285,7 @@ def main():
     roofline, kernels = None, {}
     fam_live = st.live_families
     occ = max(1, st.occupied_patches)
-    if args.profile_steps > 0:
+    if args.profile_steps > 0 and world == 1:
         sim.profile_enable(True)
         sim.profile_read(reset=True)
         stp = sim.step(args.profile_steps, allow_model_errors=True)
@@ -299,7 +310,7 @@ def main():
 
     # ---- end to end through the C ABI from host buffers -----------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         n_steps_e2e = max(1, args.steps)
         barrier()
         t0 = time.perf_counter()
@@ -343,10 +354,10 @@ def main():
             "metric": "family-updates/sec/GPU", "value": value, "unit": "family-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{cfg_name}: {W}x{H} hex grid ({W * H} patches), {n_fam} families per GPU, "
+            "config": {"workload": f"{cfg_name}: {W}x{H} hex grid ({W * H} patches), {n_fam} families in total, "
                                    f"hist_fill {hist_fill}, seed {args.seed}",
                        "l2": "working set (reach table 3.7 GB + views 64 MB + histories) exceeds the 126 MB L2; no flush",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (band partition not built yet)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} latitude bands, NCCL halo + migrant exchange, {cfg[2]} families in total",
                        "cuda_graphs": not args.no_graphs,
                        "live_families_end": int(fam_live)},
             "per_gpu_value": value / world,

@@ -16,6 +16,9 @@
 #include "dsim_math.h"
 #include "dsim_reach.h"
 
+extern "C" void dsim_mg_release(dsim_handle *h);
+extern "C" int dsim_mg_step_enqueue(dsim_handle *h);
+
 namespace {
 
 std::string g_create_error;
@@ -48,6 +51,9 @@ struct dsim_handle {
     std::vector<uint32_t> eco_off_h; /* [n+1] */
     uint64_t n_near = 0, n_reach = 0, n_reach_padded = 0;
     uint32_t max_row = 0;
+    uint32_t reach_span = 0; /* largest |node - reachable or 2-hop node|, in node ids */
+    bool mg_enabled = false;
+    uint32_t mg_lo = 0, mg_hi = 0, mg_occ_prev = 0;
 
     std::vector<void *> allocs; /* everything to cudaFree */
     ReachTable rt;
@@ -121,6 +127,9 @@ template <typename T> int download(dsim_handle *h, T *dst, const T *src, size_t 
     return DSIM_OK;
 }
 
+/* index of the list of nodes occupied by part 2 of the last step */
+uint32_t occ_prev_index(const dsim_handle *h) { return h->mg_enabled ? h->mg_occ_prev : (h->parity ^ 1u); }
+
 int sync_ctl(dsim_handle *h) { /* device -> pinned host mirror */
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -159,6 +168,8 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     a.ctl = h->ctl;
     a.mc = h->mc;
     a.parity = parity;
+    a.occ_par = parity;
+    std::memset(&a.mg, 0, sizeof a.mg);
     a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
     a.children_inline = (h->opt.flags & DSIM_OPT_MOVE_COOPERATIVE) ? 1u : 0u;
     return a;
@@ -254,6 +265,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
 }
 
 int ensure_capacity(dsim_handle *h, uint64_t n_now) {
+    if (h->mg_enabled) return DSIM_OK; /* fixed capacity per rank (dsim_options.family_capacity) */
     if (n_now * 10 <= h->cap * 7) return DSIM_OK;
     uint64_t want = std::max<uint64_t>(2 * n_now + 1024, h->cap);
     if (want == h->cap) return DSIM_OK;
@@ -350,7 +362,7 @@ uint32_t compute_acap(double minimum) {
 int recensus(dsim_handle *h) {
     int rc = sync_ctl(h);
     if (rc) return rc;
-    const uint32_t prev = h->parity ^ 1u;
+    const uint32_t prev = occ_prev_index(h);
     h->ctl_h->n_occ[prev] = 0;
     rc = push_ctl(h);
     if (rc) return rc;
@@ -563,6 +575,7 @@ const char *dsim_last_error(const dsim_handle *h) { return h ? h->err.c_str() : 
 void dsim_destroy(dsim_handle *h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    dsim_mg_release(h);
     destroy_graphs(h);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -665,7 +678,13 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         h->n_reach = hr.n_reach;
         h->n_reach_padded = hr.dst.size();
         h->max_row = 0;
-        for (uint32_t v = 0; v < n; ++v) h->max_row = std::max(h->max_row, hr.hdr[v].len);
+        for (uint32_t v = 0; v < n; ++v) {
+            h->max_row = std::max(h->max_row, hr.hdr[v].len);
+            for (uint32_t e = hr.hdr[v].start; e < hr.hdr[v].start + hr.hdr[v].len; ++e)
+                if (hr.dst[e] != 0xFFFFFFFFu) h->reach_span = std::max(h->reach_span, hr.dst[e] > v ? hr.dst[e] - v : v - hr.dst[e]);
+            for (uint32_t e = hr.near_off[v]; e < hr.near_off[v + 1]; ++e)
+                h->reach_span = std::max(h->reach_span, hr.near_dst[e] > v ? hr.near_dst[e] - v : v - hr.near_dst[e]);
+        }
         RowHdr *hdr;
         uint8_t *hash;
         uint32_t *dst, *near_off, *near_dst;
@@ -798,7 +817,7 @@ int dsim_get_patches(dsim_handle *h, double *res, double *max_res) {
     return DSIM_OK;
 }
 
-int dsim_set_families(dsim_handle *h, const dsim_families *f) {
+static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t next_id_override, bool have_override) {
     if (!h || !f) return DSIM_ERR_INVALID;
     const uint64_t n = f->n;
     if (n && (!f->id || !f->culture || !f->location || !f->size || !f->stored)) return fail(h, DSIM_ERR_INVALID, "missing family array");
@@ -810,6 +829,8 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
     CK(cudaStreamSynchronize(h->stream));
     int rc;
     uint64_t want = h->opt.family_capacity ? std::max<uint64_t>(h->opt.family_capacity, n + n / 4 + 256) : 2 * n + 1024;
+    if (want > h->cap && h->mg_enabled)
+        return fail(h, DSIM_ERR_CAPACITY, "multi-GPU handles have a fixed capacity: set dsim_options.family_capacity");
     if (want > h->cap) {
         free_list(h->fam_allocs); /* nothing to preserve */
         h->cap = h->hs_cap = 0;
@@ -883,7 +904,7 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
     ctl.t = t_keep;
     ctl.n_cur[0] = (uint32_t)n;
     ctl.hs_hwm = (uint32_t)n;
-    ctl.next_id = n ? f->id[n - 1] + 1 : 0;
+    ctl.next_id = have_override ? next_id_override : (n ? f->id[n - 1] + 1 : 0);
     ctl.cap = (uint32_t)h->cap;
     ctl.hs_cap = (uint32_t)h->hs_cap;
     if ((rc = push_ctl(h))) return rc;
@@ -893,6 +914,60 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
     if ((rc = recensus(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
+}
+
+int dsim_set_families(dsim_handle *h, const dsim_families *f) {
+    if (!h || !f) return DSIM_ERR_INVALID;
+    if (!h->mg_enabled) return set_families_impl(h, f, 0, false);
+    /* multi-GPU: keep the families of the own band; ids continue after the largest id of the FULL vector */
+    const uint64_t n = f->n;
+    if (n && (!f->id || !f->culture || !f->location || !f->size || !f->stored)) return fail(h, DSIM_ERR_INVALID, "missing family array");
+    std::vector<uint64_t> keep;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (f->location[i] >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "family location out of range");
+        if (i > 0 && f->id[i] <= f->id[i - 1]) return fail(h, DSIM_ERR_INVALID, "family ids must ascend");
+        if (f->location[i] >= h->mg_lo && f->location[i] < h->mg_hi) keep.push_back(i);
+    }
+    const uint64_t m = keep.size();
+    std::vector<uint64_t> id(m), parent(m), culture(m), hoff(m + 1, 0), aoff(m + 1, 0);
+    std::vector<uint16_t> birth(m), noff(m);
+    std::vector<uint32_t> loc(m), size(m), ta(m), tm(m), hp, ae;
+    std::vector<uint8_t> clk(m);
+    std::vector<double> stored(m), lh(m), hh, av;
+    for (uint64_t k = 0; k < m; ++k) {
+        const uint64_t i = keep[k];
+        id[k] = f->id[i];
+        parent[k] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
+        birth[k] = f->birth_index ? f->birth_index[i] : 0;
+        culture[k] = f->culture[i];
+        loc[k] = f->location[i];
+        size[k] = f->size[i];
+        stored[k] = f->stored[i];
+        lh[k] = f->last_harvest ? f->last_harvest[i] : 0.0;
+        ta[k] = f->till_adult ? f->till_adult[i] : 0;
+        tm[k] = f->till_mutation ? f->till_mutation[i] : 0;
+        clk[k] = f->has_mutation_clock ? f->has_mutation_clock[i] : 0;
+        noff[k] = f->n_offspring ? f->n_offspring[i] : 0;
+        if (f->hist_off) {
+            hp.insert(hp.end(), f->hist_patch + f->hist_off[i], f->hist_patch + f->hist_off[i + 1]);
+            hh.insert(hh.end(), f->hist_harvest + f->hist_off[i], f->hist_harvest + f->hist_off[i + 1]);
+        }
+        hoff[k + 1] = hp.size();
+        if (f->adapt_off) {
+            ae.insert(ae.end(), f->adapt_eco + f->adapt_off[i], f->adapt_eco + f->adapt_off[i + 1]);
+            av.insert(av.end(), f->adapt_val + f->adapt_off[i], f->adapt_val + f->adapt_off[i + 1]);
+        }
+        aoff[k + 1] = ae.size();
+    }
+    hp.push_back(0); hh.push_back(0.0); ae.push_back(0); av.push_back(0.0);
+    dsim_families g;
+    g.n = m;
+    g.id = id.data(); g.parent_id = parent.data(); g.birth_index = birth.data(); g.culture = culture.data();
+    g.location = loc.data(); g.size = size.data(); g.stored = stored.data(); g.last_harvest = lh.data();
+    g.till_adult = ta.data(); g.till_mutation = tm.data(); g.has_mutation_clock = clk.data(); g.n_offspring = noff.data();
+    g.hist_off = hoff.data(); g.hist_patch = hp.data(); g.hist_harvest = hh.data();
+    g.adapt_off = aoff.data(); g.adapt_eco = ae.data(); g.adapt_val = av.data();
+    return set_families_impl(h, &g, n ? f->id[n - 1] + 1 : 0, true);
 }
 
 int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *n_adapt) {
@@ -1004,7 +1079,7 @@ static int collect_storage(dsim_handle *h, std::vector<uint32_t> &node, std::vec
     int rc = sync_ctl(h);
     if (rc) return rc;
     /* the nodes visited by part 2 of the last step are the "occupied last step" list of the next one */
-    const uint32_t prev = h->parity ^ 1u;
+    const uint32_t prev = occ_prev_index(h);
     const uint32_t n = h->ctl_h->n_occ[prev];
     node.clear(); cult.clear(); size.clear();
     if (n == 0) return DSIM_OK;
@@ -1125,7 +1200,7 @@ int dsim_set_storage(dsim_handle *h, uint64_t n, const uint32_t *node, const uin
             free_list(tmp);
             return rc;
         }
-        const uint32_t prev = h->parity ^ 1u;
+        const uint32_t prev = occ_prev_index(h);
         DSIM_LAUNCH(k_apply_storage, h->geom.n_sm * 4, 256, 0, h->stream, h->ps, (const uint32_t *)d_nodes, (const uint32_t *)d_first,
                     (const uint32_t *)d_count, (uint32_t)nodes.size(), base, h->sc.occ[prev], h->ctl, prev);
         h->total_launches += 1;
@@ -1159,7 +1234,11 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
     for (uint32_t s = 0; s < n_steps; ++s) {
         if (h->steps_since_check >= 8 || h->n_known * 10 > h->cap * 7)
             if ((rc = host_check(h))) return rc;
-        if ((rc = launch_step(h))) return rc;
+        if (h->mg_enabled) {
+            if ((rc = dsim_mg_step_enqueue(h))) return rc;
+        } else if ((rc = launch_step(h))) {
+            return rc;
+        }
         h->steps_since_check += 1;
     }
     if (!stats) return DSIM_OK;
@@ -1171,7 +1250,7 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
     stats->births = c.births - births0;
     stats->deaths = c.deaths - deaths0;
     stats->family_updates = c.updates - updates0;
-    stats->occupied_patches = c.n_occ[h->parity ^ 1u];
+    stats->occupied_patches = c.n_occ[occ_prev_index(h)];
     stats->model_errors = c.errors;
     if (c.errors & ~(uint32_t)DSIM_MODEL_CAPACITY) {
         h->err = "a model assertion of the reference failed (see dsim_step_stats.model_errors)";
@@ -1206,6 +1285,7 @@ int dsim_step_timed(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats, do
 
 int dsim_step_part(dsim_handle *h, int part) {
     if (!h) return DSIM_ERR_INVALID;
+    if (h->mg_enabled) return fail(h, DSIM_ERR_INVALID, "use dsim_mg_phase on a multi-GPU handle");
     int rc;
     h->snap_valid = false;
     if (part == 1) {
@@ -1292,6 +1372,342 @@ int dsim_launch_count(dsim_handle *h, uint64_t *n) {
     if (!h || !n) return DSIM_ERR_INVALID;
     *n = h->total_launches;
     return DSIM_OK;
+}
+
+} /* extern "C" */
+
+/* ================================================================================================ *
+ * Multi-GPU: band partition (dsim_mg_kernels.cu).  One handle per GPU / process.
+ * ================================================================================================ */
+#if !defined(DSIM_EMU)
+#include <nccl.h>
+#endif
+
+struct dsim_mg_state {
+    bool enabled = false;
+    uint32_t rank = 0, world = 1, own_lo = 0, own_hi = 0;
+    MgBuffers mb;
+    std::vector<void *> allocs;
+    uint64_t split_bytes = 0, emig_bytes = 0, halo_bytes = 0;
+    uint32_t occ_par = 0;
+#if !defined(DSIM_EMU)
+    ncclComm_t comm = nullptr;
+#endif
+    bool nccl = false;
+};
+
+namespace {
+
+dsim_mg_state *mg_of(dsim_handle *h);
+
+StepArgs mg_args(dsim_handle *h, bool part2) {
+    dsim_mg_state *m = mg_of(h);
+    StepArgs a = make_args(h, h->parity);
+    a.occ_par = m->occ_par;
+    a.mg.enabled = 1;
+    a.mg.rank = m->rank;
+    a.mg.world = m->world;
+    a.mg.own_lo = m->own_lo;
+    a.mg.own_hi = m->own_hi;
+    a.mg.child_grank = m->mb.child_grank;
+    a.mg.halo_cult[0] = m->mb.halo_cult[0];
+    a.mg.halo_cult[1] = m->mb.halo_cult[1];
+    if (part2) { /* part 2 runs in place on the re-packed buffer */
+        a.next = a.cur;
+        a.sc.fslot = m->mb.fslot2;
+    }
+    return a;
+}
+
+} // namespace
+
+/* the multi-GPU state hangs off the handle through a side table keyed by the handle pointer, so that
+ * the single-GPU struct stays untouched */
+#include <map>
+namespace {
+std::map<dsim_handle *, dsim_mg_state *> g_mg;
+dsim_mg_state *mg_of(dsim_handle *h) {
+    auto it = g_mg.find(h);
+    return it == g_mg.end() ? nullptr : it->second;
+}
+} // namespace
+
+extern "C" {
+
+int dsim_mg_halo_width(dsim_handle *h, uint32_t *nodes) {
+    if (!h || !nodes) return DSIM_ERR_INVALID;
+    *nodes = 2u * h->reach_span;
+    return DSIM_OK;
+}
+
+int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint32_t *bounds) {
+    if (!h || !bounds || world == 0 || rank >= world) return DSIM_ERR_INVALID;
+    if (h->opt.flags & DSIM_OPT_MOVE_COOPERATIVE) return fail(h, DSIM_ERR_INVALID, "the multi-GPU step uses the default move kernel");
+    if (bounds[0] != 0 || bounds[world] != h->n_nodes) return fail(h, DSIM_ERR_INVALID, "bounds must cover [0, n_nodes]");
+    const uint32_t hw = 2u * h->reach_span;
+    for (uint32_t r = 0; r < world; ++r)
+        if (bounds[r + 1] <= bounds[r] || (world > 1 && bounds[r + 1] - bounds[r] < hw))
+            return fail(h, DSIM_ERR_INVALID, "every band must hold at least dsim_mg_halo_width() nodes");
+    dsim_mg_state *m = mg_of(h);
+    if (!m) {
+        m = new dsim_mg_state;
+        g_mg[h] = m;
+    }
+    free_list(m->allocs);
+    std::memset(&m->mb, 0, sizeof m->mb);
+    m->enabled = true;
+    m->rank = rank;
+    m->world = world;
+    m->own_lo = bounds[rank];
+    m->own_hi = bounds[rank + 1];
+    m->occ_par = h->parity;
+    h->mg_occ_prev = m->occ_par ^ 1u;
+    MgBuffers &mb = m->mb;
+    mb.has_peer[0] = rank > 0 ? 1u : 0u;
+    mb.has_peer[1] = rank + 1 < world ? 1u : 0u;
+    mb.scap = (uint32_t)std::max<uint64_t>(1024, h->cap / 8);
+    mb.ecap = (uint32_t)std::max<uint64_t>(256, std::min<uint64_t>(h->cap / 16, 2048));
+    mb.rec_bytes = mg_rec_bytes(h->acap, h->hcap);
+    mb.hw = hw;
+    mb.ccap = std::max<uint32_t>(1024u, hw / 2u);
+    m->split_bytes = (1 + (uint64_t)mb.scap) * 8;
+    m->emig_bytes = 16 + (uint64_t)mb.ecap * mb.rec_bytes;
+    m->halo_bytes = 16 + (uint64_t)mb.hw * sizeof(PatchView) + (uint64_t)mb.ccap * 8;
+    int rc;
+#define MA(ptr, count)                                         \
+    if ((rc = dev_alloc(h, &(ptr), (count), m->allocs)) != 0) { \
+        free_list(m->allocs);                                  \
+        return rc;                                             \
+    }
+    MA(mb.split_send, 1 + (size_t)mb.scap) MA(mb.split_recv, (size_t)world * (1 + (size_t)mb.scap))
+    MA(mb.child_grank, mb.scap) MA(mb.counters, MG_N_COUNTERS) MA(mb.emig_list, 2 * (size_t)mb.ecap)
+    MA(mb.emig_hs, 2 * (size_t)mb.ecap) MA(mb.fslot2, h->cap)
+    for (int s = 0; s < 2; ++s) {
+        MA(mb.emig_send[s], m->emig_bytes) MA(mb.emig_recv[s], m->emig_bytes)
+        MA(mb.halo_send[s], m->halo_bytes) MA(mb.halo_recv[s], m->halo_bytes)
+        MA(mb.halo_cult[s], mb.ccap)
+    }
+#undef MA
+    CK(cudaStreamSynchronize(h->stream));
+    h->mg_enabled = true;
+    h->mg_lo = m->own_lo;
+    h->mg_hi = m->own_hi;
+    destroy_graphs(h);
+    return DSIM_OK;
+}
+
+int dsim_mg_buffer(dsim_handle *h, int channel, int peer, int recv, void **dev_ptr, uint64_t *bytes) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !dev_ptr || !bytes) return DSIM_ERR_INVALID;
+    const MgBuffers &mb = m->mb;
+    switch (channel) {
+    case DSIM_MG_CH_SPLIT:
+        if (recv && (peer < 0 || (uint32_t)peer >= m->world)) return DSIM_ERR_INVALID;
+        *dev_ptr = recv ? (void *)(mb.split_recv + (size_t)peer * (1 + (size_t)mb.scap)) : (void *)mb.split_send;
+        *bytes = m->split_bytes;
+        return DSIM_OK;
+    case DSIM_MG_CH_EMIGRANTS:
+        if (peer < 0 || peer > 1) return DSIM_ERR_INVALID;
+        *dev_ptr = recv ? mb.emig_recv[peer] : mb.emig_send[peer];
+        *bytes = m->emig_bytes;
+        return DSIM_OK;
+    case DSIM_MG_CH_HALO:
+        if (peer < 0 || peer > 1) return DSIM_ERR_INVALID;
+        *dev_ptr = recv ? mb.halo_recv[peer] : mb.halo_send[peer];
+        *bytes = m->halo_bytes;
+        return DSIM_OK;
+    default: return DSIM_ERR_INVALID;
+    }
+}
+
+int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes) {
+    if (!h || !dst || !src) return DSIM_ERR_INVALID;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
+    const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
+    const MgBuffers &mb = m->mb;
+    auto K = [&](int k, const StepArgs &a) {
+        dsim_launch_kernel(k, a, h->geom, h->stream);
+        h->k_launches[k] += 1;
+        h->total_launches += 1;
+    };
+    auto M = [&](int k, const StepArgs &a) {
+        dsim_mg_launch(k, a, mb, h->geom, h->stream);
+        h->total_launches += 1;
+    };
+    switch (phase) {
+    case DSIM_MG_PHASE_LIFECYCLE:
+        K(DSIM_K_LIFECYCLE, a1); K(DSIM_K_CONTROL, a1); M(DSIM_MGK_SPLIT_IDS, a1);
+        break;
+    case DSIM_MG_PHASE_MOVE:
+        M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
+        break;
+    case DSIM_MG_PHASE_PATCH:
+        M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2); K(DSIM_K_PATCH_SMALL, a2); K(DSIM_K_PATCH, a2);
+        M(DSIM_MGK_HALO_PACK, a2);
+        break;
+    case DSIM_MG_PHASE_FINISH:
+        M(DSIM_MGK_HALO_UNPACK, a2); M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2);
+        m->occ_par ^= 1u;
+        h->mg_occ_prev = m->occ_par ^ 1u;
+        break;
+    case DSIM_MG_PHASE_HALO_PACK:
+        CK(cudaMemsetAsync(mb.counters, 0, MG_N_COUNTERS * sizeof(uint32_t), h->stream));
+        M(DSIM_MGK_HALO_PACK, a2);
+        break;
+    case DSIM_MG_PHASE_HALO_UNPACK:
+        M(DSIM_MGK_HALO_UNPACK, a2);
+        break;
+    default: return DSIM_ERR_INVALID;
+    }
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+int dsim_mg_phase(dsim_handle *h, int phase) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m) return DSIM_ERR_INVALID;
+    h->snap_valid = false;
+    int rc = mg_launch_phase(h, m, phase);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
+int dsim_mg_unique_id(void *out) {
+#if defined(DSIM_EMU)
+    (void)out;
+    return DSIM_ERR_COMM;
+#else
+    if (!out) return DSIM_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) <= DSIM_MG_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return DSIM_ERR_COMM;
+    std::memset(out, 0, DSIM_MG_UNIQUE_ID_BYTES);
+    std::memcpy(out, &id, sizeof id);
+    return DSIM_OK;
+#endif
+}
+
+int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !unique_id) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no NCCL in the CPU debugging build");
+#else
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    if (ncclCommInitRank(&m->comm, (int)m->world, id, (int)m->rank) != ncclSuccess) return fail(h, DSIM_ERR_COMM, "ncclCommInitRank failed");
+    m->nccl = true;
+    return DSIM_OK;
+#endif
+}
+
+#if !defined(DSIM_EMU)
+#define NCK(call)                                                                         \
+    do {                                                                                  \
+        ncclResult_t r_ = (call);                                                         \
+        if (r_ != ncclSuccess) {                                                          \
+            char buf_[256];                                                               \
+            std::snprintf(buf_, sizeof buf_, "%s failed: %s", #call, ncclGetErrorString(r_)); \
+            return fail(h, DSIM_ERR_COMM, buf_);                                          \
+        }                                                                                 \
+    } while (0)
+
+static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel) {
+    const MgBuffers &mb = m->mb;
+    if (channel == DSIM_MG_CH_SPLIT) {
+        NCK(ncclAllGather(mb.split_send, mb.split_recv, 1 + (size_t)mb.scap, ncclUint64, m->comm, h->stream));
+        return DSIM_OK;
+    }
+    const uint64_t bytes = channel == DSIM_MG_CH_EMIGRANTS ? m->emig_bytes : m->halo_bytes;
+    NCK(ncclGroupStart());
+    for (int s = 0; s < 2; ++s) {
+        if (!mb.has_peer[s]) continue;
+        const int peer = s == 0 ? (int)m->rank - 1 : (int)m->rank + 1;
+        unsigned char *snd = channel == DSIM_MG_CH_EMIGRANTS ? mb.emig_send[s] : mb.halo_send[s];
+        unsigned char *rcv = channel == DSIM_MG_CH_EMIGRANTS ? mb.emig_recv[s] : mb.halo_recv[s];
+        NCK(ncclSend(snd, bytes, ncclChar, peer, m->comm, h->stream));
+        NCK(ncclRecv(rcv, bytes, ncclChar, peer, m->comm, h->stream));
+    }
+    NCK(ncclGroupEnd());
+    return DSIM_OK;
+}
+#endif
+
+/* one full multi-GPU step with the built-in transport; everything is enqueued, nothing waits on the host */
+int dsim_mg_step_enqueue(dsim_handle *h) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no transport: drive dsim_mg_phase yourself");
+#else
+    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or drive dsim_mg_phase yourself");
+    int rc;
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_SPLIT))) return rc;
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_MOVE))) return rc;
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_EMIGRANTS))) return rc;
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO))) return rc;
+    return mg_launch_phase(h, m, DSIM_MG_PHASE_FINISH);
+#endif
+}
+
+int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set on every rank */
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no transport");
+#else
+    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport");
+    int rc;
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_PACK))) return rc;
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO))) return rc;
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+#endif
+}
+
+int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !stats) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no transport");
+#else
+    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport");
+    uint64_t v[6] = {stats->live_families, stats->births, stats->deaths, stats->family_updates, stats->occupied_patches,
+                     stats->model_errors};
+    uint64_t *d = nullptr;
+    std::vector<void *> tmp;
+    int rc = dev_alloc(h, &d, 6, tmp, false);
+    if (!rc) rc = upload(h, d, v, 6);
+    if (!rc && ncclAllReduce(d, d, 5, ncclUint64, ncclSum, m->comm, h->stream) != ncclSuccess) rc = fail(h, DSIM_ERR_COMM, "ncclAllReduce failed");
+    if (!rc && ncclAllReduce(d + 5, d + 5, 1, ncclUint64, ncclMax, m->comm, h->stream) != ncclSuccess) rc = fail(h, DSIM_ERR_COMM, "ncclAllReduce failed");
+    if (!rc) rc = download(h, v, d, 6);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed");
+    free_list(tmp);
+    if (rc) return rc;
+    stats->live_families = v[0]; stats->births = v[1]; stats->deaths = v[2]; stats->family_updates = v[3];
+    stats->occupied_patches = v[4];
+    return DSIM_OK;
+#endif
+}
+
+void dsim_mg_release(dsim_handle *h) {
+    dsim_mg_state *m = mg_of(h);
+    if (!m) return;
+#if !defined(DSIM_EMU)
+    if (m->comm) ncclCommDestroy(m->comm);
+#endif
+    free_list(m->allocs);
+    g_mg.erase(h);
+    delete m;
 }
 
 } /* extern "C" */

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
         ctl->child_id_base = ctl->next_id;
         ctl->next_id += n_children;
         ctl->n_cur[a.parity ^ 1u] = n_alive + n_children;
-        ctl->n_occ[a.parity] = 0;
+        ctl->n_occ[a.occ_par] = 0;
         ctl->seg_cursor = 0;
         ctl->n_small = 0;
         ctl->n_big = 0;
@@ -334,8 +334,10 @@ __device__ __forceinline__ double view_quality(const StepArgs &a, const PatchVie
     bool enemy = false;
     if (v.nb > 0u) {
         enemy = !dsim_will_cooperate(culture, v.cult0, a.mc.threshold, a.mc.inclusive);
+        const uint64_t *others = (v.stor_off & DSIM_STOR_HALO) ? a.mg.halo_cult[(v.stor_off >> 30) & 1u] + (v.stor_off & 0x3FFFFFFFu)
+                                                                : a.ps.band_cult + v.stor_off;
         for (uint32_t k = 1; k < v.nb && !enemy; ++k)
-            enemy = !dsim_will_cooperate(culture, a.ps.band_cult[v.stor_off + k], a.mc.threshold, a.mc.inclusive);
+            enemy = !dsim_will_cooperate(culture, others[k], a.mc.threshold, a.mc.inclusive);
     }
     if (enemy) return 0.0;
     const uint64_t pop_at_destination = (uint64_t)v.pop + (same_patch ? 0u : size);
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
                             a.next.misc[cpos] = 0u;
                             a.next.hs[cpos] = chs;
                             const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
-                            if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = cc.target;
+                            if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = cc.target;
                             a.sc.fslot[cpos] = slot;
                         }
                     } else if (leader) {
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
                 a.next.misc[newpos] = misc;
                 a.next.hs[newpos] = hs;
                 const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-                if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = newloc;
+                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
                 a.sc.fslot[newpos] = slot;
             }
             __syncwarp();
@@ -1077,9 +1079,13 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
         a.next.till_mut[newpos] = a.cur.till_mut[i];
         a.next.misc[newpos] = misc;
         a.next.hs[newpos] = hs;
-        const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-        if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = newloc;
-        a.sc.fslot[newpos] = slot;
+        if (!a.mg.enabled || (newloc >= a.mg.own_lo && newloc < a.mg.own_hi)) {
+            const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
+            if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
+            a.sc.fslot[newpos] = slot;
+        } else {
+            a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
+        }
     }
 }
 
@@ -1114,7 +1120,9 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
 
     for (uint32_t r = gwarp; r < n_children; r += nwarps) {
         const ChildTask t = a.sc.child_task[r];
-        const uint64_t cid = ctl->child_id_base + r;
+        /* ids follow the reference's append order = parent order; with several GPUs the rank among ALL
+         * children of the step comes from k_mg_child_rank */
+        const uint64_t cid = ctl->child_id_base + (a.mg.enabled ? a.mg.child_grank[r] : r);
         const uint32_t cpos = ctl->child_pos_base + r;
         const uint32_t ft = ctl->free_top;
         const uint32_t chs = (r < ft) ? a.sc.free_hs[ft - 1u - r] : ctl->hs_hwm + (r - ft);
@@ -1200,9 +1208,13 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             a.next.till_mut[cpos] = 0u;
             a.next.misc[cpos] = 0u;
             a.next.hs[cpos] = chs;
-            const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
-            if (slot == 0u) a.sc.occ[a.parity][atomicAdd(&ctl->n_occ[a.parity], 1u)] = cc.target;
-            a.sc.fslot[cpos] = slot;
+            if (!a.mg.enabled || (cc.target >= a.mg.own_lo && cc.target < a.mg.own_hi)) {
+                const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
+                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = cc.target;
+                a.sc.fslot[cpos] = slot;
+            } else {
+                a.sc.fslot[cpos] = 0xFFFFFFFFu;
+            }
         }
         __syncwarp();
     }
@@ -1214,9 +1226,9 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
 __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
     DevCtl *ctl = a.ctl;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const uint32_t n_occ = ctl->n_occ[a.parity];
+    const uint32_t n_occ = ctl->n_occ[a.occ_par];
     for (uint32_t k = tid; k < n_occ; k += nth) {
-        const uint32_t p = a.sc.occ[a.parity][k];
+        const uint32_t p = a.sc.occ[a.occ_par][k];
         const uint32_t c = a.ps.cnt[p];
         a.ps.seg[p] = atomicAdd(&ctl->seg_cursor, c);
         /* sparsely occupied nodes go to the thread-per-node kernel, crowded ones to the warp-per-node kernel */
@@ -1225,6 +1237,7 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         else
             a.sc.plist_big[atomicAdd(&ctl->n_big, 1u)] = p;
     }
+    if (a.mg.enabled) return; /* the multi-GPU step recycles heavy slots in k_mg_finish (emigrants, immigrants) */
     /* heavy slots vacated this step go onto the free stack, above what the children did not pop */
     const uint32_t ft = ctl->free_top, births = ctl->n_children, dead = ctl->n_dead;
     const uint32_t popped = births < ft ? births : ft;
@@ -1238,9 +1251,9 @@ __global__ void __launch_bounds__(256) k_scatter(StepArgs a) {
     const uint32_t n = ctl->n_next;
     for (uint32_t j = tid; j < n; j += nth) a.sc.members[a.ps.seg[a.next.loc[j]] + a.sc.fslot[j]] = j;
     /* nodes occupied last step and empty now: census 0, no band cultures (lib.rs:522-525, 614) */
-    const uint32_t n_prev = ctl->n_occ[a.parity ^ 1u];
+    const uint32_t n_prev = ctl->n_occ[a.occ_par ^ 1u];
     for (uint32_t k = tid; k < n_prev; k += nth) {
-        const uint32_t p = a.sc.occ[a.parity ^ 1u][k];
+        const uint32_t p = a.sc.occ[a.occ_par ^ 1u][k];
         if (a.ps.cnt[p] == 0u) {
             a.ps.view[p].pop = 0u;
             a.ps.view[p].nb = 0u;

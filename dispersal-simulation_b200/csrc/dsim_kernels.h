@@ -16,7 +16,9 @@ struct StepArgs {
     StepScratch sc;
     DevCtl *ctl;
     ModelConst mc;
-    uint32_t parity;   /* index of `cur` (0/1); also selects occ[parity] / n_occ[parity] */
+    uint32_t parity;   /* index of `cur` (0/1): ctl->n_cur[parity] families */
+    uint32_t occ_par;  /* occ[occ_par] / n_occ[occ_par] collect this step's occupied nodes, [occ_par ^ 1] hold last step's */
+    MgInfo mg;
     uint32_t children_inline; /* 1: the (cooperative) move kernel also moves the children; 0: k_children does */
     uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
 };
@@ -46,6 +48,10 @@ enum {
 
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_control", "k_move",  "k_children", "k_segments",
                                                             "k_scatter",   "k_patch_small", "k_patch", "k_advance"};
+
+enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,
+       DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH, DSIM_MGK_FINISH2 };
+void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s);
 
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s);
 void dsim_launch_init_views(const PatchState &ps, uint32_t n_nodes, double recovery, const LaunchGeom &g, cudaStream_t s);

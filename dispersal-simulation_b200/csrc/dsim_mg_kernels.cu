@@ -1,0 +1,308 @@
+/*
+ * dsim_mg_kernels.cu — kernels of the band-partitioned multi-GPU step.
+ *
+ * The reference is a single process (no communication layer at all); this is new code.
+ * Every rank holds the static tables with GLOBAL node ids and owns the nodes [own_lo, own_hi) and the
+ * families located there.  Per step three fixed-size, device-resident messages travel between ranks:
+ *   SPLIT      all ranks <-> all ranks: ids of the families that split this step, so that children get
+ *              the same consecutive ids as in a single-GPU run (ids key every random draw);
+ *   EMIGRANTS  rank <-> rank +-1: families whose new node belongs to the neighbour (56-byte record,
+ *              adaptation slots, history ring);
+ *   HALO       rank <-> rank +-1: the 32-byte views (census, quality, band cultures) of the 2S nodes on
+ *              each side of a boundary, S = largest node-id distance in the reach table.
+ * Nothing here depends on the order in which families are stored, so the partitioned run is
+ * bit-identical to the single-GPU run (tests/test_multi_rank.py).
+ */
+#include "dsim_kernels.h"
+#include "dsim_math.h"
+
+/* ---- SPLIT ------------------------------------------------------------------------------------ */
+/* ids of the local families that split, at their local child rank; split_send[0] = count */
+__global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t n = ctl->n_cur[a.parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
+        const uint32_t split_mask = a.sc.split_bits[c];
+        if (!((split_mask >> (i & 31u)) & 1u)) continue;
+        uint32_t vs = 0;
+        for (uint32_t w = c & ~7u; w < c; ++w) vs += (uint32_t)__popc(a.sc.split_bits[w]);
+        const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
+        if (crank < mb.scap)
+            mb.split_send[1 + crank] = a.cur.id[i];
+        else
+            atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) mb.split_send[0] = ctl->n_children;
+}
+
+/* global rank of every local child = number of splitting parents, on any rank, with a smaller id */
+__global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t n_local = ctl->n_children;
+    const size_t stride = 1 + (size_t)mb.scap;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_local; c += gridDim.x * blockDim.x) {
+        const uint64_t id = mb.split_send[1 + c];
+        uint32_t smaller = 0;
+        for (uint32_t r = 0; r < a.mg.world; ++r) {
+            const uint64_t *list = mb.split_recv + r * stride;
+            const uint32_t m = (uint32_t)list[0];
+            for (uint32_t k = 0; k < m; ++k) smaller += list[1 + k] < id ? 1u : 0u;
+        }
+        mb.child_grank[c] = smaller;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t total = 0;
+        for (uint32_t r = 0; r < a.mg.world; ++r) total += mb.split_recv[r * stride];
+        ctl->next_id = ctl->child_id_base + total; /* k_control had added the local count only */
+        mb.counters[MG_N_STAY] = 0;
+        mb.counters[MG_N_EMIG0] = 0;
+        mb.counters[MG_N_EMIG1] = 0;
+        mb.counters[MG_HALO_CULT0] = 0;
+        mb.counters[MG_HALO_CULT1] = 0;
+    }
+}
+
+/* ---- EMIGRANTS -------------------------------------------------------------------------------- */
+/* After part 1 the step's families sit in `next` (survivors + children).  Those whose node is owned stay:
+ * they are copied to `cur` (which part 1 no longer needs) at positions handed out by an atomic counter
+ * — storage order never influences results.  The others are listed per side for k_mg_pack. */
+__global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t n = ctl->n_next;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t loc = a.next.loc[j];
+        if (loc >= a.mg.own_lo && loc < a.mg.own_hi) {
+            const uint32_t p = atomicAdd(&mb.counters[MG_N_STAY], 1u);
+            a.cur.id[p] = a.next.id[j];
+            a.cur.culture[p] = a.next.culture[j];
+            a.cur.stored[p] = a.next.stored[j];
+            a.cur.last_harvest[p] = a.next.last_harvest[j];
+            a.cur.loc[p] = loc;
+            a.cur.size[p] = a.next.size[j];
+            a.cur.till_adult[p] = a.next.till_adult[j];
+            a.cur.till_mut[p] = a.next.till_mut[j];
+            a.cur.misc[p] = a.next.misc[j];
+            a.cur.hs[p] = a.next.hs[j];
+            mb.fslot2[p] = a.sc.fslot[j];
+        } else {
+            const uint32_t side = loc < a.mg.own_lo ? 0u : 1u;
+            const uint32_t e = atomicAdd(&mb.counters[MG_N_EMIG0 + side], 1u);
+            if (e < mb.ecap)
+                mb.emig_list[side * mb.ecap + e] = j;
+            else
+                atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+        }
+    }
+}
+
+/* one warp per emigrant: record + adaptation slots + history (chronological) into the send buffer */
+__global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
+    for (uint32_t side = 0; side < 2u; ++side) {
+        uint32_t m = mb.counters[MG_N_EMIG0 + side];
+        if (m > mb.ecap) m = mb.ecap;
+        unsigned char *buf = mb.emig_send[side];
+        if (gw == 0 && lane == 0) *reinterpret_cast<uint64_t *>(buf) = m;
+        for (uint32_t e = gw; e < m; e += nw) {
+            const uint32_t j = mb.emig_list[side * mb.ecap + e];
+            const uint32_t hs = a.next.hs[j];
+            unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
+            const uint32_t cnt = a.hv.hist_cnt[hs];
+            const uint32_t valid = cnt < hcap ? cnt : hcap;
+            if (lane == 0) {
+                uint64_t *q = reinterpret_cast<uint64_t *>(rec);
+                q[0] = a.next.id[j];
+                q[1] = a.next.culture[j];
+                q[2] = dsim_f64_to_bits(a.next.stored[j]);
+                q[3] = dsim_f64_to_bits(a.next.last_harvest[j]);
+                q[4] = a.hv.parent[hs];
+                uint32_t *w = reinterpret_cast<uint32_t *>(rec + 40);
+                w[0] = a.next.loc[j];
+                w[1] = a.next.size[j];
+                w[2] = a.next.till_adult[j];
+                w[3] = a.next.till_mut[j];
+                w[4] = a.next.misc[j];
+                w[5] = valid;
+                w[6] = a.hv.decay[hs];
+                w[7] = a.hv.birth_index[hs];
+                /* the emigrant's heavy slot is free again: listed behind the slots of the dead */
+                mb.emig_hs[atomicAdd(&mb.counters[MG_N_FREED], 1u)] = hs;
+            }
+            uint16_t *r_eco = reinterpret_cast<uint16_t *>(rec + MG_REC_HDR);
+            uint32_t *r_cnt = reinterpret_cast<uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
+            double *r_val = reinterpret_cast<double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
+            for (uint32_t k = lane; k < acap; k += 32u) {
+                r_eco[k] = a.hv.a_eco[(size_t)hs * acap + k];
+                r_cnt[k] = a.hv.a_cnt[(size_t)hs * acap + k];
+                r_val[k] = a.hv.a_val[(size_t)hs * acap + k];
+            }
+            unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
+            uint32_t *r_hp = reinterpret_cast<uint32_t *>(hist);
+            double *r_hh = reinterpret_cast<double *>(hist + mg_pad8(hcap * 4u));
+            for (uint32_t k = lane; k < valid; k += 32u) { /* chronological k = newest-first valid-1-k */
+                const uint32_t pos = (cnt - 1u - (valid - 1u - k)) % hcap;
+                r_hp[k] = a.hv.hist_patch[(size_t)hs * hcap + pos];
+                r_hh[k] = a.hv.hist_harv[(size_t)hs * hcap + pos];
+            }
+        }
+    }
+}
+
+/* one warp per immigrant: append to `cur`, take a heavy slot, count the arrival */
+__global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
+    const uint32_t n_stay = mb.counters[MG_N_STAY];
+    uint32_t base = 0;
+    for (uint32_t side = 0; side < 2u; ++side) {
+        const unsigned char *buf = mb.emig_recv[side];
+        const uint32_t m = mb.has_peer[side] ? (uint32_t)*reinterpret_cast<const uint64_t *>(buf) : 0u;
+        for (uint32_t e = gw; e < m; e += nw) {
+            const unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
+            const uint32_t p = n_stay + base + e;
+            /* heavy slots: the children popped the first n_children, the immigrants continue */
+            const uint32_t pop = ctl->n_children + base + e, ft = ctl->free_top;
+            const uint32_t hs = (pop < ft) ? a.sc.free_hs[ft - 1u - pop] : ctl->hs_hwm + (pop - ft);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(rec + 40);
+            const uint32_t loc = w[0], valid = w[5];
+            if (p >= ctl->cap || hs >= ctl->hs_cap || loc < a.mg.own_lo || loc >= a.mg.own_hi) {
+                if (lane == 0) atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+                continue;
+            }
+            const uint16_t *r_eco = reinterpret_cast<const uint16_t *>(rec + MG_REC_HDR);
+            const uint32_t *r_cnt = reinterpret_cast<const uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
+            const double *r_val = reinterpret_cast<const double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
+            for (uint32_t k = lane; k < acap; k += 32u) {
+                a.hv.a_eco[(size_t)hs * acap + k] = r_eco[k];
+                a.hv.a_cnt[(size_t)hs * acap + k] = r_cnt[k];
+                a.hv.a_val[(size_t)hs * acap + k] = r_val[k];
+            }
+            const unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
+            const uint32_t *r_hp = reinterpret_cast<const uint32_t *>(hist);
+            const double *r_hh = reinterpret_cast<const double *>(hist + mg_pad8(hcap * 4u));
+            for (uint32_t k = lane; k < valid; k += 32u) {
+                a.hv.hist_patch[(size_t)hs * hcap + k] = r_hp[k];
+                a.hv.hist_harv[(size_t)hs * hcap + k] = r_hh[k];
+            }
+            if (lane == 0) {
+                const uint64_t *q = reinterpret_cast<const uint64_t *>(rec);
+                a.cur.id[p] = q[0];
+                a.cur.culture[p] = q[1];
+                a.cur.stored[p] = dsim_bits_to_f64(q[2]);
+                a.cur.last_harvest[p] = dsim_bits_to_f64(q[3]);
+                a.hv.parent[hs] = q[4];
+                a.cur.loc[p] = loc;
+                a.cur.size[p] = w[1];
+                a.cur.till_adult[p] = w[2];
+                a.cur.till_mut[p] = w[3];
+                a.cur.misc[p] = w[4];
+                a.cur.hs[p] = hs;
+                a.hv.hist_cnt[hs] = valid;
+                a.hv.decay[hs] = w[6];
+                a.hv.birth_index[hs] = (uint16_t)w[7];
+                const uint32_t slot = atomicAdd(&a.ps.cnt[loc], 1u);
+                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = loc;
+                mb.fslot2[p] = slot;
+            }
+        }
+        base += m;
+    }
+    if (gw == 0 && lane == 0) { /* the families of part 2 */
+        ctl->n_next = n_stay + base;
+        mb.counters[MG_N_IMMIG] = base;
+        if (n_stay + base > ctl->cap) ctl->errors |= DSIM_MODEL_CAPACITY;
+    }
+}
+
+/* ---- HALO ------------------------------------------------------------------------------------- */
+/* the views of my boundary strips, with the band cultures they point to packed behind them */
+__global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) {
+    for (uint32_t side = 0; side < 2u; ++side) {
+        if (!mb.has_peer[side]) continue;
+        const uint32_t first = side == 0u ? a.mg.own_lo : a.mg.own_hi - mb.hw;
+        unsigned char *buf = mb.halo_send[side];
+        PatchView *views = reinterpret_cast<PatchView *>(buf + 16);
+        uint64_t *cults = reinterpret_cast<uint64_t *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.hw; k += gridDim.x * blockDim.x) {
+            PatchView v = a.ps.view[first + k];
+            if (v.nb >= 2u) { /* the first culture travels inline */
+                const uint32_t at = atomicAdd(&mb.counters[MG_HALO_CULT0 + side], v.nb);
+                if (at + v.nb <= mb.ccap) {
+                    for (uint32_t b = 0; b < v.nb; ++b) cults[at + b] = a.ps.band_cult[v.stor_off + b];
+                    v.stor_off = DSIM_STOR_HALO | (side << 30) | at; /* relative; the receiver knows the side */
+                } else {
+                    atomicOr(&a.ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+                    v.nb = 1u;
+                }
+            }
+            views[k] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb) {
+    for (uint32_t side = 0; side < 2u; ++side) {
+        if (!mb.has_peer[side]) continue;
+        /* what arrives from the lower neighbour is its UPPER strip: the nodes just below mine */
+        const uint32_t first = side == 0u ? a.mg.own_lo - mb.hw : a.mg.own_hi;
+        const unsigned char *buf = mb.halo_recv[side];
+        const PatchView *views = reinterpret_cast<const PatchView *>(buf + 16);
+        const uint64_t *cults = reinterpret_cast<const uint64_t *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.hw; k += gridDim.x * blockDim.x) {
+            PatchView v = views[k];
+            if (v.stor_off & DSIM_STOR_HALO) v.stor_off = DSIM_STOR_HALO | (side << 30) | (v.stor_off & 0x3FFFFFFFu);
+            a.ps.view[first + k] = v;
+        }
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.ccap; k += gridDim.x * blockDim.x)
+            mb.halo_cult[side][k] = cults[k];
+    }
+}
+
+/* ---- end of step ------------------------------------------------------------------------------ */
+__global__ void k_mg_finish(StepArgs a, MgBuffers mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    /* heavy-slot allocator: children and immigrants popped, the dead and the emigrants are pushed */
+    const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
+    const uint32_t dead = ctl->n_dead, freed = mb.counters[MG_N_FREED];
+    const uint32_t popped = pops < ft ? pops : ft;
+    const uint32_t base = ft - popped;
+    for (uint32_t k = tid; k < dead; k += nth) a.sc.free_hs[base + k] = a.sc.dead_hs[k];
+    for (uint32_t k = tid; k < freed; k += nth) a.sc.free_hs[base + dead + k] = mb.emig_hs[k];
+}
+
+__global__ void k_mg_finish2(StepArgs a, MgBuffers mb) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    DevCtl *ctl = a.ctl;
+    const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
+    const uint32_t popped = pops < ft ? pops : ft;
+    ctl->hs_hwm += pops - popped;
+    ctl->free_top = ft - popped + ctl->n_dead + mb.counters[MG_N_FREED];
+    if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
+    mb.counters[MG_N_FREED] = 0;
+    ctl->n_cur[a.parity] = ctl->n_next; /* part 2 ran in place on `cur`: the buffers do not swap */
+    ctl->t += 1u;
+}
+
+/* ---- launchers -------------------------------------------------------------------------------- */
+void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s) {
+    const uint32_t sm = g.n_sm;
+    switch (which) {
+    case DSIM_MGK_SPLIT_IDS: DSIM_LAUNCH(k_mg_split_ids, sm * 4, 256, 0, s, a, mb); break;
+    case DSIM_MGK_CHILD_RANK: DSIM_LAUNCH(k_mg_child_rank, sm * 2, 256, 0, s, a, mb); break;
+    case DSIM_MGK_SORT_OUT: DSIM_LAUNCH(k_mg_sort_out, sm * 8, 256, 0, s, a, mb); break;
+    case DSIM_MGK_PACK: DSIM_LAUNCH(k_mg_pack, sm * 4, 128, 0, s, a, mb); break;
+    case DSIM_MGK_UNPACK: DSIM_LAUNCH(k_mg_unpack, sm * 4, 128, 0, s, a, mb); break;
+    case DSIM_MGK_HALO_PACK: DSIM_LAUNCH(k_mg_halo_pack, sm * 2, 256, 0, s, a, mb); break;
+    case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm * 2, 256, 0, s, a, mb); break;
+    case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, sm, 256, 0, s, a, mb); break;
+    case DSIM_MGK_FINISH2: DSIM_LAUNCH(k_mg_finish2, 1, 32, 0, s, a, mb); break;
+    default: break;
+    }
+}

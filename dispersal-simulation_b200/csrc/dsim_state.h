@@ -18,6 +18,7 @@
 #define DSIM_ROW_HASH_MAX 192u
 #define DSIM_NIDX_NONE 0xFFFFu   /* reach entry that is not in the 2-hop `nearby` list */
 #define DSIM_ECO_EMPTY 0xFFFFu   /* free adaptation slot */
+#define DSIM_STOR_HALO 0x80000000u /* PatchView.stor_off: bit 31 = cultures live in halo_cult[bit 30] (multi-GPU) */
 #define DSIM_MISC_CLOCK 0x10000u /* misc bit 16: seasons_till_next_mutation is Some(..) */
 
 struct FamCore {            /* one column per field, index = position in the family vector */
@@ -140,6 +141,41 @@ struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed
     uint32_t k0, k1;         /* Philox key = seed                                                  */
     const uint32_t *mem_thr; /* [n_mem] history entry n is kept iff its 32-bit draw <= mem_thr[n], i.e. iff
                                 draw * 2^-32 < memory after n decays (lib.rs:847-864)                */
+};
+
+/* ---- multi-GPU (band partition, dsim_mg_kernels.cu) ------------------------------------------------ */
+struct MgInfo {              /* part of StepArgs */
+    uint32_t enabled, rank, world;
+    uint32_t own_lo, own_hi; /* this rank owns the nodes [own_lo, own_hi) and the families located there */
+    const uint32_t *child_grank;  /* [scap] rank of local child c among all children of the step, all ranks */
+    const uint64_t *halo_cult[2]; /* band cultures of the halo views received from the lower / upper neighbour */
+};
+
+enum { MG_N_STAY = 0, MG_N_EMIG0, MG_N_EMIG1, MG_N_IMMIG, MG_N_FREED, MG_HALO_CULT0, MG_HALO_CULT1, MG_N_COUNTERS = 8 };
+#define MG_REC_HDR 72u /* emigrant record: 5 x u64 + 8 x u32, then adaptation slots, then history */
+#if defined(__CUDACC__)
+#define DSIM_HD_INLINE __host__ __device__ inline
+#else
+#define DSIM_HD_INLINE inline
+#endif
+DSIM_HD_INLINE uint32_t mg_pad8(uint32_t b) { return (b + 7u) & ~7u; }
+DSIM_HD_INLINE uint32_t mg_rec_bytes(uint32_t acap, uint32_t hcap) {
+    return (MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u + mg_pad8(hcap * 4u) + hcap * 8u + 15u) & ~15u;
+}
+
+struct MgBuffers {           /* device buffers of one rank; messages have a 16-byte header (count) */
+    uint64_t *split_send;    /* [1 + scap]: count, ids of the local families that split this step       */
+    uint64_t *split_recv;    /* [world][1 + scap]                                                      */
+    uint32_t *child_grank;   /* [scap]                                                                 */
+    uint32_t *counters;      /* [MG_N_COUNTERS]                                                        */
+    uint32_t *emig_list;     /* [2][ecap] positions (in `next`) of the emigrants per side              */
+    uint32_t *emig_hs;       /* [2 * ecap] heavy slots given up by emigrants this step                 */
+    uint32_t *fslot2;        /* [cap] arrival rank, indexed like the re-packed family buffer           */
+    unsigned char *emig_send[2], *emig_recv[2]; /* [16 + ecap * rec_bytes], side 0 = lower neighbour   */
+    unsigned char *halo_send[2], *halo_recv[2]; /* [16 + hw * 32 + ccap * 8]                           */
+    uint64_t *halo_cult[2];  /* [ccap]                                                                 */
+    uint32_t has_peer[2];
+    uint32_t scap, ecap, rec_bytes, hw, ccap;
 };
 
 #endif

@@ -280,6 +280,15 @@ class Sim:
             "profile_read": (C.c_int, [vp, C.POINTER(KernelTimes), C.c_int]),
             "launch_count": (C.c_int, [vp, u64p]),
             "step_timed": (C.c_int, [vp, C.c_uint32, C.POINTER(StepStats), f64p]),
+            "mg_configure": (C.c_int, [vp, C.c_uint32, C.c_uint32, u32p]),
+            "mg_halo_width": (C.c_int, [vp, u32p]),
+            "mg_phase": (C.c_int, [vp, C.c_int]),
+            "mg_buffer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), u64p]),
+            "mg_memcpy": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_uint64]),
+            "mg_unique_id": (C.c_int, [C.c_void_p]),
+            "mg_init_nccl": (C.c_int, [vp, C.c_void_p]),
+            "mg_halo_sync": (C.c_int, [vp]),
+            "mg_reduce_stats": (C.c_int, [vp, C.POINTER(StepStats)]),
         }.items():
             if hasattr(self.lib, self.prefix + name):
                 fn = self._f(name)
@@ -408,6 +417,38 @@ class Sim:
                                          _ptr(reach_cost, C.c_double)))
         return near_off, near_dst[:a.value], reach_off, reach_dst[:b.value], reach_cost[:b.value]
 
+    # -- multi-GPU (band partition; include/dsim.h) ---------------------------------------------
+    def mg_configure(self, rank: int, world: int, bounds):
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        assert len(b) == world + 1
+        self._check(self._f("mg_configure")(self.h, rank, world, _ptr(b, C.c_uint32)))
+        self.mg_rank, self.mg_world, self.mg_bounds = rank, world, b
+
+    def mg_halo_width(self) -> int:
+        w = C.c_uint32()
+        self._check(self._f("mg_halo_width")(self.h, C.byref(w)))
+        return w.value
+
+    def mg_phase(self, phase: int):
+        self._check(self._f("mg_phase")(self.h, phase))
+
+    def mg_buffer(self, channel: int, peer: int, recv: bool):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._f("mg_buffer")(self.h, channel, peer, 1 if recv else 0, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def mg_memcpy(self, dst, src, nbytes):
+        self._check(self._f("mg_memcpy")(self.h, dst, src, nbytes))
+
+    def mg_init_nccl(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self._f("mg_init_nccl")(self.h, buf))
+        self._check(self._f("mg_halo_sync")(self.h))
+
+    def mg_reduce_stats(self, st: "StepStats"):
+        self._check(self._f("mg_reduce_stats")(self.h, C.byref(st)))
+        return st
+
     # -- measurement ------------------------------------------------------------------------
     def profile_enable(self, on: bool):
         self._check(self._f("profile_enable")(self.h, 1 if on else 0))
@@ -459,3 +500,76 @@ def synth_families(W: int, H: int, n: int, seed: int = 1, n_occupied: int = 0, h
     f.hist_patch, f.hist_harvest = f.hist_patch[:n * hist_fill], f.hist_harvest[:n * hist_fill]
     f.adapt_eco, f.adapt_val = f.adapt_eco[:0], f.adapt_val[:0]
     return f
+
+
+MG_PHASE_LIFECYCLE, MG_PHASE_MOVE, MG_PHASE_PATCH, MG_PHASE_FINISH, MG_PHASE_HALO_PACK, MG_PHASE_HALO_UNPACK = range(6)
+MG_CH_SPLIT, MG_CH_EMIGRANTS, MG_CH_HALO = range(3)
+
+
+def mg_unique_id(lib: C.CDLL) -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib.dsim_mg_unique_id(buf)
+    if rc != 0:
+        raise DsimError(rc, "dsim_mg_unique_id failed")
+    return buf.raw
+
+
+def mg_band_bounds(location: np.ndarray, n_nodes: int, world: int, halo_width: int) -> np.ndarray:
+    """Node boundaries of `world` contiguous bands holding about the same number of families each
+    (equal family counts rather than equal node counts), every band >= halo_width nodes."""
+    loc = np.sort(np.asarray(location, dtype=np.int64))
+    b = [0]
+    for r in range(1, world):
+        q = int(loc[min(len(loc) - 1, (len(loc) * r) // world)]) if len(loc) else (n_nodes * r) // world
+        q = max(q, b[-1] + halo_width)
+        q = min(q, n_nodes - (world - r) * halo_width)
+        b.append(q)
+    b.append(n_nodes)
+    out = np.array(b, dtype=np.uint32)
+    if (np.diff(out.astype(np.int64)) < halo_width).any():
+        raise ValueError("grid too small for that many bands")
+    return out
+
+
+def mg_exchange_in_process(sims, channel):
+    """Move the messages of one channel between handles that live in this process ("virtual ranks")."""
+    world = len(sims)
+    if channel == MG_CH_SPLIT:
+        for src in sims:
+            sp, nb = src.mg_buffer(channel, 0, False)
+            for dst in sims:
+                dp, _ = dst.mg_buffer(channel, src.mg_rank, True)
+                dst.mg_memcpy(dp, sp, nb)
+        return
+    for r, s in enumerate(sims):
+        if r + 1 < world:   # up: my upper send buffer -> the upper neighbour's lower recv buffer
+            sp, nb = s.mg_buffer(channel, 1, False)
+            dp, _ = sims[r + 1].mg_buffer(channel, 0, True)
+            sims[r + 1].mg_memcpy(dp, sp, nb)
+        if r > 0:           # down
+            sp, nb = s.mg_buffer(channel, 0, False)
+            dp, _ = sims[r - 1].mg_buffer(channel, 1, True)
+            sims[r - 1].mg_memcpy(dp, sp, nb)
+
+
+def mg_step_in_process(sims):
+    """One season on virtual ranks: the four phases with the three exchanges in between."""
+    for s in sims:
+        s.mg_phase(MG_PHASE_LIFECYCLE)
+    mg_exchange_in_process(sims, MG_CH_SPLIT)
+    for s in sims:
+        s.mg_phase(MG_PHASE_MOVE)
+    mg_exchange_in_process(sims, MG_CH_EMIGRANTS)
+    for s in sims:
+        s.mg_phase(MG_PHASE_PATCH)
+    mg_exchange_in_process(sims, MG_CH_HALO)
+    for s in sims:
+        s.mg_phase(MG_PHASE_FINISH)
+
+
+def mg_halo_sync_in_process(sims):
+    for s in sims:
+        s.mg_phase(MG_PHASE_HALO_PACK)
+    mg_exchange_in_process(sims, MG_CH_HALO)
+    for s in sims:
+        s.mg_phase(MG_PHASE_HALO_UNPACK)

@@ -196,6 +196,34 @@ int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach);
 int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst,
                    uint64_t *reach_off, uint32_t *reach_dst, double *reach_cost);
 
+/* ---- multi-GPU: one handle per GPU / process, contiguous node ranges ("bands") per rank ------------------------
+ * New functionality (the reference is a single process).  Rank r owns the nodes [bounds[r], bounds[r+1]) and the
+ * families located there; every rank is created with the full graph.  dsim_set_patches / dsim_set_storage take full
+ * arrays, dsim_set_families takes the full family vector and keeps the families of the own band.  Getters return
+ * the local part (families: the own ones, in no particular order; patches / storage: only the own nodes are valid).
+ * Results are bit-identical to a single-GPU run.  Every band must hold at least dsim_mg_halo_width() nodes.
+ *
+ * A step is four phases with one message exchange after each of the first three:
+ *   LIFECYCLE -> SPLIT allgather -> MOVE -> EMIGRANTS neighbour exchange -> PATCH -> HALO neighbour exchange -> FINISH.
+ * With dsim_mg_init_nccl the library moves the messages itself (NCCL on its stream) and dsim_step works as on one
+ * GPU; without it the caller drives dsim_mg_phase and moves the channel buffers (tests: "virtual ranks"). */
+enum { DSIM_MG_PHASE_LIFECYCLE = 0, DSIM_MG_PHASE_MOVE = 1, DSIM_MG_PHASE_PATCH = 2, DSIM_MG_PHASE_FINISH = 3,
+       DSIM_MG_PHASE_HALO_PACK = 4, DSIM_MG_PHASE_HALO_UNPACK = 5 /* 4,5: initial halo after the state was set */ };
+enum { DSIM_MG_CH_SPLIT = 0, DSIM_MG_CH_EMIGRANTS = 1, DSIM_MG_CH_HALO = 2 };
+int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint32_t *bounds /* [world + 1] */);
+int dsim_mg_halo_width(dsim_handle *h, uint32_t *nodes);
+int dsim_mg_phase(dsim_handle *h, int phase);
+/* Device buffers of a channel.  SPLIT: send = this rank's list, recv = slot `peer` (a rank) of the gathered lists.
+ * EMIGRANTS / HALO: peer 0 = lower neighbour (rank-1), 1 = upper neighbour (rank+1); what a rank sends to its upper
+ * neighbour arrives in that neighbour's recv buffer of peer 0.  Messages have a fixed size (*bytes). */
+int dsim_mg_buffer(dsim_handle *h, int channel, int peer, int recv, void **dev_ptr, uint64_t *bytes);
+int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes); /* device-to-device copy helper */
+#define DSIM_MG_UNIQUE_ID_BYTES 128
+int dsim_mg_unique_id(void *out /* DSIM_MG_UNIQUE_ID_BYTES, rank 0 creates and broadcasts it */);
+int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
+/* Sums the per-rank counters of a dsim_step_stats over all ranks (NCCL transport only). */
+int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
+
 /* Kernel-level timing for bench.py: device time in ms of each kernel class accumulated since the
  * last reset, measured with CUDA events on the internal stream (only while enabled; this
  * serialises the step and is off by default).  names[i] are static strings. */
