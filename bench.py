@@ -187,6 +187,7 @@ def algorithmic_bytes(sim, fam_hist_len, mem_table, rho_src):
 
 
 def main():
+    os.environ["NCCL_DEBUG"] = os.environ.get("DSIM_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -230,6 +231,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    os.environ.setdefault("DSIM_HOST_THREADS", str(max(1, len(os.sched_getaffinity(0)) // world)))
     lib = D.load()
     synth = D.load_synth()
     # N > 1: weak scaling — 100k x N families on the same Americas-scale grid, split into N latitude bands of
@@ -278,6 +280,10 @@ def main():
     else:
         dev_ms_all, updates_all = dev_ms, float(st.family_updates)
     value = updates_all / (dev_ms_all * 1e-3)
+    if world > 1:
+        dbg = (C.c_uint32 * 8)()
+        lib.dsim_mg_debug_counters(sim.h, dbg)
+        log(f"[bench] rank {rank}: most emigrants per neighbour and step {dbg[7]}")
     log(f"[bench] rank {rank}: {args.steps} steps in {dev_ms:.2f} ms, live {st.live_families}, "
         f"births {st.births}, deaths {st.deaths}, errors {st.model_errors}")
 

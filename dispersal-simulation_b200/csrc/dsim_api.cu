@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -1392,8 +1393,10 @@ struct dsim_mg_state {
     uint32_t occ_par = 0;
 #if !defined(DSIM_EMU)
     ncclComm_t comm = nullptr;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 #endif
-    bool nccl = false;
+    bool nccl = false, graph_failed = false;
+    uint64_t launches_per_step = 0;
 };
 
 namespace {
@@ -1466,7 +1469,8 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
     mb.has_peer[0] = rank > 0 ? 1u : 0u;
     mb.has_peer[1] = rank + 1 < world ? 1u : 0u;
     mb.scap = (uint32_t)std::max<uint64_t>(1024, h->cap / 8);
-    mb.ecap = (uint32_t)std::max<uint64_t>(256, std::min<uint64_t>(h->cap / 16, 2048));
+    mb.ecap = (uint32_t)std::max<uint64_t>(256, std::min<uint64_t>(h->cap / 64, 1024));
+    if (const char *e = std::getenv("DSIM_MG_EMIGRANT_SLOTS")) mb.ecap = (uint32_t)std::max(16, std::atoi(e));
     mb.rec_bytes = mg_rec_bytes(h->acap, h->hcap);
     mb.hw = hw;
     mb.ccap = std::max<uint32_t>(1024u, hw / 2u);
@@ -1552,8 +1556,6 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         break;
     case DSIM_MG_PHASE_FINISH:
         M(DSIM_MGK_HALO_UNPACK, a2); M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2);
-        m->occ_par ^= 1u;
-        h->mg_occ_prev = m->occ_par ^ 1u;
         break;
     case DSIM_MG_PHASE_HALO_PACK:
         CK(cudaMemsetAsync(mb.counters, 0, MG_N_COUNTERS * sizeof(uint32_t), h->stream));
@@ -1574,6 +1576,10 @@ int dsim_mg_phase(dsim_handle *h, int phase) {
     h->snap_valid = false;
     int rc = mg_launch_phase(h, m, phase);
     if (rc) return rc;
+    if (phase == DSIM_MG_PHASE_FINISH) { /* the occupied-node lists swap roles */
+        m->occ_par ^= 1u;
+        h->mg_occ_prev = m->occ_par ^ 1u;
+    }
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
 }
@@ -1639,14 +1645,8 @@ static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel) {
 }
 #endif
 
-/* one full multi-GPU step with the built-in transport; everything is enqueued, nothing waits on the host */
-int dsim_mg_step_enqueue(dsim_handle *h) {
-    dsim_mg_state *m = h ? mg_of(h) : nullptr;
-    if (!m) return DSIM_ERR_INVALID;
-#if defined(DSIM_EMU)
-    return fail(h, DSIM_ERR_COMM, "no transport: drive dsim_mg_phase yourself");
-#else
-    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or drive dsim_mg_phase yourself");
+#if !defined(DSIM_EMU)
+static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
     int rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
     if ((rc = mg_exchange(h, m, DSIM_MG_CH_SPLIT))) return rc;
@@ -1655,6 +1655,50 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
     if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO))) return rc;
     return mg_launch_phase(h, m, DSIM_MG_PHASE_FINISH);
+}
+#endif
+
+/* one full multi-GPU step with the built-in transport; everything is enqueued, nothing waits on the host.
+ * The 17 kernels and 3 NCCL operations of a step are captured once per occupied-list parity and replayed. */
+int dsim_mg_step_enqueue(dsim_handle *h) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no transport: drive dsim_mg_phase yourself");
+#else
+    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or drive dsim_mg_phase yourself");
+    int rc = DSIM_OK;
+    if (h->opt.use_graphs && !m->graph_failed) {
+        if (!m->gexec[m->occ_par]) {
+            cudaGraph_t g = nullptr;
+            const uint64_t launches0 = h->total_launches;
+            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                rc = mg_enqueue_step(h, m);
+                ok = cudaStreamEndCapture(h->stream, &g) == cudaSuccess && rc == DSIM_OK && g != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&m->gexec[m->occ_par], g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            m->launches_per_step = h->total_launches - launches0;
+            h->total_launches = launches0;
+            if (!ok) { /* fall back to plain launches for the rest of the run */
+                (void)cudaGetLastError();
+                m->gexec[m->occ_par] = nullptr;
+                m->graph_failed = true;
+            }
+        }
+        if (m->gexec[m->occ_par]) {
+            CK(cudaGraphLaunch(m->gexec[m->occ_par], h->stream));
+            h->total_launches += m->launches_per_step;
+            m->occ_par ^= 1u;
+            h->mg_occ_prev = m->occ_par ^ 1u;
+            return DSIM_OK;
+        }
+    }
+    if ((rc = mg_enqueue_step(h, m))) return rc;
+    m->occ_par ^= 1u;
+    h->mg_occ_prev = m->occ_par ^ 1u;
+    return DSIM_OK;
 #endif
 }
 
@@ -1699,10 +1743,22 @@ int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats) {
 #endif
 }
 
+/* diagnostics: the MG_* counters of the last step (MG_MAX_EMIG = most emigrants per side and step so far) */
+int dsim_mg_debug_counters(dsim_handle *h, uint32_t *out8) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !out8) return DSIM_ERR_INVALID;
+    int rc = download(h, out8, m->mb.counters, MG_N_COUNTERS);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DSIM_OK;
+}
+
 void dsim_mg_release(dsim_handle *h) {
     dsim_mg_state *m = mg_of(h);
     if (!m) return;
 #if !defined(DSIM_EMU)
+    for (auto &g : m->gexec)
+        if (g) cudaGraphExecDestroy(g);
     if (m->comm) ncclCommDestroy(m->comm);
 #endif
     free_list(m->allocs);

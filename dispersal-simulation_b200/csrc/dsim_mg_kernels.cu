@@ -106,7 +106,10 @@ __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
         uint32_t m = mb.counters[MG_N_EMIG0 + side];
         if (m > mb.ecap) m = mb.ecap;
         unsigned char *buf = mb.emig_send[side];
-        if (gw == 0 && lane == 0) *reinterpret_cast<uint64_t *>(buf) = m;
+        if (gw == 0 && lane == 0) {
+            *reinterpret_cast<uint64_t *>(buf) = m;
+            atomicMax(&mb.counters[MG_MAX_EMIG], mb.counters[MG_N_EMIG0 + side]);
+        }
         for (uint32_t e = gw; e < m; e += nw) {
             const uint32_t j = mb.emig_list[side * mb.ecap + e];
             const uint32_t hs = a.next.hs[j];

@@ -17,6 +17,9 @@
 #include <limits>
 #include <queue>
 #include <utility>
+#include <cstdlib>
+#include <thread>
+#include <omp.h>
 
 namespace {
 
@@ -119,8 +122,20 @@ void nearby_of(const dsim_graph *g, uint32_t node, std::vector<uint32_t> &out) {
 
 } // namespace
 
+/* host threads for the one-time table build: DSIM_HOST_THREADS, else all hardware threads (launchers such
+ * as torchrun export OMP_NUM_THREADS=1, which would make this step 16x slower for no reason) */
+static int host_threads() {
+    if (const char *e = std::getenv("DSIM_HOST_THREADS")) {
+        const int k = std::atoi(e);
+        if (k > 0) return k;
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
 int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
     const uint32_t n = g->n_nodes;
+    omp_set_num_threads(host_threads());
     const uint32_t kChunk = 2048;
     const uint32_t n_chunks = (n + kChunk - 1) / kChunk;
     struct Chunk {

@@ -151,7 +151,7 @@ struct MgInfo {              /* part of StepArgs */
     const uint64_t *halo_cult[2]; /* band cultures of the halo views received from the lower / upper neighbour */
 };
 
-enum { MG_N_STAY = 0, MG_N_EMIG0, MG_N_EMIG1, MG_N_IMMIG, MG_N_FREED, MG_HALO_CULT0, MG_HALO_CULT1, MG_N_COUNTERS = 8 };
+enum { MG_N_STAY = 0, MG_N_EMIG0, MG_N_EMIG1, MG_N_IMMIG, MG_N_FREED, MG_HALO_CULT0, MG_HALO_CULT1, MG_MAX_EMIG /* high-water mark of emigrants per side and step */, MG_N_COUNTERS = 8 };
 #define MG_REC_HDR 72u /* emigrant record: 5 x u64 + 8 x u32, then adaptation slots, then history */
 #if defined(__CUDACC__)
 #define DSIM_HD_INLINE __host__ __device__ inline

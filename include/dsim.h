@@ -223,6 +223,9 @@ int dsim_mg_unique_id(void *out /* DSIM_MG_UNIQUE_ID_BYTES, rank 0 creates and b
 int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
 /* Sums the per-rank counters of a dsim_step_stats over all ranks (NCCL transport only). */
 int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
+/* Diagnostics: internal per-step counters; out8[7] = most emigrants per neighbour and step seen so far. */
+int dsim_mg_debug_counters(dsim_handle *h, uint32_t *out8);
+int dsim_mg_halo_sync(dsim_handle *h); /* NCCL transport: initial halo exchange after the state was set on every rank */
 
 /* Kernel-level timing for bench.py: device time in ms of each kernel class accumulated since the
  * last reset, measured with CUDA events on the internal stream (only while enabled; this
