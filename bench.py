@@ -291,6 +291,16 @@ def main():
     roofline, kernels = None, {}
     fam_live = st.live_families
     occ = max(1, st.occupied_patches)
+    mg_segments = None
+    if args.profile_steps > 0 and world > 1:
+        sim.profile_enable(True)
+        sim.step(args.profile_steps, want_stats=True, allow_model_errors=True)
+        sim.profile_enable(False)
+        seg = (C.c_double * 7)()
+        lib.dsim_mg_segment_times(sim.h, seg)
+        mg_segments = dict(zip(["lifecycle", "split_exchange", "move", "emigrant_exchange", "patch", "halo_exchange", "finish"],
+                               [round(x, 4) for x in seg]))
+        log(f"[bench] rank {rank}: multi-GPU step segments (ms): {mg_segments}")
     if args.profile_steps > 0 and world == 1:
         sim.profile_enable(True)
         sim.profile_read(reset=True)
@@ -370,6 +380,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "kernels": kernels,
+            "mg_segments_ms": mg_segments,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches2 - launches1),

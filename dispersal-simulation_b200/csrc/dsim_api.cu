@@ -242,6 +242,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
         CP(nh.birth_index, h->hv.birth_index, old_hs, uint16_t)
         CP(ns.free_hs, h->sc.free_hs, old_hs, uint32_t)
         CP(ns.occ[0], h->sc.occ[0], old_cap, uint32_t) CP(ns.occ[1], h->sc.occ[1], old_cap, uint32_t)
+        CP(ns.members, h->sc.members, old_cap, uint32_t) /* the visiting order of the next k_move */
         /* band cultures: [0, old_cap) written by k_patch, [old_cap, 2 old_cap) uploaded by dsim_set_storage; the
          * views hold absolute offsets, so both halves keep their positions */
         CP(new_band_cult, h->ps.band_cult, 2 * old_cap, uint64_t) CP(new_band_size, h->ps.band_size, 2 * old_cap, uint32_t)
@@ -909,6 +910,8 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     ctl.cap = (uint32_t)h->cap;
     ctl.hs_cap = (uint32_t)h->hs_cap;
     if ((rc = push_ctl(h))) return rc;
+    dsim_launch_iota(h->sc.members, (uint32_t)n, h->geom, h->stream); /* visiting order of the first k_move */
+    h->total_launches += 1;
     h->n_known = n;
     h->steps_since_check = 0;
     h->timed_births0 = h->timed_deaths0 = h->timed_updates0 = 0;
@@ -1396,6 +1399,9 @@ struct dsim_mg_state {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 #endif
     bool nccl = false, graph_failed = false;
+    cudaEvent_t seg_ev[8] = {};
+    double seg_ms[7] = {};
+    uint64_t seg_steps = 0;
     uint64_t launches_per_step = 0;
 };
 
@@ -1551,7 +1557,16 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
         break;
     case DSIM_MG_PHASE_PATCH:
-        M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2); K(DSIM_K_PATCH_SMALL, a2); K(DSIM_K_PATCH, a2);
+        M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2);
+        /* the two patch kernels work on disjoint nodes: run them concurrently (second stream, also inside a capture) */
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        K(DSIM_K_PATCH_SMALL, a2);
+        dsim_launch_kernel(DSIM_K_PATCH, a2, h->geom, h->stream2);
+        h->k_launches[DSIM_K_PATCH] += 1;
+        h->total_launches += 1;
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         M(DSIM_MGK_HALO_PACK, a2);
         break;
     case DSIM_MG_PHASE_FINISH:
@@ -1608,6 +1623,7 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
     ncclUniqueId id;
     std::memcpy(&id, unique_id, sizeof id);
     if (ncclCommInitRank(&m->comm, (int)m->world, id, (int)m->rank) != ncclSuccess) return fail(h, DSIM_ERR_COMM, "ncclCommInitRank failed");
+    for (auto &e : m->seg_ev) CK(cudaEventCreate(&e));
     m->nccl = true;
     return DSIM_OK;
 #endif
@@ -1668,7 +1684,7 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
 #else
     if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or drive dsim_mg_phase yourself");
     int rc = DSIM_OK;
-    if (h->opt.use_graphs && !m->graph_failed) {
+    if (h->opt.use_graphs && !m->graph_failed && !h->profiling) {
         if (!m->gexec[m->occ_par]) {
             cudaGraph_t g = nullptr;
             const uint64_t launches0 = h->total_launches;
@@ -1695,11 +1711,38 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
             return DSIM_OK;
         }
     }
-    if ((rc = mg_enqueue_step(h, m))) return rc;
+    if (h->profiling) { /* per-segment device times (dsim_profile_enable): plain launches, one sync per step */
+        static const int seq[7] = {DSIM_MG_PHASE_LIFECYCLE, -1 - DSIM_MG_CH_SPLIT, DSIM_MG_PHASE_MOVE, -1 - DSIM_MG_CH_EMIGRANTS,
+                                   DSIM_MG_PHASE_PATCH, -1 - DSIM_MG_CH_HALO, DSIM_MG_PHASE_FINISH};
+        for (int k = 0; k < 7; ++k) {
+            CK(cudaEventRecord(m->seg_ev[k], h->stream));
+            rc = seq[k] >= 0 ? mg_launch_phase(h, m, seq[k]) : mg_exchange(h, m, -1 - seq[k]);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(m->seg_ev[7], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < 7; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, m->seg_ev[k], m->seg_ev[k + 1]));
+            m->seg_ms[k] += ms;
+        }
+        m->seg_steps += 1;
+    } else if ((rc = mg_enqueue_step(h, m))) {
+        return rc;
+    }
     m->occ_par ^= 1u;
     h->mg_occ_prev = m->occ_par ^ 1u;
     return DSIM_OK;
 #endif
+}
+
+/* diagnostics: mean device milliseconds of the seven segments of a multi-GPU step measured while profiling was on
+ * (lifecycle, SPLIT exchange, move, EMIGRANTS exchange, patch, HALO exchange, finish) */
+int dsim_mg_segment_times(dsim_handle *h, double *out7) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !out7) return DSIM_ERR_INVALID;
+    for (int k = 0; k < 7; ++k) out7[k] = m->seg_steps ? m->seg_ms[k] / (double)m->seg_steps : 0.0;
+    return DSIM_OK;
 }
 
 int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set on every rank */

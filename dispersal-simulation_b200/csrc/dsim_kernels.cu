@@ -957,7 +957,11 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
     for (uint32_t k = threadIdx.x; k < ((a.mc.n_mem + 7u) & ~7u); k += blockDim.x) thr[k] = k < a.mc.n_mem ? a.mc.mem_thr[k] : 0u;
     __syncthreads();
 
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        /* Families are visited in the patch-grouped order that part 2 of the previous step left in
+         * `members`: co-resident families (same reach row, same candidate views) sit in adjacent lanes, so
+         * their loads fall into the same L1 wavefronts.  The order never influences results. */
+        const uint32_t i = a.sc.members[t];
         const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
         /* ---- ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) ------------------- */
         const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
@@ -1819,6 +1823,10 @@ __global__ void k_census(PatchState ps, FamCore f, uint32_t n, uint32_t *occ, De
     }
 }
 
+__global__ void k_iota(uint32_t *v, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
 __global__ void k_reset_cnt(PatchState ps, const uint32_t *occ, const DevCtl *ctl, uint32_t parity) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n = ctl->n_occ[parity];
@@ -1859,6 +1867,10 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;
     }
+}
+
+void dsim_launch_iota(uint32_t *v, uint32_t n, const LaunchGeom &g, cudaStream_t s) {
+    DSIM_LAUNCH(k_iota, grid_for(g, 4), 256, 0, s, v, n);
 }
 
 void dsim_launch_init_views(const PatchState &ps, uint32_t n_nodes, double recovery, const LaunchGeom &g, cudaStream_t s) {

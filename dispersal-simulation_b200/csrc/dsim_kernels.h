@@ -54,6 +54,7 @@ enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_
 void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s);
 
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s);
+void dsim_launch_iota(uint32_t *v, uint32_t n, const LaunchGeom &g, cudaStream_t s);
 void dsim_launch_init_views(const PatchState &ps, uint32_t n_nodes, double recovery, const LaunchGeom &g, cudaStream_t s);
 void dsim_launch_census(const PatchState &ps, const FamCore &f, uint32_t n, uint32_t n_nodes, uint32_t *occ, DevCtl *ctl,
                         uint32_t parity, const LaunchGeom &g, cudaStream_t s);

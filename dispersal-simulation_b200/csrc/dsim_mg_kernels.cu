@@ -36,20 +36,28 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
     if (blockIdx.x == 0 && threadIdx.x == 0) mb.split_send[0] = ctl->n_children;
 }
 
-/* global rank of every local child = number of splitting parents, on any rank, with a smaller id */
+/* global rank of every local child = number of splitting parents, on any rank, with a smaller id.
+ * One warp per child: the lanes stride over the gathered lists. */
 __global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
     const uint32_t n_local = ctl->n_children;
     const size_t stride = 1 + (size_t)mb.scap;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_local; c += gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t c = gw; c < n_local; c += nw) {
         const uint64_t id = mb.split_send[1 + c];
         uint32_t smaller = 0;
         for (uint32_t r = 0; r < a.mg.world; ++r) {
             const uint64_t *list = mb.split_recv + r * stride;
             const uint32_t m = (uint32_t)list[0];
-            for (uint32_t k = 0; k < m; ++k) smaller += list[1 + k] < id ? 1u : 0u;
+            for (uint32_t k = lane; k < m; k += 32u) smaller += list[1 + k] < id ? 1u : 0u;
         }
-        mb.child_grank[c] = smaller;
+        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 16);
+        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 8);
+        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 4);
+        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 2);
+        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 1);
+        if (lane == 0) mb.child_grank[c] = smaller;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t total = 0;
@@ -70,10 +78,19 @@ __global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb)
 __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
     const uint32_t n = ctl->n_next;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t loc = a.next.loc[j];
-        if (loc >= a.mg.own_lo && loc < a.mg.own_hi) {
-            const uint32_t p = atomicAdd(&mb.counters[MG_N_STAY], 1u);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_round = (n + 31u) & ~31u; /* whole warps take part in the ballots */
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        const bool in = j < n;
+        const uint32_t loc = in ? a.next.loc[j] : 0u;
+        const bool stay = in && loc >= a.mg.own_lo && loc < a.mg.own_hi;
+        /* one atomic per warp for the families that stay */
+        const uint32_t m = __ballot_sync(DSIM_FULL, stay);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&mb.counters[MG_N_STAY], (uint32_t)__popc(m));
+        base = __shfl_sync(DSIM_FULL, base, 0);
+        if (stay) {
+            const uint32_t p = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
             a.cur.id[p] = a.next.id[j];
             a.cur.culture[p] = a.next.culture[j];
             a.cur.stored[p] = a.next.stored[j];
@@ -85,7 +102,7 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
             a.cur.misc[p] = a.next.misc[j];
             a.cur.hs[p] = a.next.hs[j];
             mb.fslot2[p] = a.sc.fslot[j];
-        } else {
+        } else if (in) {
             const uint32_t side = loc < a.mg.own_lo ? 0u : 1u;
             const uint32_t e = atomicAdd(&mb.counters[MG_N_EMIG0 + side], 1u);
             if (e < mb.ecap)

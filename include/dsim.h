@@ -225,6 +225,7 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
 int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
 /* Diagnostics: internal per-step counters; out8[7] = most emigrants per neighbour and step seen so far. */
 int dsim_mg_debug_counters(dsim_handle *h, uint32_t *out8);
+int dsim_mg_segment_times(dsim_handle *h, double *out7); /* mean ms of lifecycle, SPLIT, move, EMIGRANTS, patch, HALO, finish while profiling */
 int dsim_mg_halo_sync(dsim_handle *h); /* NCCL transport: initial halo exchange after the state was set on every rank */
 
 /* Kernel-level timing for bench.py: device time in ms of each kernel class accumulated since the
