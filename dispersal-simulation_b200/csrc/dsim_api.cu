@@ -465,12 +465,13 @@ __global__ void k_pack_storage(PatchState ps, const uint32_t *nodes, const uint6
     for (uint32_t k = tid; k < n; k += nth) {
         const uint32_t p = nodes[k];
         const PatchView v = ps.view[p];
+        const uint32_t stor_off = ps.bands[p].stor_off;
         if (out_nb) out_nb[k] = v.nb;
         if (off)
             for (uint32_t b = 0; b < v.nb; ++b) {
                 out_node[off[k] + b] = p;
-                out_cult[off[k] + b] = ps.band_cult[v.stor_off + b];
-                out_size[off[k] + b] = ps.band_size[v.stor_off + b];
+                out_cult[off[k] + b] = ps.band_cult[stor_off + b];
+                out_size[off[k] + b] = ps.band_size[stor_off + b];
             }
     }
 }
@@ -481,8 +482,8 @@ __global__ void k_apply_storage(PatchState ps, const uint32_t *nodes, const uint
     for (uint32_t k = tid; k < n; k += nth) {
         const uint32_t p = nodes[k];
         ps.view[p].nb = count[k];
-        ps.view[p].stor_off = base + first[k];
-        ps.view[p].cult0 = ps.band_cult[base + first[k]];
+        ps.bands[p].stor_off = base + first[k];
+        ps.bands[p].cult0 = ps.band_cult[base + first[k]];
         /* make sure the node is on the "occupied last step" list so that the next step clears it */
         if (ps.view[p].pop == 0u) occ[atomicAdd(&ctl->n_occ[prev], 1u)] = p;
     }
@@ -688,7 +689,7 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
                 h->reach_span = std::max(h->reach_span, hr.near_dst[e] > v ? hr.near_dst[e] - v : v - hr.near_dst[e]);
         }
         RowHdr *hdr;
-        uint8_t *hash;
+        uint16_t *hash;
         uint32_t *dst, *near_off, *near_dst;
         double *cost;
         uint16_t *nidx;
@@ -722,6 +723,7 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         uint16_t *eco_id;
         double *mx;
         TRY(dev_alloc(h, &h->ps.view, n, h->allocs));
+        TRY(dev_alloc(h, &h->ps.bands, n, h->allocs));
         TRY(dev_alloc(h, &h->ps.cnt, n, h->allocs));
         TRY(dev_alloc(h, &h->ps.seg, n, h->allocs));
         TRY(dev_alloc(h, &eco_off, (size_t)n + 1, h->allocs, false));
@@ -1482,7 +1484,7 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
     mb.ccap = std::max<uint32_t>(1024u, hw / 2u);
     m->split_bytes = (1 + (uint64_t)mb.scap) * 8;
     m->emig_bytes = 16 + (uint64_t)mb.ecap * mb.rec_bytes;
-    m->halo_bytes = 16 + (uint64_t)mb.hw * sizeof(PatchView) + (uint64_t)mb.ccap * 8;
+    m->halo_bytes = 16 + (uint64_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)) + (uint64_t)mb.ccap * 8;
     int rc;
 #define MA(ptr, count)                                         \
     if ((rc = dev_alloc(h, &(ptr), (count), m->allocs)) != 0) { \

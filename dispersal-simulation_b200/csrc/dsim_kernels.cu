@@ -329,15 +329,18 @@ __device__ __forceinline__ bool reach_lookup(const Row &row, uint32_t q, double 
 }
 
 /* destination_quality, lib.rs:1034-1062 (has_enemies lib.rs:996-1017, expected_harvest 989-994) */
-__device__ __forceinline__ double view_quality(const StepArgs &a, const PatchView &v, uint64_t culture, uint32_t size,
+__device__ __forceinline__ double view_quality(const StepArgs &a, const PatchView &v, uint32_t q, uint64_t culture, uint32_t size,
                                                bool same_patch) {
     bool enemy = false;
-    if (v.nb > 0u) {
-        enemy = !dsim_will_cooperate(culture, v.cult0, a.mc.threshold, a.mc.inclusive);
-        const uint64_t *others = (v.stor_off & DSIM_STOR_HALO) ? a.mg.halo_cult[(v.stor_off >> 30) & 1u] + (v.stor_off & 0x3FFFFFFFu)
-                                                                : a.ps.band_cult + v.stor_off;
-        for (uint32_t k = 1; k < v.nb && !enemy; ++k)
-            enemy = !dsim_will_cooperate(culture, others[k], a.mc.threshold, a.mc.inclusive);
+    if (v.nb > 0u) { /* candidates occupied last step: fetch their band cultures */
+        const PatchBands b = a.ps.bands[q];
+        enemy = !dsim_will_cooperate(culture, b.cult0, a.mc.threshold, a.mc.inclusive);
+        if (v.nb > 1u && !enemy) {
+            const uint64_t *others = (b.stor_off & DSIM_STOR_HALO) ? a.mg.halo_cult[(b.stor_off >> 30) & 1u] + (b.stor_off & 0x3FFFFFFFu)
+                                                                    : a.ps.band_cult + b.stor_off;
+            for (uint32_t k = 1; k < v.nb && !enemy; ++k)
+                enemy = !dsim_will_cooperate(culture, others[k], a.mc.threshold, a.mc.inclusive);
+        }
     }
     if (enemy) return 0.0;
     const uint64_t pop_at_destination = (uint64_t)v.pop + (same_patch ? 0u : size);
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
                     if (ok[k]) {
                         ni[k] = row.nidx[e];
                         cost[k] = row.cost[e];
-                        gain[k] = view_quality(a, pv[k], culture, size, q[k] == loc);
+                        gain[k] = view_quality(a, pv[k], q[k], culture, size, q[k] == loc);
                     }
                 }
 #pragma unroll
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
                             const uint32_t q = a.rt.near_dst[jj];
                             double cost = 0.0, gain = 0.0, g = DSIM_NEG_INF;
                             if (reach_lookup(crow, q, &cost)) {
-                                gain = view_quality(a, a.ps.view[q], culture, 2u, q == newloc);
+                                gain = view_quality(a, a.ps.view[q], q, culture, 2u, q == newloc);
                                 g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
                             }
                             gs.c_g[e] = g;
@@ -838,12 +841,13 @@ __global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs
 #define TPF_MIN_BLOCKS 4
 #endif
 #define TPF_KEPT 32 /* kept history entries buffered per thread before they are evaluated */
+#define TPF_FB 4u   /* of which this many are resolved at a time (registers) */
 
 struct RowPtr { /* a reach row in place (HBM / L1) */
     const uint32_t *dst;
     const double *cost;
     const uint16_t *nidx;
-    const uint8_t *hash; /* the row's 256-slot index, or nullptr for rows longer than DSIM_ROW_HASH_MAX */
+    const uint16_t *hash; /* the row's 32 x 8 bucket index, or nullptr for rows longer than DSIM_ROW_HASH_MAX */
     uint32_t len, n_sensed;
 };
 
@@ -858,18 +862,43 @@ __device__ __forceinline__ RowPtr row_of(const ReachTable &rt, uint32_t node, co
     return row;
 }
 
-__device__ __forceinline__ uint32_t row_hash_slot(uint32_t q) { return (q * 2654435761u) >> 24; }
+__device__ __forceinline__ uint32_t row_hash(uint32_t q) { return (q * 2654435761u) >> 19; } /* bucket = bits 8..12, tag = bits 0..7 */
+
+/* first slot of the bucket whose tag matches, as an entry position; 0xFF = none; *full = no empty slot */
+__device__ __forceinline__ uint32_t bucket_match(const uint4 &bk, uint32_t tag, uint32_t skip, bool *full) {
+    const uint32_t w[4] = {bk.x, bk.y, bk.z, bk.w};
+    uint32_t found = 0xFFu, seen = 0;
+    bool f = true;
+#pragma unroll
+    for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t slot = (w[k >> 1] >> ((k & 1u) * 16u)) & 0xFFFFu;
+        if (slot == 0xFFFFu) f = false;
+        if (slot != 0xFFFFu && (slot >> 8) == tag) {
+            if (seen == skip && found == 0xFFu) found = slot & 0xFFu;
+            ++seen;
+        }
+    }
+    *full = f;
+    return found;
+}
 
 /* position of node q in the row, or 0xFFFFFFFF (replaces travel_costs.get(), lib.rs:869) */
 __device__ __forceinline__ uint32_t row_find(const RowPtr &row, uint32_t q) {
     if (row.hash != nullptr) {
-        uint32_t h = row_hash_slot(q);
-        for (;;) {
-            const uint32_t k = row.hash[h];
-            if (k == 0xFFu) return 0xFFFFFFFFu;
-            if (row.dst[k] == q) return k;
-            h = (h + 1u) & 255u;
+        const uint32_t h = row_hash(q);
+        uint32_t b = h >> 8;
+        for (uint32_t tries = 0; tries < 32u; ++tries) {
+            const uint4 bk = *reinterpret_cast<const uint4 *>(row.hash + b * 8u);
+            bool full;
+            for (uint32_t skip = 0;; ++skip) { /* tag collisions (1/256 per occupied slot) are verified one by one */
+                const uint32_t k = bucket_match(bk, h & 0xFFu, skip, &full);
+                if (k == 0xFFu) break;
+                if (row.dst[k] == q) return k;
+            }
+            if (!full) return 0xFFFFFFFFu;
+            b = (b + 1u) & 31u;
         }
+        return 0xFFFFFFFFu;
     }
     uint32_t k = lower_bound_u32(row.dst, 0u, row.n_sensed, q);
     if (k < row.n_sensed && row.dst[k] == q) return k;
@@ -887,34 +916,77 @@ __device__ __forceinline__ void accept_one(Choice &ch, double g, double gain, do
     }
 }
 
-/* evaluate the buffered kept history entries kept[0..cnt) (ascending n) as candidates.  The memory
- * accesses are issued stage by stage for all entries (ring entry -> hash slot -> row entry -> cost),
- * so the dependent round trips are paid once per stage, not once per entry. */
+/* evaluate the buffered kept history entries kept[0..cnt) (ascending n) as candidates.  The dependent
+ * memory accesses (ring entry -> hash bucket -> row entry + cost) are issued stage by stage, TPF_FB entries
+ * at a time into registers, so that each stage costs one round trip per TPF_FB entries instead of one
+ * per entry. */
 __device__ __forceinline__ void tpf_flush(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
                                           uint32_t hs, uint32_t ring_cnt, const uint16_t *kept, uint32_t cnt, Choice &ch) {
-    uint32_t kq[TPF_KEPT], kidx[TPF_KEPT];
-    double kgain[TPF_KEPT], kcost[TPF_KEPT];
-    const size_t hbase = (size_t)hs * a.hv.hcap;
-    for (uint32_t k = 0; k < cnt; ++k) {
-        const uint32_t pos = (ring_cnt - 1u - kept[k]) % a.hv.hcap;
-        kq[k] = a.hv.hist_patch[hbase + pos];
-        kgain[k] = a.hv.hist_harv[hbase + pos];
-    }
-    if (row.hash != nullptr) {
-        for (uint32_t k = 0; k < cnt; ++k) kidx[k] = row.hash[row_hash_slot(kq[k])]; /* first probe of every entry */
-        for (uint32_t k = 0; k < cnt; ++k) {
-            uint32_t idx = kidx[k];
-            if (idx != 0xFFu && row.dst[idx] != kq[k]) idx = row_find(row, kq[k]); /* collision: walk the probe sequence */
-            kidx[k] = idx == 0xFFu ? 0xFFFFFFFFu : idx;
+    const uint32_t hcap = a.hv.hcap;
+    const size_t hbase = (size_t)hs * hcap;
+    const uint32_t newest = (ring_cnt - 1u) % hcap; /* ring position of entry 0; entry n sits n positions before it */
+    for (uint32_t k0 = 0; k0 < cnt; k0 += TPF_FB) {
+        const uint32_t m = cnt - k0 < TPF_FB ? cnt - k0 : TPF_FB;
+        uint32_t q[TPF_FB], idx[TPF_FB], d[TPF_FB], n[TPF_FB];
+        double gain[TPF_FB], cost[TPF_FB];
+#pragma unroll
+        for (uint32_t j = 0; j < TPF_FB; ++j) {
+            q[j] = 0u;
+            gain[j] = 0.0;
+            n[j] = j < m ? kept[k0 + j] : 0u;
+            if (j < m) {
+                const uint32_t pos = newest >= n[j] ? newest - n[j] : newest + hcap - n[j];
+                q[j] = a.hv.hist_patch[hbase + pos];
+                gain[j] = a.hv.hist_harv[hbase + pos];
+            }
         }
-    } else {
-        for (uint32_t k = 0; k < cnt; ++k) kidx[k] = row_find(row, kq[k]);
-    }
-    for (uint32_t k = 0; k < cnt; ++k) kcost[k] = kidx[k] != 0xFFFFFFFFu ? row.cost[kidx[k]] : 0.0;
-    for (uint32_t k = 0; k < cnt; ++k) {
-        if (kidx[k] == 0xFFFFFFFFu) continue; /* no travel cost from here: lib.rs:869 */
-        const double g = kgain[k] * noise_draw(a.mc, step, fid, n_sensed + kept[k]) - kcost[k];
-        accept_one(ch, g, kgain[k], kcost[k], kq[k]);
+        if (row.hash != nullptr) {
+            uint4 bk[TPF_FB];
+#pragma unroll
+            for (uint32_t j = 0; j < TPF_FB; ++j)
+                if (j < m) bk[j] = *reinterpret_cast<const uint4 *>(row.hash + (row_hash(q[j]) >> 8) * 8u);
+            bool slow[TPF_FB];
+#pragma unroll
+            for (uint32_t j = 0; j < TPF_FB; ++j) {
+                idx[j] = 0xFFu;
+                slow[j] = false;
+                if (j < m) {
+                    bool full;
+                    idx[j] = bucket_match(bk[j], row_hash(q[j]) & 0xFFu, 0u, &full);
+                    slow[j] = full && idx[j] == 0xFFu; /* full bucket without a match: the key may have overflowed */
+                }
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < TPF_FB; ++j) { /* the row entry and its cost are requested together */
+                d[j] = 0xFFFFFFFFu;
+                cost[j] = 0.0;
+                if (idx[j] != 0xFFu) {
+                    d[j] = row.dst[idx[j]];
+                    cost[j] = row.cost[idx[j]];
+                }
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < TPF_FB; ++j) {
+                if (idx[j] == 0xFFu && !slow[j]) {
+                    idx[j] = 0xFFFFFFFFu;
+                } else if (slow[j] || d[j] != q[j]) { /* overflowed bucket or tag collision: general search */
+                    idx[j] = row_find(row, q[j]);
+                    if (idx[j] != 0xFFFFFFFFu) cost[j] = row.cost[idx[j]];
+                }
+            }
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < TPF_FB; ++j) {
+                idx[j] = j < m ? row_find(row, q[j]) : 0xFFFFFFFFu;
+                cost[j] = idx[j] != 0xFFFFFFFFu ? row.cost[idx[j]] : 0.0;
+            }
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < TPF_FB; ++j) {
+            if (j >= m || idx[j] == 0xFFFFFFFFu) continue; /* no travel cost from here: lib.rs:869 */
+            const double g = gain[j] * noise_draw(a.mc, step, fid, n_sensed + n[j]) - cost[j];
+            accept_one(ch, g, gain[j], cost[j], q[j]);
+        }
     }
 }
 
@@ -996,27 +1068,48 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
         ch.max_gain = 0.0;
         ch.t_cost = 0.0;
         ch.m = 0.0;
-        /* sensed patches: the leading entries of the row in ascending node order, four per iteration:
-         * the four views are gathered together, the node ids of the next four are requested one
-         * iteration ahead, and entries 2k, 2k+1 share one Philox block when their noise indices do.
-         * Rows are padded to multiples of 8 entries, so the 16-byte loads never leave the row. */
+        /* sensed patches: the leading entries of the row in ascending node order, four per iteration.
+         * Software pipeline: the node ids are requested two blocks ahead, the 16-byte views, costs and noise
+         * indices one block ahead, so an iteration never waits for its own loads; entries 2k, 2k+1 share one
+         * Philox block when their noise indices do.  Rows are padded to multiples of 8 entries (padding node
+         * id 0xFFFFFFFF is never dereferenced), so the 16-byte loads never leave the row. */
         {
-            uint4 q_next = make_uint4(0u, 0u, 0u, 0u);
-            if (row.n_sensed > 0u) q_next = *reinterpret_cast<const uint4 *>(row.dst);
-            for (uint32_t e = 0; e < row.n_sensed; e += 4u) {
-                const uint4 q4 = q_next;
-                const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
-                const uint32_t m = row.n_sensed - e < 4u ? row.n_sensed - e : 4u;
-                PatchView pv[4];
+            const uint32_t ns = row.n_sensed;
+            uint4 q_cur = make_uint4(0u, 0u, 0u, 0u), q_nxt = make_uint4(0u, 0u, 0u, 0u);
+            double2 c01_cur = make_double2(0.0, 0.0), c23_cur = make_double2(0.0, 0.0);
+            uint2 nn_cur = make_uint2(0u, 0u);
+            PatchView pv_cur[4];
+            if (ns > 0u) {
+                q_cur = *reinterpret_cast<const uint4 *>(row.dst);
+                c01_cur = *reinterpret_cast<const double2 *>(row.cost);
+                c23_cur = *reinterpret_cast<const double2 *>(row.cost + 2u);
+                nn_cur = *reinterpret_cast<const uint2 *>(row.nidx);
+                if (ns > 4u) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + 4u);
+                const uint32_t q0[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
 #pragma unroll
                 for (uint32_t k = 0; k < 4u; ++k)
-                    if (k < m) pv[k] = a.ps.view[q[k]];
-                if (e + 4u < row.n_sensed) q_next = *reinterpret_cast<const uint4 *>(row.dst + e + 4u);
-                const double2 c01 = *reinterpret_cast<const double2 *>(row.cost + e);
-                const double2 c23 = *reinterpret_cast<const double2 *>(row.cost + e + 2u);
-                const uint2 nn = *reinterpret_cast<const uint2 *>(row.nidx + e);
-                const double cost[4] = {c01.x, c01.y, c23.x, c23.y};
-                const uint32_t ni[4] = {nn.x & 0xFFFFu, nn.x >> 16, nn.y & 0xFFFFu, nn.y >> 16};
+                    if (k < ns) pv_cur[k] = a.ps.view[q0[k]];
+            }
+            for (uint32_t e = 0; e < ns; e += 4u) {
+                const uint32_t q[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
+                const double cost[4] = {c01_cur.x, c01_cur.y, c23_cur.x, c23_cur.y};
+                const uint32_t ni[4] = {nn_cur.x & 0xFFFFu, nn_cur.x >> 16, nn_cur.y & 0xFFFFu, nn_cur.y >> 16};
+                const uint32_t m = ns - e < 4u ? ns - e : 4u;
+                PatchView pv[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; ++k) pv[k] = pv_cur[k];
+                /* requests for the next block (views, costs, indices) and the block after it (node ids) */
+                if (e + 4u < ns) {
+                    const uint32_t qn[4] = {q_nxt.x, q_nxt.y, q_nxt.z, q_nxt.w};
+#pragma unroll
+                    for (uint32_t k = 0; k < 4u; ++k)
+                        if (e + 4u + k < ns) pv_cur[k] = a.ps.view[qn[k]];
+                    c01_cur = *reinterpret_cast<const double2 *>(row.cost + e + 4u);
+                    c23_cur = *reinterpret_cast<const double2 *>(row.cost + e + 6u);
+                    nn_cur = *reinterpret_cast<const uint2 *>(row.nidx + e + 4u);
+                    q_cur = q_nxt;
+                    if (e + 8u < ns) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + e + 8u);
+                }
                 double u[4];
 #pragma unroll
                 for (uint32_t k = 0; k < 4u; k += 2u) {
@@ -1031,7 +1124,7 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
 #pragma unroll
                 for (uint32_t k = 0; k < 4u; ++k) {
                     if (k < m) {
-                        const double gain = view_quality(a, pv[k], culture, size, q[k] == loc);
+                        const double gain = view_quality(a, pv[k], q[k], culture, size, q[k] == loc);
                         accept_one(ch, gain * u[k] - cost[k], gain, cost[k], q[k]);
                     }
                 }
@@ -1154,7 +1247,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
                 const uint32_t k = row_find(row, q);
                 if (k != 0xFFFFFFFFu) {
                     cost = row.cost[k];
-                    gain = view_quality(a, a.ps.view[q], t.culture, 2u, q == t.new_loc);
+                    gain = view_quality(a, a.ps.view[q], q, t.culture, 2u, q == t.new_loc);
                     g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
                     cand = true;
                 }
@@ -1583,10 +1676,12 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
             v.quality = quality;
             v.pop = pop;
             v.nb = nb_alive;
-            v.cult0 = cult0;
-            v.stor_off = s0;
-            v.pad_ = 0;
             a.ps.view[p] = v;
+            PatchBands b;
+            b.cult0 = cult0;
+            b.stor_off = s0;
+            b.pad_ = 0;
+            a.ps.bands[p] = b;
             a.ps.cnt[p] = 0u;
         }
         __syncwarp();
@@ -1773,10 +1868,12 @@ __global__ void __launch_bounds__(128) k_patch_small(StepArgs a) {
         pv.quality = quality;
         pv.pop = pop;
         pv.nb = nb_alive;
-        pv.cult0 = cult0;
-        pv.stor_off = s0;
-        pv.pad_ = 0;
         a.ps.view[p] = pv;
+        PatchBands pb;
+        pb.cult0 = cult0;
+        pb.stor_off = s0;
+        pb.pad_ = 0;
+        a.ps.bands[p] = pb;
         a.ps.cnt[p] = 0u;
     }
     if (errors) atomicOr(&ctl->errors, errors);

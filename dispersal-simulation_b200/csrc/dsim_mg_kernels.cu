@@ -241,27 +241,31 @@ __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
 }
 
 /* ---- HALO ------------------------------------------------------------------------------------- */
-/* the views of my boundary strips, with the band cultures they point to packed behind them */
+/* the views of my boundary strips, with the band cultures they point to packed behind them:
+ * message = [header 16][views hw x 16][bands hw x 16][cultures ccap x 8] */
 __global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) {
     for (uint32_t side = 0; side < 2u; ++side) {
         if (!mb.has_peer[side]) continue;
         const uint32_t first = side == 0u ? a.mg.own_lo : a.mg.own_hi - mb.hw;
         unsigned char *buf = mb.halo_send[side];
         PatchView *views = reinterpret_cast<PatchView *>(buf + 16);
-        uint64_t *cults = reinterpret_cast<uint64_t *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        PatchBands *bands = reinterpret_cast<PatchBands *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        uint64_t *cults = reinterpret_cast<uint64_t *>(buf + 16 + (size_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)));
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.hw; k += gridDim.x * blockDim.x) {
             PatchView v = a.ps.view[first + k];
+            PatchBands b = a.ps.bands[first + k];
             if (v.nb >= 2u) { /* the first culture travels inline */
                 const uint32_t at = atomicAdd(&mb.counters[MG_HALO_CULT0 + side], v.nb);
                 if (at + v.nb <= mb.ccap) {
-                    for (uint32_t b = 0; b < v.nb; ++b) cults[at + b] = a.ps.band_cult[v.stor_off + b];
-                    v.stor_off = DSIM_STOR_HALO | (side << 30) | at; /* relative; the receiver knows the side */
+                    for (uint32_t c = 0; c < v.nb; ++c) cults[at + c] = a.ps.band_cult[b.stor_off + c];
+                    b.stor_off = DSIM_STOR_HALO | (side << 30) | at; /* relative; the receiver knows the side */
                 } else {
                     atomicOr(&a.ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
                     v.nb = 1u;
                 }
             }
             views[k] = v;
+            bands[k] = b;
         }
     }
 }
@@ -273,11 +277,13 @@ __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb
         const uint32_t first = side == 0u ? a.mg.own_lo - mb.hw : a.mg.own_hi;
         const unsigned char *buf = mb.halo_recv[side];
         const PatchView *views = reinterpret_cast<const PatchView *>(buf + 16);
-        const uint64_t *cults = reinterpret_cast<const uint64_t *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        const PatchBands *bands = reinterpret_cast<const PatchBands *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
+        const uint64_t *cults = reinterpret_cast<const uint64_t *>(buf + 16 + (size_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)));
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.hw; k += gridDim.x * blockDim.x) {
-            PatchView v = views[k];
-            if (v.stor_off & DSIM_STOR_HALO) v.stor_off = DSIM_STOR_HALO | (side << 30) | (v.stor_off & 0x3FFFFFFFu);
-            a.ps.view[first + k] = v;
+            PatchBands b = bands[k];
+            if (b.stor_off & DSIM_STOR_HALO) b.stor_off = DSIM_STOR_HALO | (side << 30) | (b.stor_off & 0x3FFFFFFFu);
+            a.ps.view[first + k] = views[k];
+            a.ps.bands[first + k] = b;
         }
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.ccap; k += gridDim.x * blockDim.x)
             mb.halo_cult[side][k] = cults[k];

@@ -225,19 +225,28 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
             np += ch.n_len[k];
         }
     }
-    /* per-row hash: entry index by destination node, for the travel-cost look-ups of remembered patches */
-    out->hash.assign((size_t)n * 256u, (uint8_t)0xFF);
+    /* per-row index for the travel-cost look-ups of remembered patches: 32 buckets of 8 slots, slot =
+     * tag << 8 | entry position (0xFFFF = empty); a full bucket overflows into the next one */
+    out->hash.assign((size_t)n * 256u, (uint16_t)0xFFFF);
 #pragma omp parallel for schedule(static)
     for (long v = 0; v < (long)n; ++v) {
         const HostRowHdr &hd = out->hdr[v];
         if (hd.len > DSIM_ROW_HASH_MAX) continue;
-        uint8_t *tbl = out->hash.data() + (size_t)v * 256u;
+        uint16_t *tbl = out->hash.data() + (size_t)v * 256u;
         for (uint32_t k = 0; k < hd.len; ++k) {
             const uint32_t q = out->dst[hd.start + k];
             if (q == 0xFFFFFFFFu) continue;
-            uint32_t h = dsim_row_hash(q);
-            while (tbl[h] != 0xFF) h = (h + 1u) & 255u;
-            tbl[h] = (uint8_t)k;
+            const uint32_t h = dsim_row_hash(q);
+            uint32_t b = h >> 8;
+            for (;;) {
+                uint32_t s = 0;
+                while (s < 8u && tbl[b * 8u + s] != 0xFFFF) ++s;
+                if (s < 8u) {
+                    tbl[b * 8u + s] = (uint16_t)(((h & 0xFFu) << 8) | k);
+                    break;
+                }
+                b = (b + 1u) & 31u;
+            }
         }
     }
     return DSIM_OK;

@@ -19,14 +19,14 @@ struct HostReach {
     std::vector<uint32_t> dst;      /* [sensed, ascending][others, ascending][padding 0xFFFFFFFF] */
     std::vector<double> cost;       /* OYR; padding +inf                             */
     std::vector<uint16_t> nidx;     /* sensed entries: position in the node's nearby list; others 0xFFFF */
-    std::vector<uint8_t> hash;      /* [n * 256] open-addressing index of each row (rows of <= 192 entries) */
+    std::vector<uint16_t> hash;     /* [n * 256] bucketized index of each row (rows of <= 192 entries), see dsim_state.h */
     std::vector<uint32_t> near_off; /* [n+1] */
     std::vector<uint32_t> near_dst; /* ascending within a node */
     uint64_t n_reach = 0;           /* entries without padding */
 };
 
-/* slot of node q in a row hash: top 8 bits of a Fibonacci hash; linear probing; 0xFF = empty */
-static inline uint32_t dsim_row_hash(uint32_t q) { return (q * 2654435761u) >> 24; }
+/* 13 hash bits of node q: bucket = bits 8..12, tag = bits 0..7 (dsim_state.h) */
+static inline uint32_t dsim_row_hash(uint32_t q) { return (q * 2654435761u) >> 19; }
 #define DSIM_ROW_HASH_MAX 192u
 
 int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err);

@@ -7,8 +7,8 @@
  *     lib.rs:541) and the children (appended, lib.rs:551) into buffer `next`;
  *   - HEAVY per-family state that never moves (history ring, sparse adaptation slots, lineage),
  *     addressed through the `hs` (heavy slot) column of the core record.
- * Patches (lib.rs:142-152) keep their resources in the ecoregion CSR of the graph plus one 32-byte
- * VIEW record per node that holds everything the move decision gathers for a candidate patch.
+ * Patches (lib.rs:142-152) keep their resources in the ecoregion CSR of the graph plus one 16-byte
+ * VIEW record (and a 16-byte BANDS record) per node that holds everything the move decision gathers for a candidate patch.
  */
 #ifndef DSIM_STATE_H
 #define DSIM_STATE_H
@@ -47,17 +47,21 @@ struct FamHeavy {           /* index = heavy slot */
     uint32_t hcap, acap;
 };
 
-struct __align__(16) PatchView { /* what decide_on_moving gathers per candidate (lib.rs:1034-1062) */
+struct __align__(16) PatchView { /* what decide_on_moving gathers per candidate (lib.rs:1034-1062): 16 bytes */
     double quality;         /* expected_harvest: sum_e(res + max * recovery), lib.rs:989-994       */
     uint32_t pop;           /* census cc[node], lib.rs:522-525                                    */
     uint32_t nb;            /* number of band cultures stored for the node (storage[node].len())   */
-    uint64_t cult0;         /* first of them, inline                                              */
-    uint32_t stor_off;      /* the others: band_cult[stor_off + 1 ... stor_off + nb - 1]          */
+};
+
+struct __align__(16) PatchBands { /* read only for candidates with nb > 0 (has_enemies, lib.rs:996-1017) */
+    uint64_t cult0;         /* first band culture, inline                                         */
+    uint32_t stor_off;      /* all of them: band_cult[stor_off ... stor_off + nb - 1]              */
     uint32_t pad_;
 };
 
 struct PatchState {
     PatchView *view;        /* [P]                                                                */
+    PatchBands *bands;      /* [P]                                                                */
     uint32_t *cnt;          /* [P] arrivals during part 1 (counting sort histogram), 0 between steps */
     uint32_t *seg;          /* [P] start of the node's segment in `members`                        */
     const uint32_t *eco_off;/* [P+1]                                                              */
@@ -81,8 +85,9 @@ struct ReachTable {          /* replaces bounded_dijkstra per family per step (l
     const uint32_t *dst;
     const double *cost;      /* OYR                                                                */
     const uint16_t *nidx;    /* sensed entries: index in the node's nearby list                    */
-    const uint8_t *hash;     /* [P * 256] per-row open-addressing index (entry position by node, 0xFF = empty) for
-                                rows of at most DSIM_ROW_HASH_MAX entries; longer rows are binary-searched      */
+    const uint16_t *hash;    /* [P * 256] per-row index for rows of at most DSIM_ROW_HASH_MAX entries (longer rows are
+                                binary-searched): 32 buckets x 8 slots, bucket = hash bits 8..12, slot = tag (hash
+                                bits 0..7) << 8 | entry position, 0xFFFF = empty; one 16-byte load reads a bucket  */
     const uint32_t *near_off;/* [P+1] 2-hop lists (lib.rs:1158-1178), ascending                    */
     const uint32_t *near_dst;
 };
