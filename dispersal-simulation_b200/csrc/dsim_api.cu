@@ -64,7 +64,8 @@ struct dsim_handle {
     StepScratch sc;
     DevCtl *ctl = nullptr;
     DevCtl *ctl_h = nullptr; /* pinned mirror */
-    uint32_t *mem_thr_d = nullptr;
+    uint8_t *mem_hi8_d = nullptr;
+    uint32_t *mem_lo32_d = nullptr;
     ModelConst mc;
     std::vector<void *> fam_allocs; /* family-capacity dependent arrays */
     uint64_t cap = 0, hs_cap = 0;
@@ -172,7 +173,7 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     a.occ_par = parity;
     std::memset(&a.mg, 0, sizeof a.mg);
     a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
-    a.children_inline = (h->opt.flags & DSIM_OPT_MOVE_COOPERATIVE) ? 1u : 0u;
+    a.move_tpf = (h->opt.flags & DSIM_OPT_MOVE_THREAD_PER_FAMILY) ? 1u : 0u;
     return a;
 }
 
@@ -638,7 +639,6 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     h->n_eco = (uint32_t)n_eco;
     std::memset(&h->geom, 0, sizeof h->geom);
     h->geom.n_sm = (uint32_t)std::max(1, prop.multiProcessorCount);
-    h->geom.force_global_rows = (o.flags & DSIM_OPT_ROWS_IN_PLACE) ? 1u : 0u;
     std::memset(&h->rt, 0, sizeof h->rt);
     std::memset(&h->ps, 0, sizeof h->ps);
     std::memset(&h->hv, 0, sizeof h->hv);
@@ -763,17 +763,39 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
             memory *= decay;
         }
         mc.n_mem = (uint32_t)mem.size();
-        /* entry n is kept iff draw * 2^-32 < memory_n (lib.rs:859)  <=>  draw <= ceil(memory_n * 2^32) - 1 */
-        std::vector<uint32_t> thr(mem.size());
+        /* entry n is kept iff U_n < memory_n (lib.rs:859) with the 40-bit uniform U_n = X_n 2^-40, i.e. iff the
+         * integer X_n < C_n = ceil(memory_n 2^40); the kernels compare the top byte and the low word separately */
+        const size_t n_pad = (mem.size() + 15u) & ~(size_t)15u;
+        std::vector<uint8_t> hi8(n_pad, 0);
+        std::vector<uint32_t> lo32(n_pad, 0);
+        mc.mem_always = 0;
+        mc.mem_head = 0;
         for (size_t k = 0; k < mem.size(); ++k) {
-            const double x = std::ceil(mem[k] * 4294967296.0) - 1.0;
-            thr[k] = x >= 4294967295.0 ? 4294967295u : (x <= 0.0 ? 0u : (uint32_t)x);
+            const double c = std::ceil(mem[k] * 1099511627776.0);
+            if (c >= 1099511627776.0) { /* memory_n >= 1: always kept (only n = 0) */
+                if (k != mc.mem_always) {
+                    g_create_error = "memory table: entries with memory >= 1 must form a prefix";
+                    dsim_destroy(h);
+                    return DSIM_ERR_INVALID;
+                }
+                mc.mem_always = (uint32_t)k + 1u;
+                hi8[k] = 255;
+                lo32[k] = 0xFFFFFFFFu;
+            } else {
+                const uint64_t ci = (uint64_t)c;
+                hi8[k] = (uint8_t)(ci >> 32);
+                lo32[k] = (uint32_t)ci;
+            }
+            if (hi8[k] != 0) mc.mem_head = (uint32_t)(k / 16u) + 1u;
         }
-        TRY(dev_alloc(h, &h->mem_thr_d, thr.size(), h->allocs, false));
-        TRY(upload(h, h->mem_thr_d, thr.data(), thr.size()));
+        TRY(dev_alloc(h, &h->mem_hi8_d, hi8.size(), h->allocs, false));
+        TRY(upload(h, h->mem_hi8_d, hi8.data(), hi8.size()));
+        TRY(dev_alloc(h, &h->mem_lo32_d, lo32.size(), h->allocs, false));
+        TRY(upload(h, h->mem_lo32_d, lo32.data(), lo32.size()));
         TRYCUDA(cudaStreamSynchronize(h->stream));
-        mc.mem_thr = h->mem_thr_d;
-        if (dsim_configure_kernels(&h->geom, h->max_row, mc.n_mem) != 0) {
+        mc.mem_hi8 = h->mem_hi8_d;
+        mc.mem_lo32 = h->mem_lo32_d;
+        if (dsim_configure_kernels(&h->geom) != 0) {
             g_create_error = "cannot configure the shared-memory size of k_move";
             dsim_destroy(h);
             return DSIM_ERR_CUDA;
@@ -1453,7 +1475,6 @@ int dsim_mg_halo_width(dsim_handle *h, uint32_t *nodes) {
 
 int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint32_t *bounds) {
     if (!h || !bounds || world == 0 || rank >= world) return DSIM_ERR_INVALID;
-    if (h->opt.flags & DSIM_OPT_MOVE_COOPERATIVE) return fail(h, DSIM_ERR_INVALID, "the multi-GPU step uses the default move kernel");
     if (bounds[0] != 0 || bounds[world] != h->n_nodes) return fail(h, DSIM_ERR_INVALID, "bounds must cover [0, n_nodes]");
     const uint32_t hw = 2u * h->reach_span;
     for (uint32_t r = 0; r < world; ++r)

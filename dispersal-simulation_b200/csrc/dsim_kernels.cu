@@ -29,9 +29,6 @@
 #include <cstring>
 
 #define LIFE_BLOCK 256
-#ifndef MOVE_THREADS
-#define MOVE_THREADS 128
-#endif
 #define PATCH_WARPS 4
 #define PATCH_M 64 /* families per node handled in shared memory; larger nodes spill to HBM scratch */
 #define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by one thread each */
@@ -183,124 +180,15 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
     }
 }
 
-/* ---- asynchronous bulk copies global -> shared (TMA, 1-D) with an mbarrier ------------------------ */
-#if defined(DSIM_EMU)
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
-#else
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-#endif
-
 /* ------------------------------------------------------------------------------------------ *
- * part 1c: move + split
- *
- * One warp per CHUNK of 32 consecutive families (= one word of the survivor / split bitmaps).  Lane L
- * loads the record of family 32c+L (coalesced), its reach-row header and history length; new positions
- * and children's ranks are popcounts of the bitmap word plus the per-256 offsets of k_control.  The
- * surviving families are then decided 32/G at a time, each by a GROUP of G lanes; the groups of a warp
- * run in lockstep (every collective is executed by the full warp, every loop runs while any group
- * needs it), so that one instruction stream and one memory round trip serve 32/G families.  Each
- * group stages its family's reach row in shared memory with TMA bulk copies.
- * Selected with DSIM_OPT_MOVE_COOPERATIVE; the default is the thread-per-family kernel further down.
+ * part 1c: move + split — shared pieces
  * ------------------------------------------------------------------------------------------ */
 struct Choice { /* best_location state, lib.rs:911-916 */
     uint32_t target;
     double max_gain, t_cost, m;
 };
 
-#define MOVE_ROUND 32u   /* candidates evaluated per round and group */
-#define MOVE_RING 128u   /* capacity of a group's ring of kept history indices */
 #define DSIM_NEG_INF (dsim_bits_to_f64(0xFFF0000000000000ull))
-
-struct GroupSmem { /* carved out of dynamic shared memory, one per group */
-    double *cost;     /* [row_cap] staged reach row */
-    uint32_t *dst;    /* [row_cap] */
-    uint16_t *nidx;   /* [row_cap] */
-    double *c_g;      /* [MOVE_ROUND] candidates of the current round: noised net gain (-inf = no candidate) */
-    double *c_gain;   /* [MOVE_ROUND] expected harvest */
-    double *c_cost;   /* [MOVE_ROUND] travel cost */
-    uint32_t *c_q;    /* [MOVE_ROUND] node */
-    uint16_t *ring;   /* [MOVE_RING] kept history indices awaiting evaluation */
-    uint64_t *bar;    /* mbarrier of the row staging */
-    uint32_t phase;
-};
-
-__host__ __device__ __forceinline__ uint32_t move_smem_per_group(uint32_t row_cap) {
-    return row_cap * 14u + MOVE_ROUND * 28u + MOVE_RING * 2u + 16u;
-}
-/* keep-threshold table in shared memory, padded with zeros to a multiple of 8 entries */
-__host__ __device__ __forceinline__ uint32_t move_smem_table(uint32_t n_mem) { return ((n_mem + 7u) & ~7u) * 4u; }
-
-/* A family's reach row as the kernel sees it: staged in shared memory or in place in HBM.
- * Layout: [n_sensed entries that are also in the 2-hop list, ascending dst][the other reachable
- * nodes, ascending dst][padding]. */
-struct Row {
-    const uint32_t *dst;
-    const double *cost;
-    const uint16_t *nidx;
-    uint32_t len, n_sensed;
-};
-
-/* Stage a reach row (group leader issues, every lane of the group waits).  Rows start at multiples
- * of 8 entries and are padded to multiples of 8, so every column start is 16-byte aligned and every
- * copy size a multiple of 16 bytes, as cp.async.bulk requires.  The caller guarantees (by a
- * __syncwarp) that no lane still reads the buffers. */
-template <bool STAGED>
-__device__ __forceinline__ Row stage_row(const ReachTable &rt, bool on, uint32_t start, uint32_t len, uint32_t n_sensed,
-                                         GroupSmem &gs, bool leader) {
-    Row row;
-    row.len = on ? len : 0u;
-    row.n_sensed = on ? n_sensed : 0u;
-    if (STAGED) {
-        if (on && len > 0u) {
-            if (leader) {
-                const uint32_t ns8 = (n_sensed + 7u) & ~7u;
-                mbar_expect_tx(gs.bar, len * 12u + ns8 * 2u);
-                bulk_g2s(gs.cost, rt.cost + start, len * 8u, gs.bar);
-                bulk_g2s(gs.dst, rt.dst + start, len * 4u, gs.bar);
-                if (ns8) bulk_g2s(gs.nidx, rt.nidx + start, ns8 * 2u, gs.bar);
-            }
-            mbar_wait(gs.bar, gs.phase);
-            gs.phase ^= 1u;
-        }
-        __syncwarp();
-        row.dst = gs.dst;
-        row.cost = gs.cost;
-        row.nidx = gs.nidx;
-    } else {
-        row.dst = rt.dst + start;
-        row.cost = rt.cost + start;
-        row.nidx = rt.nidx + start;
-    }
-    return row;
-}
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *v, uint32_t lo, uint32_t hi, uint32_t q) {
     while (lo < hi) {
@@ -311,21 +199,6 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *v, uint32_t 
             hi = mid;
     }
     return lo;
-}
-
-/* travel cost look-up in a reach row (replaces travel_costs.get(), lib.rs:869): both sorted segments */
-__device__ __forceinline__ bool reach_lookup(const Row &row, uint32_t q, double *cost) {
-    uint32_t k = lower_bound_u32(row.dst, 0u, row.n_sensed, q);
-    if (k < row.n_sensed && row.dst[k] == q) {
-        *cost = row.cost[k];
-        return true;
-    }
-    k = lower_bound_u32(row.dst, row.n_sensed, row.len, q);
-    if (k < row.len && row.dst[k] == q) {
-        *cost = row.cost[k];
-        return true;
-    }
-    return false;
 }
 
 /* destination_quality, lib.rs:1034-1062 (has_enemies lib.rs:996-1017, expected_harvest 989-994) */
@@ -347,480 +220,55 @@ __device__ __forceinline__ double view_quality(const StepArgs &a, const PatchVie
     return v.quality / (double)pop_at_destination;
 }
 
-template <int G> struct Lanes { /* position of a lane in its group */
-    uint32_t lane, gl, goff, gbits;
-    __device__ __forceinline__ explicit Lanes(uint32_t l) : lane(l), gl(l % G), goff(l - l % G), gbits(G == 32 ? 0xffffffffu : ((1u << G) - 1u)) {}
-    /* ballot restricted to my group (bit k = lane k of the group); executed by the full warp */
-    __device__ __forceinline__ uint32_t ballot(bool pred) const { return (__ballot_sync(DSIM_FULL, pred) >> goff) & gbits; }
-};
-
-/* Ordered acceptance scan of lib.rs:918-927 over the first `ncand` candidates of the group's round
- * buffer (c_g/c_gain/c_cost/c_q), in candidate order: a candidate is accepted iff g > m with m as left
- * by the previous acceptance.  Full-warp lockstep; `ch` is replicated in the lanes of a group. */
-template <int G>
-__device__ __forceinline__ void accept_round(const Lanes<G> &ln, const GroupSmem &gs, bool on, uint32_t ncand, Choice &ch) {
-    for (uint32_t sub = 0; __any_sync(DSIM_FULL, on && sub < ncand); sub += (uint32_t)G) {
-        const uint32_t e = sub + ln.gl;
-        const double g = (on && e < ncand) ? gs.c_g[e] : DSIM_NEG_INF;
-        uint32_t cursor = 0;
-        for (;;) {
-            const uint32_t all = __ballot_sync(DSIM_FULL, ln.gl >= cursor && g > ch.m);
-            if (all == 0u) break;
-            const uint32_t mine = (all >> ln.goff) & ln.gbits;
-            if (mine != 0u) {
-                const uint32_t L = (uint32_t)__ffs((int)mine) - 1u;
-                const uint32_t ea = sub + L;
-                ch.target = gs.c_q[ea];
-                ch.max_gain = dsim_oyr_max(ch.max_gain, gs.c_gain[ea]);
-                ch.t_cost = gs.c_cost[ea];
-                ch.m = ch.max_gain - ch.t_cost;
-                cursor = L + 1u;
-            } else {
-                cursor = (uint32_t)G;
-            }
-        }
-    }
+/* ---- remembered-patch sampling, lib.rs:854-866 ------------------------------------------------------
+ * History entry n is kept iff U_n < memory_n with the 40-bit uniform U_n = (B_n 2^32 + W_n) 2^-40 (ModelConst):
+ * one Philox block of the MEM stream holds the top bytes B_n of 16 consecutive entries; they decide all
+ * but 1/256 of the entries, the others need the word W_n of the MEM2 stream.  The byte comparisons are
+ * done four at a time on packed words (flags in bit 7 of every byte). */
+__device__ __forceinline__ uint32_t swar_ltu4(uint32_t x, uint32_t y) { /* bytes of x < bytes of y, unsigned */
+    const uint32_t d = (x | 0x80808080u) - (y & 0x7F7F7F7Fu); /* bit 7: low 7 bits of x >= low 7 bits of y; no borrows */
+    return ((~x & y) | (~(x ^ y) & ~d)) & 0x80808080u;
 }
-
-struct HistSource { /* where history entry n (0 = newest) of the deciding family comes from */
-    uint32_t hs, ring_cnt;
-    bool virt;          /* entry 0 is (v0_patch, v0_harv), entry n >= 1 is ring entry n-1 (lib.rs:1882-1885) */
-    uint32_t v0_patch;
-    double v0_harv;
-};
-
-/* evaluate up to G kept history entries (the oldest `k` of the group's ring) as candidates */
-template <int G>
-__device__ __forceinline__ void history_flush(const StepArgs &a, const Lanes<G> &ln, GroupSmem &gs, uint32_t step, bool on,
-                                              uint64_t fid, const Row &row, uint32_t n_sensed, const HistSource &hsrc,
-                                              uint32_t head, uint32_t k, Choice &ch) {
-    if (on && ln.gl < k) {
-        const uint32_t n = gs.ring[(head + ln.gl) % MOVE_RING];
-        uint32_t q;
-        double gain, cost = 0.0, g = DSIM_NEG_INF;
-        if (hsrc.virt && n == 0u) {
-            q = hsrc.v0_patch;
-            gain = hsrc.v0_harv;
-        } else {
-            const uint32_t nn = hsrc.virt ? n - 1u : n;
-            const uint32_t pos = (hsrc.ring_cnt - 1u - nn) % a.hv.hcap;
-            const size_t at = (size_t)hsrc.hs * a.hv.hcap + pos;
-            q = a.hv.hist_patch[at];
-            gain = a.hv.hist_harv[at];
-        }
-        if (reach_lookup(row, q, &cost)) g = gain * noise_draw(a.mc, step, fid, n_sensed + n) - cost;
-        gs.c_g[ln.gl] = g;
-        gs.c_gain[ln.gl] = gain;
-        gs.c_cost[ln.gl] = cost;
-        gs.c_q[ln.gl] = q;
-    }
-    __syncwarp();
-    accept_round<G>(ln, gs, on, k, ch);
-    __syncwarp();
+__device__ __forceinline__ uint32_t swar_eq4(uint32_t x, uint32_t y) { /* bytes of x == bytes of y */
+    const uint32_t z = x ^ y;
+    return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
 }
+__device__ __forceinline__ uint32_t swar_pack4(uint32_t m) { return ((m >> 7) * 0x10204080u) >> 28; } /* bit 7 of byte k -> bit k */
 
-/* The remembered-patch part of decide_on_moving (lib.rs:854-867): history entry n is kept with
- * probability memory_n (keyed 32-bit draw against an integer threshold: no memory access); kept
- * entries with a travel cost become candidates whose expected harvest is the remembered per-capita
- * harvest.  Per iteration a group examines 4G consecutive entries (one Philox block of four draws per
- * lane), appends the indices of the kept ones, in order, to its ring and evaluates them G at a time. */
-template <int G>
-__device__ __forceinline__ void history_pass(const StepArgs &a, const Lanes<G> &ln, GroupSmem &gs, uint32_t step, bool on,
-                                             uint64_t fid, const Row &row, uint32_t n_sensed, uint32_t nh, const HistSource &hsrc,
-                                             const uint32_t *thr, Choice &ch) {
-    uint32_t head = 0, tail = 0;
-    for (uint32_t nb = 0; __any_sync(DSIM_FULL, on && nb < nh); nb += 4u * (uint32_t)G) {
-        const uint32_t n4 = nb + 4u * ln.gl;
-        uint32_t flags = 0;
-        if (on && n4 < nh) {
-            /* memory draws: entry n uses Philox block n>>2, word n&3 */
-            const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, n4 >> 2);
-#pragma unroll
-            for (uint32_t w = 0; w < 4u; ++w)
-                if (n4 + w < nh && dsim_word(o, w) <= thr[n4 + w]) flags |= 1u << w; /* draw * 2^-32 < memory_n, lib.rs:859 */
-        }
-        /* exclusive prefix sum of the per-lane counts inside the group */
-        const uint32_t c = (uint32_t)__popc(flags);
-        uint32_t incl = c;
-#pragma unroll
-        for (int d = 1; d < G; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(DSIM_FULL, incl, (unsigned)d, G);
-            if ((int)ln.gl >= d) incl += up;
-        }
-        const uint32_t total = __shfl_sync(DSIM_FULL, incl, G - 1, G);
-        uint32_t at = tail + incl - c;
-#pragma unroll
-        for (uint32_t w = 0; w < 4u; ++w)
-            if (flags & (1u << w)) gs.ring[(at++) % MOVE_RING] = (uint16_t)(n4 + w);
-        tail += total;
-        __syncwarp();
-        while (__any_sync(DSIM_FULL, on && tail - head >= (uint32_t)G)) {
-            const bool go = on && tail - head >= (uint32_t)G;
-            history_flush<G>(a, ln, gs, step, go, fid, row, n_sensed, hsrc, head, (uint32_t)G, ch);
-            if (go) head += (uint32_t)G;
-        }
+/* entries [16 jb, 16 jb + 16) of family `fid` with 16 jb < nh: returns the mask of entries kept on their top byte
+ * alone; *undecided = entries whose top byte equals the threshold byte (mem_resolve decides them) */
+__device__ __forceinline__ uint32_t mem_block(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t jb, uint32_t nh,
+                                              uint32_t *undecided) {
+    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, jb);
+    uint32_t lt = 0, eq = 0;
+    if (jb >= mc.mem_head) { /* every threshold byte is zero: nothing is kept on the top byte, a zero byte is undecided */
+        const uint32_t z0 = swar_eq4(o.x, 0u), z1 = swar_eq4(o.y, 0u), z2 = swar_eq4(o.z, 0u), z3 = swar_eq4(o.w, 0u);
+        if ((z0 | z1 | z2 | z3) != 0u) eq = swar_pack4(z0) | (swar_pack4(z1) << 4) | (swar_pack4(z2) << 8) | (swar_pack4(z3) << 12);
+    } else {
+        const uint4 h = *reinterpret_cast<const uint4 *>(mc.mem_hi8 + 16u * jb);
+        lt = swar_pack4(swar_ltu4(o.x, h.x)) | (swar_pack4(swar_ltu4(o.y, h.y)) << 4) | (swar_pack4(swar_ltu4(o.z, h.z)) << 8) |
+             (swar_pack4(swar_ltu4(o.w, h.w)) << 12);
+        eq = swar_pack4(swar_eq4(o.x, h.x)) | (swar_pack4(swar_eq4(o.y, h.y)) << 4) | (swar_pack4(swar_eq4(o.z, h.z)) << 8) |
+             (swar_pack4(swar_eq4(o.w, h.w)) << 12);
     }
-    if (__any_sync(DSIM_FULL, on && tail > head)) {
-        const bool go = on && tail > head;
-        history_flush<G>(a, ln, gs, step, go, fid, row, n_sensed, hsrc, head, tail - head, ch);
-    }
+    const uint32_t n0 = 16u * jb;
+    if (n0 < mc.mem_always) lt |= (mc.mem_always - n0 >= 16u) ? 0xFFFFu : ((1u << (mc.mem_always - n0)) - 1u);
+    const uint32_t valid = (nh - n0 >= 16u) ? 0xFFFFu : ((1u << (nh - n0)) - 1u);
+    lt &= valid;
+    *undecided = eq & valid & ~lt;
+    return lt;
 }
-
-#ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 4
-#endif
-#ifndef MOVE_GROUP
-#define MOVE_GROUP 16
-#endif
-
-template <bool STAGED, int G>
-__global__ void __launch_bounds__(MOVE_THREADS, MOVE_MIN_BLOCKS) k_move(StepArgs a, uint32_t row_cap) {
-    constexpr uint32_t NG = 32 / G;          /* families decided concurrently by a warp */
-    constexpr uint32_t KP = MOVE_ROUND / G;  /* candidates per lane and round */
-    DSIM_DYN_SMEM(smem_raw);
-    DevCtl *ctl = a.ctl;
-    const uint32_t n = ctl->n_cur[a.parity];
-    const uint32_t step = ctl->t;
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const Lanes<G> ln(lane);
-    const uint32_t grp = lane / G;
-    const bool leader = ln.gl == 0u;
-    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t cap = ctl->cap;
-    const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
-    const uint32_t lt = (1u << lane) - 1u;
-
-    /* dynamic shared memory: [keep thresholds, n_mem x u32][one GroupSmem area per group] */
-    uint32_t *thr = (uint32_t *)smem_raw;
-    for (uint32_t k = threadIdx.x; k < ((a.mc.n_mem + 7u) & ~7u); k += blockDim.x) thr[k] = k < a.mc.n_mem ? a.mc.mem_thr[k] : 0u;
-    GroupSmem gs;
-    {
-        unsigned char *base = smem_raw + move_smem_table(a.mc.n_mem) + (size_t)(wib * NG + grp) * move_smem_per_group(row_cap);
-        gs.cost = (double *)base;
-        base += (size_t)row_cap * 8u;
-        gs.c_g = (double *)base;
-        gs.c_gain = gs.c_g + MOVE_ROUND;
-        gs.c_cost = gs.c_gain + MOVE_ROUND;
-        base += MOVE_ROUND * 24u;
-        gs.bar = (uint64_t *)base;
-        base += 16u;
-        gs.dst = (uint32_t *)base;
-        base += (size_t)row_cap * 4u;
-        gs.c_q = (uint32_t *)base;
-        base += MOVE_ROUND * 4u;
-        gs.nidx = (uint16_t *)base;
-        base += (size_t)row_cap * 2u;
-        gs.ring = (uint16_t *)base;
-        gs.phase = 0u;
-        if (STAGED && leader) mbar_init(gs.bar, 1u);
-    }
-    __syncthreads();
-
-    const uint32_t nchunks = (n + 31u) >> 5;
-    for (uint32_t c = gwarp; c < nchunks; c += nwarps) {
-        const uint32_t i = (c << 5) + lane;
-        const bool in = i < n;
-        /* ---- ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) ------------------- */
-        const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
-        uint32_t va = 0, vs = 0;
-        if (lane < (c & 7u)) {
-            va = (uint32_t)__popc(a.sc.alive_bits[(c & ~7u) + lane]);
-            vs = (uint32_t)__popc(a.sc.split_bits[(c & ~7u) + lane]);
-        }
-        va += __shfl_xor_sync(DSIM_FULL, va, 4);
-        vs += __shfl_xor_sync(DSIM_FULL, vs, 4);
-        va += __shfl_xor_sync(DSIM_FULL, va, 2);
-        vs += __shfl_xor_sync(DSIM_FULL, vs, 2);
-        va += __shfl_xor_sync(DSIM_FULL, va, 1);
-        vs += __shfl_xor_sync(DSIM_FULL, vs, 1);
-        va = __shfl_sync(DSIM_FULL, va, 0);
-        vs = __shfl_sync(DSIM_FULL, vs, 0);
-        const uint32_t my_newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
-        const uint32_t my_crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
-        const bool my_alive = ((alive_mask >> lane) & 1u) != 0u && my_newpos < cap;
-
-        /* ---- my family's record ------------------------------------------------------------- */
-        uint64_t m_id = 0, m_culture = 0;
-        double m_stored = 0.0, m_lh = 0.0;
-        uint32_t m_loc = 0, m_size = 0, m_till_adult = 0, m_till_mut = 0, m_misc = 0, m_hs = 0;
-        uint32_t m_start = 0, m_len = 0, m_nsensed = 0, m_nnear = 0, m_hist_cnt = 0;
-        if (in) {
-            m_hs = a.cur.hs[i];
-            if (my_alive) {
-                m_loc = a.cur.loc[i];
-                m_id = a.cur.id[i];
-                m_culture = a.cur.culture[i];
-                m_stored = a.cur.stored[i];
-                m_lh = a.cur.last_harvest[i];
-                m_size = a.cur.size[i];
-                m_till_adult = a.cur.till_adult[i];
-                m_till_mut = a.cur.till_mut[i];
-                m_misc = a.cur.misc[i];
-                const RowHdr hd = a.rt.hdr[m_loc];
-                m_start = hd.start;
-                m_len = hd.len;
-                m_nsensed = hd.n_sensed;
-                m_nnear = hd.n_near;
-                m_hist_cnt = a.hv.hist_cnt[m_hs];
-            } else if (!((alive_mask >> lane) & 1u)) {
-                a.sc.dead_hs[i - my_newpos] = m_hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
-            }
-        }
-
-        /* ---- the chunk's survivors, NG at a time ------------------------------------------------ */
-        uint32_t todo = __ballot_sync(DSIM_FULL, my_alive);
-        while (todo) {
-            /* group g takes the g-th remaining survivor */
-            int myj = -1;
-#pragma unroll
-            for (uint32_t g = 0; g < NG; ++g) {
-                int j = -1;
-                if (todo) {
-                    j = __ffs((int)todo) - 1;
-                    todo &= todo - 1u;
-                }
-                if (g == grp) myj = j;
-            }
-            const bool on = myj >= 0;
-            const int src = on ? myj : 0;
-            const uint64_t fid = __shfl_sync(DSIM_FULL, m_id, src);
-            const uint64_t culture = __shfl_sync(DSIM_FULL, m_culture, src);
-            double stored = __shfl_sync(DSIM_FULL, m_stored, src);
-            const double last_harvest = __shfl_sync(DSIM_FULL, m_lh, src);
-            const uint32_t loc = __shfl_sync(DSIM_FULL, m_loc, src);
-            uint32_t size = __shfl_sync(DSIM_FULL, m_size, src);
-            const uint32_t hs = __shfl_sync(DSIM_FULL, m_hs, src);
-            const uint32_t r_start = __shfl_sync(DSIM_FULL, m_start, src);
-            const uint32_t r_len = __shfl_sync(DSIM_FULL, m_len, src);
-            const uint32_t r_nsensed = __shfl_sync(DSIM_FULL, m_nsensed, src);
-            const uint32_t n_near = __shfl_sync(DSIM_FULL, m_nnear, src);
-            const uint32_t hist_cnt = __shfl_sync(DSIM_FULL, m_hist_cnt, src);
-            const uint32_t newpos = __shfl_sync(DSIM_FULL, my_newpos, src);
-            const uint32_t crank = __shfl_sync(DSIM_FULL, my_crank, src);
-            const uint32_t misc_in = __shfl_sync(DSIM_FULL, m_misc, src);
-            const uint32_t till_adult = __shfl_sync(DSIM_FULL, m_till_adult, src);
-            const uint32_t till_mut = __shfl_sync(DSIM_FULL, m_till_mut, src);
-            const bool split = on && ((split_mask >> src) & 1u) != 0u;
-
-            const Row row = stage_row<STAGED>(a.rt, on, r_start, r_len, r_nsensed, gs, leader);
-
-            /* ---- decide_on_moving, lib.rs:830-889 -------------------------------------------- */
-            Choice ch;
-            ch.target = loc;
-            ch.max_gain = 0.0;
-            ch.t_cost = 0.0;
-            ch.m = 0.0;
-            /* sensed patches: the leading entries of the row, in ascending node order; their noise index
-             * is their position in the 2-hop list.  MOVE_ROUND per round: a lane holds KP entries G apart,
-             * and gathers all their views before using any. */
-            for (uint32_t base = 0; __any_sync(DSIM_FULL, on && base < row.n_sensed); base += MOVE_ROUND) {
-                uint32_t q[KP];
-                PatchView pv[KP];
-                bool ok[KP];
-#pragma unroll
-                for (uint32_t k = 0; k < KP; ++k) {
-                    const uint32_t e = base + k * (uint32_t)G + ln.gl;
-                    ok[k] = on && e < row.n_sensed;
-                    q[k] = 0;
-                    if (ok[k]) {
-                        q[k] = row.dst[e];
-                        pv[k] = a.ps.view[q[k]];
-                    }
-                }
-                double gain[KP], cost[KP], u[KP];
-                uint32_t ni[KP];
-#pragma unroll
-                for (uint32_t k = 0; k < KP; ++k) {
-                    const uint32_t e = base + k * (uint32_t)G + ln.gl;
-                    gain[k] = 0.0;
-                    cost[k] = 0.0;
-                    ni[k] = 0;
-                    u[k] = 0.0;
-                    if (ok[k]) {
-                        ni[k] = row.nidx[e];
-                        cost[k] = row.cost[e];
-                        gain[k] = view_quality(a, pv[k], q[k], culture, size, q[k] == loc);
-                    }
-                }
-#pragma unroll
-                for (uint32_t k = 0; k < KP; ++k)
-                    if (ok[k]) u[k] = noise_draw(a.mc, step, fid, ni[k]);
-#pragma unroll
-                for (uint32_t k = 0; k < KP; ++k) {
-                    const uint32_t e = k * (uint32_t)G + ln.gl;
-                    if (ok[k]) {
-                        gs.c_g[e] = gain[k] * u[k] - cost[k];
-                        gs.c_gain[e] = gain[k];
-                        gs.c_cost[e] = cost[k];
-                        gs.c_q[e] = q[k];
-                    }
-                }
-                __syncwarp();
-                const uint32_t left = (on && base < row.n_sensed) ? row.n_sensed - base : 0u;
-                accept_round<G>(ln, gs, on, left < MOVE_ROUND ? left : MOVE_ROUND, ch);
-                __syncwarp();
-            }
-            const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
-            const uint32_t nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
-            HistSource hsrc;
-            hsrc.hs = hs;
-            hsrc.ring_cnt = hist_cnt;
-            hsrc.virt = false;
-            hsrc.v0_patch = 0u;
-            hsrc.v0_harv = 0.0;
-            history_pass<G>(a, ln, gs, step, on, fid, row, n_near, on ? nh : 0u, hsrc, thr, ch);
-
-            /* ---- move bookkeeping, lib.rs:1826-1833 ------------------------------------------ */
-            const double harv0 = last_harvest / (double)size; /* pushed to the history */
-            stored = stored + last_harvest;
-            const uint32_t newloc = ch.target;
-            stored = stored - ch.t_cost;
-            uint32_t misc = misc_in;
-
-            /* ---- maybe_procreate + the child's move, lib.rs:1840-1855, 1869-1897 --------------- */
-            if (__any_sync(DSIM_FULL, split)) {
-                const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
-                double take = 0.0;
-                if (split) {
-                    misc = (misc & ~0xFFFFu) | n_off;
-                    take = stored * 2.0 / (double)size;
-                    stored = stored - take;
-                    size -= 2u;
-                }
-                uint64_t cid = 0;
-                uint32_t cpos = 0, chs = 0;
-                RowHdr chd;
-                chd.start = chd.len = chd.n_sensed = chd.n_near = 0u;
-                uint32_t nl0 = 0, nl1 = 0;
-                if (split) {
-                    cid = ctl->child_id_base + crank;
-                    cpos = ctl->child_pos_base + crank;
-                    const uint32_t ft = ctl->free_top;
-                    chs = (crank < ft) ? a.sc.free_hs[ft - 1u - crank] : ctl->hs_hwm + (crank - ft);
-                    chd = a.rt.hdr[newloc];
-                    nl0 = a.rt.near_off[loc];
-                    nl1 = a.rt.near_off[loc + 1];
-                }
-                Choice cc;
-                cc.target = newloc;
-                cc.max_gain = 0.0;
-                cc.t_cost = 0.0;
-                cc.m = 0.0;
-                /* the parent's row is no longer needed: reuse the buffers for the child's row */
-                __syncwarp();
-                const Row crow = stage_row<STAGED>(a.rt, split, chd.start, chd.len, chd.n_sensed, gs, leader);
-                /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
-                const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
-                for (uint32_t base = first; __any_sync(DSIM_FULL, split && base < nl1); base += MOVE_ROUND) {
-#pragma unroll
-                    for (uint32_t k = 0; k < KP; ++k) {
-                        const uint32_t e = k * (uint32_t)G + ln.gl;
-                        const uint32_t jj = base + e;
-                        if (split && jj < nl1) {
-                            const uint32_t q = a.rt.near_dst[jj];
-                            double cost = 0.0, gain = 0.0, g = DSIM_NEG_INF;
-                            if (reach_lookup(crow, q, &cost)) {
-                                gain = view_quality(a, a.ps.view[q], q, culture, 2u, q == newloc);
-                                g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
-                            }
-                            gs.c_g[e] = g;
-                            gs.c_gain[e] = gain;
-                            gs.c_cost[e] = cost;
-                            gs.c_q[e] = q;
-                        }
-                    }
-                    __syncwarp();
-                    const uint32_t left = (split && base < nl1) ? nl1 - base : 0u;
-                    accept_round<G>(ln, gs, split, left < MOVE_ROUND ? left : MOVE_ROUND, cc);
-                    __syncwarp();
-                }
-                /* child history = newest min(len, time_to_grow_adult) entries incl. the one just pushed */
-                uint32_t child_len = hist_valid + 1u;
-                if (child_len > a.mc.adult_reset) child_len = a.mc.adult_reset;
-                if (child_len > hcap) child_len = hcap;
-                const uint32_t nhc = child_len < a.mc.n_mem ? child_len : a.mc.n_mem;
-                HistSource csrc;
-                csrc.hs = hs;
-                csrc.ring_cnt = hist_cnt;
-                csrc.virt = true;
-                csrc.v0_patch = loc;
-                csrc.v0_harv = harv0;
-                history_pass<G>(a, ln, gs, step, split, cid, crow, nl1 - first, split ? nhc : 0u, csrc, thr, cc);
-
-                if (split) {
-                    if (cpos < cap && chs < ctl->hs_cap) {
-                        const size_t pb = (size_t)hs * hcap, cb = (size_t)chs * hcap;
-                        for (uint32_t k = ln.gl; k < child_len; k += (uint32_t)G) { /* chronological index k */
-                            const uint32_t nn = child_len - 1u - k;                /* newest-first index      */
-                            uint32_t hp;
-                            double hh;
-                            if (nn == 0u) {
-                                hp = loc;
-                                hh = harv0;
-                            } else {
-                                const uint32_t pos = (hist_cnt - 1u - (nn - 1u)) % hcap;
-                                hp = a.hv.hist_patch[pb + pos];
-                                hh = a.hv.hist_harv[pb + pos];
-                            }
-                            a.hv.hist_patch[cb + k] = hp;
-                            a.hv.hist_harv[cb + k] = hh;
-                        }
-                        for (uint32_t k = ln.gl; k < acap; k += (uint32_t)G) { /* adaptation: family.adaptation, lib.rs:1893 */
-                            a.hv.a_eco[(size_t)chs * acap + k] = a.hv.a_eco[(size_t)hs * acap + k];
-                            a.hv.a_cnt[(size_t)chs * acap + k] = a.hv.a_cnt[(size_t)hs * acap + k];
-                            a.hv.a_val[(size_t)chs * acap + k] = a.hv.a_val[(size_t)hs * acap + k];
-                        }
-                        if (leader) {
-                            a.hv.hist_cnt[chs] = child_len;
-                            a.hv.decay[chs] = a.hv.decay[hs];
-                            a.hv.parent[chs] = fid;
-                            a.hv.birth_index[chs] = (uint16_t)n_off;
-                            a.next.id[cpos] = cid;
-                            a.next.culture[cpos] = culture;
-                            a.next.stored[cpos] = take - cc.t_cost; /* descendant.stored_resources -= cost */
-                            a.next.last_harvest[cpos] = 0.0;
-                            a.next.loc[cpos] = cc.target;
-                            a.next.size[cpos] = 2u;
-                            a.next.till_adult[cpos] = a.mc.adult_reset;
-                            a.next.till_mut[cpos] = 0u;
-                            a.next.misc[cpos] = 0u;
-                            a.next.hs[cpos] = chs;
-                            const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
-                            if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = cc.target;
-                            a.sc.fslot[cpos] = slot;
-                        }
-                    } else if (leader) {
-                        atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
-                    }
-                }
-            }
-            /* every lane of the group has read the family's history by now (the child copied it above):
-             * the leader pushes the new entry and stores the compacted record */
-            __syncwarp();
-            if (on && leader) {
-                /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
-                const uint32_t pos = hist_cnt % hcap;
-                a.hv.hist_patch[(size_t)hs * hcap + pos] = loc;
-                a.hv.hist_harv[(size_t)hs * hcap + pos] = harv0;
-                a.hv.hist_cnt[hs] = hist_cnt + 1u;
-                a.next.id[newpos] = fid;
-                a.next.culture[newpos] = culture;
-                a.next.stored[newpos] = stored;
-                a.next.last_harvest[newpos] = 0.0;
-                a.next.loc[newpos] = newloc;
-                a.next.size[newpos] = size;
-                a.next.till_adult[newpos] = till_adult;
-                a.next.till_mut[newpos] = till_mut;
-                a.next.misc[newpos] = misc;
-                a.next.hs[newpos] = hs;
-                const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
-                a.sc.fslot[newpos] = slot;
-            }
-            __syncwarp();
-        }
-    }
+__device__ __forceinline__ bool mem_resolve(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t n) {
+    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM2, n >> 2);
+    return dsim_word(o, n & 3u) < mc.mem_lo32[n];
+}
+/* one entry, both levels (k_children: a lane per entry) */
+__device__ __forceinline__ bool mem_keep(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t n) {
+    if (n < mc.mem_always) return true;
+    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, n >> 4);
+    const uint32_t b = (dsim_word(o, (n >> 2) & 3u) >> (8u * (n & 3u))) & 0xFFu, h = mc.mem_hi8[n];
+    if (b != h) return b < h;
+    return mem_resolve(mc, step, fid, n);
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -990,27 +438,27 @@ __device__ __forceinline__ void tpf_flush(const StepArgs &a, uint32_t step, uint
     }
 }
 
-/* The remembered-patch part of decide_on_moving (lib.rs:854-867) for one thread: history entry n is
- * kept iff its keyed 32-bit draw is <= thr[n] (i.e. draw * 2^-32 < memory_n); kept entries with a
- * travel cost are candidates whose expected harvest is the remembered per-capita harvest. */
+/* The remembered-patch part of decide_on_moving (lib.rs:854-867) for one thread: the kept history entries
+ * (mem_block / mem_resolve) that have a travel cost are candidates whose expected harvest is the remembered
+ * per-capita harvest. */
 __device__ __forceinline__ void tpf_history(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
-                                            uint32_t hs, uint32_t ring_cnt, uint32_t nh, const uint32_t *thr, Choice &ch) {
+                                            uint32_t hs, uint32_t ring_cnt, uint32_t nh, Choice &ch) {
     uint16_t kept[TPF_KEPT];
     uint32_t cnt = 0;
-    for (uint32_t n8 = 0; n8 < nh; n8 += 8u) { /* two independent Philox blocks per iteration (entry n: block n>>2, word n&3) */
-        const dsim_u4 o0 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, n8 >> 2);
-        const dsim_u4 o1 = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_MEM, (n8 >> 2) + 1u);
-        /* the table is padded to a multiple of 8 entries; the index is warp-uniform (broadcast) */
-        const uint4 t0 = *reinterpret_cast<const uint4 *>(thr + n8), t1 = *reinterpret_cast<const uint4 *>(thr + n8 + 4u);
-        uint32_t mask = (o0.x <= t0.x ? 1u : 0u) | (o0.y <= t0.y ? 2u : 0u) | (o0.z <= t0.z ? 4u : 0u) | (o0.w <= t0.w ? 8u : 0u) |
-                        (o1.x <= t1.x ? 16u : 0u) | (o1.y <= t1.y ? 32u : 0u) | (o1.z <= t1.z ? 64u : 0u) | (o1.w <= t1.w ? 128u : 0u);
-        if (nh - n8 < 8u) mask &= (1u << (nh - n8)) - 1u;
+    for (uint32_t n16 = 0; n16 < nh; n16 += 16u) {
+        uint32_t undecided;
+        uint32_t mask = mem_block(a.mc, step, fid, n16 >> 4, nh, &undecided);
+        while (undecided) {
+            const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
+            undecided &= undecided - 1u;
+            if (mem_resolve(a.mc, step, fid, n16 + b)) mask |= 1u << b;
+        }
         if (mask == 0u) continue; /* the common case beyond the first few dozen entries */
         while (mask) {
-            kept[cnt++] = (uint16_t)(n8 + (uint32_t)__ffs((int)mask) - 1u);
+            kept[cnt++] = (uint16_t)(n16 + (uint32_t)__ffs((int)mask) - 1u);
             mask &= mask - 1u;
         }
-        if (cnt > TPF_KEPT - 8u) {
+        if (cnt > TPF_KEPT - 16u) {
             tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
             cnt = 0;
         }
@@ -1019,15 +467,11 @@ __device__ __forceinline__ void tpf_history(const StepArgs &a, uint32_t step, ui
 }
 
 __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepArgs a) {
-    DSIM_DYN_SMEM(smem_raw);
     DevCtl *ctl = a.ctl;
     const uint32_t n = ctl->n_cur[a.parity];
     const uint32_t step = ctl->t;
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap;
-    uint32_t *thr = (uint32_t *)smem_raw; /* keep thresholds: read with a warp-uniform index (broadcast) */
-    for (uint32_t k = threadIdx.x; k < ((a.mc.n_mem + 7u) & ~7u); k += blockDim.x) thr[k] = k < a.mc.n_mem ? a.mc.mem_thr[k] : 0u;
-    __syncthreads();
 
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         /* Families are visited in the patch-grouped order that part 2 of the previous step left in
@@ -1069,21 +513,18 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
         ch.t_cost = 0.0;
         ch.m = 0.0;
         /* sensed patches: the leading entries of the row in ascending node order, four per iteration.
-         * Software pipeline: the node ids are requested two blocks ahead, the 16-byte views, costs and noise
-         * indices one block ahead, so an iteration never waits for its own loads; entries 2k, 2k+1 share one
-         * Philox block when their noise indices do.  Rows are padded to multiples of 8 entries (padding node
+         * Software pipeline: the node ids are requested two blocks ahead, the 16-byte views and costs one block
+         * ahead, so an iteration never waits for its own loads; entries 2k, 2k+1 share one Philox block.  Rows are padded to multiples of 8 entries (padding node
          * id 0xFFFFFFFF is never dereferenced), so the 16-byte loads never leave the row. */
         {
             const uint32_t ns = row.n_sensed;
             uint4 q_cur = make_uint4(0u, 0u, 0u, 0u), q_nxt = make_uint4(0u, 0u, 0u, 0u);
             double2 c01_cur = make_double2(0.0, 0.0), c23_cur = make_double2(0.0, 0.0);
-            uint2 nn_cur = make_uint2(0u, 0u);
             PatchView pv_cur[4];
             if (ns > 0u) {
                 q_cur = *reinterpret_cast<const uint4 *>(row.dst);
                 c01_cur = *reinterpret_cast<const double2 *>(row.cost);
                 c23_cur = *reinterpret_cast<const double2 *>(row.cost + 2u);
-                nn_cur = *reinterpret_cast<const uint2 *>(row.nidx);
                 if (ns > 4u) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + 4u);
                 const uint32_t q0[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
 #pragma unroll
@@ -1093,7 +534,6 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
             for (uint32_t e = 0; e < ns; e += 4u) {
                 const uint32_t q[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
                 const double cost[4] = {c01_cur.x, c01_cur.y, c23_cur.x, c23_cur.y};
-                const uint32_t ni[4] = {nn_cur.x & 0xFFFFu, nn_cur.x >> 16, nn_cur.y & 0xFFFFu, nn_cur.y >> 16};
                 const uint32_t m = ns - e < 4u ? ns - e : 4u;
                 PatchView pv[4];
 #pragma unroll
@@ -1106,19 +546,17 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
                         if (e + 4u + k < ns) pv_cur[k] = a.ps.view[qn[k]];
                     c01_cur = *reinterpret_cast<const double2 *>(row.cost + e + 4u);
                     c23_cur = *reinterpret_cast<const double2 *>(row.cost + e + 6u);
-                    nn_cur = *reinterpret_cast<const uint2 *>(row.nidx + e + 4u);
                     q_cur = q_nxt;
                     if (e + 8u < ns) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + e + 8u);
                 }
+                /* noise index of a sensed patch = its position among the sensed patches with a travel cost = e + k */
                 double u[4];
 #pragma unroll
                 for (uint32_t k = 0; k < 4u; k += 2u) {
                     if (k < m) {
-                        const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, noise_block(ni[k]));
-                        u[k] = noise_pick(o, ni[k]);
-                        if (k + 1u < m)
-                            u[k + 1] = (noise_block(ni[k + 1]) == noise_block(ni[k])) ? noise_pick(o, ni[k + 1])
-                                                                                       : noise_draw(a.mc, step, fid, ni[k + 1]);
+                        const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, noise_block(e + k));
+                        u[k] = dsim_u53(o.x, o.y);
+                        u[k + 1] = dsim_u53(o.z, o.w);
                     }
                 }
 #pragma unroll
@@ -1132,7 +570,7 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
         }
         const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
         const uint32_t nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
-        tpf_history(a, step, fid, row, hd.n_near, hs, hist_cnt, nh, thr, ch);
+        tpf_history(a, step, fid, row, hd.n_near, hs, hist_cnt, nh, ch);
 
         /* ---- move bookkeeping, lib.rs:1826-1833 ---------------------------------------------- */
         const double harv0 = last_harvest / (double)size;
@@ -1186,6 +624,356 @@ __global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepAr
     }
 }
 
+/* ------------------------------------------------------------------------------------------ *
+ * part 1c (default): move, one BLOCK per tile of 32 families, work items spread over all threads.
+ *
+ * The decision of one family is a short ORDERED scan (lib.rs:918-927) over ~60 sensed patches and ~18
+ * remembered patches, but everything that feeds the scan is independent per candidate: 40 Philox blocks
+ * of memory draws, one Philox block per pair of sensed patches plus two 16-byte view gathers, and per
+ * remembered patch a ring read, a reach-row look-up and one Philox block.  A thread per family
+ * serialises all of that behind its own memory round trips; a warp per family replicates the scan in
+ * 32 lanes.  Here a block of 256 threads takes 32 families and alternates between
+ *   - ITEM phases: (family, work item) pairs are dealt round-robin to all 256 threads; every load of
+ *     the tile is in flight at once; results (noised net gain g, expected harvest, row position) go to
+ *     per-family candidate slots in shared memory;
+ *   - SCAN phases: lane f of warp 0 runs family f's ordered acceptance scan over its slots.
+ * Several blocks are resident per SM, so scan phases of one block overlap item phases of the others.
+ * Candidate slots, kept-entry lists and draw masks have fixed capacities; longer candidate streams are
+ * processed in rounds, so no size is assumed about rows or histories.
+ * ------------------------------------------------------------------------------------------ */
+#define BLK_FAM 32u       /* families per tile */
+#define BLK_THREADS 256u
+/* the capacities can be overridden at compile time: the CPU test-suite builds a variant with tiny ones so
+ * that every multi-round path runs */
+#ifndef BLK_CAND
+#define BLK_CAND 64u      /* candidate slots per family and round (even) */
+#endif
+#ifndef BLK_HCHUNK
+#define BLK_HCHUNK 1024u  /* history entries whose draws are evaluated per chunk (a multiple of 32) */
+#endif
+#ifndef BLK_EQ
+#define BLK_EQ 256u       /* undecided top bytes queued per chunk (expected 32 * 625 / 256 = 78) */
+#endif
+#define BLK_GSTRIDE (BLK_CAND + 1u)        /* slot stride in doubles: odd, so lane f of a scan and lane j of an item phase never collide */
+#define BLK_MSTRIDE (BLK_HCHUNK / 16u + 2u) /* 16-bit masks per family, padded; even: 32-bit atomics stay inside a family */
+
+struct BlkShared {
+    double g[BLK_FAM * BLK_GSTRIDE];    /* gain * U - cost of the candidate in a slot; -inf = no candidate */
+    double gain[BLK_FAM * BLK_GSTRIDE];
+    uint64_t fid[BLK_FAM], culture[BLK_FAM];
+    uint32_t ridx[BLK_FAM * BLK_CAND];  /* position of the candidate in the family's reach row (node, cost) */
+    uint32_t loc[BLK_FAM], size[BLK_FAM], hs[BLK_FAM], hist_cnt[BLK_FAM], nh[BLK_FAM];
+    uint32_t row_start[BLK_FAM], row_len[BLK_FAM], ns[BLK_FAM], n_near[BLK_FAM], cnt[BLK_FAM];
+    uint32_t eq_q[BLK_EQ];              /* (family << 16) | entry index in the chunk */
+    uint32_t eq_cnt, more, max_cnt, max_ns, max_nh, pad_[3];
+    uint16_t kept[BLK_FAM * BLK_CAND];  /* kept history entries of the round, relative to the chunk */
+    uint16_t masks[BLK_FAM * BLK_MSTRIDE];
+};
+
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(DSIM_FULL, v, d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
+    DSIM_DYN_SMEM(smem_raw);
+    BlkShared &S = *reinterpret_cast<BlkShared *>(smem_raw);
+    DevCtl *ctl = a.ctl;
+    const uint32_t n = ctl->n_cur[a.parity];
+    const uint32_t step = ctl->t;
+    const uint32_t cap = ctl->cap;
+    const uint32_t hcap = a.hv.hcap;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t ntiles = (n + BLK_FAM - 1u) / BLK_FAM;
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        /* ---- prologue: thread f < 32 owns family f of the tile ------------------------------------ */
+        bool live = false, split = false;
+        uint32_t i = 0, c = 0, lt = 0, newpos = 0, vs = 0, split_mask = 0, misc = 0, m_loc = 0, m_hs = 0, m_size = 0, m_hist_cnt = 0;
+        uint64_t m_fid = 0, m_culture = 0;
+        double stored = 0.0, last_harvest = 0.0;
+        const uint32_t *r_dst = nullptr;
+        const double *r_cost = nullptr;
+        if (tid < BLK_FAM) {
+            /* Families are visited in the patch-grouped order that part 2 of the previous step left in
+             * `members`: co-resident families (same reach row, same candidate views) share a tile.  The
+             * order never influences results. */
+            const uint32_t t = tile * BLK_FAM + tid;
+            uint32_t ns = 0, nh = 0;
+            if (t < n) {
+                i = a.sc.members[t];
+                c = i >> 5;
+                lt = (1u << (i & 31u)) - 1u;
+                /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
+                const uint32_t alive_mask = a.sc.alive_bits[c];
+                split_mask = a.sc.split_bits[c];
+                uint32_t va = 0;
+                for (uint32_t w = c & ~7u; w < c; ++w) {
+                    va += (uint32_t)__popc(a.sc.alive_bits[w]);
+                    vs += (uint32_t)__popc(a.sc.split_bits[w]);
+                }
+                newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
+                m_hs = a.cur.hs[i];
+                if (!((alive_mask >> (i & 31u)) & 1u)) {
+                    a.sc.dead_hs[i - newpos] = m_hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
+                } else if (newpos < cap) {           /* else: capacity error already flagged by k_control */
+                    live = true;
+                    split = ((split_mask >> (i & 31u)) & 1u) != 0u;
+                    m_loc = a.cur.loc[i];
+                    m_fid = a.cur.id[i];
+                    m_culture = a.cur.culture[i];
+                    stored = a.cur.stored[i];
+                    last_harvest = a.cur.last_harvest[i];
+                    m_size = a.cur.size[i];
+                    misc = a.cur.misc[i];
+                    const RowHdr hd = a.rt.hdr[m_loc];
+                    m_hist_cnt = a.hv.hist_cnt[m_hs];
+                    const uint32_t hist_valid = m_hist_cnt < hcap ? m_hist_cnt : hcap;
+                    nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
+                    ns = hd.n_sensed;
+                    r_dst = a.rt.dst + hd.start;
+                    r_cost = a.rt.cost + hd.start;
+                    S.fid[tid] = m_fid;
+                    S.culture[tid] = m_culture;
+                    S.loc[tid] = m_loc;
+                    S.size[tid] = m_size;
+                    S.hs[tid] = m_hs;
+                    S.hist_cnt[tid] = m_hist_cnt;
+                    S.row_start[tid] = hd.start;
+                    S.row_len[tid] = hd.len;
+                    S.n_near[tid] = hd.n_near;
+                }
+            }
+            S.ns[tid] = ns;
+            S.nh[tid] = nh;
+            const uint32_t mx_ns = warp_max_u32(ns), mx_nh = warp_max_u32(nh);
+            if (tid == 0) {
+                S.max_ns = mx_ns;
+                S.max_nh = mx_nh;
+                S.eq_cnt = 0u;
+            }
+        }
+        __syncthreads();
+        const uint32_t max_ns = S.max_ns, max_nh = S.max_nh;
+
+        /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------------- */
+        Choice ch;
+        ch.target = m_loc;
+        ch.max_gain = 0.0;
+        ch.t_cost = 0.0;
+        ch.m = 0.0;
+
+        /* sensed patches: the leading entries of the reach row, in ascending node order; item = a pair of
+         * entries (one Philox block: the noise index of a sensed patch is its position among the sensed
+         * patches that have a travel cost, i.e. its position in the row) */
+        for (uint32_t base = 0; base < max_ns; base += BLK_CAND) {
+            const uint32_t span = max_ns - base < BLK_CAND ? max_ns - base : BLK_CAND;
+            const uint32_t pairs = (span + 1u) >> 1;
+            for (uint32_t it = tid; it < BLK_FAM * pairs; it += BLK_THREADS) {
+                const uint32_t f = it / pairs, j = it - f * pairs;
+                const uint32_t e0 = base + 2u * j, ns = S.ns[f];
+                if (e0 >= ns) continue;
+                const uint32_t start = S.row_start[f];
+                /* rows start at multiples of 8 entries and are padded to multiples of 8: aligned 8/16-byte loads
+                 * (the padding node id 0xFFFFFFFF is never dereferenced) */
+                const uint2 qq = *reinterpret_cast<const uint2 *>(a.rt.dst + start + e0);
+                const double2 cc = *reinterpret_cast<const double2 *>(a.rt.cost + start + e0);
+                const bool two = e0 + 1u < ns;
+                const PatchView v0 = a.ps.view[qq.x];
+                PatchView v1 = v0;
+                if (two) v1 = a.ps.view[qq.y];
+                const uint64_t fid = S.fid[f], culture = S.culture[f];
+                const uint32_t loc = S.loc[f], size = S.size[f];
+                const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, e0 >> 1);
+                const double gain0 = view_quality(a, v0, qq.x, culture, size, qq.x == loc);
+                S.g[f * BLK_GSTRIDE + 2u * j] = gain0 * dsim_u53(o.x, o.y) - cc.x;
+                S.gain[f * BLK_GSTRIDE + 2u * j] = gain0;
+                if (two) {
+                    const double gain1 = view_quality(a, v1, qq.y, culture, size, qq.y == loc);
+                    S.g[f * BLK_GSTRIDE + 2u * j + 1u] = gain1 * dsim_u53(o.z, o.w) - cc.y;
+                    S.gain[f * BLK_GSTRIDE + 2u * j + 1u] = gain1;
+                }
+            }
+            __syncthreads();
+            if (tid < BLK_FAM && live) {
+                const uint32_t ns = S.ns[tid];
+                const uint32_t cnt = ns > base ? (ns - base < BLK_CAND ? ns - base : BLK_CAND) : 0u;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const double g = S.g[tid * BLK_GSTRIDE + k];
+                    if (g > ch.m) accept_one(ch, g, S.gain[tid * BLK_GSTRIDE + k], r_cost[base + k], r_dst[base + k]);
+                }
+            }
+            __syncthreads();
+        }
+
+        /* remembered patches, lib.rs:854-867 */
+        for (uint32_t hbase = 0; hbase < max_nh; hbase += BLK_HCHUNK) {
+            /* draws: item = (family, 16 history entries).  Blocks whose thresholds have a non-zero top byte
+             * (the newest ~100 entries) take the full byte comparison; they are dealt separately from the
+             * others so that no warp runs both code paths. */
+            const uint32_t span = max_nh - hbase < BLK_HCHUNK ? max_nh - hbase : BLK_HCHUNK;
+            const uint32_t nblk = (span + 15u) >> 4, jb0 = hbase >> 4;
+            const uint32_t n_head = a.mc.mem_head > jb0 ? (a.mc.mem_head - jb0 < nblk ? a.mc.mem_head - jb0 : nblk) : 0u;
+            for (uint32_t pass = 0; pass < 2u; ++pass) {
+                const uint32_t j_lo = pass ? n_head : 0u, nj = pass ? nblk - n_head : n_head;
+                for (uint32_t it = tid; it < BLK_FAM * nj; it += BLK_THREADS) {
+                    const uint32_t f = it / nj, j = j_lo + (it - f * nj);
+                    const uint32_t nh = S.nh[f];
+                    uint32_t kept = 0u;
+                    if (hbase + 16u * j < nh) {
+                        const uint64_t fid = S.fid[f];
+                        uint32_t undecided;
+                        kept = mem_block(a.mc, step, fid, jb0 + j, nh, &undecided);
+                        while (undecided) {
+                            const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
+                            undecided &= undecided - 1u;
+                            const uint32_t slot = atomicAdd(&S.eq_cnt, 1u);
+                            if (slot < BLK_EQ)
+                                S.eq_q[slot] = (f << 16) | (16u * j + b);
+                            else if (mem_resolve(a.mc, step, fid, hbase + 16u * j + b)) /* queue full: decide it here */
+                                kept |= 1u << b;
+                        }
+                    }
+                    S.masks[f * BLK_MSTRIDE + j] = (uint16_t)kept;
+                }
+            }
+            __syncthreads();
+            { /* the queued undecided entries: one Philox block of the MEM2 stream each */
+                const uint32_t nq = S.eq_cnt < BLK_EQ ? S.eq_cnt : BLK_EQ;
+                for (uint32_t k = tid; k < nq; k += BLK_THREADS) {
+                    const uint32_t f = S.eq_q[k] >> 16, e = S.eq_q[k] & 0xFFFFu;
+                    if (mem_resolve(a.mc, step, S.fid[f], hbase + e)) {
+                        const uint32_t at = f * BLK_MSTRIDE + (e >> 4); /* 16-bit mask index */
+                        atomicOr(reinterpret_cast<uint32_t *>(S.masks) + (at >> 1), (1u << (e & 15u)) << ((at & 1u) * 16u));
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) S.eq_cnt = 0u;
+
+            /* rounds of at most BLK_CAND kept entries per family (one round unless a family keeps more) */
+            uint32_t cj = 0, cur = 0; /* compaction cursor of thread f: mask block and its remaining bits */
+            const uint32_t my_nblk = (tid < BLK_FAM && S.nh[tid] > hbase) ? ((S.nh[tid] - hbase < BLK_HCHUNK ? S.nh[tid] - hbase : BLK_HCHUNK) + 15u) >> 4 : 0u;
+            if (my_nblk > 0u) cur = S.masks[tid * BLK_MSTRIDE];
+            for (;;) {
+                if (tid < BLK_FAM) {
+                    uint32_t cnt = 0;
+                    for (;;) {
+                        while (cur == 0u && cj + 1u < my_nblk) cur = S.masks[tid * BLK_MSTRIDE + (++cj)];
+                        if (cur == 0u || cnt == BLK_CAND) break;
+                        S.kept[tid * BLK_CAND + cnt++] = (uint16_t)(16u * cj + (uint32_t)__ffs((int)cur) - 1u);
+                        cur &= cur - 1u;
+                    }
+                    S.cnt[tid] = cnt;
+                    const uint32_t more = __ballot_sync(DSIM_FULL, cur != 0u), mx = warp_max_u32(cnt);
+                    if (tid == 0) {
+                        S.more = more;
+                        S.max_cnt = mx;
+                    }
+                }
+                __syncthreads();
+                const uint32_t per = S.max_cnt, more = S.more;
+                /* item = one kept entry: ring entry -> row look-up -> cost, one Philox block for the noise */
+                for (uint32_t it = tid; it < BLK_FAM * per; it += BLK_THREADS) {
+                    const uint32_t f = it / per, k = it - f * per;
+                    if (k >= S.cnt[f]) continue;
+                    const uint32_t nn = hbase + S.kept[f * BLK_CAND + k]; /* entry nn, 0 = newest */
+                    const uint32_t newest = (S.hist_cnt[f] - 1u) % hcap;
+                    const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
+                    const size_t at = (size_t)S.hs[f] * hcap + pos;
+                    const uint32_t q = a.hv.hist_patch[at];
+                    const double gain = a.hv.hist_harv[at];
+                    RowHdr hd;
+                    hd.start = S.row_start[f];
+                    hd.len = S.row_len[f];
+                    hd.n_sensed = S.ns[f];
+                    hd.n_near = S.n_near[f];
+                    const RowPtr row = row_of(a.rt, S.loc[f], hd);
+                    const uint32_t idx = row_find(row, q);
+                    double g = DSIM_NEG_INF; /* no travel cost from here: not a candidate, lib.rs:869 */
+                    if (idx != 0xFFFFFFFFu) g = gain * noise_draw(a.mc, step, S.fid[f], hd.n_near + nn) - row.cost[idx];
+                    S.g[f * BLK_GSTRIDE + k] = g;
+                    S.gain[f * BLK_GSTRIDE + k] = gain;
+                    S.ridx[f * BLK_CAND + k] = idx;
+                }
+                __syncthreads();
+                if (tid < BLK_FAM && live) {
+                    const uint32_t cnt = S.cnt[tid];
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const double g = S.g[tid * BLK_GSTRIDE + k];
+                        if (g > ch.m) {
+                            const uint32_t idx = S.ridx[tid * BLK_CAND + k];
+                            accept_one(ch, g, S.gain[tid * BLK_GSTRIDE + k], r_cost[idx], r_dst[idx]);
+                        }
+                    }
+                }
+                if (more == 0u) break;
+                /* the next round's compaction is done by the threads that just scanned; its item phase
+                 * starts after the barrier above */
+            }
+            __syncthreads();
+        }
+
+        /* ---- epilogue: thread f ------------------------------------------------------------------- */
+        if (tid < BLK_FAM && live) {
+            /* move bookkeeping, lib.rs:1826-1833 */
+            uint32_t size = m_size;
+            const double harv0 = last_harvest / (double)size;
+            stored = stored + last_harvest;
+            const uint32_t newloc = ch.target;
+            stored = stored - ch.t_cost;
+            {
+                /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
+                const uint32_t pos = m_hist_cnt % hcap;
+                a.hv.hist_patch[(size_t)m_hs * hcap + pos] = m_loc;
+                a.hv.hist_harv[(size_t)m_hs * hcap + pos] = harv0;
+                a.hv.hist_cnt[m_hs] = m_hist_cnt + 1u;
+            }
+            /* maybe_procreate, lib.rs:1869-1897: the child moves in k_children */
+            if (split) {
+                const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
+                const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
+                misc = (misc & ~0xFFFFu) | n_off;
+                const double take = stored * 2.0 / (double)size;
+                stored = stored - take;
+                size -= 2u;
+                ChildTask t;
+                t.parent_id = m_fid;
+                t.culture = m_culture;
+                t.take = take;
+                t.old_loc = m_loc;
+                t.new_loc = newloc;
+                t.parent_hs = m_hs;
+                t.hist_cnt = m_hist_cnt + 1u;
+                t.n_off = n_off;
+                t.pad_ = 0u;
+                a.sc.child_task[crank] = t;
+            }
+            a.next.id[newpos] = m_fid;
+            a.next.culture[newpos] = m_culture;
+            a.next.stored[newpos] = stored;
+            a.next.last_harvest[newpos] = 0.0;
+            a.next.loc[newpos] = newloc;
+            a.next.size[newpos] = size;
+            a.next.till_adult[newpos] = a.cur.till_adult[i];
+            a.next.till_mut[newpos] = a.cur.till_mut[i];
+            a.next.misc[newpos] = misc;
+            a.next.hs[newpos] = m_hs;
+            if (!a.mg.enabled || (newloc >= a.mg.own_lo && newloc < a.mg.own_hi)) {
+                const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
+                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
+                a.sc.fslot[newpos] = slot;
+            } else {
+                a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
+            }
+        }
+    }
+}
+
 /* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in
  * lane order: a candidate is accepted iff g > m with m as left by the previous acceptance. */
 __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double g, double gain, double cost, uint32_t q,
@@ -1209,7 +997,7 @@ __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double 
 __global__ void __launch_bounds__(128) k_children(StepArgs a) {
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
-    const uint32_t n_children = a.children_inline ? 0u : ctl->n_children;
+    const uint32_t n_children = ctl->n_children;
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1237,21 +1025,24 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
         /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
         const uint32_t nl0 = a.rt.near_off[t.old_loc], nl1 = a.rt.near_off[t.old_loc + 1];
         const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
+        uint32_t n_considered = 0; /* noise index = ordinal among the sensed patches that have a travel cost */
         for (uint32_t base = first; base < nl1; base += 32u) {
             const uint32_t jj = base + lane;
             bool cand = false;
             double g = 0.0, gain = 0.0, cost = 0.0;
-            uint32_t q = 0;
+            uint32_t q = 0, k = 0xFFFFFFFFu;
             if (jj < nl1) {
                 q = a.rt.near_dst[jj];
-                const uint32_t k = row_find(row, q);
-                if (k != 0xFFFFFFFFu) {
-                    cost = row.cost[k];
-                    gain = view_quality(a, a.ps.view[q], q, t.culture, 2u, q == t.new_loc);
-                    g = gain * noise_draw(a.mc, step, cid, jj - first) - cost;
-                    cand = true;
-                }
+                k = row_find(row, q);
+                cand = k != 0xFFFFFFFFu;
             }
+            const uint32_t cmask = __ballot_sync(DSIM_FULL, cand);
+            if (cand) {
+                cost = row.cost[k];
+                gain = view_quality(a, a.ps.view[q], q, t.culture, 2u, q == t.new_loc);
+                g = gain * noise_draw(a.mc, step, cid, n_considered + (uint32_t)__popc(cmask & ((1u << lane) - 1u))) - cost;
+            }
+            n_considered += (uint32_t)__popc(cmask);
             accept_scan_warp(cc, cand, g, gain, cost, q, lane);
         }
         /* history = the parent's newest min(len, time_to_grow_adult) entries, the one pushed this step included */
@@ -1264,18 +1055,15 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             bool cand = false;
             double g = 0.0, gain = 0.0, cost = 0.0;
             uint32_t q = 0;
-            if (n < nhc) {
-                const dsim_u4 o = dsim_draw(stream_of(a.mc), step, cid, DSIM_P_MEM, n >> 2); /* entry n: block n>>2, word n&3 */
-                if (dsim_word(o, n & 3u) <= a.mc.mem_thr[n]) {
-                    const uint32_t pos = (t.hist_cnt - 1u - n) % hcap;
-                    q = a.hv.hist_patch[pb + pos];
-                    gain = a.hv.hist_harv[pb + pos];
-                    const uint32_t k = row_find(row, q);
-                    if (k != 0xFFFFFFFFu) {
-                        cost = row.cost[k];
-                        g = gain * noise_draw(a.mc, step, cid, (nl1 - first) + n) - cost;
-                        cand = true;
-                    }
+            if (n < nhc && mem_keep(a.mc, step, cid, n)) {
+                const uint32_t pos = (t.hist_cnt - 1u - n) % hcap;
+                q = a.hv.hist_patch[pb + pos];
+                gain = a.hv.hist_harv[pb + pos];
+                const uint32_t k = row_find(row, q);
+                if (k != 0xFFFFFFFFu) {
+                    cost = row.cost[k];
+                    g = gain * noise_draw(a.mc, step, cid, (nl1 - first) + n) - cost;
+                    cand = true;
                 }
             }
             accept_scan_warp(cc, cand, g, gain, cost, q, lane);
@@ -1939,23 +1727,12 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     switch (which) {
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
     case DSIM_K_CONTROL: DSIM_LAUNCH(k_control, 1, CTL_THREADS, 0, s, a); break;
-    case DSIM_K_MOVE: {
-        if (!a.children_inline) { /* default: one thread per family */
-            DSIM_LAUNCH(k_move_tpf, grid_for(g, 2 * TPF_MIN_BLOCKS), TPF_THREADS, move_smem_table(a.mc.n_mem), s, a);
-            break;
-        }
-        /* cooperative variant: rows up to g.row_cap entries are staged in shared memory by TMA; longer
-         * rows (or g.row_cap == 0) are read in place */
-        const uint32_t groups = (MOVE_THREADS / 32) * (32 / MOVE_GROUP);
-        if (g.row_cap > 0u) {
-            const uint32_t smem = move_smem_table(a.mc.n_mem) + groups * move_smem_per_group(g.row_cap);
-            DSIM_LAUNCH((k_move<true, MOVE_GROUP>), grid_for(g, g.move_blocks_per_sm), MOVE_THREADS, smem, s, a, g.row_cap);
-        } else {
-            const uint32_t smem = move_smem_table(a.mc.n_mem) + groups * move_smem_per_group(0u);
-            DSIM_LAUNCH((k_move<false, MOVE_GROUP>), grid_for(g, 4), MOVE_THREADS, smem, s, a, 0u);
-        }
+    case DSIM_K_MOVE:
+        if (a.move_tpf) /* test / comparison variant: one thread per family */
+            DSIM_LAUNCH(k_move_tpf, grid_for(g, 2 * TPF_MIN_BLOCKS), TPF_THREADS, 0, s, a);
+        else
+            DSIM_LAUNCH(k_move_blk, grid_for(g, 16), BLK_THREADS, sizeof(BlkShared), s, a);
         break;
-    }
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
@@ -1981,31 +1758,11 @@ void dsim_launch_census(const PatchState &ps, const FamCore &f, uint32_t n, uint
     DSIM_LAUNCH(k_reset_cnt, grid_for(g, 4), 256, 0, s, ps, (const uint32_t *)occ, (const DevCtl *)ctl, parity);
 }
 
-int dsim_configure_kernels(LaunchGeom *g, uint32_t max_row, uint32_t n_mem) {
-    /* shared-memory budget of k_move: keep-threshold table + one row buffer, candidate round and ring
-     * per group; stage rows when at least one block fits on an SM */
-    g->row_cap = 0u;
-    g->move_blocks_per_sm = 4u;
-    const uint32_t row_cap = (max_row + 7u) & ~7u;
-    const uint32_t groups = (MOVE_THREADS / 32) * (32 / MOVE_GROUP);
-    uint32_t smem = move_smem_table(n_mem) + groups * move_smem_per_group(0u);
-    if (row_cap != 0u && !g->force_global_rows) {
-        const uint32_t staged = move_smem_table(n_mem) + groups * move_smem_per_group(row_cap);
-        if (staged <= 200u * 1024u) {
-            smem = staged;
-            g->row_cap = row_cap;
-        }
-    }
+int dsim_configure_kernels(LaunchGeom *g) {
+    (void)g;
 #if !defined(DSIM_EMU)
-    if (smem > 48u * 1024u) {
-        cudaError_t e = g->row_cap ? cudaFuncSetAttribute(k_move<true, MOVE_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                   : cudaFuncSetAttribute(k_move<false, MOVE_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_move_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkShared));
+    if (e != cudaSuccess) return (int)e;
 #endif
-    uint32_t per_sm = (220u * 1024u) / (smem + 1024u);
-    if (per_sm > 8u) per_sm = 8u;
-    if (per_sm < 1u) per_sm = 1u;
-    g->move_blocks_per_sm = per_sm;
     return 0;
 }

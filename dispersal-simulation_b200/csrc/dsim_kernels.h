@@ -19,19 +19,16 @@ struct StepArgs {
     uint32_t parity;   /* index of `cur` (0/1): ctl->n_cur[parity] families */
     uint32_t occ_par;  /* occ[occ_par] / n_occ[occ_par] collect this step's occupied nodes, [occ_par ^ 1] hold last step's */
     MgInfo mg;
-    uint32_t children_inline; /* 1: the (cooperative) move kernel also moves the children; 0: k_children does */
+    uint32_t move_tpf; /* 1: k_move_tpf (one thread per family) instead of k_move_blk (DSIM_OPT_MOVE_THREAD_PER_FAMILY) */
     uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
 };
 
 struct LaunchGeom {
     uint32_t n_sm;               /* grids are multiples of the SM count (148 on B200); kernels are grid-stride */
-    uint32_t row_cap;            /* reach-row capacity of k_move's shared-memory staging; 0 = read rows in place */
-    uint32_t move_blocks_per_sm;
-    uint32_t force_global_rows;  /* test knob: never stage */
 };
 
-/* choose the k_move variant for a reach table whose longest (padded) row has max_row entries */
-int dsim_configure_kernels(LaunchGeom *g, uint32_t max_row, uint32_t n_mem);
+/* one-time function attributes (dynamic shared memory of k_move_blk) */
+int dsim_configure_kernels(LaunchGeom *g);
 
 enum {
     DSIM_K_LIFECYCLE = 0,

@@ -18,13 +18,14 @@
 #endif
 
 enum dsim_purpose : uint32_t {
-    DSIM_P_MEM = 1,     /* remembered-patch sampling, lib.rs:859; entity = family id           */
+    DSIM_P_MEM = 1,     /* remembered-patch sampling, lib.rs:859 (top byte of the draw); entity = family id */
     DSIM_P_NOISE = 2,   /* resource_uncertainty, lib.rs:1317; entity = family id               */
     DSIM_P_SHUF = 3,    /* shuffle key, lib.rs:1333; entity = family id                        */
     DSIM_P_FIGHT = 4,   /* fight_is_deadly x2, lib.rs:1219,1226; entity = newcomer family id   */
     DSIM_P_PIVOT = 5,   /* select_pivot_family, lib.rs:1295; entity = node id                  */
     DSIM_P_MUT = 6,     /* mutation clock and bit, lib.rs:1270-1285; entity = family id        */
     DSIM_P_REGROW = 7,  /* recover_resources_proportion, lib.rs:1309; entity = node id         */
+    DSIM_P_MEM2 = 8,    /* low 32 bits of the remembered-patch draw, lib.rs:859; entity = family id */
     /* workload generation only (dsim_synth) */
     DSIM_P_SYN_EDGE = 32, DSIM_P_SYN_POPCAP = 33, DSIM_P_SYN_FAMILY = 34, DSIM_P_SYN_CULTURE = 35,
     DSIM_P_SYN_HIST = 36, DSIM_P_SYN_SITE = 37

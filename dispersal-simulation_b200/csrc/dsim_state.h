@@ -144,8 +144,14 @@ struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed
     uint32_t n_mem;          /* history entries the memory loop can still sample (lib.rs:856)       */
     uint32_t n_nodes;
     uint32_t k0, k1;         /* Philox key = seed                                                  */
-    const uint32_t *mem_thr; /* [n_mem] history entry n is kept iff its 32-bit draw <= mem_thr[n], i.e. iff
-                                draw * 2^-32 < memory after n decays (lib.rs:847-864)                */
+    /* History entry n is kept iff U_n < memory after n decays (lib.rs:847-864), U_n = (B_n 2^32 + W_n) 2^-40 with
+     * B_n a byte of the MEM stream and W_n a word of the MEM2 stream, i.e. iff (B_n, W_n) < C_n = ceil(memory_n 2^40)
+     * lexicographically: B_n < mem_hi8[n], or B_n == mem_hi8[n] and W_n < mem_lo32[n] (W_n is only drawn then).
+     * Both tables are zero-padded to a multiple of 16 entries. */
+    const uint8_t *mem_hi8;  /* C_n >> 32 (entries n < mem_always have C_n = 2^40 and are always kept) */
+    const uint32_t *mem_lo32;/* C_n & 0xFFFFFFFF                                                   */
+    uint32_t mem_always;     /* leading entries with memory_n >= 1                                  */
+    uint32_t mem_head;       /* 16-entry blocks [0, mem_head) contain a non-zero mem_hi8             */
 };
 
 /* ---- multi-GPU (band partition, dsim_mg_kernels.cu) ------------------------------------------------ */

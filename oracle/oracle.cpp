@@ -64,7 +64,8 @@ enum Purpose : uint32_t {
     P_FIGHT = 4,   /* fight_is_deadly lib.rs:1325 (both calls of one encounter) entity = newcomer  */
     P_PIVOT = 5,   /* select_pivot_family lib.rs:1295, band b                   entity = node id   */
     P_MUT = 6,     /* time_till_next_mutation / change_random_bitvec_component  entity = family id */
-    P_REGROW = 7   /* recover_resources_proportion lib.rs:1309, ecoregion slot  entity = node id   */
+    P_REGROW = 7,  /* recover_resources_proportion lib.rs:1309, ecoregion slot  entity = node id   */
+    P_MEM2 = 8     /* low 32 bits of the memory draw of history entry n         entity = family id */
 };
 
 struct Stream {
@@ -361,9 +362,10 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
     uint32_t out[4];
 
     auto consider = [&](uint32_t q, double gain, double l_cost, uint32_t noise_index) {
-        /* lib.rs:918-927.  CANON noise index: position in `known_destinations` for sensed patches,
-         * n_known + n for the n-th newest history entry; two draws per Philox block: index i uses
-         * block i>>1, words (0,1) if i is even, else (2,3). */
+        /* lib.rs:918-927.  CANON noise index: the reference draws once per candidate that has a travel
+         * cost, in iteration order; a sensed patch uses its ordinal among the sensed patches that have a
+         * travel cost, the n-th newest history entry uses n_known + n (whether or not earlier entries were
+         * kept); two draws per Philox block: index i uses block i>>1, words (0,1) if i is even, else (2,3). */
         h.rng.draw(h.t, family.id, P_NOISE, noise_index >> 1, out);
         const double u = (noise_index & 1u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
         const double g = gain * u - l_cost;
@@ -376,21 +378,26 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
     };
 
     /* known_destinations.iter().map(|d| (d, None)), lib.rs:851-853, filtered by lib.rs:869 */
+    uint32_t n_considered = 0;
     for (size_t i = 0; i < n_known; ++i) {
         double c;
         if (!cost_of(known[i], &c)) continue;
         const double harvest = destination_quality(h, known[i], family, population[known[i]]);
-        consider(known[i], harvest, c, (uint32_t)i);
+        consider(known[i], harvest, c, n_considered++);
     }
     /* family.history.iter().rev().filter_map(...), lib.rs:854-867 */
     size_t n = 0;
     for (auto it = family.history.rbegin(); it != family.history.rend(); ++it, ++n) {
         if (n >= h.mem_table.size()) break; /* memory < f64::EPSILON from here on, lib.rs:856 */
         const double memory = h.mem_table[n];
-        /* CANON: 32-bit uniform for the memory draws, four per Philox block: entry n uses block n>>2,
-         * word n&3 */
-        h.rng.draw(h.t, family.id, P_MEM, (uint32_t)(n >> 2), out);
-        const double u = (double)out[n & 3] * (1.0 / 4294967296.0);
+        /* CANON: `fastrand::f64() < memory` (lib.rs:859) with a 40-bit uniform U_n = (B_n * 2^32 + W_n) * 2^-40:
+         * B_n = byte n&15 of Philox block n>>4 of the MEM stream (16 entries per block), W_n = word n&3 of
+         * block n>>2 of the MEM2 stream.  (The device evaluates W_n only when B_n alone does not decide.) */
+        h.rng.draw(h.t, family.id, P_MEM, (uint32_t)(n >> 4), out);
+        const uint64_t b = (out[(n >> 2) & 3] >> (8 * (n & 3))) & 0xFFu;
+        h.rng.draw(h.t, family.id, P_MEM2, (uint32_t)(n >> 2), out);
+        const uint64_t x = (b << 32) | out[n & 3];
+        const double u = (double)x * (1.0 / 1099511627776.0);
         if (!(u < memory)) continue;
         double c;
         if (!cost_of(it->first, &c)) continue;

@@ -37,6 +37,12 @@ def load_emu() -> C.CDLL:
     return C.CDLL(EMU_PATH)
 
 
+def load_emu_small() -> C.CDLL:
+    """Same, compiled with tiny capacities in k_move_blk (tests/emu/Makefile) so that the multi-round paths run."""
+    _make(os.path.join(REPO, "tests", "emu"))
+    return C.CDLL(os.path.join(REPO, "tests", "emu", "libdsim_emu_small.so"))
+
+
 def load_synth() -> C.CDLL:
     _make(os.path.join(REPO, "dispersal-simulation_b200"), "synth")
     return D.load_synth()

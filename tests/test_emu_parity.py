@@ -79,10 +79,10 @@ def test_extinction_and_empty(oracle, emu, synth):
     pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)   # stepping an empty world is a no-op
 
 
-@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_COOPERATIVE, pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE, pc.D.OPT_PATCH_WARP_ONLY,
-                                   pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE | pc.D.OPT_PATCH_WARP_ONLY])
+@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_THREAD_PER_FAMILY, pc.D.OPT_PATCH_WARP_ONLY,
+                                   pc.D.OPT_MOVE_THREAD_PER_FAMILY | pc.D.OPT_PATCH_WARP_ONLY])
 def test_kernel_variants(oracle, emu, synth, flags):
-    """The group-cooperative k_move (TMA-staged rows, or rows read in place) and k_patch (warp per node) for every node."""
+    """The thread-per-family k_move_tpf and k_patch (warp per node) for every node."""
     o, d = pc.build_pair(oracle, emu, synth, 24, 30, 400, hist_fill=40, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 6, hist_cap=96)
 
@@ -90,3 +90,29 @@ def test_kernel_variants(oracle, emu, synth, flags):
         p.cooperation_threshold = 65
     o, d = pc.build_pair(oracle, emu, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 40, by_parts=False, hist_cap=96, check_every=4)
+
+
+def test_move_rounds_with_tiny_capacities():
+    """k_move_blk compiled with 6 candidate slots, 32-entry history chunks and a 1-entry queue of undecided draws
+    (tests/emu/libdsim_emu_small.so): sensed patches take ~10 rounds, the history several chunks and rounds, the
+    queue overflows.  Runs in its own interpreter: two builds of the same sources do not share a process."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys
+sys.path.insert(0, %r)
+import helpers, parity_cases as pc
+oracle, synth, emu_small = helpers.load_oracle(), helpers.load_synth(), helpers.load_emu_small()
+o, d = pc.build_pair(oracle, emu_small, synth, 24, 30, 300, hist_fill=200, hist_cap=256)
+pc.run_lockstep(o, d, 5, hist_cap=256)
+o, d = pc.build_pair(oracle, emu_small, synth, 20, 24, 200, hist_fill=40, hist_cap=96, graph_edit=pc.sparse_edges_graph)
+pc.run_lockstep(o, d, 6, hist_cap=96)
+def peaceful(p):
+    p.cooperation_threshold = 65
+o, d = pc.build_pair(oracle, emu_small, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96)
+pc.run_lockstep(o, d, 30, by_parts=False, hist_cap=96, check_every=5)
+print("tiny capacities ok")
+""" % os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "tiny capacities ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -106,10 +106,10 @@ def test_no_device_fallback_is_absent(gpu_lib):
     assert helpers.D.LIB_PATH.endswith("libdsim_b200.so")
 
 
-@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_COOPERATIVE, pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE, pc.D.OPT_PATCH_WARP_ONLY,
-                                   pc.D.OPT_MOVE_COOPERATIVE | pc.D.OPT_ROWS_IN_PLACE | pc.D.OPT_PATCH_WARP_ONLY])
+@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_THREAD_PER_FAMILY, pc.D.OPT_PATCH_WARP_ONLY,
+                                   pc.D.OPT_MOVE_THREAD_PER_FAMILY | pc.D.OPT_PATCH_WARP_ONLY])
 def test_kernel_variants(oracle, gpu_lib, synth, flags):
-    """The group-cooperative k_move (TMA-staged rows, or rows read in place) and k_patch (warp per node) for every node."""
+    """The thread-per-family k_move_tpf and k_patch (warp per node) for every node."""
     o, d = pc.build_pair(oracle, gpu_lib, synth, 24, 30, 400, hist_fill=40, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 6, hist_cap=96)
 
