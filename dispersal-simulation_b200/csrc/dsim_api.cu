@@ -173,7 +173,6 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     a.occ_par = parity;
     std::memset(&a.mg, 0, sizeof a.mg);
     a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
-    a.move_tpf = (h->opt.flags & DSIM_OPT_MOVE_THREAD_PER_FAMILY) ? 1u : 0u;
     return a;
 }
 

@@ -40,11 +40,12 @@ __device__ __forceinline__ dsim_stream stream_of(const ModelConst &mc) {
     return s;
 }
 
-/* resource_uncertainty (lib.rs:1317) for candidate `i` of family `fid`: two draws per Philox block;
- * index i uses block i>>1 and words (x,y) if i is even, (z,w) otherwise. */
-__device__ __forceinline__ uint32_t noise_block(uint32_t i) { return i >> 1; }
+/* resource_uncertainty (lib.rs:1317) for the candidate with noise index `i` of family `fid`: two draws per
+ * Philox block; indices i and i + 32 of every run of 64 share a block (a lane of k_move takes both):
+ * block = (i / 64) * 32 + i % 32, words (x,y) if i % 64 < 32, (z,w) otherwise. */
+__device__ __forceinline__ uint32_t noise_block(uint32_t i) { return ((i >> 6) << 5) | (i & 31u); }
 __device__ __forceinline__ double noise_pick(const dsim_u4 &o, uint32_t i) {
-    return (i & 1u) ? dsim_u53(o.z, o.w) : dsim_u53(o.x, o.y);
+    return (i & 32u) ? dsim_u53(o.z, o.w) : dsim_u53(o.x, o.y);
 }
 __device__ __forceinline__ double noise_draw(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t i) {
     const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_NOISE, noise_block(i));
@@ -271,26 +272,7 @@ __device__ __forceinline__ bool mem_keep(const ModelConst &mc, uint32_t step, ui
     return mem_resolve(mc, step, fid, n);
 }
 
-/* ------------------------------------------------------------------------------------------ *
- * part 1c (default): move, one THREAD per family.
- *
- * Measured on B200 (profiles/): with one warp — or a group of 8/16 lanes — per family the kernel is
- * bound by the latency of its own instruction stream (shuffles, ballots, shared-memory round trips,
- * work replicated in every lane) long before HBM; 32 independent families per warp need ~half the
- * warp-instructions per family and no collectives at all.  Lane L of a warp owns family 32c+L, so the
- * 56-byte records are still read and written coalesced; a family's reach row is a contiguous,
- * 16-byte-aligned run that its thread streams with 8/16-byte loads (every sector is used in full).
- * Families that split leave a ChildTask; k_children moves the children afterwards.
- * ------------------------------------------------------------------------------------------ */
-#ifndef TPF_THREADS
-#define TPF_THREADS 128
-#endif
-#ifndef TPF_MIN_BLOCKS
-#define TPF_MIN_BLOCKS 4
-#endif
-#define TPF_KEPT 32 /* kept history entries buffered per thread before they are evaluated */
-#define TPF_FB 4u   /* of which this many are resolved at a time (registers) */
-
+/* ---- reach rows in place ------------------------------------------------------------------------- */
 struct RowPtr { /* a reach row in place (HBM / L1) */
     const uint32_t *dst;
     const double *cost;
@@ -355,319 +337,67 @@ __device__ __forceinline__ uint32_t row_find(const RowPtr &row, uint32_t q) {
     return 0xFFFFFFFFu;
 }
 
-__device__ __forceinline__ void accept_one(Choice &ch, double g, double gain, double cost, uint32_t q) {
-    if (g > ch.m) { /* lib.rs:921-926 */
-        ch.target = q;
-        ch.max_gain = dsim_oyr_max(ch.max_gain, gain);
-        ch.t_cost = cost;
+/* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in lane
+ * order: a candidate is accepted iff g > m with m as left by the previous acceptance.  `ch` is
+ * warp-uniform.  An acceptance raises m to at least the accepted g (m' = max(max_gain, gain) - cost >=
+ * gain U - cost), so the candidates before the accepted lane, which failed against the smaller m, and
+ * the accepted lane itself drop out of the next ballot without a cursor. */
+__device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double g, double gain, double cost, uint32_t q) {
+    for (;;) {
+        const uint32_t mask = __ballot_sync(DSIM_FULL, valid && g > ch.m);
+        if (mask == 0u) break;
+        const int L = __ffs((int)mask) - 1;
+        const double m_before = ch.m;
+        ch.target = __shfl_sync(DSIM_FULL, q, L);
+        ch.max_gain = dsim_oyr_max(ch.max_gain, __shfl_sync(DSIM_FULL, gain, L));
+        ch.t_cost = __shfl_sync(DSIM_FULL, cost, L);
         ch.m = ch.max_gain - ch.t_cost;
-    }
-}
-
-/* evaluate the buffered kept history entries kept[0..cnt) (ascending n) as candidates.  The dependent
- * memory accesses (ring entry -> hash bucket -> row entry + cost) are issued stage by stage, TPF_FB entries
- * at a time into registers, so that each stage costs one round trip per TPF_FB entries instead of one
- * per entry. */
-__device__ __forceinline__ void tpf_flush(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
-                                          uint32_t hs, uint32_t ring_cnt, const uint16_t *kept, uint32_t cnt, Choice &ch) {
-    const uint32_t hcap = a.hv.hcap;
-    const size_t hbase = (size_t)hs * hcap;
-    const uint32_t newest = (ring_cnt - 1u) % hcap; /* ring position of entry 0; entry n sits n positions before it */
-    for (uint32_t k0 = 0; k0 < cnt; k0 += TPF_FB) {
-        const uint32_t m = cnt - k0 < TPF_FB ? cnt - k0 : TPF_FB;
-        uint32_t q[TPF_FB], idx[TPF_FB], d[TPF_FB], n[TPF_FB];
-        double gain[TPF_FB], cost[TPF_FB];
-#pragma unroll
-        for (uint32_t j = 0; j < TPF_FB; ++j) {
-            q[j] = 0u;
-            gain[j] = 0.0;
-            n[j] = j < m ? kept[k0 + j] : 0u;
-            if (j < m) {
-                const uint32_t pos = newest >= n[j] ? newest - n[j] : newest + hcap - n[j];
-                q[j] = a.hv.hist_patch[hbase + pos];
-                gain[j] = a.hv.hist_harv[hbase + pos];
-            }
-        }
-        if (row.hash != nullptr) {
-            uint4 bk[TPF_FB];
-#pragma unroll
-            for (uint32_t j = 0; j < TPF_FB; ++j)
-                if (j < m) bk[j] = *reinterpret_cast<const uint4 *>(row.hash + (row_hash(q[j]) >> 8) * 8u);
-            bool slow[TPF_FB];
-#pragma unroll
-            for (uint32_t j = 0; j < TPF_FB; ++j) {
-                idx[j] = 0xFFu;
-                slow[j] = false;
-                if (j < m) {
-                    bool full;
-                    idx[j] = bucket_match(bk[j], row_hash(q[j]) & 0xFFu, 0u, &full);
-                    slow[j] = full && idx[j] == 0xFFu; /* full bucket without a match: the key may have overflowed */
-                }
-            }
-#pragma unroll
-            for (uint32_t j = 0; j < TPF_FB; ++j) { /* the row entry and its cost are requested together */
-                d[j] = 0xFFFFFFFFu;
-                cost[j] = 0.0;
-                if (idx[j] != 0xFFu) {
-                    d[j] = row.dst[idx[j]];
-                    cost[j] = row.cost[idx[j]];
-                }
-            }
-#pragma unroll
-            for (uint32_t j = 0; j < TPF_FB; ++j) {
-                if (idx[j] == 0xFFu && !slow[j]) {
-                    idx[j] = 0xFFFFFFFFu;
-                } else if (slow[j] || d[j] != q[j]) { /* overflowed bucket or tag collision: general search */
-                    idx[j] = row_find(row, q[j]);
-                    if (idx[j] != 0xFFFFFFFFu) cost[j] = row.cost[idx[j]];
-                }
-            }
-        } else {
-#pragma unroll
-            for (uint32_t j = 0; j < TPF_FB; ++j) {
-                idx[j] = j < m ? row_find(row, q[j]) : 0xFFFFFFFFu;
-                cost[j] = idx[j] != 0xFFFFFFFFu ? row.cost[idx[j]] : 0.0;
-            }
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < TPF_FB; ++j) {
-            if (j >= m || idx[j] == 0xFFFFFFFFu) continue; /* no travel cost from here: lib.rs:869 */
-            const double g = gain[j] * noise_draw(a.mc, step, fid, n_sensed + n[j]) - cost[j];
-            accept_one(ch, g, gain[j], cost[j], q[j]);
-        }
-    }
-}
-
-/* The remembered-patch part of decide_on_moving (lib.rs:854-867) for one thread: the kept history entries
- * (mem_block / mem_resolve) that have a travel cost are candidates whose expected harvest is the remembered
- * per-capita harvest. */
-__device__ __forceinline__ void tpf_history(const StepArgs &a, uint32_t step, uint64_t fid, const RowPtr &row, uint32_t n_sensed,
-                                            uint32_t hs, uint32_t ring_cnt, uint32_t nh, Choice &ch) {
-    uint16_t kept[TPF_KEPT];
-    uint32_t cnt = 0;
-    for (uint32_t n16 = 0; n16 < nh; n16 += 16u) {
-        uint32_t undecided;
-        uint32_t mask = mem_block(a.mc, step, fid, n16 >> 4, nh, &undecided);
-        while (undecided) {
-            const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
-            undecided &= undecided - 1u;
-            if (mem_resolve(a.mc, step, fid, n16 + b)) mask |= 1u << b;
-        }
-        if (mask == 0u) continue; /* the common case beyond the first few dozen entries */
-        while (mask) {
-            kept[cnt++] = (uint16_t)(n16 + (uint32_t)__ffs((int)mask) - 1u);
-            mask &= mask - 1u;
-        }
-        if (cnt > TPF_KEPT - 16u) {
-            tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
-            cnt = 0;
-        }
-    }
-    if (cnt) tpf_flush(a, step, fid, row, n_sensed, hs, ring_cnt, kept, cnt, ch);
-}
-
-__global__ void __launch_bounds__(TPF_THREADS, TPF_MIN_BLOCKS) k_move_tpf(StepArgs a) {
-    DevCtl *ctl = a.ctl;
-    const uint32_t n = ctl->n_cur[a.parity];
-    const uint32_t step = ctl->t;
-    const uint32_t cap = ctl->cap;
-    const uint32_t hcap = a.hv.hcap;
-
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        /* Families are visited in the patch-grouped order that part 2 of the previous step left in
-         * `members`: co-resident families (same reach row, same candidate views) sit in adjacent lanes, so
-         * their loads fall into the same L1 wavefronts.  The order never influences results. */
-        const uint32_t i = a.sc.members[t];
-        const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
-        /* ---- ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) ------------------- */
-        const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
-        uint32_t va = 0, vs = 0;
-        for (uint32_t w = c & ~7u; w < c; ++w) { /* warp-uniform addresses */
-            va += (uint32_t)__popc(a.sc.alive_bits[w]);
-            vs += (uint32_t)__popc(a.sc.split_bits[w]);
-        }
-        const uint32_t newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
-        const uint32_t hs = a.cur.hs[i];
-        if (!((alive_mask >> (i & 31u)) & 1u)) { /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
-            a.sc.dead_hs[i - newpos] = hs;
-            continue;
-        }
-        if (newpos >= cap) continue; /* capacity error already flagged by k_control */
-        const bool split = ((split_mask >> (i & 31u)) & 1u) != 0u;
-
-        const uint32_t loc = a.cur.loc[i];
-        const uint64_t fid = a.cur.id[i];
-        const uint64_t culture = a.cur.culture[i];
-        double stored = a.cur.stored[i];
-        const double last_harvest = a.cur.last_harvest[i];
-        uint32_t size = a.cur.size[i];
-        uint32_t misc = a.cur.misc[i];
-        const RowHdr hd = a.rt.hdr[loc];
-        const uint32_t hist_cnt = a.hv.hist_cnt[hs];
-        const RowPtr row = row_of(a.rt, loc, hd);
-
-        /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------ */
-        Choice ch;
-        ch.target = loc;
-        ch.max_gain = 0.0;
-        ch.t_cost = 0.0;
-        ch.m = 0.0;
-        /* sensed patches: the leading entries of the row in ascending node order, four per iteration.
-         * Software pipeline: the node ids are requested two blocks ahead, the 16-byte views and costs one block
-         * ahead, so an iteration never waits for its own loads; entries 2k, 2k+1 share one Philox block.  Rows are padded to multiples of 8 entries (padding node
-         * id 0xFFFFFFFF is never dereferenced), so the 16-byte loads never leave the row. */
-        {
-            const uint32_t ns = row.n_sensed;
-            uint4 q_cur = make_uint4(0u, 0u, 0u, 0u), q_nxt = make_uint4(0u, 0u, 0u, 0u);
-            double2 c01_cur = make_double2(0.0, 0.0), c23_cur = make_double2(0.0, 0.0);
-            PatchView pv_cur[4];
-            if (ns > 0u) {
-                q_cur = *reinterpret_cast<const uint4 *>(row.dst);
-                c01_cur = *reinterpret_cast<const double2 *>(row.cost);
-                c23_cur = *reinterpret_cast<const double2 *>(row.cost + 2u);
-                if (ns > 4u) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + 4u);
-                const uint32_t q0[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
-#pragma unroll
-                for (uint32_t k = 0; k < 4u; ++k)
-                    if (k < ns) pv_cur[k] = a.ps.view[q0[k]];
-            }
-            for (uint32_t e = 0; e < ns; e += 4u) {
-                const uint32_t q[4] = {q_cur.x, q_cur.y, q_cur.z, q_cur.w};
-                const double cost[4] = {c01_cur.x, c01_cur.y, c23_cur.x, c23_cur.y};
-                const uint32_t m = ns - e < 4u ? ns - e : 4u;
-                PatchView pv[4];
-#pragma unroll
-                for (uint32_t k = 0; k < 4u; ++k) pv[k] = pv_cur[k];
-                /* requests for the next block (views, costs, indices) and the block after it (node ids) */
-                if (e + 4u < ns) {
-                    const uint32_t qn[4] = {q_nxt.x, q_nxt.y, q_nxt.z, q_nxt.w};
-#pragma unroll
-                    for (uint32_t k = 0; k < 4u; ++k)
-                        if (e + 4u + k < ns) pv_cur[k] = a.ps.view[qn[k]];
-                    c01_cur = *reinterpret_cast<const double2 *>(row.cost + e + 4u);
-                    c23_cur = *reinterpret_cast<const double2 *>(row.cost + e + 6u);
-                    q_cur = q_nxt;
-                    if (e + 8u < ns) q_nxt = *reinterpret_cast<const uint4 *>(row.dst + e + 8u);
-                }
-                /* noise index of a sensed patch = its position among the sensed patches with a travel cost = e + k */
-                double u[4];
-#pragma unroll
-                for (uint32_t k = 0; k < 4u; k += 2u) {
-                    if (k < m) {
-                        const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, noise_block(e + k));
-                        u[k] = dsim_u53(o.x, o.y);
-                        u[k + 1] = dsim_u53(o.z, o.w);
-                    }
-                }
-#pragma unroll
-                for (uint32_t k = 0; k < 4u; ++k) {
-                    if (k < m) {
-                        const double gain = view_quality(a, pv[k], q[k], culture, size, q[k] == loc);
-                        accept_one(ch, gain * u[k] - cost[k], gain, cost[k], q[k]);
-                    }
-                }
-            }
-        }
-        const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
-        const uint32_t nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
-        tpf_history(a, step, fid, row, hd.n_near, hs, hist_cnt, nh, ch);
-
-        /* ---- move bookkeeping, lib.rs:1826-1833 ---------------------------------------------- */
-        const double harv0 = last_harvest / (double)size;
-        stored = stored + last_harvest;
-        const uint32_t newloc = ch.target;
-        stored = stored - ch.t_cost;
-        {
-            /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
-            const uint32_t pos = hist_cnt % hcap;
-            a.hv.hist_patch[(size_t)hs * hcap + pos] = loc;
-            a.hv.hist_harv[(size_t)hs * hcap + pos] = harv0;
-            a.hv.hist_cnt[hs] = hist_cnt + 1u;
-        }
-        /* ---- maybe_procreate, lib.rs:1869-1897: the child moves in k_children ------------------- */
-        if (split) {
-            const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
-            const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
-            misc = (misc & ~0xFFFFu) | n_off;
-            const double take = stored * 2.0 / (double)size;
-            stored = stored - take;
-            size -= 2u;
-            ChildTask t;
-            t.parent_id = fid;
-            t.culture = culture;
-            t.take = take;
-            t.old_loc = loc;
-            t.new_loc = newloc;
-            t.parent_hs = hs;
-            t.hist_cnt = hist_cnt + 1u;
-            t.n_off = n_off;
-            t.pad_ = 0u;
-            a.sc.child_task[crank] = t;
-        }
-        a.next.id[newpos] = fid;
-        a.next.culture[newpos] = culture;
-        a.next.stored[newpos] = stored;
-        a.next.last_harvest[newpos] = 0.0;
-        a.next.loc[newpos] = newloc;
-        a.next.size[newpos] = size;
-        a.next.till_adult[newpos] = a.cur.till_adult[i];
-        a.next.till_mut[newpos] = a.cur.till_mut[i];
-        a.next.misc[newpos] = misc;
-        a.next.hs[newpos] = hs;
-        if (!a.mg.enabled || (newloc >= a.mg.own_lo && newloc < a.mg.own_hi)) {
-            const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-            if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
-            a.sc.fslot[newpos] = slot;
-        } else {
-            a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
-        }
+        if (!(ch.m > m_before)) break; /* cannot happen for finite non-negative gains; guards against a livelock on NaN/inf input */
     }
 }
 
 /* ------------------------------------------------------------------------------------------ *
- * part 1c (default): move, one BLOCK per tile of 32 families, work items spread over all threads.
+ * part 1c: move, one WARP per tile of MOVE_WF families, work items spread over the lanes.
  *
  * The decision of one family is a short ORDERED scan (lib.rs:918-927) over ~60 sensed patches and ~18
  * remembered patches, but everything that feeds the scan is independent per candidate: 40 Philox blocks
- * of memory draws, one Philox block per pair of sensed patches plus two 16-byte view gathers, and per
- * remembered patch a ring read, a reach-row look-up and one Philox block.  A thread per family
- * serialises all of that behind its own memory round trips; a warp per family replicates the scan in
- * 32 lanes.  Here a block of 256 threads takes 32 families and alternates between
- *   - ITEM phases: (family, work item) pairs are dealt round-robin to all 256 threads; every load of
- *     the tile is in flight at once; results (noised net gain g, expected harvest, row position) go to
- *     per-family candidate slots in shared memory;
- *   - SCAN phases: lane f of warp 0 runs family f's ordered acceptance scan over its slots.
- * Several blocks are resident per SM, so scan phases of one block overlap item phases of the others.
- * Candidate slots, kept-entry lists and draw masks have fixed capacities; longer candidate streams are
- * processed in rounds, so no size is assumed about rows or histories.
+ * of memory draws, one Philox block per two sensed patches plus a 16-byte view gather each, and per
+ * remembered patch a ring read, a reach-row look-up and one Philox block.  Measured on B200
+ * (profiles/): a thread per family serialises all of that behind its own memory round trips (330 us
+ * at 85 k families); a block per 32 families with block-wide phases idles at its barriers (270 us).
+ * Here a warp owns MOVE_WF families from their records to their new records and needs no block
+ * barrier:
+ *   - memory draws: (family, 16 entries) items dealt to the lanes across the tile's families;
+ *   - per family: sensed patches 64 per pass (lane L takes entries L and L+32 of the pass, which share
+ *     one Philox block), kept history entries 32 per pass; after each pass the ordered acceptance is a
+ *     ballot loop with one iteration per acceptance (accept_scan_warp).
+ * The state of a tile lives in ~1 KB of shared memory per warp, so occupancy is bounded by registers only.
  * ------------------------------------------------------------------------------------------ */
-#define BLK_FAM 32u       /* families per tile */
-#define BLK_THREADS 256u
-/* the capacities can be overridden at compile time: the CPU test-suite builds a variant with tiny ones so
- * that every multi-round path runs */
-#ifndef BLK_CAND
-#define BLK_CAND 64u      /* candidate slots per family and round (even) */
+#ifndef MOVE_WF
+#define MOVE_WF 4u        /* families per warp tile (a power of two, at most 32) */
 #endif
-#ifndef BLK_HCHUNK
-#define BLK_HCHUNK 1024u  /* history entries whose draws are evaluated per chunk (a multiple of 32) */
+#ifndef MOVE_HCHUNK
+#define MOVE_HCHUNK 1024u /* history entries whose draws are evaluated per chunk: a multiple of 32, at most 1024 (one 32-bit mask word per lane) */
 #endif
-#ifndef BLK_EQ
-#define BLK_EQ 256u       /* undecided top bytes queued per chunk (expected 32 * 625 / 256 = 78) */
+#ifndef MOVE_EQ
+#define MOVE_EQ 32u       /* undecided top bytes queued per chunk and tile (expected MOVE_WF * 625 / 256 = 10) */
 #endif
-#define BLK_GSTRIDE (BLK_CAND + 1u)        /* slot stride in doubles: odd, so lane f of a scan and lane j of an item phase never collide */
-#define BLK_MSTRIDE (BLK_HCHUNK / 16u + 2u) /* 16-bit masks per family, padded; even: 32-bit atomics stay inside a family */
+#define MOVE_WARPS 4u
+#ifndef MOVE_MIN_BLOCKS
+#define MOVE_MIN_BLOCKS 8 /* 64 registers per thread */
+#endif
+#define MOVE_MWORDS (MOVE_HCHUNK / 32u)
 
-struct BlkShared {
-    double g[BLK_FAM * BLK_GSTRIDE];    /* gain * U - cost of the candidate in a slot; -inf = no candidate */
-    double gain[BLK_FAM * BLK_GSTRIDE];
-    uint64_t fid[BLK_FAM], culture[BLK_FAM];
-    uint32_t ridx[BLK_FAM * BLK_CAND];  /* position of the candidate in the family's reach row (node, cost) */
-    uint32_t loc[BLK_FAM], size[BLK_FAM], hs[BLK_FAM], hist_cnt[BLK_FAM], nh[BLK_FAM];
-    uint32_t row_start[BLK_FAM], row_len[BLK_FAM], ns[BLK_FAM], n_near[BLK_FAM], cnt[BLK_FAM];
-    uint32_t eq_q[BLK_EQ];              /* (family << 16) | entry index in the chunk */
-    uint32_t eq_cnt, more, max_cnt, max_ns, max_nh, pad_[3];
-    uint16_t kept[BLK_FAM * BLK_CAND];  /* kept history entries of the round, relative to the chunk */
-    uint16_t masks[BLK_FAM * BLK_MSTRIDE];
+struct MoveTile { /* per warp */
+    uint64_t fid[MOVE_WF], culture[MOVE_WF];
+    double max_gain[MOVE_WF], t_cost[MOVE_WF], m[MOVE_WF]; /* best_location state of each family (lib.rs:911-916) */
+    uint32_t target[MOVE_WF];
+    uint32_t loc[MOVE_WF], size[MOVE_WF], hs[MOVE_WF], hist_cnt[MOVE_WF], nh[MOVE_WF];
+    uint32_t row_start[MOVE_WF], row_len[MOVE_WF], ns[MOVE_WF], n_near[MOVE_WF];
+    uint32_t masks[MOVE_WF * MOVE_MWORDS]; /* bit n of family f: history entry hbase + n is kept */
+    uint32_t eq_q[MOVE_EQ];                /* (family << 16) | entry index in the chunk */
+    uint32_t eq_cnt;
+    uint16_t kept[32];                     /* kept entries of the current pass, relative to the chunk */
 };
 
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
@@ -678,32 +408,40 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
     }
     return v;
 }
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(DSIM_FULL, v, (unsigned)d);
+        if ((int)lane >= d) v += o;
+    }
+    return v;
+}
 
-__global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
-    DSIM_DYN_SMEM(smem_raw);
-    BlkShared &S = *reinterpret_cast<BlkShared *>(smem_raw);
+__global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepArgs a) {
+    __shared__ MoveTile tiles[MOVE_WARPS];
+    MoveTile &S = tiles[threadIdx.x >> 5];
     DevCtl *ctl = a.ctl;
     const uint32_t n = ctl->n_cur[a.parity];
     const uint32_t step = ctl->t;
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t ntiles = (n + BLK_FAM - 1u) / BLK_FAM;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_lanes = (1u << lane) - 1u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t ntiles = (n + MOVE_WF - 1u) / MOVE_WF;
+    const dsim_stream rs = stream_of(a.mc);
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        /* ---- prologue: thread f < 32 owns family f of the tile ------------------------------------ */
+    for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
+        /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- */
         bool live = false, split = false;
-        uint32_t i = 0, c = 0, lt = 0, newpos = 0, vs = 0, split_mask = 0, misc = 0, m_loc = 0, m_hs = 0, m_size = 0, m_hist_cnt = 0;
-        uint64_t m_fid = 0, m_culture = 0;
+        uint32_t i = 0, c = 0, lt = 0, newpos = 0, vs = 0, split_mask = 0, misc = 0, m_hs = 0, m_hist_cnt = 0, nh = 0;
         double stored = 0.0, last_harvest = 0.0;
-        const uint32_t *r_dst = nullptr;
-        const double *r_cost = nullptr;
-        if (tid < BLK_FAM) {
+        if (lane < MOVE_WF) {
             /* Families are visited in the patch-grouped order that part 2 of the previous step left in
-             * `members`: co-resident families (same reach row, same candidate views) share a tile.  The
-             * order never influences results. */
-            const uint32_t t = tile * BLK_FAM + tid;
-            uint32_t ns = 0, nh = 0;
+             * `members`: co-resident families (same reach row, same candidate views) share a tile or sit in
+             * neighbouring ones.  The order never influences results. */
+            const uint32_t t = tile * MOVE_WF + lane;
+            uint32_t ns = 0;
             if (t < n) {
                 i = a.sc.members[t];
                 c = i >> 5;
@@ -723,213 +461,199 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
                 } else if (newpos < cap) {           /* else: capacity error already flagged by k_control */
                     live = true;
                     split = ((split_mask >> (i & 31u)) & 1u) != 0u;
-                    m_loc = a.cur.loc[i];
-                    m_fid = a.cur.id[i];
-                    m_culture = a.cur.culture[i];
+                    const uint32_t loc = a.cur.loc[i];
+                    S.fid[lane] = a.cur.id[i];
+                    S.culture[lane] = a.cur.culture[i];
                     stored = a.cur.stored[i];
                     last_harvest = a.cur.last_harvest[i];
-                    m_size = a.cur.size[i];
+                    S.size[lane] = a.cur.size[i];
                     misc = a.cur.misc[i];
-                    const RowHdr hd = a.rt.hdr[m_loc];
+                    const RowHdr hd = a.rt.hdr[loc];
                     m_hist_cnt = a.hv.hist_cnt[m_hs];
                     const uint32_t hist_valid = m_hist_cnt < hcap ? m_hist_cnt : hcap;
                     nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
                     ns = hd.n_sensed;
-                    r_dst = a.rt.dst + hd.start;
-                    r_cost = a.rt.cost + hd.start;
-                    S.fid[tid] = m_fid;
-                    S.culture[tid] = m_culture;
-                    S.loc[tid] = m_loc;
-                    S.size[tid] = m_size;
-                    S.hs[tid] = m_hs;
-                    S.hist_cnt[tid] = m_hist_cnt;
-                    S.row_start[tid] = hd.start;
-                    S.row_len[tid] = hd.len;
-                    S.n_near[tid] = hd.n_near;
+                    S.loc[lane] = loc;
+                    S.hs[lane] = m_hs;
+                    S.hist_cnt[lane] = m_hist_cnt;
+                    S.row_start[lane] = hd.start;
+                    S.row_len[lane] = hd.len;
+                    S.n_near[lane] = hd.n_near;
+                    /* best_location state, lib.rs:911-916 */
+                    S.target[lane] = loc;
+                    S.max_gain[lane] = 0.0;
+                    S.t_cost[lane] = 0.0;
+                    S.m[lane] = 0.0;
                 }
             }
-            S.ns[tid] = ns;
-            S.nh[tid] = nh;
-            const uint32_t mx_ns = warp_max_u32(ns), mx_nh = warp_max_u32(nh);
-            if (tid == 0) {
-                S.max_ns = mx_ns;
-                S.max_nh = mx_nh;
-                S.eq_cnt = 0u;
+            S.ns[lane] = ns;
+            S.nh[lane] = nh;
+            if (lane == 0) S.eq_cnt = 0u;
+        }
+        const uint32_t max_nh = warp_max_u32(nh);
+        const uint32_t live_mask = __ballot_sync(DSIM_FULL, live);
+        __syncwarp();
+
+        /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------------- *
+         * sensed patches: the leading entries of the reach row, in ascending node order; the noise index of a
+         * sensed patch is its position among the sensed patches that have a travel cost, i.e. in the row */
+        for (uint32_t f = 0; f < MOVE_WF; ++f) {
+            if (!((live_mask >> f) & 1u)) continue;
+            const uint32_t ns = S.ns[f];
+            if (ns == 0u) continue;
+            const uint64_t fid = S.fid[f], culture = S.culture[f];
+            const uint32_t loc = S.loc[f], size = S.size[f];
+            const uint32_t *r_dst = a.rt.dst + S.row_start[f];
+            const double *r_cost = a.rt.cost + S.row_start[f];
+            Choice ch;
+            ch.target = S.target[f];
+            ch.max_gain = S.max_gain[f];
+            ch.t_cost = S.t_cost[f];
+            ch.m = S.m[f];
+            for (uint32_t base = 0; base < ns; base += 64u) {
+                const uint32_t eA = base + lane, eB = eA + 32u;
+                const bool vA = eA < ns, vB = eB < ns;
+                uint32_t qA = 0, qB = 0;
+                double cA = 0.0, cB = 0.0, gainA = 0.0, gainB = 0.0;
+                PatchView pA, pB;
+                if (vA) {
+                    qA = r_dst[eA];
+                    cA = r_cost[eA];
+                }
+                if (vB) {
+                    qB = r_dst[eB];
+                    cB = r_cost[eB];
+                }
+                if (vA) pA = a.ps.view[qA];
+                if (vB) pB = a.ps.view[qB];
+                /* entries e and e + 32 of a pass share one Philox block (noise_block / noise_half) */
+                const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(eA));
+                if (vA) gainA = view_quality(a, pA, qA, culture, size, qA == loc);
+                if (vB) gainB = view_quality(a, pB, qB, culture, size, qB == loc);
+                accept_scan_warp(ch, vA, gainA * dsim_u53(o.x, o.y) - cA, gainA, cA, qA);
+                accept_scan_warp(ch, vB, gainB * dsim_u53(o.z, o.w) - cB, gainB, cB, qB);
+            }
+            if (lane == 0) {
+                S.target[f] = ch.target;
+                S.max_gain[f] = ch.max_gain;
+                S.t_cost[f] = ch.t_cost;
+                S.m[f] = ch.m;
             }
         }
-        __syncthreads();
-        const uint32_t max_ns = S.max_ns, max_nh = S.max_nh;
+        __syncwarp();
 
-        /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------------- */
-        Choice ch;
-        ch.target = m_loc;
-        ch.max_gain = 0.0;
-        ch.t_cost = 0.0;
-        ch.m = 0.0;
-
-        /* sensed patches: the leading entries of the reach row, in ascending node order; item = a pair of
-         * entries (one Philox block: the noise index of a sensed patch is its position among the sensed
-         * patches that have a travel cost, i.e. its position in the row) */
-        for (uint32_t base = 0; base < max_ns; base += BLK_CAND) {
-            const uint32_t span = max_ns - base < BLK_CAND ? max_ns - base : BLK_CAND;
-            const uint32_t pairs = (span + 1u) >> 1;
-            for (uint32_t it = tid; it < BLK_FAM * pairs; it += BLK_THREADS) {
-                const uint32_t f = it / pairs, j = it - f * pairs;
-                const uint32_t e0 = base + 2u * j, ns = S.ns[f];
-                if (e0 >= ns) continue;
-                const uint32_t start = S.row_start[f];
-                /* rows start at multiples of 8 entries and are padded to multiples of 8: aligned 8/16-byte loads
-                 * (the padding node id 0xFFFFFFFF is never dereferenced) */
-                const uint2 qq = *reinterpret_cast<const uint2 *>(a.rt.dst + start + e0);
-                const double2 cc = *reinterpret_cast<const double2 *>(a.rt.cost + start + e0);
-                const bool two = e0 + 1u < ns;
-                const PatchView v0 = a.ps.view[qq.x];
-                PatchView v1 = v0;
-                if (two) v1 = a.ps.view[qq.y];
-                const uint64_t fid = S.fid[f], culture = S.culture[f];
-                const uint32_t loc = S.loc[f], size = S.size[f];
-                const dsim_u4 o = dsim_draw(stream_of(a.mc), step, fid, DSIM_P_NOISE, e0 >> 1);
-                const double gain0 = view_quality(a, v0, qq.x, culture, size, qq.x == loc);
-                S.g[f * BLK_GSTRIDE + 2u * j] = gain0 * dsim_u53(o.x, o.y) - cc.x;
-                S.gain[f * BLK_GSTRIDE + 2u * j] = gain0;
-                if (two) {
-                    const double gain1 = view_quality(a, v1, qq.y, culture, size, qq.y == loc);
-                    S.g[f * BLK_GSTRIDE + 2u * j + 1u] = gain1 * dsim_u53(o.z, o.w) - cc.y;
-                    S.gain[f * BLK_GSTRIDE + 2u * j + 1u] = gain1;
-                }
-            }
-            __syncthreads();
-            if (tid < BLK_FAM && live) {
-                const uint32_t ns = S.ns[tid];
-                const uint32_t cnt = ns > base ? (ns - base < BLK_CAND ? ns - base : BLK_CAND) : 0u;
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    const double g = S.g[tid * BLK_GSTRIDE + k];
-                    if (g > ch.m) accept_one(ch, g, S.gain[tid * BLK_GSTRIDE + k], r_cost[base + k], r_dst[base + k]);
-                }
-            }
-            __syncthreads();
-        }
-
-        /* remembered patches, lib.rs:854-867 */
-        for (uint32_t hbase = 0; hbase < max_nh; hbase += BLK_HCHUNK) {
-            /* draws: item = (family, 16 history entries).  Blocks whose thresholds have a non-zero top byte
-             * (the newest ~100 entries) take the full byte comparison; they are dealt separately from the
-             * others so that no warp runs both code paths. */
-            const uint32_t span = max_nh - hbase < BLK_HCHUNK ? max_nh - hbase : BLK_HCHUNK;
+        /* ---- remembered patches, lib.rs:854-867 --------------------------------------------------- */
+        for (uint32_t hbase = 0; hbase < max_nh; hbase += MOVE_HCHUNK) {
+            /* draws: item = (family, 16 history entries), block index major so that the few blocks whose
+             * thresholds have a non-zero top byte (full byte comparison) share the first pass */
+            const uint32_t span = max_nh - hbase < MOVE_HCHUNK ? max_nh - hbase : MOVE_HCHUNK;
             const uint32_t nblk = (span + 15u) >> 4, jb0 = hbase >> 4;
-            const uint32_t n_head = a.mc.mem_head > jb0 ? (a.mc.mem_head - jb0 < nblk ? a.mc.mem_head - jb0 : nblk) : 0u;
-            for (uint32_t pass = 0; pass < 2u; ++pass) {
-                const uint32_t j_lo = pass ? n_head : 0u, nj = pass ? nblk - n_head : n_head;
-                for (uint32_t it = tid; it < BLK_FAM * nj; it += BLK_THREADS) {
-                    const uint32_t f = it / nj, j = j_lo + (it - f * nj);
-                    const uint32_t nh = S.nh[f];
-                    uint32_t kept = 0u;
-                    if (hbase + 16u * j < nh) {
-                        const uint64_t fid = S.fid[f];
-                        uint32_t undecided;
-                        kept = mem_block(a.mc, step, fid, jb0 + j, nh, &undecided);
-                        while (undecided) {
-                            const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
-                            undecided &= undecided - 1u;
-                            const uint32_t slot = atomicAdd(&S.eq_cnt, 1u);
-                            if (slot < BLK_EQ)
-                                S.eq_q[slot] = (f << 16) | (16u * j + b);
-                            else if (mem_resolve(a.mc, step, fid, hbase + 16u * j + b)) /* queue full: decide it here */
-                                kept |= 1u << b;
-                        }
-                    }
-                    S.masks[f * BLK_MSTRIDE + j] = (uint16_t)kept;
+            for (uint32_t k = lane; k < MOVE_WF * MOVE_MWORDS; k += 32u) S.masks[k] = 0u;
+            __syncwarp();
+            for (uint32_t it = lane; it < MOVE_WF * nblk; it += 32u) {
+                const uint32_t j = it / MOVE_WF, f = it % MOVE_WF;
+                const uint32_t nhf = S.nh[f];
+                if (hbase + 16u * j >= nhf) continue;
+                const uint64_t fid = S.fid[f];
+                uint32_t undecided;
+                uint32_t kept = mem_block(a.mc, step, fid, jb0 + j, nhf, &undecided);
+                while (undecided) {
+                    const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
+                    undecided &= undecided - 1u;
+                    const uint32_t slot = atomicAdd(&S.eq_cnt, 1u);
+                    if (slot < MOVE_EQ)
+                        S.eq_q[slot] = (f << 16) | (16u * j + b);
+                    else if (mem_resolve(a.mc, step, fid, hbase + 16u * j + b)) /* queue full: decide it here */
+                        kept |= 1u << b;
                 }
+                reinterpret_cast<uint16_t *>(S.masks)[(f * MOVE_MWORDS) * 2u + j] = (uint16_t)kept;
             }
-            __syncthreads();
+            __syncwarp();
             { /* the queued undecided entries: one Philox block of the MEM2 stream each */
-                const uint32_t nq = S.eq_cnt < BLK_EQ ? S.eq_cnt : BLK_EQ;
-                for (uint32_t k = tid; k < nq; k += BLK_THREADS) {
+                const uint32_t nq = S.eq_cnt < MOVE_EQ ? S.eq_cnt : MOVE_EQ;
+                for (uint32_t k = lane; k < nq; k += 32u) {
                     const uint32_t f = S.eq_q[k] >> 16, e = S.eq_q[k] & 0xFFFFu;
-                    if (mem_resolve(a.mc, step, S.fid[f], hbase + e)) {
-                        const uint32_t at = f * BLK_MSTRIDE + (e >> 4); /* 16-bit mask index */
-                        atomicOr(reinterpret_cast<uint32_t *>(S.masks) + (at >> 1), (1u << (e & 15u)) << ((at & 1u) * 16u));
-                    }
+                    if (mem_resolve(a.mc, step, S.fid[f], hbase + e)) atomicOr(&S.masks[f * MOVE_MWORDS + (e >> 5)], 1u << (e & 31u));
                 }
             }
-            __syncthreads();
-            if (tid == 0) S.eq_cnt = 0u;
+            __syncwarp();
+            if (lane == 0) S.eq_cnt = 0u;
 
-            /* rounds of at most BLK_CAND kept entries per family (one round unless a family keeps more) */
-            uint32_t cj = 0, cur = 0; /* compaction cursor of thread f: mask block and its remaining bits */
-            const uint32_t my_nblk = (tid < BLK_FAM && S.nh[tid] > hbase) ? ((S.nh[tid] - hbase < BLK_HCHUNK ? S.nh[tid] - hbase : BLK_HCHUNK) + 15u) >> 4 : 0u;
-            if (my_nblk > 0u) cur = S.masks[tid * BLK_MSTRIDE];
-            for (;;) {
-                if (tid < BLK_FAM) {
-                    uint32_t cnt = 0;
-                    for (;;) {
-                        while (cur == 0u && cj + 1u < my_nblk) cur = S.masks[tid * BLK_MSTRIDE + (++cj)];
-                        if (cur == 0u || cnt == BLK_CAND) break;
-                        S.kept[tid * BLK_CAND + cnt++] = (uint16_t)(16u * cj + (uint32_t)__ffs((int)cur) - 1u);
-                        cur &= cur - 1u;
+            for (uint32_t f = 0; f < MOVE_WF; ++f) {
+                if (!((live_mask >> f) & 1u) || S.nh[f] <= hbase) continue;
+                /* kept entries in ascending order, 32 per pass: lane w holds mask word w and the number of kept entries before it */
+                const uint32_t word = lane < MOVE_MWORDS ? S.masks[f * MOVE_MWORDS + lane] : 0u;
+                const uint32_t incl = warp_incl_scan_u32((uint32_t)__popc(word), lane);
+                const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
+                if (total == 0u) continue;
+                const uint32_t before = incl - (uint32_t)__popc(word);
+                const uint32_t nonzero = __ballot_sync(DSIM_FULL, word != 0u);
+                const uint64_t fid = S.fid[f];
+                const uint32_t n_near = S.n_near[f];
+                RowHdr hd;
+                hd.start = S.row_start[f];
+                hd.len = S.row_len[f];
+                hd.n_sensed = S.ns[f];
+                hd.n_near = n_near;
+                const RowPtr row = row_of(a.rt, S.loc[f], hd);
+                const uint32_t newest = (S.hist_cnt[f] - 1u) % hcap; /* ring position of entry 0; entry n sits n positions before it */
+                const size_t hb = (size_t)S.hs[f] * hcap;
+                Choice ch;
+                ch.target = S.target[f];
+                ch.max_gain = S.max_gain[f];
+                ch.t_cost = S.t_cost[f];
+                ch.m = S.m[f];
+                for (uint32_t r0 = 0; r0 < total; r0 += 32u) {
+                    for (uint32_t nz = nonzero; nz != 0u; nz &= nz - 1u) { /* scatter the kept entries r0 .. r0+31 to S.kept */
+                        const int w = __ffs((int)nz) - 1;
+                        const uint32_t ww = __shfl_sync(DSIM_FULL, word, w), wb = __shfl_sync(DSIM_FULL, before, w);
+                        const uint32_t pos = wb + (uint32_t)__popc(ww & lt_lanes);
+                        if (((ww >> lane) & 1u) && pos >= r0 && pos < r0 + 32u) S.kept[pos - r0] = (uint16_t)(32u * (uint32_t)w + lane);
                     }
-                    S.cnt[tid] = cnt;
-                    const uint32_t more = __ballot_sync(DSIM_FULL, cur != 0u), mx = warp_max_u32(cnt);
-                    if (tid == 0) {
-                        S.more = more;
-                        S.max_cnt = mx;
-                    }
-                }
-                __syncthreads();
-                const uint32_t per = S.max_cnt, more = S.more;
-                /* item = one kept entry: ring entry -> row look-up -> cost, one Philox block for the noise */
-                for (uint32_t it = tid; it < BLK_FAM * per; it += BLK_THREADS) {
-                    const uint32_t f = it / per, k = it - f * per;
-                    if (k >= S.cnt[f]) continue;
-                    const uint32_t nn = hbase + S.kept[f * BLK_CAND + k]; /* entry nn, 0 = newest */
-                    const uint32_t newest = (S.hist_cnt[f] - 1u) % hcap;
-                    const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
-                    const size_t at = (size_t)S.hs[f] * hcap + pos;
-                    const uint32_t q = a.hv.hist_patch[at];
-                    const double gain = a.hv.hist_harv[at];
-                    RowHdr hd;
-                    hd.start = S.row_start[f];
-                    hd.len = S.row_len[f];
-                    hd.n_sensed = S.ns[f];
-                    hd.n_near = S.n_near[f];
-                    const RowPtr row = row_of(a.rt, S.loc[f], hd);
-                    const uint32_t idx = row_find(row, q);
-                    double g = DSIM_NEG_INF; /* no travel cost from here: not a candidate, lib.rs:869 */
-                    if (idx != 0xFFFFFFFFu) g = gain * noise_draw(a.mc, step, S.fid[f], hd.n_near + nn) - row.cost[idx];
-                    S.g[f * BLK_GSTRIDE + k] = g;
-                    S.gain[f * BLK_GSTRIDE + k] = gain;
-                    S.ridx[f * BLK_CAND + k] = idx;
-                }
-                __syncthreads();
-                if (tid < BLK_FAM && live) {
-                    const uint32_t cnt = S.cnt[tid];
-                    for (uint32_t k = 0; k < cnt; ++k) {
-                        const double g = S.g[tid * BLK_GSTRIDE + k];
-                        if (g > ch.m) {
-                            const uint32_t idx = S.ridx[tid * BLK_CAND + k];
-                            accept_one(ch, g, S.gain[tid * BLK_GSTRIDE + k], r_cost[idx], r_dst[idx]);
+                    __syncwarp();
+                    const bool on = r0 + lane < total;
+                    bool cand = false;
+                    double g = 0.0, gain = 0.0, cost = 0.0;
+                    uint32_t q = 0;
+                    if (on) {
+                        const uint32_t nn = hbase + S.kept[lane]; /* entry nn, 0 = newest */
+                        const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
+                        q = a.hv.hist_patch[hb + pos];
+                        gain = a.hv.hist_harv[hb + pos];
+                        const uint32_t idx = row_find(row, q);
+                        if (idx != 0xFFFFFFFFu) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
+                            cost = row.cost[idx];
+                            g = gain * noise_draw(a.mc, step, fid, n_near + nn) - cost;
+                            cand = true;
                         }
                     }
+                    accept_scan_warp(ch, cand, g, gain, cost, q);
+                    __syncwarp();
                 }
-                if (more == 0u) break;
-                /* the next round's compaction is done by the threads that just scanned; its item phase
-                 * starts after the barrier above */
+                if (lane == 0) {
+                    S.target[f] = ch.target;
+                    S.max_gain[f] = ch.max_gain;
+                    S.t_cost[f] = ch.t_cost;
+                    S.m[f] = ch.m;
+                }
             }
-            __syncthreads();
+            __syncwarp();
         }
 
-        /* ---- epilogue: thread f ------------------------------------------------------------------- */
-        if (tid < BLK_FAM && live) {
+        /* ---- epilogue: lane f ---------------------------------------------------------------------- */
+        if (lane < MOVE_WF && live) {
+            const uint32_t loc = S.loc[lane];
+            const uint64_t fid = S.fid[lane], culture = S.culture[lane];
             /* move bookkeeping, lib.rs:1826-1833 */
-            uint32_t size = m_size;
+            uint32_t size = S.size[lane];
             const double harv0 = last_harvest / (double)size;
             stored = stored + last_harvest;
-            const uint32_t newloc = ch.target;
-            stored = stored - ch.t_cost;
+            const uint32_t newloc = S.target[lane];
+            stored = stored - S.t_cost[lane];
             {
                 /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
                 const uint32_t pos = m_hist_cnt % hcap;
-                a.hv.hist_patch[(size_t)m_hs * hcap + pos] = m_loc;
+                a.hv.hist_patch[(size_t)m_hs * hcap + pos] = loc;
                 a.hv.hist_harv[(size_t)m_hs * hcap + pos] = harv0;
                 a.hv.hist_cnt[m_hs] = m_hist_cnt + 1u;
             }
@@ -942,10 +666,10 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
                 stored = stored - take;
                 size -= 2u;
                 ChildTask t;
-                t.parent_id = m_fid;
-                t.culture = m_culture;
+                t.parent_id = fid;
+                t.culture = culture;
                 t.take = take;
-                t.old_loc = m_loc;
+                t.old_loc = loc;
                 t.new_loc = newloc;
                 t.parent_hs = m_hs;
                 t.hist_cnt = m_hist_cnt + 1u;
@@ -953,8 +677,8 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
                 t.pad_ = 0u;
                 a.sc.child_task[crank] = t;
             }
-            a.next.id[newpos] = m_fid;
-            a.next.culture[newpos] = m_culture;
+            a.next.id[newpos] = fid;
+            a.next.culture[newpos] = culture;
             a.next.stored[newpos] = stored;
             a.next.last_harvest[newpos] = 0.0;
             a.next.loc[newpos] = newloc;
@@ -971,23 +695,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_move_blk(StepArgs a) {
                 a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
             }
         }
-    }
-}
-
-/* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in
- * lane order: a candidate is accepted iff g > m with m as left by the previous acceptance. */
-__device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double g, double gain, double cost, uint32_t q,
-                                                 uint32_t lane) {
-    uint32_t cursor = 0;
-    for (;;) {
-        const uint32_t mask = __ballot_sync(DSIM_FULL, valid && lane >= cursor && g > ch.m);
-        if (mask == 0u) break;
-        const int L = __ffs((int)mask) - 1;
-        ch.target = __shfl_sync(DSIM_FULL, q, L);
-        ch.max_gain = dsim_oyr_max(ch.max_gain, __shfl_sync(DSIM_FULL, gain, L));
-        ch.t_cost = __shfl_sync(DSIM_FULL, cost, L);
-        ch.m = ch.max_gain - ch.t_cost;
-        cursor = (uint32_t)L + 1u;
+        __syncwarp();
     }
 }
 
@@ -1043,7 +751,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
                 g = gain * noise_draw(a.mc, step, cid, n_considered + (uint32_t)__popc(cmask & ((1u << lane) - 1u))) - cost;
             }
             n_considered += (uint32_t)__popc(cmask);
-            accept_scan_warp(cc, cand, g, gain, cost, q, lane);
+            accept_scan_warp(cc, cand, g, gain, cost, q);
         }
         /* history = the parent's newest min(len, time_to_grow_adult) entries, the one pushed this step included */
         const uint32_t valid = t.hist_cnt < hcap ? t.hist_cnt : hcap;
@@ -1066,7 +774,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
                     cand = true;
                 }
             }
-            accept_scan_warp(cc, cand, g, gain, cost, q, lane);
+            accept_scan_warp(cc, cand, g, gain, cost, q);
         }
         for (uint32_t k = lane; k < child_len; k += 32u) { /* chronological index k = newest-first index child_len-1-k */
             const uint32_t pos = (t.hist_cnt - 1u - (child_len - 1u - k)) % hcap;
@@ -1727,12 +1435,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     switch (which) {
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
     case DSIM_K_CONTROL: DSIM_LAUNCH(k_control, 1, CTL_THREADS, 0, s, a); break;
-    case DSIM_K_MOVE:
-        if (a.move_tpf) /* test / comparison variant: one thread per family */
-            DSIM_LAUNCH(k_move_tpf, grid_for(g, 2 * TPF_MIN_BLOCKS), TPF_THREADS, 0, s, a);
-        else
-            DSIM_LAUNCH(k_move_blk, grid_for(g, 16), BLK_THREADS, sizeof(BlkShared), s, a);
-        break;
+    case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, 8), MOVE_WARPS * 32, 0, s, a); break;
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
@@ -1760,9 +1463,5 @@ void dsim_launch_census(const PatchState &ps, const FamCore &f, uint32_t n, uint
 
 int dsim_configure_kernels(LaunchGeom *g) {
     (void)g;
-#if !defined(DSIM_EMU)
-    cudaError_t e = cudaFuncSetAttribute(k_move_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkShared));
-    if (e != cudaSuccess) return (int)e;
-#endif
     return 0;
 }

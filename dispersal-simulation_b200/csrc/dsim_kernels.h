@@ -19,7 +19,6 @@ struct StepArgs {
     uint32_t parity;   /* index of `cur` (0/1): ctl->n_cur[parity] families */
     uint32_t occ_par;  /* occ[occ_par] / n_occ[occ_par] collect this step's occupied nodes, [occ_par ^ 1] hold last step's */
     MgInfo mg;
-    uint32_t move_tpf; /* 1: k_move_tpf (one thread per family) instead of k_move_blk (DSIM_OPT_MOVE_THREAD_PER_FAMILY) */
     uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
 };
 
@@ -27,7 +26,7 @@ struct LaunchGeom {
     uint32_t n_sm;               /* grids are multiples of the SM count (148 on B200); kernels are grid-stride */
 };
 
-/* one-time function attributes (dynamic shared memory of k_move_blk) */
+/* one-time function attributes (none at present) */
 int dsim_configure_kernels(LaunchGeom *g);
 
 enum {

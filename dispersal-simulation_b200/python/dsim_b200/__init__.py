@@ -24,7 +24,6 @@ SYNTH_LIB_PATH = os.path.join(PKG_ROOT, "libdsim_synth.so")
 
 N_ECOREGIONS = 304
 OPT_PATCH_WARP_ONLY = 0x2
-OPT_MOVE_THREAD_PER_FAMILY = 0x4
 NO_PARENT = 2**64 - 1
 
 u8p = C.POINTER(C.c_uint8)

@@ -130,7 +130,6 @@ typedef struct dsim_options {
     uint32_t flags;            /* DSIM_OPT_* test knobs, 0 by default */
 } dsim_options;
 #define DSIM_OPT_PATCH_WARP_ONLY 0x2u /* every occupied node takes the warp-per-node kernel */
-#define DSIM_OPT_MOVE_THREAD_PER_FAMILY 0x4u /* k_move_tpf (one thread per family) instead of the block-cooperative k_move_blk */
 
 typedef struct dsim_step_stats {
     uint64_t t;               /* State.t after the call (lib.rs:308; `s.t += 1`, cli.rs:154) */

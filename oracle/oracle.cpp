@@ -365,9 +365,10 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
         /* lib.rs:918-927.  CANON noise index: the reference draws once per candidate that has a travel
          * cost, in iteration order; a sensed patch uses its ordinal among the sensed patches that have a
          * travel cost, the n-th newest history entry uses n_known + n (whether or not earlier entries were
-         * kept); two draws per Philox block: index i uses block i>>1, words (0,1) if i is even, else (2,3). */
-        h.rng.draw(h.t, family.id, P_NOISE, noise_index >> 1, out);
-        const double u = (noise_index & 1u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
+         * kept); two draws per Philox block: indices i and i + 32 of every run of 64 share a block,
+         * block = (i / 64) * 32 + i % 32, words (0,1) if i % 64 < 32, else (2,3). */
+        h.rng.draw(h.t, family.id, P_NOISE, ((noise_index >> 6) << 5) | (noise_index & 31u), out);
+        const double u = (noise_index & 32u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
         const double g = gain * u - l_cost;
         if (g > m) {
             target = q;

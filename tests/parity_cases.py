@@ -104,6 +104,39 @@ def sparse_edges_graph(g, res, mx):
     return g2, res, mx
 
 
+def long_range_graph(W):
+    """Add four fast long-range edges per node (3 columns / 3 rows away): the 2-hop `nearby` lists grow beyond 64
+    entries, so the sensed patches of a family take more than one 64-entry pass of k_move."""
+    def edit(g, res, mx):
+        n = g.n_nodes
+        off = g.edge_off.astype(np.int64)
+        src = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))
+        extra_src, extra_dst = [], []
+        for delta in (3, -3, 3 * W, -3 * W):
+            v = np.arange(n, dtype=np.int64)
+            w = v + delta
+            ok = (w >= 0) & (w < n)
+            if abs(delta) == 3:                      # stay inside the grid row
+                ok &= (v // W) == (w // W)
+            extra_src.append(v[ok])
+            extra_dst.append(w[ok])
+        all_src = np.concatenate([src] + extra_src)
+        all_dst = np.concatenate([g.edge_dst.astype(np.int64)] + extra_dst)
+        all_sec = np.concatenate([g.edge_sec] + [np.full(len(x), 9000.0) for x in extra_src])
+        order = np.lexsort((all_dst, all_src))
+        all_src, all_dst, all_sec = all_src[order], all_dst[order], all_sec[order]
+        keep = np.ones(len(all_src), bool)           # drop duplicates of existing edges (keep the first)
+        keep[1:] = (all_src[1:] != all_src[:-1]) | (all_dst[1:] != all_dst[:-1])
+        all_src, all_dst, all_sec = all_src[keep], all_dst[keep], all_sec[keep]
+        edge_off = np.zeros(n + 1, np.uint64)
+        edge_off[1:] = np.cumsum(np.bincount(all_src, minlength=n))
+        g2 = D.Graph(n_nodes=n, eco_off=g.eco_off, eco_id=g.eco_id, edge_off=edge_off,
+                     edge_dst=np.ascontiguousarray(all_dst.astype(g.edge_dst.dtype)), edge_sec=np.ascontiguousarray(all_sec),
+                     popcap=g.popcap, h3=g.h3, lon=g.lon, lat=g.lat)
+        return g2, res, mx
+    return edit
+
+
 def check_reach(o, d):
     a, b = o.get_reach(), d.get_reach()
     for x, y, name in zip(a, b, ["near_off", "near_dst", "reach_off", "reach_dst", "reach_cost"]):

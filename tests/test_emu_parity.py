@@ -1,6 +1,7 @@
 """The CUDA kernels, compiled for the CPU by the test-only fiber emulator (tests/emu), against the
 oracle.  This is how the kernels are debugged in a container without a GPU; the GPU tests
 (test_gpu_parity.py) run the same scenarios through the real library on a B200."""
+import numpy as np
 import pytest
 
 import parity_cases as pc
@@ -57,6 +58,26 @@ def test_ragged_graph(oracle, emu, synth):
     pc.run_lockstep(o, d, 8, hist_cap=96)
 
 
+def test_many_sensed_patches(oracle, emu, synth):
+    """2-hop lists longer than 64 entries: several sensed passes per family in k_move."""
+    o, d = pc.build_pair(oracle, emu, synth, 24, 30, 200, hist_fill=30, hist_cap=96, graph_edit=pc.long_range_graph(24))
+    near_off = o.get_reach()[0]
+    assert np.diff(near_off.astype(np.int64)).max() > 70, "scenario must exceed one 64-entry pass"
+    pc.run_lockstep(o, d, 6, hist_cap=96)
+
+
+def test_slow_memory_decay(oracle, emu, synth):
+    """A short season (1/24 year) makes the memory decay slowly: ~70 remembered patches are kept per decision
+    (several 32-entry passes) and the memory loop reaches back 2500 entries (several 1024-entry chunks)."""
+    def edit(p):
+        p.season_length_in_years = 1.0 / 24.0
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 40, hist_fill=2600, params_edit=edit)
+    f = d.get_families()
+    cap = int(f.hist_off[1] - f.hist_off[0])
+    assert cap >= 2400
+    pc.run_lockstep(o, d, 3, hist_cap=cap)
+
+
 def test_parameter_variants(oracle, emu, synth):
     def edit(p):
         p.cooperation_inclusive = 1
@@ -79,10 +100,9 @@ def test_extinction_and_empty(oracle, emu, synth):
     pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)   # stepping an empty world is a no-op
 
 
-@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_THREAD_PER_FAMILY, pc.D.OPT_PATCH_WARP_ONLY,
-                                   pc.D.OPT_MOVE_THREAD_PER_FAMILY | pc.D.OPT_PATCH_WARP_ONLY])
+@pytest.mark.parametrize("flags", [pc.D.OPT_PATCH_WARP_ONLY])
 def test_kernel_variants(oracle, emu, synth, flags):
-    """The thread-per-family k_move_tpf and k_patch (warp per node) for every node."""
+    """k_patch (warp per node) for every node."""
     o, d = pc.build_pair(oracle, emu, synth, 24, 30, 400, hist_fill=40, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 6, hist_cap=96)
 
@@ -93,9 +113,8 @@ def test_kernel_variants(oracle, emu, synth, flags):
 
 
 def test_move_rounds_with_tiny_capacities():
-    """k_move_blk compiled with 6 candidate slots, 32-entry history chunks and a 1-entry queue of undecided draws
-    (tests/emu/libdsim_emu_small.so): sensed patches take ~10 rounds, the history several chunks and rounds, the
-    queue overflows.  Runs in its own interpreter: two builds of the same sources do not share a process."""
+    """k_move compiled with 32-entry history chunks, a 1-entry queue of undecided draws and 2 families per warp tile
+    (tests/emu/libdsim_emu_small.so): the history takes several chunks, the queue overflows.  Runs in its own interpreter: two builds of the same sources do not share a process."""
     import os
     import subprocess
     import sys

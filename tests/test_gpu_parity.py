@@ -54,6 +54,26 @@ def test_ragged_graph(oracle, gpu_lib, synth):
     pc.run_lockstep(o, d, 8, hist_cap=96)
 
 
+def test_many_sensed_patches(oracle, gpu_lib, synth):
+    """2-hop lists longer than 64 entries: several sensed passes per family in k_move."""
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 24, 30, 200, hist_fill=30, hist_cap=96, graph_edit=pc.long_range_graph(24))
+    near_off = o.get_reach()[0]
+    assert np.diff(near_off.astype(np.int64)).max() > 70, "scenario must exceed one 64-entry pass"
+    pc.run_lockstep(o, d, 6, hist_cap=96)
+
+
+def test_slow_memory_decay(oracle, gpu_lib, synth):
+    """A short season (1/24 year) makes the memory decay slowly: ~70 remembered patches are kept per decision
+    (several 32-entry passes) and the memory loop reaches back 2500 entries (several 1024-entry chunks)."""
+    def edit(p):
+        p.season_length_in_years = 1.0 / 24.0
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 20, 24, 40, hist_fill=2600, params_edit=edit)
+    f = d.get_families()
+    cap = int(f.hist_off[1] - f.hist_off[0])
+    assert cap >= 2400
+    pc.run_lockstep(o, d, 3, hist_cap=cap)
+
+
 def test_parameter_variants(oracle, gpu_lib, synth):
     def edit(p):
         p.cooperation_inclusive = 1
@@ -106,10 +126,9 @@ def test_no_device_fallback_is_absent(gpu_lib):
     assert helpers.D.LIB_PATH.endswith("libdsim_b200.so")
 
 
-@pytest.mark.parametrize("flags", [pc.D.OPT_MOVE_THREAD_PER_FAMILY, pc.D.OPT_PATCH_WARP_ONLY,
-                                   pc.D.OPT_MOVE_THREAD_PER_FAMILY | pc.D.OPT_PATCH_WARP_ONLY])
+@pytest.mark.parametrize("flags", [pc.D.OPT_PATCH_WARP_ONLY])
 def test_kernel_variants(oracle, gpu_lib, synth, flags):
-    """The thread-per-family k_move_tpf and k_patch (warp per node) for every node."""
+    """k_patch (warp per node) for every node."""
     o, d = pc.build_pair(oracle, gpu_lib, synth, 24, 30, 400, hist_fill=40, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 6, hist_cap=96)
 
