@@ -243,8 +243,11 @@ __device__ __forceinline__ uint32_t mem_block(const ModelConst &mc, uint32_t ste
     const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, jb);
     uint32_t lt = 0, eq = 0;
     if (jb >= mc.mem_head) { /* every threshold byte is zero: nothing is kept on the top byte, a zero byte is undecided */
-        const uint32_t z0 = swar_eq4(o.x, 0u), z1 = swar_eq4(o.y, 0u), z2 = swar_eq4(o.z, 0u), z3 = swar_eq4(o.w, 0u);
-        if ((z0 | z1 | z2 | z3) != 0u) eq = swar_pack4(z0) | (swar_pack4(z1) << 4) | (swar_pack4(z2) << 8) | (swar_pack4(z3) << 12);
+        /* cheap test for "some byte is zero" first (exact as a presence test), the exact per-byte flags only then */
+        const uint32_t any = ((o.x - 0x01010101u) & ~o.x) | ((o.y - 0x01010101u) & ~o.y) | ((o.z - 0x01010101u) & ~o.z) | ((o.w - 0x01010101u) & ~o.w);
+        if ((any & 0x80808080u) != 0u)
+            eq = swar_pack4(swar_eq4(o.x, 0u)) | (swar_pack4(swar_eq4(o.y, 0u)) << 4) | (swar_pack4(swar_eq4(o.z, 0u)) << 8) |
+                 (swar_pack4(swar_eq4(o.w, 0u)) << 12);
     } else {
         const uint4 h = *reinterpret_cast<const uint4 *>(mc.mem_hi8 + 16u * jb);
         lt = swar_pack4(swar_ltu4(o.x, h.x)) | (swar_pack4(swar_ltu4(o.y, h.y)) << 4) | (swar_pack4(swar_ltu4(o.z, h.z)) << 8) |
@@ -294,47 +297,41 @@ __device__ __forceinline__ RowPtr row_of(const ReachTable &rt, uint32_t node, co
 
 __device__ __forceinline__ uint32_t row_hash(uint32_t q) { return (q * 2654435761u) >> 19; } /* bucket = bits 8..12, tag = bits 0..7 */
 
-/* first slot of the bucket whose tag matches, as an entry position; 0xFF = none; *full = no empty slot */
-__device__ __forceinline__ uint32_t bucket_match(const uint4 &bk, uint32_t tag, uint32_t skip, bool *full) {
-    const uint32_t w[4] = {bk.x, bk.y, bk.z, bk.w};
-    uint32_t found = 0xFFu, seen = 0;
-    bool f = true;
-#pragma unroll
-    for (uint32_t k = 0; k < 8u; ++k) {
-        const uint32_t slot = (w[k >> 1] >> ((k & 1u) * 16u)) & 0xFFFFu;
-        if (slot == 0xFFFFu) f = false;
-        if (slot != 0xFFFFu && (slot >> 8) == tag) {
-            if (seen == skip && found == 0xFFu) found = slot & 0xFFu;
-            ++seen;
-        }
-    }
-    *full = f;
-    return found;
+/* position of node q in the row, or 0xFFFFFFFF (replaces travel_costs.get(), lib.rs:869), by binary search in
+ * the two sorted segments of the row */
+__device__ __noinline__ uint32_t row_find_sorted(const uint32_t *dst, uint32_t n_sensed, uint32_t len, uint32_t q) {
+    uint32_t k = lower_bound_u32(dst, 0u, n_sensed, q);
+    if (k < n_sensed && dst[k] == q) return k;
+    k = lower_bound_u32(dst, n_sensed, len, q);
+    if (k < len && dst[k] == q) return k;
+    return 0xFFFFFFFFu;
 }
 
-/* position of node q in the row, or 0xFFFFFFFF (replaces travel_costs.get(), lib.rs:869) */
+/* Same through the row's bucket index (rows of at most DSIM_ROW_HASH_MAX entries): one 16-byte load reads the
+ * key's home bucket of 8 slots (tag << 8 | position, 0xFFFF = empty); the first slot with the key's tag is
+ * verified against the row.  Everything else — a tag collision (1/256 per slot), a full bucket that may have
+ * overflowed into the next one — falls back to the binary search. */
 __device__ __forceinline__ uint32_t row_find(const RowPtr &row, uint32_t q) {
     if (row.hash != nullptr) {
         const uint32_t h = row_hash(q);
-        uint32_t b = h >> 8;
-        for (uint32_t tries = 0; tries < 32u; ++tries) {
-            const uint4 bk = *reinterpret_cast<const uint4 *>(row.hash + b * 8u);
-            bool full;
-            for (uint32_t skip = 0;; ++skip) { /* tag collisions (1/256 per occupied slot) are verified one by one */
-                const uint32_t k = bucket_match(bk, h & 0xFFu, skip, &full);
-                if (k == 0xFFu) break;
-                if (row.dst[k] == q) return k;
-            }
-            if (!full) return 0xFFFFFFFFu;
-            b = (b + 1u) & 31u;
+        const uint4 bk = *reinterpret_cast<const uint4 *>(row.hash + (h >> 8) * 8u);
+        const uint32_t t2 = (h & 0xFFu) * 0x01000100u; /* the tag in the high byte of both 16-bit slots of a word */
+        const uint32_t f0 = swar_eq4(bk.x & 0xFF00FF00u, t2) & 0x80008000u, f1 = swar_eq4(bk.y & 0xFF00FF00u, t2) & 0x80008000u;
+        const uint32_t f2 = swar_eq4(bk.z & 0xFF00FF00u, t2) & 0x80008000u, f3 = swar_eq4(bk.w & 0xFF00FF00u, t2) & 0x80008000u;
+        if ((f0 | f1 | f2 | f3) != 0u) {
+            /* first matching slot in slot order: low half of x, high half of x, low half of y, ... */
+            const uint32_t w = f0 ? bk.x : f1 ? bk.y : f2 ? bk.z : bk.w;
+            const uint32_t f = f0 ? f0 : f1 ? f1 : f2 ? f2 : f3;
+            const uint32_t pos = (f & 0x8000u) ? (w & 0xFFu) : ((w >> 16) & 0xFFu);
+            if (pos < row.len && row.dst[pos] == q) return pos;
+        } else {
+            /* no slot carries the tag: absent unless the bucket is full (the key may have overflowed) */
+            const uint32_t e0 = ~bk.x, e1 = ~bk.y, e2 = ~bk.z, e3 = ~bk.w; /* an empty slot becomes a zero halfword */
+            const uint32_t z = ((e0 - 0x00010001u) & ~e0) | ((e1 - 0x00010001u) & ~e1) | ((e2 - 0x00010001u) & ~e2) | ((e3 - 0x00010001u) & ~e3);
+            if ((z & 0x80008000u) != 0u) return 0xFFFFFFFFu;
         }
-        return 0xFFFFFFFFu;
     }
-    uint32_t k = lower_bound_u32(row.dst, 0u, row.n_sensed, q);
-    if (k < row.n_sensed && row.dst[k] == q) return k;
-    k = lower_bound_u32(row.dst, row.n_sensed, row.len, q);
-    if (k < row.len && row.dst[k] == q) return k;
-    return 0xFFFFFFFFu;
+    return row_find_sorted(row.dst, row.n_sensed, row.len, q);
 }
 
 /* Ordered acceptance scan of lib.rs:918-927 over the (up to) 32 candidates held one per lane, in lane
@@ -394,6 +391,9 @@ struct MoveTile { /* per warp */
     uint32_t target[MOVE_WF];
     uint32_t loc[MOVE_WF], size[MOVE_WF], hs[MOVE_WF], hist_cnt[MOVE_WF], nh[MOVE_WF];
     uint32_t row_start[MOVE_WF], row_len[MOVE_WF], ns[MOVE_WF], n_near[MOVE_WF];
+    /* what only the epilogue of family f needs (kept out of registers during the candidate passes) */
+    double stored[MOVE_WF], last_harvest[MOVE_WF];
+    uint32_t idx[MOVE_WF], newpos[MOVE_WF], crank[MOVE_WF], misc[MOVE_WF], newest[MOVE_WF];
     uint32_t masks[MOVE_WF * MOVE_MWORDS]; /* bit n of family f: history entry hbase + n is kept */
     uint32_t eq_q[MOVE_EQ];                /* (family << 16) | entry index in the chunk */
     uint32_t eq_cnt;
@@ -433,9 +433,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
 
     for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
         /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- */
-        bool live = false, split = false;
-        uint32_t i = 0, c = 0, lt = 0, newpos = 0, vs = 0, split_mask = 0, misc = 0, m_hs = 0, m_hist_cnt = 0, nh = 0;
-        double stored = 0.0, last_harvest = 0.0;
+        uint32_t nh = 0, state = 0; /* state: bit 0 = decides (survivor), bit 1 = splits */
         if (lane < MOVE_WF) {
             /* Families are visited in the patch-grouped order that part 2 of the previous step left in
              * `members`: co-resident families (same reach row, same candidate views) share a tile or sit in
@@ -443,39 +441,40 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             const uint32_t t = tile * MOVE_WF + lane;
             uint32_t ns = 0;
             if (t < n) {
-                i = a.sc.members[t];
-                c = i >> 5;
-                lt = (1u << (i & 31u)) - 1u;
+                const uint32_t i = a.sc.members[t];
+                const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
                 /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
-                const uint32_t alive_mask = a.sc.alive_bits[c];
-                split_mask = a.sc.split_bits[c];
-                uint32_t va = 0;
+                const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
+                uint32_t va = 0, vs = 0;
                 for (uint32_t w = c & ~7u; w < c; ++w) {
                     va += (uint32_t)__popc(a.sc.alive_bits[w]);
                     vs += (uint32_t)__popc(a.sc.split_bits[w]);
                 }
-                newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
-                m_hs = a.cur.hs[i];
+                const uint32_t newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
+                const uint32_t hs = a.cur.hs[i];
                 if (!((alive_mask >> (i & 31u)) & 1u)) {
-                    a.sc.dead_hs[i - newpos] = m_hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
-                } else if (newpos < cap) {           /* else: capacity error already flagged by k_control */
-                    live = true;
-                    split = ((split_mask >> (i & 31u)) & 1u) != 0u;
+                    a.sc.dead_hs[i - newpos] = hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
+                } else if (newpos < cap) {         /* else: capacity error already flagged by k_control */
+                    state = 1u | (((split_mask >> (i & 31u)) & 1u) << 1);
                     const uint32_t loc = a.cur.loc[i];
                     S.fid[lane] = a.cur.id[i];
                     S.culture[lane] = a.cur.culture[i];
-                    stored = a.cur.stored[i];
-                    last_harvest = a.cur.last_harvest[i];
+                    S.stored[lane] = a.cur.stored[i];
+                    S.last_harvest[lane] = a.cur.last_harvest[i];
                     S.size[lane] = a.cur.size[i];
-                    misc = a.cur.misc[i];
+                    S.misc[lane] = a.cur.misc[i];
+                    S.idx[lane] = i;
+                    S.newpos[lane] = newpos;
+                    S.crank[lane] = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
                     const RowHdr hd = a.rt.hdr[loc];
-                    m_hist_cnt = a.hv.hist_cnt[m_hs];
-                    const uint32_t hist_valid = m_hist_cnt < hcap ? m_hist_cnt : hcap;
+                    const uint32_t hist_cnt = a.hv.hist_cnt[hs];
+                    const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
                     nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
                     ns = hd.n_sensed;
                     S.loc[lane] = loc;
-                    S.hs[lane] = m_hs;
-                    S.hist_cnt[lane] = m_hist_cnt;
+                    S.hs[lane] = hs;
+                    S.hist_cnt[lane] = hist_cnt;
+                    S.newest[lane] = (hist_cnt - 1u) % hcap; /* ring position of entry 0; entry n sits n positions before it */
                     S.row_start[lane] = hd.start;
                     S.row_len[lane] = hd.len;
                     S.n_near[lane] = hd.n_near;
@@ -491,7 +490,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             if (lane == 0) S.eq_cnt = 0u;
         }
         const uint32_t max_nh = warp_max_u32(nh);
-        const uint32_t live_mask = __ballot_sync(DSIM_FULL, live);
+        const uint32_t live_mask = __ballot_sync(DSIM_FULL, (state & 1u) != 0u);
         __syncwarp();
 
         /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------------- *
@@ -511,27 +510,22 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             ch.t_cost = S.t_cost[f];
             ch.m = S.m[f];
             for (uint32_t base = 0; base < ns; base += 64u) {
+                /* lane L takes entries base + L and base + 32 + L; out-of-range lanes re-read the last entry and
+                 * are masked at the acceptance, so the loads need no branches */
                 const uint32_t eA = base + lane, eB = eA + 32u;
                 const bool vA = eA < ns, vB = eB < ns;
-                uint32_t qA = 0, qB = 0;
-                double cA = 0.0, cB = 0.0, gainA = 0.0, gainB = 0.0;
-                PatchView pA, pB;
-                if (vA) {
-                    qA = r_dst[eA];
-                    cA = r_cost[eA];
-                }
-                if (vB) {
-                    qB = r_dst[eB];
-                    cB = r_cost[eB];
-                }
-                if (vA) pA = a.ps.view[qA];
-                if (vB) pB = a.ps.view[qB];
-                /* entries e and e + 32 of a pass share one Philox block (noise_block / noise_half) */
+                const uint32_t iA = vA ? eA : ns - 1u, iB = vB ? eB : ns - 1u;
+                const uint32_t qA = r_dst[iA], qB = r_dst[iB];
+                const double cA = r_cost[iA], cB = r_cost[iB];
+                const PatchView pA = a.ps.view[qA], pB = a.ps.view[qB];
+                /* entries e and e + 32 of a pass share one Philox block (noise_block / noise_pick) */
                 const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(eA));
-                if (vA) gainA = view_quality(a, pA, qA, culture, size, qA == loc);
-                if (vB) gainB = view_quality(a, pB, qB, culture, size, qB == loc);
+                const double gainA = view_quality(a, pA, qA, culture, size, qA == loc);
                 accept_scan_warp(ch, vA, gainA * dsim_u53(o.x, o.y) - cA, gainA, cA, qA);
-                accept_scan_warp(ch, vB, gainB * dsim_u53(o.z, o.w) - cB, gainB, cB, qB);
+                if (base + 32u < ns) {
+                    const double gainB = view_quality(a, pB, qB, culture, size, qB == loc);
+                    accept_scan_warp(ch, vB, gainB * dsim_u53(o.z, o.w) - cB, gainB, cB, qB);
+                }
             }
             if (lane == 0) {
                 S.target[f] = ch.target;
@@ -596,7 +590,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 hd.n_sensed = S.ns[f];
                 hd.n_near = n_near;
                 const RowPtr row = row_of(a.rt, S.loc[f], hd);
-                const uint32_t newest = (S.hist_cnt[f] - 1u) % hcap; /* ring position of entry 0; entry n sits n positions before it */
+                const uint32_t newest = S.newest[f];
                 const size_t hb = (size_t)S.hs[f] * hcap;
                 Choice ch;
                 ch.target = S.target[f];
@@ -641,25 +635,27 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
         }
 
         /* ---- epilogue: lane f ---------------------------------------------------------------------- */
-        if (lane < MOVE_WF && live) {
-            const uint32_t loc = S.loc[lane];
+        if (state & 1u) {
+            const uint32_t loc = S.loc[lane], hs = S.hs[lane], hist_cnt = S.hist_cnt[lane];
+            const uint32_t i = S.idx[lane], newpos = S.newpos[lane];
             const uint64_t fid = S.fid[lane], culture = S.culture[lane];
+            const double last_harvest = S.last_harvest[lane];
+            uint32_t misc = S.misc[lane];
             /* move bookkeeping, lib.rs:1826-1833 */
             uint32_t size = S.size[lane];
             const double harv0 = last_harvest / (double)size;
-            stored = stored + last_harvest;
+            double stored = S.stored[lane] + last_harvest;
             const uint32_t newloc = S.target[lane];
             stored = stored - S.t_cost[lane];
             {
                 /* family.history.push((location, last_harvest / size)), lib.rs:1826-1829 */
-                const uint32_t pos = m_hist_cnt % hcap;
-                a.hv.hist_patch[(size_t)m_hs * hcap + pos] = loc;
-                a.hv.hist_harv[(size_t)m_hs * hcap + pos] = harv0;
-                a.hv.hist_cnt[m_hs] = m_hist_cnt + 1u;
+                const uint32_t pos = hist_cnt % hcap;
+                a.hv.hist_patch[(size_t)hs * hcap + pos] = loc;
+                a.hv.hist_harv[(size_t)hs * hcap + pos] = harv0;
+                a.hv.hist_cnt[hs] = hist_cnt + 1u;
             }
             /* maybe_procreate, lib.rs:1869-1897: the child moves in k_children */
-            if (split) {
-                const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
+            if (state & 2u) {
                 const uint32_t n_off = ((misc & 0xFFFFu) + 1u) & 0xFFFFu;
                 misc = (misc & ~0xFFFFu) | n_off;
                 const double take = stored * 2.0 / (double)size;
@@ -671,11 +667,11 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 t.take = take;
                 t.old_loc = loc;
                 t.new_loc = newloc;
-                t.parent_hs = m_hs;
-                t.hist_cnt = m_hist_cnt + 1u;
+                t.parent_hs = hs;
+                t.hist_cnt = hist_cnt + 1u;
                 t.n_off = n_off;
                 t.pad_ = 0u;
-                a.sc.child_task[crank] = t;
+                a.sc.child_task[S.crank[lane]] = t;
             }
             a.next.id[newpos] = fid;
             a.next.culture[newpos] = culture;
@@ -686,7 +682,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             a.next.till_adult[newpos] = a.cur.till_adult[i];
             a.next.till_mut[newpos] = a.cur.till_mut[i];
             a.next.misc[newpos] = misc;
-            a.next.hs[newpos] = m_hs;
+            a.next.hs[newpos] = hs;
             if (!a.mg.enabled || (newloc >= a.mg.own_lo && newloc < a.mg.own_hi)) {
                 const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
                 if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
