@@ -203,7 +203,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
     A(nh.decay, hs_cap) A(nh.parent, hs_cap) A(nh.birth_index, hs_cap)
     nh.hcap = h->hcap;
     nh.acap = h->acap;
-    A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8)
+    A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8) A(ns.word_pre, new_cap / 32 + 8)
     A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
     A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
     A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_small, new_cap) A(ns.plist_big, new_cap)

@@ -98,14 +98,18 @@ __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
             s_split[w] = (uint32_t)__popc(sb);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x <= LIFE_BLOCK / 32) { /* thread k: counts of the words before word k; thread 8: the group's totals */
             uint32_t sa = 0, ss = 0;
-            for (int k = 0; k < LIFE_BLOCK / 32; ++k) {
+            for (uint32_t k = 0; k < threadIdx.x; ++k) {
                 sa += s_alive[k];
                 ss += s_split[k];
             }
-            a.sc.blk_alive[vb] = sa;
-            a.sc.blk_split[vb] = ss;
+            if (threadIdx.x < LIFE_BLOCK / 32) {
+                a.sc.word_pre[vb * (LIFE_BLOCK / 32) + threadIdx.x] = sa | (ss << 16);
+            } else {
+                a.sc.blk_alive[vb] = sa;
+                a.sc.blk_split[vb] = ss;
+            }
         }
         __syncthreads();
     }
@@ -202,12 +206,27 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *v, uint32_t 
     return lo;
 }
 
-/* destination_quality, lib.rs:1034-1062 (has_enemies lib.rs:996-1017, expected_harvest 989-994) */
-__device__ __forceinline__ double view_quality(const StepArgs &a, const PatchView &v, uint32_t q, uint64_t culture, uint32_t size,
+/* destination_quality, lib.rs:1034-1062 (has_enemies lib.rs:996-1017, expected_harvest 989-994), in two
+ * steps so that a caller can request the band cultures of several candidates before it uses any. */
+struct BandsRef {
+    uint64_t cult0;    /* first band culture stored for the node */
+    uint32_t stor_off; /* where all of them are */
+};
+__device__ __forceinline__ BandsRef bands_fetch(const StepArgs &a, const PatchView &v, uint32_t q) {
+    BandsRef r;
+    r.cult0 = 0;
+    r.stor_off = 0;
+    if (v.nb > 0u) { /* candidates occupied last step */
+        const PatchBands b = a.ps.bands[q];
+        r.cult0 = b.cult0;
+        r.stor_off = b.stor_off;
+    }
+    return r;
+}
+__device__ __forceinline__ double quality_eval(const StepArgs &a, const PatchView &v, const BandsRef &b, uint64_t culture, uint32_t size,
                                                bool same_patch) {
     bool enemy = false;
-    if (v.nb > 0u) { /* candidates occupied last step: fetch their band cultures */
-        const PatchBands b = a.ps.bands[q];
+    if (v.nb > 0u) {
         enemy = !dsim_will_cooperate(culture, b.cult0, a.mc.threshold, a.mc.inclusive);
         if (v.nb > 1u && !enemy) {
             const uint64_t *others = (b.stor_off & DSIM_STOR_HALO) ? a.mg.halo_cult[(b.stor_off >> 30) & 1u] + (b.stor_off & 0x3FFFFFFFu)
@@ -219,6 +238,11 @@ __device__ __forceinline__ double view_quality(const StepArgs &a, const PatchVie
     if (enemy) return 0.0;
     const uint64_t pop_at_destination = (uint64_t)v.pop + (same_patch ? 0u : size);
     return v.quality / (double)pop_at_destination;
+}
+__device__ __forceinline__ double view_quality(const StepArgs &a, const PatchView &v, uint32_t q, uint64_t culture, uint32_t size,
+                                               bool same_patch) {
+    const BandsRef b = bands_fetch(a, v, q);
+    return quality_eval(a, v, b, culture, size, same_patch);
 }
 
 /* ---- remembered-patch sampling, lib.rs:854-866 ------------------------------------------------------
@@ -307,29 +331,38 @@ __device__ __noinline__ uint32_t row_find_sorted(const uint32_t *dst, uint32_t n
     return 0xFFFFFFFFu;
 }
 
-/* Same through the row's bucket index (rows of at most DSIM_ROW_HASH_MAX entries): one 16-byte load reads the
- * key's home bucket of 8 slots (tag << 8 | position, 0xFFFF = empty); the first slot with the key's tag is
- * verified against the row.  Everything else — a tag collision (1/256 per slot), a full bucket that may have
- * overflowed into the next one — falls back to the binary search. */
+/* The row's bucket index (rows of at most DSIM_ROW_HASH_MAX entries): one 16-byte load reads the key's home
+ * bucket of 8 slots (tag << 8 | position, 0xFFFF = empty).  bucket_probe returns the position of the first
+ * slot with the key's tag (to be verified against the row), ROW_ABSENT when no slot has it and the bucket
+ * has a free slot, ROW_SEARCH otherwise (full bucket: the key may have overflowed into the next one).
+ * A failed verification (tag collision, 1/256 per slot) also falls back to the binary search. */
+#define ROW_ABSENT 0xFFFFFFFFu
+#define ROW_SEARCH 0xFFFFFFFEu
+__device__ __forceinline__ const uint4 *bucket_of(const uint16_t *hash, uint32_t q) {
+    return reinterpret_cast<const uint4 *>(hash + (row_hash(q) >> 8) * 8u);
+}
+__device__ __forceinline__ uint32_t bucket_probe(const uint4 &bk, uint32_t q) {
+    const uint32_t t2 = (row_hash(q) & 0xFFu) * 0x01000100u; /* the tag in the high byte of both 16-bit slots of a word */
+    const uint32_t f0 = swar_eq4(bk.x & 0xFF00FF00u, t2) & 0x80008000u, f1 = swar_eq4(bk.y & 0xFF00FF00u, t2) & 0x80008000u;
+    const uint32_t f2 = swar_eq4(bk.z & 0xFF00FF00u, t2) & 0x80008000u, f3 = swar_eq4(bk.w & 0xFF00FF00u, t2) & 0x80008000u;
+    if ((f0 | f1 | f2 | f3) != 0u) {
+        /* first matching slot in slot order: low half of x, high half of x, low half of y, ... */
+        const uint32_t w = f0 ? bk.x : f1 ? bk.y : f2 ? bk.z : bk.w;
+        const uint32_t f = f0 ? f0 : f1 ? f1 : f2 ? f2 : f3;
+        return (f & 0x8000u) ? (w & 0xFFu) : ((w >> 16) & 0xFFu);
+    }
+    const uint32_t e0 = ~bk.x, e1 = ~bk.y, e2 = ~bk.z, e3 = ~bk.w; /* an empty slot becomes a zero halfword */
+    const uint32_t z = ((e0 - 0x00010001u) & ~e0) | ((e1 - 0x00010001u) & ~e1) | ((e2 - 0x00010001u) & ~e2) | ((e3 - 0x00010001u) & ~e3);
+    return (z & 0x80008000u) != 0u ? ROW_ABSENT : ROW_SEARCH;
+}
+
+/* position of node q in the row, or ROW_ABSENT (replaces travel_costs.get(), lib.rs:869) */
 __device__ __forceinline__ uint32_t row_find(const RowPtr &row, uint32_t q) {
     if (row.hash != nullptr) {
-        const uint32_t h = row_hash(q);
-        const uint4 bk = *reinterpret_cast<const uint4 *>(row.hash + (h >> 8) * 8u);
-        const uint32_t t2 = (h & 0xFFu) * 0x01000100u; /* the tag in the high byte of both 16-bit slots of a word */
-        const uint32_t f0 = swar_eq4(bk.x & 0xFF00FF00u, t2) & 0x80008000u, f1 = swar_eq4(bk.y & 0xFF00FF00u, t2) & 0x80008000u;
-        const uint32_t f2 = swar_eq4(bk.z & 0xFF00FF00u, t2) & 0x80008000u, f3 = swar_eq4(bk.w & 0xFF00FF00u, t2) & 0x80008000u;
-        if ((f0 | f1 | f2 | f3) != 0u) {
-            /* first matching slot in slot order: low half of x, high half of x, low half of y, ... */
-            const uint32_t w = f0 ? bk.x : f1 ? bk.y : f2 ? bk.z : bk.w;
-            const uint32_t f = f0 ? f0 : f1 ? f1 : f2 ? f2 : f3;
-            const uint32_t pos = (f & 0x8000u) ? (w & 0xFFu) : ((w >> 16) & 0xFFu);
-            if (pos < row.len && row.dst[pos] == q) return pos;
-        } else {
-            /* no slot carries the tag: absent unless the bucket is full (the key may have overflowed) */
-            const uint32_t e0 = ~bk.x, e1 = ~bk.y, e2 = ~bk.z, e3 = ~bk.w; /* an empty slot becomes a zero halfword */
-            const uint32_t z = ((e0 - 0x00010001u) & ~e0) | ((e1 - 0x00010001u) & ~e1) | ((e2 - 0x00010001u) & ~e2) | ((e3 - 0x00010001u) & ~e3);
-            if ((z & 0x80008000u) != 0u) return 0xFFFFFFFFu;
-        }
+        const uint4 bk = *bucket_of(row.hash, q);
+        const uint32_t pos = bucket_probe(bk, q);
+        if (pos == ROW_ABSENT) return ROW_ABSENT;
+        if (pos < row.len && row.dst[pos] == q) return pos;
     }
     return row_find_sorted(row.dst, row.n_sensed, row.len, q);
 }
@@ -371,7 +404,7 @@ __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double 
  * The state of a tile lives in ~1 KB of shared memory per warp, so occupancy is bounded by registers only.
  * ------------------------------------------------------------------------------------------ */
 #ifndef MOVE_WF
-#define MOVE_WF 4u        /* families per warp tile (a power of two, at most 32) */
+#define MOVE_WF 4u        /* families per warp tile (a power of two, 2 ... 32) */
 #endif
 #ifndef MOVE_HCHUNK
 #define MOVE_HCHUNK 1024u /* history entries whose draws are evaluated per chunk: a multiple of 32, at most 1024 (one 32-bit mask word per lane) */
@@ -432,7 +465,10 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
     const dsim_stream rs = stream_of(a.mc);
 
     for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
-        /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- */
+        /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- *
+         * Every load that depends only on the family's position is requested before any is used (also for
+         * families that turn out to be dead: their columns are still valid memory), so the prologue costs
+         * three memory round trips: members -> record columns and bitmaps -> row header and history length. */
         uint32_t nh = 0, state = 0; /* state: bit 0 = decides (survivor), bit 1 = splits */
         if (lane < MOVE_WF) {
             /* Families are visited in the patch-grouped order that part 2 of the previous step left in
@@ -443,31 +479,29 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             if (t < n) {
                 const uint32_t i = a.sc.members[t];
                 const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
-                /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
                 const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
-                uint32_t va = 0, vs = 0;
-                for (uint32_t w = c & ~7u; w < c; ++w) {
-                    va += (uint32_t)__popc(a.sc.alive_bits[w]);
-                    vs += (uint32_t)__popc(a.sc.split_bits[w]);
-                }
-                const uint32_t newpos = a.sc.blk_alive[c >> 3] + va + (uint32_t)__popc(alive_mask & lt);
-                const uint32_t hs = a.cur.hs[i];
+                const uint32_t base_alive = a.sc.blk_alive[c >> 3], base_split = a.sc.blk_split[c >> 3];
+                const uint32_t hs = a.cur.hs[i], loc = a.cur.loc[i], size = a.cur.size[i], misc = a.cur.misc[i];
+                const uint64_t fid = a.cur.id[i], culture = a.cur.culture[i];
+                const double stored = a.cur.stored[i], last_harvest = a.cur.last_harvest[i];
+                /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
+                const uint32_t pre = a.sc.word_pre[c], va = pre & 0xFFFFu, vs = pre >> 16;
+                const RowHdr hd = a.rt.hdr[loc];
+                const uint32_t hist_cnt = a.hv.hist_cnt[hs];
+                const uint32_t newpos = base_alive + va + (uint32_t)__popc(alive_mask & lt);
                 if (!((alive_mask >> (i & 31u)) & 1u)) {
                     a.sc.dead_hs[i - newpos] = hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
                 } else if (newpos < cap) {         /* else: capacity error already flagged by k_control */
                     state = 1u | (((split_mask >> (i & 31u)) & 1u) << 1);
-                    const uint32_t loc = a.cur.loc[i];
-                    S.fid[lane] = a.cur.id[i];
-                    S.culture[lane] = a.cur.culture[i];
-                    S.stored[lane] = a.cur.stored[i];
-                    S.last_harvest[lane] = a.cur.last_harvest[i];
-                    S.size[lane] = a.cur.size[i];
-                    S.misc[lane] = a.cur.misc[i];
+                    S.fid[lane] = fid;
+                    S.culture[lane] = culture;
+                    S.stored[lane] = stored;
+                    S.last_harvest[lane] = last_harvest;
+                    S.size[lane] = size;
+                    S.misc[lane] = misc;
                     S.idx[lane] = i;
                     S.newpos[lane] = newpos;
-                    S.crank[lane] = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
-                    const RowHdr hd = a.rt.hdr[loc];
-                    const uint32_t hist_cnt = a.hv.hist_cnt[hs];
+                    S.crank[lane] = base_split + vs + (uint32_t)__popc(split_mask & lt);
                     const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
                     nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
                     ns = hd.n_sensed;
@@ -615,7 +649,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                         q = a.hv.hist_patch[hb + pos];
                         gain = a.hv.hist_harv[hb + pos];
                         const uint32_t idx = row_find(row, q);
-                        if (idx != 0xFFFFFFFFu) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
+                        if (idx != ROW_ABSENT) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
                             cost = row.cost[idx];
                             g = gain * noise_draw(a.mc, step, fid, n_near + nn) - cost;
                             cand = true;

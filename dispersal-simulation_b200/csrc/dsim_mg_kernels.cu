@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         const uint32_t split_mask = a.sc.split_bits[c];
         if (!((split_mask >> (i & 31u)) & 1u)) continue;
         uint32_t vs = 0;
-        for (uint32_t w = c & ~7u; w < c; ++w) vs += (uint32_t)__popc(a.sc.split_bits[w]);
+        vs += a.sc.word_pre[c] >> 16;
         const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
         if (crank < mb.scap)
             mb.split_send[1 + crank] = a.cur.id[i];

@@ -103,6 +103,8 @@ struct ChildTask { /* what k_children needs about a family that split (lib.rs:18
 struct StepScratch {
     uint32_t *alive_bits;   /* [cap/32] bit i: family i survives `retain` (lib.rs:541)             */
     uint32_t *split_bits;   /* [cap/32] bit i: family i procreates (lib.rs:1870)                    */
+    uint32_t *word_pre;     /* [cap/32] survivors (bits 0..15) and splitting families (bits 16..31) in the words of
+                               the same group of 256 families before word i                         */
     uint32_t *blk_alive;    /* [cap/256] per-256 counts, then exclusive offsets                    */
     uint32_t *blk_split;
     uint32_t *dead_hs;      /* [cap] heavy slots vacated this step                                 */
