@@ -1216,191 +1216,243 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
 }
 
 /* ------------------------------------------------------------------------------------------ *
- * part 2c': one THREAD per sparsely occupied node (at most PATCH_SMALL_MAX families).
- * Same rules as k_patch; with one to a handful of families per node (the common case on the
- * continental grid) a warp per node would leave 30 lanes idle, so 32 nodes share a warp instead.
+ * part 2c': a GROUP of 8 lanes per sparsely occupied node (at most PATCH_SMALL_MAX = 8 families).
+ * Same rules as k_patch.  With one to a handful of families per node (the common case on the
+ * continental grid) a warp per node would leave most lanes idle, and a thread per node walks its
+ * families one dependent memory round trip after the other; here lane j of the group owns the family
+ * at position j of the shuffled order, so the records, adaptation slots and draws of all the families
+ * of a node are in flight together and four nodes share a warp.  The groups of a warp are independent:
+ * every collective names only the lanes of its group.
  * ------------------------------------------------------------------------------------------ */
+#define PG 8u /* lanes per group = PATCH_SMALL_MAX */
+
+struct Grp {
+    uint32_t gl, goff, gmask;
+    __device__ __forceinline__ explicit Grp(uint32_t lane) : gl(lane % PG), goff(lane - lane % PG), gmask(((1u << PG) - 1u) << (lane - lane % PG)) {}
+    template <typename T> __device__ __forceinline__ T get(T v, uint32_t src) const { return __shfl_sync(gmask, v, (int)src, (int)PG); }
+    __device__ __forceinline__ uint32_t ballot(bool pred) const { return (__ballot_sync(gmask, pred) >> goff) & ((1u << PG) - 1u); }
+};
+
 __global__ void __launch_bounds__(128) k_patch_small(StepArgs a) {
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n_small = ctl->n_small;
     const dsim_stream rs = stream_of(a.mc);
     const double season = a.mc.season;
+    const Grp G(threadIdx.x & 31u);
+    const uint32_t gl = G.gl;
+    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / PG, ngroups = (gridDim.x * blockDim.x) / PG;
     uint32_t errors = 0;
 
-    for (uint32_t v = tid; v < n_small; v += nth) {
+    for (uint32_t v = group; v < n_small; v += ngroups) {
         const uint32_t p = a.sc.plist_small[v];
         const uint32_t n = a.ps.cnt[p];
         const uint32_t s0 = a.ps.seg[p];
-        uint32_t idx[PATCH_SMALL_MAX], size[PATCH_SMALL_MAX], band[PATCH_SMALL_MAX];
-        uint64_t fid[PATCH_SMALL_MAX], key[PATCH_SMALL_MAX], cult[PATCH_SMALL_MAX];
-        double stored[PATCH_SMALL_MAX], contrib[PATCH_SMALL_MAX], lh[PATCH_SMALL_MAX];
-        uint64_t bcult[PATCH_SMALL_MAX];
-        uint32_t btot[PATCH_SMALL_MAX];
-        double beff[PATCH_SMALL_MAX], bcoef[PATCH_SMALL_MAX];
+        const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
+        const bool mine = gl < n;
 
-        /* shuffle (lib.rs:1376): insertion sort by (keyed random number, id) */
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint32_t i = a.sc.members[s0 + j];
-            const uint64_t id = a.next.id[i];
-            const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
-            const uint64_t k = ((uint64_t)o.y << 32) | o.x;
-            uint32_t r = j;
-            while (r > 0u && (key[r - 1] > k || (key[r - 1] == k && fid[r - 1] > id))) {
-                key[r] = key[r - 1];
-                fid[r] = fid[r - 1];
-                idx[r] = idx[r - 1];
-                --r;
+        /* ---- the family at position gl of the segment: everything part 2 reads of its record ------ */
+        uint32_t idx = 0, size = 0, hs = 0, misc = 0, clock = 0;
+        uint64_t fid = 0, cult = 0;
+        double stored = 0.0;
+        if (mine) {
+            idx = a.sc.members[s0 + gl];
+            fid = a.next.id[idx];
+            cult = a.next.culture[idx];
+            size = a.next.size[idx];
+            stored = a.next.stored[idx];
+            hs = a.next.hs[idx];
+            misc = a.next.misc[idx];
+            clock = a.next.till_mut[idx];
+        }
+        /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id); lane r takes the
+         * family of rank r ---------------------------------------------------------------------------- */
+        if (n > 1u) {
+            uint64_t key = 0;
+            if (mine) {
+                const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_SHUF, 0u);
+                key = ((uint64_t)o.y << 32) | o.x;
             }
-            key[r] = k;
-            fid[r] = id;
-            idx[r] = i;
+            uint32_t rank = 0;
+            for (uint32_t k = 0; k < n; ++k) {
+                const uint64_t kk = G.get(key, k), ik = G.get(fid, k);
+                rank += (kk < key || (kk == key && ik < fid)) ? 1u : 0u;
+            }
+            uint32_t src = gl;
+            for (uint32_t k = 0; k < n; ++k)
+                if (G.get(rank, k) == gl) src = k;
+            idx = G.get(idx, src);
+            fid = G.get(fid, src);
+            cult = G.get(cult, src);
+            size = G.get(size, src);
+            stored = G.get(stored, src);
+            hs = G.get(hs, src);
+            misc = G.get(misc, src);
+            clock = G.get(clock, src);
         }
-        for (uint32_t r = 0; r < n; ++r) {
-            const uint32_t i = idx[r];
-            cult[r] = a.next.culture[i];
-            size[r] = a.next.size[i];
-            stored[r] = a.next.stored[i];
-        }
-        /* cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 */
-        uint32_t nb = 0;
+        /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 ---------- */
+        uint32_t band = 0xFFFFFFFFu, nb = 0;
         for (uint32_t i = 0; i < n; ++i) {
+            const uint64_t cf = G.get(cult, i), fi = G.get(fid, i);
+            uint32_t sz = G.get(size, i);
+            double st = G.get(stored, i);
             int joined = -1;
             for (uint32_t B = 0; B < nb && joined < 0; ++B) {
-                bool any_hostile = false;
-                for (uint32_t j = 0; j < i; ++j) {
-                    if (band[j] != B || dsim_will_cooperate(cult[i], cult[j], a.mc.threshold, a.mc.inclusive)) continue;
-                    any_hostile = true;
-                    const uint32_t reduction = size[i] < size[j] ? size[i] : size[j];
-                    const dsim_u4 o = dsim_draw(rs, step, fid[i], DSIM_P_FIGHT, j);
-                    if (o.x < a.mc.deadliness) {
-                        size[j] -= reduction;
-                        if (size[j] == 0u) {
-                            stored[i] = stored[i] + stored[j];
-                            stored[j] = 0.0;
+                uint32_t hostile = G.ballot(gl < i && band == B && !dsim_will_cooperate(cf, cult, a.mc.threshold, a.mc.inclusive));
+                if (hostile == 0u) {
+                    joined = (int)B;
+                    break;
+                }
+                while (hostile != 0u) { /* hostile members in join order */
+                    const uint32_t jj = (uint32_t)__ffs((int)hostile) - 1u;
+                    hostile &= hostile - 1u;
+                    uint32_t so = G.get(size, jj);
+                    double sto = G.get(stored, jj);
+                    const uint32_t reduction = sz < so ? sz : so;
+                    const dsim_u4 o = dsim_draw(rs, step, fi, DSIM_P_FIGHT, jj);
+                    if (o.x < a.mc.deadliness) { /* fight_is_deadly, lib.rs:1219 */
+                        so -= reduction;
+                        if (so == 0u) {
+                            st = st + sto;
+                            sto = 0.0;
                         }
                     }
-                    if (o.y < a.mc.deadliness) size[i] -= reduction;
-                }
-                if (!any_hostile) joined = (int)B;
-            }
-            band[i] = joined < 0 ? nb++ : (uint32_t)joined;
-        }
-        /* band culture = culture of a random member; empty bands are dropped, lib.rs:1400-1416 */
-        uint32_t nb_alive = 0;
-        uint64_t cult0 = 0;
-        for (uint32_t B = 0; B < nb; ++B) {
-            uint32_t cnt = 0, tot = 0;
-            for (uint32_t j = 0; j < n; ++j)
-                if (band[j] == B) {
-                    cnt += 1u;
-                    tot += size[j];
-                }
-            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
-            const uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)cnt);
-            uint64_t c = 0;
-            uint32_t seen = 0;
-            for (uint32_t j = 0; j < n; ++j)
-                if (band[j] == B) {
-                    if (seen == pick) {
-                        c = cult[j];
-                        break;
+                    if (o.y < a.mc.deadliness) sz -= reduction; /* lib.rs:1226 */
+                    if (gl == jj) {
+                        size = so;
+                        stored = sto;
                     }
-                    ++seen;
                 }
-            bcult[B] = c;
-            btot[B] = tot;
-            if (tot > 0u) { /* storage', lib.rs:622-633 */
-                if (nb_alive == 0u) cult0 = c;
-                a.ps.band_cult[s0 + nb_alive] = c;
-                a.ps.band_size[s0 + nb_alive] = tot;
-                ++nb_alive;
+            }
+            if (joined < 0) joined = (int)nb++;
+            if (gl == i) {
+                band = (uint32_t)joined;
+                size = sz;
+                stored = st;
             }
         }
-        /* adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 */
-        for (uint32_t r = 0; r < n; ++r) {
-            if (btot[band[r]] == 0u) continue;
-            const uint32_t i = idx[r];
-            uint64_t c = bcult[band[r]];
-            uint32_t misc = a.next.misc[i];
-            uint32_t clock = a.next.till_mut[i];
-            const dsim_u4 o = dsim_draw(rs, step, fid[r], DSIM_P_MUT, 0u);
-            if (!(misc & DSIM_MISC_CLOCK)) {
-                misc |= DSIM_MISC_CLOCK;
-                clock = dsim_time_till_next_mutation(dsim_u53(o.x, o.y), a.mc.log1m_rate);
+        /* ---- band culture = culture of a random member; empty bands are dropped, lib.rs:1400-1416.
+         * Lane B holds band B (nb <= n <= PG). ------------------------------------------------------- */
+        uint64_t bcult = 0;
+        uint32_t btot = 0;
+        for (uint32_t B = 0; B < nb; ++B) {
+            const uint32_t members = G.ballot(mine && band == B);
+            uint32_t tot = (mine && band == B) ? size : 0u;
+            tot += __shfl_xor_sync(G.gmask, tot, 4, (int)PG);
+            tot += __shfl_xor_sync(G.gmask, tot, 2, (int)PG);
+            tot += __shfl_xor_sync(G.gmask, tot, 1, (int)PG);
+            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
+            uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)__popc(members));
+            uint32_t m = members;
+            while (pick > 0u) { /* the pick-th member in join order */
+                m &= m - 1u;
+                --pick;
             }
-            if (clock == 0u) {
-                c ^= (uint64_t)1 << (o.z >> 26);
-                const dsim_u4 o2 = dsim_draw(rs, step, fid[r], DSIM_P_MUT, 1u);
-                clock = dsim_time_till_next_mutation(dsim_u53(o2.x, o2.y), a.mc.log1m_rate);
-            } else {
-                clock -= 1u;
+            const uint64_t c = G.get(cult, (uint32_t)__ffs((int)m) - 1u);
+            if (gl == B) {
+                bcult = c;
+                btot = tot;
             }
-            cult[r] = c;
-            a.next.misc[i] = misc;
-            a.next.till_mut[i] = clock;
         }
-        /* exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 */
-        const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
-        double quality = 0.0;
+        /* storage' (lib.rs:622-633): cultures and sizes of the surviving bands, creation order */
+        const uint32_t alive_bands = G.ballot(gl < nb && btot > 0u);
+        if (gl < nb && btot > 0u) {
+            const uint32_t k = (uint32_t)__popc(alive_bands & ((1u << gl) - 1u));
+            a.ps.band_cult[s0 + k] = bcult;
+            a.ps.band_size[s0 + k] = btot;
+        }
+        const uint64_t cult0 = alive_bands ? G.get(bcult, (uint32_t)__ffs((int)alive_bands) - 1u) : 0ull;
+        const bool balive = mine && ((alive_bands >> (mine ? band : 0u)) & 1u) != 0u;
+        /* ---- adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 --------------------------------- */
+        {
+            const uint64_t c_band = G.get(bcult, mine ? band : 0u);
+            if (balive) {
+                uint64_t c = c_band;
+                const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_MUT, 0u);
+                if (!(misc & DSIM_MISC_CLOCK)) { /* None => draw, then re-enter, lib.rs:1763-1774 */
+                    misc |= DSIM_MISC_CLOCK;
+                    clock = dsim_time_till_next_mutation(dsim_u53(o.x, o.y), a.mc.log1m_rate);
+                }
+                if (clock == 0u) { /* Some(0): flip one of 64 bits, redraw, lib.rs:1775-1780, 1277-1285 */
+                    c ^= (uint64_t)1 << (o.z >> 26);
+                    const dsim_u4 o2 = dsim_draw(rs, step, fid, DSIM_P_MUT, 1u);
+                    clock = dsim_time_till_next_mutation(dsim_u53(o2.x, o2.y), a.mc.log1m_rate);
+                } else {
+                    clock -= 1u;
+                }
+                cult = c;
+                a.next.misc[idx] = misc;
+                a.next.till_mut[idx] = clock;
+            }
+        }
+        /* ---- exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 ------------------- */
+        double quality = 0.0, lh = 0.0;
         for (uint32_t e = e0; e < e1; ++e) {
             const uint32_t eco = a.ps.eco_id[e];
-            for (uint32_t B = 0; B < nb; ++B) beff[B] = 0.0;
-            for (uint32_t r = 0; r < n; ++r) {
-                if (btot[band[r]] == 0u) continue;
-                contrib[r] = (double)size[r] * adapt_touch(a, a.next.hs[idx[r]], eco, &errors);
-                beff[band[r]] = beff[band[r]] + contrib[r];
-            }
-            double total_squared = 1.0;
-            for (uint32_t B = 0; B < nb; ++B)
-                if (btot[B] > 0u) total_squared = total_squared + beff[B] * beff[B];
             double res = a.ps.res[e];
             const double mx = a.ps.max_res[e];
+            /* raw_family_contribution, lib.rs:1947-1958 */
+            const double contrib = balive ? (double)size * adapt_touch(a, hs, eco, &errors) : 0.0;
+            double beff = 0.0; /* lane B: sum_effort of band B, in join order */
+            for (uint32_t j = 0; j < n; ++j) {
+                const double cj = G.get(contrib, j);
+                const uint32_t bj = G.get(band, j);
+                if (bj == gl) beff = beff + cj;
+            }
+            double total_squared = 1.0;
             for (uint32_t B = 0; B < nb; ++B) {
-                if (btot[B] == 0u) continue;
-                const double eff = beff[B];
+                const double eff = G.get(beff, B);
+                if ((alive_bands >> B) & 1u) total_squared = total_squared + eff * eff;
+            }
+            double bcoef = 0.0;
+            for (uint32_t B = 0; B < nb; ++B) {
+                const double eff = G.get(beff, B);
+                if (!((alive_bands >> B) & 1u)) continue;
                 if (!(eff > 0.0)) errors |= DSIM_MODEL_EFFORT_NOT_POSITIVE;
                 const double harvest = dsim_oyr_min(res * (eff * eff) / total_squared, a.mc.cap_harvest * season * eff);
                 if (!(harvest > 0.0)) errors |= DSIM_MODEL_HARVEST_NOT_POSITIVE;
                 const double coefficient = dsim_oyr_min(harvest / eff, 2.5);
                 if (!(coefficient > 0.0)) errors |= DSIM_MODEL_COEFF_NOT_POSITIVE;
-                bcoef[B] = coefficient;
+                if (gl == B) bcoef = coefficient;
                 res = res - coefficient * eff;
                 if (!(res >= 0.0)) errors |= DSIM_MODEL_RESOURCES_NEGATIVE;
             }
-            for (uint32_t r = 0; r < n; ++r)
-                if (btot[band[r]] > 0u) lh[r] = bcoef[band[r]] * season * contrib[r];
+            const double my_coef = G.get(bcoef, mine ? band : 0u);
+            if (balive) lh = my_coef * season * contrib;
+            /* recover, lib.rs:2100-2108 */
             if (res < mx) {
                 const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_REGROW, e - e0);
                 res = dsim_oyr_min(mx, mx * a.mc.recovery * (2.0 * dsim_u53(o.x, o.y)) + res);
             }
-            a.ps.res[e] = res;
-            quality = quality + (res + mx * a.mc.recovery);
+            if (gl == 0u) a.ps.res[e] = res;
+            quality = quality + (res + mx * a.mc.recovery); /* expected_harvest for the next step */
         }
-        /* write back */
-        uint32_t pop = 0;
-        for (uint32_t r = 0; r < n; ++r) {
-            const uint32_t i = idx[r];
-            a.next.size[i] = size[r];
-            a.next.stored[i] = stored[r];
-            if (btot[band[r]] > 0u) {
-                a.next.culture[i] = cult[r];
-                if (e1 > e0) a.next.last_harvest[i] = lh[r];
+        /* ---- write back ----------------------------------------------------------------------------- */
+        uint32_t pop = mine ? size : 0u;
+        pop += __shfl_xor_sync(G.gmask, pop, 4, (int)PG);
+        pop += __shfl_xor_sync(G.gmask, pop, 2, (int)PG);
+        pop += __shfl_xor_sync(G.gmask, pop, 1, (int)PG);
+        if (mine) {
+            a.next.size[idx] = size;
+            a.next.stored[idx] = stored;
+            if (balive) {
+                a.next.culture[idx] = cult;
+                if (e1 > e0) a.next.last_harvest[idx] = lh;
             }
-            pop += size[r];
         }
-        PatchView pv;
-        pv.quality = quality;
-        pv.pop = pop;
-        pv.nb = nb_alive;
-        a.ps.view[p] = pv;
-        PatchBands pb;
-        pb.cult0 = cult0;
-        pb.stor_off = s0;
-        pb.pad_ = 0;
-        a.ps.bands[p] = pb;
-        a.ps.cnt[p] = 0u;
+        if (gl == 0u) {
+            PatchView pv;
+            pv.quality = quality;
+            pv.pop = pop;
+            pv.nb = (uint32_t)__popc(alive_bands);
+            a.ps.view[p] = pv;
+            PatchBands pb;
+            pb.cult0 = cult0;
+            pb.stor_off = s0;
+            pb.pad_ = 0;
+            a.ps.bands[p] = pb;
+            a.ps.cnt[p] = 0u;
+        }
     }
     if (errors) atomicOr(&ctl->errors, errors);
 }
