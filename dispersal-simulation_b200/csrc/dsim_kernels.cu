@@ -903,14 +903,17 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
     const size_t base = (size_t)hs * acap;
     const double minimum = a.mc.min_adapt;
     const uint32_t d = a.hv.decay[hs];
+    /* the ecoregion ids of all slots, four per 8-byte load (acap is a multiple of 4), requested together: the scan
+     * costs one memory round trip instead of one per slot */
     int found = -1, spare = -1;
-    for (uint32_t k = 0; k < acap; ++k) {
-        const uint32_t e = a.hv.a_eco[base + k];
-        if (e == eco) {
-            found = (int)k;
-            break;
+    for (uint32_t k = 0; k < acap; k += 4u) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(a.hv.a_eco + base + k);
+        const uint32_t e4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) {
+            if (e4[j] == eco && found < 0) found = (int)(k + j);
+            if (e4[j] == DSIM_ECO_EMPTY && spare < 0) spare = (int)(k + j);
         }
-        if (e == DSIM_ECO_EMPTY && spare < 0) spare = (int)k;
     }
     double v = minimum;
     int slot = found;
