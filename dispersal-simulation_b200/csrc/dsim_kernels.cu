@@ -1228,6 +1228,9 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
  * every collective names only the lanes of its group.
  * ------------------------------------------------------------------------------------------ */
 #define PG 8u /* lanes per group = PATCH_SMALL_MAX */
+#ifndef PATCH_SMALL_MIN_BLOCKS
+#define PATCH_SMALL_MIN_BLOCKS 8
+#endif
 
 struct Grp {
     uint32_t gl, goff, gmask;
@@ -1236,7 +1239,7 @@ struct Grp {
     __device__ __forceinline__ uint32_t ballot(bool pred) const { return (__ballot_sync(gmask, pred) >> goff) & ((1u << PG) - 1u); }
 };
 
-__global__ void __launch_bounds__(128) k_patch_small(StepArgs a) {
+__global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
     const uint32_t n_small = ctl->n_small;
@@ -1524,7 +1527,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
-    case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 4), 128, 0, s, a); break;
+    case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
     case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, 4), PATCH_WARPS * 32, 0, s, a); break;
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;
