@@ -30,6 +30,9 @@
 
 #define LIFE_BLOCK 256
 #define PATCH_WARPS 4
+#ifndef PATCH_MIN_BLOCKS
+#define PATCH_MIN_BLOCKS 8
+#endif
 #define PATCH_M 64 /* families per node handled in shared memory; larger nodes spill to HBM scratch */
 #define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by one thread each */
 
@@ -943,7 +946,247 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
     return v;
 }
 
-__global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
+/* one node of k_patch; inlined twice, once with the working arrays in shared memory (fixed offsets) and once
+ * with them in HBM scratch, so that neither copy carries seventeen live pointers */
+__device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t lane,
+                                           uint32_t step, const dsim_stream rs, double season, uint32_t &errors) {
+    __syncwarp();
+
+    /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id) ----------- */
+    for (uint32_t j = lane; j < n; j += 32u) {
+        const uint32_t i = a.sc.members[s0 + j];
+        const uint64_t id = a.next.id[i];
+        const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
+        M.tidx[j] = i;
+        M.tfid[j] = id;
+        M.key[j] = ((uint64_t)o.y << 32) | o.x;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < n; j += 32u) {
+        const uint64_t kj = M.key[j], ij = M.tfid[j];
+        uint32_t r = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint64_t kk = M.key[k], ik = M.tfid[k];
+            r += (kk < kj || (kk == kj && ik < ij)) ? 1u : 0u;
+        }
+        M.idx[r] = M.tidx[j];
+        M.fid[r] = ij;
+    }
+    __syncwarp();
+    for (uint32_t r = lane; r < n; r += 32u) {
+        const uint32_t i = M.idx[r];
+        M.cult[r] = a.next.culture[i];
+        M.size[r] = a.next.size[i];
+        M.stored[r] = a.next.stored[i];
+        M.band[r] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+
+    /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 -------- */
+    uint32_t nb = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t cf = M.cult[i], fid = M.fid[i];
+        uint32_t sz = M.size[i];
+        double st = M.stored[i];
+        int joined = -1;
+        for (uint32_t B = 0; B < nb && joined < 0; ++B) {
+            bool any_hostile = false;
+            for (uint32_t j0 = 0; j0 < i; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                bool hostile = false;
+                if (j < i) hostile = (M.band[j] == B) && !dsim_will_cooperate(cf, M.cult[j], a.mc.threshold, a.mc.inclusive);
+                uint32_t mask = __ballot_sync(DSIM_FULL, hostile);
+                while (mask != 0u) { /* hostile members in join order */
+                    const uint32_t jj = j0 + (uint32_t)(__ffs((int)mask) - 1);
+                    mask &= mask - 1u;
+                    any_hostile = true;
+                    uint32_t so = M.size[jj];
+                    double sto = M.stored[jj];
+                    __syncwarp();
+                    const uint32_t reduction = sz < so ? sz : so;
+                    const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, jj);
+                    if (o.x < a.mc.deadliness) { /* fight_is_deadly, lib.rs:1219 */
+                        so -= reduction;
+                        if (so == 0u) {
+                            st = st + sto;
+                            sto = 0.0;
+                        }
+                    }
+                    if (o.y < a.mc.deadliness) sz -= reduction; /* lib.rs:1226 */
+                    if (lane == 0) {
+                        M.size[jj] = so;
+                        M.stored[jj] = sto;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!any_hostile) joined = (int)B;
+        }
+        if (joined < 0) joined = (int)nb++;
+        if (lane == 0) {
+            M.band[i] = (uint32_t)joined;
+            M.size[i] = sz;
+            M.stored[i] = st;
+        }
+        __syncwarp();
+    }
+
+    /* ---- band culture = culture of a random member; drop empty bands, lib.rs:1400-1416 -------- */
+    for (uint32_t B = lane; B < nb; B += 32u) {
+        uint32_t cnt = 0, tot = 0;
+        for (uint32_t j = 0; j < n; ++j)
+            if (M.band[j] == B) {
+                cnt += 1u;
+                tot += M.size[j];
+            }
+        const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
+        const uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)cnt);
+        uint64_t c = 0;
+        uint32_t seen = 0;
+        for (uint32_t j = 0; j < n; ++j)
+            if (M.band[j] == B) {
+                if (seen == pick) {
+                    c = M.cult[j];
+                    break;
+                }
+                ++seen;
+            }
+        M.bcult[B] = c;
+        M.bcnt[B] = cnt;
+        M.btot[B] = tot;
+        M.balive[B] = tot > 0u ? 1 : 0;
+    }
+    __syncwarp();
+
+    /* ---- storage' (lib.rs:622-633): cultures and sizes of the surviving bands, creation order -- */
+    uint32_t nb_alive = 0;
+    uint64_t cult0 = 0;
+    for (uint32_t B0 = 0; B0 < nb; B0 += 32u) {
+        const uint32_t B = B0 + lane;
+        const bool al = (B < nb) && M.balive[B];
+        const uint32_t mask = __ballot_sync(DSIM_FULL, al);
+        if (al) {
+            const uint32_t k = nb_alive + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            a.ps.band_cult[s0 + k] = M.bcult[B];
+            a.ps.band_size[s0 + k] = M.btot[B];
+        }
+        if (nb_alive == 0u && mask != 0u) cult0 = __shfl_sync(DSIM_FULL, al ? M.bcult[B] : 0ull, __ffs((int)mask) - 1);
+        nb_alive += (uint32_t)__popc(mask);
+    }
+
+    /* ---- adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 ------------------------------- */
+    for (uint32_t r = lane; r < n; r += 32u) {
+        const uint32_t B = M.band[r];
+        if (!M.balive[B]) continue;
+        const uint32_t i = M.idx[r];
+        uint64_t c = M.bcult[B];
+        uint32_t misc = a.next.misc[i];
+        uint32_t clock = a.next.till_mut[i];
+        const dsim_u4 o = dsim_draw(rs, step, M.fid[r], DSIM_P_MUT, 0u);
+        if (!(misc & DSIM_MISC_CLOCK)) { /* None => draw, then re-enter, lib.rs:1763-1774 */
+            misc |= DSIM_MISC_CLOCK;
+            clock = dsim_time_till_next_mutation(dsim_u53(o.x, o.y), a.mc.log1m_rate);
+        }
+        if (clock == 0u) { /* Some(0): flip one of 64 bits, redraw, lib.rs:1775-1780, 1277-1285 */
+            c ^= (uint64_t)1 << (o.z >> 26);
+            const dsim_u4 o2 = dsim_draw(rs, step, M.fid[r], DSIM_P_MUT, 1u);
+            clock = dsim_time_till_next_mutation(dsim_u53(o2.x, o2.y), a.mc.log1m_rate);
+        } else {
+            clock -= 1u;
+        }
+        M.cult[r] = c;
+        a.next.misc[i] = misc;
+        a.next.till_mut[i] = clock;
+    }
+    __syncwarp();
+
+    /* ---- exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 ------------------ */
+    const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
+    double quality = 0.0;
+    for (uint32_t e = e0; e < e1; ++e) {
+        const uint32_t eco = a.ps.eco_id[e];
+        for (uint32_t r = lane; r < n; r += 32u) { /* raw_family_contribution, lib.rs:1947-1958 */
+            double c = 0.0;
+            if (M.balive[M.band[r]]) c = (double)M.size[r] * adapt_touch(a, a.next.hs[M.idx[r]], eco, &errors);
+            M.contrib[r] = c;
+        }
+        __syncwarp();
+        for (uint32_t B = lane; B < nb; B += 32u) { /* sum_effort in join order */
+            double eff = 0.0;
+            if (M.balive[B])
+                for (uint32_t j = 0; j < n; ++j)
+                    if (M.band[j] == B) eff = eff + M.contrib[j];
+            M.beff[B] = eff;
+        }
+        __syncwarp();
+        double total_squared = 1.0;
+        for (uint32_t B = 0; B < nb; ++B)
+            if (M.balive[B]) total_squared = total_squared + M.beff[B] * M.beff[B];
+        double res = a.ps.res[e];
+        const double mx = a.ps.max_res[e];
+        for (uint32_t B = 0; B < nb; ++B) {
+            if (!M.balive[B]) continue;
+            const double eff = M.beff[B];
+            if (!(eff > 0.0)) errors |= DSIM_MODEL_EFFORT_NOT_POSITIVE;
+            const double harvest = dsim_oyr_min(res * (eff * eff) / total_squared, a.mc.cap_harvest * season * eff);
+            if (!(harvest > 0.0)) errors |= DSIM_MODEL_HARVEST_NOT_POSITIVE;
+            const double coefficient = dsim_oyr_min(harvest / eff, 2.5);
+            if (!(coefficient > 0.0)) errors |= DSIM_MODEL_COEFF_NOT_POSITIVE;
+            if (lane == 0) M.bcoef[B] = coefficient;
+            res = res - coefficient * eff;
+            if (!(res >= 0.0)) errors |= DSIM_MODEL_RESOURCES_NEGATIVE;
+        }
+        __syncwarp();
+        for (uint32_t r = lane; r < n; r += 32u) {
+            const uint32_t B = M.band[r];
+            if (M.balive[B]) M.lh[r] = M.bcoef[B] * season * M.contrib[r];
+        }
+        /* recover, lib.rs:2100-2108 */
+        if (res < mx) {
+            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_REGROW, e - e0);
+            const double proportion = 2.0 * dsim_u53(o.x, o.y);
+            res = dsim_oyr_min(mx, mx * a.mc.recovery * proportion + res);
+        }
+        if (lane == 0) a.ps.res[e] = res;
+        quality = quality + (res + mx * a.mc.recovery); /* expected_harvest for the next step */
+        __syncwarp();
+    }
+
+    /* ---- write back ----------------------------------------------------------------------- */
+    uint32_t pop = 0;
+    for (uint32_t r = lane; r < n; r += 32u) {
+        const uint32_t i = M.idx[r];
+        const uint32_t sz = M.size[r];
+        a.next.size[i] = sz;
+        a.next.stored[i] = M.stored[r];
+        if (M.balive[M.band[r]]) {
+            a.next.culture[i] = M.cult[r];
+            if (e1 > e0) a.next.last_harvest[i] = M.lh[r];
+        }
+        pop += sz;
+    }
+    pop += __shfl_xor_sync(DSIM_FULL, pop, 16);
+    pop += __shfl_xor_sync(DSIM_FULL, pop, 8);
+    pop += __shfl_xor_sync(DSIM_FULL, pop, 4);
+    pop += __shfl_xor_sync(DSIM_FULL, pop, 2);
+    pop += __shfl_xor_sync(DSIM_FULL, pop, 1);
+    if (lane == 0) {
+        PatchView v;
+        v.quality = quality;
+        v.pop = pop;
+        v.nb = nb_alive;
+        a.ps.view[p] = v;
+        PatchBands b;
+        b.cult0 = cult0;
+        b.stor_off = s0;
+        b.pad_ = 0;
+        a.ps.bands[p] = b;
+        a.ps.cnt[p] = 0u;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(StepArgs a) {
     __shared__ uint32_t s_u32[PATCH_WARPS][6][PATCH_M];
     __shared__ uint64_t s_u64[PATCH_WARPS][5][PATCH_M];
     __shared__ double s_f64[PATCH_WARPS][5][PATCH_M];
@@ -971,6 +1214,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
             M.stored = s_f64[wib][0]; M.contrib = s_f64[wib][1]; M.lh = s_f64[wib][2]; M.beff = s_f64[wib][3];
             M.bcoef = s_f64[wib][4];
             M.balive = s_u8[wib];
+            patch_node(a, M, p, n, s0, lane, step, rs, season, errors);
         } else {
             M.idx = a.sc.x_idx + s0; M.tidx = a.sc.x_tidx + s0; M.size = a.sc.x_size + s0; M.band = a.sc.x_band + s0;
             M.bcnt = a.sc.x_bcnt + s0; M.btot = a.sc.x_btot + s0;
@@ -979,241 +1223,8 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32) k_patch(StepArgs a) {
             M.stored = a.sc.x_stored + s0; M.contrib = a.sc.x_contrib + s0; M.lh = a.sc.x_lh + s0;
             M.beff = a.sc.x_beff + s0; M.bcoef = a.sc.x_bcoef + s0;
             M.balive = a.sc.x_balive + s0;
+            patch_node(a, M, p, n, s0, lane, step, rs, season, errors);
         }
-        __syncwarp();
-
-        /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id) ----------- */
-        for (uint32_t j = lane; j < n; j += 32u) {
-            const uint32_t i = a.sc.members[s0 + j];
-            const uint64_t id = a.next.id[i];
-            const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
-            M.tidx[j] = i;
-            M.tfid[j] = id;
-            M.key[j] = ((uint64_t)o.y << 32) | o.x;
-        }
-        __syncwarp();
-        for (uint32_t j = lane; j < n; j += 32u) {
-            const uint64_t kj = M.key[j], ij = M.tfid[j];
-            uint32_t r = 0;
-            for (uint32_t k = 0; k < n; ++k) {
-                const uint64_t kk = M.key[k], ik = M.tfid[k];
-                r += (kk < kj || (kk == kj && ik < ij)) ? 1u : 0u;
-            }
-            M.idx[r] = M.tidx[j];
-            M.fid[r] = ij;
-        }
-        __syncwarp();
-        for (uint32_t r = lane; r < n; r += 32u) {
-            const uint32_t i = M.idx[r];
-            M.cult[r] = a.next.culture[i];
-            M.size[r] = a.next.size[i];
-            M.stored[r] = a.next.stored[i];
-            M.band[r] = 0xFFFFFFFFu;
-        }
-        __syncwarp();
-
-        /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 -------- */
-        uint32_t nb = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint64_t cf = M.cult[i], fid = M.fid[i];
-            uint32_t sz = M.size[i];
-            double st = M.stored[i];
-            int joined = -1;
-            for (uint32_t B = 0; B < nb && joined < 0; ++B) {
-                bool any_hostile = false;
-                for (uint32_t j0 = 0; j0 < i; j0 += 32u) {
-                    const uint32_t j = j0 + lane;
-                    bool hostile = false;
-                    if (j < i) hostile = (M.band[j] == B) && !dsim_will_cooperate(cf, M.cult[j], a.mc.threshold, a.mc.inclusive);
-                    uint32_t mask = __ballot_sync(DSIM_FULL, hostile);
-                    while (mask != 0u) { /* hostile members in join order */
-                        const uint32_t jj = j0 + (uint32_t)(__ffs((int)mask) - 1);
-                        mask &= mask - 1u;
-                        any_hostile = true;
-                        uint32_t so = M.size[jj];
-                        double sto = M.stored[jj];
-                        __syncwarp();
-                        const uint32_t reduction = sz < so ? sz : so;
-                        const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, jj);
-                        if (o.x < a.mc.deadliness) { /* fight_is_deadly, lib.rs:1219 */
-                            so -= reduction;
-                            if (so == 0u) {
-                                st = st + sto;
-                                sto = 0.0;
-                            }
-                        }
-                        if (o.y < a.mc.deadliness) sz -= reduction; /* lib.rs:1226 */
-                        if (lane == 0) {
-                            M.size[jj] = so;
-                            M.stored[jj] = sto;
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (!any_hostile) joined = (int)B;
-            }
-            if (joined < 0) joined = (int)nb++;
-            if (lane == 0) {
-                M.band[i] = (uint32_t)joined;
-                M.size[i] = sz;
-                M.stored[i] = st;
-            }
-            __syncwarp();
-        }
-
-        /* ---- band culture = culture of a random member; drop empty bands, lib.rs:1400-1416 -------- */
-        for (uint32_t B = lane; B < nb; B += 32u) {
-            uint32_t cnt = 0, tot = 0;
-            for (uint32_t j = 0; j < n; ++j)
-                if (M.band[j] == B) {
-                    cnt += 1u;
-                    tot += M.size[j];
-                }
-            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
-            const uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)cnt);
-            uint64_t c = 0;
-            uint32_t seen = 0;
-            for (uint32_t j = 0; j < n; ++j)
-                if (M.band[j] == B) {
-                    if (seen == pick) {
-                        c = M.cult[j];
-                        break;
-                    }
-                    ++seen;
-                }
-            M.bcult[B] = c;
-            M.bcnt[B] = cnt;
-            M.btot[B] = tot;
-            M.balive[B] = tot > 0u ? 1 : 0;
-        }
-        __syncwarp();
-
-        /* ---- storage' (lib.rs:622-633): cultures and sizes of the surviving bands, creation order -- */
-        uint32_t nb_alive = 0;
-        uint64_t cult0 = 0;
-        for (uint32_t B0 = 0; B0 < nb; B0 += 32u) {
-            const uint32_t B = B0 + lane;
-            const bool al = (B < nb) && M.balive[B];
-            const uint32_t mask = __ballot_sync(DSIM_FULL, al);
-            if (al) {
-                const uint32_t k = nb_alive + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                a.ps.band_cult[s0 + k] = M.bcult[B];
-                a.ps.band_size[s0 + k] = M.btot[B];
-            }
-            if (nb_alive == 0u && mask != 0u) cult0 = __shfl_sync(DSIM_FULL, al ? M.bcult[B] : 0ull, __ffs((int)mask) - 1);
-            nb_alive += (uint32_t)__popc(mask);
-        }
-
-        /* ---- adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 ------------------------------- */
-        for (uint32_t r = lane; r < n; r += 32u) {
-            const uint32_t B = M.band[r];
-            if (!M.balive[B]) continue;
-            const uint32_t i = M.idx[r];
-            uint64_t c = M.bcult[B];
-            uint32_t misc = a.next.misc[i];
-            uint32_t clock = a.next.till_mut[i];
-            const dsim_u4 o = dsim_draw(rs, step, M.fid[r], DSIM_P_MUT, 0u);
-            if (!(misc & DSIM_MISC_CLOCK)) { /* None => draw, then re-enter, lib.rs:1763-1774 */
-                misc |= DSIM_MISC_CLOCK;
-                clock = dsim_time_till_next_mutation(dsim_u53(o.x, o.y), a.mc.log1m_rate);
-            }
-            if (clock == 0u) { /* Some(0): flip one of 64 bits, redraw, lib.rs:1775-1780, 1277-1285 */
-                c ^= (uint64_t)1 << (o.z >> 26);
-                const dsim_u4 o2 = dsim_draw(rs, step, M.fid[r], DSIM_P_MUT, 1u);
-                clock = dsim_time_till_next_mutation(dsim_u53(o2.x, o2.y), a.mc.log1m_rate);
-            } else {
-                clock -= 1u;
-            }
-            M.cult[r] = c;
-            a.next.misc[i] = misc;
-            a.next.till_mut[i] = clock;
-        }
-        __syncwarp();
-
-        /* ---- exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 ------------------ */
-        const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
-        double quality = 0.0;
-        for (uint32_t e = e0; e < e1; ++e) {
-            const uint32_t eco = a.ps.eco_id[e];
-            for (uint32_t r = lane; r < n; r += 32u) { /* raw_family_contribution, lib.rs:1947-1958 */
-                double c = 0.0;
-                if (M.balive[M.band[r]]) c = (double)M.size[r] * adapt_touch(a, a.next.hs[M.idx[r]], eco, &errors);
-                M.contrib[r] = c;
-            }
-            __syncwarp();
-            for (uint32_t B = lane; B < nb; B += 32u) { /* sum_effort in join order */
-                double eff = 0.0;
-                if (M.balive[B])
-                    for (uint32_t j = 0; j < n; ++j)
-                        if (M.band[j] == B) eff = eff + M.contrib[j];
-                M.beff[B] = eff;
-            }
-            __syncwarp();
-            double total_squared = 1.0;
-            for (uint32_t B = 0; B < nb; ++B)
-                if (M.balive[B]) total_squared = total_squared + M.beff[B] * M.beff[B];
-            double res = a.ps.res[e];
-            const double mx = a.ps.max_res[e];
-            for (uint32_t B = 0; B < nb; ++B) {
-                if (!M.balive[B]) continue;
-                const double eff = M.beff[B];
-                if (!(eff > 0.0)) errors |= DSIM_MODEL_EFFORT_NOT_POSITIVE;
-                const double harvest = dsim_oyr_min(res * (eff * eff) / total_squared, a.mc.cap_harvest * season * eff);
-                if (!(harvest > 0.0)) errors |= DSIM_MODEL_HARVEST_NOT_POSITIVE;
-                const double coefficient = dsim_oyr_min(harvest / eff, 2.5);
-                if (!(coefficient > 0.0)) errors |= DSIM_MODEL_COEFF_NOT_POSITIVE;
-                if (lane == 0) M.bcoef[B] = coefficient;
-                res = res - coefficient * eff;
-                if (!(res >= 0.0)) errors |= DSIM_MODEL_RESOURCES_NEGATIVE;
-            }
-            __syncwarp();
-            for (uint32_t r = lane; r < n; r += 32u) {
-                const uint32_t B = M.band[r];
-                if (M.balive[B]) M.lh[r] = M.bcoef[B] * season * M.contrib[r];
-            }
-            /* recover, lib.rs:2100-2108 */
-            if (res < mx) {
-                const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_REGROW, e - e0);
-                const double proportion = 2.0 * dsim_u53(o.x, o.y);
-                res = dsim_oyr_min(mx, mx * a.mc.recovery * proportion + res);
-            }
-            if (lane == 0) a.ps.res[e] = res;
-            quality = quality + (res + mx * a.mc.recovery); /* expected_harvest for the next step */
-            __syncwarp();
-        }
-
-        /* ---- write back ----------------------------------------------------------------------- */
-        uint32_t pop = 0;
-        for (uint32_t r = lane; r < n; r += 32u) {
-            const uint32_t i = M.idx[r];
-            const uint32_t sz = M.size[r];
-            a.next.size[i] = sz;
-            a.next.stored[i] = M.stored[r];
-            if (M.balive[M.band[r]]) {
-                a.next.culture[i] = M.cult[r];
-                if (e1 > e0) a.next.last_harvest[i] = M.lh[r];
-            }
-            pop += sz;
-        }
-        pop += __shfl_xor_sync(DSIM_FULL, pop, 16);
-        pop += __shfl_xor_sync(DSIM_FULL, pop, 8);
-        pop += __shfl_xor_sync(DSIM_FULL, pop, 4);
-        pop += __shfl_xor_sync(DSIM_FULL, pop, 2);
-        pop += __shfl_xor_sync(DSIM_FULL, pop, 1);
-        if (lane == 0) {
-            PatchView v;
-            v.quality = quality;
-            v.pop = pop;
-            v.nb = nb_alive;
-            a.ps.view[p] = v;
-            PatchBands b;
-            b.cult0 = cult0;
-            b.stor_off = s0;
-            b.pad_ = 0;
-            a.ps.bands[p] = b;
-            a.ps.cnt[p] = 0u;
-        }
-        __syncwarp();
     }
     if (errors) atomicOr(&ctl->errors, errors);
 }
@@ -1528,7 +1539,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
     case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
-    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, 4), PATCH_WARPS * 32, 0, s, a); break;
+    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, 0, s, a); break;
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;
     }
