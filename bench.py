@@ -187,7 +187,10 @@ def algorithmic_bytes(sim, fam_hist_len, mem_table, rho_src):
 
 
 def main():
-    os.environ["NCCL_DEBUG"] = os.environ.get("DSIM_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
+    # stdout carries exactly one JSON line: NCCL's own messages (version banner at NCCL_DEBUG=VERSION/WARN/INFO) go to stderr
+    if "DSIM_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["DSIM_NCCL_DEBUG"]
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
