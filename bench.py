@@ -167,7 +167,7 @@ def run_reference(args, cfg_name, cfg):
         "e2e": {"value": rate, "unit": "family-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -186,7 +186,26 @@ def algorithmic_bytes(sim, fam_hist_len, mem_table, rho_src):
     return b, {"K": K, "R": R, "n_h": n_h, "rho": rho_src}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that native libraries print there (NCCL's version banner,
+    # for one) is sent to stderr by pointing file descriptor 1 at it; emit() writes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     # stdout carries exactly one JSON line: NCCL's own messages (version banner at NCCL_DEBUG=VERSION/WARN/INFO) go to stderr
     if "DSIM_NCCL_DEBUG" in os.environ:
         os.environ["NCCL_DEBUG"] = os.environ["DSIM_NCCL_DEBUG"]
@@ -388,7 +407,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches2 - launches1),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

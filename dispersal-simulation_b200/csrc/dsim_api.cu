@@ -1559,6 +1559,8 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes) {
     return DSIM_OK;
 }
 
+enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
+
 static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
     const MgBuffers &mb = m->mb;
@@ -1575,9 +1577,18 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     case DSIM_MG_PHASE_LIFECYCLE:
         K(DSIM_K_LIFECYCLE, a1); K(DSIM_K_CONTROL, a1); M(DSIM_MGK_SPLIT_IDS, a1);
         break;
-    case DSIM_MG_PHASE_MOVE:
-        M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
+    case DSIM_MG_PHASE_MOVE: /* the children's ids (CHILD_RANK, from the SPLIT exchange) are first needed by k_children */
+        K(DSIM_K_MOVE, a1); M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
         break;
+    case MG_PHASE_MOVE_A: K(DSIM_K_MOVE, a1); break;
+    case MG_PHASE_MOVE_B:
+        M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
+        break;
+    case MG_PHASE_FINISH_HALO: /* on the second stream, next to MG_PHASE_FINISH_BOOK */
+        dsim_mg_launch(DSIM_MGK_HALO_UNPACK, a2, mb, h->geom, h->stream2);
+        h->total_launches += 1;
+        break;
+    case MG_PHASE_FINISH_BOOK: M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2); break;
     case DSIM_MG_PHASE_PATCH:
         M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2);
         /* the two patch kernels work on disjoint nodes: run them concurrently (second stream, also inside a capture) */
@@ -1662,10 +1673,11 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
         }                                                                                 \
     } while (0)
 
-static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel) {
+static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel, cudaStream_t stream = nullptr) {
     const MgBuffers &mb = m->mb;
+    if (stream == nullptr) stream = h->stream;
     if (channel == DSIM_MG_CH_SPLIT) {
-        NCK(ncclAllGather(mb.split_send, mb.split_recv, 1 + (size_t)mb.scap, ncclUint64, m->comm, h->stream));
+        NCK(ncclAllGather(mb.split_send, mb.split_recv, 1 + (size_t)mb.scap, ncclUint64, m->comm, stream));
         return DSIM_OK;
     }
     const uint64_t bytes = channel == DSIM_MG_CH_EMIGRANTS ? m->emig_bytes : m->halo_bytes;
@@ -1675,8 +1687,8 @@ static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel) {
         const int peer = s == 0 ? (int)m->rank - 1 : (int)m->rank + 1;
         unsigned char *snd = channel == DSIM_MG_CH_EMIGRANTS ? mb.emig_send[s] : mb.halo_send[s];
         unsigned char *rcv = channel == DSIM_MG_CH_EMIGRANTS ? mb.emig_recv[s] : mb.halo_recv[s];
-        NCK(ncclSend(snd, bytes, ncclChar, peer, m->comm, h->stream));
-        NCK(ncclRecv(rcv, bytes, ncclChar, peer, m->comm, h->stream));
+        NCK(ncclSend(snd, bytes, ncclChar, peer, m->comm, stream));
+        NCK(ncclRecv(rcv, bytes, ncclChar, peer, m->comm, stream));
     }
     NCK(ncclGroupEnd());
     return DSIM_OK;
@@ -1685,14 +1697,29 @@ static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel) {
 
 #if !defined(DSIM_EMU)
 static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
+    /* Two of the three exchanges ride on the second stream next to work that does not need them: the SPLIT
+     * all-gather (children's ids, first used by k_children) next to k_move, and the HALO exchange (views for the next
+     * step's k_move) next to the allocator bookkeeping.  The communicator sees its operations in one order: every
+     * exchange is joined back into the main stream before the next one is enqueued. */
     int rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
-    if ((rc = mg_exchange(h, m, DSIM_MG_CH_SPLIT))) return rc;
-    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_MOVE))) return rc;
+    CK(cudaEventRecord(h->fork_ev, h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_SPLIT, h->stream2))) return rc;
+    CK(cudaEventRecord(h->join_ev, h->stream2));
+    if ((rc = mg_launch_phase(h, m, MG_PHASE_MOVE_A))) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+    if ((rc = mg_launch_phase(h, m, MG_PHASE_MOVE_B))) return rc;
     if ((rc = mg_exchange(h, m, DSIM_MG_CH_EMIGRANTS))) return rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
-    if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO))) return rc;
-    return mg_launch_phase(h, m, DSIM_MG_PHASE_FINISH);
+    CK(cudaEventRecord(h->fork_ev, h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+    if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO, h->stream2))) return rc;
+    if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_HALO))) return rc;
+    CK(cudaEventRecord(h->join_ev, h->stream2));
+    if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_BOOK))) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+    return DSIM_OK;
 }
 #endif
 
