@@ -175,8 +175,9 @@ def algorithmic_bytes(sim, fam_hist_len, mem_table, rho_src):
     """Algorithmic HBM bytes per family-update of k_move, SURVEY.md §8d's formula restricted to part 1
     (DESIGN.md §5): core record read + write (2 x 56), history append (16), the n_h remembered entries
     that are sampled (16 each), and per sensed candidate the reach entry (dest u32 + cost f64 = 12) plus
-    what is gathered about the candidate patch (census, quality, band cultures: one 32-byte view); the
-    candidate terms are shared by the rho families that start the step on the same patch."""
+    what is gathered about the candidate patch (census and quality: a 16-byte view; band cultures: a
+    16-byte record, counted for every candidate as SURVEY.md does); the candidate terms are shared by
+    the rho families that start the step on the same patch."""
     near_off, _, reach_off, _, _ = sim.get_reach()
     n = len(near_off) - 1
     K = float(near_off[n]) / n          # sensed candidates per patch (2-hop list)
@@ -283,7 +284,8 @@ def main():
 
     launches0 = sim.launch_count()
     barrier()
-    sim.step(args.warmup, want_stats=True, allow_model_errors=True)
+    st_w = sim.step(args.warmup, want_stats=True, allow_model_errors=True)
+    log(f"[bench] rank {rank}: {st_w.live_families} live families after {args.warmup} warm-up steps")
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -342,8 +344,19 @@ def main():
             bytes_per_launch = (152 + 90 / max(fam_live / occ, 1.0)) * upd_per_launch
         dur_s = kernels[top]["ms_per_launch"] * 1e-3
         achieved = bytes_per_launch / dur_s / 1e9
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (per family-update there,
+        # scaled to this run's launch size)
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(REPO, "profiles", "r01_k_move_ncu.json")) as f:
+                ncu = json.load(f)
+            if top == "k_move":
+                traffic = ncu["dram_bytes_per_family_update"] * upd_per_launch
+                traffic_src = "profiles/r01_k_move_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum per family-update x families per launch"
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_family_update": b_move if top == "k_move" else None, "terms": parts}
 
     # ---- end to end through the C ABI from host buffers -----------------------------------------------

@@ -1,23 +1,25 @@
 /*
  * dsim_kernels.cu — the step loop of the dispersal model as sm_100a kernels.
  *
- * One season = `step` (lib.rs:477-496) = seven launches, replayed as a CUDA graph:
+ * One season = `step` (lib.rs:477-496) = nine launches, replayed as a CUDA graph:
  *
  *   part 1, update_each_family_step (lib.rs:511-552)
  *     k_lifecycle   consume / shrink / grow per family (lib.rs:527-539, 1912-1937); survivor and
- *                   split bitmaps + per-256 counts (the `retain` of lib.rs:541 becomes a scan)
+ *                   split bitmaps, per-word and per-256 counts (the `retain` of lib.rs:541 becomes a scan)
  *     k_control     single block: exclusive scan of the per-256 counts, step bookkeeping
- *     k_move        one warp per family: decide_on_moving + best_location (lib.rs:830-929),
- *                   destination_quality (lib.rs:1034-1062), move bookkeeping (lib.rs:1826-1833),
- *                   maybe_procreate + the child's own move (lib.rs:1840-1855, 1869-1897); writes the
- *                   compacted next family buffer; counts arrivals per node (histogram of the
- *                   counting sort by patch)
+ *     k_move        one warp per tile of 4 families: decide_on_moving + best_location (lib.rs:830-929),
+ *                   destination_quality (lib.rs:1034-1062), move bookkeeping (lib.rs:1826-1833), the
+ *                   parent's half of maybe_procreate (lib.rs:1869-1897); writes the compacted next
+ *                   family buffer; counts arrivals per node (histogram of the counting sort by patch)
+ *     k_children    one warp per child: its record, history and adaptation, its own move
+ *                   (lib.rs:1840-1855, 1877-1895)
  *   part 2, distribute_each_patch_resources_step (lib.rs:591-655)
  *     k_segments    one thread per occupied node: claim a segment of `members`
  *     k_scatter     one thread per family: counting-sort scatter; clears the views of vacated nodes
- *     k_patch       one warp per occupied node: cooperate_or_fight (lib.rs:1372-1417), adjust_culture
- *                   / mutate (lib.rs:1754-1785, 1960-1970), exploit_patch + recover (lib.rs:2021-2109),
- *                   next step's census, quality and band cultures (lib.rs:522-525, 989-994, 622-633)
+ *     k_patch_small eight lanes per node with at most 8 families, k_patch one warp per crowded node (the two
+ *                   run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
+ *                   (lib.rs:1754-1785, 1960-1970), exploit_patch + recover (lib.rs:2021-2109), next step's
+ *                   census, quality and band cultures (lib.rs:522-525, 989-994, 622-633)
  *     k_advance     one thread: heavy-slot allocator bookkeeping, t += 1 (src/cli.rs:154)
  *
  * Floating point: doubles, IEEE operations only, compiled with -fmad=false so that every decision
@@ -34,7 +36,7 @@
 #define PATCH_MIN_BLOCKS 8
 #endif
 #define PATCH_M 64 /* families per node handled in shared memory; larger nodes spill to HBM scratch */
-#define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by one thread each */
+#define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by a group of 8 lanes each */
 
 __device__ __forceinline__ dsim_stream stream_of(const ModelConst &mc) {
     dsim_stream s;
