@@ -229,7 +229,7 @@ class Sim:
 
     def __init__(self, lib: C.CDLL, graph: Graph, params: Optional[Params] = None, seed: int = 1,
                  options: Optional[Options] = None, prefix: str = "dsim_"):
-        self.lib, self.prefix, self.graph = lib, prefix, graph
+        self.lib, self.prefix, self.graph, self.seed = lib, prefix, graph, int(seed)
         self._declare()
         self.params = params if params is not None else self.default_params()
         self.options = options if options is not None else self.default_options()
