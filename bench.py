@@ -40,6 +40,10 @@ CONFIGS = {
     "c2": (1155, 1732, 100_000, 0, 625),     # Americas-scale grid, 1 GPU (the metric's configuration)
     "c3": (1155, 1732, 1_000_000, 0, 625),   # Americas-scale grid, 1M families
     "c4": (2582, 3873, 10_000_000, 1_250_000, 64),  # stress: dense co-residence
+    # diagnostics (not bench lines): the C2 population with short histories on the continental grid and on a grid
+    # whose reach table fits in L2 -- separates memory-system effects from instruction effects in k_move
+    "x_big_h64": (1155, 1732, 100_000, 0, 64),
+    "x_small_h64": (120, 180, 100_000, 0, 64),
 }
 
 
@@ -269,6 +273,9 @@ def main():
     opt.flags = args.flags
     if world > 1:
         opt.family_capacity = 4 * cfg[2] // world + 65536
+    elif cfg[2] >= 5_000_000:
+        # 10M families: the default capacity (2x) of exact-length histories (628 entries) would not fit 180 GB
+        opt.family_capacity = int(1.2 * cfg[2])
     t0 = time.time()
     sim = D.Sim(lib, g, seed=args.sim_seed, options=opt)
     log(f"[bench] rank {rank}: handle + reach table in {time.time() - t0:.1f}s")
@@ -363,11 +370,24 @@ def main():
     e2e = None
     if not args.no_e2e and world == 1:
         n_steps_e2e = max(1, args.steps)
+        # the host side of the end-to-end run lives in pinned memory (the caller's buffers of a resumed run)
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)), pin_memory=True)
+            v = t.numpy()
+            v[...] = a
+            return v, t
+        keep = []
+        res_p, t_ = pinned(res); keep.append(t_)
+        mx_p, t_ = pinned(mx); keep.append(t_)
+        fam_p = D.Families(fam.n)
+        for name in [n_ for n_, _ in D._FAM_FIELDS] + ["hist_off", "hist_patch", "hist_harvest", "adapt_off", "adapt_eco", "adapt_val"]:
+            v, t_ = pinned(getattr(fam, name)); keep.append(t_)
+            setattr(fam_p, name, v)
         barrier()
         t0 = time.perf_counter()
         sim2 = sim  # same handle: re-upload the initial state, run, download
-        sim2.set_patches(res, mx)
-        sim2.set_families(fam)
+        sim2.set_patches(res_p, mx_p)
+        sim2.set_families(fam_p)
         upd = 0
         for _ in range(n_steps_e2e):
             s1 = sim2.step(1, allow_model_errors=True)      # stats read-back every step (cli.rs:138 extinction check)
@@ -388,7 +408,7 @@ def main():
             dt_all, upd_all = dt, float(upd)
         e2e = {"value": upd_all / dt_all, "unit": "family-updates/s", "h2d_bytes_per_step": h2d / n_steps_e2e,
                "d2h_bytes_per_step": d2h / n_steps_e2e, "steps": n_steps_e2e,
-               "what": "dsim_set_patches + dsim_set_families from host arrays, steps with per-step stats read-back, "
+               "what": "dsim_set_patches + dsim_set_families from pinned host arrays, steps with per-step stats read-back, "
                        "dsim_get_families (core columns) + dsim_get_patches, wall clock"}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
