@@ -268,8 +268,11 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
 
 int ensure_capacity(dsim_handle *h, uint64_t n_now) {
     if (h->mg_enabled) return DSIM_OK; /* fixed capacity per rank (dsim_options.family_capacity) */
-    if (n_now * 10 <= h->cap * 7) return DSIM_OK;
-    uint64_t want = std::max<uint64_t>(2 * n_now + 1024, h->cap);
+    /* default: keep 30 % head room and double; with a capacity chosen by the caller (dsim_options.family_capacity,
+     * e.g. because twice the population would not fit the device) grow late and by a quarter */
+    const bool tight = h->opt.family_capacity != 0;
+    if (tight ? (n_now * 100 <= h->cap * 92) : (n_now * 10 <= h->cap * 7)) return DSIM_OK;
+    uint64_t want = std::max<uint64_t>(tight ? n_now + n_now / 4 + 1024 : 2 * n_now + 1024, h->cap);
     if (want == h->cap) return DSIM_OK;
     int rc = sync_ctl(h);
     if (rc) return rc;
