@@ -136,3 +136,48 @@ def test_kernel_variants(oracle, gpu_lib, synth, flags):
         p.cooperation_threshold = 65
     o, d = pc.build_pair(oracle, gpu_lib, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96, flags=flags)
     pc.run_lockstep(o, d, 40, by_parts=False, hist_cap=96, check_every=4)
+
+
+def test_full_size_invariants(gpu_lib, synth):
+    """BASELINE.json configs[1] at full size (1155x1732 patches, 100k families, 625-entry histories), where the oracle
+    would take minutes per step: properties that do not depend on the size.
+    * determinism: two handles fed the same state agree bit for bit after the same steps (no race decides anything);
+    * batching: 6 steps in one call (CUDA-graph replay) == 6 calls of one step;
+    * census: the `storage` map (lib.rs:622-633) holds exactly the families' sizes, per patch;
+    * the family vector stays in id order with unique ids (lib.rs:541,551: retain + append), ids of children above
+      every id of the start state, parents known;
+    * resources stay within [0, max] (lib.rs:2060-2063, 2100-2108)."""
+    import bench
+    g, res, mx, fam = bench.build_workload(bench.CONFIGS["c2"], 1, synth)
+
+    def make():
+        s = pc.D.Sim(gpu_lib, g, seed=7)
+        s.set_patches(res, mx)
+        s.set_families(fam)
+        return s
+    a, b = make(), make()
+    sa = a.step(6, allow_model_errors=True)
+    for _ in range(6):
+        sb = b.step(1, allow_model_errors=True)
+    assert sa.model_errors == 0 and sb.model_errors == 0
+    assert sa.live_families == sb.live_families and sa.t == sb.t == 6
+    fa, fb = a.get_families(), b.get_families()
+    for name, _ in pc.D._FAM_FIELDS:
+        x, y = getattr(fa, name), getattr(fb, name)
+        assert x.shape == y.shape and (x.view(np.uint8) == y.view(np.uint8)).all(), name
+    assert (fa.hist_off == fb.hist_off).all() and (fa.hist_patch == fb.hist_patch).all()
+    assert (fa.hist_harvest.view(np.uint64) == fb.hist_harvest.view(np.uint64)).all()
+    ra, ma = a.get_patches()
+    rb, _ = b.get_patches()
+    assert (ra.view(np.uint64) == rb.view(np.uint64)).all()
+    # vector order = id order, unique; children are younger than every initial family
+    assert (np.diff(fa.id.astype(np.int64)) > 0).all()
+    born = fa.parent_id != pc.D.NO_PARENT
+    assert born.sum() > 0 and fa.id[born].min() >= fam.n and (fa.parent_id[born] < fa.id[born]).all()
+    assert (fa.size >= 0).all() and (fa.location < g.n_nodes).all()
+    # census: storage' sums the sizes of the families of every patch (bands of total size 0 are dropped)
+    node, cul, size = a.get_storage()
+    per_patch = np.bincount(fa.location.astype(np.int64), weights=fa.size.astype(np.float64), minlength=g.n_nodes)
+    from_storage = np.bincount(node.astype(np.int64), weights=size.astype(np.float64), minlength=g.n_nodes)
+    assert (per_patch == from_storage).all()
+    assert (ra >= 0).all() and (ra <= ma).all()
