@@ -45,8 +45,8 @@ struct dsim_handle {
     dsim_params p;
     dsim_options opt;
     uint64_t seed = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr;
     LaunchGeom geom;
     uint32_t n_nodes = 0, n_eco = 0;
     std::vector<uint32_t> eco_off_h; /* [n+1] */
@@ -173,6 +173,7 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     a.occ_par = parity;
     std::memset(&a.mg, 0, sizeof a.mg);
     a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
+    a.mid_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 32u;
     return a;
 }
 
@@ -206,7 +207,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
     A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8) A(ns.word_pre, new_cap / 32 + 8)
     A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
     A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
-    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_small, new_cap) A(ns.plist_big, new_cap)
+    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_small, new_cap) A(ns.plist_mid, new_cap) A(ns.plist_big, new_cap)
     A(ns.child_task, new_cap)
     A(ns.x_idx, new_cap) A(ns.x_tidx, new_cap) A(ns.x_size, new_cap) A(ns.x_band, new_cap)
     A(ns.x_bcnt, new_cap) A(ns.x_btot, new_cap)
@@ -294,10 +295,14 @@ int build_graphs(dsim_handle *h) {
         for (int k = 0; k < DSIM_K_PATCH_SMALL; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
         CK(cudaEventRecord(h->fork_ev, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
         dsim_launch_kernel(DSIM_K_PATCH_SMALL, a, h->geom, h->stream);
+        dsim_launch_kernel(DSIM_K_PATCH_MID, a, h->geom, h->stream3);
         dsim_launch_kernel(DSIM_K_PATCH, a, h->geom, h->stream2);
         CK(cudaEventRecord(h->join_ev, h->stream2));
+        CK(cudaEventRecord(h->join3_ev, h->stream3));
         CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
         for (int k = DSIM_K_PATCH + 1; k < DSIM_K_COUNT; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
         CK(cudaStreamEndCapture(h->stream, &g));
         CK(cudaGraphInstantiate(&h->gexec[par], g, 0));
@@ -592,7 +597,9 @@ void dsim_destroy(dsim_handle *h) {
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->join_ev) cudaEventDestroy(h->join_ev);
+    if (h->join3_ev) cudaEventDestroy(h->join3_ev);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -661,8 +668,10 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     TRYCUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&h->join3_ev, cudaEventDisableTiming));
     for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
     for (auto &e : h->tev) TRYCUDA(cudaEventCreate(&e));
     TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
@@ -1597,12 +1606,17 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         /* the two patch kernels work on disjoint nodes: run them concurrently (second stream, also inside a capture) */
         CK(cudaEventRecord(h->fork_ev, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
         K(DSIM_K_PATCH_SMALL, a2);
+        dsim_launch_kernel(DSIM_K_PATCH_MID, a2, h->geom, h->stream3);
         dsim_launch_kernel(DSIM_K_PATCH, a2, h->geom, h->stream2);
+        h->k_launches[DSIM_K_PATCH_MID] += 1;
         h->k_launches[DSIM_K_PATCH] += 1;
-        h->total_launches += 1;
+        h->total_launches += 2;
         CK(cudaEventRecord(h->join_ev, h->stream2));
+        CK(cudaEventRecord(h->join3_ev, h->stream3));
         CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
         M(DSIM_MGK_HALO_PACK, a2);
         break;
     case DSIM_MG_PHASE_FINISH:

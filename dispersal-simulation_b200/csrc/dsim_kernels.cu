@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
         ctl->n_occ[a.occ_par] = 0;
         ctl->seg_cursor = 0;
         ctl->n_small = 0;
+        ctl->n_mid = 0;
         ctl->n_big = 0;
         ctl->births += n_children;
         ctl->deaths += n - n_alive;
@@ -862,6 +863,8 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         /* sparsely occupied nodes go to the thread-per-node kernel, crowded ones to the warp-per-node kernel */
         if (c <= a.small_max)
             a.sc.plist_small[atomicAdd(&ctl->n_small, 1u)] = p;
+        else if (c <= a.mid_max)
+            a.sc.plist_mid[atomicAdd(&ctl->n_mid, 1u)] = p;
         else
             a.sc.plist_big[atomicAdd(&ctl->n_big, 1u)] = p;
     }
@@ -1240,31 +1243,41 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
  * of a node are in flight together and four nodes share a warp.  The groups of a warp are independent:
  * every collective names only the lanes of its group.
  * ------------------------------------------------------------------------------------------ */
-#define PG 8u /* lanes per group = PATCH_SMALL_MAX */
+
 #ifndef PATCH_SMALL_MIN_BLOCKS
 #define PATCH_SMALL_MIN_BLOCKS 8
 #endif
+#define PATCH_MID_MAX 32 /* nodes with 9..32 families: the same kernel with a whole warp per node (k_patch_mid) */
 
-struct Grp {
+template <uint32_t PG> struct Grp { /* PG lanes per node: 8 (four nodes per warp) or 32 */
     uint32_t gl, goff, gmask;
-    __device__ __forceinline__ explicit Grp(uint32_t lane) : gl(lane % PG), goff(lane - lane % PG), gmask(((1u << PG) - 1u) << (lane - lane % PG)) {}
+    __device__ __forceinline__ explicit Grp(uint32_t lane)
+        : gl(lane % PG), goff(lane - lane % PG), gmask(PG == 32u ? 0xFFFFFFFFu : (((1u << (PG & 31u)) - 1u) << (lane - lane % PG))) {}
     template <typename T> __device__ __forceinline__ T get(T v, uint32_t src) const { return __shfl_sync(gmask, v, (int)src, (int)PG); }
-    __device__ __forceinline__ uint32_t ballot(bool pred) const { return (__ballot_sync(gmask, pred) >> goff) & ((1u << PG) - 1u); }
+    __device__ __forceinline__ uint32_t ballot(bool pred) const {
+        const uint32_t b = __ballot_sync(gmask, pred) >> goff;
+        return PG == 32u ? b : (b & ((1u << (PG & 31u)) - 1u));
+    }
+    __device__ __forceinline__ uint32_t sum(uint32_t v) const {
+#pragma unroll
+        for (uint32_t d = PG / 2u; d > 0u; d >>= 1) v += __shfl_xor_sync(gmask, v, (int)d, (int)PG);
+        return v;
+    }
 };
 
-__global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
+template <uint32_t PG>
+__device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *plist, uint32_t n_list) {
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
-    const uint32_t n_small = ctl->n_small;
     const dsim_stream rs = stream_of(a.mc);
     const double season = a.mc.season;
-    const Grp G(threadIdx.x & 31u);
+    const Grp<PG> G(threadIdx.x & 31u);
     const uint32_t gl = G.gl;
     const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / PG, ngroups = (gridDim.x * blockDim.x) / PG;
     uint32_t errors = 0;
 
-    for (uint32_t v = group; v < n_small; v += ngroups) {
-        const uint32_t p = a.sc.plist_small[v];
+    for (uint32_t v = group; v < n_list; v += ngroups) {
+        const uint32_t p = plist[v];
         const uint32_t n = a.ps.cnt[p];
         const uint32_t s0 = a.ps.seg[p];
         const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
@@ -1356,10 +1369,7 @@ __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(Ste
         uint32_t btot = 0;
         for (uint32_t B = 0; B < nb; ++B) {
             const uint32_t members = G.ballot(mine && band == B);
-            uint32_t tot = (mine && band == B) ? size : 0u;
-            tot += __shfl_xor_sync(G.gmask, tot, 4, (int)PG);
-            tot += __shfl_xor_sync(G.gmask, tot, 2, (int)PG);
-            tot += __shfl_xor_sync(G.gmask, tot, 1, (int)PG);
+            const uint32_t tot = G.sum((mine && band == B) ? size : 0u);
             const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
             uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)__popc(members));
             uint32_t m = members;
@@ -1376,7 +1386,7 @@ __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(Ste
         /* storage' (lib.rs:622-633): cultures and sizes of the surviving bands, creation order */
         const uint32_t alive_bands = G.ballot(gl < nb && btot > 0u);
         if (gl < nb && btot > 0u) {
-            const uint32_t k = (uint32_t)__popc(alive_bands & ((1u << gl) - 1u));
+            const uint32_t k = (uint32_t)__popc(alive_bands & (((1u << gl) - 1u)));
             a.ps.band_cult[s0 + k] = bcult;
             a.ps.band_size[s0 + k] = btot;
         }
@@ -1447,10 +1457,7 @@ __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(Ste
             quality = quality + (res + mx * a.mc.recovery); /* expected_harvest for the next step */
         }
         /* ---- write back ----------------------------------------------------------------------------- */
-        uint32_t pop = mine ? size : 0u;
-        pop += __shfl_xor_sync(G.gmask, pop, 4, (int)PG);
-        pop += __shfl_xor_sync(G.gmask, pop, 2, (int)PG);
-        pop += __shfl_xor_sync(G.gmask, pop, 1, (int)PG);
+        const uint32_t pop = G.sum(mine ? size : 0u);
         if (mine) {
             a.next.size[idx] = size;
             a.next.stored[idx] = stored;
@@ -1474,6 +1481,13 @@ __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(Ste
         }
     }
     if (errors) atomicOr(&ctl->errors, errors);
+}
+
+__global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
+    patch_groups<8u>(a, a.sc.plist_small, a.ctl->n_small);
+}
+__global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_mid(StepArgs a) {
+    patch_groups<32u>(a, a.sc.plist_mid, a.ctl->n_mid);
 }
 
 __global__ void k_advance(StepArgs a) {
@@ -1541,6 +1555,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
     case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
+    case DSIM_K_PATCH_MID: DSIM_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
     case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, 0, s, a); break;
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;

@@ -19,6 +19,7 @@ struct StepArgs {
     uint32_t parity;   /* index of `cur` (0/1): ctl->n_cur[parity] families */
     uint32_t occ_par;  /* occ[occ_par] / n_occ[occ_par] collect this step's occupied nodes, [occ_par ^ 1] hold last step's */
     MgInfo mg;
+    uint32_t mid_max;   /* nodes with small_max < n <= mid_max families take k_patch_mid (a warp per node) */
     uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
 };
 
@@ -37,13 +38,14 @@ enum {
     DSIM_K_SEGMENTS,
     DSIM_K_SCATTER,
     DSIM_K_PATCH_SMALL,
+    DSIM_K_PATCH_MID,
     DSIM_K_PATCH,
     DSIM_K_ADVANCE,
     DSIM_K_COUNT
 };
 
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_control", "k_move",  "k_children", "k_segments",
-                                                            "k_scatter",   "k_patch_small", "k_patch", "k_advance"};
+                                                            "k_scatter",   "k_patch_small", "k_patch_mid", "k_patch", "k_advance"};
 
 enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,
        DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH, DSIM_MGK_FINISH2 };

@@ -36,6 +36,15 @@ def test_dense_coresidence_spill_path(oracle, gpu_lib, synth):
     pc.run_lockstep(o, d, 3, hist_cap=96)
 
 
+def test_mid_sized_nodes(oracle, gpu_lib, synth):
+    """Nodes with 9..32 families (k_patch_mid: a warp per node, lane per family), hostile neighbours included."""
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 20, 24, 1500, n_occupied=80, hist_cap=96)
+    f = o.get_families(history=False, adaptation=False)
+    counts = np.unique(f.location, return_counts=True)[1]
+    assert ((counts > 8) & (counts <= 32)).sum() > 20, "scenario must exercise the 9..32 range"
+    pc.run_lockstep(o, d, 5, hist_cap=96)
+
+
 def test_prefilled_history_exact_capacity(oracle, gpu_lib, synth):
     o, d = pc.build_pair(oracle, gpu_lib, synth, 24, 30, 60, hist_fill=700)
     f = d.get_families()
