@@ -288,6 +288,11 @@ def main():
         uid = [D.mg_unique_id(lib) if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         sim.mg_init_nccl(uid[0])     # communicator + initial halo exchange
+        if os.environ.get("DSIM_MG_TRANSPORT", "peer") == "peer":
+            # the step's exchanges as remote stores over NVLink peer memory (CUDA IPC) instead of NCCL operations
+            handles = [None] * world
+            dist.all_gather_object(handles, sim.mg_ipc_export())
+            sim.mg_ipc_connect(handles)
 
     launches0 = sim.launch_count()
     barrier()

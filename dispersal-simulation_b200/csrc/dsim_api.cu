@@ -1433,7 +1433,8 @@ struct dsim_mg_state {
     ncclComm_t comm = nullptr;
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 #endif
-    bool nccl = false, graph_failed = false;
+    bool nccl = false, graph_failed = false, p2p = false;
+    std::vector<void *> ipc_opened;
     cudaEvent_t seg_ev[8] = {};
     double seg_ms[7] = {};
     uint64_t seg_steps = 0;
@@ -1531,6 +1532,7 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
         MA(mb.halo_send[s], m->halo_bytes) MA(mb.halo_recv[s], m->halo_bytes)
         MA(mb.halo_cult[s], mb.ccap)
     }
+    MA(mb.seq, 1) MA(mb.done, 4) MA(mb.flags, MG_FLAG_SPLIT0 + DSIM_MG_MAX_WORLD)
 #undef MA
     CK(cudaStreamSynchronize(h->stream));
     h->mg_enabled = true;
@@ -1679,6 +1681,67 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
 #endif
 }
 
+int dsim_mg_ipc_export(dsim_handle *h, void *out) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !out) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no peer memory in the CPU debugging build");
+#else
+    static_assert(6 * sizeof(cudaIpcMemHandle_t) == DSIM_MG_IPC_BYTES, "handle block size");
+    cudaIpcMemHandle_t *hd = reinterpret_cast<cudaIpcMemHandle_t *>(out);
+    void *bufs[6] = {m->mb.emig_recv[0], m->mb.emig_recv[1], m->mb.halo_recv[0], m->mb.halo_recv[1], m->mb.split_recv, m->mb.flags};
+    for (int k = 0; k < 6; ++k) CK(cudaIpcGetMemHandle(&hd[k], bufs[k]));
+    return DSIM_OK;
+#endif
+}
+
+int dsim_mg_ipc_connect(dsim_handle *h, const void *all) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !all) return DSIM_ERR_INVALID;
+#if defined(DSIM_EMU)
+    return fail(h, DSIM_ERR_COMM, "no peer memory in the CPU debugging build");
+#else
+    if (m->world > DSIM_MG_MAX_WORLD) return fail(h, DSIM_ERR_INVALID, "peer-memory transport: at most 8 ranks");
+    MgBuffers &mb = m->mb;
+    const cudaIpcMemHandle_t *hd = reinterpret_cast<const cudaIpcMemHandle_t *>(all);
+    auto open = [&](uint32_t rank, int k, void **out) -> int {
+        CK(cudaIpcOpenMemHandle(out, hd[rank * 6 + k], cudaIpcMemLazyEnablePeerAccess));
+        m->ipc_opened.push_back(*out);
+        return DSIM_OK;
+    };
+    int rc;
+    for (uint32_t r = 0; r < m->world; ++r) {
+        if (r == m->rank) {
+            mb.peer_split_recv[r] = mb.split_recv;
+            mb.peer_flags[r] = mb.flags;
+            continue;
+        }
+        void *p = nullptr;
+        if ((rc = open(r, 4, &p))) return rc;
+        mb.peer_split_recv[r] = (uint64_t *)p;
+        if ((rc = open(r, 5, &p))) return rc;
+        mb.peer_flags[r] = (uint32_t *)p;
+    }
+    for (int s = 0; s < 2; ++s) {
+        if (!mb.has_peer[s]) continue;
+        const uint32_t r = s == 0 ? m->rank - 1u : m->rank + 1u;
+        void *p = nullptr; /* my lower neighbour receives from me in its UPPER-side buffers (index 1), and vice versa */
+        if ((rc = open(r, 0 + (1 - s), &p))) return rc;
+        mb.peer_emig_recv[s] = (unsigned char *)p;
+        if ((rc = open(r, 2 + (1 - s), &p))) return rc;
+        mb.peer_halo_recv[s] = (unsigned char *)p;
+    }
+    mb.p2p = 1u;
+    m->p2p = true;
+    for (int k = 0; k < 2; ++k) /* the captured steps used NCCL */
+        if (m->gexec[k]) {
+            cudaGraphExecDestroy(m->gexec[k]);
+            m->gexec[k] = nullptr;
+        }
+    return DSIM_OK;
+#endif
+}
+
 #if !defined(DSIM_EMU)
 #define NCK(call)                                                                         \
     do {                                                                                  \
@@ -1693,6 +1756,16 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
 static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel, cudaStream_t stream = nullptr) {
     const MgBuffers &mb = m->mb;
     if (stream == nullptr) stream = h->stream;
+    if (m->p2p) { /* remote stores into the neighbours' buffers + flag, then wait for the neighbours' flags */
+        const StepArgs a = mg_args(h, false);
+        static const int push[3] = {DSIM_MGK_PUSH_SPLIT, DSIM_MGK_PUSH_EMIG, DSIM_MGK_PUSH_HALO};
+        static const int wait[3] = {DSIM_MGK_WAIT_SPLIT, DSIM_MGK_WAIT_EMIG, DSIM_MGK_WAIT_HALO};
+        dsim_mg_launch(push[channel], a, mb, h->geom, stream);
+        dsim_mg_launch(wait[channel], a, mb, h->geom, stream);
+        h->total_launches += 2;
+        CK(cudaGetLastError());
+        return DSIM_OK;
+    }
     if (channel == DSIM_MG_CH_SPLIT) {
         NCK(ncclAllGather(mb.split_send, mb.split_recv, 1 + (size_t)mb.scap, ncclUint64, m->comm, stream));
         return DSIM_OK;
@@ -1820,7 +1893,11 @@ int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set
     if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport");
     int rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_PACK))) return rc;
-    if ((rc = mg_exchange(h, m, DSIM_MG_CH_HALO))) return rc;
+    const bool p2p = m->p2p; /* outside the steps there is no exchange round: always NCCL */
+    m->p2p = false;
+    rc = mg_exchange(h, m, DSIM_MG_CH_HALO);
+    m->p2p = p2p;
+    if (rc) return rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
@@ -1869,6 +1946,7 @@ void dsim_mg_release(dsim_handle *h) {
     for (auto &g : m->gexec)
         if (g) cudaGraphExecDestroy(g);
     if (m->comm) ncclCommDestroy(m->comm);
+    for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
 #endif
     free_list(m->allocs);
     g_mg.erase(h);

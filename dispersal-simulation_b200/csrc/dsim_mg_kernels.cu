@@ -33,7 +33,10 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         else
             atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) mb.split_send[0] = ctl->n_children;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        mb.split_send[0] = ctl->n_children;
+        if (mb.p2p) *mb.seq += 1u; /* the exchange round of this step (first kernel of the step that knows the transport) */
+    }
 }
 
 /* global rank of every local child = number of splitting parents, on any rank, with a smaller id.
@@ -290,6 +293,98 @@ __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb
     }
 }
 
+/* ---- peer-memory transport ------------------------------------------------------------------------------------
+ * k_mg_push copies the USED part of a send buffer into the neighbour's receive buffer with 16-byte remote stores
+ * (NVLink peer memory, mapped through CUDA IPC), then the last block to finish publishes the round number in the
+ * neighbour's flag word; k_mg_wait spins on this rank's flag words until the round has arrived.  Buffers need no
+ * double buffering: a rank cannot start the push of round r+1 on a channel before its neighbour has consumed round
+ * r (it first has to receive that neighbour's later messages of round r). */
+#if defined(DSIM_EMU)
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
+__device__ __forceinline__ void fence_sys() {}
+__device__ __forceinline__ void backoff() {}
+#else
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
+__device__ __forceinline__ void backoff() { __nanosleep(100); }
+#endif
+
+__device__ __forceinline__ void copy16(unsigned char *dst, const unsigned char *src, uint64_t bytes) { /* bytes: a multiple of 16 */
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < bytes / 16u; k += (uint64_t)gridDim.x * blockDim.x) d[k] = s[k];
+}
+
+__global__ void __launch_bounds__(256) k_mg_push(StepArgs a, MgBuffers mb, int channel) {
+    const uint32_t round = *mb.seq;
+    if (channel == DSIM_MG_CH_SPLIT) {
+        const uint64_t words = 1u + mb.split_send[0]; /* count, ids: 8-byte words (a rank's slot is only 8-byte aligned) */
+        for (uint32_t r = 0; r < a.mg.world; ++r) {
+            uint64_t *dst = mb.peer_split_recv[r] + (size_t)a.mg.rank * (1 + (size_t)mb.scap);
+            for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (uint64_t)gridDim.x * blockDim.x) dst[k] = mb.split_send[k];
+        }
+    } else {
+        for (uint32_t side = 0; side < 2u; ++side) {
+            if (!mb.has_peer[side]) continue;
+            if (channel == DSIM_MG_CH_EMIGRANTS) {
+                const uint64_t m = *reinterpret_cast<const uint64_t *>(mb.emig_send[side]);
+                copy16(mb.peer_emig_recv[side], mb.emig_send[side], 16u + m * mb.rec_bytes); /* rec_bytes is a multiple of 16 */
+            } else {
+                uint32_t nc = mb.counters[MG_HALO_CULT0 + side];
+                if (nc > mb.ccap) nc = mb.ccap;
+                const uint64_t bytes = (16u + (uint64_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)) + (uint64_t)nc * 8u + 15u) & ~(uint64_t)15u;
+                copy16(mb.peer_halo_recv[side], mb.halo_send[side], bytes);
+            }
+        }
+    }
+    /* the last block to get here publishes the round in the receivers' flag words */
+    fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&mb.done[channel], 1u);
+        if (prev == gridDim.x - 1u) {
+            mb.done[channel] = 0u;
+            fence_sys();
+            if (channel == DSIM_MG_CH_SPLIT) {
+                for (uint32_t r = 0; r < a.mg.world; ++r) st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + a.mg.rank, round);
+            } else {
+                const uint32_t slot0 = channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0;
+                /* what I send to my lower neighbour (side 0) arrives from ITS upper side (slot 1), and vice versa */
+                if (mb.has_peer[0]) st_release_sys(mb.peer_flags[a.mg.rank - 1u] + slot0 + 1u, round);
+                if (mb.has_peer[1]) st_release_sys(mb.peer_flags[a.mg.rank + 1u] + slot0 + 0u, round);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_mg_wait(StepArgs a, MgBuffers mb, int channel) {
+    const uint32_t round = *mb.seq;
+    uint32_t slot = 0xFFFFFFFFu;
+    if (channel == DSIM_MG_CH_SPLIT) {
+        if (threadIdx.x < a.mg.world) slot = MG_FLAG_SPLIT0 + threadIdx.x;
+    } else if (threadIdx.x < 2u && mb.has_peer[threadIdx.x]) {
+        slot = (channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0) + threadIdx.x;
+    }
+    if (slot != 0xFFFFFFFFu) {
+        uint32_t spins = 0;
+        /* rounds only grow; a neighbour that is a step ahead may already have published the next one */
+        while ((int32_t)(ld_acquire_sys(mb.flags + slot) - round) < 0) {
+            backoff();
+            if (++spins > (1u << 25)) { /* several seconds: the neighbour is gone; flag it instead of hanging the device */
+                atomicOr(&a.ctl->errors, (uint32_t)DSIM_MODEL_COMM_TIMEOUT);
+                break;
+            }
+        }
+    }
+    fence_sys();
+}
+
 /* ---- end of step ------------------------------------------------------------------------------ */
 __global__ void k_mg_finish(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
@@ -329,6 +424,12 @@ void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const Lau
     case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm * 2, 256, 0, s, a, mb); break;
     case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, sm, 256, 0, s, a, mb); break;
     case DSIM_MGK_FINISH2: DSIM_LAUNCH(k_mg_finish2, 1, 32, 0, s, a, mb); break;
+    case DSIM_MGK_PUSH_SPLIT: DSIM_LAUNCH(k_mg_push, 8, 256, 0, s, a, mb, (int)DSIM_MG_CH_SPLIT); break;
+    case DSIM_MGK_PUSH_EMIG: DSIM_LAUNCH(k_mg_push, sm, 256, 0, s, a, mb, (int)DSIM_MG_CH_EMIGRANTS); break;
+    case DSIM_MGK_PUSH_HALO: DSIM_LAUNCH(k_mg_push, 32, 256, 0, s, a, mb, (int)DSIM_MG_CH_HALO); break;
+    case DSIM_MGK_WAIT_SPLIT: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_SPLIT); break;
+    case DSIM_MGK_WAIT_EMIG: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_EMIGRANTS); break;
+    case DSIM_MGK_WAIT_HALO: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_HALO); break;
     default: break;
     }
 }

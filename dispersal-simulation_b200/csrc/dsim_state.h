@@ -166,6 +166,7 @@ struct MgInfo {              /* part of StepArgs */
 };
 
 enum { MG_N_STAY = 0, MG_N_EMIG0, MG_N_EMIG1, MG_N_IMMIG, MG_N_FREED, MG_HALO_CULT0, MG_HALO_CULT1, MG_MAX_EMIG /* high-water mark of emigrants per side and step */, MG_N_COUNTERS = 8 };
+#define DSIM_MG_MAX_WORLD 8u
 #define MG_REC_HDR 72u /* emigrant record: 5 x u64 + 8 x u32, then adaptation slots, then history */
 #if defined(__CUDACC__)
 #define DSIM_HD_INLINE __host__ __device__ inline
@@ -190,6 +191,17 @@ struct MgBuffers {           /* device buffers of one rank; messages have a 16-b
     uint64_t *halo_cult[2];  /* [ccap]                                                                 */
     uint32_t has_peer[2];
     uint32_t scap, ecap, rec_bytes, hw, ccap;
+    /* peer-memory transport (dsim_mg_ipc_connect): the exchanges are remote stores over NVLink into the neighbours'
+     * receive buffers followed by a flag, instead of NCCL operations */
+    uint32_t p2p;
+    uint32_t *seq;                      /* [1] exchange round of this rank, bumped at the start of every step        */
+    uint32_t *done;                     /* [3] blocks of a push kernel that have finished, per channel               */
+    uint32_t *flags;                    /* [MG_FLAG_SPLIT0 + world] round of the last complete message per source     */
+    unsigned char *peer_emig_recv[2];   /* side s: the receive buffer of that neighbour that faces me                 */
+    unsigned char *peer_halo_recv[2];
+    uint64_t *peer_split_recv[DSIM_MG_MAX_WORLD]; /* rank r's split_recv                                               */
+    uint32_t *peer_flags[DSIM_MG_MAX_WORLD];
 };
+enum { MG_FLAG_EMIG0 = 0, MG_FLAG_HALO0 = 2, MG_FLAG_SPLIT0 = 4 };
 
 #endif

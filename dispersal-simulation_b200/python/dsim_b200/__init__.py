@@ -25,6 +25,7 @@ SYNTH_LIB_PATH = os.path.join(PKG_ROOT, "libdsim_synth.so")
 N_ECOREGIONS = 304
 OPT_PATCH_WARP_ONLY = 0x2
 NO_PARENT = 2**64 - 1
+MG_IPC_BYTES = 384
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
@@ -285,6 +286,8 @@ class Sim:
             "mg_memcpy": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_uint64]),
             "mg_unique_id": (C.c_int, [C.c_void_p]),
             "mg_init_nccl": (C.c_int, [vp, C.c_void_p]),
+            "mg_ipc_export": (C.c_int, [vp, C.c_void_p]),
+            "mg_ipc_connect": (C.c_int, [vp, C.c_void_p]),
             "mg_halo_sync": (C.c_int, [vp]),
             "mg_reduce_stats": (C.c_int, [vp, C.POINTER(StepStats)]),
         }.items():
@@ -442,6 +445,18 @@ class Sim:
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self._f("mg_init_nccl")(self.h, buf))
         self._check(self._f("mg_halo_sync")(self.h))
+
+    def mg_ipc_export(self) -> bytes:
+        """CUDA IPC handles of this rank's receive buffers (peer-memory transport, include/dsim.h)."""
+        buf = C.create_string_buffer(MG_IPC_BYTES)
+        self._check(self._f("mg_ipc_export")(self.h, buf))
+        return buf.raw
+
+    def mg_ipc_connect(self, handles_of_all_ranks):
+        """`handles_of_all_ranks[r]` = mg_ipc_export() of rank r; from now on the steps exchange through peer memory."""
+        blob = b"".join(handles_of_all_ranks)
+        assert len(blob) == MG_IPC_BYTES * len(handles_of_all_ranks)
+        self._check(self._f("mg_ipc_connect")(self.h, C.create_string_buffer(blob, len(blob))))
 
     def mg_reduce_stats(self, st: "StepStats"):
         self._check(self._f("mg_reduce_stats")(self.h, C.byref(st)))

@@ -52,6 +52,7 @@ typedef enum dsim_status {
 #define DSIM_MODEL_ADAPTATION_OVERFLOW   0x10u /* more live adaptation entries than slots (not reachable
                                                   from states whose adaptation values are <= 1)        */
 #define DSIM_MODEL_CAPACITY              0x20u /* family capacity exceeded inside a batch of steps     */
+#define DSIM_MODEL_COMM_TIMEOUT          0x40u /* multi-GPU, peer-memory transport: a neighbour's message did not arrive */
 
 /* Mirrors `Parameters` (parameters.rs:5-20) minus the graph, which is passed separately.
  * Defaults: parameters.rs:22-54, filled in by dsim_default_params. */
@@ -219,6 +220,13 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes); 
 #define DSIM_MG_UNIQUE_ID_BYTES 128
 int dsim_mg_unique_id(void *out /* DSIM_MG_UNIQUE_ID_BYTES, rank 0 creates and broadcasts it */);
 int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
+/* Peer-memory transport (optional, after dsim_mg_init_nccl, all ranks on one NVLink node, one process per GPU): every
+ * rank exports CUDA IPC handles of its receive buffers (DSIM_MG_IPC_BYTES), the caller gathers them from all ranks
+ * (rank-major) and hands them back; from then on dsim_mg_step_enqueue replaces the three NCCL exchanges of a step by
+ * remote stores into the neighbours' buffers plus a flag (k_mg_push / k_mg_wait).  Results are unchanged. */
+#define DSIM_MG_IPC_BYTES 384 /* 6 handles of 64 bytes */
+int dsim_mg_ipc_export(dsim_handle *h, void *out /* DSIM_MG_IPC_BYTES */);
+int dsim_mg_ipc_connect(dsim_handle *h, const void *all /* world x DSIM_MG_IPC_BYTES */);
 /* Sums the per-rank counters of a dsim_step_stats over all ranks (NCCL transport only). */
 int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
 /* Diagnostics: internal per-step counters; out8[7] = most emigrants per neighbour and step seen so far. */

@@ -41,6 +41,12 @@ sim = make(local, True)
 uid = [D.mg_unique_id(lib) if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 sim.mg_init_nccl(uid[0])
+if os.environ.get("DSIM_MG_TRANSPORT", "peer") == "peer":
+    handles = [None] * world
+    dist.all_gather_object(handles, sim.mg_ipc_export())
+    sim.mg_ipc_connect(handles)
+    if rank == 0:
+        print("[mg check] transport: peer memory (CUDA IPC over NVLink)")
 st = sim.step(STEPS, allow_model_errors=True)
 tot = sim.mg_reduce_stats(D.StepStats.from_buffer_copy(st))
 f = sim.get_families()
