@@ -703,12 +703,10 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         uint16_t *hash;
         uint32_t *dst, *near_off, *near_dst;
         double *cost;
-        uint16_t *nidx;
         static_assert(sizeof(RowHdr) == sizeof(HostRowHdr), "row header layouts must agree");
         TRY(dev_alloc(h, &hdr, hr.hdr.size(), h->allocs, false));
         TRY(dev_alloc(h, &dst, hr.dst.size() + 8, h->allocs, false));
         TRY(dev_alloc(h, &cost, hr.cost.size() + 8, h->allocs, false));
-        TRY(dev_alloc(h, &nidx, hr.nidx.size() + 8, h->allocs, false));
         TRY(dev_alloc(h, &hash, hr.hash.size(), h->allocs, false));
         TRY(upload(h, hash, hr.hash.data(), hr.hash.size()));
         TRY(dev_alloc(h, &near_off, hr.near_off.size(), h->allocs, false));
@@ -716,12 +714,11 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         TRY(upload(h, (HostRowHdr *)hdr, hr.hdr.data(), hr.hdr.size()));
         TRY(upload(h, dst, hr.dst.data(), hr.dst.size()));
         TRY(upload(h, cost, hr.cost.data(), hr.cost.size()));
-        TRY(upload(h, nidx, hr.nidx.data(), hr.nidx.size()));
         TRY(upload(h, near_off, hr.near_off.data(), hr.near_off.size()));
         TRY(upload(h, near_dst, hr.near_dst.data(), hr.near_dst.size()));
         TRYCUDA(cudaStreamSynchronize(h->stream));
         h->rt.hash = hash;
-        h->rt.hdr = hdr; h->rt.dst = dst; h->rt.cost = cost; h->rt.nidx = nidx;
+        h->rt.hdr = hdr; h->rt.dst = dst; h->rt.cost = cost;
         h->rt.near_off = near_off; h->rt.near_dst = near_dst;
     }
     /* patches */

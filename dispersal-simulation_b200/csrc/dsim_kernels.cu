@@ -309,7 +309,6 @@ __device__ __forceinline__ bool mem_keep(const ModelConst &mc, uint32_t step, ui
 struct RowPtr { /* a reach row in place (HBM / L1) */
     const uint32_t *dst;
     const double *cost;
-    const uint16_t *nidx;
     const uint16_t *hash; /* the row's 32 x 8 bucket index, or nullptr for rows longer than DSIM_ROW_HASH_MAX */
     uint32_t len, n_sensed;
 };
@@ -318,7 +317,6 @@ __device__ __forceinline__ RowPtr row_of(const ReachTable &rt, uint32_t node, co
     RowPtr row;
     row.dst = rt.dst + hd.start;
     row.cost = rt.cost + hd.start;
-    row.nidx = rt.nidx + hd.start;
     row.hash = hd.len <= DSIM_ROW_HASH_MAX ? rt.hash + (size_t)node * 256u : nullptr;
     row.len = hd.len;
     row.n_sensed = hd.n_sensed;

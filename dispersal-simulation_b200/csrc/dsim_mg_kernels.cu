@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
 
 /* one warp per emigrant: record + adaptation slots + history (chronological) into the send buffer */
 __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
-    DevCtl *ctl = a.ctl;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;

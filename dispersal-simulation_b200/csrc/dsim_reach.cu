@@ -141,7 +141,6 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
     struct Chunk {
         std::vector<uint32_t> r_len, n_len, r_dst, n_dst, r_sensed;
         std::vector<double> r_cost;
-        std::vector<uint16_t> r_nidx;
     };
     std::vector<Chunk> chunks(n_chunks);
     int failed = 0;
@@ -174,7 +173,6 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
                         if (sensed != (pass == 0)) continue;
                         ch.r_dst.push_back(qc.first);
                         ch.r_cost.push_back(qc.second);
-                        ch.r_nidx.push_back(sensed ? (uint16_t)(it - near.begin()) : (uint16_t)0xFFFFu);
                         n_sensed += sensed ? 1u : 0u;
                     }
                 ch.r_sensed.push_back(n_sensed);
@@ -209,7 +207,6 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
     out->n_reach = n_reach;
     out->dst.assign(ro, 0xFFFFFFFFu);
     out->cost.assign(ro, std::numeric_limits<double>::infinity());
-    out->nidx.assign(ro, (uint16_t)0xFFFFu);
     out->near_dst.assign(no, 0);
 #pragma omp parallel for schedule(dynamic, 1)
     for (long c = 0; c < (long)n_chunks; ++c) {
@@ -219,7 +216,6 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
         for (size_t k = 0; k < ch.r_len.size(); ++k) {
             std::copy(ch.r_dst.begin() + rp, ch.r_dst.begin() + rp + ch.r_len[k], out->dst.begin() + out->hdr[v0 + k].start);
             std::copy(ch.r_cost.begin() + rp, ch.r_cost.begin() + rp + ch.r_len[k], out->cost.begin() + out->hdr[v0 + k].start);
-            std::copy(ch.r_nidx.begin() + rp, ch.r_nidx.begin() + rp + ch.r_len[k], out->nidx.begin() + out->hdr[v0 + k].start);
             std::copy(ch.n_dst.begin() + np, ch.n_dst.begin() + np + ch.n_len[k], out->near_dst.begin() + out->near_off[v0 + k]);
             rp += ch.r_len[k];
             np += ch.n_len[k];

@@ -18,7 +18,6 @@ struct HostReach {
     std::vector<HostRowHdr> hdr;    /* [n] rows padded to multiples of 8 entries */
     std::vector<uint32_t> dst;      /* [sensed, ascending][others, ascending][padding 0xFFFFFFFF] */
     std::vector<double> cost;       /* OYR; padding +inf                             */
-    std::vector<uint16_t> nidx;     /* sensed entries: position in the node's nearby list; others 0xFFFF */
     std::vector<uint16_t> hash;     /* [n * 256] bucketized index of each row (rows of <= 192 entries), see dsim_state.h */
     std::vector<uint32_t> near_off; /* [n+1] */
     std::vector<uint32_t> near_dst; /* ascending within a node */

@@ -84,7 +84,6 @@ struct ReachTable {          /* replaces bounded_dijkstra per family per step (l
     /* row = [sensed entries, ascending dst][other reachable nodes, ascending dst][padding 0xFFFFFFFF] */
     const uint32_t *dst;
     const double *cost;      /* OYR                                                                */
-    const uint16_t *nidx;    /* sensed entries: index in the node's nearby list                    */
     const uint16_t *hash;    /* [P * 256] per-row index for rows of at most DSIM_ROW_HASH_MAX entries (longer rows are
                                 binary-searched): 32 buckets x 8 slots, bucket = hash bits 8..12, slot = tag (hash
                                 bits 0..7) << 8 | entry position, 0xFFFF = empty; one 16-byte load reads a bucket  */
