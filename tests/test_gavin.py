@@ -1,0 +1,74 @@
+"""gavin2017processbased: the oracle against the reference's own functions (golden vectors made
+by tests/golden/make_gavin_golden.py from supplement/gavin2017processbased/language.py), its invariants, and the
+batched CUDA path against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+import gavin as G  # noqa: E402  (test infrastructure)
+
+GOLD = np.load(os.path.join(REPO, "tests", "golden", "gavin_functions.npz"))
+
+
+def test_dhondt_matches_reference():
+    for k in range(len(GOLD["seats"])):
+        v = GOLD["votes"][k]
+        n = int(np.sum(~np.isnan(v)))
+        assert G.dhondt(float(GOLD["seats"][k]), [float(x) for x in v[:n]]) == GOLD["dhondt"][k, :n].tolist(), k
+
+
+def test_distribute_matches_reference():
+    for k in range(len(GOLD["growth"])):
+        pc = GOLD["popcap"][k]
+        n = int(np.sum(~np.isnan(pc)))
+        space = [float(pc[i]) - int(GOLD["population"][k, i]) for i in range(n)]
+        keys = sorted((int(GOLD["keys"][k, i]), i) for i in range(1, n))
+        order = [0] + [i for _, i in keys]
+        got, left = G.distribute(float(GOLD["growth"][k]), space, order)
+        want = [(int(i), int(GOLD["got"][k, i])) for i in GOLD["visit"][k] if i >= 0]
+        assert got == want, (k, got, want)          # values AND the insertion order of the reference's Counter
+        assert left == GOLD["left"][k], k
+
+
+def test_philox_kat():
+    # Random123 known-answer vector for Philox4x32-10 (same generator as the dispersal model's streams)
+    assert G.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF)) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert G.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+
+
+def small_member(seed=5, R=10, C=12, alpha=10 ** -8.07, beta=2.64, gf=1.1):
+    P = G.synthetic_precipitation(R, C)
+    return G.Member(R, C, G.population_capacity(P, alpha, beta), gf, seed, G.synthetic_lang_caps())
+
+
+def test_oracle_invariants():
+    m = small_member()
+    n_lang = m.run()
+    assert n_lang >= 3
+    owned = m.language != 0
+    assert (m.population[~owned] == 0).all() and (m.population[owned] >= 1).all()
+    assert (m.popcap[owned] >= 1).all(), "only cells that can hold an individual are settled (model.py:262, 346-349)"
+    assert set(np.unique(m.language[owned])) == set(range(1, n_lang + 1))
+    # the run ended because no free neighbour is left (model.py:364-366)
+    for c in np.flatnonzero(owned):
+        for q in m.neighbors(int(c), m.language[c]):
+            assert owned[q] or m.popcap[q] <= 0
+    # every language is connected through its own cells
+    for lid in range(1, n_lang + 1):
+        cells = set(np.flatnonzero(m.language == lid).tolist())
+        seen, todo = set(), [next(iter(cells))]
+        while todo:
+            c = todo.pop()
+            if c in seen:
+                continue
+            seen.add(c)
+            todo += [int(q) for q in m.nb[c] if int(q) in cells]
+        assert seen == cells, lid
+    # determinism
+    m2 = small_member()
+    m2.run()
+    assert (m2.language == m.language).all() and (m2.population == m.population).all()
