@@ -327,7 +327,7 @@ __device__ __forceinline__ uint32_t row_hash(uint32_t q) { return (q * 265443576
 
 /* position of node q in the row, or 0xFFFFFFFF (replaces travel_costs.get(), lib.rs:869), by binary search in
  * the two sorted segments of the row */
-__device__ __noinline__ uint32_t row_find_sorted(const uint32_t *dst, uint32_t n_sensed, uint32_t len, uint32_t q) {
+__device__ DSIM_NOINLINE uint32_t row_find_sorted(const uint32_t *dst, uint32_t n_sensed, uint32_t len, uint32_t q) {
     uint32_t k = lower_bound_u32(dst, 0u, n_sensed, q);
     if (k < n_sensed && dst[k] == q) return k;
     k = lower_bound_u32(dst, n_sensed, len, q);

@@ -19,6 +19,12 @@
 #define DSIM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+#if defined(DSIM_EMU)
+#define DSIM_NOINLINE __attribute__((noinline))
+#else
+#define DSIM_NOINLINE __noinline__
+#endif
+
 #define DSIM_FULL 0xffffffffu
 
 #endif

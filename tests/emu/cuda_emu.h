@@ -27,7 +27,6 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)

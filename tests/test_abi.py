@@ -25,6 +25,30 @@ def test_product_library_exports_dsim_h():
     assert lib.dsim_abi_version() == 1
 
 
+def test_product_library_exports_gavin_h():
+    lib = C.CDLL(D.LIB_PATH)
+    names = _declared("gavin.h", "gavin_")
+    assert names == ["gavin_last_error", "gavin_run"]
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_gavin_without_device_fails_loudly():
+    """The batched gavin2017 model has no CPU fallback either: without a GPU gavin_run refuses."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import numpy as np
+    from dsim_b200 import gavin as GB
+    lib = C.CDLL(D.LIB_PATH)
+    with pytest.raises(RuntimeError) as e:
+        GB.run_sweep(lib, 4, 4, np.full((1, 32), 5.0), np.array([1.1]), np.array([1], np.uint64), np.array([100.0]))
+    assert "-2" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
 def test_synth_library_exports_dsim_synth_h(synth):
     for n in _declared("dsim_synth.h", "dsim_synth_"):
         assert hasattr(synth, n), n

@@ -72,3 +72,60 @@ def test_oracle_invariants():
     m2 = small_member()
     m2.run()
     assert (m2.language == m.language).all() and (m2.population == m.population).all()
+
+
+# ---- the batched CUDA path against the oracle --------------------------------------------------------------------
+def _sweep_case(S=6, R=8, C=10):
+    sys.path.insert(0, os.path.join(REPO, "dispersal-simulation_b200", "python"))
+    from dsim_b200 import gavin as GB
+    P = G.synthetic_precipitation(R, C)
+    alpha = 10 ** np.linspace(-8.3, -7.8, S)[:, None]
+    beta = np.linspace(2.5, 2.75, S)[:, None]
+    popcap = GB.population_capacity(P[None, :], alpha, beta)
+    assert (popcap == G.population_capacity(P[None, :], alpha, beta)).all()
+    gf = np.linspace(1.05, 1.3, S)
+    seed = np.arange(S, dtype=np.uint64) * 7919 + 11
+    return GB, R, C, popcap, gf, seed, G.synthetic_lang_caps()
+
+
+def _check_sweep(lib):
+    GB, R, C, popcap, gf, seed, caps = _sweep_case()
+    got = GB.run_sweep(lib, R, C, popcap, gf, seed, caps)
+    calls = cells = 0
+    for k in range(len(gf)):
+        m = G.Member(R, C, popcap[k], gf[k], int(seed[k]), caps)
+        n_lang = m.run()
+        assert got.n_languages[k] == n_lang, (k, got.n_languages[k], n_lang)
+        assert (got.language[k] == m.language).all(), f"member {k}: language map"
+        assert (got.population[k] == m.population).all(), f"member {k}: populations"
+        calls += m.grow_calls
+    assert got.grow_calls == calls
+    assert len(set(got.n_languages.tolist())) > 1, "the sweep members must differ"
+    # a capped run: stop after three languages
+    got3 = GB.run_sweep(lib, R, C, popcap[:2], gf[:2], seed[:2], caps, max_languages=3)
+    for k in range(2):
+        m = G.Member(R, C, popcap[k], gf[k], int(seed[k]), caps, max_languages=3)
+        m.run()
+        assert (got3.language[k] == m.language).all() and (got3.population[k] == m.population).all()
+
+
+def test_sweep_matches_oracle_emu():
+    import helpers
+    _check_sweep(helpers.load_emu())
+
+
+@pytest.mark.gpu
+def test_sweep_matches_oracle_gpu():
+    import helpers
+    _check_sweep(helpers.D.load())
+
+
+@pytest.mark.gpu
+def test_sweep_members_are_independent_gpu():
+    """A member's result does not depend on the other members of the batch (one warp each, no shared state)."""
+    import helpers
+    GB, R, C, popcap, gf, seed, caps = _sweep_case(S=40, R=12, C=12)
+    lib = helpers.D.load()
+    whole = GB.run_sweep(lib, R, C, popcap, gf, seed, caps)
+    part = GB.run_sweep(lib, R, C, popcap[17:23], gf[17:23], seed[17:23], caps)
+    assert (whole.language[17:23] == part.language).all() and (whole.population[17:23] == part.population).all()
