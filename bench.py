@@ -42,6 +42,7 @@ CONFIGS = {
     "c4": (2582, 3873, 10_000_000, 1_250_000, 64),  # stress: dense co-residence
     # diagnostics (not bench lines): the C2 population with short histories on the continental grid and on a grid
     # whose reach table fits in L2 -- separates memory-system effects from instruction effects in k_move
+    "x_800k": (1155, 1732, 800_000, 0, 625),          # the population of the 8-GPU weak-scaling run, on one GPU
     "x_big_h64": (1155, 1732, 100_000, 0, 64),
     "x_small_h64": (120, 180, 100_000, 0, 64),
 }

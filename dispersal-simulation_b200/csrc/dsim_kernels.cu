@@ -31,11 +31,15 @@
 #include <cstring>
 
 #define LIFE_BLOCK 256
-#define PATCH_WARPS 4
-#ifndef PATCH_MIN_BLOCKS
-#define PATCH_MIN_BLOCKS 8
+#ifndef PATCH_WARPS
+#define PATCH_WARPS 1 /* k_patch: one warp per block */
 #endif
-#define PATCH_M 64 /* families per node handled in shared memory; larger nodes spill to HBM scratch */
+#ifndef PATCH_MIN_BLOCKS
+#define PATCH_MIN_BLOCKS 4
+#endif
+#ifndef PATCH_M
+#define PATCH_M 512u /* families per node handled in shared memory (54 KB); larger nodes spill to HBM scratch */
+#endif
 #define PATCH_SMALL_MAX 8 /* nodes with at most this many families are handled by a group of 8 lanes each */
 
 __device__ __forceinline__ dsim_stream stream_of(const ModelConst &mc) {
@@ -1189,16 +1193,22 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     __syncwarp();
 }
 
+/* shared-memory working set of one node of up to PATCH_M families: 105 bytes per family */
+#define PATCH_SMEM_BYTES (PATCH_M * (6u * 4u + 5u * 8u + 5u * 8u + 1u))
+
 __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(StepArgs a) {
-    __shared__ uint32_t s_u32[PATCH_WARPS][6][PATCH_M];
-    __shared__ uint64_t s_u64[PATCH_WARPS][5][PATCH_M];
-    __shared__ double s_f64[PATCH_WARPS][5][PATCH_M];
-    __shared__ uint8_t s_u8[PATCH_WARPS][PATCH_M];
+    /* one warp per block: crowded nodes are few, and a node of hundreds of families walks its member arrays n times
+     * (every newcomer meets every member, lib.rs:1380-1399) — from shared memory, not from HBM scratch */
+    DSIM_DYN_SMEM(smem_raw);
+    uint64_t *const s_u64 = reinterpret_cast<uint64_t *>(smem_raw);
+    double *const s_f64 = reinterpret_cast<double *>(smem_raw + 5u * 8u * PATCH_M);
+    uint32_t *const s_u32 = reinterpret_cast<uint32_t *>(smem_raw + 10u * 8u * PATCH_M);
+    uint8_t *const s_u8 = smem_raw + 10u * 8u * PATCH_M + 6u * 4u * PATCH_M;
 
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * PATCH_WARPS + wib, nwarps = gridDim.x * PATCH_WARPS;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gwarp = blockIdx.x, nwarps = gridDim.x;
     const uint32_t n_big = ctl->n_big;
     const dsim_stream rs = stream_of(a.mc);
     const double season = a.mc.season;
@@ -1210,13 +1220,13 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
         const uint32_t s0 = a.ps.seg[p];
         PatchMem M;
         if (n <= PATCH_M) {
-            M.idx = s_u32[wib][0]; M.tidx = s_u32[wib][1]; M.size = s_u32[wib][2]; M.band = s_u32[wib][3];
-            M.bcnt = s_u32[wib][4]; M.btot = s_u32[wib][5];
-            M.key = s_u64[wib][0]; M.fid = s_u64[wib][1]; M.tfid = s_u64[wib][2]; M.cult = s_u64[wib][3];
-            M.bcult = s_u64[wib][4];
-            M.stored = s_f64[wib][0]; M.contrib = s_f64[wib][1]; M.lh = s_f64[wib][2]; M.beff = s_f64[wib][3];
-            M.bcoef = s_f64[wib][4];
-            M.balive = s_u8[wib];
+            M.idx = s_u32; M.tidx = s_u32 + PATCH_M; M.size = s_u32 + 2u * PATCH_M; M.band = s_u32 + 3u * PATCH_M;
+            M.bcnt = s_u32 + 4u * PATCH_M; M.btot = s_u32 + 5u * PATCH_M;
+            M.key = s_u64; M.fid = s_u64 + PATCH_M; M.tfid = s_u64 + 2u * PATCH_M; M.cult = s_u64 + 3u * PATCH_M;
+            M.bcult = s_u64 + 4u * PATCH_M;
+            M.stored = s_f64; M.contrib = s_f64 + PATCH_M; M.lh = s_f64 + 2u * PATCH_M; M.beff = s_f64 + 3u * PATCH_M;
+            M.bcoef = s_f64 + 4u * PATCH_M;
+            M.balive = s_u8;
             patch_node(a, M, p, n, s0, lane, step, rs, season, errors);
         } else {
             M.idx = a.sc.x_idx + s0; M.tidx = a.sc.x_tidx + s0; M.size = a.sc.x_size + s0; M.band = a.sc.x_band + s0;
@@ -1554,7 +1564,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
     case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
     case DSIM_K_PATCH_MID: DSIM_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
-    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, 0, s, a); break;
+    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, PATCH_SMEM_BYTES, s, a); break;
     case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
     default: break;
     }
@@ -1577,5 +1587,9 @@ void dsim_launch_census(const PatchState &ps, const FamCore &f, uint32_t n, uint
 
 int dsim_configure_kernels(LaunchGeom *g) {
     (void)g;
+#if !defined(DSIM_EMU)
+    cudaError_t e = cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+#endif
     return 0;
 }

@@ -33,10 +33,19 @@ def test_growth_and_splits(oracle, emu, synth):
 
 
 def test_dense_coresidence_spill_path(oracle, emu, synth):
-    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2500, n_occupied=6, hist_cap=96)
+    """Nodes with more families than k_patch holds in shared memory (512): the HBM scratch path."""
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 3600, n_occupied=5, hist_cap=96)
     f = o.get_families(history=False, adaptation=False)
-    import numpy as np
-    assert np.unique(f.location, return_counts=True)[1].max() > 64, "scenario must exceed the shared-memory path"
+    assert np.unique(f.location, return_counts=True)[1].max() > 512, "scenario must exceed the shared-memory path"
+    pc.run_lockstep(o, d, 2, hist_cap=96)
+
+
+def test_crowded_nodes_in_shared_memory(oracle, emu, synth):
+    """Nodes with 33..512 families: k_patch, one warp per node, working arrays in shared memory."""
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2000, n_occupied=8, hist_cap=96)
+    f = o.get_families(history=False, adaptation=False)
+    c = np.unique(f.location, return_counts=True)[1]
+    assert c.max() > 64 and c.max() <= 512
     pc.run_lockstep(o, d, 3, hist_cap=96)
 
 
