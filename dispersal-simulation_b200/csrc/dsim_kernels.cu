@@ -1003,29 +1003,40 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                 bool hostile = false;
                 if (j < i) hostile = (M.band[j] == B) && !dsim_will_cooperate(cf, M.cult[j], a.mc.threshold, a.mc.inclusive);
                 uint32_t mask = __ballot_sync(DSIM_FULL, hostile);
-                while (mask != 0u) { /* hostile members in join order */
-                    const uint32_t jj = j0 + (uint32_t)(__ffs((int)mask) - 1);
+                if (mask == 0u) continue;
+                any_hostile = true;
+                /* every hostile member's lane draws its own fight (the draws do not depend on the outcome of the
+                 * earlier fights); only the sizes are then resolved one fight after the other, in join order */
+                uint32_t so_mine = 0;
+                double sto_mine = 0.0;
+                bool dx = false, dy = false;
+                if (hostile) {
+                    so_mine = M.size[j];
+                    sto_mine = M.stored[j];
+                    const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, j);
+                    dx = o.x < a.mc.deadliness; /* fight_is_deadly, lib.rs:1219 */
+                    dy = o.y < a.mc.deadliness; /* lib.rs:1226 */
+                }
+                const uint32_t mdx = __ballot_sync(DSIM_FULL, dx), mdy = __ballot_sync(DSIM_FULL, dy);
+                while (mask != 0u) {
+                    const uint32_t l = (uint32_t)(__ffs((int)mask) - 1);
                     mask &= mask - 1u;
-                    any_hostile = true;
-                    uint32_t so = M.size[jj];
-                    double sto = M.stored[jj];
-                    __syncwarp();
+                    const uint32_t so = __shfl_sync(DSIM_FULL, so_mine, l);
                     const uint32_t reduction = sz < so ? sz : so;
-                    const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, jj);
-                    if (o.x < a.mc.deadliness) { /* fight_is_deadly, lib.rs:1219 */
-                        so -= reduction;
-                        if (so == 0u) {
-                            st = st + sto;
-                            sto = 0.0;
+                    if ((mdx >> l) & 1u) {
+                        if (lane == l) so_mine = so - reduction;
+                        if (so == reduction) { /* the member is wiped out: its stores go to the newcomer */
+                            st = st + __shfl_sync(DSIM_FULL, sto_mine, l);
+                            if (lane == l) sto_mine = 0.0;
                         }
                     }
-                    if (o.y < a.mc.deadliness) sz -= reduction; /* lib.rs:1226 */
-                    if (lane == 0) {
-                        M.size[jj] = so;
-                        M.stored[jj] = sto;
-                    }
-                    __syncwarp();
+                    if ((mdy >> l) & 1u) sz -= reduction;
                 }
+                if (hostile) {
+                    M.size[j] = so_mine;
+                    M.stored[j] = sto_mine;
+                }
+                __syncwarp();
             }
             if (!any_hostile) joined = (int)B;
         }
@@ -1338,30 +1349,33 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
             double st = G.get(stored, i);
             int joined = -1;
             for (uint32_t B = 0; B < nb && joined < 0; ++B) {
-                uint32_t hostile = G.ballot(gl < i && band == B && !dsim_will_cooperate(cf, cult, a.mc.threshold, a.mc.inclusive));
+                const bool host = gl < i && band == B && !dsim_will_cooperate(cf, cult, a.mc.threshold, a.mc.inclusive);
+                uint32_t hostile = G.ballot(host);
                 if (hostile == 0u) {
                     joined = (int)B;
                     break;
                 }
-                while (hostile != 0u) { /* hostile members in join order */
+                /* every hostile member's lane draws its own fight; the sizes are then resolved in join order */
+                bool dx = false, dy = false;
+                if (host) {
+                    const dsim_u4 o = dsim_draw(rs, step, fi, DSIM_P_FIGHT, gl);
+                    dx = o.x < a.mc.deadliness; /* fight_is_deadly, lib.rs:1219 */
+                    dy = o.y < a.mc.deadliness; /* lib.rs:1226 */
+                }
+                const uint32_t mdx = G.ballot(dx), mdy = G.ballot(dy);
+                while (hostile != 0u) {
                     const uint32_t jj = (uint32_t)__ffs((int)hostile) - 1u;
                     hostile &= hostile - 1u;
-                    uint32_t so = G.get(size, jj);
-                    double sto = G.get(stored, jj);
+                    const uint32_t so = G.get(size, jj);
                     const uint32_t reduction = sz < so ? sz : so;
-                    const dsim_u4 o = dsim_draw(rs, step, fi, DSIM_P_FIGHT, jj);
-                    if (o.x < a.mc.deadliness) { /* fight_is_deadly, lib.rs:1219 */
-                        so -= reduction;
-                        if (so == 0u) {
-                            st = st + sto;
-                            sto = 0.0;
+                    if ((mdx >> jj) & 1u) {
+                        if (gl == jj) size = so - reduction;
+                        if (so == reduction) { /* the member is wiped out: its stores go to the newcomer */
+                            st = st + G.get(stored, jj);
+                            if (gl == jj) stored = 0.0;
                         }
                     }
-                    if (o.y < a.mc.deadliness) sz -= reduction; /* lib.rs:1226 */
-                    if (gl == jj) {
-                        size = so;
-                        stored = sto;
-                    }
+                    if ((mdy >> jj) & 1u) sz -= reduction;
                 }
             }
             if (joined < 0) joined = (int)nb++;
@@ -1375,11 +1389,15 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
          * Lane B holds band B (nb <= n <= PG). ------------------------------------------------------- */
         uint64_t bcult = 0;
         uint32_t btot = 0;
+        uint64_t pivot = 0; /* lane B draws for band B */
+        if (gl < nb) {
+            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, gl);
+            pivot = ((uint64_t)o.y << 32) | o.x;
+        }
         for (uint32_t B = 0; B < nb; ++B) {
             const uint32_t members = G.ballot(mine && band == B);
             const uint32_t tot = G.sum((mine && band == B) ? size : 0u);
-            const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
-            uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)__popc(members));
+            uint32_t pick = (uint32_t)__umul64hi(G.get(pivot, B), (uint64_t)__popc(members));
             uint32_t m = members;
             while (pick > 0u) { /* the pick-th member in join order */
                 m &= m - 1u;
