@@ -32,7 +32,7 @@
 
 #define LIFE_BLOCK 256
 #ifndef PATCH_WARPS
-#define PATCH_WARPS 1 /* k_patch: one warp per block */
+#define PATCH_WARPS 4 /* k_patch: one block of four warps per node */
 #endif
 #ifndef PATCH_MIN_BLOCKS
 #define PATCH_MIN_BLOCKS 4
@@ -953,14 +953,19 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
     return v;
 }
 
-/* one node of k_patch; inlined twice, once with the working arrays in shared memory (fixed offsets) and once
- * with them in HBM scratch, so that neither copy carries seventeen live pointers */
-__device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t lane,
-                                           uint32_t step, const dsim_stream rs, double season, uint32_t &errors) {
-    __syncwarp();
+/* marks, in the band column, a newcomer that is hostile to an earlier member: its band is decided in join order */
+#define PATCH_TODO 0xFFFFFFFEu
+
+/* one node of k_patch, worked on by the whole block; inlined twice, once with the working arrays in shared memory
+ * (fixed offsets) and once with them in HBM scratch, so that neither copy carries seventeen live pointers.
+ * s_ctl: two shared words (number of bands, population). */
+__device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t tid,
+                                           uint32_t step, const dsim_stream rs, double season, uint32_t &errors, uint32_t *s_ctl) {
+    const uint32_t lane = tid & 31u, nthr = PATCH_WARPS * 32u;
+    __syncthreads();
 
     /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id) ----------- */
-    for (uint32_t j = lane; j < n; j += 32u) {
+    for (uint32_t j = tid; j < n; j += nthr) {
         const uint32_t i = a.sc.members[s0 + j];
         const uint64_t id = a.next.id[i];
         const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
@@ -968,8 +973,8 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         M.tfid[j] = id;
         M.key[j] = ((uint64_t)o.y << 32) | o.x;
     }
-    __syncwarp();
-    for (uint32_t j = lane; j < n; j += 32u) {
+    __syncthreads();
+    for (uint32_t j = tid; j < n; j += nthr) {
         const uint64_t kj = M.key[j], ij = M.tfid[j];
         uint32_t r = 0;
         for (uint32_t k = 0; k < n; ++k) {
@@ -979,78 +984,97 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         M.idx[r] = M.tidx[j];
         M.fid[r] = ij;
     }
-    __syncwarp();
-    for (uint32_t r = lane; r < n; r += 32u) {
+    __syncthreads();
+    for (uint32_t r = tid; r < n; r += nthr) {
         const uint32_t i = M.idx[r];
         M.cult[r] = a.next.culture[i];
         M.size[r] = a.next.size[i];
         M.stored[r] = a.next.stored[i];
-        M.band[r] = 0xFFFFFFFFu;
     }
-    __syncwarp();
+    __syncthreads();
 
-    /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 -------- */
-    uint32_t nb = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t cf = M.cult[i], fid = M.fid[i];
-        uint32_t sz = M.size[i];
-        double st = M.stored[i];
-        int joined = -1;
-        for (uint32_t B = 0; B < nb && joined < 0; ++B) {
-            bool any_hostile = false;
-            for (uint32_t j0 = 0; j0 < i; j0 += 32u) {
-                const uint32_t j = j0 + lane;
-                bool hostile = false;
-                if (j < i) hostile = (M.band[j] == B) && !dsim_will_cooperate(cf, M.cult[j], a.mc.threshold, a.mc.inclusive);
-                uint32_t mask = __ballot_sync(DSIM_FULL, hostile);
-                if (mask == 0u) continue;
-                any_hostile = true;
-                /* every hostile member's lane draws its own fight (the draws do not depend on the outcome of the
-                 * earlier fights); only the sizes are then resolved one fight after the other, in join order */
-                uint32_t so_mine = 0;
-                double sto_mine = 0.0;
-                bool dx = false, dy = false;
-                if (hostile) {
-                    so_mine = M.size[j];
-                    sto_mine = M.stored[j];
-                    const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, j);
-                    dx = o.x < a.mc.deadliness; /* fight_is_deadly, lib.rs:1219 */
-                    dy = o.y < a.mc.deadliness; /* lib.rs:1226 */
-                }
-                const uint32_t mdx = __ballot_sync(DSIM_FULL, dx), mdy = __ballot_sync(DSIM_FULL, dy);
-                while (mask != 0u) {
-                    const uint32_t l = (uint32_t)(__ffs((int)mask) - 1);
-                    mask &= mask - 1u;
-                    const uint32_t so = __shfl_sync(DSIM_FULL, so_mine, l);
-                    const uint32_t reduction = sz < so ? sz : so;
-                    if ((mdx >> l) & 1u) {
-                        if (lane == l) so_mine = so - reduction;
-                        if (so == reduction) { /* the member is wiped out: its stores go to the newcomer */
-                            st = st + __shfl_sync(DSIM_FULL, sto_mine, l);
-                            if (lane == l) sto_mine = 0.0;
+    /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 --------
+     * A newcomer that is hostile to none of the members before it finds no hostile member in the first band, joins
+     * it and changes nothing else: those are settled here, all at once.  Only the others walk the bands. */
+    for (uint32_t r = tid; r < n; r += nthr) {
+        const uint64_t c = M.cult[r];
+        bool h = false;
+        for (uint32_t j = 0; j < r; ++j) h |= !dsim_will_cooperate(c, M.cult[j], a.mc.threshold, a.mc.inclusive);
+        M.band[r] = h ? PATCH_TODO : 0u;
+    }
+    if (tid == 0) s_ctl[1] = 0u;
+    __syncthreads();
+    if (tid < 32u) { /* the first warp: hostile newcomers one after the other */
+        uint32_t nb = 1;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
+            uint32_t todo = __ballot_sync(DSIM_FULL, i0 + lane < n && M.band[i0 + lane] == PATCH_TODO);
+            while (todo != 0u) {
+                const uint32_t i = i0 + (uint32_t)(__ffs((int)todo) - 1);
+                todo &= todo - 1u;
+                const uint64_t cf = M.cult[i], fid = M.fid[i];
+                uint32_t sz = M.size[i];
+                double st = M.stored[i];
+                int joined = -1;
+                for (uint32_t B = 0; B < nb && joined < 0; ++B) {
+                    bool any_hostile = false;
+                    for (uint32_t j0 = 0; j0 < i; j0 += 32u) {
+                        const uint32_t j = j0 + lane;
+                        bool hostile = false;
+                        if (j < i) hostile = (M.band[j] == B) && !dsim_will_cooperate(cf, M.cult[j], a.mc.threshold, a.mc.inclusive);
+                        uint32_t mask = __ballot_sync(DSIM_FULL, hostile);
+                        if (mask == 0u) continue;
+                        any_hostile = true;
+                        /* every hostile member's lane draws its own fight (the draws do not depend on the outcome of
+                         * the earlier fights); only the sizes are then resolved one fight after the other, in join order */
+                        uint32_t so_mine = 0;
+                        double sto_mine = 0.0;
+                        bool dx = false, dy = false;
+                        if (hostile) {
+                            so_mine = M.size[j];
+                            sto_mine = M.stored[j];
+                            const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_FIGHT, j);
+                            dx = o.x < a.mc.deadliness; /* fight_is_deadly, lib.rs:1219 */
+                            dy = o.y < a.mc.deadliness; /* lib.rs:1226 */
                         }
+                        const uint32_t mdx = __ballot_sync(DSIM_FULL, dx), mdy = __ballot_sync(DSIM_FULL, dy);
+                        while (mask != 0u) {
+                            const uint32_t l = (uint32_t)(__ffs((int)mask) - 1);
+                            mask &= mask - 1u;
+                            const uint32_t so = __shfl_sync(DSIM_FULL, so_mine, l);
+                            const uint32_t reduction = sz < so ? sz : so;
+                            if ((mdx >> l) & 1u) {
+                                if (lane == l) so_mine = so - reduction;
+                                if (so == reduction) { /* the member is wiped out: its stores go to the newcomer */
+                                    st = st + __shfl_sync(DSIM_FULL, sto_mine, l);
+                                    if (lane == l) sto_mine = 0.0;
+                                }
+                            }
+                            if ((mdy >> l) & 1u) sz -= reduction;
+                        }
+                        if (hostile) {
+                            M.size[j] = so_mine;
+                            M.stored[j] = sto_mine;
+                        }
+                        __syncwarp();
                     }
-                    if ((mdy >> l) & 1u) sz -= reduction;
+                    if (!any_hostile) joined = (int)B;
                 }
-                if (hostile) {
-                    M.size[j] = so_mine;
-                    M.stored[j] = sto_mine;
+                if (joined < 0) joined = (int)nb++;
+                if (lane == 0) {
+                    M.band[i] = (uint32_t)joined;
+                    M.size[i] = sz;
+                    M.stored[i] = st;
                 }
                 __syncwarp();
             }
-            if (!any_hostile) joined = (int)B;
         }
-        if (joined < 0) joined = (int)nb++;
-        if (lane == 0) {
-            M.band[i] = (uint32_t)joined;
-            M.size[i] = sz;
-            M.stored[i] = st;
-        }
-        __syncwarp();
+        if (lane == 0) s_ctl[0] = nb;
     }
+    __syncthreads();
+    const uint32_t nb = s_ctl[0];
 
     /* ---- band culture = culture of a random member; drop empty bands, lib.rs:1400-1416 -------- */
-    for (uint32_t B = lane; B < nb; B += 32u) {
+    for (uint32_t B = tid; B < nb; B += nthr) {
         uint32_t cnt = 0, tot = 0;
         for (uint32_t j = 0; j < n; ++j)
             if (M.band[j] == B) {
@@ -1074,26 +1098,27 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         M.btot[B] = tot;
         M.balive[B] = tot > 0u ? 1 : 0;
     }
-    __syncwarp();
+    __syncthreads();
 
     /* ---- storage' (lib.rs:622-633): cultures and sizes of the surviving bands, creation order -- */
     uint32_t nb_alive = 0;
     uint64_t cult0 = 0;
-    for (uint32_t B0 = 0; B0 < nb; B0 += 32u) {
-        const uint32_t B = B0 + lane;
-        const bool al = (B < nb) && M.balive[B];
-        const uint32_t mask = __ballot_sync(DSIM_FULL, al);
-        if (al) {
-            const uint32_t k = nb_alive + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-            a.ps.band_cult[s0 + k] = M.bcult[B];
-            a.ps.band_size[s0 + k] = M.btot[B];
+    if (tid < 32u)
+        for (uint32_t B0 = 0; B0 < nb; B0 += 32u) {
+            const uint32_t B = B0 + lane;
+            const bool al = (B < nb) && M.balive[B];
+            const uint32_t mask = __ballot_sync(DSIM_FULL, al);
+            if (al) {
+                const uint32_t k = nb_alive + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                a.ps.band_cult[s0 + k] = M.bcult[B];
+                a.ps.band_size[s0 + k] = M.btot[B];
+            }
+            if (nb_alive == 0u && mask != 0u) cult0 = __shfl_sync(DSIM_FULL, al ? M.bcult[B] : 0ull, __ffs((int)mask) - 1);
+            nb_alive += (uint32_t)__popc(mask);
         }
-        if (nb_alive == 0u && mask != 0u) cult0 = __shfl_sync(DSIM_FULL, al ? M.bcult[B] : 0ull, __ffs((int)mask) - 1);
-        nb_alive += (uint32_t)__popc(mask);
-    }
 
     /* ---- adjust_culture / mutate, lib.rs:1960-1970, 1754-1785 ------------------------------- */
-    for (uint32_t r = lane; r < n; r += 32u) {
+    for (uint32_t r = tid; r < n; r += nthr) {
         const uint32_t B = M.band[r];
         if (!M.balive[B]) continue;
         const uint32_t i = M.idx[r];
@@ -1116,27 +1141,27 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         a.next.misc[i] = misc;
         a.next.till_mut[i] = clock;
     }
-    __syncwarp();
+    __syncthreads();
 
     /* ---- exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 ------------------ */
     const uint32_t e0 = a.ps.eco_off[p], e1 = a.ps.eco_off[p + 1];
     double quality = 0.0;
     for (uint32_t e = e0; e < e1; ++e) {
         const uint32_t eco = a.ps.eco_id[e];
-        for (uint32_t r = lane; r < n; r += 32u) { /* raw_family_contribution, lib.rs:1947-1958 */
+        for (uint32_t r = tid; r < n; r += nthr) { /* raw_family_contribution, lib.rs:1947-1958 */
             double c = 0.0;
             if (M.balive[M.band[r]]) c = (double)M.size[r] * adapt_touch(a, a.next.hs[M.idx[r]], eco, &errors);
             M.contrib[r] = c;
         }
-        __syncwarp();
-        for (uint32_t B = lane; B < nb; B += 32u) { /* sum_effort in join order */
+        __syncthreads();
+        for (uint32_t B = tid; B < nb; B += nthr) { /* sum_effort in join order */
             double eff = 0.0;
             if (M.balive[B])
                 for (uint32_t j = 0; j < n; ++j)
                     if (M.band[j] == B) eff = eff + M.contrib[j];
             M.beff[B] = eff;
         }
-        __syncwarp();
+        __syncthreads();
         double total_squared = 1.0;
         for (uint32_t B = 0; B < nb; ++B)
             if (M.balive[B]) total_squared = total_squared + M.beff[B] * M.beff[B];
@@ -1150,12 +1175,12 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             if (!(harvest > 0.0)) errors |= DSIM_MODEL_HARVEST_NOT_POSITIVE;
             const double coefficient = dsim_oyr_min(harvest / eff, 2.5);
             if (!(coefficient > 0.0)) errors |= DSIM_MODEL_COEFF_NOT_POSITIVE;
-            if (lane == 0) M.bcoef[B] = coefficient;
+            if (tid == 0) M.bcoef[B] = coefficient;
             res = res - coefficient * eff;
             if (!(res >= 0.0)) errors |= DSIM_MODEL_RESOURCES_NEGATIVE;
         }
-        __syncwarp();
-        for (uint32_t r = lane; r < n; r += 32u) {
+        __syncthreads();
+        for (uint32_t r = tid; r < n; r += nthr) {
             const uint32_t B = M.band[r];
             if (M.balive[B]) M.lh[r] = M.bcoef[B] * season * M.contrib[r];
         }
@@ -1165,14 +1190,14 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             const double proportion = 2.0 * dsim_u53(o.x, o.y);
             res = dsim_oyr_min(mx, mx * a.mc.recovery * proportion + res);
         }
-        if (lane == 0) a.ps.res[e] = res;
         quality = quality + (res + mx * a.mc.recovery); /* expected_harvest for the next step */
-        __syncwarp();
+        __syncthreads(); /* every thread has read res[e] before it is replaced */
+        if (tid == 0) a.ps.res[e] = res;
     }
 
     /* ---- write back ----------------------------------------------------------------------- */
     uint32_t pop = 0;
-    for (uint32_t r = lane; r < n; r += 32u) {
+    for (uint32_t r = tid; r < n; r += nthr) {
         const uint32_t i = M.idx[r];
         const uint32_t sz = M.size[r];
         a.next.size[i] = sz;
@@ -1188,10 +1213,12 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     pop += __shfl_xor_sync(DSIM_FULL, pop, 4);
     pop += __shfl_xor_sync(DSIM_FULL, pop, 2);
     pop += __shfl_xor_sync(DSIM_FULL, pop, 1);
-    if (lane == 0) {
+    if (lane == 0 && pop != 0u) atomicAdd(&s_ctl[1], pop);
+    __syncthreads();
+    if (tid == 0) {
         PatchView v;
         v.quality = quality;
-        v.pop = pop;
+        v.pop = s_ctl[1];
         v.nb = nb_alive;
         a.ps.view[p] = v;
         PatchBands b;
@@ -1201,16 +1228,16 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         a.ps.bands[p] = b;
         a.ps.cnt[p] = 0u;
     }
-    __syncwarp();
 }
 
 /* shared-memory working set of one node of up to PATCH_M families: 105 bytes per family */
 #define PATCH_SMEM_BYTES (PATCH_M * (6u * 4u + 5u * 8u + 5u * 8u + 1u))
 
 __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(StepArgs a) {
-    /* one warp per block: crowded nodes are few, and a node of hundreds of families walks its member arrays n times
+    /* one block per node: crowded nodes are few, and a node of hundreds of families walks its member arrays n times
      * (every newcomer meets every member, lib.rs:1380-1399) — from shared memory, not from HBM scratch */
     DSIM_DYN_SMEM(smem_raw);
+    __shared__ uint32_t s_ctl[2];
     uint64_t *const s_u64 = reinterpret_cast<uint64_t *>(smem_raw);
     double *const s_f64 = reinterpret_cast<double *>(smem_raw + 5u * 8u * PATCH_M);
     uint32_t *const s_u32 = reinterpret_cast<uint32_t *>(smem_raw + 10u * 8u * PATCH_M);
@@ -1218,7 +1245,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
 
     DevCtl *ctl = a.ctl;
     const uint32_t step = ctl->t;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tid = threadIdx.x;
     const uint32_t gwarp = blockIdx.x, nwarps = gridDim.x;
     const uint32_t n_big = ctl->n_big;
     const dsim_stream rs = stream_of(a.mc);
@@ -1238,7 +1265,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
             M.stored = s_f64; M.contrib = s_f64 + PATCH_M; M.lh = s_f64 + 2u * PATCH_M; M.beff = s_f64 + 3u * PATCH_M;
             M.bcoef = s_f64 + 4u * PATCH_M;
             M.balive = s_u8;
-            patch_node(a, M, p, n, s0, lane, step, rs, season, errors);
+            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl);
         } else {
             M.idx = a.sc.x_idx + s0; M.tidx = a.sc.x_tidx + s0; M.size = a.sc.x_size + s0; M.band = a.sc.x_band + s0;
             M.bcnt = a.sc.x_bcnt + s0; M.btot = a.sc.x_btot + s0;
@@ -1247,7 +1274,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
             M.stored = a.sc.x_stored + s0; M.contrib = a.sc.x_contrib + s0; M.lh = a.sc.x_lh + s0;
             M.beff = a.sc.x_beff + s0; M.bcoef = a.sc.x_bcoef + s0;
             M.balive = a.sc.x_balive + s0;
-            patch_node(a, M, p, n, s0, lane, step, rs, season, errors);
+            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl);
         }
     }
     if (errors) atomicOr(&ctl->errors, errors);
