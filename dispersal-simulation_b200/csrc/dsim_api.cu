@@ -1586,7 +1586,7 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     };
     switch (phase) {
     case DSIM_MG_PHASE_LIFECYCLE:
-        K(DSIM_K_LIFECYCLE, a1); K(DSIM_K_CONTROL, a1); M(DSIM_MGK_SPLIT_IDS, a1);
+        K(DSIM_K_LIFECYCLE, a1); M(DSIM_MGK_SPLIT_IDS, a1);
         break;
     case DSIM_MG_PHASE_MOVE: /* the children's ids (CHILD_RANK, from the SPLIT exchange) are first needed by k_children */
         K(DSIM_K_MOVE, a1); M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);

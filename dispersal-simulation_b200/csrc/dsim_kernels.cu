@@ -6,7 +6,7 @@
  *   part 1, update_each_family_step (lib.rs:511-552)
  *     k_lifecycle   consume / shrink / grow per family (lib.rs:527-539, 1912-1937); survivor and
  *                   split bitmaps, per-word and per-256 counts (the `retain` of lib.rs:541 becomes a scan)
- *     k_control     single block: exclusive scan of the per-256 counts, step bookkeeping
+ *                   + (last block to finish) exclusive scan of the per-256 counts, step bookkeeping
  *     k_move        one warp per tile of 4 families: decide_on_moving + best_location (lib.rs:830-929),
  *                   destination_quality (lib.rs:1034-1062), move bookkeeping (lib.rs:1826-1833), the
  *                   parent's half of maybe_procreate (lib.rs:1869-1897); writes the compacted next
@@ -16,8 +16,8 @@
  *   part 2, distribute_each_patch_resources_step (lib.rs:591-655)
  *     k_segments    one thread per occupied node: claim a segment of `members`
  *     k_scatter     one thread per family: counting-sort scatter; clears the views of vacated nodes
- *     k_patch_small eight lanes per node with at most 8 families, k_patch one warp per crowded node (the two
- *                   run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
+ *     k_patch_small eight lanes per node with at most 8 families, k_patch_mid a warp per node with 9..32, k_patch a
+ *                   block per crowded node (the three run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
  *                   (lib.rs:1754-1785, 1960-1970), exploit_patch + recover (lib.rs:2021-2109), next step's
  *                   census, quality and band cultures (lib.rs:522-525, 989-994, 622-633)
  *     k_advance     one thread: heavy-slot allocator bookkeeping, t += 1 (src/cli.rs:154)
@@ -64,6 +64,8 @@ __device__ __forceinline__ double noise_draw(const ModelConst &mc, uint32_t step
 /* ------------------------------------------------------------------------------------------ *
  * part 1a: lifecycle
  * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint32_t nvb);
+
 __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
     const uint32_t n = a.ctl->n_cur[a.parity];
     const uint32_t nvb = (n + LIFE_BLOCK - 1) / LIFE_BLOCK;
@@ -122,54 +124,65 @@ __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
         }
         __syncthreads();
     }
+    /* the last block to get here does part 1b */
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ctl->life_done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    control_tail(a, n, nvb);
 }
 
 /* ------------------------------------------------------------------------------------------ *
- * part 1b: scan of the per-256 counts + bookkeeping (single block)
+ * part 1b: exclusive scan of the per-256 counts + bookkeeping, by the last block of k_lifecycle to finish
  * ------------------------------------------------------------------------------------------ */
-#define CTL_THREADS 1024
-__global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
-    __shared__ uint32_t sa[CTL_THREADS], ss[CTL_THREADS];
-    __shared__ uint32_t carry_a, carry_s;
+__device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint32_t nvb) {
+    __shared__ uint32_t w_a[LIFE_BLOCK / 32], w_s[LIFE_BLOCK / 32];
     DevCtl *ctl = a.ctl;
-    const uint32_t n = ctl->n_cur[a.parity];
-    const uint32_t nvb = (n + LIFE_BLOCK - 1) / LIFE_BLOCK;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {
-        carry_a = 0;
-        carry_s = 0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    /* thread k owns the entries [k * per, (k + 1) * per) */
+    const uint32_t per = (nvb + LIFE_BLOCK - 1) / LIFE_BLOCK;
+    const uint32_t k0 = tid * per < nvb ? tid * per : nvb, k1 = k0 + per < nvb ? k0 + per : nvb;
+    uint32_t ta = 0, ts = 0;
+    for (uint32_t k = k0; k < k1; ++k) {
+        ta += DSIM_LDCG(a.sc.blk_alive + k);
+        ts += DSIM_LDCG(a.sc.blk_split + k);
+    }
+    uint32_t ia = ta, is = ts; /* inclusive scan over the block */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oa = __shfl_up_sync(DSIM_FULL, ia, d), os = __shfl_up_sync(DSIM_FULL, is, d);
+        if ((int)lane >= d) {
+            ia += oa;
+            is += os;
+        }
+    }
+    if (lane == 31u) {
+        w_a[w] = ia;
+        w_s[w] = is;
     }
     __syncthreads();
-    for (uint32_t base = 0; base < nvb; base += CTL_THREADS) {
-        const uint32_t k = base + tid;
-        const uint32_t va = (k < nvb) ? a.sc.blk_alive[k] : 0u;
-        const uint32_t vs = (k < nvb) ? a.sc.blk_split[k] : 0u;
-        sa[tid] = va;
-        ss[tid] = vs;
-        __syncthreads();
-        for (uint32_t off = 1; off < CTL_THREADS; off <<= 1) { /* inclusive Hillis-Steele */
-            uint32_t xa = 0, xs = 0;
-            if (tid >= off) {
-                xa = sa[tid - off];
-                xs = ss[tid - off];
-            }
-            __syncthreads();
-            sa[tid] += xa;
-            ss[tid] += xs;
-            __syncthreads();
+    uint32_t ba = 0, bs = 0, tot_a = 0, tot_s = 0;
+    for (uint32_t k = 0; k < LIFE_BLOCK / 32; ++k) {
+        if (k < w) {
+            ba += w_a[k];
+            bs += w_s[k];
         }
-        if (k < nvb) {
-            a.sc.blk_alive[k] = carry_a + sa[tid] - va; /* exclusive */
-            a.sc.blk_split[k] = carry_s + ss[tid] - vs;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            carry_a += sa[CTL_THREADS - 1];
-            carry_s += ss[CTL_THREADS - 1];
-        }
-        __syncthreads();
+        tot_a += w_a[k];
+        tot_s += w_s[k];
+    }
+    uint32_t ea = ba + ia - ta, es = bs + is - ts; /* exclusive prefix of this thread's first entry */
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t va = DSIM_LDCG(a.sc.blk_alive + k), vs = DSIM_LDCG(a.sc.blk_split + k);
+        a.sc.blk_alive[k] = ea;
+        a.sc.blk_split[k] = es;
+        ea += va;
+        es += vs;
     }
     if (tid == 0) {
+        const uint32_t carry_a = tot_a, carry_s = tot_s;
         const uint32_t n_alive = carry_a, n_children = carry_s;
         ctl->n_alive = n_alive;
         ctl->n_children = n_children;
@@ -192,6 +205,7 @@ __global__ void __launch_bounds__(CTL_THREADS) k_control(StepArgs a) {
             ctl->n_next = ctl->cap;
             ctl->n_cur[a.parity ^ 1u] = ctl->cap;
         }
+        ctl->life_done = 0;
     }
 }
 
@@ -499,7 +513,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 const uint32_t newpos = base_alive + va + (uint32_t)__popc(alive_mask & lt);
                 if (!((alive_mask >> (i & 31u)) & 1u)) {
                     a.sc.dead_hs[i - newpos] = hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
-                } else if (newpos < cap) {         /* else: capacity error already flagged by k_control */
+                } else if (newpos < cap) {         /* else: capacity error already flagged by k_lifecycle's tail */
                     state = 1u | (((split_mask >> (i & 31u)) & 1u) << 1);
                     S.fid[lane] = fid;
                     S.culture[lane] = culture;
@@ -1602,7 +1616,6 @@ static uint32_t grid_for(const LaunchGeom &g, uint32_t per_sm) { return g.n_sm *
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s) {
     switch (which) {
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
-    case DSIM_K_CONTROL: DSIM_LAUNCH(k_control, 1, CTL_THREADS, 0, s, a); break;
     case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, 8), MOVE_WARPS * 32, 0, s, a); break;
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;

@@ -32,7 +32,6 @@ int dsim_configure_kernels(LaunchGeom *g);
 
 enum {
     DSIM_K_LIFECYCLE = 0,
-    DSIM_K_CONTROL,
     DSIM_K_MOVE,
     DSIM_K_CHILDREN,
     DSIM_K_SEGMENTS,
@@ -44,7 +43,7 @@ enum {
     DSIM_K_COUNT
 };
 
-static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_control", "k_move",  "k_children", "k_segments",
+static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_move",  "k_children", "k_segments",
                                                             "k_scatter",   "k_patch_small", "k_patch_mid", "k_patch", "k_advance"};
 
 enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t total = 0;
         for (uint32_t r = 0; r < a.mg.world; ++r) total += mb.split_recv[r * stride];
-        ctl->next_id = ctl->child_id_base + total; /* k_control had added the local count only */
+        ctl->next_id = ctl->child_id_base + total; /* k_lifecycle's tail had added the local count only */
         mb.counters[MG_N_STAY] = 0;
         mb.counters[MG_N_EMIG0] = 0;
         mb.counters[MG_N_EMIG1] = 0;

@@ -21,8 +21,10 @@
 
 #if defined(DSIM_EMU)
 #define DSIM_NOINLINE __attribute__((noinline))
+#define DSIM_LDCG(p) (*(p))
 #else
 #define DSIM_NOINLINE __noinline__
+#define DSIM_LDCG(p) __ldcg(p) /* read at L2: data another block of the same launch has just written */
 #endif
 
 #define DSIM_FULL 0xffffffffu

@@ -134,6 +134,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t t;              /* State.t                                                            */
     uint32_t errors;
     uint32_t cap, hs_cap;
+    uint32_t life_done;      /* blocks of k_lifecycle that have finished (the last one scans and resets it) */
     uint64_t child_id_base, next_id;
     uint64_t births, deaths, updates;
 };

@@ -15,11 +15,13 @@ from helpers import D
 
 
 def build_pair(oracle_lib, dev_lib, synth, W, H, n_fam, seed=1, sim_seed=7, n_occupied=0, hist_fill=0,
-               params_edit=None, hist_cap=0, graph_edit=None, dev_prefix="dsim_", use_graphs=1, flags=0):
+               params_edit=None, hist_cap=0, graph_edit=None, dev_prefix="dsim_", use_graphs=1, flags=0, families_edit=None):
     g, res, mx = D.synth_grid(W, H, seed, lib=synth)
     if graph_edit is not None:
         g, res, mx = graph_edit(g, res, mx)
     fam = D.synth_families(W, H, n_fam, seed, n_occupied=n_occupied, hist_fill=hist_fill, lib=synth)
+    if families_edit is not None:
+        families_edit(fam)
     p = helpers.default_params(oracle_lib)
     if params_edit is not None:
         params_edit(p)
@@ -145,3 +147,14 @@ def check_reach(o, d):
             assert (x.view(np.uint64) == y.view(np.uint64)).all(), name
         else:
             assert (x == y).all(), name
+
+
+def hostile_cultures(n_cultures, seed=5):
+    """families_edit: every family gets one of `n_cultures` random 64-bit cultures (pairwise about 32 bits apart, so
+    members of different cultures never cooperate): crowded nodes then hold several bands, and most newcomers fight
+    their way past the bands before theirs (lib.rs:1209-1232, 1380-1399), wiping out members on the way."""
+    def edit(fam):
+        rng = np.random.default_rng(seed)
+        pool = rng.integers(0, 1 << 63, n_cultures, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n_cultures, dtype=np.uint64)
+        fam.culture[:] = pool[rng.integers(0, n_cultures, len(fam.culture))]
+    return edit

@@ -40,11 +40,21 @@ def test_dense_coresidence_spill_path(oracle, gpu_lib, synth):
 
 
 def test_crowded_nodes_in_shared_memory(oracle, gpu_lib, synth):
-    """Nodes with 33..512 families: k_patch, one warp per node, working arrays in shared memory."""
+    """Nodes with 33..512 families: k_patch, one block per node, working arrays in shared memory."""
     o, d = pc.build_pair(oracle, gpu_lib, synth, 30, 40, 2000, n_occupied=8, hist_cap=96)
     f = o.get_families(history=False, adaptation=False)
     c = np.unique(f.location, return_counts=True)[1]
     assert c.max() > 64 and c.max() <= 512
+    pc.run_lockstep(o, d, 3, hist_cap=96)
+
+
+def test_crowded_nodes_many_hostile_bands(oracle, gpu_lib, synth):
+    """Crowded nodes whose families belong to 6 mutually hostile cultures, and all sizes of node with 3: several bands
+    per node, newcomers fighting their way through the bands before theirs, members wiped out (lib.rs:1209-1232)."""
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=pc.hostile_cultures(6))
+    pc.run_lockstep(o, d, 3, hist_cap=96)
+    assert np.unique(o.get_storage()[0], return_counts=True)[1].max() >= 4, "scenario must produce several bands on one node"
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 20, 24, 1500, n_occupied=80, hist_cap=96, families_edit=pc.hostile_cultures(3))
     pc.run_lockstep(o, d, 3, hist_cap=96)
 
 
