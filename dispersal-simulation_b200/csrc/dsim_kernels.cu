@@ -670,10 +670,32 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                         const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
                         q = a.hv.hist_patch[hb + pos];
                         gain = a.hv.hist_harv[hb + pos];
-                        const uint32_t idx = row_find(row, q);
+                        /* the chain entry -> bucket -> row is three dependent loads: the draw is computed while the
+                         * bucket is in flight, and the cost is requested together with the row entry that verifies
+                         * the bucket's answer */
+                        uint32_t idx = ROW_SEARCH;
+                        uint4 bk = make_uint4(0u, 0u, 0u, 0u);
+                        if (row.hash != nullptr) bk = *bucket_of(row.hash, q);
+                        const double u = noise_draw(a.mc, step, fid, n_near + nn);
+                        if (row.hash != nullptr) {
+                            const uint32_t bp = bucket_probe(bk, q);
+                            if (bp == ROW_ABSENT) {
+                                idx = ROW_ABSENT;
+                            } else if (bp < row.len) {
+                                const uint32_t dq = row.dst[bp];
+                                const double c = row.cost[bp];
+                                if (dq == q) {
+                                    idx = bp;
+                                    cost = c;
+                                }
+                            }
+                        }
+                        if (idx == ROW_SEARCH) {
+                            idx = row_find_sorted(row.dst, row.n_sensed, row.len, q);
+                            if (idx != ROW_ABSENT) cost = row.cost[idx];
+                        }
                         if (idx != ROW_ABSENT) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
-                            cost = row.cost[idx];
-                            g = gain * noise_draw(a.mc, step, fid, n_near + nn) - cost;
+                            g = gain * u - cost;
                             cand = true;
                         }
                     }
