@@ -31,6 +31,9 @@
 #include <cstring>
 
 #define LIFE_BLOCK 256
+#ifndef CHILD_HR
+#define CHILD_HR 3u /* k_children: rounds of 32 history entries handled together (3 x 32 >= the default child history of 91) */
+#endif
 #ifndef PATCH_WARPS
 #define PATCH_WARPS 4 /* k_patch: one block of four warps per node */
 #endif
@@ -807,62 +810,187 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
         /* `&nearby[1..]` of the parent's OLD patch (lib.rs:1846), costs from the child's patch */
         const uint32_t nl0 = a.rt.near_off[t.old_loc], nl1 = a.rt.near_off[t.old_loc + 1];
         const uint32_t first = nl0 + ((nl1 > nl0) ? 1u : 0u);
-        uint32_t n_considered = 0; /* noise index = ordinal among the sensed patches that have a travel cost */
-        for (uint32_t base = first; base < nl1; base += 32u) {
-            const uint32_t jj = base + lane;
-            bool cand = false;
-            double g = 0.0, gain = 0.0, cost = 0.0;
-            uint32_t q = 0, k = 0xFFFFFFFFu;
-            if (jj < nl1) {
-                q = a.rt.near_dst[jj];
-                k = row_find(row, q);
-                cand = k != 0xFFFFFFFFu;
-            }
-            const uint32_t cmask = __ballot_sync(DSIM_FULL, cand);
-            if (cand) {
-                cost = row.cost[k];
-                gain = view_quality(a, a.ps.view[q], q, t.culture, 2u, q == t.new_loc);
-                g = gain * noise_draw(a.mc, step, cid, n_considered + (uint32_t)__popc(cmask & ((1u << lane) - 1u))) - cost;
-            }
-            n_considered += (uint32_t)__popc(cmask);
-            accept_scan_warp(cc, cand, g, gain, cost, q);
-        }
         /* history = the parent's newest min(len, time_to_grow_adult) entries, the one pushed this step included */
         const uint32_t valid = t.hist_cnt < hcap ? t.hist_cnt : hcap;
         const uint32_t child_len = valid < a.mc.adult_reset ? valid : a.mc.adult_reset;
         const uint32_t nhc = child_len < a.mc.n_mem ? child_len : a.mc.n_mem;
         const size_t pb = (size_t)t.parent_hs * hcap, cb = (size_t)chs * hcap;
-        for (uint32_t base = 0; base < nhc; base += 32u) {
-            const uint32_t n = base + lane;
-            bool cand = false;
-            double g = 0.0, gain = 0.0, cost = 0.0;
-            uint32_t q = 0;
-            if (n < nhc && mem_keep(a.mc, step, cid, n)) {
+
+        /* The kernel is a chain of memory round trips (few children, a warp each), so everything that depends only on
+         * the task is requested first and used last: the parent's newest entries (candidates AND the child's copy of
+         * the history, CHILD_HR x 32 per chunk) and its adaptation slots. */
+        uint32_t hp[CHILD_HR];
+        double hh[CHILD_HR];
+#pragma unroll
+        for (uint32_t s = 0; s < CHILD_HR; ++s) {
+            const uint32_t n = 32u * s + lane;
+            hp[s] = 0u;
+            hh[s] = 0.0;
+            if (n < child_len) {
                 const uint32_t pos = (t.hist_cnt - 1u - n) % hcap;
-                q = a.hv.hist_patch[pb + pos];
-                gain = a.hv.hist_harv[pb + pos];
-                const uint32_t k = row_find(row, q);
-                if (k != 0xFFFFFFFFu) {
-                    cost = row.cost[k];
-                    g = gain * noise_draw(a.mc, step, cid, (nl1 - first) + n) - cost;
-                    cand = true;
+                hp[s] = a.hv.hist_patch[pb + pos];
+                hh[s] = a.hv.hist_harv[pb + pos];
+            }
+        }
+        uint16_t ad_eco = 0;
+        uint32_t ad_cnt = 0;
+        double ad_val = 0.0;
+        if (lane < acap) {
+            ad_eco = a.hv.a_eco[(size_t)t.parent_hs * acap + lane];
+            ad_cnt = a.hv.a_cnt[(size_t)t.parent_hs * acap + lane];
+            ad_val = a.hv.a_val[(size_t)t.parent_hs * acap + lane];
+        }
+        const uint32_t parent_decay = a.hv.decay[t.parent_hs];
+
+        /* ---- sensed patches, two rounds of 32 at a time: entry -> {bucket, view, bands} -> {row entry, cost} ---- */
+        uint32_t n_considered = 0; /* noise index = ordinal among the sensed patches that have a travel cost */
+        for (uint32_t base = first; base < nl1; base += 64u) {
+            uint32_t q[2], bp[2];
+            bool on[2], cand[2];
+            uint4 bk[2];
+            PatchView pv[2];
+            PatchBands pbn[2];
+            uint32_t dq[2];
+            double c[2];
+#pragma unroll
+            for (uint32_t s = 0; s < 2u; ++s) {
+                const uint32_t jj = base + 32u * s + lane;
+                on[s] = jj < nl1;
+                q[s] = a.rt.near_dst[on[s] ? jj : nl1 - 1u];
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < 2u; ++s) {
+                bk[s] = make_uint4(0u, 0u, 0u, 0u);
+                if (row.hash != nullptr) bk[s] = *bucket_of(row.hash, q[s]);
+                pv[s] = a.ps.view[q[s]];
+                pbn[s] = a.ps.bands[q[s]];
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < 2u; ++s) {
+                bp[s] = row.hash != nullptr ? bucket_probe(bk[s], q[s]) : ROW_SEARCH;
+                const uint32_t at = bp[s] < row.len ? bp[s] : 0u;
+                dq[s] = row.len ? row.dst[at] : 0xFFFFFFFFu;
+                c[s] = row.len ? row.cost[at] : 0.0;
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < 2u; ++s) {
+                cand[s] = false;
+                if (on[s] && bp[s] != ROW_ABSENT) {
+                    if (bp[s] < row.len && dq[s] == q[s]) {
+                        cand[s] = true;
+                    } else {
+                        const uint32_t k = row_find_sorted(row.dst, row.n_sensed, row.len, q[s]);
+                        if (k != ROW_ABSENT) {
+                            cand[s] = true;
+                            c[s] = row.cost[k];
+                        }
+                    }
                 }
             }
-            accept_scan_warp(cc, cand, g, gain, cost, q);
+#pragma unroll
+            for (uint32_t s = 0; s < 2u; ++s) {
+                if (s == 1u && base + 32u >= nl1) break;
+                const uint32_t cmask = __ballot_sync(DSIM_FULL, cand[s]);
+                double g = 0.0, gain = 0.0;
+                if (cand[s]) {
+                    BandsRef br;
+                    br.cult0 = pbn[s].cult0;
+                    br.stor_off = pbn[s].stor_off;
+                    gain = quality_eval(a, pv[s], br, t.culture, 2u, q[s] == t.new_loc);
+                    g = gain * noise_draw(a.mc, step, cid, n_considered + (uint32_t)__popc(cmask & ((1u << lane) - 1u))) - c[s];
+                }
+                n_considered += (uint32_t)__popc(cmask);
+                accept_scan_warp(cc, cand[s], g, gain, cand[s] ? c[s] : 0.0, q[s]);
+            }
         }
-        for (uint32_t k = lane; k < child_len; k += 32u) { /* chronological index k = newest-first index child_len-1-k */
-            const uint32_t pos = (t.hist_cnt - 1u - (child_len - 1u - k)) % hcap;
-            a.hv.hist_patch[cb + k] = a.hv.hist_patch[pb + pos];
-            a.hv.hist_harv[cb + k] = a.hv.hist_harv[pb + pos];
+
+        /* ---- remembered patches and the copy of the history, CHILD_HR rounds of 32 entries at a time ---------- */
+        for (uint32_t c0 = 0; c0 < child_len; c0 += 32u * CHILD_HR) {
+            bool keep[CHILD_HR], cand[CHILD_HR];
+            uint4 bk[CHILD_HR];
+            uint32_t bp[CHILD_HR], dq[CHILD_HR];
+            double c[CHILD_HR], u[CHILD_HR];
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                const uint32_t n = c0 + 32u * s + lane;
+                keep[s] = n < nhc && mem_keep(a.mc, step, cid, n);
+                bk[s] = make_uint4(0u, 0u, 0u, 0u);
+                if (row.hash != nullptr && keep[s]) bk[s] = *bucket_of(row.hash, hp[s]);
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) { /* the draws, while the buckets are in flight */
+                const uint32_t n = c0 + 32u * s + lane;
+                u[s] = keep[s] ? noise_draw(a.mc, step, cid, (nl1 - first) + n) : 0.0;
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                bp[s] = row.hash != nullptr ? bucket_probe(bk[s], hp[s]) : ROW_SEARCH;
+                const uint32_t at = bp[s] < row.len ? bp[s] : 0u;
+                dq[s] = 0xFFFFFFFFu;
+                c[s] = 0.0;
+                if (keep[s] && row.len) {
+                    dq[s] = row.dst[at];
+                    c[s] = row.cost[at];
+                }
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                cand[s] = false;
+                if (keep[s] && bp[s] != ROW_ABSENT) {
+                    if (bp[s] < row.len && dq[s] == hp[s]) {
+                        cand[s] = true;
+                    } else {
+                        const uint32_t k = row_find_sorted(row.dst, row.n_sensed, row.len, hp[s]);
+                        if (k != ROW_ABSENT) {
+                            cand[s] = true;
+                            c[s] = row.cost[k];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                if (c0 + 32u * s >= nhc) break;
+                const double cost = cand[s] ? c[s] : 0.0;
+                accept_scan_warp(cc, cand[s], cand[s] ? hh[s] * u[s] - cost : 0.0, cand[s] ? hh[s] : 0.0, cost, cand[s] ? hp[s] : 0u);
+            }
+            /* the child's ring: chronological index k = newest-first index child_len - 1 - k */
+#pragma unroll
+            for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                const uint32_t n = c0 + 32u * s + lane;
+                if (n < child_len) {
+                    a.hv.hist_patch[cb + (child_len - 1u - n)] = hp[s];
+                    a.hv.hist_harv[cb + (child_len - 1u - n)] = hh[s];
+                }
+            }
+            if (c0 + 32u * CHILD_HR < child_len) { /* next chunk (longer child histories than the default 91) */
+#pragma unroll
+                for (uint32_t s = 0; s < CHILD_HR; ++s) {
+                    const uint32_t n = c0 + 32u * CHILD_HR + 32u * s + lane;
+                    hp[s] = 0u;
+                    hh[s] = 0.0;
+                    if (n < child_len) {
+                        const uint32_t pos = (t.hist_cnt - 1u - n) % hcap;
+                        hp[s] = a.hv.hist_patch[pb + pos];
+                        hh[s] = a.hv.hist_harv[pb + pos];
+                    }
+                }
+            }
         }
-        for (uint32_t k = lane; k < acap; k += 32u) { /* adaptation: family.adaptation, lib.rs:1893 */
+        /* adaptation: family.adaptation, lib.rs:1893 */
+        if (lane < acap) {
+            a.hv.a_eco[(size_t)chs * acap + lane] = ad_eco;
+            a.hv.a_cnt[(size_t)chs * acap + lane] = ad_cnt;
+            a.hv.a_val[(size_t)chs * acap + lane] = ad_val;
+        }
+        for (uint32_t k = 32u + lane; k < acap; k += 32u) {
             a.hv.a_eco[(size_t)chs * acap + k] = a.hv.a_eco[(size_t)t.parent_hs * acap + k];
             a.hv.a_cnt[(size_t)chs * acap + k] = a.hv.a_cnt[(size_t)t.parent_hs * acap + k];
             a.hv.a_val[(size_t)chs * acap + k] = a.hv.a_val[(size_t)t.parent_hs * acap + k];
         }
         if (lane == 0) {
             a.hv.hist_cnt[chs] = child_len;
-            a.hv.decay[chs] = a.hv.decay[t.parent_hs];
+            a.hv.decay[chs] = parent_decay;
             a.hv.parent[chs] = t.parent_id;
             a.hv.birth_index[chs] = (uint16_t)t.n_off;
             a.next.id[cpos] = cid;
