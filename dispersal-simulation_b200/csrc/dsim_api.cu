@@ -207,7 +207,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
     A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8) A(ns.word_pre, new_cap / 32 + 8)
     A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
     A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
-    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_small, new_cap) A(ns.plist_mid, new_cap) A(ns.plist_big, new_cap)
+    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_one, new_cap) A(ns.plist_small, new_cap) A(ns.plist_mid, new_cap) A(ns.plist_big, new_cap)
     A(ns.child_task, new_cap)
     A(ns.x_idx, new_cap) A(ns.x_tidx, new_cap) A(ns.x_size, new_cap) A(ns.x_band, new_cap)
     A(ns.x_bcnt, new_cap) A(ns.x_btot, new_cap)

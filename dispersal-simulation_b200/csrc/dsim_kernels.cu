@@ -198,6 +198,7 @@ __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint
         ctl->n_occ[a.occ_par] = 0;
         ctl->seg_cursor = 0;
         ctl->n_small = 0;
+        ctl->n_one = 0;
         ctl->n_mid = 0;
         ctl->n_big = 0;
         ctl->births += n_children;
@@ -1026,8 +1027,10 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         const uint32_t p = a.sc.occ[a.occ_par][k];
         const uint32_t c = a.ps.cnt[p];
         a.ps.seg[p] = atomicAdd(&ctl->seg_cursor, c);
-        /* sparsely occupied nodes go to the thread-per-node kernel, crowded ones to the warp-per-node kernel */
-        if (c <= a.small_max)
+        /* by family count: a thread, eight lanes, a warp or a block per node */
+        if (c == 1u && a.small_max >= 1u)
+            a.sc.plist_one[atomicAdd(&ctl->n_one, 1u)] = p;
+        else if (c <= a.small_max)
             a.sc.plist_small[atomicAdd(&ctl->n_small, 1u)] = p;
         else if (c <= a.mid_max)
             a.sc.plist_mid[atomicAdd(&ctl->n_mid, 1u)] = p;
@@ -1701,6 +1704,7 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
 }
 
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
+    patch_groups<1u>(a, a.sc.plist_one, a.ctl->n_one); /* a family alone on its node: a thread per node */
     patch_groups<8u>(a, a.sc.plist_small, a.ctl->n_small);
 }
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_mid(StepArgs a) {

@@ -111,7 +111,8 @@ struct StepScratch {
     uint32_t *fslot;        /* [cap] arrival rank of family j at its new node                      */
     uint32_t *members;      /* [cap] family positions grouped by node                              */
     uint32_t *occ[2];       /* [cap] occupied nodes of this / the previous step                    */
-    uint32_t *plist_small;  /* [cap] occupied nodes with few families (thread-per-node kernel)       */
+    uint32_t *plist_one;    /* [cap] occupied nodes with exactly one family (a thread per node)              */
+    uint32_t *plist_small;  /* [cap] occupied nodes with 2..8 families (eight lanes per node)                 */
     uint32_t *plist_mid;    /* [cap] occupied nodes with 9..32 families (a warp per node, registers only)    */
     uint32_t *plist_big;    /* [cap] the others (warp per node, shared memory / HBM scratch)                */
     ChildTask *child_task;  /* [cap] indexed by child rank                                          */
@@ -129,7 +130,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t n_alive, n_children, n_dead, n_next;
     uint32_t child_pos_base; /* = n_alive                                                         */
     uint32_t seg_cursor;
-    uint32_t n_small, n_mid, n_big; /* lengths of plist_small / plist_mid / plist_big                       */
+    uint32_t n_one, n_small, n_mid, n_big; /* lengths of plist_one / plist_small / plist_mid / plist_big         */
     uint32_t free_top, hs_hwm;
     uint32_t t;              /* State.t                                                            */
     uint32_t errors;
