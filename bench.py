@@ -384,6 +384,7 @@ def main():
             return v, t
         keep = []
         res_p, t_ = pinned(res); keep.append(t_)
+        res_out, t_ = pinned(res); keep.append(t_)  # the caller's buffer for the downloaded resources
         mx_p, t_ = pinned(mx); keep.append(t_)
         fam_p = D.Families(fam.n)
         for name in [n_ for n_, _ in D._FAM_FIELDS] + ["hist_off", "hist_patch", "hist_harvest", "adapt_off", "adapt_eco", "adapt_val"]:
@@ -403,7 +404,7 @@ def main():
                 upd += s1.family_updates
             t2 = time.perf_counter()
             out = sim2.get_families(history=False, adaptation=False)
-            r_out, _ = sim2.get_patches()
+            r_out, _ = sim2.get_patches(maximum=False, out=res_out)  # the maxima are inputs and never change
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             log(f"[bench] rank {rank}: end to end #{rep}: {dt * 1e3:.1f} ms = upload {1e3 * (t1 - t0):.1f} + {n_steps_e2e} steps "

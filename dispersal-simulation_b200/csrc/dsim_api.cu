@@ -41,6 +41,22 @@ struct DevBuf { /* one cudaMalloc'd array */
 
 } // namespace
 
+/* page-locked host memory for std::vector (the staging buffers of the getters) */
+template <typename T> struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U> PinnedAlloc(const PinnedAlloc<U> &) {}
+    T *allocate(size_t n) {
+        T *p = nullptr;
+        if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess) throw std::bad_alloc();
+        return p;
+    }
+    void deallocate(T *p, size_t) { cudaFreeHost(p); }
+    template <class U> bool operator==(const PinnedAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const PinnedAlloc<U> &) const { return false; }
+};
+template <typename T> using pinned_vector = std::vector<T, PinnedAlloc<T>>;
+
 struct dsim_handle {
     dsim_params p;
     dsim_options opt;
@@ -87,14 +103,17 @@ struct dsim_handle {
     uint64_t k_launches[DSIM_K_COUNT] = {};
     uint64_t total_launches = 0;
 
-    /* host snapshot for the getters */
-    bool snap_valid = false;
-    std::vector<uint64_t> s_id, s_culture;
-    std::vector<double> s_stored, s_lh;
-    std::vector<uint32_t> s_loc, s_size, s_till_adult, s_till_mut, s_misc, s_hs, s_hist_len;
-    std::vector<uint16_t> s_a_eco;
-    std::vector<double> s_a_val;
-    std::vector<uint32_t> s_a_n;
+    /* host snapshot for the getters: the record columns and history lengths (snap_valid) and, on demand, the
+     * adaptation slots replayed to the current decay count (snap_adapt_valid); page-locked, so that the downloads are
+     * plain DMA transfers */
+    bool snap_valid = false, snap_adapt_valid = false;
+    pinned_vector<uint64_t> s_id, s_culture;
+    pinned_vector<double> s_stored, s_lh;
+    pinned_vector<uint32_t> s_loc, s_size, s_till_adult, s_till_mut, s_misc, s_hs, s_hist_cnt;
+    std::vector<uint32_t> s_hist_len;
+    pinned_vector<uint16_t> s_a_eco;
+    pinned_vector<double> s_a_val;
+    pinned_vector<uint32_t> s_a_n;
 
     std::vector<uint32_t> storage_nodes; /* nodes named by dsim_set_storage */
     std::string err;
@@ -383,7 +402,7 @@ int recensus(dsim_handle *h) {
     return DSIM_OK;
 }
 
-int take_snapshot(dsim_handle *h);
+int take_snapshot(dsim_handle *h, bool want_adapt);
 
 } // namespace
 
@@ -504,53 +523,61 @@ __global__ void k_clear_storage(PatchState ps, uint32_t n_nodes) {
 
 namespace {
 
-int take_snapshot(dsim_handle *h) {
-    if (h->snap_valid) return DSIM_OK;
-    int rc = sync_ctl(h);
-    if (rc) return rc;
-    const uint32_t buf = h->mid_step ? (h->parity ^ 1u) : h->parity;
-    const uint32_t n = h->mid_step ? h->ctl_h->n_next : h->ctl_h->n_cur[h->parity];
-    const FamCore &f = h->fam[buf];
-    h->s_id.resize(n); h->s_culture.resize(n); h->s_stored.resize(n); h->s_lh.resize(n);
-    h->s_loc.resize(n); h->s_size.resize(n); h->s_till_adult.resize(n); h->s_till_mut.resize(n);
-    h->s_misc.resize(n); h->s_hs.resize(n); h->s_hist_len.resize(n); h->s_a_n.resize(n);
-    h->s_a_eco.resize((size_t)n * h->acap); h->s_a_val.resize((size_t)n * h->acap);
-    if ((rc = download(h, h->s_id.data(), f.id, n))) return rc;
-    if ((rc = download(h, h->s_culture.data(), f.culture, n))) return rc;
-    if ((rc = download(h, h->s_stored.data(), f.stored, n))) return rc;
-    if ((rc = download(h, h->s_lh.data(), f.last_harvest, n))) return rc;
-    if ((rc = download(h, h->s_loc.data(), f.loc, n))) return rc;
-    if ((rc = download(h, h->s_size.data(), f.size, n))) return rc;
-    if ((rc = download(h, h->s_till_adult.data(), f.till_adult, n))) return rc;
-    if ((rc = download(h, h->s_till_mut.data(), f.till_mut, n))) return rc;
-    if ((rc = download(h, h->s_misc.data(), f.misc, n))) return rc;
-    if ((rc = download(h, h->s_hs.data(), f.hs, n))) return rc;
-    /* adaptation, replayed to the current decay count */
-    std::vector<void *> tmp;
-    uint16_t *d_eco;
-    double *d_val;
-    uint32_t *d_n;
-    if ((rc = dev_alloc(h, &d_eco, (size_t)n * h->acap, tmp, false)) || (rc = dev_alloc(h, &d_val, (size_t)n * h->acap, tmp, false)) ||
-        (rc = dev_alloc(h, &d_n, n, tmp, false))) {
+int take_snapshot(dsim_handle *h, bool want_adapt) {
+    int rc;
+    if (!h->snap_valid) {
+        if ((rc = sync_ctl(h))) return rc;
+        const uint32_t buf = h->mid_step ? (h->parity ^ 1u) : h->parity;
+        const uint32_t n = h->mid_step ? h->ctl_h->n_next : h->ctl_h->n_cur[h->parity];
+        const FamCore &f = h->fam[buf];
+        h->snap_adapt_valid = false;
+        h->s_id.resize(n); h->s_culture.resize(n); h->s_stored.resize(n); h->s_lh.resize(n);
+        h->s_loc.resize(n); h->s_size.resize(n); h->s_till_adult.resize(n); h->s_till_mut.resize(n);
+        h->s_misc.resize(n); h->s_hs.resize(n); h->s_hist_len.resize(n); h->s_hist_cnt.resize(h->hs_cap);
+        if ((rc = download(h, h->s_id.data(), f.id, n))) return rc;
+        if ((rc = download(h, h->s_culture.data(), f.culture, n))) return rc;
+        if ((rc = download(h, h->s_stored.data(), f.stored, n))) return rc;
+        if ((rc = download(h, h->s_lh.data(), f.last_harvest, n))) return rc;
+        if ((rc = download(h, h->s_loc.data(), f.loc, n))) return rc;
+        if ((rc = download(h, h->s_size.data(), f.size, n))) return rc;
+        if ((rc = download(h, h->s_till_adult.data(), f.till_adult, n))) return rc;
+        if ((rc = download(h, h->s_till_mut.data(), f.till_mut, n))) return rc;
+        if ((rc = download(h, h->s_misc.data(), f.misc, n))) return rc;
+        if ((rc = download(h, h->s_hs.data(), f.hs, n))) return rc;
+        if ((rc = download(h, h->s_hist_cnt.data(), h->hv.hist_cnt, h->hs_cap))) return rc; /* history lengths */
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
+        for (uint32_t i = 0; i < n; ++i) h->s_hist_len[i] = std::min(h->s_hist_cnt[h->s_hs[i]], h->hcap);
+        h->snap_valid = true;
+    }
+    if (want_adapt && !h->snap_adapt_valid) {
+        /* adaptation, replayed to the current decay count */
+        const uint32_t buf = h->mid_step ? (h->parity ^ 1u) : h->parity;
+        const FamCore &f = h->fam[buf];
+        const uint32_t n = (uint32_t)h->s_id.size();
+        h->s_a_n.resize(n);
+        h->s_a_eco.resize((size_t)n * h->acap); h->s_a_val.resize((size_t)n * h->acap);
+        std::vector<void *> tmp;
+        uint16_t *d_eco;
+        double *d_val;
+        uint32_t *d_n;
+        if ((rc = dev_alloc(h, &d_eco, (size_t)n * h->acap, tmp, false)) || (rc = dev_alloc(h, &d_val, (size_t)n * h->acap, tmp, false)) ||
+            (rc = dev_alloc(h, &d_n, n, tmp, false))) {
+            free_list(tmp);
+            return rc;
+        }
+        if (n) {
+            DSIM_LAUNCH(k_pack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint32_t *)f.hs, n, h->p.minimum_adaptation,
+                        d_eco, d_val, d_n);
+            h->total_launches += 1;
+        }
+        rc = download(h, h->s_a_eco.data(), d_eco, (size_t)n * h->acap);
+        if (!rc) rc = download(h, h->s_a_val.data(), d_val, (size_t)n * h->acap);
+        if (!rc) rc = download(h, h->s_a_n.data(), d_n, n);
+        if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
         free_list(tmp);
-        return rc;
+        if (rc) return rc;
+        h->snap_adapt_valid = true;
     }
-    if (n) {
-        DSIM_LAUNCH(k_pack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint32_t *)f.hs, n, h->p.minimum_adaptation,
-                    d_eco, d_val, d_n);
-        h->total_launches += 1;
-    }
-    rc = download(h, h->s_a_eco.data(), d_eco, (size_t)n * h->acap);
-    if (!rc) rc = download(h, h->s_a_val.data(), d_val, (size_t)n * h->acap);
-    if (!rc) rc = download(h, h->s_a_n.data(), d_n, n);
-    /* history lengths */
-    std::vector<uint32_t> cnt(h->hs_cap);
-    if (!rc) rc = download(h, cnt.data(), h->hv.hist_cnt, h->hs_cap);
-    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
-    free_list(tmp);
-    if (rc) return rc;
-    for (uint32_t i = 0; i < n; ++i) h->s_hist_len[i] = std::min(cnt[h->s_hs[i]], h->hcap);
-    h->snap_valid = true;
     return DSIM_OK;
 }
 
@@ -1008,12 +1035,17 @@ int dsim_set_families(dsim_handle *h, const dsim_families *f) {
 
 int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *n_adapt) {
     if (!h) return DSIM_ERR_INVALID;
-    int rc = take_snapshot(h);
-    if (rc) return rc;
+    int rc;
+    if (!n_hist && !n_adapt) { /* the number of families alone needs no snapshot */
+        if ((rc = sync_ctl(h))) return rc;
+        if (n) *n = h->mid_step ? h->ctl_h->n_next : h->ctl_h->n_cur[h->parity];
+        return DSIM_OK;
+    }
+    if ((rc = take_snapshot(h, n_adapt != nullptr))) return rc;
     uint64_t nh = 0, na = 0;
     for (size_t i = 0; i < h->s_id.size(); ++i) {
         nh += h->s_hist_len[i];
-        na += h->s_a_n[i];
+        if (n_adapt) na += h->s_a_n[i];
     }
     if (n) *n = h->s_id.size();
     if (n_hist) *n_hist = nh;
@@ -1023,7 +1055,7 @@ int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *
 
 int dsim_get_families(dsim_handle *h, dsim_families *f) {
     if (!h || !f) return DSIM_ERR_INVALID;
-    int rc = take_snapshot(h);
+    int rc = take_snapshot(h, f->adapt_off != nullptr);
     if (rc) return rc;
     const size_t n = h->s_id.size();
     f->n = n;

@@ -329,23 +329,29 @@ class Sim:
         assert res.shape[0] == self.n_eco and max_res.shape[0] == self.n_eco
         self._check(self._f("set_patches")(self.h, _ptr(res, C.c_double), _ptr(max_res, C.c_double)))
 
-    def get_patches(self):
-        res = np.zeros(self.n_eco, dtype=np.float64)
-        mx = np.zeros(self.n_eco, dtype=np.float64)
-        self._check(self._f("get_patches")(self.h, _ptr(res, C.c_double), _ptr(mx, C.c_double)))
+    def get_patches(self, maximum: bool = True, out=None):
+        """(current resources, maxima) per (patch, ecoregion) entry.  `maximum=False` skips the maxima (they never
+        change; None is returned for them); `out` = a caller-owned float64 array for the resources (e.g. page-locked)."""
+        res = np.zeros(self.n_eco, dtype=np.float64) if out is None else out
+        if res.dtype != np.float64 or res.shape != (self.n_eco,) or not res.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array with one entry per (patch, ecoregion)")
+        mx = np.zeros(self.n_eco, dtype=np.float64) if maximum else None
+        self._check(self._f("get_patches")(self.h, _ptr(res, C.c_double), _ptr(mx, C.c_double) if maximum else None))
         return res, mx
 
     def set_families(self, f: Families):
         c = f.as_c()
         self._check(self._f("set_families")(self.h, C.byref(c)))
 
-    def family_counts(self):
+    def family_counts(self, history: bool = True, adaptation: bool = True):
+        """(families, history entries, adaptation entries); a count that is not asked for is not computed (0)."""
         n, nh, na = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        self._check(self._f("family_counts")(self.h, C.byref(n), C.byref(nh), C.byref(na)))
+        self._check(self._f("family_counts")(self.h, C.byref(n), C.byref(nh) if history else None,
+                                             C.byref(na) if adaptation else None))
         return n.value, nh.value, na.value
 
     def get_families(self, history: bool = True, adaptation: bool = True) -> Families:
-        n, nh, na = self.family_counts()
+        n, nh, na = self.family_counts(history, adaptation)
         f = Families.empty(n, nh if history else 0, na if adaptation else 0)
         if not history:
             f.hist_off = f.hist_patch = f.hist_harvest = None

@@ -164,7 +164,7 @@ int dsim_get_patches(dsim_handle *h, double *res, double *max_res); /* either ma
 
 /* State.families (lib.rs:301) and State.t (lib.rs:308). */
 int dsim_set_families(dsim_handle *h, const dsim_families *f);
-int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *n_adapt);
+int dsim_family_counts(dsim_handle *h, uint64_t *n, uint64_t *n_hist, uint64_t *n_adapt); /* a NULL count is not computed */
 int dsim_get_families(dsim_handle *h, dsim_families *f);  /* arrays sized by dsim_family_counts; NULL members are skipped */
 int dsim_set_time(dsim_handle *h, uint64_t t);
 int dsim_get_time(dsim_handle *h, uint64_t *t);

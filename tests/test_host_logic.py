@@ -46,6 +46,15 @@ def test_family_round_trip(emu, synth):
     out = s.get_families()
     assert not helpers.compare_families(f, out)
     assert s.family_counts() == (n, int(lens.sum()), int(alens.sum()))
+    # counts and columns that are not asked for are not computed; the partial snapshots agree with the full one
+    s.set_families(f)
+    assert s.family_counts(history=False, adaptation=False) == (n, 0, 0)
+    core = s.get_families(history=False, adaptation=False)
+    assert core.hist_off is None and core.adapt_off is None
+    for name, _ in D._FAM_FIELDS:
+        assert (getattr(core, name) == getattr(f, name)).all(), name
+    assert s.family_counts(adaptation=False) == (n, int(lens.sum()), 0)
+    assert not helpers.compare_families(f, s.get_families())  # adaptation fetched after the record columns
 
 
 def test_history_longer_than_ring_keeps_newest(emu, synth):
