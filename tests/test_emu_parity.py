@@ -106,6 +106,20 @@ def test_slow_memory_decay(oracle, emu, synth):
     pc.run_lockstep(o, d, 3, hist_cap=cap)
 
 
+def test_children_with_long_histories(oracle, emu, synth):
+    """A short season makes time_to_grow_adult 361 seasons (lib.rs:1878): a child inherits up to 361 history entries,
+    several 96-entry chunks of k_children, and samples its remembered patches from all of them."""
+    def edit(p):
+        p.season_length_in_years = 1.0 / 24.0
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 600, hist_fill=300, params_edit=edit, hist_cap=420)
+    pc.run_lockstep(o, d, 1, hist_cap=420)
+    f = o.get_families(adaptation=False)
+    born = np.flatnonzero(f.parent_id != pc.D.NO_PARENT)
+    assert len(born) > 3, "scenario must produce children"
+    assert max(int(f.hist_off[i + 1] - f.hist_off[i]) for i in born) > 200, "children must inherit long histories"
+    pc.run_lockstep(o, d, 3, hist_cap=420)
+
+
 def test_parameter_variants(oracle, emu, synth):
     def edit(p):
         p.cooperation_inclusive = 1
