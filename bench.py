@@ -154,7 +154,8 @@ def run_reference(args, cfg_name, cfg):
         return 0
     synth = D.load_synth()
     g, res, mx, fam = build_workload(cfg, args.seed, synth)
-    rate, cores, steps, t_total, per_step = cpu_reference_rate(g, res, mx, fam, args.sim_seed, args.cpu_seconds * max(1, args.steps),
+    budget_s = min(args.cpu_seconds * max(1, args.steps), 150.0)  # at most 2.5 minutes of sampling whatever --steps says
+    rate, cores, steps, t_total, per_step = cpu_reference_rate(g, res, mx, fam, args.sim_seed, budget_s,
                                                                max_steps=args.warmup + args.steps, warm_steps=0)
     # first `warmup` steps are part of the sample only if the budget allowed nothing else
     timed = per_step[args.warmup:] if len(per_step) > args.warmup else per_step
