@@ -404,6 +404,103 @@ int recensus(dsim_handle *h) {
 
 int take_snapshot(dsim_handle *h, bool want_adapt);
 
+/* The reach table built by the device kernels of dsim_reach.cu (DSIM_OPT_REACH_ON_DEVICE).  *built stays false when a
+ * node does not fit the per-warp tables; the caller then builds the table on the host. */
+int build_reach_device(dsim_handle *h, const dsim_graph *g, bool *built) {
+    *built = false;
+    const uint32_t n = g->n_nodes;
+    const uint64_t n_edge = g->edge_off[n];
+    std::vector<void *> tmp;
+    uint64_t *d_eoff;
+    uint32_t *d_edst, *d_lens, *d_stats;
+    double *d_esec;
+    int rc;
+    if ((rc = dev_alloc(h, &d_eoff, (size_t)n + 1, tmp, false)) || (rc = dev_alloc(h, &d_edst, n_edge, tmp, false)) ||
+        (rc = dev_alloc(h, &d_esec, n_edge, tmp, false)) || (rc = dev_alloc(h, &d_lens, (size_t)n * 4, tmp)) ||
+        (rc = dev_alloc(h, &d_stats, 4, tmp)) || (rc = upload(h, d_eoff, g->edge_off, (size_t)n + 1)) ||
+        (rc = upload(h, d_edst, g->edge_dst, n_edge)) || (rc = upload(h, d_esec, g->edge_sec, n_edge))) {
+        free_list(tmp);
+        return rc;
+    }
+    ReachDevGraph dg{d_eoff, d_edst, d_esec, n};
+    ReachDevOut out{d_lens, d_stats, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    dsim_reach_device_pass(0, dg, out, h->geom.n_sm, (void *)h->stream);
+    std::vector<uint32_t> lens((size_t)n * 4);
+    uint32_t stats[4] = {0, 0, 0, 0};
+    if ((rc = download(h, lens.data(), d_lens, (size_t)n * 4)) || (rc = download(h, stats, d_stats, 4)) ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        free_list(tmp);
+        return rc ? rc : fail(h, DSIM_ERR_CUDA, "reach table: the counting pass failed");
+    }
+    if (stats[0] != 0u) { /* a reach set or 2-hop neighbourhood larger than the per-warp tables */
+        free_list(tmp);
+        return DSIM_OK;
+    }
+    /* layout: rows padded to multiples of 8 entries (16-byte aligned starts for every column), as dsim_build_reach */
+    std::vector<HostRowHdr> hdr(n);
+    std::vector<uint32_t> near_off((size_t)n + 1);
+    uint64_t ro = 0, no = 0, n_reach = 0;
+    uint32_t max_row = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        const uint32_t r_len = lens[4 * (size_t)v], n_sensed = lens[4 * (size_t)v + 1], n_near = lens[4 * (size_t)v + 2];
+        if (n_near >= 0xFFFFu) {
+            free_list(tmp);
+            return fail(h, DSIM_ERR_INVALID, "a node has 65535 or more nodes in its 2-hop neighbourhood");
+        }
+        const uint32_t padded = (r_len + 7u) & ~7u;
+        if (ro > 0xFFFFFFF0ull || no > 0xFFFFFFF0ull) break;
+        hdr[v] = HostRowHdr{(uint32_t)ro, padded, n_sensed, n_near};
+        near_off[v] = (uint32_t)no;
+        ro += padded;
+        no += n_near;
+        n_reach += r_len;
+        max_row = std::max(max_row, padded);
+    }
+    if (ro > 0xFFFFFFF0ull || no > 0xFFFFFFF0ull) {
+        free_list(tmp);
+        return fail(h, DSIM_ERR_CAPACITY, "reach table exceeds 2^32 entries");
+    }
+    near_off[n] = (uint32_t)no;
+    RowHdr *d_hdr;
+    uint16_t *d_hash;
+    uint32_t *d_dst, *d_noff, *d_ndst;
+    double *d_cost;
+    if ((rc = dev_alloc(h, &d_hdr, n, h->allocs, false)) || (rc = dev_alloc(h, &d_dst, ro + 8, h->allocs, false)) ||
+        (rc = dev_alloc(h, &d_cost, ro + 8, h->allocs, false)) || (rc = dev_alloc(h, &d_hash, (size_t)n * 256u, h->allocs, false)) ||
+        (rc = dev_alloc(h, &d_noff, (size_t)n + 1, h->allocs, false)) || (rc = dev_alloc(h, &d_ndst, no, h->allocs, false)) ||
+        (rc = upload(h, (HostRowHdr *)d_hdr, hdr.data(), n)) || (rc = upload(h, d_noff, near_off.data(), (size_t)n + 1))) {
+        free_list(tmp);
+        return rc;
+    }
+    out.hdr = (const HostRowHdr *)d_hdr;
+    out.dst = d_dst;
+    out.cost = d_cost;
+    out.hash = d_hash;
+    out.near_off = d_noff;
+    out.near_dst = d_ndst;
+    dsim_reach_device_pass(1, dg, out, h->geom.n_sm, (void *)h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        free_list(tmp);
+        return fail(h, DSIM_ERR_CUDA, "reach table: the fill pass failed");
+    }
+    free_list(tmp);
+    h->n_near = no;
+    h->n_reach = n_reach;
+    h->n_reach_padded = ro;
+    h->max_row = max_row;
+    h->reach_span = std::max(h->reach_span, stats[1]);
+    h->rt.hash = d_hash;
+    h->rt.hdr = d_hdr;
+    h->rt.dst = d_dst;
+    h->rt.cost = d_cost;
+    h->rt.near_off = d_noff;
+    h->rt.near_dst = d_ndst;
+    *built = true;
+    if (std::getenv("DSIM_DEBUG")) std::fprintf(stderr, "[dsim] reach table built on the device: %llu entries, %llu nearby, span %u\n",
+                                                (unsigned long long)n_reach, (unsigned long long)no, h->reach_span);
+    return DSIM_OK;
+}
+
 } // namespace
 
 /* kernels used only by the getters / setters ----------------------------------------------------- */
@@ -706,7 +803,9 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     TRY(dev_alloc(h, &h->ctl, 1, h->allocs));
 
     /* reach table (replaces bounded_dijkstra per family per step and the nearby_cache) */
-    {
+    bool reach_built = false;
+    if (o.flags & DSIM_OPT_REACH_ON_DEVICE) TRY(build_reach_device(h, g, &reach_built));
+    if (!reach_built) {
         HostReach hr;
         std::string err;
         rc = dsim_build_reach(g, &hr, &err);

@@ -1,5 +1,6 @@
 /*
- * dsim_reach.cu — host-side (OpenMP) construction of the reach table, once per graph.
+ * dsim_reach.cu — construction of the reach table, once per graph: on the host (OpenMP, the default) or on the
+ * device (a warp per node; second half of this file).
  *
  * For every node: (a) the set of nodes that a Dijkstra search started there ever assigns a score to
  * while it settles nodes in order of distance and stops at the first one beyond
@@ -11,6 +12,8 @@
  * iteration order is random, the canonical order is ascending.
  */
 #include "dsim_reach.h"
+#include "dsim_rt.h"
+#include "dsim_math.h"
 
 #include <algorithm>
 #include <cmath>
@@ -246,4 +249,256 @@ int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err) {
         }
     }
     return DSIM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * The same table on the device.  One warp per start node.  The search is label-correcting instead of Dijkstra's
+ * ordered one: every node whose tentative distance is within range relaxes its out-edges, again whenever its
+ * distance has improved, until nothing changes.  The fixed point is the same — d(q) = min over predecessors u within
+ * range of d(u) + w(u, q), evaluated in the same floating-point order along every path, and the same set of nodes
+ * ever given a distance (a node relaxes only when its final distance is within range too, since tentative >= final).
+ * ------------------------------------------------------------------------------------------ */
+#define RB_WARPS 2
+#define RB_CAP 512u  /* slots of the per-warp distance table (at most DSIM_REACH_DEV_MAX used) */
+#define NB_CAP 1024u /* slots of the per-warp 2-hop set (at most DSIM_NEAR_DEV_MAX used)       */
+#define RB_EMPTY 0xFFFFFFFFu
+#define RB_INF 0x7FF0000000000000ull
+
+struct ReachWarpMem {
+    unsigned long long dist[RB_CAP]; /* bit patterns of non-negative doubles order like the doubles; later: row keys */
+    unsigned long long done[RB_CAP]; /* distance at which the slot last relaxed its edges; later: compacted distances */
+    uint32_t key[RB_CAP];            /* later: sensed flag of compacted entry i */
+    uint32_t ckey[RB_CAP];           /* compacted keys */
+    uint32_t nset[NB_CAP];
+    uint32_t nkey[DSIM_NEAR_DEV_MAX];
+    uint16_t tbl[256];
+    uint32_t cnt[4]; /* entries in dist table, entries in 2-hop set, unsupported */
+};
+
+__device__ __forceinline__ uint32_t rb_hash(uint32_t q) { return q * 2654435761u; }
+
+template <bool FILL>
+__global__ void __launch_bounds__(RB_WARPS * 32) k_reach_build(ReachDevGraph g, ReachDevOut o, double bound, double cost_per_second) {
+    __shared__ ReachWarpMem mem[RB_WARPS];
+    ReachWarpMem &M = mem[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+
+    for (uint32_t v = gwarp; v < g.n; v += nwarps) {
+        for (uint32_t s = lane; s < RB_CAP; s += 32u) {
+            M.key[s] = RB_EMPTY;
+            M.dist[s] = RB_INF;
+            M.done[s] = ~0ull;
+        }
+        for (uint32_t s = lane; s < NB_CAP; s += 32u) M.nset[s] = RB_EMPTY;
+        for (uint32_t s = lane; s < 256u; s += 32u) M.tbl[s] = 0xFFFFu;
+        if (lane < 4u) M.cnt[lane] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t s = rb_hash(v) & (RB_CAP - 1u);
+            M.key[s] = v;
+            M.dist[s] = 0ull;
+            M.cnt[0] = 1u;
+        }
+        __syncwarp();
+
+        /* ---- distances (movementgraph.rs:64-115) ---- */
+        for (;;) {
+            bool changed = false;
+            for (uint32_t s = lane; s < RB_CAP; s += 32u) {
+                const uint32_t k = M.key[s];
+                if (k == RB_EMPTY) continue;
+                const unsigned long long d = M.dist[s];
+                if (d >= M.done[s]) continue;
+                const double dd = dsim_bits_to_f64(d);
+                if (bound < dd) continue; /* beyond the range: given a distance, but does not relax (the search stops there) */
+                M.done[s] = d;
+                for (uint64_t e = g.edge_off[k]; e < g.edge_off[k + 1]; ++e) {
+                    const uint32_t q = g.edge_dst[e];
+                    const unsigned long long nd = dsim_f64_to_bits(dd + g.edge_sec[e]);
+                    uint32_t slot = rb_hash(q) & (RB_CAP - 1u);
+                    bool have = false;
+                    for (;;) {
+                        const uint32_t cur = *(volatile uint32_t *)&M.key[slot];
+                        if (cur == q) {
+                            have = true;
+                            break;
+                        }
+                        if (cur == RB_EMPTY) {
+                            if (*(volatile uint32_t *)&M.cnt[0] >= DSIM_REACH_DEV_MAX) { /* keeps the table from filling up */
+                                M.cnt[2] = 1u;
+                                break;
+                            }
+                            const uint32_t prev = atomicCAS(&M.key[slot], RB_EMPTY, q);
+                            if (prev == RB_EMPTY) {
+                                atomicAdd(&M.cnt[0], 1u);
+                                have = true;
+                                break;
+                            }
+                            if (prev == q) {
+                                have = true;
+                                break;
+                            }
+                        }
+                        slot = (slot + 1u) & (RB_CAP - 1u);
+                    }
+                    if (have && nd < atomicMin(&M.dist[slot], nd)) changed = true;
+                }
+            }
+            __syncwarp();
+            if (*(volatile uint32_t *)&M.cnt[2] != 0u) break;
+            if (!__any_sync(DSIM_FULL, changed)) break;
+        }
+        /* ---- 2-hop out-neighbourhood (lib.rs:1158-1178) ---- */
+        for (uint64_t e1 = g.edge_off[v]; e1 < g.edge_off[v + 1]; ++e1) {
+            const uint32_t nb = g.edge_dst[e1];
+            for (uint64_t e2 = g.edge_off[nb] + lane; e2 < g.edge_off[nb + 1]; e2 += 32u) {
+                const uint32_t q = g.edge_dst[e2];
+                uint32_t slot = rb_hash(q) & (NB_CAP - 1u);
+                for (;;) {
+                    const uint32_t cur = *(volatile uint32_t *)&M.nset[slot];
+                    if (cur == q) break;
+                    if (cur == RB_EMPTY) {
+                        if (*(volatile uint32_t *)&M.cnt[1] >= DSIM_NEAR_DEV_MAX) {
+                            M.cnt[2] = 1u;
+                            break;
+                        }
+                        const uint32_t prev = atomicCAS(&M.nset[slot], RB_EMPTY, q);
+                        if (prev == RB_EMPTY) {
+                            atomicAdd(&M.cnt[1], 1u);
+                            break;
+                        }
+                        if (prev == q) break;
+                    }
+                    slot = (slot + 1u) & (NB_CAP - 1u);
+                }
+            }
+        }
+        __syncwarp();
+        if (M.cnt[2] != 0u) { /* does not fit the per-warp tables: the caller builds the table on the host */
+            if (lane == 0) atomicOr(&o.stats[0], 1u);
+            __syncwarp();
+            continue;
+        }
+        /* ---- compaction: entries with a normal distance (lib.rs:1147 drops the start node, d = 0) ---- */
+        uint32_t m = 0, nn = 0;
+        for (uint32_t s0 = 0; s0 < RB_CAP; s0 += 32u) {
+            const uint32_t k = M.key[s0 + lane];
+            const unsigned long long d = M.dist[s0 + lane];
+            const uint32_t ex = (uint32_t)(d >> 52) & 0x7FFu;
+            const bool ok = k != RB_EMPTY && ex != 0u && ex != 0x7FFu;
+            const uint32_t mask = __ballot_sync(DSIM_FULL, ok);
+            if (ok) {
+                const uint32_t pos = m + (uint32_t)__popc(mask & lt);
+                M.ckey[pos] = k;
+                M.done[pos] = d;
+            }
+            m += (uint32_t)__popc(mask);
+        }
+        for (uint32_t s0 = 0; s0 < NB_CAP; s0 += 32u) {
+            const uint32_t k = M.nset[s0 + lane];
+            const uint32_t mask = __ballot_sync(DSIM_FULL, k != RB_EMPTY);
+            if (k != RB_EMPTY) M.nkey[nn + (uint32_t)__popc(mask & lt)] = k;
+            nn += (uint32_t)__popc(mask);
+        }
+        __syncwarp();
+        /* sensed = also in the 2-hop set */
+        uint32_t n_sensed = 0, span = 0;
+        for (uint32_t i0 = 0; i0 < m; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            bool sensed = false;
+            if (i < m) {
+                const uint32_t q = M.ckey[i];
+                uint32_t slot = rb_hash(q) & (NB_CAP - 1u);
+                for (;;) {
+                    const uint32_t cur = M.nset[slot];
+                    if (cur == q) {
+                        sensed = true;
+                        break;
+                    }
+                    if (cur == RB_EMPTY) break;
+                    slot = (slot + 1u) & (NB_CAP - 1u);
+                }
+                M.key[i] = sensed ? 1u : 0u;
+                const uint32_t dq = q > v ? q - v : v - q;
+                span = dq > span ? dq : span;
+            }
+            n_sensed += (uint32_t)__popc(__ballot_sync(DSIM_FULL, sensed));
+        }
+        for (uint32_t i = lane; i < nn; i += 32u) {
+            const uint32_t q = M.nkey[i];
+            const uint32_t dq = q > v ? q - v : v - q;
+            span = dq > span ? dq : span;
+        }
+        __syncwarp();
+        if (!FILL) {
+            for (int d = 16; d > 0; d >>= 1) {
+                const uint32_t other = __shfl_xor_sync(DSIM_FULL, span, d);
+                span = other > span ? other : span;
+            }
+            if (lane == 0) {
+                o.lens[4u * v + 0u] = m;
+                o.lens[4u * v + 1u] = n_sensed;
+                o.lens[4u * v + 2u] = nn;
+                o.lens[4u * v + 3u] = 0u;
+                atomicMax(&o.stats[1], span);
+            }
+            __syncwarp();
+            continue;
+        }
+        /* ---- rows: [sensed, ascending][others, ascending][padding]; nearby list ascending ---- */
+        const HostRowHdr hd = o.hdr[v];
+        uint32_t *rowkey = reinterpret_cast<uint32_t *>(M.dist);
+        for (uint32_t i = lane; i < m; i += 32u) {
+            const uint32_t ki = M.ckey[i], si = M.key[i];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < m; ++j) r += (M.key[j] == si && M.ckey[j] < ki) ? 1u : 0u;
+            const uint32_t pos = si ? r : n_sensed + r;
+            o.dst[hd.start + pos] = ki;
+            o.cost[hd.start + pos] = cost_per_second * dsim_bits_to_f64(M.done[i]);
+            rowkey[pos] = ki;
+        }
+        for (uint32_t k = m + lane; k < hd.len; k += 32u) {
+            o.dst[hd.start + k] = 0xFFFFFFFFu;
+            o.cost[hd.start + k] = dsim_bits_to_f64(RB_INF);
+        }
+        const uint32_t n0 = o.near_off[v];
+        for (uint32_t i = lane; i < nn; i += 32u) {
+            const uint32_t ki = M.nkey[i];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < nn; ++j) r += M.nkey[j] < ki ? 1u : 0u;
+            o.near_dst[n0 + r] = ki;
+        }
+        __syncwarp();
+        /* ---- the row's bucket index, filled in row order like the host does (a full bucket overflows into the next) ---- */
+        if (lane == 0 && hd.len <= DSIM_ROW_HASH_MAX) {
+            for (uint32_t k = 0; k < m; ++k) {
+                const uint32_t hsh = (rowkey[k] * 2654435761u) >> 19; /* = dsim_row_hash */
+                uint32_t b = hsh >> 8;
+                for (;;) {
+                    uint32_t s = 0;
+                    while (s < 8u && M.tbl[b * 8u + s] != 0xFFFFu) ++s;
+                    if (s < 8u) {
+                        M.tbl[b * 8u + s] = (uint16_t)(((hsh & 0xFFu) << 8) | k);
+                        break;
+                    }
+                    b = (b + 1u) & 31u;
+                }
+            }
+        }
+        __syncwarp();
+        for (uint32_t s = lane; s < 256u; s += 32u) o.hash[(size_t)v * 256u + s] = M.tbl[s];
+        __syncwarp();
+    }
+}
+
+double dsim_reach_cost_per_second(void) { return 1. / kSecondsPerYear * 3.; }
+
+void dsim_reach_device_pass(int fill, const ReachDevGraph &g, const ReachDevOut &o, uint32_t n_sm, void *stream) {
+    const uint32_t grid = n_sm * 6u; /* 37 KB of shared memory per block */
+    cudaStream_t s = (cudaStream_t)stream;
+    if (fill)
+        DSIM_LAUNCH(k_reach_build<true>, grid, RB_WARPS * 32, 0, s, g, o, kMaxSeasonRange, dsim_reach_cost_per_second());
+    else
+        DSIM_LAUNCH(k_reach_build<false>, grid, RB_WARPS * 32, 0, s, g, o, kMaxSeasonRange, dsim_reach_cost_per_second());
 }

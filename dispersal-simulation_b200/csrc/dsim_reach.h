@@ -30,4 +30,31 @@ static inline uint32_t dsim_row_hash(uint32_t q) { return (q * 2654435761u) >> 1
 
 int dsim_build_reach(const dsim_graph *g, HostReach *out, std::string *err);
 
+/* The same table built on the device (dsim_options.flags & DSIM_OPT_REACH_ON_DEVICE): a warp per node, two passes.
+ * Pass 1 (fill = 0) writes per node {reach entries, sensed entries, nearby entries, 0} to `lens` and
+ * {unsupported, largest |dst - node|, -, -} to `stats`; the caller lays the rows out (offsets, padding) and pass 2
+ * (fill = 1) writes rows, nearby lists and bucket indices.  `unsupported` is raised for a node whose reach set or
+ * 2-hop neighbourhood does not fit the per-warp tables (DSIM_REACH_DEV_MAX / DSIM_NEAR_DEV_MAX entries): the caller
+ * then falls back to dsim_build_reach. */
+#define DSIM_REACH_DEV_MAX 384u
+#define DSIM_NEAR_DEV_MAX 512u
+struct ReachDevGraph {
+    const uint64_t *edge_off;
+    const uint32_t *edge_dst;
+    const double *edge_sec;
+    uint32_t n;
+};
+struct ReachDevOut {
+    uint32_t *lens;  /* [4 n] */
+    uint32_t *stats; /* [4]   */
+    const HostRowHdr *hdr;
+    uint32_t *dst;
+    double *cost;
+    uint16_t *hash;
+    const uint32_t *near_off;
+    uint32_t *near_dst;
+};
+void dsim_reach_device_pass(int fill, const ReachDevGraph &g, const ReachDevOut &o, uint32_t n_sm, void *stream);
+double dsim_reach_cost_per_second(void);
+
 #endif

@@ -24,6 +24,7 @@ SYNTH_LIB_PATH = os.path.join(PKG_ROOT, "libdsim_synth.so")
 
 N_ECOREGIONS = 304
 OPT_PATCH_WARP_ONLY = 0x2
+OPT_REACH_ON_DEVICE = 0x4
 NO_PARENT = 2**64 - 1
 MG_IPC_BYTES = 384
 
