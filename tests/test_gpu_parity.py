@@ -239,3 +239,30 @@ def test_full_size_invariants(gpu_lib, synth):
     from_storage = np.bincount(node.astype(np.int64), weights=size.astype(np.float64), minlength=g.n_nodes)
     assert (per_patch == from_storage).all()
     assert (ra >= 0).all() and (ra <= ma).all()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_random_scenarios(oracle, gpu_lib, synth, case):
+    """Randomly drawn small scenarios (grid, crowding, history length, parameters, graph variants): every state
+    column bit-identical to the oracle after every part of every step."""
+    rng = np.random.default_rng(1000 + case)
+    W, H = int(rng.integers(8, 26)), int(rng.integers(8, 30))
+    n_fam = int(rng.integers(20, 500))
+    n_occ = int(rng.choice([0, 0, max(1, n_fam // 40), max(1, n_fam // 8)]))
+    hist_fill = int(rng.choice([0, 3, 40, 130]))
+    graph_edit = [None, None, pc.sparse_edges_graph, pc.two_ecoregion_graph, pc.long_range_graph(W)][int(rng.integers(0, 5))]
+    fam_edit = [None, None, pc.hostile_cultures(int(rng.integers(2, 9)), seed=case)][int(rng.integers(0, 3))]
+    flags = int(rng.choice([0, 0, pc.D.OPT_PATCH_WARP_ONLY, pc.D.OPT_REACH_ON_DEVICE]))
+
+    def edit(p):
+        p.cooperation_threshold = int(rng.integers(2, 12))
+        p.cooperation_inclusive = int(rng.integers(0, 2))
+        p.fight_deadliness = int(rng.choice([1 << 29, 1 << 31, 3 << 30]))
+        p.culture_mutation_rate = float(rng.choice([6e-3, 0.05, 0.3]))
+        p.resource_recovery_per_season = float(rng.choice([0.05, 0.10, 0.2]))
+        p.minimum_adaptation = float(rng.choice([0.3, 0.5]))
+        if rng.random() < 0.3:
+            p.maximum_resources_one_adult_can_harvest = 0.25
+    o, d = pc.build_pair(oracle, gpu_lib, synth, W, H, n_fam, seed=case + 1, sim_seed=100 + case, n_occupied=n_occ, hist_fill=hist_fill,
+                         params_edit=edit, hist_cap=160, graph_edit=graph_edit, families_edit=fam_edit, flags=flags)
+    pc.run_lockstep(o, d, int(rng.integers(3, 9)), hist_cap=160)
