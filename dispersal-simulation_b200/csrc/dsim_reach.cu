@@ -497,6 +497,7 @@ double dsim_reach_cost_per_second(void) { return 1. / kSecondsPerYear * 3.; }
 void dsim_reach_device_pass(int fill, const ReachDevGraph &g, const ReachDevOut &o, uint32_t n_sm, void *stream) {
     const uint32_t grid = n_sm * 6u; /* 37 KB of shared memory per block */
     cudaStream_t s = (cudaStream_t)stream;
+    (void)s;
     if (fill)
         DSIM_LAUNCH(k_reach_build<true>, grid, RB_WARPS * 32, 0, s, g, o, kMaxSeasonRange, dsim_reach_cost_per_second());
     else

@@ -192,6 +192,13 @@ print("tiny capacities ok")
     assert r.returncode == 0 and "tiny capacities ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_more_families_than_one_scan_pass(oracle, emu, synth):
+    """70 000 families: the count scan at the end of k_lifecycle handles several per-256 blocks per thread, ids and
+    positions of survivors and children come out of multi-level prefixes (lib.rs:541, 551)."""
+    o, d = pc.build_pair(oracle, emu, synth, 120, 160, 70000, hist_cap=32, hist_fill=4)
+    pc.run_lockstep(o, d, 2, hist_cap=32)
+
+
 @pytest.mark.parametrize("case", range(10))
 def test_random_scenarios(oracle, emu, synth, case):
     """Randomly drawn small scenarios (grid, crowding, history length, parameters, graph variants): every state
