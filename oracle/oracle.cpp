@@ -1131,6 +1131,14 @@ double oracle_adapt_touch(double v, double minimum) { return adapt_entry_decay(v
 
 uint32_t oracle_time_till_next_mutation(double u, double rate) { return time_till_next_mutation(u, rate); }
 
+int oracle_will_cooperate(uint64_t a, uint64_t b, uint32_t threshold, int inclusive) {
+    dsim_params p;
+    oracle_default_params(&p);
+    p.cooperation_threshold = threshold;
+    p.cooperation_inclusive = inclusive ? 1 : 0;
+    return will_cooperate(a, b, p) ? 1 : 0;
+}
+
 void oracle_constants(double season, uint32_t *adult_reset, uint32_t *grow_reset, double *range_s, double *cost_per_s,
                       double *decay, uint32_t *n_mem) {
     oracle_handle h;

@@ -77,6 +77,9 @@ double   oracle_exploit_one(int n, const uint32_t *size, const double *adapt, co
 double   oracle_adapt_touch(double v, double minimum);
 /* lib.rs:1270-1272 with U supplied */
 uint32_t oracle_time_till_next_mutation(double u, double rate);
+/* emergence::will_cooperate (missing from lib.rs; call sites lib.rs:958,1010,1212).  Pinned against the reference's own
+ * analysis code, plotting/plot.py:100-101,138: `cultural_distance(c1, c2) < cooperation_threshold` (tests/golden/cooperation.npz) */
+int      oracle_will_cooperate(uint64_t a, uint64_t b, uint32_t threshold, int inclusive);
 /* constants of SURVEY.md appendix A as the oracle evaluates them */
 void     oracle_constants(double season, uint32_t *adult_reset, uint32_t *grow_reset, double *range_s,
                           double *cost_per_s, double *decay, uint32_t *n_mem);

@@ -171,3 +171,20 @@ def test_log_and_mutation_clock(oracle):
     assert oracle.oracle_f64_as_u32(-3.5) == 0
     assert oracle.oracle_f64_as_u32(17.578125) == 17
     assert oracle.oracle_f64_as_u32(1e20) == 0xFFFFFFFF
+
+
+def test_will_cooperate_against_the_reference_analysis_code(oracle):
+    """`emergence::will_cooperate` is missing from lib.rs; the reference's plotting code evaluates the predicate as
+    `cultural_distance(c1, c2) < cooperation_threshold` (plot.py:100-101, 138).  tests/golden/cooperation.npz holds the
+    outputs of those two expressions, executed from plot.py's syntax tree (make_cooperation_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cooperation.npz"))
+    oracle.oracle_will_cooperate.restype = C.c_int
+    oracle.oracle_will_cooperate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]
+    c1, c2, dist, coop = g["c1"], g["c2"], g["distance"], g["cooperate"]
+    assert dist.max() > 20 and (np.bincount(dist)[:12] > 100).all()
+    for k, t in enumerate(g["thresholds"]):
+        strict = np.array([oracle.oracle_will_cooperate(int(a), int(b), int(t), 0) for a, b in zip(c1, c2)], bool)
+        assert (strict == coop[:, k]).all(), f"threshold {t}"
+        incl = np.array([oracle.oracle_will_cooperate(int(a), int(b), int(t), 1) for a, b in zip(c1, c2)], bool)
+        assert (incl == (dist <= t)).all(), f"threshold {t}, inclusive"
