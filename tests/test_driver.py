@@ -54,6 +54,31 @@ def _check_log_protocol(lib, synth, prefix, oracle):
         assert sorted(content) == want, f"POPULATION line of t={t}"
     fo = o.get_families(history=False, adaptation=False)
     assert path[-1][1] == int(fo.location[0])
+    # ... and the reference's own parser expressions (taken out of plot.py's syntax tree, tests/golden/log_parser.json)
+    # read the same out of the log: dispatch on the line prefixes as plot.py:290-370 does
+    import json
+    import re
+    from ast import literal_eval
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "log_parser.json")))
+    bitvec = re.compile(ref["bitvec_pattern"])
+    season = sim.params.season_length_in_years
+    ref_steps, ref_path, timestamp = [], [], None
+    for line in io.StringIO(text):
+        if line.startswith("t: "):
+            timestamp = eval(ref["timestamp_expr"], {"line": line, "season_length_in_years": season, "int": int})
+        elif line.startswith("POPULATION: ["):
+            line = bitvec.sub(ref["bitvec_repl"], line)
+            ref_steps.append((timestamp, eval(ref["content_expr"], {"line": line, "literal_eval": literal_eval, "len": len, "int": int})))
+        elif line.startswith("F:"):
+            match = re.search(ref["f_regex"], line)
+            assert match, line
+            ref_path.append((match.group(1), int(match.group(2))))
+    assert [c for _, c in ref_steps] == [c for _, c in steps]
+    assert [ts for ts, _ in ref_steps] == [t * season for t, _ in steps]
+    assert ref_path == path
+    known = tuple(ref["prefixes"])
+    other = [line for line in io.StringIO(text) if line.strip() and not line.startswith(known)]
+    assert all(re.fullmatch(r"\d+ % \d+\n", line) for line in other), other  # only the `t % store_every` trace of src/cli.rs:142-149
 
 
 def _check_resume(lib, synth, prefix, tmp_path):
