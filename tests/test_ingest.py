@@ -2,6 +2,7 @@
 (src/serialize_graph.rs:9-116), contraction of unpopulated nodes (src/serialize_graph.rs:161-197) and `initialization`
 (lib.rs:1501-1635), then the step loop on that state against the oracle."""
 import ctypes as C
+import os
 import sqlite3
 
 import numpy as np
@@ -130,3 +131,26 @@ def test_initialization_and_steps_gpu(oracle, gpu_lib, synth, tmp_path):
     o, d = _real_pair(oracle, gpu_lib, synth, tmp_path)
     trace = pc.run_lockstep(o, d, 260, by_parts=False, check_every=20)
     assert trace[-1] > 4
+
+
+def test_database_has_the_reference_schema(tmp_path):
+    """The test database has the tables and columns that supplement/distances/database.py declares (fixture generated
+    from its syntax tree, tests/golden/db_schema.json), and the loader queries only columns that exist there."""
+    import json
+    import re
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "db_schema.json")))["tables"]
+    path = str(tmp_path / "network.sqlite")
+    make_db(path)
+    conn = sqlite3.connect(path)
+    sql_type = {"Integer": "INTEGER", "Float": "FLOAT", "Boolean": "BOOLEAN", "String": "VARCHAR"}
+    for table, decl in ref.items():
+        have = conn.execute(f"PRAGMA table_info({table})").fetchall()
+        assert [(c[1], c[2]) for c in have] == [(c["name"], sql_type[c["type"]]) for c in decl["columns"]], table
+        pk = [c[1] for c in sorted(have, key=lambda c: c[5]) if c[5] > 0]
+        want_pk = decl["primary_key_constraint"] or [c["name"] for c in decl["columns"] if c["primary_key"]]
+        assert pk == want_pk, table
+    import inspect
+    src = inspect.getsource(ingest.read_graph_from_db)
+    used = set(re.findall(r"\b(node_id|longitude|latitude|node1|node2|travel_time|ecoregion|population_capacity|node)\b", src))
+    declared = {c["name"] for t in ref.values() for c in t["columns"]}
+    assert used <= declared, used - declared
