@@ -7,7 +7,8 @@ population cap drawn for it is used up or nothing grows any more; then the next 
 neighbouring cell.  Only tests/, tools/bench_gavin.py's CPU leg and __graft_entry__.smoke() may import this module.
 
 PARITY: `dhondt` and `distribute` are pinned against the reference's own functions (tests/golden/make_gavin_golden.py
-imports language.py with a stub `popcaps` module; tests/golden/gavin_*.npz).  Above that level the reference is not
+imports language.py with a stub `popcaps` module; tests/golden/gavin_*.npz), `neighbors_table` and `Member.neighbors`
+against `Grid.gridcell` / `Grid.neighbors` taken out of model.py's syntax tree (make_gavin_grid_golden.py).  Above that level the reference is not
 reproducible (iteration order of Python sets of cell objects, the global numpy generator, inputs that are not in
 the repository: a WorldClim raster at an absolute path, a Binford table outside the tree), so — as for the
 dispersal model — the orders and draws are canonical:

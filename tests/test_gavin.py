@@ -34,6 +34,27 @@ def test_distribute_matches_reference():
         assert left == GOLD["left"][k], k
 
 
+def test_grid_topology_matches_reference():
+    """`Grid.gridcell` / `Grid.neighbors` of the reference (model.py:193-262), executed from model.py's syntax tree
+    (tests/golden/make_gavin_grid_golden.py): the six neighbours in the reference's order with the cell itself where
+    the grid ends, and the default filter (same or no language, capacity of at least 1) on random states."""
+    gold = np.load(os.path.join(REPO, "tests", "golden", "gavin_grid.npz"))
+    assert G.AREA == float(gold["area"])
+    for R, C in gold["shapes"]:
+        R, C = int(R), int(C)
+        assert (G.neighbors_table(R, C) == gold[f"all_{R}x{C}"]).all(), (R, C)
+        popcap, language = gold[f"popcap_{R}x{C}"], gold[f"language_{R}x{C}"]
+        m = G.Member(R, C, popcap, 1.1, 1, [100.0])
+        m.language[:] = language
+        off, flat = gold[f"default_off_{R}x{C}"], gold[f"default_{R}x{C}"]
+        for c in range(2 * R * C):
+            assert m.neighbors(c, int(language[c])) == [int(q) for q in flat[off[c]:off[c + 1]]], (R, C, c)
+    # the published capacity model (model.py:265-267) evaluated the way the callers do
+    p = np.array([10.0, 250.0, 1800.0])
+    want = float(gold["alpha"]) * p ** float(gold["beta"]) * float(gold["area"]) / 1000000
+    assert (G.population_capacity(p, float(gold["alpha"]), float(gold["beta"])) == want).all()
+
+
 def test_philox_kat():
     # Random123 known-answer vector for Philox4x32-10 (same generator as the dispersal model's streams)
     assert G.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF)) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
