@@ -1062,7 +1062,7 @@ __global__ void __launch_bounds__(256) k_scatter(StepArgs a) {
 }
 
 /* ------------------------------------------------------------------------------------------ *
- * part 2c: one warp per occupied node
+ * part 2c: one block per crowded node
  * ------------------------------------------------------------------------------------------ */
 struct PatchMem { /* per-warp working arrays: shared memory, or HBM scratch for crowded nodes */
     uint32_t *idx, *tidx, *size, *band, *bcnt, *btot;

@@ -114,7 +114,7 @@ struct StepScratch {
     uint32_t *plist_one;    /* [cap] occupied nodes with exactly one family (a thread per node)              */
     uint32_t *plist_small;  /* [cap] occupied nodes with 2..8 families (eight lanes per node)                 */
     uint32_t *plist_mid;    /* [cap] occupied nodes with 9..32 families (a warp per node, registers only)    */
-    uint32_t *plist_big;    /* [cap] the others (warp per node, shared memory / HBM scratch)                */
+    uint32_t *plist_big;    /* [cap] the others (a block per node, shared memory / HBM scratch)             */
     ChildTask *child_task;  /* [cap] indexed by child rank                                          */
     /* patch-kernel spill arrays for nodes with more families than fit in shared memory, indexed
      * by segment position */

@@ -130,7 +130,7 @@ typedef struct dsim_options {
     uint32_t use_graphs;       /* 1 = replay the step as a CUDA graph (default), 0 = plain launches */
     uint32_t flags;            /* DSIM_OPT_* test knobs, 0 by default */
 } dsim_options;
-#define DSIM_OPT_PATCH_WARP_ONLY 0x2u /* every occupied node takes the warp-per-node kernel */
+#define DSIM_OPT_PATCH_WARP_ONLY 0x2u /* every occupied node takes the block-per-node kernel (k_patch) */
 #define DSIM_OPT_REACH_ON_DEVICE 0x4u /* build the reach table with the device kernels (falls back to the host builder for
                                         * graphs with reach sets of more than 384 or 2-hop sets of more than 512 nodes) */
 
