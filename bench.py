@@ -65,7 +65,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.stop_flag, self.th = gpu_index, False, None
-        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.sm, self.ts, self.reasons, self.sm_max = [], [], set(), None
 
     def _loop(self):
         try:
@@ -80,12 +80,13 @@ class ClockSampler:
             bits = {k: getattr(N, v, getattr(N, legacy[k], 0)) for k, v in names.items()}
             get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag:
+                self.ts.append(time.perf_counter())
                 self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
                 r = get(h)
                 for k, b in bits.items():
                     if b and (r & b):
                         self.reasons.add(k)
-                time.sleep(0.002)
+                time.sleep(0.0002)
         except Exception as e:  # NVML missing: report no samples rather than fail the bench
             self.err = repr(e)
 
@@ -94,13 +95,20 @@ class ClockSampler:
         self.th = threading.Thread(target=self._loop, daemon=True)
         self.th.start()
 
-    def stop(self):
+    def stop(self, timed=None):
+        """timed = (t0, t1) perf_counter bounds of the timed region: the median is taken over the samples that fall
+        inside it when there are any (a 20-step region lasts a few milliseconds), else over the whole window the
+        sampler ran (warm-up + timed steps, the GPU busy throughout); `window` says which."""
         self.stop_flag = True
         if self.th is not None:
             self.th.join(timeout=2)
-        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm)}
-        if self.sm:
-            out["sm_mhz"] = statistics.median(self.sm)
+        n = min(len(self.sm), len(self.ts))
+        inside = [self.sm[i] for i in range(n) if timed and timed[0] <= self.ts[i] <= timed[1]]
+        use, window = (inside, "timed region") if inside else (self.sm[:n], "warm-up + timed region")
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(use),
+               "samples_in_timed_region": len(inside), "window": window}
+        if use:
+            out["sm_mhz"] = statistics.median(use)
         return out
 
 
@@ -115,15 +123,33 @@ def build_workload(cfg, seed, synth):
 
 
 def load_oracle():
-    subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle")], check=True, stdout=subprocess.DEVNULL)
-    lib = C.CDLL(os.path.join(REPO, "oracle", "liboracle.so"))
+    """The CPU arm's library and how it was built.  BASELINE.md times the CPU baseline with -O3 -march=native: that
+    variant is compiled here, on the host that is timed (it cannot be shipped: the development container's CPU is not
+    the GPU box's); the portable -O3 build that travels with the snapshot is the fall-back."""
+    odir = os.path.join(REPO, "oracle")
+    build = "-O3 -march=native -ffp-contract=off, OpenMP"
+    try:
+        subprocess.run(["make", "-s", "-C", odir, "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        lib = C.CDLL(os.path.join(odir, "liboracle_native.so"))
+    except Exception:
+        subprocess.run(["make", "-s", "-C", odir], check=True, stdout=subprocess.DEVNULL)
+        lib = C.CDLL(os.path.join(odir, "liboracle.so"))
+        build = "-O3 -march=x86-64-v3 -ffp-contract=off, OpenMP (native build failed on this host)"
     lib.oracle_set_mode.argtypes = [C.c_void_p, C.c_int]
-    return lib
+    lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_set_threads.restype = C.c_int
+    return lib, build
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0))
 
 
 def cpu_reference_rate(g, res, mx, fam, seed, budget_s, max_steps, warm_steps=0):
-    """family-updates/s of the oracle port in reference-shaped mode on all host cores."""
-    lib = load_oracle()
+    """family-updates/s of the oracle port in reference-shaped mode on all host cores (set explicitly: a launcher's
+    OMP_NUM_THREADS — torch.distributed.run exports 1 — does not apply to the CPU arm)."""
+    lib, build = load_oracle()
+    cores = lib.oracle_set_threads(host_cores())
     s = D.Sim(lib, g, seed=seed, prefix="oracle_")
     lib.oracle_set_mode(s.h, 0)
     s.set_patches(res, mx)
@@ -141,35 +167,81 @@ def cpu_reference_rate(g, res, mx, fam, seed, budget_s, max_steps, warm_steps=0)
         updates += st.family_updates
         steps += 1
     s.close()
-    cores = len(os.sched_getaffinity(0))
-    omp = os.environ.get("OMP_NUM_THREADS")
-    if omp:
-        cores = min(cores, int(omp))
-    return updates / t_total, cores, steps, t_total, per_step
+    return updates / t_total, cores, steps, t_total, per_step, build
+
+
+METRIC = "family-updates/sec (whole job over n_gpus; per_gpu_value = per GPU)"
+
+
+def config_of(cfg_name, cfg, seed, world):
+    """The `config` object of the JSON line — identical in both arms for the same command line."""
+    W, H, n_fam, n_occ, hist_fill = cfg
+    return {"workload": f"{cfg_name}: {W}x{H} hex grid ({W * H} patches), {n_fam} families in total, "
+                        f"hist_fill {hist_fill}, seed {seed}",
+            "l2": "working set (reach table 3.7 GB + views 64 MB + histories) exceeds the 126 MB L2; no flush",
+            "parallelism": "1 GPU" if world == 1 else f"{world} latitude bands of about equal family counts, halo + migrant "
+                                                      f"exchange every step, {n_fam} families in total"}
 
 
 def run_reference(args, cfg_name, cfg):
+    """The reference arm: the reference algorithm's CPU implementation (oracle port, reference-shaped mode) on all host
+    cores, same workload as the GPU arm at this N (families scaled by N like there), exactly --warmup + --steps steps.
+    When the full workload would not finish in a few minutes, every step runs on a bounded sample of it: the same grid
+    with fewer families drawn by the same generator (the cost of a family-update in this mode is the bounded Dijkstra
+    and the memory loop of that family, lib.rs:843-866, and does not depend on how many other families there are)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)
+    if world > 1:
+        cfg = (cfg[0], cfg[1], cfg[2] * world, cfg[3], cfg[4])
     synth = D.load_synth()
     g, res, mx, fam = build_workload(cfg, args.seed, synth)
-    budget_s = min(args.cpu_seconds * max(1, args.steps), 150.0)  # at most 2.5 minutes of sampling whatever --steps says
-    rate, cores, steps, t_total, per_step = cpu_reference_rate(g, res, mx, fam, args.sim_seed, budget_s,
-                                                               max_steps=args.warmup + args.steps, warm_steps=0)
-    # first `warmup` steps are part of the sample only if the budget allowed nothing else
-    timed = per_step[args.warmup:] if len(per_step) > args.warmup else per_step
+    lib, build = load_oracle()
+    cores = lib.oracle_set_threads(host_cores())
+    budget_s = 150.0
+    n_steps = args.warmup + args.steps
+
+    def make(families):
+        sim = D.Sim(lib, g, seed=args.sim_seed, prefix="oracle_")
+        lib.oracle_set_mode(sim.h, 0)
+        sim.set_patches(res, mx)
+        sim.set_families(families)
+        return sim
+    # calibration: one step of the full workload
+    sim = make(fam)
+    t0 = time.perf_counter()
+    sim.step(1, allow_model_errors=True)
+    t1 = time.perf_counter() - t0
+    sim.close()
+    n_sample = cfg[2]
+    if t1 * n_steps > budget_s:
+        n_sample = max(10_000, int(cfg[2] * budget_s / (t1 * n_steps)))
+        fam = D.synth_families(cfg[0], cfg[1], n_sample, args.seed, n_occupied=min(cfg[3], n_sample), hist_fill=cfg[4], lib=synth)
+    log(f"[bench] reference arm: one full step {t1:.2f} s on {cores} threads; {n_steps} steps on {n_sample} of {cfg[2]} families")
+    sim = make(fam)
+    per_step, updates = [], []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        st = sim.step(1, allow_model_errors=True)
+        per_step.append(time.perf_counter() - t0)
+        updates.append(st.family_updates)
+    sim.close()
+    timed, upd = per_step[args.warmup:], updates[args.warmup:]
+    rate = sum(upd) / sum(timed)
     ms = 1000.0 * sum(timed) / len(timed)
+    sample = (f"{args.steps} steps after {args.warmup} warm-up steps on "
+              + ("the whole workload" if n_sample == cfg[2] else f"a sample of {n_sample} of the {cfg[2]} families (same grid, same generator)")
+              + f", {sum(timed):.1f} s; built {build}")
     line = {
-        "impl": "reference", "metric": "family-updates/sec/GPU", "value": rate, "unit": "family-updates/s",
-        "n_gpus": args.gpus, "steps": len(timed), "warmup": min(args.warmup, len(per_step) - len(timed)),
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "family-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{cfg_name}: {cfg[0]}x{cfg[1]} hex grid, {cfg[2]} families, hist_fill {cfg[4]}",
-                   "note": "CPU arm: C++ port of the reference algorithm (reference-shaped: Dijkstra per family per "
-                           "decision), OpenMP"},
-        "cpu_baseline": {"value": rate, "unit": "family-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of the same workload ({t_total:.1f} s)"},
+        "config": config_of(cfg_name, cfg, args.seed, world),
+        "note": "CPU arm: C++ port of the reference algorithm (reference-shaped: one bounded Dijkstra per family per "
+                "decision, dense 304-entry adaptation vectors), OpenMP over the reference's rayon sites",
+        "cpu_baseline": {"value": rate, "unit": "family-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "family-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -296,17 +368,23 @@ def main():
             dist.all_gather_object(handles, sim.mg_ipc_export())
             sim.mg_ipc_connect(handles)
 
-    launches0 = sim.launch_count()
+    transport = "single GPU"
+    if world > 1:
+        transport = ("peer-memory stores over NVLink (CUDA IPC) for the SPLIT / EMIGRANTS / HALO exchanges of a step; NCCL "
+                     "for set-up" if os.environ.get("DSIM_MG_TRANSPORT", "peer") == "peer"
+                     else "NCCL point-to-point (grouped send/recv) + all-gather")
     barrier()
+    sampler = ClockSampler(local_rank)   # samples from the warm-up on: the timed region of a 20-step run lasts milliseconds
+    sampler.start()
     st_w = sim.step(args.warmup, want_stats=True, allow_model_errors=True)
     log(f"[bench] rank {rank}: {st_w.live_families} live families after {args.warmup} warm-up steps")
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches1 = sim.launch_count()
+    t_timed0 = time.perf_counter()
     st, dev_ms = sim.step_timed(args.steps)
+    t_timed1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop((t_timed0, t_timed1))
     launches2 = sim.launch_count()
     t = torch.tensor([dev_ms, float(st.family_updates)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -361,14 +439,17 @@ def main():
         # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (per family-update there,
         # scaled to this run's launch size)
         traffic, traffic_src = None, None
-        try:
-            with open(os.path.join(REPO, "profiles", "r01_k_move_ncu.json")) as f:
-                ncu = json.load(f)
-            if top == "k_move":
-                traffic = ncu["dram_bytes_per_family_update"] * upd_per_launch
-                traffic_src = "profiles/r01_k_move_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum per family-update x families per launch"
-        except Exception:
-            pass
+        for name in ("r02_k_move_ncu.json", "r01_k_move_ncu.json"):   # newest capture of the kernel in the timed regime
+            try:
+                with open(os.path.join(REPO, "profiles", name)) as f:
+                    ncu = json.load(f)
+                if top == "k_move":
+                    traffic = ncu["dram_bytes_per_family_update"] * upd_per_launch
+                    traffic_src = (f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum per family-update "
+                                   f"(captured at rho = {ncu.get('rho', '?')}) x families per launch")
+                break
+            except Exception:
+                continue
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_family_update": b_move if top == "k_move" else None, "terms": parts}
@@ -412,6 +493,13 @@ def main():
                 f"{1e3 * (t2 - t1):.1f} + download {1e3 * (t0 + dt - t2):.1f}")
             reps.append((dt, upd))
         dt, upd = sorted(reps)[1]
+        dt_best = min(r[0] for r in reps)
+        # the same K steps with the per-step stats read-back, state already resident (no upload, no download)
+        t0 = time.perf_counter()
+        upd_s = 0
+        for _ in range(n_steps_e2e):
+            upd_s += sim.step(1, allow_model_errors=True).family_updates
+        dt_steps = time.perf_counter() - t0
         h2d = (res.nbytes + mx.nbytes + sum(getattr(fam, n).nbytes for n, _ in D._FAM_FIELDS) + fam.hist_patch.nbytes
                + fam.hist_harvest.nbytes + fam.hist_off.nbytes)
         d2h = sum(getattr(out, n).nbytes for n, _ in D._FAM_FIELDS) + r_out.nbytes + n_steps_e2e * C.sizeof(D.StepStats)
@@ -426,28 +514,30 @@ def main():
                "d2h_bytes_per_step": d2h / n_steps_e2e, "steps": n_steps_e2e,
                "what": "dsim_set_patches + dsim_set_families from pinned host arrays, steps with per-step stats read-back, "
                        "dsim_get_families (core columns) + dsim_get_patches, wall clock; median of 3 repetitions",
-               "repetitions_ms": [round(1e3 * r[0], 2) for r in reps]}
+               "repetitions_ms": [round(1e3 * r[0], 2) for r in reps],
+               "value_best": upd / dt_best,
+               "steps_only_value": upd_s / dt_steps,
+               "steps_only_what": "the same number of single steps through dsim_step with the stats read back after each "
+                                  "(cli.rs:138), state resident: no upload, no download"}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, steps_cpu, t_cpu, _ = cpu_reference_rate(g, res, mx, fam, args.sim_seed, args.cpu_seconds, max_steps=20)
+        rate, cores, steps_cpu, t_cpu, _, build = cpu_reference_rate(g, res, mx, fam, args.sim_seed, args.cpu_seconds, max_steps=20)
         cpu = {"value": rate, "unit": "family-updates/s", "cores": cores, "kind": "port",
                "sample": f"first {steps_cpu} steps of the same workload, oracle in reference-shaped mode "
-                         f"(Dijkstra per family per decision), {t_cpu:.1f} s"}
+                         f"(Dijkstra per family per decision), {t_cpu:.1f} s; built {build}"}
 
     if rank == 0:
-        W, H, n_fam, n_occ, hist_fill = cfg
         line = {
-            "metric": "family-updates/sec/GPU", "value": value, "unit": "family-updates/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "family-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{cfg_name}: {W}x{H} hex grid ({W * H} patches), {n_fam} families in total, "
-                                   f"hist_fill {hist_fill}, seed {args.seed}",
-                       "l2": "working set (reach table 3.7 GB + views 64 MB + histories) exceeds the 126 MB L2; no flush",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} latitude bands, NCCL halo + migrant exchange, {cfg[2]} families in total",
-                       "cuda_graphs": not args.no_graphs,
-                       "live_families_end": int(fam_live)},
+            "config": config_of(cfg_name, cfg, args.seed, world),
+            "transport": transport,
+            "cuda_graphs": not args.no_graphs,
+            "live_families_end": int(fam_live),
+            "family_updates_timed": int(updates_all),
             "per_gpu_value": value / world,
             "clocks": clocks,
             "roofline": roofline,

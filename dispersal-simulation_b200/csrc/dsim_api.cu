@@ -98,7 +98,6 @@ struct dsim_handle {
     bool profiling = false;
     cudaEvent_t ev[DSIM_K_COUNT + 1] = {};
     cudaEvent_t tev[2] = {};
-    uint64_t timed_births0 = 0, timed_deaths0 = 0, timed_updates0 = 0;
     double k_ms[DSIM_K_COUNT] = {};
     uint64_t k_launches[DSIM_K_COUNT] = {};
     uint64_t total_launches = 0;
@@ -1072,7 +1071,6 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     h->total_launches += 1;
     h->n_known = n;
     h->steps_since_check = 0;
-    h->timed_births0 = h->timed_deaths0 = h->timed_updates0 = 0;
     if ((rc = recensus(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
@@ -1428,25 +1426,24 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
 
 int dsim_step_timed(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats, double *device_ms) {
     if (!h || !stats || !device_ms) return DSIM_ERR_INVALID;
-    CK(cudaStreamSynchronize(h->stream));
+    /* the counters at the entry of THIS call: births, deaths and family_updates cover exactly the n_steps timed steps,
+     * whatever ran before (warm-up steps through dsim_step included) */
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    const uint64_t b0 = h->ctl_h->births, d0 = h->ctl_h->deaths, u0 = h->ctl_h->updates;
     CK(cudaEventRecord(h->tev[0], h->stream));
     /* enqueue without the final read-back, then close the timed region on the device */
-    int rc = dsim_step(h, n_steps, nullptr);
+    rc = dsim_step(h, n_steps, nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->tev[1], h->stream));
     CK(cudaEventSynchronize(h->tev[1]));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]));
     *device_ms = ms;
-    /* dsim_step(.., stats) reports deltas from its own start; recompute them over the timed call */
-    const uint64_t b0 = h->timed_births0, d0 = h->timed_deaths0, u0 = h->timed_updates0;
-    rc = dsim_step(h, 0, stats);
+    rc = dsim_step(h, 0, stats); /* reads the counters back; its own deltas are zero */
     stats->births = h->ctl_h->births - b0;
     stats->deaths = h->ctl_h->deaths - d0;
     stats->family_updates = h->ctl_h->updates - u0;
-    h->timed_births0 = h->ctl_h->births;
-    h->timed_deaths0 = h->ctl_h->deaths;
-    h->timed_updates0 = h->ctl_h->updates;
     return rc;
 }
 

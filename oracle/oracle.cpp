@@ -17,6 +17,9 @@
  */
 #include "oracle.h"
 
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -843,6 +846,19 @@ int oracle_set_mode(oracle_handle *h, int mode) {
     if (!h || mode < 0 || mode > 1) return DSIM_ERR_INVALID;
     h->mode = mode;
     return DSIM_OK;
+}
+
+/* OpenMP threads of the oracle's parallel loops (the rayon sites of lib.rs:527,607,615,1813).  n <= 0 restores the
+ * runtime's default; returns the number of threads the next parallel region will use.  bench.py sets it explicitly:
+ * torch.distributed.run exports OMP_NUM_THREADS=1 into every rank. */
+int oracle_set_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 int oracle_set_patches(oracle_handle *h, const double *res, const double *max_res) {

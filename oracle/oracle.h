@@ -40,6 +40,9 @@ const char *oracle_last_error(const oracle_handle *h);
  *        used by the tests at sizes where mode 0 would take minutes. */
 int oracle_set_mode(oracle_handle *h, int mode);
 
+/* threads of the OpenMP loops (n <= 0: the runtime's default); returns the number that will be used */
+int oracle_set_threads(int n);
+
 int oracle_set_patches(oracle_handle *h, const double *res, const double *max_res);
 int oracle_get_patches(oracle_handle *h, double *res, double *max_res);
 int oracle_set_families(oracle_handle *h, const dsim_families *f);

@@ -123,3 +123,48 @@ def compare_sims(oracle: D.Sim, dev: D.Sim, rtol=0.0, hist_cap=None, what=""):
     if oracle.get_time() != dev.get_time():
         msgs.append(f"{what}: t differs: {oracle.get_time()} vs {dev.get_time()}")
     return msgs
+
+
+def compare_sims_bulk(oracle: D.Sim, dev: D.Sim, what=""):
+    """compare_sims for states of 10^5..10^6 families: whole-array comparisons only (no per-family Python loop), all
+    bit-exact.  Requires that the device's history ring has not wrapped (history_capacity >= the longest history),
+    so that both sides report the same entries."""
+    msgs = []
+    a, b = oracle.get_families(), dev.get_families()
+    if a.n != b.n:
+        return [f"{what}: family count {a.n} vs {b.n}"]
+    for name in INT_FIELDS + FLOAT_FIELDS:
+        x, y = getattr(a, name), getattr(b, name)
+        bad = np.nonzero(x.view(np.uint8).reshape(len(x), -1) != y.view(np.uint8).reshape(len(y), -1))[0]
+        if len(bad):
+            i = int(bad[0])
+            msgs.append(f"{what}: {name} differs at {len(np.unique(bad))} families, first i={i} id={int(a.id[i])}: {x[i]!r} vs {y[i]!r}")
+    for off, cols in (("hist_off", ("hist_patch", "hist_harvest")), ("adapt_off", ("adapt_eco", "adapt_val"))):
+        xo, yo = getattr(a, off), getattr(b, off)
+        if len(xo) != len(yo) or (xo != yo).any():
+            msgs.append(f"{what}: {off} differs")
+            continue
+        n = int(xo[-1])
+        for c in cols:
+            x, y = getattr(a, c)[:n], getattr(b, c)[:n]
+            if x.dtype == np.float64:
+                bad = np.nonzero(x.view(np.uint64) != y.view(np.uint64))[0]
+            else:
+                bad = np.nonzero(x != y)[0]
+            if len(bad):
+                k = int(bad[0])
+                i = int(np.searchsorted(xo, k, side="right") - 1)
+                msgs.append(f"{what}: {c} differs at {len(bad)} entries, first in family i={i} id={int(a.id[i])}: {x[k]!r} vs {y[k]!r}")
+    ra, _ = oracle.get_patches()
+    rb, _ = dev.get_patches()
+    bad = np.nonzero(ra.view(np.uint64) != rb.view(np.uint64))[0]
+    if len(bad):
+        k = int(bad[0])
+        msgs.append(f"{what}: patch resources differ at {len(bad)} entries, first {k}: {ra[k]!r} vs {rb[k]!r}")
+    na, ca, sa = oracle.get_storage()
+    nb, cb, sb = dev.get_storage()
+    if len(na) != len(nb) or (na != nb).any() or (ca != cb).any() or (sa != sb).any():
+        msgs.append(f"{what}: storage differs: {len(na)} vs {len(nb)} entries")
+    if oracle.get_time() != dev.get_time():
+        msgs.append(f"{what}: t differs: {oracle.get_time()} vs {dev.get_time()}")
+    return msgs

@@ -266,3 +266,57 @@ def test_random_scenarios(oracle, gpu_lib, synth, case):
     o, d = pc.build_pair(oracle, gpu_lib, synth, W, H, n_fam, seed=case + 1, sim_seed=100 + case, n_occupied=n_occ, hist_fill=hist_fill,
                          params_edit=edit, hist_cap=160, graph_edit=graph_edit, families_edit=fam_edit, flags=flags)
     pc.run_lockstep(o, d, int(rng.integers(3, 9)), hist_cap=160)
+
+
+def _full_size_pair(oracle, gpu_lib, synth, W, H, n_fam, n_occ, hist_fill, flags=0):
+    """The named BASELINE.json configuration on both sides.  The oracle runs in its reference-shaped mode (one bounded
+    Dijkstra per family per decision, lib.rs:843) with OpenMP on all host cores: 0.4 s per step at C2 on 16 cores."""
+    import os
+    g, res, mx = pc.D.synth_grid(W, H, 1, lib=synth)
+    fam = pc.D.synth_families(W, H, n_fam, 1, n_occupied=n_occ, hist_fill=hist_fill, lib=synth)
+    oracle.oracle_set_threads.argtypes = [helpers.C.c_int]
+    oracle.oracle_set_threads(len(os.sched_getaffinity(0)))
+    o = helpers.oracle_sim(oracle, g, seed=7, mode=0)
+    opt = pc.D.Options()
+    gpu_lib.dsim_default_options(opt)
+    opt.flags = flags
+    d = pc.D.Sim(gpu_lib, g, seed=7, options=opt)
+    for s in (o, d):
+        s.set_patches(res, mx)
+        s.set_families(fam)
+    return o, d
+
+
+def _lockstep_bulk(o, d, steps, what):
+    for k in range(steps):
+        so, sd = o.step(1, allow_model_errors=True), d.step(1, allow_model_errors=True)
+        assert so.as_dict() == sd.as_dict(), (what, k, so.as_dict(), sd.as_dict())
+        msgs = helpers.compare_sims_bulk(o, d, what=f"{what} step {k}")
+        assert not msgs, "\n".join(msgs)
+    return so
+
+
+def test_c2_full_size_vs_oracle(oracle, gpu_lib, synth):
+    """BASELINE.json configs[1] at its real size — 1155x1732 patches, 100k families, 625-entry histories — three steps,
+    every column of the state bit-identical to the oracle after each (625 + 3 entries still fit the 628-entry ring)."""
+    o, d = _full_size_pair(oracle, gpu_lib, synth, 1155, 1732, 100_000, 0, 625)
+    st = _lockstep_bulk(o, d, 3, "C2")
+    assert st.live_families > 50_000 and st.model_errors == 0
+
+
+def test_c3_one_step_vs_oracle(oracle, gpu_lib, synth):
+    """BASELINE.json configs[2]: the same grid with 1M families; one step against the oracle.  Histories of 128 entries
+    (the head of the memory loop and the start of its tail) keep the oracle's array-of-structs state at ~5 GB."""
+    o, d = _full_size_pair(oracle, gpu_lib, synth, 1155, 1732, 1_000_000, 0, 128)
+    st = _lockstep_bulk(o, d, 1, "C3")
+    assert st.live_families > 500_000
+
+
+def test_c4_shaped_dense_coresidence_vs_oracle(oracle, gpu_lib, synth):
+    """BASELINE.json configs[3] in shape: dense co-residence, mean 8 families per occupied patch with a geometric tail
+    (200k families on 25k of 135k patches), two steps against the oracle — the harvest-competition-bound regime."""
+    o, d = _full_size_pair(oracle, gpu_lib, synth, 300, 450, 200_000, 25_000, 64)
+    f = o.get_families(history=False, adaptation=False)
+    c = np.unique(f.location, return_counts=True)[1]
+    assert 7.0 < c.mean() < 9.0 and c.max() > 32
+    _lockstep_bulk(o, d, 2, "C4-shaped")

@@ -146,3 +146,19 @@ def test_stats_accumulate_per_call(oracle, emu, synth):
     for k in (1, 3, 7):
         so, sd = o.step(k), d.step(k)
         assert so.as_dict() == sd.as_dict()
+
+
+def test_step_timed_counts_only_its_own_steps(oracle, emu, synth):
+    """dsim_step_timed reports the births, deaths and family-updates of exactly the steps it ran, whatever ran before
+    it (bench.py warms up with dsim_step and then times: the warm-up's updates must not be in `value`)."""
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 200, hist_cap=64)
+    o.step(5)
+    d.step(5, want_stats=False)                       # warm-up without a read-back, as bench.py enqueues it
+    so = o.step(20)
+    sd, ms = d.step_timed(20)
+    assert ms >= 0.0
+    assert (sd.family_updates, sd.births, sd.deaths) == (so.family_updates, so.births, so.deaths)
+    assert sd.live_families == so.live_families and sd.t == so.t == 25
+    so2 = o.step(3)                                   # and again, after a stats-carrying call
+    sd2, _ = d.step_timed(3)
+    assert (sd2.family_updates, sd2.births, sd2.deaths) == (so2.family_updates, so2.births, so2.deaths)
