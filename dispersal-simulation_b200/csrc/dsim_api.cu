@@ -503,6 +503,19 @@ int build_reach_device(dsim_handle *h, const dsim_graph *g, bool *built) {
 } // namespace
 
 /* kernels used only by the getters / setters ----------------------------------------------------- */
+__global__ void k_digest32(const uint32_t *w, uint64_t n, unsigned long long *acc) {
+    /* sum over i of mix(i, w[i]) mod 2^64: independent of the order in which threads add */
+    uint64_t s = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (i << 32) ^ (i >> 32) ^ ((uint64_t)w[i] * 0x9E3779B97F4A7C15ull);
+        x ^= x >> 29;
+        x *= 0xBF58476D1CE4E5B9ull;
+        x ^= x >> 32;
+        s += x;
+    }
+    atomicAdd(acc, (unsigned long long)s);
+}
+
 __global__ void k_pack_adaptation(FamHeavy hv, const uint32_t *hs_of, uint32_t n, double minimum, uint16_t *out_eco,
                                   double *out_val, uint32_t *out_n) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -803,7 +816,12 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
 
     /* reach table (replaces bounded_dijkstra per family per step and the nearby_cache) */
     bool reach_built = false;
-    if (o.flags & DSIM_OPT_REACH_ON_DEVICE) TRY(build_reach_device(h, g, &reach_built));
+#if defined(DSIM_EMU)
+    const bool reach_on_device = (o.flags & DSIM_OPT_REACH_ON_DEVICE) != 0; /* the CPU debugging build keeps the host builder */
+#else
+    const bool reach_on_device = !(o.flags & DSIM_OPT_REACH_ON_HOST);
+#endif
+    if (reach_on_device) TRY(build_reach_device(h, g, &reach_built));
     if (!reach_built) {
         HostReach hr;
         std::string err;
@@ -1508,6 +1526,28 @@ int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst, uint6
     if (near_off) near_off[n] = noff[n];
     if (reach_off) reach_off[n] = w;
     return DSIM_OK;
+}
+
+int dsim_reach_digest(dsim_handle *h, uint64_t out[5]) {
+    if (!h || !out) return DSIM_ERR_INVALID;
+    std::vector<void *> tmp;
+    unsigned long long *acc = nullptr;
+    int rc = dev_alloc(h, &acc, 5, tmp);
+    if (rc) return rc;
+    const struct { const void *p; uint64_t words; } part[5] = {
+        {h->rt.hdr, (uint64_t)h->n_nodes * 4u},       {h->rt.dst, h->n_reach_padded},
+        {h->rt.cost, h->n_reach_padded * 2u},         {h->rt.hash, (uint64_t)h->n_nodes * 128u},
+        {h->rt.near_dst, h->n_near}};
+    for (int k = 0; k < 5; ++k)
+        DSIM_LAUNCH(k_digest32, h->geom.n_sm * 8, 256, 0, h->stream, (const uint32_t *)part[k].p, part[k].words, acc + k);
+    DSIM_LAUNCH(k_digest32, h->geom.n_sm * 8, 256, 0, h->stream, (const uint32_t *)h->rt.near_off, (uint64_t)h->n_nodes + 1u, acc + 4);
+    h->total_launches += 6;
+    unsigned long long host[5];
+    rc = download(h, host, (const unsigned long long *)acc, 5);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in dsim_reach_digest");
+    free_list(tmp);
+    for (int k = 0; k < 5; ++k) out[k] = host[k];
+    return rc;
 }
 
 int dsim_profile_enable(dsim_handle *h, int on) {

@@ -25,6 +25,7 @@ SYNTH_LIB_PATH = os.path.join(PKG_ROOT, "libdsim_synth.so")
 N_ECOREGIONS = 304
 OPT_PATCH_WARP_ONLY = 0x2
 OPT_REACH_ON_DEVICE = 0x4
+OPT_REACH_ON_HOST = 0x8
 NO_PARENT = 2**64 - 1
 MG_IPC_BYTES = 384
 
@@ -272,6 +273,8 @@ class Sim:
             "reach_counts": (C.c_int, [vp, u64p, u64p]),
             "get_reach": (C.c_int, [vp, u64p, u32p, u64p, u32p, f64p]),
         }
+        if self.prefix == "dsim_":
+            sig["reach_digest"] = (C.c_int, [vp, u64p])
         for name, (res, args) in sig.items():
             fn = self._f(name)
             fn.restype, fn.argtypes = res, args
@@ -424,6 +427,13 @@ class Sim:
                                          _ptr(reach_off, C.c_uint64), _ptr(reach_dst, C.c_uint32),
                                          _ptr(reach_cost, C.c_double)))
         return near_off, near_dst[:a.value], reach_off, reach_dst[:b.value], reach_cost[:b.value]
+
+    def reach_digest(self):
+        """Five order-independent digests of the reach table in HBM (headers, destinations, costs, bucket indices,
+        2-hop lists)."""
+        out = (C.c_uint64 * 5)()
+        self._check(self._f("reach_digest")(self.h, out))
+        return tuple(int(x) for x in out)
 
     # -- multi-GPU (band partition; include/dsim.h) ---------------------------------------------
     def mg_configure(self, rank: int, world: int, bounds):

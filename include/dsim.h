@@ -131,8 +131,10 @@ typedef struct dsim_options {
     uint32_t flags;            /* DSIM_OPT_* test knobs, 0 by default */
 } dsim_options;
 #define DSIM_OPT_PATCH_WARP_ONLY 0x2u /* every occupied node takes the block-per-node kernel (k_patch) */
-#define DSIM_OPT_REACH_ON_DEVICE 0x4u /* build the reach table with the device kernels (falls back to the host builder for
-                                        * graphs with reach sets of more than 384 or 2-hop sets of more than 512 nodes) */
+#define DSIM_OPT_REACH_ON_DEVICE 0x4u /* build the reach table with the device kernels: the default since round 2 (falls back
+                                        * to the host builder for graphs with reach sets of more than 384 or 2-hop sets of
+                                        * more than 512 nodes); the flag is accepted and changes nothing */
+#define DSIM_OPT_REACH_ON_HOST 0x8u   /* build the reach table with the host (OpenMP) builder */
 
 typedef struct dsim_step_stats {
     uint64_t t;               /* State.t after the call (lib.rs:308; `s.t += 1`, cli.rs:154) */
@@ -196,6 +198,11 @@ int dsim_step_part(dsim_handle *h, int part);
 int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach);
 int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst,
                    uint64_t *reach_off, uint32_t *reach_dst, double *reach_cost);
+/* Order-independent 64-bit digests of the reach table as it lies in HBM, computed on the device: out[0] row headers,
+ * out[1] destinations (padding included), out[2] costs (bit patterns), out[3] per-row bucket indices, out[4] 2-hop
+ * lists and their offsets.  Two handles on the same graph hold identical tables iff the digests agree (used to compare
+ * the device-built table with the host-built one at sizes where dsim_get_reach would move gigabytes). */
+int dsim_reach_digest(dsim_handle *h, uint64_t out[5]);
 
 /* ---- multi-GPU: one handle per GPU / process, contiguous node ranges ("bands") per rank ------------------------
  * New functionality (the reference is a single process).  Rank r owns the nodes [bounds[r], bounds[r+1]) and the
