@@ -82,6 +82,7 @@ struct dsim_handle {
     DevCtl *ctl_h = nullptr; /* pinned mirror */
     uint8_t *mem_hi8_d = nullptr;
     uint32_t *mem_lo32_d = nullptr;
+    double *mem_tail_d = nullptr;
     ModelConst mc;
     std::vector<void *> fam_allocs; /* family-capacity dependent arrays */
     uint64_t cap = 0, hs_cap = 0;
@@ -939,6 +940,21 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
             }
             if (hi8[k] != 0) mc.mem_head = (uint32_t)(k / 16u) + 1u;
         }
+        /* stream v2: at most 16 head blocks; the entries after the head are sampled by skipping against the survival
+         * products (same recurrence, same operation order as the oracle's table) */
+        if (mc.mem_head > 16u) mc.mem_head = 16u;
+        mc.mem_tail0 = 16u * mc.mem_head;
+        std::vector<double> tail;
+        {
+            double survive = 1.0;
+            for (size_t k = mc.mem_tail0; k < mem.size(); ++k) {
+                survive = survive * (1.0 - mem[k]);
+                tail.push_back(survive);
+            }
+        }
+        mc.mem_tail_len = (uint32_t)tail.size();
+        TRY(dev_alloc(h, &h->mem_tail_d, tail.size(), h->allocs, false));
+        TRY(upload(h, h->mem_tail_d, tail.data(), tail.size()));
         TRY(dev_alloc(h, &h->mem_hi8_d, hi8.size(), h->allocs, false));
         TRY(upload(h, h->mem_hi8_d, hi8.data(), hi8.size()));
         TRY(dev_alloc(h, &h->mem_lo32_d, lo32.size(), h->allocs, false));
@@ -946,6 +962,7 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         TRYCUDA(cudaStreamSynchronize(h->stream));
         mc.mem_hi8 = h->mem_hi8_d;
         mc.mem_lo32 = h->mem_lo32_d;
+        mc.mem_tail = h->mem_tail_d;
         if (dsim_configure_kernels(&h->geom) != 0) {
             g_create_error = "cannot configure the shared-memory size of k_move";
             dsim_destroy(h);

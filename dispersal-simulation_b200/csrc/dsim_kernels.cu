@@ -25,6 +25,7 @@
  * Floating point: doubles, IEEE operations only, compiled with -fmad=false so that every decision
  * (`g > m`, `res < max`, `stored - size*season < 0`) matches the CPU oracle bit for bit.
  */
+#include "dsim_async.h"
 #include "dsim_kernels.h"
 #include "dsim_math.h"
 
@@ -210,6 +211,7 @@ __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint
             ctl->n_cur[a.parity ^ 1u] = ctl->cap;
         }
         ctl->life_done = 0;
+        ctl->move_next = 0; /* k_move hands its tiles out from here */
     }
 }
 
@@ -273,11 +275,14 @@ __device__ __forceinline__ double view_quality(const StepArgs &a, const PatchVie
     return quality_eval(a, v, b, culture, size, same_patch);
 }
 
-/* ---- remembered-patch sampling, lib.rs:854-866 ------------------------------------------------------
- * History entry n is kept iff U_n < memory_n with the 40-bit uniform U_n = (B_n 2^32 + W_n) 2^-40 (ModelConst):
- * one Philox block of the MEM stream holds the top bytes B_n of 16 consecutive entries; they decide all
- * but 1/256 of the entries, the others need the word W_n of the MEM2 stream.  The byte comparisons are
- * done four at a time on packed words (flags in bit 7 of every byte). */
+/* ---- remembered-patch sampling, lib.rs:854-866 (canonical stream v2, ModelConst) ---------------------------
+ * Head: history entry n < mem_tail0 is kept iff U_n < memory_n with the 40-bit uniform U_n = (B_n 2^32 + W_n) 2^-40:
+ * one Philox block of the MEM stream holds the top bytes B_n of 16 consecutive entries; they decide all but 1/256 of
+ * the entries, the others need the word W_n of the MEM2 stream.  The byte comparisons are done four at a time on
+ * packed words (flags in bit 7 of every byte).
+ * Tail: the entries n >= mem_tail0 (memory_n < 2^-8, 0.07 kept entries expected out of 500) are sampled by skipping:
+ * one uniform finds the next kept entry in the table of survival products, so a family costs one Philox block for its
+ * whole tail instead of one per 16 entries. */
 __device__ __forceinline__ uint32_t swar_ltu4(uint32_t x, uint32_t y) { /* bytes of x < bytes of y, unsigned */
     const uint32_t d = (x | 0x80808080u) - (y & 0x7F7F7F7Fu); /* bit 7: low 7 bits of x >= low 7 bits of y; no borrows */
     return ((~x & y) | (~(x ^ y) & ~d)) & 0x80808080u;
@@ -288,43 +293,88 @@ __device__ __forceinline__ uint32_t swar_eq4(uint32_t x, uint32_t y) { /* bytes 
 }
 __device__ __forceinline__ uint32_t swar_pack4(uint32_t m) { return ((m >> 7) * 0x10204080u) >> 28; } /* bit 7 of byte k -> bit k */
 
-/* entries [16 jb, 16 jb + 16) of family `fid` with 16 jb < nh: returns the mask of entries kept on their top byte
- * alone; *undecided = entries whose top byte equals the threshold byte (mem_resolve decides them) */
-__device__ __forceinline__ uint32_t mem_block(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t jb, uint32_t nh,
-                                              uint32_t *undecided) {
-    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, jb);
-    uint32_t lt = 0, eq = 0;
-    if (jb >= mc.mem_head) { /* every threshold byte is zero: nothing is kept on the top byte, a zero byte is undecided */
-        /* cheap test for "some byte is zero" first (exact as a presence test), the exact per-byte flags only then */
-        const uint32_t any = ((o.x - 0x01010101u) & ~o.x) | ((o.y - 0x01010101u) & ~o.y) | ((o.z - 0x01010101u) & ~o.z) | ((o.w - 0x01010101u) & ~o.w);
-        if ((any & 0x80808080u) != 0u)
-            eq = swar_pack4(swar_eq4(o.x, 0u)) | (swar_pack4(swar_eq4(o.y, 0u)) << 4) | (swar_pack4(swar_eq4(o.z, 0u)) << 8) |
-                 (swar_pack4(swar_eq4(o.w, 0u)) << 12);
-    } else {
-        const uint4 h = *reinterpret_cast<const uint4 *>(mc.mem_hi8 + 16u * jb);
-        lt = swar_pack4(swar_ltu4(o.x, h.x)) | (swar_pack4(swar_ltu4(o.y, h.y)) << 4) | (swar_pack4(swar_ltu4(o.z, h.z)) << 8) |
-             (swar_pack4(swar_ltu4(o.w, h.w)) << 12);
-        eq = swar_pack4(swar_eq4(o.x, h.x)) | (swar_pack4(swar_eq4(o.y, h.y)) << 4) | (swar_pack4(swar_eq4(o.z, h.z)) << 8) |
-             (swar_pack4(swar_eq4(o.w, h.w)) << 12);
-    }
-    const uint32_t n0 = 16u * jb;
-    if (n0 < mc.mem_always) lt |= (mc.mem_always - n0 >= 16u) ? 0xFFFFu : ((1u << (mc.mem_always - n0)) - 1u);
-    const uint32_t valid = (nh - n0 >= 16u) ? 0xFFFFu : ((1u << (nh - n0)) - 1u);
-    lt &= valid;
-    *undecided = eq & valid & ~lt;
-    return lt;
-}
 __device__ __forceinline__ bool mem_resolve(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t n) {
     const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM2, n >> 2);
     return dsim_word(o, n & 3u) < mc.mem_lo32[n];
 }
-/* one entry, both levels (k_children: a lane per entry) */
-__device__ __forceinline__ bool mem_keep(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t n) {
+/* head entries [16 jb, 16 jb + 16) of family `fid` (jb < mem_head, 16 jb < nh): the mask of the kept ones */
+__device__ __forceinline__ uint32_t mem_block(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t jb, uint32_t nh) {
+    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, jb);
+    const uint4 h = *reinterpret_cast<const uint4 *>(mc.mem_hi8 + 16u * jb);
+    uint32_t lt = swar_pack4(swar_ltu4(o.x, h.x)) | (swar_pack4(swar_ltu4(o.y, h.y)) << 4) | (swar_pack4(swar_ltu4(o.z, h.z)) << 8) |
+                  (swar_pack4(swar_ltu4(o.w, h.w)) << 12);
+    const uint32_t eq = swar_pack4(swar_eq4(o.x, h.x)) | (swar_pack4(swar_eq4(o.y, h.y)) << 4) | (swar_pack4(swar_eq4(o.z, h.z)) << 8) |
+                        (swar_pack4(swar_eq4(o.w, h.w)) << 12);
+    const uint32_t n0 = 16u * jb;
+    if (n0 < mc.mem_always) lt |= (mc.mem_always - n0 >= 16u) ? 0xFFFFu : ((1u << (mc.mem_always - n0)) - 1u);
+    const uint32_t valid = (nh - n0 >= 16u) ? 0xFFFFu : ((1u << (nh - n0)) - 1u);
+    lt &= valid;
+    uint32_t undecided = eq & valid & ~lt; /* top byte equal to the threshold byte (1/256 per entry): the low word decides */
+    while (undecided) {
+        const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
+        undecided &= undecided - 1u;
+        if (mem_resolve(mc, step, fid, n0 + b)) lt |= 1u << b;
+    }
+    return lt;
+}
+/* The tail of a family with L tail entries, from the state (j0, base, d) = (first undecided tail entry, survival
+ * product before it, uniforms used so far): appends kept entries (absolute indices) to out[0 .. cap) and returns
+ * their number; *more = the list filled up before the tail was exhausted (call again with the updated state). */
+struct TailState {
+    uint32_t j0, d;
+    double base;
+};
+__device__ __forceinline__ uint32_t mem_tail_run(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t L, TailState &ts, uint32_t *out,
+                                                 uint32_t cap, bool *more) {
+    uint32_t n_out = 0;
+    *more = false;
+    while (ts.j0 < L) {
+        if (n_out == cap) {
+            *more = true;
+            break;
+        }
+        const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEMT, ts.d >> 1);
+        const double u = (ts.d & 1u) ? dsim_u53(o.z, o.w) : dsim_u53(o.x, o.y);
+        const double thr = u * ts.base;
+        if (mc.mem_tail[L - 1u] > thr) { /* no entry of the rest of the tail is kept (93 % of the first draws) */
+            ts.j0 = L;
+            break;
+        }
+        uint32_t lo = ts.j0, hi = L - 1u; /* smallest j >= j0 with mem_tail[j] <= thr; the table decreases */
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (mc.mem_tail[mid] <= thr)
+                hi = mid;
+            else
+                lo = mid + 1u;
+        }
+        out[n_out++] = mc.mem_tail0 + lo;
+        ts.base = mc.mem_tail[lo];
+        ts.j0 = lo + 1u;
+        ts.d += 1u;
+    }
+    return n_out;
+}
+/* one entry n < nh of a history of nh sampled entries (k_children: a lane per entry) */
+__device__ __forceinline__ bool mem_keep(const ModelConst &mc, uint32_t step, uint64_t fid, uint32_t n, uint32_t nh) {
     if (n < mc.mem_always) return true;
-    const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, n >> 4);
-    const uint32_t b = (dsim_word(o, (n >> 2) & 3u) >> (8u * (n & 3u))) & 0xFFu, h = mc.mem_hi8[n];
-    if (b != h) return b < h;
-    return mem_resolve(mc, step, fid, n);
+    if (n < mc.mem_tail0) {
+        const dsim_u4 o = dsim_draw(stream_of(mc), step, fid, DSIM_P_MEM, n >> 4);
+        const uint32_t b = (dsim_word(o, (n >> 2) & 3u) >> (8u * (n & 3u))) & 0xFFu, h = mc.mem_hi8[n];
+        if (b != h) return b < h;
+        return mem_resolve(mc, step, fid, n);
+    }
+    TailState ts; /* replay the skipping process up to entry n */
+    ts.j0 = 0u;
+    ts.d = 0u;
+    ts.base = 1.0;
+    const uint32_t L = nh - mc.mem_tail0;
+    for (;;) {
+        uint32_t got;
+        bool more;
+        if (mem_tail_run(mc, step, fid, L, ts, &got, 1u, &more) == 0u) return false;
+        if (got >= n) return got == n;
+    }
 }
 
 /* ---- reach rows in place ------------------------------------------------------------------------- */
@@ -416,57 +466,60 @@ __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double 
  * part 1c: move, one WARP per tile of MOVE_WF families, work items spread over the lanes.
  *
  * The decision of one family is a short ORDERED scan (lib.rs:918-927) over ~60 sensed patches and ~18
- * remembered patches, but everything that feeds the scan is independent per candidate: 40 Philox blocks
+ * remembered patches, but everything that feeds the scan is independent per candidate: 8 Philox blocks
  * of memory draws, one Philox block per two sensed patches plus a 16-byte view gather each, and per
- * remembered patch a ring read, a reach-row look-up and one Philox block.  Measured on B200
- * (profiles/): a thread per family serialises all of that behind its own memory round trips (330 us
- * at 85 k families); a block per 32 families with block-wide phases idles at its barriers (270 us).
- * Here a warp owns MOVE_WF families from their records to their new records and needs no block
- * barrier:
- *   - memory draws: (family, 16 entries) items dealt to the lanes across the tile's families;
- *   - per family: sensed patches 64 per pass (lane L takes entries L and L+32 of the pass, which share
- *     one Philox block), kept history entries 32 per pass; after each pass the ordered acceptance is a
- *     ballot loop with one iteration per acceptance (accept_scan_warp).
- * The state of a tile lives in ~1 KB of shared memory per warp, so occupancy is bounded by registers only.
+ * remembered patch a ring read, a reach-row look-up and one Philox block.  Measured on B200 (profiles/):
+ * a thread per family serialises all of that behind its own memory round trips (330 us at 85 k families);
+ * a block per 32 families with block-wide phases idles at its barriers (270 us); a warp per tile that
+ * walks its families one after the other is bound by the ~28 dependent memory round trips of a tile
+ * (129 us, round 1).  Here a warp owns MOVE_WF families from their records to their new records, needs
+ * no block barrier, and keeps the memory system busy for the whole tile at once:
+ *   - the reach rows of all the tile's families (destinations and costs of the sensed patches) are
+ *     fetched by the TMA engine — one bulk copy per row column, completion on an mbarrier — while the
+ *     warp computes the memory draws: (family, 16 entries) items and the tails dealt to the lanes;
+ *   - the candidate views of all families are then gathered with 16-byte cp.async into shared memory
+ *     while the warp lists the kept history entries;
+ *   - sensed patches: 64 per pass from shared memory (lane L takes entries L and L+32, which share one
+ *     Philox block), the ordered acceptance a ballot loop with one iteration per acceptance;
+ *   - remembered patches: the kept entries of ALL the tile's families form one list, 32 per pass whatever
+ *     family they belong to; the acceptance runs per family present in the pass.
+ * Tiles are handed out through an atomic counter (no tail of idle warps at 4 tiles per warp).
  * ------------------------------------------------------------------------------------------ */
 #ifndef MOVE_WF
-#define MOVE_WF 4u        /* families per warp tile (a power of two, 2 ... 32) */
+#define MOVE_WF 4u        /* families per warp tile (a power of two, 2 ... 8) */
 #endif
-#ifndef MOVE_HCHUNK
-#define MOVE_HCHUNK 1024u /* history entries whose draws are evaluated per chunk: a multiple of 32, at most 1024 (one 32-bit mask word per lane) */
+#ifndef MOVE_LCAP
+#define MOVE_LCAP 128u    /* kept history entries of a tile listed at a time (expected MOVE_WF * 18) */
 #endif
-#ifndef MOVE_EQ
-#define MOVE_EQ 32u       /* undecided top bytes queued per chunk and tile (expected MOVE_WF * 625 / 256 = 10) */
+#ifndef MOVE_TAILQ
+#define MOVE_TAILQ 4u     /* kept tail entries per family listed at a time (expected 0.07) */
 #endif
+#define MOVE_SSTAGE 64u   /* sensed entries per family staged in shared memory: the first pass */
+#define MOVE_HB_MAX 16u   /* head blocks of 16 history entries (ModelConst.mem_head <= 16) */
 #define MOVE_WARPS 4u
 #ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 8 /* 64 registers per thread */
+#define MOVE_MIN_BLOCKS 6 /* 8.8 KB of shared memory per warp: 24 warps per SM, 80 registers per thread */
 #endif
-#define MOVE_MWORDS (MOVE_HCHUNK / 32u)
 
-struct MoveTile { /* per warp */
+struct __align__(16) MoveTile { /* per warp */
+    /* filled by asynchronous copies */
+    PatchView view[MOVE_WF][MOVE_SSTAGE];  /* candidate views of the first MOVE_SSTAGE sensed patches (cp.async) */
+    double r_cost[MOVE_WF][MOVE_SSTAGE];   /* their travel costs and node ids: the head of the reach row (TMA bulk copy) */
+    uint32_t r_dst[MOVE_WF][MOVE_SSTAGE];
     uint64_t fid[MOVE_WF], culture[MOVE_WF];
     double max_gain[MOVE_WF], t_cost[MOVE_WF], m[MOVE_WF]; /* best_location state of each family (lib.rs:911-916) */
+    double stored[MOVE_WF], last_harvest[MOVE_WF], tbase[MOVE_WF];
     uint32_t target[MOVE_WF];
     uint32_t loc[MOVE_WF], size[MOVE_WF], hs[MOVE_WF], hist_cnt[MOVE_WF], nh[MOVE_WF];
     uint32_t row_start[MOVE_WF], row_len[MOVE_WF], ns[MOVE_WF], n_near[MOVE_WF];
-    /* what only the epilogue of family f needs (kept out of registers during the candidate passes) */
-    double stored[MOVE_WF], last_harvest[MOVE_WF];
     uint32_t idx[MOVE_WF], newpos[MOVE_WF], crank[MOVE_WF], misc[MOVE_WF], newest[MOVE_WF];
-    uint32_t masks[MOVE_WF * MOVE_MWORDS]; /* bit n of family f: history entry hbase + n is kept */
-    uint32_t eq_q[MOVE_EQ];                /* (family << 16) | entry index in the chunk */
-    uint32_t eq_cnt;
-    uint16_t kept[32];                     /* kept entries of the current pass, relative to the chunk */
+    uint32_t tj0[MOVE_WF], td[MOVE_WF], ntail[MOVE_WF], tmore[MOVE_WF]; /* tail sampling state (mem_tail_run) */
+    uint32_t tail[MOVE_WF][MOVE_TAILQ];    /* kept tail entries */
+    uint32_t list[MOVE_LCAP];              /* kept entries of the tile: family << 24 | entry, family-major, ascending */
+    uint16_t hmask[MOVE_WF][MOVE_HB_MAX];  /* kept head entries, 16 per block */
+    dsim_mbar bar;                         /* completion of the bulk copies of a tile */
 };
 
-__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const uint32_t o = __shfl_xor_sync(DSIM_FULL, v, d);
-        v = o > v ? o : v;
-    }
-    return v;
-}
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -485,17 +538,28 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_lanes = (1u << lane) - 1u;
-    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t ntiles = (n + MOVE_WF - 1u) / MOVE_WF;
     const dsim_stream rs = stream_of(a.mc);
+    const uint32_t HB = a.mc.mem_head;          /* head blocks; item j == HB of a family is its tail */
+    const uint32_t n_items = MOVE_WF * (HB + 1u);
+    uint32_t phase = 0;                         /* parity of the mbarrier phase the next wait completes */
 
-    for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    if (lane == 0) dsim_mbar_init(&S.bar, 1u);
+    __syncwarp();
+
+    /* tiles are handed out by a counter: the claim for the next tile is in flight while this one is worked on */
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&ctl->move_next, 1u);
+    tile = __shfl_sync(DSIM_FULL, tile, 0);
+    while (tile < ntiles) {
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(&ctl->move_next, 1u);
+
         /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- *
          * Every load that depends only on the family's position is requested before any is used (also for
          * families that turn out to be dead: their columns are still valid memory), so the prologue costs
          * three memory round trips: members -> record columns and bitmaps -> row header and history length. */
-        uint32_t nh = 0, state = 0; /* state: bit 0 = decides (survivor), bit 1 = splits */
+        uint32_t nh = 0, state = 0, nst = 0; /* state: bit 0 = decides (survivor), bit 1 = splits; nst: staged sensed entries, padded to 8 */
         if (lane < MOVE_WF) {
             /* Families are visited in the patch-grouped order that part 2 of the previous step left in
              * `members`: co-resident families (same reach row, same candidate views) share a tile or sit in
@@ -531,6 +595,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                     const uint32_t hist_valid = hist_cnt < hcap ? hist_cnt : hcap;
                     nh = hist_valid < a.mc.n_mem ? hist_valid : a.mc.n_mem;
                     ns = hd.n_sensed;
+                    nst = ((ns < MOVE_SSTAGE ? ns : MOVE_SSTAGE) + 7u) & ~7u; /* rows are padded to 8 entries */
                     S.loc[lane] = loc;
                     S.hs[lane] = hs;
                     S.hist_cnt[lane] = hist_cnt;
@@ -547,44 +612,116 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             }
             S.ns[lane] = ns;
             S.nh[lane] = nh;
-            if (lane == 0) S.eq_cnt = 0u;
         }
-        const uint32_t max_nh = warp_max_u32(nh);
         const uint32_t live_mask = __ballot_sync(DSIM_FULL, (state & 1u) != 0u);
+        /* ---- the reach rows of the tile, by bulk copy ---------------------------------------------- */
+        uint32_t stage_entries = nst; /* sum over the tile's families */
+#pragma unroll
+        for (uint32_t d = 1; d < MOVE_WF; d <<= 1) stage_entries += __shfl_xor_sync(DSIM_FULL, stage_entries, (int)d);
+        stage_entries = __shfl_sync(DSIM_FULL, stage_entries, 0);
+        dsim_fence_proxy_async(); /* the previous tile's reads of the staging arrays come before this tile's copies into them */
+        __syncwarp();
+        if (stage_entries != 0u) {
+            if (lane == 0) dsim_mbar_expect_tx(&S.bar, stage_entries * 12u);
+            __syncwarp();
+            const uint32_t f = lane >> 1;
+            const uint32_t nst_f = __shfl_sync(DSIM_FULL, nst, (int)(f < MOVE_WF ? f : 0u));
+            if (f < MOVE_WF && nst_f != 0u) {
+                if (lane & 1u)
+                    dsim_bulk_g2s(&S.r_cost[f][0], a.rt.cost + S.row_start[f], nst_f * 8u, &S.bar);
+                else
+                    dsim_bulk_g2s(&S.r_dst[f][0], a.rt.dst + S.row_start[f], nst_f * 4u, &S.bar);
+            }
+        }
+
+        /* ---- memory draws, lib.rs:854-866: item (family f, block j) of the head or (f, HB) = the tail -- */
+        for (uint32_t it = lane; it < n_items; it += 32u) {
+            const uint32_t f = it / (HB + 1u), j = it - f * (HB + 1u);
+            const uint32_t nhf = S.nh[f];
+            if (j < HB) {
+                uint32_t kept = 0;
+                if (16u * j < nhf) kept = mem_block(a.mc, step, S.fid[f], j, nhf < a.mc.mem_tail0 ? nhf : a.mc.mem_tail0);
+                S.hmask[f][j] = (uint16_t)kept;
+            } else {
+                TailState ts;
+                ts.j0 = 0u;
+                ts.d = 0u;
+                ts.base = 1.0;
+                uint32_t cnt = 0;
+                bool more = false;
+                if (nhf > a.mc.mem_tail0) cnt = mem_tail_run(a.mc, step, S.fid[f], nhf - a.mc.mem_tail0, ts, &S.tail[f][0], MOVE_TAILQ, &more);
+                S.ntail[f] = cnt;
+                S.tmore[f] = more ? 1u : 0u;
+                S.tj0[f] = ts.j0;
+                S.td[f] = ts.d;
+                S.tbase[f] = ts.base;
+            }
+        }
+
+        /* ---- the candidate views of the staged sensed patches: 16-byte gathers into shared memory --- */
+        if (stage_entries != 0u) {
+            dsim_mbar_wait(&S.bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (uint32_t f = 0; f < MOVE_WF; ++f) {
+                if (!((live_mask >> f) & 1u)) continue;
+                const uint32_t ns = S.ns[f];
+                if (lane < ns) dsim_cp_async16(&S.view[f][lane], &a.ps.view[S.r_dst[f][lane]]);
+                if (lane + 32u < ns && lane + 32u < MOVE_SSTAGE) dsim_cp_async16(&S.view[f][lane + 32u], &a.ps.view[S.r_dst[f][lane + 32u]]);
+            }
+            dsim_cp_async_commit();
+        }
         __syncwarp();
 
         /* ---- decide_on_moving, lib.rs:830-889 ------------------------------------------------------- *
          * sensed patches: the leading entries of the reach row, in ascending node order; the noise index of a
          * sensed patch is its position among the sensed patches that have a travel cost, i.e. in the row */
+        dsim_cp_async_wait_all();
+        __syncwarp();
         for (uint32_t f = 0; f < MOVE_WF; ++f) {
             if (!((live_mask >> f) & 1u)) continue;
             const uint32_t ns = S.ns[f];
             if (ns == 0u) continue;
             const uint64_t fid = S.fid[f], culture = S.culture[f];
             const uint32_t loc = S.loc[f], size = S.size[f];
-            const uint32_t *r_dst = a.rt.dst + S.row_start[f];
-            const double *r_cost = a.rt.cost + S.row_start[f];
             Choice ch;
             ch.target = S.target[f];
             ch.max_gain = S.max_gain[f];
             ch.t_cost = S.t_cost[f];
             ch.m = S.m[f];
-            for (uint32_t base = 0; base < ns; base += 64u) {
-                /* lane L takes entries base + L and base + 32 + L; out-of-range lanes re-read the last entry and
-                 * are masked at the acceptance, so the loads need no branches */
-                const uint32_t eA = base + lane, eB = eA + 32u;
-                const bool vA = eA < ns, vB = eB < ns;
-                const uint32_t iA = vA ? eA : ns - 1u, iB = vB ? eB : ns - 1u;
-                const uint32_t qA = r_dst[iA], qB = r_dst[iB];
-                const double cA = r_cost[iA], cB = r_cost[iB];
-                const PatchView pA = a.ps.view[qA], pB = a.ps.view[qB];
+            { /* first pass: entries 0..63 from shared memory.  Lane L takes entries L and 32 + L; out-of-range lanes read
+               * entry 0 and are masked at the acceptance, so the loads need no branches */
+                const bool vA = lane < ns, vB = lane + 32u < ns;
+                const uint32_t iA = vA ? lane : 0u, iB = vB ? lane + 32u : 0u;
+                const uint32_t qA = S.r_dst[f][iA], qB = S.r_dst[f][iB];
+                const double cA = S.r_cost[f][iA], cB = S.r_cost[f][iB];
+                const PatchView pA = S.view[f][iA], pB = S.view[f][iB];
                 /* entries e and e + 32 of a pass share one Philox block (noise_block / noise_pick) */
-                const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(eA));
+                const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(lane));
                 const double gainA = view_quality(a, pA, qA, culture, size, qA == loc);
                 accept_scan_warp(ch, vA, gainA * dsim_u53(o.x, o.y) - cA, gainA, cA, qA);
-                if (base + 32u < ns) {
+                if (32u < ns) {
                     const double gainB = view_quality(a, pB, qB, culture, size, qB == loc);
                     accept_scan_warp(ch, vB, gainB * dsim_u53(o.z, o.w) - cB, gainB, cB, qB);
+                }
+            }
+            if (ns > MOVE_SSTAGE) { /* longer lists of sensed patches: further passes straight from the row */
+                const uint32_t *r_dst = a.rt.dst + S.row_start[f];
+                const double *r_cost = a.rt.cost + S.row_start[f];
+                for (uint32_t base = MOVE_SSTAGE; base < ns; base += 64u) {
+                    const uint32_t eA = base + lane, eB = eA + 32u;
+                    const bool vA = eA < ns, vB = eB < ns;
+                    const uint32_t iA = vA ? eA : ns - 1u, iB = vB ? eB : ns - 1u;
+                    const uint32_t qA = r_dst[iA], qB = r_dst[iB];
+                    const double cA = r_cost[iA], cB = r_cost[iB];
+                    const PatchView pA = a.ps.view[qA], pB = a.ps.view[qB];
+                    const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(eA));
+                    const double gainA = view_quality(a, pA, qA, culture, size, qA == loc);
+                    accept_scan_warp(ch, vA, gainA * dsim_u53(o.x, o.y) - cA, gainA, cA, qA);
+                    if (base + 32u < ns) {
+                        const double gainB = view_quality(a, pB, qB, culture, size, qB == loc);
+                        accept_scan_warp(ch, vB, gainB * dsim_u53(o.z, o.w) - cB, gainB, cB, qB);
+                    }
                 }
             }
             if (lane == 0) {
@@ -596,98 +733,78 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
         }
         __syncwarp();
 
-        /* ---- remembered patches, lib.rs:854-867 --------------------------------------------------- */
-        for (uint32_t hbase = 0; hbase < max_nh; hbase += MOVE_HCHUNK) {
-            /* draws: item = (family, 16 history entries), block index major so that the few blocks whose
-             * thresholds have a non-zero top byte (full byte comparison) share the first pass */
-            const uint32_t span = max_nh - hbase < MOVE_HCHUNK ? max_nh - hbase : MOVE_HCHUNK;
-            const uint32_t nblk = (span + 15u) >> 4, jb0 = hbase >> 4;
-            for (uint32_t k = lane; k < MOVE_WF * MOVE_MWORDS; k += 32u) S.masks[k] = 0u;
-            __syncwarp();
-            for (uint32_t it = lane; it < MOVE_WF * nblk; it += 32u) {
-                const uint32_t j = it / MOVE_WF, f = it % MOVE_WF;
-                const uint32_t nhf = S.nh[f];
-                if (hbase + 16u * j >= nhf) continue;
-                const uint64_t fid = S.fid[f];
-                uint32_t undecided;
-                uint32_t kept = mem_block(a.mc, step, fid, jb0 + j, nhf, &undecided);
-                while (undecided) {
-                    const uint32_t b = (uint32_t)__ffs((int)undecided) - 1u;
-                    undecided &= undecided - 1u;
-                    const uint32_t slot = atomicAdd(&S.eq_cnt, 1u);
-                    if (slot < MOVE_EQ)
-                        S.eq_q[slot] = (f << 16) | (16u * j + b);
-                    else if (mem_resolve(a.mc, step, fid, hbase + 16u * j + b)) /* queue full: decide it here */
-                        kept |= 1u << b;
-                }
-                reinterpret_cast<uint16_t *>(S.masks)[(f * MOVE_MWORDS) * 2u + j] = (uint16_t)kept;
-            }
-            __syncwarp();
-            { /* the queued undecided entries: one Philox block of the MEM2 stream each */
-                const uint32_t nq = S.eq_cnt < MOVE_EQ ? S.eq_cnt : MOVE_EQ;
-                for (uint32_t k = lane; k < nq; k += 32u) {
-                    const uint32_t f = S.eq_q[k] >> 16, e = S.eq_q[k] & 0xFFFFu;
-                    if (mem_resolve(a.mc, step, S.fid[f], hbase + e)) atomicOr(&S.masks[f * MOVE_MWORDS + (e >> 5)], 1u << (e & 31u));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) S.eq_cnt = 0u;
-
-            for (uint32_t f = 0; f < MOVE_WF; ++f) {
-                if (!((live_mask >> f) & 1u) || S.nh[f] <= hbase) continue;
-                /* kept entries in ascending order, 32 per pass: lane w holds mask word w and the number of kept entries before it */
-                const uint32_t word = lane < MOVE_MWORDS ? S.masks[f * MOVE_MWORDS + lane] : 0u;
-                const uint32_t incl = warp_incl_scan_u32((uint32_t)__popc(word), lane);
-                const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
-                if (total == 0u) continue;
-                const uint32_t before = incl - (uint32_t)__popc(word);
-                const uint32_t nonzero = __ballot_sync(DSIM_FULL, word != 0u);
-                const uint64_t fid = S.fid[f];
-                const uint32_t n_near = S.n_near[f];
-                RowHdr hd;
-                hd.start = S.row_start[f];
-                hd.len = S.row_len[f];
-                hd.n_sensed = S.ns[f];
-                hd.n_near = n_near;
-                const RowPtr row = row_of(a.rt, S.loc[f], hd);
-                const uint32_t newest = S.newest[f];
-                const size_t hb = (size_t)S.hs[f] * hcap;
-                Choice ch;
-                ch.target = S.target[f];
-                ch.max_gain = S.max_gain[f];
-                ch.t_cost = S.t_cost[f];
-                ch.m = S.m[f];
-                for (uint32_t r0 = 0; r0 < total; r0 += 32u) {
-                    for (uint32_t nz = nonzero; nz != 0u; nz &= nz - 1u) { /* scatter the kept entries r0 .. r0+31 to S.kept */
-                        const int w = __ffs((int)nz) - 1;
-                        const uint32_t ww = __shfl_sync(DSIM_FULL, word, w), wb = __shfl_sync(DSIM_FULL, before, w);
-                        const uint32_t pos = wb + (uint32_t)__popc(ww & lt_lanes);
-                        if (((ww >> lane) & 1u) && pos >= r0 && pos < r0 + 32u) S.kept[pos - r0] = (uint16_t)(32u * (uint32_t)w + lane);
+        /* ---- remembered patches, lib.rs:854-867: the kept entries of the whole tile, family-major ------ *
+         * round 0 lists the kept head entries and the first MOVE_TAILQ kept tail entries of every family; further
+         * rounds (a family with more kept tail entries than that: practically never) list tail entries only */
+        for (uint32_t round = 0;; ++round) {
+            for (uint32_t win = 0;; win += MOVE_LCAP) {
+                /* positions by a scan over the items in (family, block) order; entries inside the window are listed */
+                uint32_t run = 0;
+                for (uint32_t it0 = 0; it0 < n_items; it0 += 32u) {
+                    const uint32_t it = it0 + lane;
+                    uint32_t f = 0, j = 0, mask = 0, cnt = 0;
+                    if (it < n_items) {
+                        f = it / (HB + 1u);
+                        j = it - f * (HB + 1u);
+                        if (!((live_mask >> f) & 1u)) {
+                            cnt = 0u;
+                        } else if (j < HB) {
+                            mask = round == 0u ? (uint32_t)S.hmask[f][j] : 0u;
+                            cnt = (uint32_t)__popc(mask);
+                        } else {
+                            cnt = S.ntail[f];
+                        }
                     }
-                    __syncwarp();
-                    const bool on = r0 + lane < total;
+                    const uint32_t incl = warp_incl_scan_u32(cnt, lane);
+                    uint32_t p = run + incl - cnt;
+                    run += __shfl_sync(DSIM_FULL, incl, 31);
+                    if (j < HB) {
+                        while (mask) {
+                            const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+                            mask &= mask - 1u;
+                            if (p >= win && p < win + MOVE_LCAP) S.list[p - win] = (f << 24) | (16u * j + b);
+                            ++p;
+                        }
+                    } else {
+                        for (uint32_t k = 0; k < cnt; ++k, ++p)
+                            if (p >= win && p < win + MOVE_LCAP) S.list[p - win] = (f << 24) | S.tail[f][k];
+                    }
+                }
+                __syncwarp();
+                const uint32_t total = run;
+                if (total <= win) break;
+                const uint32_t nwin = total - win < MOVE_LCAP ? total - win : MOVE_LCAP;
+                for (uint32_t p0 = 0; p0 < nwin; p0 += 32u) {
+                    const bool on = p0 + lane < nwin;
+                    const uint32_t item = S.list[on ? p0 + lane : p0];
+                    const uint32_t f = item >> 24, nn = item & 0xFFFFFFu; /* entry nn of family f, 0 = newest */
                     bool cand = false;
                     double g = 0.0, gain = 0.0, cost = 0.0;
                     uint32_t q = 0;
                     if (on) {
-                        const uint32_t nn = hbase + S.kept[lane]; /* entry nn, 0 = newest */
+                        const uint32_t newest = S.newest[f];
                         const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
+                        const size_t hb = (size_t)S.hs[f] * hcap;
                         q = a.hv.hist_patch[hb + pos];
                         gain = a.hv.hist_harv[hb + pos];
+                        const uint32_t r_len = S.row_len[f], r_ns = S.ns[f];
+                        const uint32_t *r_dst = a.rt.dst + S.row_start[f];
+                        const double *r_cost = a.rt.cost + S.row_start[f];
+                        const uint16_t *r_hash = r_len <= DSIM_ROW_HASH_MAX ? a.rt.hash + (size_t)S.loc[f] * 256u : nullptr;
                         /* the chain entry -> bucket -> row is three dependent loads: the draw is computed while the
                          * bucket is in flight, and the cost is requested together with the row entry that verifies
                          * the bucket's answer */
                         uint32_t idx = ROW_SEARCH;
                         uint4 bk = make_uint4(0u, 0u, 0u, 0u);
-                        if (row.hash != nullptr) bk = *bucket_of(row.hash, q);
-                        const double u = noise_draw(a.mc, step, fid, n_near + nn);
-                        if (row.hash != nullptr) {
+                        if (r_hash != nullptr) bk = *bucket_of(r_hash, q);
+                        const double u = noise_draw(a.mc, step, S.fid[f], S.n_near[f] + nn);
+                        if (r_hash != nullptr) {
                             const uint32_t bp = bucket_probe(bk, q);
                             if (bp == ROW_ABSENT) {
                                 idx = ROW_ABSENT;
-                            } else if (bp < row.len) {
-                                const uint32_t dq = row.dst[bp];
-                                const double c = row.cost[bp];
+                            } else if (bp < r_len) {
+                                const uint32_t dq = r_dst[bp];
+                                const double c = r_cost[bp];
                                 if (dq == q) {
                                     idx = bp;
                                     cost = c;
@@ -695,23 +812,54 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                             }
                         }
                         if (idx == ROW_SEARCH) {
-                            idx = row_find_sorted(row.dst, row.n_sensed, row.len, q);
-                            if (idx != ROW_ABSENT) cost = row.cost[idx];
+                            idx = row_find_sorted(r_dst, r_ns, r_len, q);
+                            if (idx != ROW_ABSENT) cost = r_cost[idx];
                         }
                         if (idx != ROW_ABSENT) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
                             g = gain * u - cost;
                             cand = true;
                         }
                     }
-                    accept_scan_warp(ch, cand, g, gain, cost, q);
-                    __syncwarp();
+                    /* ordered acceptance, one family of the pass after the other (the list is family-major) */
+                    const uint32_t n_act = nwin - p0 < 32u ? nwin - p0 : 32u;
+                    const uint32_t f_lo = __shfl_sync(DSIM_FULL, f, 0), f_hi = __shfl_sync(DSIM_FULL, f, (int)(n_act - 1u));
+                    for (uint32_t ff = f_lo; ff <= f_hi; ++ff) {
+                        Choice ch;
+                        ch.target = S.target[ff];
+                        ch.max_gain = S.max_gain[ff];
+                        ch.t_cost = S.t_cost[ff];
+                        ch.m = S.m[ff];
+                        __syncwarp();
+                        accept_scan_warp(ch, on && cand && f == ff, g, gain, cost, q);
+                        if (lane == 0) {
+                            S.target[ff] = ch.target;
+                            S.max_gain[ff] = ch.max_gain;
+                            S.t_cost[ff] = ch.t_cost;
+                            S.m[ff] = ch.m;
+                        }
+                        __syncwarp();
+                    }
                 }
-                if (lane == 0) {
-                    S.target[f] = ch.target;
-                    S.max_gain[f] = ch.max_gain;
-                    S.t_cost[f] = ch.t_cost;
-                    S.m[f] = ch.m;
+                if (win + MOVE_LCAP >= total) break;
+            }
+            /* families whose tail list filled up before their tail was exhausted go on from where they stopped */
+            const bool cont = lane < MOVE_WF && ((live_mask >> lane) & 1u) != 0u && S.tmore[lane] != 0u;
+            if (__ballot_sync(DSIM_FULL, cont) == 0u) break;
+            if (lane < MOVE_WF) {
+                uint32_t cnt = 0;
+                bool more = false;
+                if (cont) {
+                    TailState ts;
+                    ts.j0 = S.tj0[lane];
+                    ts.d = S.td[lane];
+                    ts.base = S.tbase[lane];
+                    cnt = mem_tail_run(a.mc, step, S.fid[lane], S.nh[lane] - a.mc.mem_tail0, ts, &S.tail[lane][0], MOVE_TAILQ, &more);
+                    S.tj0[lane] = ts.j0;
+                    S.td[lane] = ts.d;
+                    S.tbase[lane] = ts.base;
                 }
+                S.ntail[lane] = cnt;
+                S.tmore[lane] = more ? 1u : 0u;
             }
             __syncwarp();
         }
@@ -774,6 +922,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             }
         }
         __syncwarp();
+        tile = __shfl_sync(DSIM_FULL, next_tile, 0);
     }
 }
 
@@ -914,7 +1063,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
 #pragma unroll
             for (uint32_t s = 0; s < CHILD_HR; ++s) {
                 const uint32_t n = c0 + 32u * s + lane;
-                keep[s] = n < nhc && mem_keep(a.mc, step, cid, n);
+                keep[s] = n < nhc && mem_keep(a.mc, step, cid, n, nhc);
                 bk[s] = make_uint4(0u, 0u, 0u, 0u);
                 if (row.hash != nullptr && keep[s]) bk[s] = *bucket_of(row.hash, hp[s]);
             }
@@ -1770,7 +1919,7 @@ static uint32_t grid_for(const LaunchGeom &g, uint32_t per_sm) { return g.n_sm *
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s) {
     switch (which) {
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
-    case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, 8), MOVE_WARPS * 32, 0, s, a); break;
+    case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, MOVE_MIN_BLOCKS), MOVE_WARPS * 32, 0, s, a); break;
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
     case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;

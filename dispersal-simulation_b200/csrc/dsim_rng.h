@@ -26,6 +26,7 @@ enum dsim_purpose : uint32_t {
     DSIM_P_MUT = 6,     /* mutation clock and bit, lib.rs:1270-1285; entity = family id        */
     DSIM_P_REGROW = 7,  /* recover_resources_proportion, lib.rs:1309; entity = node id         */
     DSIM_P_MEM2 = 8,    /* low 32 bits of the remembered-patch draw, lib.rs:859; entity = family id */
+    DSIM_P_MEMT = 9,    /* skip sampling over the tail of the history, lib.rs:859; entity = family id */
     /* workload generation only (dsim_synth) */
     DSIM_P_SYN_EDGE = 32, DSIM_P_SYN_POPCAP = 33, DSIM_P_SYN_FAMILY = 34, DSIM_P_SYN_CULTURE = 35,
     DSIM_P_SYN_HIST = 36, DSIM_P_SYN_SITE = 37

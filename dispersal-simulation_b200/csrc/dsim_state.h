@@ -136,6 +136,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t errors;
     uint32_t cap, hs_cap;
     uint32_t life_done;      /* blocks of k_lifecycle that have finished (the last one scans and resets it) */
+    uint32_t move_next;      /* next tile of k_move to hand out (reset by the tail of k_lifecycle)           */
     uint64_t child_id_base, next_id;
     uint64_t births, deaths, updates;
 };
@@ -148,14 +149,19 @@ struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed
     uint32_t n_mem;          /* history entries the memory loop can still sample (lib.rs:856)       */
     uint32_t n_nodes;
     uint32_t k0, k1;         /* Philox key = seed                                                  */
-    /* History entry n is kept iff U_n < memory after n decays (lib.rs:847-864), U_n = (B_n 2^32 + W_n) 2^-40 with
-     * B_n a byte of the MEM stream and W_n a word of the MEM2 stream, i.e. iff (B_n, W_n) < C_n = ceil(memory_n 2^40)
-     * lexicographically: B_n < mem_hi8[n], or B_n == mem_hi8[n] and W_n < mem_lo32[n] (W_n is only drawn then).
-     * Both tables are zero-padded to a multiple of 16 entries. */
+    /* Remembered-patch sampling (lib.rs:847-866), canonical stream v2.
+     * Head, n < mem_tail0 = 16 mem_head: entry n is kept iff U_n < memory_n with the 40-bit uniform
+     * U_n = (B_n 2^32 + W_n) 2^-40, B_n a byte of the MEM stream and W_n a word of the MEM2 stream, i.e. iff
+     * (B_n, W_n) < C_n = ceil(memory_n 2^40) lexicographically: B_n < mem_hi8[n], or B_n == mem_hi8[n] and
+     * W_n < mem_lo32[n] (W_n is only drawn then).  Both tables are zero-padded to a multiple of 16 entries.
+     * Tail, n >= mem_tail0 (memory_n < 2^-8): exact skip sampling against the survival products
+     * mem_tail[j] = prod_{k <= j} (1 - memory_{mem_tail0 + k}), one uniform of the MEMT stream per kept entry + 1. */
     const uint8_t *mem_hi8;  /* C_n >> 32 (entries n < mem_always have C_n = 2^40 and are always kept) */
     const uint32_t *mem_lo32;/* C_n & 0xFFFFFFFF                                                   */
+    const double *mem_tail;  /* [mem_tail_len]                                                     */
     uint32_t mem_always;     /* leading entries with memory_n >= 1                                  */
-    uint32_t mem_head;       /* 16-entry blocks [0, mem_head) contain a non-zero mem_hi8             */
+    uint32_t mem_head;       /* 16-entry blocks of the head (at most 16)                             */
+    uint32_t mem_tail0, mem_tail_len;
 };
 
 /* ---- multi-GPU (band partition, dsim_mg_kernels.cu) ------------------------------------------------ */

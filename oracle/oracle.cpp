@@ -68,7 +68,8 @@ enum Purpose : uint32_t {
     P_PIVOT = 5,   /* select_pivot_family lib.rs:1295, band b                   entity = node id   */
     P_MUT = 6,     /* time_till_next_mutation / change_random_bitvec_component  entity = family id */
     P_REGROW = 7,  /* recover_resources_proportion lib.rs:1309, ecoregion slot  entity = node id   */
-    P_MEM2 = 8     /* low 32 bits of the memory draw of history entry n         entity = family id */
+    P_MEM2 = 8,    /* low 32 bits of the memory draw of history entry n         entity = family id */
+    P_MEMT = 9     /* skip sampling over the tail of the history (stream v2)    entity = family id */
 };
 
 struct Stream {
@@ -84,6 +85,41 @@ struct Stream {
 inline double u53(uint32_t lo, uint32_t hi) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* ---- the canonical draws, one function per call site of the reference's `stochasticity` module (lib.rs:1260-1336);
+ * the step below and the statistical tests (oracle_draw_* exports, tests/test_oracle_stats.py) both go through these */
+inline double draw_noise(const Stream &rng, uint64_t t, uint64_t fid, uint32_t noise_index) {
+    /* resource_uncertainty, lib.rs:1317.  Two draws per Philox block: indices i and i + 32 of every run of 64 share a
+     * block, block = (i / 64) * 32 + i % 32, words (0,1) if i % 64 < 32, else (2,3). */
+    uint32_t out[4];
+    rng.draw(t, fid, P_NOISE, ((noise_index >> 6) << 5) | (noise_index & 31u), out);
+    return (noise_index & 32u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
+}
+inline uint64_t draw_shuffle_key(const Stream &rng, uint64_t t, uint64_t fid) { /* shuffle, lib.rs:1333 */
+    uint32_t out[4];
+    rng.draw(t, fid, P_SHUF, 0, out);
+    return ((uint64_t)out[1] << 32) | out[0];
+}
+inline void draw_fight(const Stream &rng, uint64_t t, uint64_t newcomer, uint32_t opponent_position, uint32_t deadliness,
+                       bool *opponent_hit, bool *newcomer_hit) { /* fight_is_deadly x2, lib.rs:1219,1226,1325 */
+    uint32_t out[4];
+    rng.draw(t, newcomer, P_FIGHT, opponent_position, out);
+    *opponent_hit = out[0] < deadliness;
+    *newcomer_hit = out[1] < deadliness;
+}
+inline uint64_t draw_pivot(const Stream &rng, uint64_t t, uint64_t node, uint32_t band, uint64_t len) {
+    /* select_pivot_family, lib.rs:1295-1298: fastrand::usize(0..len) */
+    uint32_t out[4];
+    rng.draw(t, node, P_PIVOT, band, out);
+    const uint64_t r = ((uint64_t)out[1] << 32) | out[0];
+    return (uint64_t)(((unsigned __int128)r * (unsigned __int128)len) >> 64);
+}
+inline double draw_regrowth(const Stream &rng, uint64_t t, uint64_t node, uint32_t eco_slot) {
+    /* recover_resources_proportion, lib.rs:1309-1311: 2 * f64() */
+    uint32_t out[4];
+    rng.draw(t, node, P_REGROW, eco_slot, out);
+    return 2.0 * u53(out[0], out[1]);
 }
 
 /* CANON: natural logarithm evaluated with +,-,*,/ only, in a fixed order, so that host and device
@@ -208,6 +244,8 @@ struct oracle_handle {
     std::vector<std::unique_ptr<std::vector<uint32_t>>> nearby_cache;            /* lib.rs:487 */
     std::vector<std::unique_ptr<std::vector<std::pair<uint32_t, double>>>> reach_cache; /* mode 1 */
     std::vector<double> mem_table; /* memory after n decays, lib.rs:847-866 */
+    uint32_t mem_tail0 = 0;        /* first history entry sampled by skipping (CANON, see remembered_entries) */
+    std::vector<double> mem_tail;  /* mem_tail[j] = prod_{k <= j} (1 - memory_{mem_tail0 + k}) */
     std::string err;
     uint32_t model_errors = 0;
     uint64_t births = 0, deaths = 0, updates = 0, occupied = 0;
@@ -332,6 +370,51 @@ struct Decision {
     double cost;
 };
 
+/* Which of the `len` newest history entries (0 = newest) a family remembers this step: the reference keeps entry n
+ * iff `fastrand::f64() < memory_n`, memory_n = 0.5^(n * season / 2) by repeated multiplication, one independent draw
+ * per entry while memory_n >= f64::EPSILON (lib.rs:847-866).  CANON (stream v2), same distribution:
+ *  - head, n < tail0: a 40-bit uniform U_n = (B_n * 2^32 + W_n) * 2^-40 per entry, B_n = byte n&15 of Philox block
+ *    n>>4 of the MEM stream (16 entries per block), W_n = word n&3 of block n>>2 of the MEM2 stream; kept iff
+ *    U_n < memory_n.  (The device draws W_n only when B_n alone does not decide.)
+ *  - tail, n >= tail0 (every memory_n < 2^-8: 0.07 entries expected out of 500): the independent draws are replaced
+ *    by exact skip sampling.  With S_j = prod_{k <= j} (1 - memory_{tail0 + k}) (`tail`, the probability that none of
+ *    the first j+1 tail entries is kept), given that the entries before j0 are decided and base = S_{j0-1} (1 at the
+ *    start), the next kept entry is the smallest j >= j0 with S_j <= U * base for one uniform U — P(J > j) =
+ *    S_j / base, exactly the law of independent draws; then j0 = J + 1, base = S_J and the next uniform decides the
+ *    entry after that.  Uniform d of the family and step is u53 of words (0,1) (d even) or (2,3) (d odd) of block
+ *    d>>1 of the MEMT stream.
+ * Output: kept entry indices, ascending (the order the reference considers them in). */
+void remembered_entries(const Stream &rng, uint64_t t, uint64_t fid, uint32_t len, const std::vector<double> &mem,
+                        uint32_t tail0, const std::vector<double> &tail, std::vector<uint32_t> &kept) {
+    uint32_t out[4];
+    kept.clear();
+    const uint32_t n_head = std::min(len, tail0);
+    for (uint32_t n = 0; n < n_head; ++n) {
+        rng.draw(t, fid, P_MEM, n >> 4, out);
+        const uint64_t b = (out[(n >> 2) & 3] >> (8 * (n & 3))) & 0xFFu;
+        rng.draw(t, fid, P_MEM2, n >> 2, out);
+        const uint64_t x = (b << 32) | out[n & 3];
+        const double u = (double)x * (1.0 / 1099511627776.0);
+        if (u < mem[n]) kept.push_back(n);
+    }
+    if (len <= tail0) return;
+    const uint32_t L = len - tail0; /* tail entries this family has */
+    uint32_t j0 = 0, d = 0;
+    double base = 1.0;
+    while (j0 < L) {
+        rng.draw(t, fid, P_MEMT, d >> 1, out);
+        const double u = (d & 1u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
+        const double thr = u * base;
+        uint32_t j = j0;
+        while (j < L && tail[j] > thr) ++j;
+        if (j >= L) break;
+        kept.push_back(tail0 + j);
+        base = tail[j];
+        j0 = j + 1;
+        d += 1;
+    }
+}
+
 Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t *known, size_t n_known,
                           const std::vector<uint64_t> &population) {
     /* lib.rs:843: one bounded Dijkstra per call */
@@ -362,7 +445,6 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
     uint32_t target = family.location;
     double max_gain = 0.0, t_cost = 0.0;
     double m = max_gain - t_cost;
-    uint32_t out[4];
 
     auto consider = [&](uint32_t q, double gain, double l_cost, uint32_t noise_index) {
         /* lib.rs:918-927.  CANON noise index: the reference draws once per candidate that has a travel
@@ -370,8 +452,7 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
          * travel cost, the n-th newest history entry uses n_known + n (whether or not earlier entries were
          * kept); two draws per Philox block: indices i and i + 32 of every run of 64 share a block,
          * block = (i / 64) * 32 + i % 32, words (0,1) if i % 64 < 32, else (2,3). */
-        h.rng.draw(h.t, family.id, P_NOISE, ((noise_index >> 6) << 5) | (noise_index & 31u), out);
-        const double u = (noise_index & 32u) ? u53(out[2], out[3]) : u53(out[0], out[1]);
+        const double u = draw_noise(h.rng, h.t, family.id, noise_index);
         const double g = gain * u - l_cost;
         if (g > m) {
             target = q;
@@ -390,22 +471,14 @@ Decision decide_on_moving(oracle_handle &h, const Family &family, const uint32_t
         consider(known[i], harvest, c, n_considered++);
     }
     /* family.history.iter().rev().filter_map(...), lib.rs:854-867 */
-    size_t n = 0;
-    for (auto it = family.history.rbegin(); it != family.history.rend(); ++it, ++n) {
-        if (n >= h.mem_table.size()) break; /* memory < f64::EPSILON from here on, lib.rs:856 */
-        const double memory = h.mem_table[n];
-        /* CANON: `fastrand::f64() < memory` (lib.rs:859) with a 40-bit uniform U_n = (B_n * 2^32 + W_n) * 2^-40:
-         * B_n = byte n&15 of Philox block n>>4 of the MEM stream (16 entries per block), W_n = word n&3 of
-         * block n>>2 of the MEM2 stream.  (The device evaluates W_n only when B_n alone does not decide.) */
-        h.rng.draw(h.t, family.id, P_MEM, (uint32_t)(n >> 4), out);
-        const uint64_t b = (out[(n >> 2) & 3] >> (8 * (n & 3))) & 0xFFu;
-        h.rng.draw(h.t, family.id, P_MEM2, (uint32_t)(n >> 2), out);
-        const uint64_t x = (b << 32) | out[n & 3];
-        const double u = (double)x * (1.0 / 1099511627776.0);
-        if (!(u < memory)) continue;
+    std::vector<uint32_t> kept;
+    remembered_entries(h.rng, h.t, family.id, (uint32_t)std::min<size_t>(family.history.size(), h.mem_table.size()), h.mem_table,
+                       h.mem_tail0, h.mem_tail, kept);
+    for (const uint32_t n : kept) {
+        const auto &entry = family.history[family.history.size() - 1 - n];
         double c;
-        if (!cost_of(it->first, &c)) continue;
-        consider(it->first, it->second, c, (uint32_t)(n_known + n));
+        if (!cost_of(entry.first, &c)) continue;
+        consider(entry.first, entry.second, c, (uint32_t)(n_known + n));
     }
     return Decision{target, t_cost};
 }
@@ -529,7 +602,6 @@ void update_each_family_step(oracle_handle &h) {
 /* ------------------------------------------------------------------------------------------ *
  * 4.8/4.10 Interaction and collectives (lib.rs:1196-1246, 1351-1418)
  * ------------------------------------------------------------------------------------------ */
-bool fight_is_deadly(uint32_t word, uint32_t fight_deadliness) { return word < fight_deadliness; } /* lib.rs:1325 */
 
 /* `Band` is missing from the reference; inferred from lib.rs:1390-1393 as {culture, families}.
  * Each member's position in the shuffled list is carried alongside so that the fight draws can be
@@ -545,21 +617,21 @@ struct PBand {
 
 bool encounter_maybe_join(oracle_handle &h, Family *family, PBand &group) {
     bool join = true;
-    uint32_t out[4];
     for (Member &other : group.families) {
         Family *other_family = other.family;
         if (!will_cooperate(family->culture, other_family->culture, h.p)) {
             join = false;
             const uint64_t reduction = std::min(family->effective_size, other_family->effective_size);
-            h.rng.draw(h.t, family->id, P_FIGHT, other.position, out);
-            if (fight_is_deadly(out[0], h.p.fight_deadliness)) {
+            bool other_hit, self_hit;
+            draw_fight(h.rng, h.t, family->id, other.position, h.p.fight_deadliness, &other_hit, &self_hit);
+            if (other_hit) {
                 other_family->effective_size -= reduction;
                 if (other_family->effective_size == 0) {
                     family->stored_resources += other_family->stored_resources;
                     other_family->stored_resources = 0.0;
                 }
             }
-            if (fight_is_deadly(out[1], h.p.fight_deadliness)) family->effective_size -= reduction;
+            if (self_hit) family->effective_size -= reduction;
         }
     }
     return join;
@@ -572,11 +644,7 @@ std::vector<PBand> cooperate_or_fight(oracle_handle &h, uint32_t node, std::vect
      * does not depend on the order the families were pushed (lib.rs:607-612 is a parallel push). */
     std::vector<std::pair<std::pair<uint64_t, uint64_t>, Family *>> keyed;
     keyed.reserve(families_in_this_location.size());
-    uint32_t out[4];
-    for (Family *f : families_in_this_location) {
-        h.rng.draw(h.t, f->id, P_SHUF, 0, out);
-        keyed.push_back({{((uint64_t)out[1] << 32) | out[0], f->id}, f});
-    }
+    for (Family *f : families_in_this_location) keyed.push_back({{draw_shuffle_key(h.rng, h.t, f->id), f->id}, f});
     std::sort(keyed.begin(), keyed.end(),
               [](const auto &a, const auto &b) { return a.first < b.first; });
 
@@ -599,9 +667,7 @@ std::vector<PBand> cooperate_or_fight(oracle_handle &h, uint32_t node, std::vect
     for (uint32_t b = 0; b < bands.size(); ++b) {
         PBand &band = bands[b];
         /* select_pivot_family, lib.rs:1295-1298: fastrand::usize(0..len) */
-        h.rng.draw(h.t, node, P_PIVOT, b, out);
-        const uint64_t r = ((uint64_t)out[1] << 32) | out[0];
-        const uint64_t index = (uint64_t)(((unsigned __int128)r * (unsigned __int128)band.families.size()) >> 64);
+        const uint64_t index = draw_pivot(h.rng, h.t, node, b, band.families.size());
         band.culture = band.families[index].family->culture;
         uint64_t bandsize = 0;
         for (Member &m : band.families) bandsize += m.family->effective_size;
@@ -737,9 +803,7 @@ void distribute_each_patch_resources_step(oracle_handle &h) {
             double res = exploit_ecoregion(&h, groups, h.g.eco_id[k], h.res[k],
                                            h.p.maximum_resources_one_adult_can_harvest, h.p.season_length_in_years,
                                            h.p.minimum_adaptation, &errors);
-            uint32_t out[4];
-            h.rng.draw(h.t, patch_id, P_REGROW, (uint32_t)(k - h.g.eco_off[patch_id]), out);
-            const double proportion = 2.0 * u53(out[0], out[1]); /* lib.rs:1309-1311 */
+            const double proportion = draw_regrowth(h.rng, h.t, patch_id, (uint32_t)(k - h.g.eco_off[patch_id]));
             h.res[k] = recover(res, h.max_res[k], h.p.resource_recovery_per_season, proportion);
         }
     }
@@ -762,6 +826,21 @@ void build_mem_table(oracle_handle &h) {
     while (!(memory < std::numeric_limits<double>::epsilon()) && h.mem_table.size() < (1u << 20)) {
         h.mem_table.push_back(memory);
         memory *= memory_decay_per_season;
+    }
+    /* CANON stream v2: the head is made of the leading 16-entry blocks that hold an entry with memory_n >= 2^-8 (top
+     * byte of ceil(memory_n * 2^40) non-zero), at most 16 blocks; the entries after it are sampled by skipping */
+    uint32_t head_blocks = 0;
+    for (size_t k = 0; k < h.mem_table.size(); ++k) {
+        const double c = std::ceil(h.mem_table[k] * 1099511627776.0);
+        if (c >= 4294967296.0) head_blocks = (uint32_t)(k / 16u) + 1u;
+    }
+    if (head_blocks > 16u) head_blocks = 16u;
+    h.mem_tail0 = 16u * head_blocks;
+    h.mem_tail.clear();
+    double survive = 1.0;
+    for (size_t k = h.mem_tail0; k < h.mem_table.size(); ++k) {
+        survive = survive * (1.0 - h.mem_table[k]);
+        h.mem_tail.push_back(survive);
     }
 }
 
@@ -1153,6 +1232,61 @@ int oracle_will_cooperate(uint64_t a, uint64_t b, uint32_t threshold, int inclus
     p.cooperation_threshold = threshold;
     p.cooperation_inclusive = inclusive ? 1 : 0;
     return will_cooperate(a, b, p) ? 1 : 0;
+}
+
+/* ---- the canonical draws, for tests/test_oracle_stats.py (distribution of each draw against the reference's formula) */
+static Stream stream_of_seed(uint64_t seed) {
+    Stream r;
+    r.key[0] = (uint32_t)seed;
+    r.key[1] = (uint32_t)(seed >> 32);
+    return r;
+}
+/* kept[n] = 1 iff the family remembers its n-th newest history entry this step (lib.rs:854-866); returns n_mem */
+uint32_t oracle_draw_remembered(double season, uint64_t seed, uint64_t step, uint64_t fid, uint32_t len, uint8_t *kept) {
+    oracle_handle h;
+    h.p.season_length_in_years = season;
+    build_mem_table(h);
+    std::vector<uint32_t> k;
+    const uint32_t n = (uint32_t)std::min<size_t>(len, h.mem_table.size());
+    remembered_entries(stream_of_seed(seed), step, fid, n, h.mem_table, h.mem_tail0, h.mem_tail, k);
+    std::memset(kept, 0, len);
+    for (uint32_t e : k) kept[e] = 1;
+    return (uint32_t)h.mem_table.size();
+}
+double oracle_draw_noise(uint64_t seed, uint64_t step, uint64_t fid, uint32_t index) { return draw_noise(stream_of_seed(seed), step, fid, index); }
+uint64_t oracle_draw_shuffle_key(uint64_t seed, uint64_t step, uint64_t fid) { return draw_shuffle_key(stream_of_seed(seed), step, fid); }
+void oracle_draw_fight(uint64_t seed, uint64_t step, uint64_t fid, uint32_t position, uint32_t deadliness, int out[2]) {
+    bool a, b;
+    draw_fight(stream_of_seed(seed), step, fid, position, deadliness, &a, &b);
+    out[0] = a;
+    out[1] = b;
+}
+uint64_t oracle_draw_pivot(uint64_t seed, uint64_t step, uint64_t node, uint32_t band, uint64_t len) {
+    return draw_pivot(stream_of_seed(seed), step, node, band, len);
+}
+double oracle_draw_regrowth(uint64_t seed, uint64_t step, uint64_t node, uint32_t slot) { return draw_regrowth(stream_of_seed(seed), step, node, slot); }
+/* the mutation draws of one family and step through `mutate` itself (lib.rs:1754-1785): clock[0] = the clock drawn for a
+ * family without one, clock[1] = the clock drawn after a flip, *bit = the bit flipped when the clock is at zero */
+void oracle_draw_mutation(uint64_t seed, uint64_t step, uint64_t fid, double rate, uint32_t clock[2], uint32_t *bit) {
+    oracle_handle h;
+    oracle_default_params(&h.p);
+    h.p.culture_mutation_rate = rate;
+    h.rng = stream_of_seed(seed);
+    h.t = step;
+    Family f;
+    f.id = fid;
+    f.has_mutation_clock = false;
+    mutate(h, f, 0);                      /* None: draws clock[0] (then decrements it, or flips at once when it is 0) */
+    uint32_t a[4];
+    h.rng.draw(step, fid, P_MUT, 0, a);
+    clock[0] = time_till_next_mutation(u53(a[0], a[1]), rate);
+    f = Family();
+    f.id = fid;
+    f.has_mutation_clock = true;
+    f.seasons_till_next_mutation = 0;
+    mutate(h, f, 0);                      /* Some(0): flips one bit of culture 0 and redraws */
+    *bit = (uint32_t)__builtin_ctzll(f.culture);
+    clock[1] = f.seasons_till_next_mutation;
 }
 
 void oracle_constants(double season, uint32_t *adult_reset, uint32_t *grow_reset, double *range_s, double *cost_per_s,

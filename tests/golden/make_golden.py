@@ -21,6 +21,9 @@ CASES = {
     "mixed_hostility": (30, 36, 300, 0, 0, 30, {"cooperation_threshold": 30}),
     "peaceful_growth": (24, 30, 120, 0, 0, 40, {"cooperation_threshold": 65}),
     "dense_history": (16, 20, 600, 5, 30, 6, {"maximum_resources_one_adult_can_harvest": 0.25}),
+    # histories longer than the memory loop reaches (625 entries at season 1/6): the head of the memory draws AND the
+    # skip-sampled tail (canonical stream v2)
+    "long_memory": (20, 24, 60, 0, 700, 12, {}),
 }
 
 
