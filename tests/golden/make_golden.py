@@ -27,8 +27,23 @@ CASES = {
 }
 
 
+HIST_KEEP = 628   # the default history ring of the device path at season 1/6: every entry the memory loop can sample (625), rounded up to 4
+
+
+def trim_histories(f, keep):
+    """The newest `keep` entries of every history: the oracle keeps the reference's unbounded vector (lib.rs:218), the
+    device path a ring of the entries the memory loop of lib.rs:854-866 can still reach."""
+    lens = np.diff(f.hist_off.astype(np.int64))
+    new_lens = np.minimum(lens, keep)
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(new_lens)
+    idx = np.concatenate([np.arange(int(f.hist_off[i + 1]) - int(new_lens[i]), int(f.hist_off[i + 1])) for i in range(len(lens))] + [np.zeros(0, np.int64)]).astype(np.int64)
+    f.hist_patch, f.hist_harvest, f.hist_off = f.hist_patch[idx], f.hist_harvest[idx], off
+
+
 def state_arrays(sim):
     f = sim.get_families()
+    trim_histories(f, HIST_KEEP)
     res, _ = sim.get_patches()
     node, cult, size = sim.get_storage()
     out = {name: getattr(f, name) for name, _ in D._FAM_FIELDS}
