@@ -18,6 +18,8 @@ static inline void dsim_mbar_expect_tx(dsim_mbar *, unsigned) {}
 static inline void dsim_mbar_wait(dsim_mbar *, unsigned) { __syncwarp(); } /* the copies are made by the lanes themselves: wait for all of them */
 static inline void dsim_bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, dsim_mbar *) { std::memcpy(smem_dst, gsrc, bytes); }
 static inline void dsim_cp_async16(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 16); }
+static inline void dsim_cp_async8(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 8); }
+static inline void dsim_cp_async4(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 4); }
 static inline void dsim_cp_async_commit() {}
 static inline void dsim_cp_async_wait_all() {}
 static inline void dsim_fence_proxy_async() {}
@@ -52,6 +54,12 @@ __device__ __forceinline__ void dsim_bulk_g2s(void *smem_dst, const void *gsrc, 
 }
 __device__ __forceinline__ void dsim_cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dsim_cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dsim_cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void dsim_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void dsim_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

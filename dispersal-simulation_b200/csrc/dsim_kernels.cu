@@ -513,6 +513,7 @@ struct __align__(16) MoveTile { /* per warp */
     uint32_t loc[MOVE_WF], size[MOVE_WF], hs[MOVE_WF], hist_cnt[MOVE_WF], nh[MOVE_WF];
     uint32_t row_start[MOVE_WF], row_len[MOVE_WF], ns[MOVE_WF], n_near[MOVE_WF];
     uint32_t idx[MOVE_WF], newpos[MOVE_WF], crank[MOVE_WF], misc[MOVE_WF], newest[MOVE_WF];
+    uint32_t till_adult[MOVE_WF], till_mut[MOVE_WF];
     uint32_t tj0[MOVE_WF], td[MOVE_WF], ntail[MOVE_WF], tmore[MOVE_WF]; /* tail sampling state (mem_tail_run) */
     uint32_t tail[MOVE_WF][MOVE_TAILQ];    /* kept tail entries */
     uint32_t list[MOVE_LCAP];              /* kept entries of the tile: family << 24 | entry, family-major, ascending */
@@ -543,6 +544,19 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
     const uint32_t HB = a.mc.mem_head;          /* head blocks; item j == HB of a family is its tail */
     const uint32_t n_items = MOVE_WF * (HB + 1u);
     uint32_t phase = 0;                         /* parity of the mbarrier phase the next wait completes */
+    uint32_t pend_pos = 0xFFFFFFFFu, pend_slot = 0; /* arrival rank of this lane's last family, not yet written */
+    /* staging of the remembered-patch look-ups, in the arrays of the sensed phase (dead by then): ring entries (node,
+     * harvest), index buckets | row entries (cost, node) | noise draws */
+    static_assert(28u * MOVE_LCAP <= sizeof(S.view) && 12u * MOVE_LCAP <= sizeof(S.r_cost) && 8u * MOVE_LCAP <= sizeof(S.r_dst) &&
+                      MOVE_LCAP % 32u == 0u,
+                  "MOVE_LCAP entries must fit the staging arrays");
+    unsigned char *const st_view = reinterpret_cast<unsigned char *>(&S.view[0][0]);
+    uint32_t *const rq = reinterpret_cast<uint32_t *>(st_view);
+    double *const rgain = reinterpret_cast<double *>(st_view + 4u * MOVE_LCAP);
+    uint4 *const rbk = reinterpret_cast<uint4 *>(st_view + 12u * MOVE_LCAP);
+    double *const rc = &S.r_cost[0][0];
+    uint32_t *const rdq = reinterpret_cast<uint32_t *>(&S.r_cost[0][0] + MOVE_LCAP);
+    double *const ru = reinterpret_cast<double *>(&S.r_dst[0][0]);
 
     if (lane == 0) dsim_mbar_init(&S.bar, 1u);
     __syncwarp();
@@ -574,6 +588,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 const uint32_t hs = a.cur.hs[i], loc = a.cur.loc[i], size = a.cur.size[i], misc = a.cur.misc[i];
                 const uint64_t fid = a.cur.id[i], culture = a.cur.culture[i];
                 const double stored = a.cur.stored[i], last_harvest = a.cur.last_harvest[i];
+                const uint32_t till_adult = a.cur.till_adult[i], till_mut = a.cur.till_mut[i];
                 /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
                 const uint32_t pre = a.sc.word_pre[c], va = pre & 0xFFFFu, vs = pre >> 16;
                 const RowHdr hd = a.rt.hdr[loc];
@@ -583,6 +598,8 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                     a.sc.dead_hs[i - newpos] = hs; /* dropped by `retain`, lib.rs:541: hand the heavy slot back */
                 } else if (newpos < cap) {         /* else: capacity error already flagged by k_lifecycle's tail */
                     state = 1u | (((split_mask >> (i & 31u)) & 1u) << 1);
+                    S.till_adult[lane] = till_adult;
+                    S.till_mut[lane] = till_mut;
                     S.fid[lane] = fid;
                     S.culture[lane] = culture;
                     S.stored[lane] = stored;
@@ -774,51 +791,95 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 const uint32_t total = run;
                 if (total <= win) break;
                 const uint32_t nwin = total - win < MOVE_LCAP ? total - win : MOVE_LCAP;
+                /* The look-up of a remembered patch is a chain of three dependent loads: ring entry -> bucket of the
+                 * reach row's index -> row entry (node to verify the bucket's answer, cost).  Every level is requested for
+                 * ALL the listed entries at once — cp.async into the staging arrays, which the sensed phase no longer needs —
+                 * so a tile pays three memory round trips here, not three per pass.  Lane L owns entries L, L + 32, ... */
+                uint32_t verify = 0, search = 0; /* per pass of this lane: row entry requested / needs the binary search */
+#pragma unroll
+                for (uint32_t p = 0; p < MOVE_LCAP / 32u; ++p) {
+                    const uint32_t i = 32u * p + lane;
+                    if (i < nwin) {
+                        const uint32_t item = S.list[i], f = item >> 24, nn = item & 0xFFFFFFu; /* entry nn of family f, 0 = newest */
+                        const uint32_t newest = S.newest[f];
+                        const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
+                        const size_t hb = (size_t)S.hs[f] * hcap;
+                        dsim_cp_async4(&rq[i], &a.hv.hist_patch[hb + pos]);
+                        dsim_cp_async8(&rgain[i], &a.hv.hist_harv[hb + pos]);
+                    }
+                }
+                dsim_cp_async_commit();
+#pragma unroll
+                for (uint32_t p = 0; p < MOVE_LCAP / 32u; ++p) { /* the noise draws, while the ring entries are in flight */
+                    const uint32_t i = 32u * p + lane;
+                    if (i < nwin) {
+                        const uint32_t item = S.list[i], f = item >> 24, nn = item & 0xFFFFFFu;
+                        ru[i] = noise_draw(a.mc, step, S.fid[f], S.n_near[f] + nn);
+                    }
+                }
+                dsim_cp_async_wait_all();
+#pragma unroll
+                for (uint32_t p = 0; p < MOVE_LCAP / 32u; ++p) {
+                    const uint32_t i = 32u * p + lane;
+                    if (i < nwin) {
+                        const uint32_t f = S.list[i] >> 24;
+                        if (S.row_len[f] <= DSIM_ROW_HASH_MAX) dsim_cp_async16(&rbk[i], bucket_of(a.rt.hash + (size_t)S.loc[f] * 256u, rq[i]));
+                    }
+                }
+                dsim_cp_async_commit();
+                dsim_cp_async_wait_all();
+#pragma unroll
+                for (uint32_t p = 0; p < MOVE_LCAP / 32u; ++p) {
+                    const uint32_t i = 32u * p + lane;
+                    if (i < nwin) {
+                        const uint32_t f = S.list[i] >> 24, r_len = S.row_len[f];
+                        if (r_len <= DSIM_ROW_HASH_MAX) {
+                            const uint32_t bp = bucket_probe(rbk[i], rq[i]);
+                            if (bp == ROW_ABSENT) {
+                                /* no travel cost from here: not a candidate (lib.rs:869) */
+                            } else if (bp < r_len) {
+                                dsim_cp_async4(&rdq[i], a.rt.dst + S.row_start[f] + bp);
+                                dsim_cp_async8(&rc[i], a.rt.cost + S.row_start[f] + bp);
+                                verify |= 1u << p;
+                            } else {
+                                search |= 1u << p;
+                            }
+                        } else {
+                            search |= 1u << p;
+                        }
+                    }
+                }
+                dsim_cp_async_commit();
+                dsim_cp_async_wait_all();
                 for (uint32_t p0 = 0; p0 < nwin; p0 += 32u) {
-                    const bool on = p0 + lane < nwin;
-                    const uint32_t item = S.list[on ? p0 + lane : p0];
-                    const uint32_t f = item >> 24, nn = item & 0xFFFFFFu; /* entry nn of family f, 0 = newest */
+                    const uint32_t p = p0 >> 5, i = p0 + lane;
+                    const bool on = i < nwin;
+                    const uint32_t item = S.list[on ? i : p0];
+                    const uint32_t f = item >> 24;
                     bool cand = false;
                     double g = 0.0, gain = 0.0, cost = 0.0;
                     uint32_t q = 0;
                     if (on) {
-                        const uint32_t newest = S.newest[f];
-                        const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
-                        const size_t hb = (size_t)S.hs[f] * hcap;
-                        q = a.hv.hist_patch[hb + pos];
-                        gain = a.hv.hist_harv[hb + pos];
-                        const uint32_t r_len = S.row_len[f], r_ns = S.ns[f];
-                        const uint32_t *r_dst = a.rt.dst + S.row_start[f];
-                        const double *r_cost = a.rt.cost + S.row_start[f];
-                        const uint16_t *r_hash = r_len <= DSIM_ROW_HASH_MAX ? a.rt.hash + (size_t)S.loc[f] * 256u : nullptr;
-                        /* the chain entry -> bucket -> row is three dependent loads: the draw is computed while the
-                         * bucket is in flight, and the cost is requested together with the row entry that verifies
-                         * the bucket's answer */
-                        uint32_t idx = ROW_SEARCH;
-                        uint4 bk = make_uint4(0u, 0u, 0u, 0u);
-                        if (r_hash != nullptr) bk = *bucket_of(r_hash, q);
-                        const double u = noise_draw(a.mc, step, S.fid[f], S.n_near[f] + nn);
-                        if (r_hash != nullptr) {
-                            const uint32_t bp = bucket_probe(bk, q);
-                            if (bp == ROW_ABSENT) {
-                                idx = ROW_ABSENT;
-                            } else if (bp < r_len) {
-                                const uint32_t dq = r_dst[bp];
-                                const double c = r_cost[bp];
-                                if (dq == q) {
-                                    idx = bp;
-                                    cost = c;
-                                }
+                        q = rq[i];
+                        gain = rgain[i];
+                        bool do_search = ((search >> p) & 1u) != 0u;
+                        if ((verify >> p) & 1u) {
+                            if (rdq[i] == q) { /* the bucket's answer holds */
+                                cost = rc[i];
+                                cand = true;
+                            } else {           /* tag collision (1/256 per slot) */
+                                do_search = true;
                             }
                         }
-                        if (idx == ROW_SEARCH) {
-                            idx = row_find_sorted(r_dst, r_ns, r_len, q);
-                            if (idx != ROW_ABSENT) cost = r_cost[idx];
+                        if (do_search) {
+                            const uint32_t *r_dst = a.rt.dst + S.row_start[f];
+                            const uint32_t idx = row_find_sorted(r_dst, S.ns[f], S.row_len[f], q);
+                            if (idx != ROW_ABSENT) {
+                                cost = a.rt.cost[S.row_start[f] + idx];
+                                cand = true;
+                            }
                         }
-                        if (idx != ROW_ABSENT) { /* else: no travel cost from here, not a candidate (lib.rs:869) */
-                            g = gain * u - cost;
-                            cand = true;
-                        }
+                        if (cand) g = gain * ru[i] - cost;
                     }
                     /* ordered acceptance, one family of the pass after the other (the list is family-major) */
                     const uint32_t n_act = nwin - p0 < 32u ? nwin - p0 : 32u;
@@ -829,8 +890,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                         ch.max_gain = S.max_gain[ff];
                         ch.t_cost = S.t_cost[ff];
                         ch.m = S.m[ff];
-                        __syncwarp();
-                        accept_scan_warp(ch, on && cand && f == ff, g, gain, cost, q);
+                        accept_scan_warp(ch, cand && f == ff, g, gain, cost, q);
                         if (lane == 0) {
                             S.target[ff] = ch.target;
                             S.max_gain[ff] = ch.max_gain;
@@ -867,7 +927,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
         /* ---- epilogue: lane f ---------------------------------------------------------------------- */
         if (state & 1u) {
             const uint32_t loc = S.loc[lane], hs = S.hs[lane], hist_cnt = S.hist_cnt[lane];
-            const uint32_t i = S.idx[lane], newpos = S.newpos[lane];
+            const uint32_t newpos = S.newpos[lane];
             const uint64_t fid = S.fid[lane], culture = S.culture[lane];
             const double last_harvest = S.last_harvest[lane];
             uint32_t misc = S.misc[lane];
@@ -909,14 +969,17 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             a.next.last_harvest[newpos] = 0.0;
             a.next.loc[newpos] = newloc;
             a.next.size[newpos] = size;
-            a.next.till_adult[newpos] = a.cur.till_adult[i];
-            a.next.till_mut[newpos] = a.cur.till_mut[i];
+            a.next.till_adult[newpos] = S.till_adult[lane];
+            a.next.till_mut[newpos] = S.till_mut[lane];
             a.next.misc[newpos] = misc;
             a.next.hs[newpos] = hs;
+            /* arrival at the new node = histogram of the counting sort by patch.  The rank the atomic returns is
+             * written when the NEXT tile gets here (or after the last one): nothing of this tile waits for it. */
+            if (pend_pos != 0xFFFFFFFFu) a.sc.fslot[pend_pos] = pend_slot;
+            pend_pos = 0xFFFFFFFFu;
             if (!a.mg.enabled || (newloc >= a.mg.own_lo && newloc < a.mg.own_hi)) {
-                const uint32_t slot = atomicAdd(&a.ps.cnt[newloc], 1u);
-                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = newloc;
-                a.sc.fslot[newpos] = slot;
+                pend_slot = atomicAdd(&a.ps.cnt[newloc], 1u);
+                pend_pos = newpos;
             } else {
                 a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
             }
@@ -924,6 +987,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
         __syncwarp();
         tile = __shfl_sync(DSIM_FULL, next_tile, 0);
     }
+    if (pend_pos != 0xFFFFFFFFu) a.sc.fslot[pend_pos] = pend_slot;
 }
 
 /* part 1d: the children of this step (lib.rs:1840-1855, 1877-1895), one WARP per child: there are few
@@ -1154,9 +1218,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             a.next.misc[cpos] = 0u;
             a.next.hs[cpos] = chs;
             if (!a.mg.enabled || (cc.target >= a.mg.own_lo && cc.target < a.mg.own_hi)) {
-                const uint32_t slot = atomicAdd(&a.ps.cnt[cc.target], 1u);
-                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = cc.target;
-                a.sc.fslot[cpos] = slot;
+                a.sc.fslot[cpos] = atomicAdd(&a.ps.cnt[cc.target], 1u);
             } else {
                 a.sc.fslot[cpos] = 0xFFFFFFFFu;
             }
@@ -1168,23 +1230,51 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
 /* ------------------------------------------------------------------------------------------ *
  * part 2a/2b: counting sort by node (families_by_location, lib.rs:602-612)
  * ------------------------------------------------------------------------------------------ */
+/* warp-aggregated append: the lanes with `pred` get consecutive positions from *counter (one atomic per warp) */
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred, uint32_t lane) {
+    const uint32_t m = __ballot_sync(DSIM_FULL, pred);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(DSIM_FULL, base, 0);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
+    /* One thread per family.  The first arrival at a node (rank 0 of the histogram that k_move, k_children and
+     * k_mg_unpack counted) speaks for the node: it claims the node's segment of `members`, lists the node as occupied
+     * and hands it to the patch kernel for its family count.  Every counter is bumped once per warp. */
     DevCtl *ctl = a.ctl;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const uint32_t n_occ = ctl->n_occ[a.occ_par];
-    for (uint32_t k = tid; k < n_occ; k += nth) {
-        const uint32_t p = a.sc.occ[a.occ_par][k];
-        const uint32_t c = a.ps.cnt[p];
-        a.ps.seg[p] = atomicAdd(&ctl->seg_cursor, c);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = ctl->n_next;
+    const uint32_t n_round = (n + 31u) & ~31u; /* whole warps take part in the ballots */
+    for (uint32_t j = tid; j < n_round; j += nth) {
+        const bool first = j < n && a.sc.fslot[j] == 0u;
+        uint32_t p = 0, c = 0;
+        if (first) {
+            p = a.next.loc[j];
+            c = a.ps.cnt[p];
+        }
+        /* segment starts: exclusive scan of the counts over the warp + one atomic for the warp's total */
+        const uint32_t incl = warp_incl_scan_u32(c, lane);
+        uint32_t base = 0;
+        const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
+        if (lane == 0 && total) base = atomicAdd(&ctl->seg_cursor, total);
+        base = __shfl_sync(DSIM_FULL, base, 0);
+        if (first) a.ps.seg[p] = base + incl - c;
+        const uint32_t k_occ = warp_append(&ctl->n_occ[a.occ_par], first, lane);
+        if (first) a.sc.occ[a.occ_par][k_occ] = p;
         /* by family count: a thread, eight lanes, a warp or a block per node */
-        if (c == 1u && a.small_max >= 1u)
-            a.sc.plist_one[atomicAdd(&ctl->n_one, 1u)] = p;
-        else if (c <= a.small_max)
-            a.sc.plist_small[atomicAdd(&ctl->n_small, 1u)] = p;
-        else if (c <= a.mid_max)
-            a.sc.plist_mid[atomicAdd(&ctl->n_mid, 1u)] = p;
-        else
-            a.sc.plist_big[atomicAdd(&ctl->n_big, 1u)] = p;
+        const bool one = first && c == 1u && a.small_max >= 1u;
+        const bool small = first && !one && c <= a.small_max;
+        const bool mid = first && !one && !small && c <= a.mid_max;
+        const bool big = first && !one && !small && !mid;
+        const uint32_t k_one = warp_append(&ctl->n_one, one, lane), k_small = warp_append(&ctl->n_small, small, lane);
+        const uint32_t k_mid = warp_append(&ctl->n_mid, mid, lane), k_big = warp_append(&ctl->n_big, big, lane);
+        if (one) a.sc.plist_one[k_one] = p;
+        if (small) a.sc.plist_small[k_small] = p;
+        if (mid) a.sc.plist_mid[k_mid] = p;
+        if (big) a.sc.plist_big[k_big] = p;
     }
     if (a.mg.enabled) return; /* the multi-GPU step recycles heavy slots in k_mg_finish (emigrants, immigrants) */
     /* heavy slots vacated this step go onto the free stack, above what the children did not pop */
@@ -1921,7 +2011,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
     case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, MOVE_MIN_BLOCKS), MOVE_WARPS * 32, 0, s, a); break;
     case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
-    case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 4), 256, 0, s, a); break;
+    case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 8), 256, 0, s, a); break;
     case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
     case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
     case DSIM_K_PATCH_MID: DSIM_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;

@@ -228,9 +228,7 @@ __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
                 a.hv.hist_cnt[hs] = valid;
                 a.hv.decay[hs] = w[6];
                 a.hv.birth_index[hs] = (uint16_t)w[7];
-                const uint32_t slot = atomicAdd(&a.ps.cnt[loc], 1u);
-                if (slot == 0u) a.sc.occ[a.occ_par][atomicAdd(&ctl->n_occ[a.occ_par], 1u)] = loc;
-                mb.fslot2[p] = slot;
+                mb.fslot2[p] = atomicAdd(&a.ps.cnt[loc], 1u); /* rank 0 = first arrival: k_segments lists the node */
             }
         }
         base += m;

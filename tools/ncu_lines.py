@@ -5,15 +5,20 @@ import csv, subprocess, sys
 rep = sys.argv[1]; kern = sys.argv[2] if len(sys.argv) > 2 else ""; top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-blocks = []; cur = None
+blocks = []; cur = None; path = ""
 for r in rows:
-    if r and r[0] == "Function Name": cur = {"name": r[1], "rows": [], "hdr": None}; blocks.append(cur)
+    if r and r[0] == "File Path": path = r[1].split("/")[-1]
+    if r and r[0] == "Function Name": cur = {"name": r[1], "rows": [], "hdr": None, "file": path}; blocks.append(cur)
     elif r and r[0] == "Line No" and cur is not None: cur["hdr"] = r
     elif cur is not None and cur["hdr"] is not None and len(r) >= len(cur["hdr"]): cur["rows"].append(r)
-seen = set()
+# one block per (function, source file): merge the files of a function
+merged = {}
 for b in blocks:
-    if kern not in b["name"] or b["name"] in seen: continue
-    seen.add(b["name"])
+    if kern not in b["name"] or b["hdr"] is None: continue
+    m = merged.setdefault(b["name"], {"name": b["name"], "hdr": b["hdr"], "rows": []})
+    for r in b["rows"]:
+        r = list(r); r[1] = b["file"] + ": " + r[1]; m["rows"].append(r)
+for b in merged.values():
     h = b["hdr"]; isamp = h.index("# Samples"); iinst = h.index("Instructions Executed")
     cols = {k: h.index(k) for k in ("stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_lg", "stall_math", "stall_no_inst", "stall_not_selected")}
     lines = []
