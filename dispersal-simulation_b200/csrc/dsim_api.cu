@@ -116,6 +116,11 @@ struct dsim_handle {
     pinned_vector<uint32_t> s_a_n;
 
     std::vector<uint32_t> storage_nodes; /* nodes named by dsim_set_storage */
+    std::vector<double> lon_h, lat_h;    /* node coordinates (movementgraph.rs:8) for the observer */
+    /* dsim_observe_population_counts keeps what it collected for the dsim_observe_population that follows */
+    std::vector<uint32_t> obs_node;
+    std::vector<uint64_t> obs_cult, obs_size;
+    bool obs_valid = false;
     std::string err;
 };
 
@@ -783,6 +788,8 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     h->seed = seed;
     h->n_nodes = n;
     h->n_eco = (uint32_t)n_eco;
+    if (g->lon) h->lon_h.assign(g->lon, g->lon + n);
+    if (g->lat) h->lat_h.assign(g->lat, g->lat + n);
     std::memset(&h->geom, 0, sizeof h->geom);
     h->geom.n_sm = (uint32_t)std::max(1, prop.multiProcessorCount);
     std::memset(&h->rt, 0, sizeof h->rt);
@@ -1331,6 +1338,46 @@ static int collect_storage(dsim_handle *h, std::vector<uint32_t> &node, std::vec
     return DSIM_OK;
 }
 
+int dsim_observe_population_counts(dsim_handle *h, uint64_t *n_nodes, uint64_t *n_entries) {
+    if (!h || !n_nodes || !n_entries) return DSIM_ERR_INVALID;
+    int rc = collect_storage(h, h->obs_node, h->obs_cult, h->obs_size);
+    if (rc) return rc;
+    h->obs_valid = true;
+    uint64_t nodes = 0;
+    for (size_t k = 0; k < h->obs_node.size(); ++k)
+        if (k == 0 || h->obs_node[k] != h->obs_node[k - 1]) ++nodes;
+    *n_nodes = nodes;
+    *n_entries = h->obs_node.size();
+    return DSIM_OK;
+}
+
+int dsim_observe_population(dsim_handle *h, uint32_t *node, double *lon, double *lat, uint64_t *off, uint64_t *culture,
+                            uint64_t *population) {
+    if (!h || !off) return DSIM_ERR_INVALID;
+    if (!h->obs_valid) {
+        int rc = collect_storage(h, h->obs_node, h->obs_cult, h->obs_size);
+        if (rc) return rc;
+    }
+    h->obs_valid = false;
+    uint64_t k_node = 0;
+    const size_t total = h->obs_node.size();
+    if ((total && (!node || !culture || !population))) return DSIM_ERR_INVALID;
+    for (size_t k = 0; k < total; ++k) {
+        const uint32_t v = h->obs_node[k];
+        if (k == 0 || v != h->obs_node[k - 1]) {
+            node[k_node] = v;
+            if (lon) lon[k_node] = h->lon_h.empty() ? 0.0 : h->lon_h[v];
+            if (lat) lat[k_node] = h->lat_h.empty() ? 0.0 : h->lat_h[v];
+            off[k_node] = k;
+            ++k_node;
+        }
+        culture[k] = h->obs_cult[k];
+        population[k] = h->obs_size[k];
+    }
+    off[k_node] = total;
+    return DSIM_OK;
+}
+
 int dsim_storage_count(dsim_handle *h, uint64_t *n) {
     if (!h || !n) return DSIM_ERR_INVALID;
     std::vector<uint32_t> node;
@@ -1426,6 +1473,7 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
     if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "dsim_step between the two parts of a step");
     int rc;
     h->snap_valid = false;
+    h->obs_valid = false;
     uint64_t births0 = 0, deaths0 = 0, updates0 = 0;
     if (stats) {
         if ((rc = sync_ctl(h))) return rc;

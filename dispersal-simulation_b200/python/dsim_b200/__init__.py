@@ -275,6 +275,8 @@ class Sim:
         }
         if self.prefix == "dsim_":
             sig["reach_digest"] = (C.c_int, [vp, u64p])
+            sig["observe_population_counts"] = (C.c_int, [vp, u64p, u64p])
+            sig["observe_population"] = (C.c_int, [vp, u32p, f64p, f64p, u64p, u64p, u64p])
         for name, (res, args) in sig.items():
             fn = self._f(name)
             fn.restype, fn.argtypes = res, args
@@ -427,6 +429,19 @@ class Sim:
                                          _ptr(reach_off, C.c_uint64), _ptr(reach_dst, C.c_uint32),
                                          _ptr(reach_cost, C.c_double)))
         return near_off, near_dst[:a.value], reach_off, reach_dst[:b.value], reach_cost[:b.value]
+
+    def observe_population(self):
+        """`print_population_by_location` (lib.rs:1443-1464) as arrays: (node, lon, lat, off, culture, population);
+        entries [off[k], off[k+1]) are the cultures of node[k]."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._f("observe_population_counts")(self.h, C.byref(a), C.byref(b)))
+        node = np.zeros(max(a.value, 1), np.uint32)
+        lon, lat = np.zeros(max(a.value, 1)), np.zeros(max(a.value, 1))
+        off = np.zeros(a.value + 1, np.uint64)
+        cult, pop = np.zeros(max(b.value, 1), np.uint64), np.zeros(max(b.value, 1), np.uint64)
+        self._check(self._f("observe_population")(self.h, _ptr(node, C.c_uint32), _ptr(lon, C.c_double), _ptr(lat, C.c_double),
+                                                  _ptr(off, C.c_uint64), _ptr(cult, C.c_uint64), _ptr(pop, C.c_uint64)))
+        return node[:a.value], lon[:a.value], lat[:a.value], off, cult[:b.value], pop[:b.value]
 
     def reach_digest(self):
         """Five order-independent digests of the reach table in HBM (headers, destinations, costs, bucket indices,

@@ -73,23 +73,38 @@ def _oyr_debug(c: float) -> str:
 
 def format_first_family(f: Families) -> str:
     """`println!("F: {:?}", families.get(0))` (lib.rs:652) with `Debug for Family` (src/debug.rs:10-21).
-    The `descendence` string of the reference ("A:1:3") is carried by the ABI as (id, parent id, birth index); the
-    line names the family by that triple."""
+    The `descendence` string of the reference ("A:1:3": the whole lineage, lib.rs:1880) is carried by the ABI as
+    (id, parent id, birth index); the line names a founder by its id and a descendant as "<parent id>:<birth index>" —
+    one level of the reference's name, unique per family, which is all plot.py:367-371 uses it for (a dictionary key)."""
     if f.n == 0:
         return "F: None"
     parent = int(f.parent_id[0])
     name = f"{int(f.id[0])}" if parent == NO_PARENT else f"{parent}:{int(f.birth_index[0])}"
-    return ("F: Some(Family { descendence: \"%s\", size: %d, location: NodeIndex(%d), culture: [%s], "
+    # `Binary for Culture` (lib.rs:260-272) writes the joined `{:b}` of the words through `write!(f, "{}", ..)`, so the
+    # `{:020b}` of src/debug.rs:17 neither pads nor brackets: the culture prints as its plain binary digits
+    return ("F: Some(Family { descendence: \"%s\", size: %d, location: NodeIndex(%d), culture: %s, "
             "stored_resources: %s, last_harvest: %s })") % (
-        name, int(f.size[0]), int(f.location[0]), format(int(f.culture[0]), "020b"),
+        name, int(f.size[0]), int(f.location[0]), format(int(f.culture[0]), "b"),
         _oyr_debug(float(f.stored[0])), _oyr_debug(float(f.last_harvest[0])))
+
+
+def format_observed_population(node, lon, lat, off, culture, population) -> str:
+    """The same line from what `dsim_observe_population` delivers (grouped per node, coordinates attached)."""
+    parts = []
+    for k in range(len(node)):
+        cults = ", ".join(f'"{int(culture[e]):x}": {int(population[e])}' for e in range(int(off[k]), int(off[k + 1])))
+        parts.append(f"({_rust_f64(float(lon[k]))}, {_rust_f64(float(lat[k]))}, {{{cults}}})")
+    return "POPULATION: [" + ", ".join(parts) + "]"
 
 
 def log_step(sim: Sim, t: int, out: TextIO):
     """The three lines `step` prints when `t % log_every == 0` (lib.rs:649-653)."""
     out.write(f"t: {t}\n")
-    node, culture, size = sim.get_storage()
-    out.write(format_population(sim.graph, node, culture, size) + "\n")
+    if sim.prefix == "dsim_":   # the product: the observer export of the C ABI
+        out.write(format_observed_population(*sim.observe_population()) + "\n")
+    else:                       # other libraries driven through the same binding (the test oracle): from the storage map
+        node, culture, size = sim.get_storage()
+        out.write(format_population(sim.graph, node, culture, size) + "\n")
     out.write(format_first_family(sim.get_families(history=False, adaptation=False)) + "\n")
 
 
@@ -184,7 +199,7 @@ def parse_log(text: str):
             content = [(x, y, n, int(c, 16)) for x, y, p in literal_eval(line[len("POPULATION: "):]) for c, n in p.items()]
             steps.append((t, content))
         elif line.startswith("F:"):
-            m = re.search(r'escendence: "([^"]*)".*ocation: NodeIndex\(([0-9]*)\),.*culture: \[?([01]*)', line)
+            m = re.search(r'escendence: "([^"]*)".*ocation: NodeIndex\(([0-9]*)\),.*culture: ([01]*)', line)
             if m:
                 path.append((m.group(1), int(m.group(2))))
     return steps, path

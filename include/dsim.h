@@ -184,6 +184,17 @@ int dsim_set_storage(dsim_handle *h, uint64_t n, const uint32_t *node, const uin
  * returns after enqueueing when stats == NULL, otherwise waits and fills *stats. */
 int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats);
 int dsim_sync(dsim_handle *h);
+/* `observation::print_population_by_location` (lib.rs:1443-1464): the linguistic landscape after the last step — for
+ * every occupied node its coordinates (`node.1`, `node.2` of the graph's node data) and the map band culture -> total
+ * population of the bands with that culture (`cultures_by_location`, lib.rs:615-647).  Grouped per node, nodes in
+ * ascending id, cultures ascending within a node: entries [off[k], off[k+1]) belong to node[k].
+ * Two calls: dsim_observe_population_counts for the sizes, then dsim_observe_population with arrays of
+ * n_nodes (node, lon, lat), n_nodes + 1 (off) and n_entries (culture, population) elements.  lon/lat are 0 when the
+ * graph was given without coordinates.  Host buffers, filled on demand (every `log_every` steps, lib.rs:649-653). */
+int dsim_observe_population_counts(dsim_handle *h, uint64_t *n_nodes, uint64_t *n_entries);
+int dsim_observe_population(dsim_handle *h, uint32_t *node, double *lon, double *lat, uint64_t *off, uint64_t *culture,
+                            uint64_t *population);
+
 /* As dsim_step with stats, and *device_ms receives the time between two CUDA events recorded on the
  * internal stream immediately before the first and after the last kernel of the n_steps steps. */
 int dsim_step_timed(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats, double *device_ms);

@@ -72,6 +72,7 @@ def _check_log_protocol(lib, synth, prefix, oracle):
         elif line.startswith("F:"):
             match = re.search(ref["f_regex"], line)
             assert match, line
+            assert match.group(3) and int(match.group(3), 2) < 2 ** 64, "plot.py's own expression reads the culture bits (src/debug.rs:17, lib.rs:260-272)"
             ref_path.append((match.group(1), int(match.group(2))))
     assert [c for _, c in ref_steps] == [c for _, c in steps]
     assert [ts for ts, _ in ref_steps] == [t * season for t, _ in steps]
