@@ -335,6 +335,14 @@ def main():
     os.environ.setdefault("DSIM_HOST_THREADS", str(max(1, len(os.sched_getaffinity(0)) // world)))
     lib = D.load()
     synth = D.load_synth()
+    # N > 1: before anything is timed, the transport the bench is about to use runs a small case (64x400 grid, 6000
+    # families, 30 steps) on all ranks and rank 0 compares every family column, every history and the resources with a
+    # single-GPU run of the same case, bit for bit (dsim_b200/mgcheck.py)
+    mg_ok, mg_detail = None, None
+    if world > 1:
+        from dsim_b200 import mgcheck
+        mg_ok, mg_detail = mgcheck.run_check(lib, synth, dist, rank, world, local_rank,
+                                             transport=os.environ.get("DSIM_MG_TRANSPORT", "peer"), log=log)
     # N > 1: weak scaling — 100k x N families on the same Americas-scale grid, split into N latitude bands of
     # about equal family counts; halo views and migrating families travel over NCCL.
     if world > 1:
@@ -543,6 +551,8 @@ def main():
             "roofline": roofline,
             "kernels": kernels,
             "mg_segments_ms": mg_segments,
+            "mg_bit_identical": mg_ok,
+            "mg_check": mg_detail,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches2 - launches1),

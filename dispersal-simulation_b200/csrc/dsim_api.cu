@@ -1754,7 +1754,7 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
         free_list(m->allocs);                                  \
         return rc;                                             \
     }
-    MA(mb.split_send, 1 + (size_t)mb.scap) MA(mb.split_recv, (size_t)world * (1 + (size_t)mb.scap))
+    MA(mb.split_send, 1 + (size_t)mb.scap) MA(mb.split_recv, 2 * (size_t)world * (1 + (size_t)mb.scap))
     MA(mb.child_grank, mb.scap) MA(mb.counters, MG_N_COUNTERS) MA(mb.emig_list, 2 * (size_t)mb.ecap)
     MA(mb.emig_hs, 2 * (size_t)mb.ecap) MA(mb.fslot2, h->cap)
     for (int s = 0; s < 2; ++s) {
@@ -1762,9 +1762,13 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
         MA(mb.halo_send[s], m->halo_bytes) MA(mb.halo_recv[s], m->halo_bytes)
         MA(mb.halo_cult[s], mb.ccap)
     }
-    MA(mb.seq, 1) MA(mb.done, 4) MA(mb.flags, MG_FLAG_SPLIT0 + DSIM_MG_MAX_WORLD)
+    MA(mb.seq, 1) MA(mb.done, 4) MA(mb.flags, MG_FLAG_SPLIT0 + 2 * DSIM_MG_MAX_WORLD)
 #undef MA
     CK(cudaStreamSynchronize(h->stream));
+#if !defined(DSIM_EMU)
+    for (auto &e : m->seg_ev)
+        if (!e) CK(cudaEventCreate(&e));
+#endif
     h->mg_enabled = true;
     h->mg_lo = m->own_lo;
     h->mg_hi = m->own_hi;
@@ -1905,7 +1909,6 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id) {
     ncclUniqueId id;
     std::memcpy(&id, unique_id, sizeof id);
     if (ncclCommInitRank(&m->comm, (int)m->world, id, (int)m->rank) != ncclSuccess) return fail(h, DSIM_ERR_COMM, "ncclCommInitRank failed");
-    for (auto &e : m->seg_ev) CK(cudaEventCreate(&e));
     m->nccl = true;
     return DSIM_OK;
 #endif
@@ -2051,7 +2054,8 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
 #if defined(DSIM_EMU)
     return fail(h, DSIM_ERR_COMM, "no transport: drive dsim_mg_phase yourself");
 #else
-    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or drive dsim_mg_phase yourself");
+    if (!m->nccl && !m->p2p)
+        return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or dsim_mg_ipc_connect, or drive dsim_mg_phase yourself");
     int rc = DSIM_OK;
     if (h->opt.use_graphs && !m->graph_failed && !h->profiling) {
         if (!m->gexec[m->occ_par]) {
@@ -2120,11 +2124,16 @@ int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set
 #if defined(DSIM_EMU)
     return fail(h, DSIM_ERR_COMM, "no transport");
 #else
-    if (!m->nccl) return fail(h, DSIM_ERR_COMM, "no transport");
+    if (!m->nccl && !m->p2p) return fail(h, DSIM_ERR_COMM, "no transport");
     int rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_PACK))) return rc;
-    const bool p2p = m->p2p; /* outside the steps there is no exchange round: always NCCL */
-    m->p2p = false;
+    const bool p2p = m->p2p;
+    if (m->nccl) {
+        m->p2p = false; /* with a communicator the exchange outside the steps is an NCCL operation (no exchange round) */
+    } else {        /* peer memory only: an exchange round of its own; every rank calls dsim_mg_halo_sync equally often */
+        dsim_mg_launch(DSIM_MGK_BUMP, mg_args(h, false), m->mb, h->geom, h->stream);
+        h->total_launches += 1;
+    }
     rc = mg_exchange(h, m, DSIM_MG_CH_HALO);
     m->p2p = p2p;
     if (rc) return rc;
@@ -2177,6 +2186,8 @@ void dsim_mg_release(dsim_handle *h) {
         if (g) cudaGraphExecDestroy(g);
     if (m->comm) ncclCommDestroy(m->comm);
     for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (auto &e : m->seg_ev)
+        if (e) cudaEventDestroy(e);
 #endif
     free_list(m->allocs);
     g_mg.erase(h);

@@ -47,11 +47,13 @@ __global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb)
     const size_t stride = 1 + (size_t)mb.scap;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    /* peer-memory transport: the lists of even and odd rounds arrive in two areas (see k_mg_push) */
+    const uint64_t *recv = mb.split_recv + (mb.p2p ? (size_t)(*mb.seq & 1u) * a.mg.world * stride : 0u);
     for (uint32_t c = gw; c < n_local; c += nw) {
         const uint64_t id = mb.split_send[1 + c];
         uint32_t smaller = 0;
         for (uint32_t r = 0; r < a.mg.world; ++r) {
-            const uint64_t *list = mb.split_recv + r * stride;
+            const uint64_t *list = recv + r * stride;
             const uint32_t m = (uint32_t)list[0];
             for (uint32_t k = lane; k < m; k += 32u) smaller += list[1 + k] < id ? 1u : 0u;
         }
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t total = 0;
-        for (uint32_t r = 0; r < a.mg.world; ++r) total += mb.split_recv[r * stride];
+        for (uint32_t r = 0; r < a.mg.world; ++r) total += recv[r * stride];
         ctl->next_id = ctl->child_id_base + total; /* k_lifecycle's tail had added the local count only */
         mb.counters[MG_N_STAY] = 0;
         mb.counters[MG_N_EMIG0] = 0;
@@ -293,9 +295,14 @@ __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb
 /* ---- peer-memory transport ------------------------------------------------------------------------------------
  * k_mg_push copies the USED part of a send buffer into the neighbour's receive buffer with 16-byte remote stores
  * (NVLink peer memory, mapped through CUDA IPC), then the last block to finish publishes the round number in the
- * neighbour's flag word; k_mg_wait spins on this rank's flag words until the round has arrived.  Buffers need no
- * double buffering: a rank cannot start the push of round r+1 on a channel before its neighbour has consumed round
- * r (it first has to receive that neighbour's later messages of round r). */
+ * neighbour's flag word; k_mg_wait spins on this rank's flag words until the round has arrived.
+ * EMIGRANTS and HALO (neighbour channels) need no double buffering: a rank cannot start the push of round r+1 on one
+ * of them before that neighbour has consumed round r (it first has to receive the neighbour's later messages of
+ * round r).  SPLIT is all-to-all, and nothing orders a rank's push of round r+1 after the consumption of round r
+ * (k_mg_child_rank, which runs after that rank's own k_move) on a rank three or more bands away: its receive area and
+ * flag words are therefore doubled by round parity.  Round r+2 cannot be pushed before every rank has pushed round
+ * r+1 (the pusher's HALO r+1 needs EMIGRANTS r+1 of its neighbour, which needs SPLIT r+1 of every rank), i.e. before
+ * every rank has consumed round r. */
 #if defined(DSIM_EMU)
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(256) k_mg_push(StepArgs a, MgBuffers mb, int c
     if (channel == DSIM_MG_CH_SPLIT) {
         const uint64_t words = 1u + mb.split_send[0]; /* count, ids: 8-byte words (a rank's slot is only 8-byte aligned) */
         for (uint32_t r = 0; r < a.mg.world; ++r) {
-            uint64_t *dst = mb.peer_split_recv[r] + (size_t)a.mg.rank * (1 + (size_t)mb.scap);
+            uint64_t *dst = mb.peer_split_recv[r] + ((size_t)(round & 1u) * a.mg.world + a.mg.rank) * (1 + (size_t)mb.scap);
             for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (uint64_t)gridDim.x * blockDim.x) dst[k] = mb.split_send[k];
         }
     } else {
@@ -349,7 +356,8 @@ __global__ void __launch_bounds__(256) k_mg_push(StepArgs a, MgBuffers mb, int c
             mb.done[channel] = 0u;
             fence_sys();
             if (channel == DSIM_MG_CH_SPLIT) {
-                for (uint32_t r = 0; r < a.mg.world; ++r) st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + a.mg.rank, round);
+                for (uint32_t r = 0; r < a.mg.world; ++r)
+                    st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + a.mg.rank, round);
             } else {
                 const uint32_t slot0 = channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0;
                 /* what I send to my lower neighbour (side 0) arrives from ITS upper side (slot 1), and vice versa */
@@ -364,13 +372,14 @@ __global__ void __launch_bounds__(32) k_mg_wait(StepArgs a, MgBuffers mb, int ch
     const uint32_t round = *mb.seq;
     uint32_t slot = 0xFFFFFFFFu;
     if (channel == DSIM_MG_CH_SPLIT) {
-        if (threadIdx.x < a.mg.world) slot = MG_FLAG_SPLIT0 + threadIdx.x;
+        if (threadIdx.x < a.mg.world) slot = MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + threadIdx.x;
     } else if (threadIdx.x < 2u && mb.has_peer[threadIdx.x]) {
         slot = (channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0) + threadIdx.x;
     }
     if (slot != 0xFFFFFFFFu) {
         uint32_t spins = 0;
-        /* rounds only grow; a neighbour that is a step ahead may already have published the next one */
+        /* rounds only grow; a neighbour that is a step ahead may already have published the next one on a neighbour
+         * channel (a SPLIT slot of this parity next sees round + 2, which nobody can publish before this round is consumed) */
         while ((int32_t)(ld_acquire_sys(mb.flags + slot) - round) < 0) {
             backoff();
             if (++spins > (1u << 25)) { /* several seconds: the neighbour is gone; flag it instead of hanging the device */
@@ -408,6 +417,12 @@ __global__ void k_mg_finish2(StepArgs a, MgBuffers mb) {
     ctl->t += 1u;
 }
 
+/* an exchange round outside the steps (the initial halo over peer memory): every rank calls it equally often */
+__global__ void k_mg_bump(StepArgs a, MgBuffers mb) {
+    (void)a;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *mb.seq += 1u;
+}
+
 /* ---- launchers -------------------------------------------------------------------------------- */
 void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s) {
     const uint32_t sm = g.n_sm;
@@ -427,6 +442,7 @@ void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const Lau
     case DSIM_MGK_WAIT_SPLIT: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_SPLIT); break;
     case DSIM_MGK_WAIT_EMIG: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_EMIGRANTS); break;
     case DSIM_MGK_WAIT_HALO: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_HALO); break;
+    case DSIM_MGK_BUMP: DSIM_LAUNCH(k_mg_bump, 1, 32, 0, s, a, mb); break;
     default: break;
     }
 }

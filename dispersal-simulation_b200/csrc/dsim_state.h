@@ -187,7 +187,7 @@ DSIM_HD_INLINE uint32_t mg_rec_bytes(uint32_t acap, uint32_t hcap) {
 
 struct MgBuffers {           /* device buffers of one rank; messages have a 16-byte header (count) */
     uint64_t *split_send;    /* [1 + scap]: count, ids of the local families that split this step       */
-    uint64_t *split_recv;    /* [world][1 + scap]                                                      */
+    uint64_t *split_recv;    /* [2][world][1 + scap]: the second area takes the odd rounds of the peer-memory transport */
     uint32_t *child_grank;   /* [scap]                                                                 */
     uint32_t *counters;      /* [MG_N_COUNTERS]                                                        */
     uint32_t *emig_list;     /* [2][ecap] positions (in `next`) of the emigrants per side              */
@@ -203,7 +203,7 @@ struct MgBuffers {           /* device buffers of one rank; messages have a 16-b
     uint32_t p2p;
     uint32_t *seq;                      /* [1] exchange round of this rank, bumped at the start of every step        */
     uint32_t *done;                     /* [3] blocks of a push kernel that have finished, per channel               */
-    uint32_t *flags;                    /* [MG_FLAG_SPLIT0 + world] round of the last complete message per source     */
+    uint32_t *flags;                    /* [MG_FLAG_SPLIT0 + 2 x MAX_WORLD] round of the last complete message per source (SPLIT: per round parity) */
     unsigned char *peer_emig_recv[2];   /* side s: the receive buffer of that neighbour that faces me                 */
     unsigned char *peer_halo_recv[2];
     uint64_t *peer_split_recv[DSIM_MG_MAX_WORLD]; /* rank r's split_recv                                               */

@@ -478,6 +478,10 @@ class Sim:
         self._check(self._f("mg_init_nccl")(self.h, buf))
         self._check(self._f("mg_halo_sync")(self.h))
 
+    def mg_halo_sync(self):
+        """Initial halo exchange over the built-in transport (every rank, after the state was set everywhere)."""
+        self._check(self._f("mg_halo_sync")(self.h))
+
     def mg_ipc_export(self) -> bytes:
         """CUDA IPC handles of this rank's receive buffers (peer-memory transport, include/dsim.h)."""
         buf = C.create_string_buffer(MG_IPC_BYTES)

@@ -240,10 +240,12 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes); 
 #define DSIM_MG_UNIQUE_ID_BYTES 128
 int dsim_mg_unique_id(void *out /* DSIM_MG_UNIQUE_ID_BYTES, rank 0 creates and broadcasts it */);
 int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
-/* Peer-memory transport (optional, after dsim_mg_init_nccl, all ranks on one NVLink node, one process per GPU): every
- * rank exports CUDA IPC handles of its receive buffers (DSIM_MG_IPC_BYTES), the caller gathers them from all ranks
- * (rank-major) and hands them back; from then on dsim_mg_step_enqueue replaces the three NCCL exchanges of a step by
- * remote stores into the neighbours' buffers plus a flag (k_mg_push / k_mg_wait).  Results are unchanged. */
+/* Peer-memory transport (all ranks on one NVLink node, one process per rank): every rank exports CUDA IPC handles of
+ * its receive buffers (DSIM_MG_IPC_BYTES), the caller gathers them from all ranks (rank-major) and hands them back;
+ * from then on dsim_mg_step_enqueue moves the three messages of a step by remote stores into the neighbours' buffers
+ * plus a flag (k_mg_push / k_mg_wait) instead of NCCL operations.  Results are unchanged.  It works with or without
+ * dsim_mg_init_nccl: without a communicator dsim_mg_halo_sync also goes through peer memory (call it on every rank
+ * once all ranks have connected) and dsim_mg_reduce_stats is not available (the caller sums the per-rank stats). */
 #define DSIM_MG_IPC_BYTES 384 /* 6 handles of 64 bytes */
 int dsim_mg_ipc_export(dsim_handle *h, void *out /* DSIM_MG_IPC_BYTES */);
 int dsim_mg_ipc_connect(dsim_handle *h, const void *all /* world x DSIM_MG_IPC_BYTES */);
@@ -252,7 +254,7 @@ int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
 /* Diagnostics: internal per-step counters; out8[7] = most emigrants per neighbour and step seen so far. */
 int dsim_mg_debug_counters(dsim_handle *h, uint32_t *out8);
 int dsim_mg_segment_times(dsim_handle *h, double *out7); /* mean ms of lifecycle, SPLIT, move, EMIGRANTS, patch, HALO, finish while profiling */
-int dsim_mg_halo_sync(dsim_handle *h); /* NCCL transport: initial halo exchange after the state was set on every rank */
+int dsim_mg_halo_sync(dsim_handle *h); /* built-in transports: initial halo exchange after the state was set on every rank */
 
 /* Kernel-level timing for bench.py: device time in ms of each kernel class accumulated since the
  * last reset, measured with CUDA events on the internal stream (only while enabled; this
