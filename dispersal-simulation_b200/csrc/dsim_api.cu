@@ -219,9 +219,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
         return rc;                                        \
     }
     for (int b = 0; b < 2; ++b) {
-        A(nf[b].id, new_cap) A(nf[b].culture, new_cap) A(nf[b].stored, new_cap) A(nf[b].last_harvest, new_cap)
-        A(nf[b].loc, new_cap) A(nf[b].size, new_cap) A(nf[b].till_adult, new_cap) A(nf[b].till_mut, new_cap)
-        A(nf[b].misc, new_cap) A(nf[b].hs, new_cap)
+        A(nf[b].key, new_cap) A(nf[b].place, new_cap) A(nf[b].stock, new_cap) A(nf[b].clock, new_cap)
     }
     A(nh.hist_cnt, hs_cap) A(nh.hist_patch, hs_cap * h->hcap) A(nh.hist_harv, hs_cap * h->hcap)
     A(nh.a_eco, hs_cap * h->acap) A(nh.a_cnt, hs_cap * h->acap) A(nh.a_val, hs_cap * h->acap)
@@ -254,11 +252,8 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
         return fail(h, DSIM_ERR_CUDA, "device copy failed while growing"); \
     }
         for (int b = 0; b < 2; ++b) {
-            CP(nf[b].id, h->fam[b].id, old_cap, uint64_t) CP(nf[b].culture, h->fam[b].culture, old_cap, uint64_t)
-            CP(nf[b].stored, h->fam[b].stored, old_cap, double) CP(nf[b].last_harvest, h->fam[b].last_harvest, old_cap, double)
-            CP(nf[b].loc, h->fam[b].loc, old_cap, uint32_t) CP(nf[b].size, h->fam[b].size, old_cap, uint32_t)
-            CP(nf[b].till_adult, h->fam[b].till_adult, old_cap, uint32_t) CP(nf[b].till_mut, h->fam[b].till_mut, old_cap, uint32_t)
-            CP(nf[b].misc, h->fam[b].misc, old_cap, uint32_t) CP(nf[b].hs, h->fam[b].hs, old_cap, uint32_t)
+            CP(nf[b].key, h->fam[b].key, old_cap, FamKey) CP(nf[b].place, h->fam[b].place, old_cap, FamPlace)
+            CP(nf[b].stock, h->fam[b].stock, old_cap, FamStock) CP(nf[b].clock, h->fam[b].clock, old_cap, FamClock)
         }
         CP(nh.hist_cnt, h->hv.hist_cnt, old_hs, uint32_t) CP(nh.hist_patch, h->hv.hist_patch, old_hs * h->hcap, uint32_t)
         CP(nh.hist_harv, h->hv.hist_harv, old_hs * h->hcap, double) CP(nh.a_eco, h->hv.a_eco, old_hs * h->acap, uint16_t)
@@ -522,11 +517,11 @@ __global__ void k_digest32(const uint32_t *w, uint64_t n, unsigned long long *ac
     atomicAdd(acc, (unsigned long long)s);
 }
 
-__global__ void k_pack_adaptation(FamHeavy hv, const uint32_t *hs_of, uint32_t n, double minimum, uint16_t *out_eco,
+__global__ void k_pack_adaptation(FamHeavy hv, const FamPlace *place, uint32_t n, double minimum, uint16_t *out_eco,
                                   double *out_val, uint32_t *out_n) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n; i += nth) {
-        const uint32_t hs = hs_of[i];
+        const uint32_t hs = place[i].hs;
         const uint32_t d = hv.decay[hs];
         uint32_t m = 0;
         for (uint32_t k = 0; k < hv.acap; ++k) {
@@ -649,18 +644,23 @@ int take_snapshot(dsim_handle *h, bool want_adapt) {
         h->s_id.resize(n); h->s_culture.resize(n); h->s_stored.resize(n); h->s_lh.resize(n);
         h->s_loc.resize(n); h->s_size.resize(n); h->s_till_adult.resize(n); h->s_till_mut.resize(n);
         h->s_misc.resize(n); h->s_hs.resize(n); h->s_hist_len.resize(n); h->s_hist_cnt.resize(h->hs_cap);
-        if ((rc = download(h, h->s_id.data(), f.id, n))) return rc;
-        if ((rc = download(h, h->s_culture.data(), f.culture, n))) return rc;
-        if ((rc = download(h, h->s_stored.data(), f.stored, n))) return rc;
-        if ((rc = download(h, h->s_lh.data(), f.last_harvest, n))) return rc;
-        if ((rc = download(h, h->s_loc.data(), f.loc, n))) return rc;
-        if ((rc = download(h, h->s_size.data(), f.size, n))) return rc;
-        if ((rc = download(h, h->s_till_adult.data(), f.till_adult, n))) return rc;
-        if ((rc = download(h, h->s_till_mut.data(), f.till_mut, n))) return rc;
-        if ((rc = download(h, h->s_misc.data(), f.misc, n))) return rc;
-        if ((rc = download(h, h->s_hs.data(), f.hs, n))) return rc;
+        /* the packed sub-records come down as they are and are split into the caller's columns here */
+        std::vector<FamKey> key(n);
+        std::vector<FamPlace> place(n);
+        std::vector<FamStock> stock(n);
+        std::vector<FamClock> clock(n);
+        if ((rc = download(h, key.data(), f.key, n))) return rc;
+        if ((rc = download(h, place.data(), f.place, n))) return rc;
+        if ((rc = download(h, stock.data(), f.stock, n))) return rc;
+        if ((rc = download(h, clock.data(), f.clock, n))) return rc;
         if ((rc = download(h, h->s_hist_cnt.data(), h->hv.hist_cnt, h->hs_cap))) return rc; /* history lengths */
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
+        for (uint32_t i = 0; i < n; ++i) {
+            h->s_id[i] = key[i].id; h->s_culture[i] = key[i].culture;
+            h->s_stored[i] = stock[i].stored; h->s_lh[i] = stock[i].last_harvest;
+            h->s_loc[i] = place[i].loc; h->s_size[i] = place[i].size; h->s_hs[i] = place[i].hs; h->s_misc[i] = place[i].misc;
+            h->s_till_adult[i] = clock[i].till_adult; h->s_till_mut[i] = clock[i].till_mut;
+        }
         for (uint32_t i = 0; i < n; ++i) h->s_hist_len[i] = std::min(h->s_hist_cnt[h->s_hs[i]], h->hcap);
         h->snap_valid = true;
     }
@@ -681,7 +681,7 @@ int take_snapshot(dsim_handle *h, bool want_adapt) {
             return rc;
         }
         if (n) {
-            DSIM_LAUNCH(k_pack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint32_t *)f.hs, n, h->p.minimum_adaptation,
+            DSIM_LAUNCH(k_pack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const FamPlace *)f.place, n, h->p.minimum_adaptation,
                         d_eco, d_val, d_n);
             h->total_launches += 1;
         }
@@ -1038,17 +1038,25 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
         if ((rc = alloc_families(h, want))) return rc;
     }
     const uint32_t acap = h->acap;
-    std::vector<uint32_t> misc(n), hs(n), till_adult(n), till_mut(n);
-    std::vector<double> lh(n);
+    /* the caller's columns are packed into the four sub-records of the core record (dsim_state.h) */
+    std::vector<FamKey> key(n);
+    std::vector<FamPlace> place(n);
+    std::vector<FamStock> stock(n);
+    std::vector<FamClock> clk(n);
     std::vector<uint64_t> parent(n);
     std::vector<uint16_t> birth(n);
     for (uint64_t i = 0; i < n; ++i) {
         const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
-        misc[i] = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
-        hs[i] = (uint32_t)i;
-        till_adult[i] = f->till_adult ? f->till_adult[i] : 0;
-        till_mut[i] = (clock && f->till_mutation) ? f->till_mutation[i] : 0;
-        lh[i] = f->last_harvest ? f->last_harvest[i] : 0.0;
+        key[i].id = f->id[i];
+        key[i].culture = f->culture[i];
+        place[i].loc = f->location[i];
+        place[i].size = f->size[i];
+        place[i].hs = (uint32_t)i;
+        place[i].misc = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
+        stock[i].stored = f->stored[i];
+        stock[i].last_harvest = f->last_harvest ? f->last_harvest[i] : 0.0;
+        clk[i].till_adult = f->till_adult ? f->till_adult[i] : 0;
+        clk[i].till_mut = (clock && f->till_mutation) ? f->till_mutation[i] : 0;
         parent[i] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
         birth[i] = f->birth_index ? f->birth_index[i] : 0;
     }
@@ -1056,12 +1064,11 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     h->mid_step = false;
     h->snap_valid = false;
     const FamCore &c = h->fam[0];
-    if ((rc = upload(h, c.id, f->id, n)) || (rc = upload(h, c.culture, f->culture, n)) || (rc = upload(h, c.stored, f->stored, n)) ||
-        (rc = upload(h, c.last_harvest, lh.data(), n)) || (rc = upload(h, c.loc, f->location, n)) || (rc = upload(h, c.size, f->size, n)) ||
-        (rc = upload(h, c.till_adult, till_adult.data(), n)) || (rc = upload(h, c.till_mut, till_mut.data(), n)) ||
-        (rc = upload(h, c.misc, misc.data(), n)) || (rc = upload(h, c.hs, hs.data(), n)) ||
+    if ((rc = upload(h, c.key, key.data(), n)) || (rc = upload(h, c.place, place.data(), n)) || (rc = upload(h, c.stock, stock.data(), n)) ||
+        (rc = upload(h, c.clock, clk.data(), n)) ||
         (rc = upload(h, h->hv.parent, parent.data(), n)) || (rc = upload(h, h->hv.birth_index, birth.data(), n)))
         return rc;
+    CK(cudaStreamSynchronize(h->stream)); /* the staging vectors are local to this function */
     CK(cudaMemsetAsync(h->hv.hist_cnt, 0, h->hs_cap * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->hv.a_eco, 0xFF, h->hs_cap * acap * sizeof(uint16_t), h->stream));
     {

@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
         const uint32_t i = vb * LIFE_BLOCK + threadIdx.x;
         bool alive = false, split = false;
         if (i < n) {
-            uint32_t size = a.cur.size[i];
-            double stored = a.cur.stored[i];
-            uint32_t till_adult = a.cur.till_adult[i];
+            uint32_t size = a.cur.place[i].size;
+            double stored = a.cur.stock[i].stored;
+            uint32_t till_adult = a.cur.clock[i].till_adult;
             /* use_resources_and_maybe_shrink, lib.rs:1923-1937 */
             bool has_shrunk = false;
             while ((stored - (double)size * season) < 0.0 && size > 0u) {
@@ -98,9 +98,9 @@ __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
             } else {
                 till_adult -= 1u;
             }
-            a.cur.size[i] = size;
-            a.cur.stored[i] = stored;
-            a.cur.till_adult[i] = till_adult;
+            a.cur.place[i].size = size;
+            a.cur.stock[i].stored = stored;
+            a.cur.clock[i].till_adult = till_adult;
             alive = size >= 2u;  /* can_survive, lib.rs:1939-1941 */
             split = size >= 10u; /* maybe_procreate, lib.rs:1870 (the move does not change the size) */
         }
@@ -585,10 +585,15 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
                 const uint32_t alive_mask = a.sc.alive_bits[c], split_mask = a.sc.split_bits[c];
                 const uint32_t base_alive = a.sc.blk_alive[c >> 3], base_split = a.sc.blk_split[c >> 3];
-                const uint32_t hs = a.cur.hs[i], loc = a.cur.loc[i], size = a.cur.size[i], misc = a.cur.misc[i];
-                const uint64_t fid = a.cur.id[i], culture = a.cur.culture[i];
-                const double stored = a.cur.stored[i], last_harvest = a.cur.last_harvest[i];
-                const uint32_t till_adult = a.cur.till_adult[i], till_mut = a.cur.till_mut[i];
+                /* the 56-byte record: three 128-bit loads and one 64-bit load */
+                const FamPlace pl = a.cur.place[i];
+                const FamKey ky = a.cur.key[i];
+                const FamStock sk = a.cur.stock[i];
+                const FamClock ck = a.cur.clock[i];
+                const uint32_t hs = pl.hs, loc = pl.loc, size = pl.size, misc = pl.misc;
+                const uint64_t fid = ky.id, culture = ky.culture;
+                const double stored = sk.stored, last_harvest = sk.last_harvest;
+                const uint32_t till_adult = ck.till_adult, till_mut = ck.till_mut;
                 /* ranks from the bitmaps (retain lib.rs:541, children lib.rs:551) */
                 const uint32_t pre = a.sc.word_pre[c], va = pre & 0xFFFFu, vs = pre >> 16;
                 const RowHdr hd = a.rt.hdr[loc];
@@ -963,16 +968,24 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 t.pad_ = 0u;
                 a.sc.child_task[S.crank[lane]] = t;
             }
-            a.next.id[newpos] = fid;
-            a.next.culture[newpos] = culture;
-            a.next.stored[newpos] = stored;
-            a.next.last_harvest[newpos] = 0.0;
-            a.next.loc[newpos] = newloc;
-            a.next.size[newpos] = size;
-            a.next.till_adult[newpos] = S.till_adult[lane];
-            a.next.till_mut[newpos] = S.till_mut[lane];
-            a.next.misc[newpos] = misc;
-            a.next.hs[newpos] = hs;
+            FamKey ky;
+            ky.id = fid;
+            ky.culture = culture;
+            FamPlace pl;
+            pl.loc = newloc;
+            pl.size = size;
+            pl.hs = hs;
+            pl.misc = misc;
+            FamStock sk;
+            sk.stored = stored;
+            sk.last_harvest = 0.0;
+            FamClock ck;
+            ck.till_adult = S.till_adult[lane];
+            ck.till_mut = S.till_mut[lane];
+            a.next.key[newpos] = ky;
+            a.next.place[newpos] = pl;
+            a.next.stock[newpos] = sk;
+            a.next.clock[newpos] = ck;
             /* arrival at the new node = histogram of the counting sort by patch.  The rank the atomic returns is
              * written when the NEXT tile gets here (or after the last one): nothing of this tile waits for it. */
             if (pend_pos != 0xFFFFFFFFu) a.sc.fslot[pend_pos] = pend_slot;
@@ -1207,16 +1220,24 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             a.hv.decay[chs] = parent_decay;
             a.hv.parent[chs] = t.parent_id;
             a.hv.birth_index[chs] = (uint16_t)t.n_off;
-            a.next.id[cpos] = cid;
-            a.next.culture[cpos] = t.culture;
-            a.next.stored[cpos] = t.take - cc.t_cost; /* descendant.stored_resources -= cost */
-            a.next.last_harvest[cpos] = 0.0;
-            a.next.loc[cpos] = cc.target;
-            a.next.size[cpos] = 2u;
-            a.next.till_adult[cpos] = a.mc.adult_reset;
-            a.next.till_mut[cpos] = 0u;
-            a.next.misc[cpos] = 0u;
-            a.next.hs[cpos] = chs;
+            FamKey ky;
+            ky.id = cid;
+            ky.culture = t.culture;
+            FamPlace pl;
+            pl.loc = cc.target;
+            pl.size = 2u;
+            pl.hs = chs;
+            pl.misc = 0u;
+            FamStock sk;
+            sk.stored = t.take - cc.t_cost; /* descendant.stored_resources -= cost */
+            sk.last_harvest = 0.0;
+            FamClock ck;
+            ck.till_adult = a.mc.adult_reset;
+            ck.till_mut = 0u;
+            a.next.key[cpos] = ky;
+            a.next.place[cpos] = pl;
+            a.next.stock[cpos] = sk;
+            a.next.clock[cpos] = ck;
             if (!a.mg.enabled || (cc.target >= a.mg.own_lo && cc.target < a.mg.own_hi)) {
                 a.sc.fslot[cpos] = atomicAdd(&a.ps.cnt[cc.target], 1u);
             } else {
@@ -1252,7 +1273,7 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         const bool first = j < n && a.sc.fslot[j] == 0u;
         uint32_t p = 0, c = 0;
         if (first) {
-            p = a.next.loc[j];
+            p = a.next.place[j].loc;
             c = a.ps.cnt[p];
         }
         /* segment starts: exclusive scan of the counts over the warp + one atomic for the warp's total */
@@ -1288,7 +1309,7 @@ __global__ void __launch_bounds__(256) k_scatter(StepArgs a) {
     DevCtl *ctl = a.ctl;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n = ctl->n_next;
-    for (uint32_t j = tid; j < n; j += nth) a.sc.members[a.ps.seg[a.next.loc[j]] + a.sc.fslot[j]] = j;
+    for (uint32_t j = tid; j < n; j += nth) a.sc.members[a.ps.seg[a.next.place[j].loc] + a.sc.fslot[j]] = j;
     /* nodes occupied last step and empty now: census 0, no band cultures (lib.rs:522-525, 614) */
     const uint32_t n_prev = ctl->n_occ[a.occ_par ^ 1u];
     for (uint32_t k = tid; k < n_prev; k += nth) {
@@ -1373,7 +1394,7 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id) ----------- */
     for (uint32_t j = tid; j < n; j += nthr) {
         const uint32_t i = a.sc.members[s0 + j];
-        const uint64_t id = a.next.id[i];
+        const uint64_t id = a.next.key[i].id;
         const dsim_u4 o = dsim_draw(rs, step, id, DSIM_P_SHUF, 0u);
         M.tidx[j] = i;
         M.tfid[j] = id;
@@ -1393,9 +1414,9 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     __syncthreads();
     for (uint32_t r = tid; r < n; r += nthr) {
         const uint32_t i = M.idx[r];
-        M.cult[r] = a.next.culture[i];
-        M.size[r] = a.next.size[i];
-        M.stored[r] = a.next.stored[i];
+        M.cult[r] = a.next.key[i].culture;
+        M.size[r] = a.next.place[i].size;
+        M.stored[r] = a.next.stock[i].stored;
     }
     __syncthreads();
 
@@ -1529,8 +1550,8 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         if (!M.balive[B]) continue;
         const uint32_t i = M.idx[r];
         uint64_t c = M.bcult[B];
-        uint32_t misc = a.next.misc[i];
-        uint32_t clock = a.next.till_mut[i];
+        uint32_t misc = a.next.place[i].misc;
+        uint32_t clock = a.next.clock[i].till_mut;
         const dsim_u4 o = dsim_draw(rs, step, M.fid[r], DSIM_P_MUT, 0u);
         if (!(misc & DSIM_MISC_CLOCK)) { /* None => draw, then re-enter, lib.rs:1763-1774 */
             misc |= DSIM_MISC_CLOCK;
@@ -1544,8 +1565,8 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             clock -= 1u;
         }
         M.cult[r] = c;
-        a.next.misc[i] = misc;
-        a.next.till_mut[i] = clock;
+        a.next.place[i].misc = misc;
+        a.next.clock[i].till_mut = clock;
     }
     __syncthreads();
 
@@ -1556,7 +1577,7 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         const uint32_t eco = a.ps.eco_id[e];
         for (uint32_t r = tid; r < n; r += nthr) { /* raw_family_contribution, lib.rs:1947-1958 */
             double c = 0.0;
-            if (M.balive[M.band[r]]) c = (double)M.size[r] * adapt_touch(a, a.next.hs[M.idx[r]], eco, &errors);
+            if (M.balive[M.band[r]]) c = (double)M.size[r] * adapt_touch(a, a.next.place[M.idx[r]].hs, eco, &errors);
             M.contrib[r] = c;
         }
         __syncthreads();
@@ -1606,11 +1627,11 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     for (uint32_t r = tid; r < n; r += nthr) {
         const uint32_t i = M.idx[r];
         const uint32_t sz = M.size[r];
-        a.next.size[i] = sz;
-        a.next.stored[i] = M.stored[r];
+        a.next.place[i].size = sz;
+        a.next.stock[i].stored = M.stored[r];
         if (M.balive[M.band[r]]) {
-            a.next.culture[i] = M.cult[r];
-            if (e1 > e0) a.next.last_harvest[i] = M.lh[r];
+            a.next.key[i].culture = M.cult[r];
+            if (e1 > e0) a.next.stock[i].last_harvest = M.lh[r];
         }
         pop += sz;
     }
@@ -1741,13 +1762,15 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
         double stored = 0.0;
         if (mine) {
             idx = a.sc.members[s0 + gl];
-            fid = a.next.id[idx];
-            cult = a.next.culture[idx];
-            size = a.next.size[idx];
-            stored = a.next.stored[idx];
-            hs = a.next.hs[idx];
-            misc = a.next.misc[idx];
-            clock = a.next.till_mut[idx];
+            const FamKey ky = a.next.key[idx]; /* two 128-bit loads + two 64-bit halves */
+            const FamPlace pl = a.next.place[idx];
+            fid = ky.id;
+            cult = ky.culture;
+            size = pl.size;
+            hs = pl.hs;
+            misc = pl.misc;
+            stored = a.next.stock[idx].stored;
+            clock = a.next.clock[idx].till_mut;
         }
         /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id); lane r takes the
          * family of rank r ---------------------------------------------------------------------------- */
@@ -1869,8 +1892,8 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
                     clock -= 1u;
                 }
                 cult = c;
-                a.next.misc[idx] = misc;
-                a.next.till_mut[idx] = clock;
+                a.next.place[idx].misc = misc;
+                a.next.clock[idx].till_mut = clock;
             }
         }
         /* ---- exploit_patch + recover per ecoregion, lib.rs:2021-2067, 2095-2109 ------------------- */
@@ -1918,11 +1941,11 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
         /* ---- write back ----------------------------------------------------------------------------- */
         const uint32_t pop = G.sum(mine ? size : 0u);
         if (mine) {
-            a.next.size[idx] = size;
-            a.next.stored[idx] = stored;
+            a.next.place[idx].size = size;
+            a.next.stock[idx].stored = stored;
             if (balive) {
-                a.next.culture[idx] = cult;
-                if (e1 > e0) a.next.last_harvest[idx] = lh;
+                a.next.key[idx].culture = cult;
+                if (e1 > e0) a.next.stock[idx].last_harvest = lh;
             }
         }
         if (gl == 0u) {
@@ -1984,8 +2007,9 @@ __global__ void k_clear_census(PatchState ps, uint32_t n_nodes) {
 __global__ void k_census(PatchState ps, FamCore f, uint32_t n, uint32_t *occ, DevCtl *ctl, uint32_t parity) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n; i += nth) {
-        const uint32_t p = f.loc[i];
-        atomicAdd(&ps.view[p].pop, f.size[i]);
+        const FamPlace pl = f.place[i];
+        const uint32_t p = pl.loc;
+        atomicAdd(&ps.view[p].pop, pl.size);
         /* remember the node as "occupied last step" so that the first step clears stale censuses */
         if (atomicAdd(&ps.cnt[p], 1u) == 0u) occ[atomicAdd(&ctl->n_occ[parity], 1u)] = p;
     }

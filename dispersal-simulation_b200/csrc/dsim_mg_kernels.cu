@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         vs += a.sc.word_pre[c] >> 16;
         const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
         if (crank < mb.scap)
-            mb.split_send[1 + crank] = a.cur.id[i];
+            mb.split_send[1 + crank] = a.cur.key[i].id;
         else
             atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
     }
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
     const uint32_t n_round = (n + 31u) & ~31u; /* whole warps take part in the ballots */
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         const bool in = j < n;
-        const uint32_t loc = in ? a.next.loc[j] : 0u;
+        const uint32_t loc = in ? a.next.place[j].loc : 0u;
         const bool stay = in && loc >= a.mg.own_lo && loc < a.mg.own_hi;
         /* one atomic per warp for the families that stay */
         const uint32_t m = __ballot_sync(DSIM_FULL, stay);
@@ -96,16 +96,10 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
         base = __shfl_sync(DSIM_FULL, base, 0);
         if (stay) {
             const uint32_t p = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-            a.cur.id[p] = a.next.id[j];
-            a.cur.culture[p] = a.next.culture[j];
-            a.cur.stored[p] = a.next.stored[j];
-            a.cur.last_harvest[p] = a.next.last_harvest[j];
-            a.cur.loc[p] = loc;
-            a.cur.size[p] = a.next.size[j];
-            a.cur.till_adult[p] = a.next.till_adult[j];
-            a.cur.till_mut[p] = a.next.till_mut[j];
-            a.cur.misc[p] = a.next.misc[j];
-            a.cur.hs[p] = a.next.hs[j];
+            a.cur.key[p] = a.next.key[j];
+            a.cur.place[p] = a.next.place[j];
+            a.cur.stock[p] = a.next.stock[j];
+            a.cur.clock[p] = a.next.clock[j];
             mb.fslot2[p] = a.sc.fslot[j];
         } else if (in) {
             const uint32_t side = loc < a.mg.own_lo ? 0u : 1u;
@@ -133,23 +127,27 @@ __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
         }
         for (uint32_t e = gw; e < m; e += nw) {
             const uint32_t j = mb.emig_list[side * mb.ecap + e];
-            const uint32_t hs = a.next.hs[j];
+            const FamPlace pl = a.next.place[j];
+            const uint32_t hs = pl.hs;
             unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
             const uint32_t cnt = a.hv.hist_cnt[hs];
             const uint32_t valid = cnt < hcap ? cnt : hcap;
             if (lane == 0) {
                 uint64_t *q = reinterpret_cast<uint64_t *>(rec);
-                q[0] = a.next.id[j];
-                q[1] = a.next.culture[j];
-                q[2] = dsim_f64_to_bits(a.next.stored[j]);
-                q[3] = dsim_f64_to_bits(a.next.last_harvest[j]);
+                const FamKey ky = a.next.key[j];
+                const FamStock sk = a.next.stock[j];
+                const FamClock ck = a.next.clock[j];
+                q[0] = ky.id;
+                q[1] = ky.culture;
+                q[2] = dsim_f64_to_bits(sk.stored);
+                q[3] = dsim_f64_to_bits(sk.last_harvest);
                 q[4] = a.hv.parent[hs];
                 uint32_t *w = reinterpret_cast<uint32_t *>(rec + 40);
-                w[0] = a.next.loc[j];
-                w[1] = a.next.size[j];
-                w[2] = a.next.till_adult[j];
-                w[3] = a.next.till_mut[j];
-                w[4] = a.next.misc[j];
+                w[0] = pl.loc;
+                w[1] = pl.size;
+                w[2] = ck.till_adult;
+                w[3] = ck.till_mut;
+                w[4] = pl.misc;
                 w[5] = valid;
                 w[6] = a.hv.decay[hs];
                 w[7] = a.hv.birth_index[hs];
@@ -216,17 +214,25 @@ __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
             }
             if (lane == 0) {
                 const uint64_t *q = reinterpret_cast<const uint64_t *>(rec);
-                a.cur.id[p] = q[0];
-                a.cur.culture[p] = q[1];
-                a.cur.stored[p] = dsim_bits_to_f64(q[2]);
-                a.cur.last_harvest[p] = dsim_bits_to_f64(q[3]);
+                FamKey ky;
+                ky.id = q[0];
+                ky.culture = q[1];
+                FamStock sk;
+                sk.stored = dsim_bits_to_f64(q[2]);
+                sk.last_harvest = dsim_bits_to_f64(q[3]);
+                FamPlace pl;
+                pl.loc = loc;
+                pl.size = w[1];
+                pl.hs = hs;
+                pl.misc = w[4];
+                FamClock ck;
+                ck.till_adult = w[2];
+                ck.till_mut = w[3];
+                a.cur.key[p] = ky;
+                a.cur.stock[p] = sk;
+                a.cur.place[p] = pl;
+                a.cur.clock[p] = ck;
                 a.hv.parent[hs] = q[4];
-                a.cur.loc[p] = loc;
-                a.cur.size[p] = w[1];
-                a.cur.till_adult[p] = w[2];
-                a.cur.till_mut[p] = w[3];
-                a.cur.misc[p] = w[4];
-                a.cur.hs[p] = hs;
                 a.hv.hist_cnt[hs] = valid;
                 a.hv.decay[hs] = w[6];
                 a.hv.birth_index[hs] = (uint16_t)w[7];

@@ -2,8 +2,8 @@
  * dsim_state.h — HBM layout of the simulation state.
  *
  * Families (lib.rs:178-229) are split into
- *   - a 56-byte CORE record, structure-of-arrays, kept in the reference's vector order and
- *     double-buffered: part 1 of the step reads buffer `cur` and writes the survivors (compacted,
+ *   - a 56-byte CORE record in four packed sub-records (16 + 16 + 16 + 8 bytes, an array each), kept in the
+ *     reference's vector order and double-buffered: part 1 of the step reads buffer `cur` and writes the survivors (compacted,
  *     lib.rs:541) and the children (appended, lib.rs:551) into buffer `next`;
  *   - HEAVY per-family state that never moves (history ring, sparse adaptation slots, lineage),
  *     addressed through the `hs` (heavy slot) column of the core record.
@@ -21,17 +21,32 @@
 #define DSIM_STOR_HALO 0x80000000u /* PatchView.stor_off: bit 31 = cultures live in halo_cult[bit 30] (multi-GPU) */
 #define DSIM_MISC_CLOCK 0x10000u /* misc bit 16: seasons_till_next_mutation is Some(..) */
 
-struct FamCore {            /* one column per field, index = position in the family vector */
-    uint64_t *id;           /* birth-order id; keys every random draw of the family              */
-    uint64_t *culture;      /* Culture.in_memory[0]                                             */
-    double *stored;         /* stored_resources                                                 */
-    double *last_harvest;
-    uint32_t *loc;          /* location (node id)                                               */
-    uint32_t *size;         /* effective_size                                                   */
-    uint32_t *till_adult;   /* seasons_till_next_adult                                          */
-    uint32_t *till_mut;     /* seasons_till_next_mutation (valid iff misc & DSIM_MISC_CLOCK)    */
-    uint32_t *misc;         /* bits 0..15 number_offspring, bit 16 mutation clock present       */
-    uint32_t *hs;           /* heavy slot                                                       */
+/* The 56-byte core record as four packed sub-records, one array each (index = position in the family vector): a
+ * kernel that gathers a family through `members` or a segment reads it with three 128-bit loads and one 64-bit load
+ * (four sectors) instead of ten scattered 4/8-byte loads (ten sectors); streaming passes stay coalesced. */
+struct __align__(16) FamKey {   /* what keys the family's draws and its relations */
+    uint64_t id;            /* birth-order id; keys every random draw of the family              */
+    uint64_t culture;       /* Culture.in_memory[0]                                             */
+};
+struct __align__(16) FamPlace {
+    uint32_t loc;           /* location (node id)                                               */
+    uint32_t size;          /* effective_size                                                   */
+    uint32_t hs;            /* heavy slot                                                       */
+    uint32_t misc;          /* bits 0..15 number_offspring, bit 16 mutation clock present       */
+};
+struct __align__(16) FamStock {
+    double stored;          /* stored_resources                                                 */
+    double last_harvest;
+};
+struct __align__(8) FamClock {
+    uint32_t till_adult;    /* seasons_till_next_adult                                          */
+    uint32_t till_mut;      /* seasons_till_next_mutation (valid iff misc & DSIM_MISC_CLOCK)    */
+};
+struct FamCore {
+    FamKey *key;
+    FamPlace *place;
+    FamStock *stock;
+    FamClock *clock;
 };
 
 struct FamHeavy {           /* index = heavy slot */
