@@ -20,6 +20,12 @@ static inline void dsim_bulk_g2s(void *smem_dst, const void *gsrc, unsigned byte
 static inline void dsim_cp_async16(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 16); }
 static inline void dsim_cp_async8(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 8); }
 static inline void dsim_cp_async4(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 4); }
+static inline unsigned long long dsim_policy_evict_last() { return 0; }
+static inline unsigned long long dsim_policy_evict_first() { return 0; }
+static inline void dsim_bulk_g2s_hint(void *smem_dst, const void *gsrc, unsigned bytes, dsim_mbar *, unsigned long long) { std::memcpy(smem_dst, gsrc, bytes); }
+static inline void dsim_cp_async16_hint(void *smem_dst, const void *gsrc, unsigned long long) { std::memcpy(smem_dst, gsrc, 16); }
+static inline void dsim_cp_async8_hint(void *smem_dst, const void *gsrc, unsigned long long) { std::memcpy(smem_dst, gsrc, 8); }
+static inline void dsim_cp_async4_hint(void *smem_dst, const void *gsrc, unsigned long long) { std::memcpy(smem_dst, gsrc, 4); }
 static inline void dsim_cp_async_commit() {}
 static inline void dsim_cp_async_wait_all() {}
 static inline void dsim_fence_proxy_async() {}
@@ -60,6 +66,33 @@ __device__ __forceinline__ void dsim_cp_async8(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void dsim_cp_async4(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+/* L2 eviction priorities (createpolicy + .L2::cache_hint): the small arrays every decision gathers from (candidate views,
+ * band records: 64 MB at 2 M nodes) are kept in L2 ahead of the reach rows and history rings that stream through it */
+__device__ __forceinline__ unsigned long long dsim_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long dsim_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void dsim_bulk_g2s_hint(void *smem_dst, const void *gsrc, unsigned bytes, dsim_mbar *b, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     dsim_smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(dsim_smem_u32(b)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void dsim_cp_async16_hint(void *smem_dst, const void *gsrc, unsigned long long pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void dsim_cp_async8_hint(void *smem_dst, const void *gsrc, unsigned long long pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void dsim_cp_async4_hint(void *smem_dst, const void *gsrc, unsigned long long pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dsim_smem_u32(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void dsim_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void dsim_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

@@ -496,7 +496,9 @@ __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double 
 #endif
 #define MOVE_SSTAGE 64u   /* sensed entries per family staged in shared memory: the first pass */
 #define MOVE_HB_MAX 16u   /* head blocks of 16 history entries (ModelConst.mem_head <= 16) */
+#ifndef MOVE_WARPS
 #define MOVE_WARPS 4u
+#endif
 #ifndef MOVE_MIN_BLOCKS
 #define MOVE_MIN_BLOCKS 6 /* 8.8 KB of shared memory per warp: 24 warps per SM, 80 registers per thread */
 #endif
@@ -515,6 +517,7 @@ struct __align__(16) MoveTile { /* per warp */
     uint32_t idx[MOVE_WF], newpos[MOVE_WF], crank[MOVE_WF], misc[MOVE_WF], newest[MOVE_WF];
     uint32_t till_adult[MOVE_WF], till_mut[MOVE_WF];
     uint32_t tj0[MOVE_WF], td[MOVE_WF], ntail[MOVE_WF], tmore[MOVE_WF]; /* tail sampling state (mem_tail_run) */
+    uint32_t src[MOVE_WF];                 /* the family of the tile whose staged row and views this one uses (same node) */
     uint32_t tail[MOVE_WF][MOVE_TAILQ];    /* kept tail entries */
     uint32_t list[MOVE_LCAP];              /* kept entries of the tile: family << 24 | entry, family-major, ascending */
     uint16_t hmask[MOVE_WF][MOVE_HB_MAX];  /* kept head entries, 16 per block */
@@ -560,6 +563,12 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
 
     if (lane == 0) dsim_mbar_init(&S.bar, 1u);
     __syncwarp();
+#ifndef MOVE_HINTS
+#define MOVE_HINTS 3
+#endif
+    const unsigned long long pol_keep = dsim_policy_evict_last(), pol_stream = dsim_policy_evict_first();
+    (void)pol_keep;
+    (void)pol_stream;
 
     /* tiles are handed out by a counter: the claim for the next tile is in flight while this one is worked on */
     uint32_t tile = 0;
@@ -571,8 +580,10 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
 
         /* ---- prologue: lane f < MOVE_WF owns family f of the tile ---------------------------------- *
          * Every load that depends only on the family's position is requested before any is used (also for
-         * families that turn out to be dead: their columns are still valid memory), so the prologue costs
-         * three memory round trips: members -> record columns and bitmaps -> row header and history length. */
+         * families that turn out to be dead: their records are still valid memory), so the prologue costs
+         * three memory round trips: members -> record and bitmaps -> row header and history length.
+         * (Fetching the next tile's prologue with cp.async while this tile is worked on was measured and
+         * brought nothing: the other resident warps already cover these round trips.) */
         uint32_t nh = 0, state = 0, nst = 0; /* state: bit 0 = decides (survivor), bit 1 = splits; nst: staged sensed entries, padded to 8 */
         if (lane < MOVE_WF) {
             /* Families are visited in the patch-grouped order that part 2 of the previous step left in
@@ -636,6 +647,21 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             S.nh[lane] = nh;
         }
         const uint32_t live_mask = __ballot_sync(DSIM_FULL, (state & 1u) != 0u);
+        /* Co-resident families (the visiting order groups them) look at the same row and the same views: only the
+         * first one of a tile stages them, the others read its copy. */
+        {
+            const uint32_t my_loc = (lane < MOVE_WF && (state & 1u)) ? S.loc[lane] : 0xFFFFFFFFu;
+            uint32_t from = lane;
+#pragma unroll
+            for (uint32_t g = MOVE_WF - 1u; g-- > 0u;) { /* g = MOVE_WF-2 ... 0: the smallest g wins */
+                const uint32_t lg = __shfl_sync(DSIM_FULL, my_loc, (int)g);
+                if (g < lane && lg == my_loc && my_loc != 0xFFFFFFFFu) from = g;
+            }
+            if (lane < MOVE_WF) {
+                S.src[lane] = from;
+                if (from != lane) nst = 0u;
+            }
+        }
         /* ---- the reach rows of the tile, by bulk copy ---------------------------------------------- */
         uint32_t stage_entries = nst; /* sum over the tile's families */
 #pragma unroll
@@ -649,10 +675,17 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             const uint32_t f = lane >> 1;
             const uint32_t nst_f = __shfl_sync(DSIM_FULL, nst, (int)(f < MOVE_WF ? f : 0u));
             if (f < MOVE_WF && nst_f != 0u) {
+#if MOVE_HINTS & 2
+                if (lane & 1u)
+                    dsim_bulk_g2s_hint(&S.r_cost[f][0], a.rt.cost + S.row_start[f], nst_f * 8u, &S.bar, pol_stream);
+                else
+                    dsim_bulk_g2s_hint(&S.r_dst[f][0], a.rt.dst + S.row_start[f], nst_f * 4u, &S.bar, pol_stream);
+#else
                 if (lane & 1u)
                     dsim_bulk_g2s(&S.r_cost[f][0], a.rt.cost + S.row_start[f], nst_f * 8u, &S.bar);
                 else
                     dsim_bulk_g2s(&S.r_dst[f][0], a.rt.dst + S.row_start[f], nst_f * 4u, &S.bar);
+#endif
             }
         }
 
@@ -686,10 +719,16 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
             phase ^= 1u;
 #pragma unroll
             for (uint32_t f = 0; f < MOVE_WF; ++f) {
-                if (!((live_mask >> f) & 1u)) continue;
+                if (!((live_mask >> f) & 1u) || S.src[f] != f) continue;
                 const uint32_t ns = S.ns[f];
+#if MOVE_HINTS & 1
+                if (lane < ns) dsim_cp_async16_hint(&S.view[f][lane], &a.ps.view[S.r_dst[f][lane]], pol_keep);
+                if (lane + 32u < ns && lane + 32u < MOVE_SSTAGE)
+                    dsim_cp_async16_hint(&S.view[f][lane + 32u], &a.ps.view[S.r_dst[f][lane + 32u]], pol_keep);
+#else
                 if (lane < ns) dsim_cp_async16(&S.view[f][lane], &a.ps.view[S.r_dst[f][lane]]);
                 if (lane + 32u < ns && lane + 32u < MOVE_SSTAGE) dsim_cp_async16(&S.view[f][lane + 32u], &a.ps.view[S.r_dst[f][lane + 32u]]);
+#endif
             }
             dsim_cp_async_commit();
         }
@@ -715,9 +754,10 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                * entry 0 and are masked at the acceptance, so the loads need no branches */
                 const bool vA = lane < ns, vB = lane + 32u < ns;
                 const uint32_t iA = vA ? lane : 0u, iB = vB ? lane + 32u : 0u;
-                const uint32_t qA = S.r_dst[f][iA], qB = S.r_dst[f][iB];
-                const double cA = S.r_cost[f][iA], cB = S.r_cost[f][iB];
-                const PatchView pA = S.view[f][iA], pB = S.view[f][iB];
+                const uint32_t sf = S.src[f];
+                const uint32_t qA = S.r_dst[sf][iA], qB = S.r_dst[sf][iB];
+                const double cA = S.r_cost[sf][iA], cB = S.r_cost[sf][iB];
+                const PatchView pA = S.view[sf][iA], pB = S.view[sf][iB];
                 /* entries e and e + 32 of a pass share one Philox block (noise_block / noise_pick) */
                 const dsim_u4 o = dsim_draw(rs, step, fid, DSIM_P_NOISE, noise_block(lane));
                 const double gainA = view_quality(a, pA, qA, culture, size, qA == loc);
@@ -809,8 +849,13 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                         const uint32_t newest = S.newest[f];
                         const uint32_t pos = newest >= nn ? newest - nn : newest + hcap - nn;
                         const size_t hb = (size_t)S.hs[f] * hcap;
+#if MOVE_HINTS & 4
+                        dsim_cp_async4_hint(&rq[i], &a.hv.hist_patch[hb + pos], pol_stream);
+                        dsim_cp_async8_hint(&rgain[i], &a.hv.hist_harv[hb + pos], pol_stream);
+#else
                         dsim_cp_async4(&rq[i], &a.hv.hist_patch[hb + pos]);
                         dsim_cp_async8(&rgain[i], &a.hv.hist_harv[hb + pos]);
+#endif
                     }
                 }
                 dsim_cp_async_commit();
