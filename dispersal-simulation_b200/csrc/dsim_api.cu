@@ -159,6 +159,9 @@ uint32_t occ_prev_index(const dsim_handle *h) { return h->mg_enabled ? h->mg_occ
 int sync_ctl(dsim_handle *h) { /* device -> pinned host mirror */
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    /* the host sees the step as finished: bookkeeping the device would only apply at its next step is applied to the
+     * mirror (every writer pushes the whole mirror back, so the two never disagree about what is still due) */
+    dsim_apply_advance(h->ctl_h);
     return DSIM_OK;
 }
 int push_ctl(dsim_handle *h) {
@@ -792,6 +795,8 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     if (g->lat) h->lat_h.assign(g->lat, g->lat + n);
     std::memset(&h->geom, 0, sizeof h->geom);
     h->geom.n_sm = (uint32_t)std::max(1, prop.multiProcessorCount);
+    h->geom.pdl = (h->opt.flags & DSIM_OPT_NO_PDL) ? 0u : DSIM_PDL_DEFAULT_MASK;
+    if (const char *e = std::getenv("DSIM_PDL_MASK")) h->geom.pdl = (uint32_t)std::strtoul(e, nullptr, 0); /* developer A/B */
     std::memset(&h->rt, 0, sizeof h->rt);
     std::memset(&h->ps, 0, sizeof h->ps);
     std::memset(&h->hv, 0, sizeof h->hv);

@@ -1,7 +1,7 @@
 /*
  * dsim_kernels.cu — the step loop of the dispersal model as sm_100a kernels.
  *
- * One season = `step` (lib.rs:477-496) = nine launches, replayed as a CUDA graph:
+ * One season = `step` (lib.rs:477-496) = eight launches (the last three concurrent), replayed as a CUDA graph:
  *
  *   part 1, update_each_family_step (lib.rs:511-552)
  *     k_lifecycle   consume / shrink / grow per family (lib.rs:527-539, 1912-1937); survivor and
@@ -20,7 +20,8 @@
  *                   block per crowded node (the three run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
  *                   (lib.rs:1754-1785, 1960-1970), exploit_patch + recover (lib.rs:2021-2109), next step's
  *                   census, quality and band cultures (lib.rs:522-525, 989-994, 622-633)
- *     k_advance     one thread: heavy-slot allocator bookkeeping, t += 1 (src/cli.rs:154)
+ *     (the heavy-slot allocator bookkeeping and t += 1, src/cli.rs:154, are marked as due by k_scatter and applied by
+ *     the tail of the next k_lifecycle or by the host's read of the control block: dsim_apply_advance)
  *
  * Floating point: doubles, IEEE operations only, compiled with -fmad=false so that every decision
  * (`g > m`, `res < max`, `stored - size*season < 0`) matches the CPU oracle bit for bit.
@@ -71,6 +72,7 @@ __device__ __forceinline__ double noise_draw(const ModelConst &mc, uint32_t step
 __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint32_t nvb);
 
 __global__ void __launch_bounds__(LIFE_BLOCK) k_lifecycle(StepArgs a) {
+    dsim_pdl_wait();
     const uint32_t n = a.ctl->n_cur[a.parity];
     const uint32_t nvb = (n + LIFE_BLOCK - 1) / LIFE_BLOCK;
     __shared__ uint32_t s_alive[LIFE_BLOCK / 32], s_split[LIFE_BLOCK / 32];
@@ -186,6 +188,7 @@ __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint
         es += vs;
     }
     if (tid == 0) {
+        dsim_apply_advance(ctl); /* the end of the previous step: before its n_children / n_dead are replaced */
         const uint32_t carry_a = tot_a, carry_s = tot_s;
         const uint32_t n_alive = carry_a, n_children = carry_s;
         ctl->n_alive = n_alive;
@@ -537,6 +540,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
     __shared__ MoveTile tiles[MOVE_WARPS];
     MoveTile &S = tiles[threadIdx.x >> 5];
     DevCtl *ctl = a.ctl;
+    dsim_pdl_wait();
     const uint32_t n = ctl->n_cur[a.parity];
     const uint32_t step = ctl->t;
     const uint32_t cap = ctl->cap;
@@ -1053,6 +1057,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
  * over the lanes. */
 __global__ void __launch_bounds__(128) k_children(StepArgs a) {
     DevCtl *ctl = a.ctl;
+    dsim_pdl_wait();
     const uint32_t step = ctl->t;
     const uint32_t n_children = ctl->n_children;
     const uint32_t cap = ctl->cap;
@@ -1310,6 +1315,7 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
      * k_mg_unpack counted) speaks for the node: it claims the node's segment of `members`, lists the node as occupied
      * and hands it to the patch kernel for its family count.  Every counter is bumped once per warp. */
     DevCtl *ctl = a.ctl;
+    dsim_pdl_wait();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = ctl->n_next;
@@ -1321,26 +1327,42 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
             p = a.next.place[j].loc;
             c = a.ps.cnt[p];
         }
-        /* segment starts: exclusive scan of the counts over the warp + one atomic for the warp's total */
-        const uint32_t incl = warp_incl_scan_u32(c, lane);
-        uint32_t base = 0;
-        const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
-        if (lane == 0 && total) base = atomicAdd(&ctl->seg_cursor, total);
-        base = __shfl_sync(DSIM_FULL, base, 0);
-        if (first) a.ps.seg[p] = base + incl - c;
-        const uint32_t k_occ = warp_append(&ctl->n_occ[a.occ_par], first, lane);
-        if (first) a.sc.occ[a.occ_par][k_occ] = p;
         /* by family count: a thread, eight lanes, a warp or a block per node */
         const bool one = first && c == 1u && a.small_max >= 1u;
         const bool small = first && !one && c <= a.small_max;
         const bool mid = first && !one && !small && c <= a.mid_max;
         const bool big = first && !one && !small && !mid;
-        const uint32_t k_one = warp_append(&ctl->n_one, one, lane), k_small = warp_append(&ctl->n_small, small, lane);
-        const uint32_t k_mid = warp_append(&ctl->n_mid, mid, lane), k_big = warp_append(&ctl->n_big, big, lane);
-        if (one) a.sc.plist_one[k_one] = p;
-        if (small) a.sc.plist_small[k_small] = p;
-        if (mid) a.sc.plist_mid[k_mid] = p;
-        if (big) a.sc.plist_big[k_big] = p;
+        /* segment starts: exclusive scan of the counts over the warp; positions in the five lists: rank among the
+         * warp's lanes.  Lane 0 then bumps the six counters with six atomics that are in flight together (one memory
+         * round trip per warp instead of six). */
+        const uint32_t incl = warp_incl_scan_u32(c, lane);
+        const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
+        const uint32_t m_first = __ballot_sync(DSIM_FULL, first), m_one = __ballot_sync(DSIM_FULL, one);
+        const uint32_t m_small = __ballot_sync(DSIM_FULL, small), m_mid = __ballot_sync(DSIM_FULL, mid), m_big = __ballot_sync(DSIM_FULL, big);
+        uint32_t b_seg = 0, b_occ = 0, b_one = 0, b_small = 0, b_mid = 0, b_big = 0;
+        if (lane == 0 && m_first) {
+            b_seg = atomicAdd(&ctl->seg_cursor, total);
+            b_occ = atomicAdd(&ctl->n_occ[a.occ_par], (uint32_t)__popc(m_first));
+            if (m_one) b_one = atomicAdd(&ctl->n_one, (uint32_t)__popc(m_one));
+            if (m_small) b_small = atomicAdd(&ctl->n_small, (uint32_t)__popc(m_small));
+            if (m_mid) b_mid = atomicAdd(&ctl->n_mid, (uint32_t)__popc(m_mid));
+            if (m_big) b_big = atomicAdd(&ctl->n_big, (uint32_t)__popc(m_big));
+        }
+        b_seg = __shfl_sync(DSIM_FULL, b_seg, 0);
+        b_occ = __shfl_sync(DSIM_FULL, b_occ, 0);
+        b_one = __shfl_sync(DSIM_FULL, b_one, 0);
+        b_small = __shfl_sync(DSIM_FULL, b_small, 0);
+        b_mid = __shfl_sync(DSIM_FULL, b_mid, 0);
+        b_big = __shfl_sync(DSIM_FULL, b_big, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (first) {
+            a.ps.seg[p] = b_seg + incl - c;
+            a.sc.occ[a.occ_par][b_occ + (uint32_t)__popc(m_first & below)] = p;
+        }
+        if (one) a.sc.plist_one[b_one + (uint32_t)__popc(m_one & below)] = p;
+        if (small) a.sc.plist_small[b_small + (uint32_t)__popc(m_small & below)] = p;
+        if (mid) a.sc.plist_mid[b_mid + (uint32_t)__popc(m_mid & below)] = p;
+        if (big) a.sc.plist_big[b_big + (uint32_t)__popc(m_big & below)] = p;
     }
     if (a.mg.enabled) return; /* the multi-GPU step recycles heavy slots in k_mg_finish (emigrants, immigrants) */
     /* heavy slots vacated this step go onto the free stack, above what the children did not pop */
@@ -1352,9 +1374,15 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
 
 __global__ void __launch_bounds__(256) k_scatter(StepArgs a) {
     DevCtl *ctl = a.ctl;
+    dsim_pdl_wait();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n = ctl->n_next;
     for (uint32_t j = tid; j < n; j += nth) a.sc.members[a.ps.seg[a.next.place[j].loc] + a.sc.fslot[j]] = j;
+    /* The end-of-step bookkeeping (heavy-slot allocator, `s.t += 1`, src/cli.rs:154) has no kernel of its own: it is
+     * marked as due here — k_children, the last reader of the allocator fields, is done; the patch kernels still read
+     * ctl->t, which does not change yet — and applied by the tail of the next k_lifecycle, or by the host when it
+     * reads the control block (sync_ctl).  The multi-GPU step keeps its own k_mg_finish2. */
+    if (tid == 0 && !a.mg.enabled) ctl->advance_pending = 1u;
     /* nodes occupied last step and empty now: census 0, no band cultures (lib.rs:522-525, 614) */
     const uint32_t n_prev = ctl->n_occ[a.occ_par ^ 1u];
     for (uint32_t k = tid; k < n_prev; k += nth) {
@@ -1716,6 +1744,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
     uint8_t *const s_u8 = smem_raw + 10u * 8u * PATCH_M + 6u * 4u * PATCH_M;
 
     DevCtl *ctl = a.ctl;
+    dsim_pdl_wait();
     const uint32_t step = ctl->t;
     const uint32_t tid = threadIdx.x;
     const uint32_t gwarp = blockIdx.x, nwarps = gridDim.x;
@@ -2011,23 +2040,15 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
 }
 
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
+    dsim_pdl_wait();
     patch_groups<1u>(a, a.sc.plist_one, a.ctl->n_one); /* a family alone on its node: a thread per node */
     patch_groups<8u>(a, a.sc.plist_small, a.ctl->n_small);
 }
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_mid(StepArgs a) {
+    dsim_pdl_wait();
     patch_groups<32u>(a, a.sc.plist_mid, a.ctl->n_mid);
 }
 
-__global__ void k_advance(StepArgs a) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    DevCtl *ctl = a.ctl;
-    const uint32_t ft = ctl->free_top, births = ctl->n_children, dead = ctl->n_dead;
-    const uint32_t popped = births < ft ? births : ft;
-    ctl->hs_hwm += births - popped;
-    ctl->free_top = ft - popped + dead;
-    if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
-    ctl->t += 1u; /* s.t += 1, src/cli.rs:154 */
-}
 
 /* ------------------------------------------------------------------------------------------ *
  * census for freshly loaded states: view.pop and view.quality (lib.rs:522-525, 989-994)
@@ -2076,18 +2097,27 @@ __global__ void k_reset_cnt(PatchState ps, const uint32_t *occ, const DevCtl *ct
 static uint32_t grid_for(const LaunchGeom &g, uint32_t per_sm) { return g.n_sm * per_sm; }
 
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s) {
+    /* every kernel of the step starts with dsim_pdl_wait(): with g.pdl they are launched programmatically dependent on
+     * their predecessor (dsim_rt.h) */
+#define STEP_LAUNCH(kernel, grid, block, smem)                   \
+    do {                                                         \
+        if ((g.pdl >> which) & 1u)                               \
+            DSIM_LAUNCH_PDL(kernel, grid, block, smem, s, a);    \
+        else                                                     \
+            DSIM_LAUNCH(kernel, grid, block, smem, s, a);        \
+    } while (0)
     switch (which) {
-    case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break;
-    case DSIM_K_MOVE: DSIM_LAUNCH(k_move, grid_for(g, MOVE_MIN_BLOCKS), MOVE_WARPS * 32, 0, s, a); break;
-    case DSIM_K_CHILDREN: DSIM_LAUNCH(k_children, grid_for(g, 2), 128, 0, s, a); break;
-    case DSIM_K_SEGMENTS: DSIM_LAUNCH(k_segments, grid_for(g, 8), 256, 0, s, a); break;
-    case DSIM_K_SCATTER: DSIM_LAUNCH(k_scatter, grid_for(g, 8), 256, 0, s, a); break;
-    case DSIM_K_PATCH_SMALL: DSIM_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
-    case DSIM_K_PATCH_MID: DSIM_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0, s, a); break;
-    case DSIM_K_PATCH: DSIM_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, PATCH_SMEM_BYTES, s, a); break;
-    case DSIM_K_ADVANCE: DSIM_LAUNCH(k_advance, 1, 32, 0, s, a); break;
+    case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break; /* first of the step: a full dependency on what precedes */
+    case DSIM_K_MOVE: STEP_LAUNCH(k_move, grid_for(g, MOVE_MIN_BLOCKS), MOVE_WARPS * 32, 0); break;
+    case DSIM_K_CHILDREN: STEP_LAUNCH(k_children, grid_for(g, 2), 128, 0); break;
+    case DSIM_K_SEGMENTS: STEP_LAUNCH(k_segments, grid_for(g, 8), 256, 0); break;
+    case DSIM_K_SCATTER: STEP_LAUNCH(k_scatter, grid_for(g, 8), 256, 0); break;
+    case DSIM_K_PATCH_SMALL: STEP_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
+    case DSIM_K_PATCH_MID: STEP_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
+    case DSIM_K_PATCH: STEP_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, PATCH_SMEM_BYTES); break;
     default: break;
     }
+#undef STEP_LAUNCH
 }
 
 void dsim_launch_iota(uint32_t *v, uint32_t n, const LaunchGeom &g, cudaStream_t s) {

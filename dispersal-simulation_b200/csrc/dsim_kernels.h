@@ -25,7 +25,14 @@ struct StepArgs {
 
 struct LaunchGeom {
     uint32_t n_sm;               /* grids are multiples of the SM count (148 on B200); kernels are grid-stride */
+    uint32_t pdl;                /* bit k: kernel DSIM_K_<k> of a step is launched programmatically dependent on its predecessor */
 };
+
+/* Programmatic dependent launches were measured on B200 (profiles/r02_step_ab.md): inside a replayed CUDA graph the
+ * kernel-to-kernel gaps are already ~1 us, PDL without an early trigger changes nothing (0.1805 vs 0.1815 ms per step
+ * at C2) and with griddepcontrol.launch_dependents at the top of every kernel it costs 5-10 % (parked blocks of the
+ * dependent kernel take SM resources from the tail of the running one).  Off by default; DSIM_PDL_MASK selects kernels. */
+#define DSIM_PDL_DEFAULT_MASK 0x00u
 
 /* one-time function attributes (none at present) */
 int dsim_configure_kernels(LaunchGeom *g);
@@ -39,12 +46,11 @@ enum {
     DSIM_K_PATCH_SMALL,
     DSIM_K_PATCH_MID,
     DSIM_K_PATCH,
-    DSIM_K_ADVANCE,
     DSIM_K_COUNT
 };
 
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_move",  "k_children", "k_segments",
-                                                            "k_scatter",   "k_patch_small", "k_patch_mid", "k_patch", "k_advance"};
+                                                            "k_scatter",   "k_patch_small", "k_patch_mid", "k_patch"};
 
 enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,
        DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH, DSIM_MGK_FINISH2, DSIM_MGK_PUSH_SPLIT, DSIM_MGK_PUSH_EMIG, DSIM_MGK_PUSH_HALO,

@@ -15,6 +15,8 @@
 
 #include <stdint.h>
 
+#include "../../include/dsim.h"
+
 #define DSIM_ROW_HASH_MAX 192u
 #define DSIM_NIDX_NONE 0xFFFFu   /* reach entry that is not in the 2-hop `nearby` list */
 #define DSIM_ECO_EMPTY 0xFFFFu   /* free adaptation slot */
@@ -152,9 +154,27 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t cap, hs_cap;
     uint32_t life_done;      /* blocks of k_lifecycle that have finished (the last one scans and resets it) */
     uint32_t move_next;      /* next tile of k_move to hand out (reset by the tail of k_lifecycle)           */
+    uint32_t advance_pending;/* the end-of-step bookkeeping of the last step is still due (dsim_apply_advance)      */
+    uint32_t pad_;
     uint64_t child_id_base, next_id;
     uint64_t births, deaths, updates;
 };
+
+/* End-of-step bookkeeping: heavy slots popped by the children and pushed by the dead, `s.t += 1` (src/cli.rs:154).
+ * Runs in the tail of the next k_lifecycle (device) or when the host reads the control block, whichever comes first. */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void dsim_apply_advance(DevCtl *ctl) {
+    if (!ctl->advance_pending) return;
+    const uint32_t ft = ctl->free_top, births = ctl->n_children, dead = ctl->n_dead;
+    const uint32_t popped = births < ft ? births : ft;
+    ctl->hs_hwm += births - popped;
+    ctl->free_top = ft - popped + dead;
+    if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= (uint32_t)DSIM_MODEL_CAPACITY;
+    ctl->t += 1u;
+    ctl->advance_pending = 0u;
+}
 
 struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed by value          */
     double recovery, season, cap_harvest, min_adapt, log1m_rate;

@@ -135,6 +135,7 @@ typedef struct dsim_options {
                                         * to the host builder for graphs with reach sets of more than 384 or 2-hop sets of
                                         * more than 512 nodes); the flag is accepted and changes nothing */
 #define DSIM_OPT_REACH_ON_HOST 0x8u   /* build the reach table with the host (OpenMP) builder */
+#define DSIM_OPT_NO_PDL 0x10u         /* plain stream-ordered launches instead of programmatic dependent launches (A/B knob) */
 
 typedef struct dsim_step_stats {
     uint64_t t;               /* State.t after the call (lib.rs:308; `s.t += 1`, cli.rs:154) */
