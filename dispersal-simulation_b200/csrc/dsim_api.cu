@@ -61,8 +61,8 @@ struct dsim_handle {
     dsim_params p;
     dsim_options opt;
     uint64_t seed = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr, join4_ev = nullptr;
     LaunchGeom geom;
     uint32_t n_nodes = 0, n_eco = 0;
     std::vector<uint32_t> eco_off_h; /* [n+1] */
@@ -307,25 +307,42 @@ int ensure_capacity(dsim_handle *h, uint64_t n_now) {
 }
 
 #if !defined(DSIM_EMU)
+/* The four patch kernels work on disjoint sets of nodes: they fork from the main stream onto three side streams and
+ * join it again (also inside a stream capture, where the events become graph edges), so they run concurrently. */
+int launch_patch_kernels(dsim_handle *h, const StepArgs &a) {
+    CK(cudaEventRecord(h->fork_ev, h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+    CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
+    CK(cudaStreamWaitEvent(h->stream4, h->fork_ev, 0));
+    dsim_launch_kernel(DSIM_K_PATCH_SMALL, a, h->geom, h->stream);
+    dsim_launch_kernel(DSIM_K_PATCH_ONE, a, h->geom, h->stream4);
+    dsim_launch_kernel(DSIM_K_PATCH_MID, a, h->geom, h->stream3);
+    dsim_launch_kernel(DSIM_K_PATCH, a, h->geom, h->stream2);
+    CK(cudaEventRecord(h->join_ev, h->stream2));
+    CK(cudaEventRecord(h->join3_ev, h->stream3));
+    CK(cudaEventRecord(h->join4_ev, h->stream4));
+    CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+    CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
+    CK(cudaStreamWaitEvent(h->stream, h->join4_ev, 0));
+    for (int k = DSIM_K_PATCH_ONE; k <= DSIM_K_PATCH; ++k) h->k_launches[k] += 1;
+    h->total_launches += 4;
+    return DSIM_OK;
+}
+
 int build_graphs(dsim_handle *h) {
-    /* one graph per buffer parity.  k_patch_small and k_patch work on disjoint sets of nodes, so they are
-     * captured on two branches (fork/join through events on a second stream) and run concurrently. */
+    /* one graph per buffer parity */
     for (uint32_t par = 0; par < 2; ++par) {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const StepArgs a = make_args(h, par);
-        for (int k = 0; k < DSIM_K_PATCH_SMALL; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
-        CK(cudaEventRecord(h->fork_ev, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
-        CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
-        dsim_launch_kernel(DSIM_K_PATCH_SMALL, a, h->geom, h->stream);
-        dsim_launch_kernel(DSIM_K_PATCH_MID, a, h->geom, h->stream3);
-        dsim_launch_kernel(DSIM_K_PATCH, a, h->geom, h->stream2);
-        CK(cudaEventRecord(h->join_ev, h->stream2));
-        CK(cudaEventRecord(h->join3_ev, h->stream3));
-        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
-        CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
-        for (int k = DSIM_K_PATCH + 1; k < DSIM_K_COUNT; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        for (int k = 0; k < DSIM_K_PATCH_ONE; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        const uint64_t tl = h->total_launches; /* counted per replay, not per capture */
+        uint64_t kl[DSIM_K_COUNT];
+        std::memcpy(kl, h->k_launches, sizeof kl);
+        int rc = launch_patch_kernels(h, a);
+        h->total_launches = tl;
+        std::memcpy(h->k_launches, kl, sizeof kl);
+        if (rc) return rc;
         CK(cudaStreamEndCapture(h->stream, &g));
         CK(cudaGraphInstantiate(&h->gexec[par], g, 0));
         CK(cudaGraphDestroy(g));
@@ -743,6 +760,8 @@ void dsim_destroy(dsim_handle *h) {
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->join_ev) cudaEventDestroy(h->join_ev);
     if (h->join3_ev) cudaEventDestroy(h->join3_ev);
+    if (h->join4_ev) cudaEventDestroy(h->join4_ev);
+    if (h->stream4) cudaStreamDestroy(h->stream4);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -818,9 +837,11 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
     TRYCUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join3_ev, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&h->join4_ev, cudaEventDisableTiming));
     for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
     for (auto &e : h->tev) TRYCUDA(cudaEventCreate(&e));
     TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
@@ -1851,20 +1872,14 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     case MG_PHASE_FINISH_BOOK: M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2); break;
     case DSIM_MG_PHASE_PATCH:
         M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2);
-        /* the two patch kernels work on disjoint nodes: run them concurrently (second stream, also inside a capture) */
-        CK(cudaEventRecord(h->fork_ev, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
-        CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
-        K(DSIM_K_PATCH_SMALL, a2);
-        dsim_launch_kernel(DSIM_K_PATCH_MID, a2, h->geom, h->stream3);
-        dsim_launch_kernel(DSIM_K_PATCH, a2, h->geom, h->stream2);
-        h->k_launches[DSIM_K_PATCH_MID] += 1;
-        h->k_launches[DSIM_K_PATCH] += 1;
-        h->total_launches += 2;
-        CK(cudaEventRecord(h->join_ev, h->stream2));
-        CK(cudaEventRecord(h->join3_ev, h->stream3));
-        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
-        CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
+#if defined(DSIM_EMU)
+        for (int k = DSIM_K_PATCH_ONE; k <= DSIM_K_PATCH; ++k) K(k, a2);
+#else
+        {
+            int rc = launch_patch_kernels(h, a2);
+            if (rc) return rc;
+        }
+#endif
         M(DSIM_MGK_HALO_PACK, a2);
         break;
     case DSIM_MG_PHASE_FINISH:

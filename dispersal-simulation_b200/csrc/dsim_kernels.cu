@@ -1,7 +1,7 @@
 /*
  * dsim_kernels.cu — the step loop of the dispersal model as sm_100a kernels.
  *
- * One season = `step` (lib.rs:477-496) = eight launches (the last three concurrent), replayed as a CUDA graph:
+ * One season = `step` (lib.rs:477-496) = nine launches (the last four concurrent), replayed as a CUDA graph:
  *
  *   part 1, update_each_family_step (lib.rs:511-552)
  *     k_lifecycle   consume / shrink / grow per family (lib.rs:527-539, 1912-1937); survivor and
@@ -16,8 +16,8 @@
  *   part 2, distribute_each_patch_resources_step (lib.rs:591-655)
  *     k_segments    one thread per occupied node: claim a segment of `members`
  *     k_scatter     one thread per family: counting-sort scatter; clears the views of vacated nodes
- *     k_patch_small eight lanes per node with at most 8 families, k_patch_mid a warp per node with 9..32, k_patch a
- *                   block per crowded node (the three run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
+ *     k_patch_one   a thread per node with a single family, k_patch_small eight lanes per node with 2..8 families,
+ *     k_patch_mid   a warp per node with 9..32, k_patch a block per crowded node (the four run concurrently): cooperate_or_fight (lib.rs:1372-1417), adjust_culture / mutate
  *                   (lib.rs:1754-1785, 1960-1970), exploit_patch + recover (lib.rs:2021-2109), next step's
  *                   census, quality and band cultures (lib.rs:522-525, 989-994, 622-633)
  *     (the heavy-slot allocator bookkeeping and t += 1, src/cli.rs:154, are marked as due by k_scatter and applied by
@@ -1313,14 +1313,17 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred, ui
 __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
     /* One thread per family.  The first arrival at a node (rank 0 of the histogram that k_move, k_children and
      * k_mg_unpack counted) speaks for the node: it claims the node's segment of `members`, lists the node as occupied
-     * and hands it to the patch kernel for its family count.  Every counter is bumped once per warp. */
+     * and hands it to the patch kernel for its family count.  The six counters (all in one cache line of the control
+     * block) are bumped once per BLOCK of 256 families: per warp they cost half of the kernel's time in same-address
+     * atomics (profiles/r02_small_kernels.md). */
     DevCtl *ctl = a.ctl;
     dsim_pdl_wait();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint32_t s_tot[8][6], s_base[8][6];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t n = ctl->n_next;
-    const uint32_t n_round = (n + 31u) & ~31u; /* whole warps take part in the ballots */
-    for (uint32_t j = tid; j < n_round; j += nth) {
+    const uint32_t n_round = (n + 255u) & ~255u; /* whole blocks take part in the barriers */
+    for (uint32_t j0 = blockIdx.x * 256u; j0 < n_round; j0 += gridDim.x * 256u) {
+        const uint32_t j = j0 + threadIdx.x;
         const bool first = j < n && a.sc.fslot[j] == 0u;
         uint32_t p = 0, c = 0;
         if (first) {
@@ -1332,38 +1335,42 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         const bool small = first && !one && c <= a.small_max;
         const bool mid = first && !one && !small && c <= a.mid_max;
         const bool big = first && !one && !small && !mid;
-        /* segment starts: exclusive scan of the counts over the warp; positions in the five lists: rank among the
-         * warp's lanes.  Lane 0 then bumps the six counters with six atomics that are in flight together (one memory
-         * round trip per warp instead of six). */
+        /* segment starts: exclusive scan of the counts; positions in the five lists: rank among the block's threads */
         const uint32_t incl = warp_incl_scan_u32(c, lane);
-        const uint32_t total = __shfl_sync(DSIM_FULL, incl, 31);
         const uint32_t m_first = __ballot_sync(DSIM_FULL, first), m_one = __ballot_sync(DSIM_FULL, one);
         const uint32_t m_small = __ballot_sync(DSIM_FULL, small), m_mid = __ballot_sync(DSIM_FULL, mid), m_big = __ballot_sync(DSIM_FULL, big);
-        uint32_t b_seg = 0, b_occ = 0, b_one = 0, b_small = 0, b_mid = 0, b_big = 0;
-        if (lane == 0 && m_first) {
-            b_seg = atomicAdd(&ctl->seg_cursor, total);
-            b_occ = atomicAdd(&ctl->n_occ[a.occ_par], (uint32_t)__popc(m_first));
-            if (m_one) b_one = atomicAdd(&ctl->n_one, (uint32_t)__popc(m_one));
-            if (m_small) b_small = atomicAdd(&ctl->n_small, (uint32_t)__popc(m_small));
-            if (m_mid) b_mid = atomicAdd(&ctl->n_mid, (uint32_t)__popc(m_mid));
-            if (m_big) b_big = atomicAdd(&ctl->n_big, (uint32_t)__popc(m_big));
+        if (lane == 31u) {
+            s_tot[w][0] = incl;
+            s_tot[w][1] = (uint32_t)__popc(m_first);
+            s_tot[w][2] = (uint32_t)__popc(m_one);
+            s_tot[w][3] = (uint32_t)__popc(m_small);
+            s_tot[w][4] = (uint32_t)__popc(m_mid);
+            s_tot[w][5] = (uint32_t)__popc(m_big);
         }
-        b_seg = __shfl_sync(DSIM_FULL, b_seg, 0);
-        b_occ = __shfl_sync(DSIM_FULL, b_occ, 0);
-        b_one = __shfl_sync(DSIM_FULL, b_one, 0);
-        b_small = __shfl_sync(DSIM_FULL, b_small, 0);
-        b_mid = __shfl_sync(DSIM_FULL, b_mid, 0);
-        b_big = __shfl_sync(DSIM_FULL, b_big, 0);
+        __syncthreads();
+        if (threadIdx.x < 6u) { /* thread k: counter k — six atomics in flight together, one memory round trip per block */
+            uint32_t *counter = threadIdx.x == 0u ? &ctl->seg_cursor : threadIdx.x == 1u ? &ctl->n_occ[a.occ_par] : threadIdx.x == 2u ? &ctl->n_one
+                                : threadIdx.x == 3u ? &ctl->n_small : threadIdx.x == 4u ? &ctl->n_mid : &ctl->n_big;
+            uint32_t tot = 0;
+            for (uint32_t k = 0; k < 8u; ++k) tot += s_tot[k][threadIdx.x];
+            uint32_t base = tot ? atomicAdd(counter, tot) : 0u;
+            for (uint32_t k = 0; k < 8u; ++k) {
+                s_base[k][threadIdx.x] = base;
+                base += s_tot[k][threadIdx.x];
+            }
+        }
+        __syncthreads();
         const uint32_t below = (1u << lane) - 1u;
         if (first) {
-            a.ps.seg[p] = b_seg + incl - c;
-            a.sc.occ[a.occ_par][b_occ + (uint32_t)__popc(m_first & below)] = p;
+            a.ps.seg[p] = s_base[w][0] + incl - c;
+            a.sc.occ[a.occ_par][s_base[w][1] + (uint32_t)__popc(m_first & below)] = p;
         }
-        if (one) a.sc.plist_one[b_one + (uint32_t)__popc(m_one & below)] = p;
-        if (small) a.sc.plist_small[b_small + (uint32_t)__popc(m_small & below)] = p;
-        if (mid) a.sc.plist_mid[b_mid + (uint32_t)__popc(m_mid & below)] = p;
-        if (big) a.sc.plist_big[b_big + (uint32_t)__popc(m_big & below)] = p;
+        if (one) a.sc.plist_one[s_base[w][2] + (uint32_t)__popc(m_one & below)] = p;
+        if (small) a.sc.plist_small[s_base[w][3] + (uint32_t)__popc(m_small & below)] = p;
+        if (mid) a.sc.plist_mid[s_base[w][4] + (uint32_t)__popc(m_mid & below)] = p;
+        if (big) a.sc.plist_big[s_base[w][5] + (uint32_t)__popc(m_big & below)] = p;
     }
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (a.mg.enabled) return; /* the multi-GPU step recycles heavy slots in k_mg_finish (emigrants, immigrants) */
     /* heavy slots vacated this step go onto the free stack, above what the children did not pop */
     const uint32_t ft = ctl->free_top, births = ctl->n_children, dead = ctl->n_dead;
@@ -2039,9 +2046,14 @@ __device__ __forceinline__ void patch_groups(const StepArgs &a, const uint32_t *
     if (errors) atomicOr(&ctl->errors, errors);
 }
 
+/* a family alone on its node: a thread per node; a kernel of its own so that its chain of memory round trips runs
+ * next to the one of the eight-lane groups instead of ahead of it */
+__global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_one(StepArgs a) {
+    dsim_pdl_wait();
+    patch_groups<1u>(a, a.sc.plist_one, a.ctl->n_one);
+}
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_small(StepArgs a) {
     dsim_pdl_wait();
-    patch_groups<1u>(a, a.sc.plist_one, a.ctl->n_one); /* a family alone on its node: a thread per node */
     patch_groups<8u>(a, a.sc.plist_small, a.ctl->n_small);
 }
 __global__ void __launch_bounds__(128, PATCH_SMALL_MIN_BLOCKS) k_patch_mid(StepArgs a) {
@@ -2112,6 +2124,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_CHILDREN: STEP_LAUNCH(k_children, grid_for(g, 2), 128, 0); break;
     case DSIM_K_SEGMENTS: STEP_LAUNCH(k_segments, grid_for(g, 8), 256, 0); break;
     case DSIM_K_SCATTER: STEP_LAUNCH(k_scatter, grid_for(g, 8), 256, 0); break;
+    case DSIM_K_PATCH_ONE: STEP_LAUNCH(k_patch_one, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
     case DSIM_K_PATCH_SMALL: STEP_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
     case DSIM_K_PATCH_MID: STEP_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
     case DSIM_K_PATCH: STEP_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, PATCH_SMEM_BYTES); break;

@@ -43,6 +43,7 @@ enum {
     DSIM_K_CHILDREN,
     DSIM_K_SEGMENTS,
     DSIM_K_SCATTER,
+    DSIM_K_PATCH_ONE,
     DSIM_K_PATCH_SMALL,
     DSIM_K_PATCH_MID,
     DSIM_K_PATCH,
@@ -50,7 +51,7 @@ enum {
 };
 
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_move",  "k_children", "k_segments",
-                                                            "k_scatter",   "k_patch_small", "k_patch_mid", "k_patch"};
+                                                            "k_scatter",   "k_patch_one", "k_patch_small", "k_patch_mid", "k_patch"};
 
 enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,
        DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH, DSIM_MGK_FINISH2, DSIM_MGK_PUSH_SPLIT, DSIM_MGK_PUSH_EMIG, DSIM_MGK_PUSH_HALO,
