@@ -1717,7 +1717,13 @@ StepArgs mg_args(dsim_handle *h, bool part2) {
     a.mg.world = m->world;
     a.mg.own_lo = m->own_lo;
     a.mg.own_hi = m->own_hi;
-    a.mg.child_grank = m->mb.child_grank;
+    a.mg.split_send = m->mb.split_send;
+    a.mg.split_recv = m->mb.split_recv;
+    a.mg.scap = m->mb.scap;
+    a.mg.p2p = m->mb.p2p;
+    a.mg.seq = m->mb.seq;
+    a.mg.flags = m->mb.flags;
+    a.mg.counters = m->mb.counters;
     a.mg.halo_cult[0] = m->mb.halo_cult[0];
     a.mg.halo_cult[1] = m->mb.halo_cult[1];
     if (part2) { /* part 2 runs in place on the re-packed buffer */
@@ -1788,7 +1794,7 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
         return rc;                                             \
     }
     MA(mb.split_send, 1 + (size_t)mb.scap) MA(mb.split_recv, 2 * (size_t)world * (1 + (size_t)mb.scap))
-    MA(mb.child_grank, mb.scap) MA(mb.counters, MG_N_COUNTERS) MA(mb.emig_list, 2 * (size_t)mb.ecap)
+    MA(mb.counters, MG_N_COUNTERS) MA(mb.emig_list, 2 * (size_t)mb.ecap)
     MA(mb.emig_hs, 2 * (size_t)mb.ecap) MA(mb.fslot2, h->cap)
     for (int s = 0; s < 2; ++s) {
         MA(mb.emig_send[s], m->emig_bytes) MA(mb.emig_recv[s], m->emig_bytes)
@@ -1858,18 +1864,16 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     case DSIM_MG_PHASE_LIFECYCLE:
         K(DSIM_K_LIFECYCLE, a1); M(DSIM_MGK_SPLIT_IDS, a1);
         break;
-    case DSIM_MG_PHASE_MOVE: /* the children's ids (CHILD_RANK, from the SPLIT exchange) are first needed by k_children */
-        K(DSIM_K_MOVE, a1); M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
+    case DSIM_MG_PHASE_MOVE: /* the children's ids (from the SPLIT exchange) are first needed by k_children */
+        K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
         break;
     case MG_PHASE_MOVE_A: K(DSIM_K_MOVE, a1); break;
-    case MG_PHASE_MOVE_B:
-        M(DSIM_MGK_CHILD_RANK, a1); K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1);
-        break;
+    case MG_PHASE_MOVE_B: K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1); break;
     case MG_PHASE_FINISH_HALO: /* on the second stream, next to MG_PHASE_FINISH_BOOK */
         dsim_mg_launch(DSIM_MGK_HALO_UNPACK, a2, mb, h->geom, h->stream2);
         h->total_launches += 1;
         break;
-    case MG_PHASE_FINISH_BOOK: M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2); break;
+    case MG_PHASE_FINISH_BOOK: M(DSIM_MGK_FINISH, a2); break;
     case DSIM_MG_PHASE_PATCH:
         M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2);
 #if defined(DSIM_EMU)
@@ -1883,7 +1887,7 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         M(DSIM_MGK_HALO_PACK, a2);
         break;
     case DSIM_MG_PHASE_FINISH:
-        M(DSIM_MGK_HALO_UNPACK, a2); M(DSIM_MGK_FINISH, a2); M(DSIM_MGK_FINISH2, a2);
+        M(DSIM_MGK_HALO_UNPACK, a2); M(DSIM_MGK_FINISH, a2);
         break;
     case DSIM_MG_PHASE_HALO_PACK:
         CK(cudaMemsetAsync(mb.counters, 0, MG_N_COUNTERS * sizeof(uint32_t), h->stream));
@@ -2016,16 +2020,10 @@ int dsim_mg_ipc_connect(dsim_handle *h, const void *all) {
 static int mg_exchange(dsim_handle *h, dsim_mg_state *m, int channel, cudaStream_t stream = nullptr) {
     const MgBuffers &mb = m->mb;
     if (stream == nullptr) stream = h->stream;
-    if (m->p2p) { /* remote stores into the neighbours' buffers + flag, then wait for the neighbours' flags */
-        const StepArgs a = mg_args(h, false);
-        static const int push[3] = {DSIM_MGK_PUSH_SPLIT, DSIM_MGK_PUSH_EMIG, DSIM_MGK_PUSH_HALO};
-        static const int wait[3] = {DSIM_MGK_WAIT_SPLIT, DSIM_MGK_WAIT_EMIG, DSIM_MGK_WAIT_HALO};
-        dsim_mg_launch(push[channel], a, mb, h->geom, stream);
-        dsim_mg_launch(wait[channel], a, mb, h->geom, stream);
-        h->total_launches += 2;
-        CK(cudaGetLastError());
-        return DSIM_OK;
-    }
+    /* peer-memory transport: nothing to do here — the packing kernels (k_mg_split_ids, k_mg_pack, k_mg_halo_pack) store
+     * straight into the receivers' buffers and publish a flag, the consuming kernels (k_children, k_mg_unpack,
+     * k_mg_halo_unpack) start by waiting for it */
+    if (m->p2p) return DSIM_OK;
     if (channel == DSIM_MG_CH_SPLIT) {
         NCK(ncclAllGather(mb.split_send, mb.split_recv, 1 + (size_t)mb.scap, ncclUint64, m->comm, stream));
         return DSIM_OK;
@@ -2052,6 +2050,18 @@ static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
      * step's k_move) next to the allocator bookkeeping.  The communicator sees its operations in one order: every
      * exchange is joined back into the main stream before the next one is enqueued. */
     int rc;
+    if (m->p2p) { /* peer memory: the messages travel inside the packing kernels; 18 launches, 14 of them in sequence */
+        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
+        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_MOVE))) return rc;
+        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_HALO))) return rc; /* waits for the neighbours' halos next to the bookkeeping */
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_BOOK))) return rc;
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        return DSIM_OK;
+    }
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
     CK(cudaEventRecord(h->fork_ev, h->stream));
     CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
@@ -2153,16 +2163,12 @@ int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set
 #else
     if (!m->nccl && !m->p2p) return fail(h, DSIM_ERR_COMM, "no transport");
     int rc;
-    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_PACK))) return rc;
-    const bool p2p = m->p2p;
-    if (m->nccl) {
-        m->p2p = false; /* with a communicator the exchange outside the steps is an NCCL operation (no exchange round) */
-    } else {        /* peer memory only: an exchange round of its own; every rank calls dsim_mg_halo_sync equally often */
+    if (m->p2p) { /* peer memory: an exchange round of its own; every rank calls dsim_mg_halo_sync equally often */
         dsim_mg_launch(DSIM_MGK_BUMP, mg_args(h, false), m->mb, h->geom, h->stream);
         h->total_launches += 1;
     }
+    if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_PACK))) return rc;
     rc = mg_exchange(h, m, DSIM_MG_CH_HALO);
-    m->p2p = p2p;
     if (rc) return rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
     CK(cudaStreamSynchronize(h->stream));

@@ -29,6 +29,7 @@
 #include "dsim_async.h"
 #include "dsim_kernels.h"
 #include "dsim_math.h"
+#include "dsim_mg_sync.h"
 
 #include <cstring>
 
@@ -1065,11 +1066,45 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 
+    /* Several GPUs: children get the ids the reference's append order (= parent order over ALL ranks) gives them, so a
+     * child's rank is the number of splitting parents, on any rank, with a smaller id — counted below from the SPLIT
+     * lists of all ranks.  With the peer-memory transport the lists were stored into this rank's receive area by the
+     * other ranks' k_mg_split_ids while k_move ran; the kernel starts by waiting for their flags. */
+    const uint64_t *split_lists = nullptr;
+    const size_t split_stride = 1 + (size_t)a.mg.scap;
+    if (a.mg.enabled) {
+        const uint32_t round = a.mg.p2p ? *a.mg.seq : 0u;
+        if (a.mg.p2p)
+            mg_wait_flags(a.mg.flags, MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD, a.mg.world, (1u << a.mg.world) - 1u, round, &ctl->errors);
+        split_lists = a.mg.split_recv + (a.mg.p2p ? (size_t)(round & 1u) * a.mg.world * split_stride : 0u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            uint64_t total = 0;
+            for (uint32_t r = 0; r < a.mg.world; ++r) total += split_lists[r * split_stride];
+            ctl->next_id = ctl->child_id_base + total; /* k_lifecycle's tail had added the local count only */
+            a.mg.counters[MG_N_STAY] = 0;
+            a.mg.counters[MG_N_EMIG0] = 0;
+            a.mg.counters[MG_N_EMIG1] = 0;
+            a.mg.counters[MG_HALO_CULT0] = 0;
+            a.mg.counters[MG_HALO_CULT1] = 0;
+        }
+    }
+
     for (uint32_t r = gwarp; r < n_children; r += nwarps) {
         const ChildTask t = a.sc.child_task[r];
-        /* ids follow the reference's append order = parent order; with several GPUs the rank among ALL
-         * children of the step comes from k_mg_child_rank */
-        const uint64_t cid = ctl->child_id_base + (a.mg.enabled ? a.mg.child_grank[r] : r);
+        uint32_t grank = r;
+        if (a.mg.enabled) { /* the lanes stride over the gathered lists */
+            const uint64_t id = a.mg.split_send[1 + r];
+            uint32_t smaller = 0;
+            for (uint32_t q = 0; q < a.mg.world; ++q) {
+                const uint64_t *list = split_lists + q * split_stride;
+                const uint32_t m = (uint32_t)list[0];
+                for (uint32_t k = lane; k < m; k += 32u) smaller += list[1 + k] < id ? 1u : 0u;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) smaller += __shfl_xor_sync(DSIM_FULL, smaller, d);
+            grank = smaller;
+        }
+        const uint64_t cid = ctl->child_id_base + grank;
         const uint32_t cpos = ctl->child_pos_base + r;
         const uint32_t ft = ctl->free_top;
         const uint32_t chs = (r < ft) ? a.sc.free_hs[ft - 1u - r] : ctl->hs_hwm + (r - ft);

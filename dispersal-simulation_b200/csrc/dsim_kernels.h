@@ -53,9 +53,8 @@ enum {
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_move",  "k_children", "k_segments",
                                                             "k_scatter",   "k_patch_one", "k_patch_small", "k_patch_mid", "k_patch"};
 
-enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_CHILD_RANK, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK,
-       DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH, DSIM_MGK_FINISH2, DSIM_MGK_PUSH_SPLIT, DSIM_MGK_PUSH_EMIG, DSIM_MGK_PUSH_HALO,
-       DSIM_MGK_WAIT_SPLIT, DSIM_MGK_WAIT_EMIG, DSIM_MGK_WAIT_HALO, DSIM_MGK_BUMP };
+enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK, DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH,
+       DSIM_MGK_BUMP };
 void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s);
 
 void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaStream_t s);

@@ -15,12 +15,38 @@
  */
 #include "dsim_kernels.h"
 #include "dsim_math.h"
+#include "dsim_mg_sync.h"
+
+/* The last block of a packing kernel to finish publishes the message: `publish` runs in one thread after every block's
+ * stores have been fenced at system scope. */
+template <typename F> __device__ __forceinline__ void mg_last_block(uint32_t *ticket, F publish) {
+    mg_fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(ticket, 1u);
+        if (prev == gridDim.x - 1u) {
+            *ticket = 0u;
+            mg_fence_sys();
+            publish();
+        }
+    }
+}
 
 /* ---- SPLIT ------------------------------------------------------------------------------------ */
-/* ids of the local families that split, at their local child rank; split_send[0] = count */
+/* ids of the local families that split, at their local child rank; split_send[0] = count.
+ * Peer-memory transport: the list also goes straight into every rank's receive area of this round's parity (remote
+ * 8-byte stores) and the last block to finish starts the exchange round of the step and publishes it in the
+ * receivers' flag words — the SPLIT message costs no kernel of its own.
+ * SPLIT is all-to-all, and nothing orders a rank's message of round r+1 after the consumption of round r (k_children,
+ * which runs after that rank's own k_move) on a rank three or more bands away: receive areas and flag words are
+ * doubled by round parity.  Round r+2 cannot be sent before every rank has sent round r+1 (the sender's HALO r+1 needs
+ * EMIGRANTS r+1 of its neighbour, which needs SPLIT r+1 of every rank), i.e. before every rank has consumed round r. */
 __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
     const uint32_t n = ctl->n_cur[a.parity];
+    const uint32_t round = mb.p2p ? *mb.seq + 1u : 0u; /* read before any block can have taken the last ticket */
+    const size_t stride = 1 + (size_t)mb.scap;
+    const size_t slot = ((size_t)(round & 1u) * a.mg.world + a.mg.rank) * stride;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
         const uint32_t split_mask = a.sc.split_bits[c];
@@ -28,52 +54,26 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         uint32_t vs = 0;
         vs += a.sc.word_pre[c] >> 16;
         const uint32_t crank = a.sc.blk_split[c >> 3] + vs + (uint32_t)__popc(split_mask & lt);
-        if (crank < mb.scap)
-            mb.split_send[1 + crank] = a.cur.key[i].id;
-        else
+        if (crank < mb.scap) {
+            const uint64_t id = a.cur.key[i].id;
+            mb.split_send[1 + crank] = id;
+            if (mb.p2p)
+                for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot + 1 + crank] = id;
+        } else {
             atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         mb.split_send[0] = ctl->n_children;
-        if (mb.p2p) *mb.seq += 1u; /* the exchange round of this step (first kernel of the step that knows the transport) */
+        if (mb.p2p)
+            for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot] = ctl->n_children;
     }
-}
-
-/* global rank of every local child = number of splitting parents, on any rank, with a smaller id.
- * One warp per child: the lanes stride over the gathered lists. */
-__global__ void __launch_bounds__(256) k_mg_child_rank(StepArgs a, MgBuffers mb) {
-    DevCtl *ctl = a.ctl;
-    const uint32_t n_local = ctl->n_children;
-    const size_t stride = 1 + (size_t)mb.scap;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    /* peer-memory transport: the lists of even and odd rounds arrive in two areas (see k_mg_push) */
-    const uint64_t *recv = mb.split_recv + (mb.p2p ? (size_t)(*mb.seq & 1u) * a.mg.world * stride : 0u);
-    for (uint32_t c = gw; c < n_local; c += nw) {
-        const uint64_t id = mb.split_send[1 + c];
-        uint32_t smaller = 0;
-        for (uint32_t r = 0; r < a.mg.world; ++r) {
-            const uint64_t *list = recv + r * stride;
-            const uint32_t m = (uint32_t)list[0];
-            for (uint32_t k = lane; k < m; k += 32u) smaller += list[1 + k] < id ? 1u : 0u;
-        }
-        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 16);
-        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 8);
-        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 4);
-        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 2);
-        smaller += __shfl_xor_sync(DSIM_FULL, smaller, 1);
-        if (lane == 0) mb.child_grank[c] = smaller;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        uint64_t total = 0;
-        for (uint32_t r = 0; r < a.mg.world; ++r) total += recv[r * stride];
-        ctl->next_id = ctl->child_id_base + total; /* k_lifecycle's tail had added the local count only */
-        mb.counters[MG_N_STAY] = 0;
-        mb.counters[MG_N_EMIG0] = 0;
-        mb.counters[MG_N_EMIG1] = 0;
-        mb.counters[MG_HALO_CULT0] = 0;
-        mb.counters[MG_HALO_CULT1] = 0;
-    }
+    if (!mb.p2p) return;
+    mg_last_block(&mb.done[DSIM_MG_CH_SPLIT], [&] {
+        *mb.seq = round; /* the exchange round of this step */
+        for (uint32_t r = 0; r < a.mg.world; ++r)
+            mg_st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + a.mg.rank, round);
+    });
 }
 
 /* ---- EMIGRANTS -------------------------------------------------------------------------------- */
@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
     }
 }
 
-/* one warp per emigrant: record + adaptation slots + history (chronological) into the send buffer */
+/* one warp per emigrant: record + adaptation slots + history (chronological) into the send buffer — with the
+ * peer-memory transport straight into the neighbour's receive buffer (remote stores over NVLink: the transfer overlaps
+ * the packing record by record), published by the last block to finish */
 __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
     for (uint32_t side = 0; side < 2u; ++side) {
         uint32_t m = mb.counters[MG_N_EMIG0 + side];
         if (m > mb.ecap) m = mb.ecap;
-        unsigned char *buf = mb.emig_send[side];
+        unsigned char *buf = (mb.p2p && mb.has_peer[side]) ? mb.peer_emig_recv[side] : mb.emig_send[side];
         if (gw == 0 && lane == 0) {
             *reinterpret_cast<uint64_t *>(buf) = m;
             atomicMax(&mb.counters[MG_MAX_EMIG], mb.counters[MG_N_EMIG0 + side]);
@@ -172,6 +174,13 @@ __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
             }
         }
     }
+    if (!mb.p2p) return;
+    mg_last_block(&mb.done[DSIM_MG_CH_EMIGRANTS], [&] {
+        const uint32_t round = *mb.seq;
+        /* what I send to my lower neighbour (side 0) arrives from ITS upper side (slot 1), and vice versa */
+        if (mb.has_peer[0]) mg_st_release_sys(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_EMIG0 + 1u, round);
+        if (mb.has_peer[1]) mg_st_release_sys(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_EMIG0 + 0u, round);
+    });
 }
 
 /* one warp per immigrant: append to `cur`, take a heavy slot, count the arrival */
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
+    if (mb.p2p) mg_wait_flags(mb.flags, MG_FLAG_EMIG0, 2u, mb.has_peer[0] | (mb.has_peer[1] << 1), *mb.seq, &ctl->errors);
     const uint32_t n_stay = mb.counters[MG_N_STAY];
     uint32_t base = 0;
     for (uint32_t side = 0; side < 2u; ++side) {
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) 
     for (uint32_t side = 0; side < 2u; ++side) {
         if (!mb.has_peer[side]) continue;
         const uint32_t first = side == 0u ? a.mg.own_lo : a.mg.own_hi - mb.hw;
-        unsigned char *buf = mb.halo_send[side];
+        unsigned char *buf = mb.p2p ? mb.peer_halo_recv[side] : mb.halo_send[side];
         PatchView *views = reinterpret_cast<PatchView *>(buf + 16);
         PatchBands *bands = reinterpret_cast<PatchBands *>(buf + 16 + (size_t)mb.hw * sizeof(PatchView));
         uint64_t *cults = reinterpret_cast<uint64_t *>(buf + 16 + (size_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)));
@@ -276,9 +286,16 @@ __global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) 
             bands[k] = b;
         }
     }
+    if (!mb.p2p) return;
+    mg_last_block(&mb.done[DSIM_MG_CH_HALO], [&] {
+        const uint32_t round = *mb.seq;
+        if (mb.has_peer[0]) mg_st_release_sys(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_HALO0 + 1u, round);
+        if (mb.has_peer[1]) mg_st_release_sys(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_HALO0 + 0u, round);
+    });
 }
 
 __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb) {
+    if (mb.p2p) mg_wait_flags(mb.flags, MG_FLAG_HALO0, 2u, mb.has_peer[0] | (mb.has_peer[1] << 1), *mb.seq, &a.ctl->errors);
     for (uint32_t side = 0; side < 2u; ++side) {
         if (!mb.has_peer[side]) continue;
         /* what arrives from the lower neighbour is its UPPER strip: the nodes just below mine */
@@ -298,125 +315,21 @@ __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb
     }
 }
 
-/* ---- peer-memory transport ------------------------------------------------------------------------------------
- * k_mg_push copies the USED part of a send buffer into the neighbour's receive buffer with 16-byte remote stores
- * (NVLink peer memory, mapped through CUDA IPC), then the last block to finish publishes the round number in the
- * neighbour's flag word; k_mg_wait spins on this rank's flag words until the round has arrived.
- * EMIGRANTS and HALO (neighbour channels) need no double buffering: a rank cannot start the push of round r+1 on one
- * of them before that neighbour has consumed round r (it first has to receive the neighbour's later messages of
- * round r).  SPLIT is all-to-all, and nothing orders a rank's push of round r+1 after the consumption of round r
- * (k_mg_child_rank, which runs after that rank's own k_move) on a rank three or more bands away: its receive area and
- * flag words are therefore doubled by round parity.  Round r+2 cannot be pushed before every rank has pushed round
- * r+1 (the pusher's HALO r+1 needs EMIGRANTS r+1 of its neighbour, which needs SPLIT r+1 of every rank), i.e. before
- * every rank has consumed round r. */
-#if defined(DSIM_EMU)
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
-__device__ __forceinline__ void fence_sys() {}
-__device__ __forceinline__ void backoff() {}
-#else
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
-__device__ __forceinline__ void backoff() { __nanosleep(100); }
-#endif
-
-__device__ __forceinline__ void copy16(unsigned char *dst, const unsigned char *src, uint64_t bytes) { /* bytes: a multiple of 16 */
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < bytes / 16u; k += (uint64_t)gridDim.x * blockDim.x) d[k] = s[k];
-}
-
-__global__ void __launch_bounds__(256) k_mg_push(StepArgs a, MgBuffers mb, int channel) {
-    const uint32_t round = *mb.seq;
-    if (channel == DSIM_MG_CH_SPLIT) {
-        const uint64_t words = 1u + mb.split_send[0]; /* count, ids: 8-byte words (a rank's slot is only 8-byte aligned) */
-        for (uint32_t r = 0; r < a.mg.world; ++r) {
-            uint64_t *dst = mb.peer_split_recv[r] + ((size_t)(round & 1u) * a.mg.world + a.mg.rank) * (1 + (size_t)mb.scap);
-            for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (uint64_t)gridDim.x * blockDim.x) dst[k] = mb.split_send[k];
-        }
-    } else {
-        for (uint32_t side = 0; side < 2u; ++side) {
-            if (!mb.has_peer[side]) continue;
-            if (channel == DSIM_MG_CH_EMIGRANTS) {
-                const uint64_t m = *reinterpret_cast<const uint64_t *>(mb.emig_send[side]);
-                copy16(mb.peer_emig_recv[side], mb.emig_send[side], 16u + m * mb.rec_bytes); /* rec_bytes is a multiple of 16 */
-            } else {
-                uint32_t nc = mb.counters[MG_HALO_CULT0 + side];
-                if (nc > mb.ccap) nc = mb.ccap;
-                const uint64_t bytes = (16u + (uint64_t)mb.hw * (sizeof(PatchView) + sizeof(PatchBands)) + (uint64_t)nc * 8u + 15u) & ~(uint64_t)15u;
-                copy16(mb.peer_halo_recv[side], mb.halo_send[side], bytes);
-            }
-        }
-    }
-    /* the last block to get here publishes the round in the receivers' flag words */
-    fence_sys();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(&mb.done[channel], 1u);
-        if (prev == gridDim.x - 1u) {
-            mb.done[channel] = 0u;
-            fence_sys();
-            if (channel == DSIM_MG_CH_SPLIT) {
-                for (uint32_t r = 0; r < a.mg.world; ++r)
-                    st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + a.mg.rank, round);
-            } else {
-                const uint32_t slot0 = channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0;
-                /* what I send to my lower neighbour (side 0) arrives from ITS upper side (slot 1), and vice versa */
-                if (mb.has_peer[0]) st_release_sys(mb.peer_flags[a.mg.rank - 1u] + slot0 + 1u, round);
-                if (mb.has_peer[1]) st_release_sys(mb.peer_flags[a.mg.rank + 1u] + slot0 + 0u, round);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(32) k_mg_wait(StepArgs a, MgBuffers mb, int channel) {
-    const uint32_t round = *mb.seq;
-    uint32_t slot = 0xFFFFFFFFu;
-    if (channel == DSIM_MG_CH_SPLIT) {
-        if (threadIdx.x < a.mg.world) slot = MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + threadIdx.x;
-    } else if (threadIdx.x < 2u && mb.has_peer[threadIdx.x]) {
-        slot = (channel == DSIM_MG_CH_EMIGRANTS ? MG_FLAG_EMIG0 : MG_FLAG_HALO0) + threadIdx.x;
-    }
-    if (slot != 0xFFFFFFFFu) {
-        uint32_t spins = 0;
-        /* rounds only grow; a neighbour that is a step ahead may already have published the next one on a neighbour
-         * channel (a SPLIT slot of this parity next sees round + 2, which nobody can publish before this round is consumed) */
-        while ((int32_t)(ld_acquire_sys(mb.flags + slot) - round) < 0) {
-            backoff();
-            if (++spins > (1u << 25)) { /* several seconds: the neighbour is gone; flag it instead of hanging the device */
-                atomicOr(&a.ctl->errors, (uint32_t)DSIM_MODEL_COMM_TIMEOUT);
-                break;
-            }
-        }
-    }
-    fence_sys();
-}
-
 /* ---- end of step ------------------------------------------------------------------------------ */
-__global__ void k_mg_finish(StepArgs a, MgBuffers mb) {
+/* one block: heavy-slot allocator (children and immigrants popped, the dead and the emigrants pushed), t += 1 */
+__global__ void __launch_bounds__(256) k_mg_finish(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    /* heavy-slot allocator: children and immigrants popped, the dead and the emigrants are pushed */
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
     const uint32_t dead = ctl->n_dead, freed = mb.counters[MG_N_FREED];
     const uint32_t popped = pops < ft ? pops : ft;
     const uint32_t base = ft - popped;
     for (uint32_t k = tid; k < dead; k += nth) a.sc.free_hs[base + k] = a.sc.dead_hs[k];
     for (uint32_t k = tid; k < freed; k += nth) a.sc.free_hs[base + dead + k] = mb.emig_hs[k];
-}
-
-__global__ void k_mg_finish2(StepArgs a, MgBuffers mb) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    DevCtl *ctl = a.ctl;
-    const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
-    const uint32_t popped = pops < ft ? pops : ft;
+    __syncthreads();
+    if (tid != 0) return;
     ctl->hs_hwm += pops - popped;
-    ctl->free_top = ft - popped + ctl->n_dead + mb.counters[MG_N_FREED];
+    ctl->free_top = ft - popped + dead + freed;
     if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
     mb.counters[MG_N_FREED] = 0;
     ctl->n_cur[a.parity] = ctl->n_next; /* part 2 ran in place on `cur`: the buffers do not swap */
@@ -434,20 +347,12 @@ void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const Lau
     const uint32_t sm = g.n_sm;
     switch (which) {
     case DSIM_MGK_SPLIT_IDS: DSIM_LAUNCH(k_mg_split_ids, sm * 4, 256, 0, s, a, mb); break;
-    case DSIM_MGK_CHILD_RANK: DSIM_LAUNCH(k_mg_child_rank, sm * 2, 256, 0, s, a, mb); break;
     case DSIM_MGK_SORT_OUT: DSIM_LAUNCH(k_mg_sort_out, sm * 8, 256, 0, s, a, mb); break;
     case DSIM_MGK_PACK: DSIM_LAUNCH(k_mg_pack, sm * 4, 128, 0, s, a, mb); break;
     case DSIM_MGK_UNPACK: DSIM_LAUNCH(k_mg_unpack, sm * 4, 128, 0, s, a, mb); break;
     case DSIM_MGK_HALO_PACK: DSIM_LAUNCH(k_mg_halo_pack, sm * 2, 256, 0, s, a, mb); break;
     case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm * 2, 256, 0, s, a, mb); break;
-    case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, sm, 256, 0, s, a, mb); break;
-    case DSIM_MGK_FINISH2: DSIM_LAUNCH(k_mg_finish2, 1, 32, 0, s, a, mb); break;
-    case DSIM_MGK_PUSH_SPLIT: DSIM_LAUNCH(k_mg_push, 8, 256, 0, s, a, mb, (int)DSIM_MG_CH_SPLIT); break;
-    case DSIM_MGK_PUSH_EMIG: DSIM_LAUNCH(k_mg_push, sm, 256, 0, s, a, mb, (int)DSIM_MG_CH_EMIGRANTS); break;
-    case DSIM_MGK_PUSH_HALO: DSIM_LAUNCH(k_mg_push, 32, 256, 0, s, a, mb, (int)DSIM_MG_CH_HALO); break;
-    case DSIM_MGK_WAIT_SPLIT: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_SPLIT); break;
-    case DSIM_MGK_WAIT_EMIG: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_EMIGRANTS); break;
-    case DSIM_MGK_WAIT_HALO: DSIM_LAUNCH(k_mg_wait, 1, 32, 0, s, a, mb, (int)DSIM_MG_CH_HALO); break;
+    case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, 1, 256, 0, s, a, mb); break;
     case DSIM_MGK_BUMP: DSIM_LAUNCH(k_mg_bump, 1, 32, 0, s, a, mb); break;
     default: break;
     }

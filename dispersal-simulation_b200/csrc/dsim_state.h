@@ -203,7 +203,13 @@ struct ModelConst {          /* parameters.rs:5-20 and derived constants, passed
 struct MgInfo {              /* part of StepArgs */
     uint32_t enabled, rank, world;
     uint32_t own_lo, own_hi; /* this rank owns the nodes [own_lo, own_hi) and the families located there */
-    const uint32_t *child_grank;  /* [scap] rank of local child c among all children of the step, all ranks */
+    /* what k_children needs to give its children their global ids: the ids of all families that split this step */
+    const uint64_t *split_send;   /* [1 + scap] this rank's list (count, ids in local child order)                 */
+    const uint64_t *split_recv;   /* [2][world][1 + scap] the lists of all ranks (second area: odd rounds, peer memory) */
+    uint32_t scap, p2p;
+    const uint32_t *seq;          /* peer-memory transport: the exchange round                                     */
+    const uint32_t *flags;        /* ... and this rank's flag words                                                */
+    uint32_t *counters;           /* MG_* counters, reset for the step by k_children                                */
     const uint64_t *halo_cult[2]; /* band cultures of the halo views received from the lower / upper neighbour */
 };
 
@@ -223,7 +229,6 @@ DSIM_HD_INLINE uint32_t mg_rec_bytes(uint32_t acap, uint32_t hcap) {
 struct MgBuffers {           /* device buffers of one rank; messages have a 16-byte header (count) */
     uint64_t *split_send;    /* [1 + scap]: count, ids of the local families that split this step       */
     uint64_t *split_recv;    /* [2][world][1 + scap]: the second area takes the odd rounds of the peer-memory transport */
-    uint32_t *child_grank;   /* [scap]                                                                 */
     uint32_t *counters;      /* [MG_N_COUNTERS]                                                        */
     uint32_t *emig_list;     /* [2][ecap] positions (in `next`) of the emigrants per side              */
     uint32_t *emig_hs;       /* [2 * ecap] heavy slots given up by emigrants this step                 */
