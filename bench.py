@@ -424,6 +424,11 @@ def main():
         lib.dsim_mg_segment_times(sim.h, seg)
         mg_segments = dict(zip(["lifecycle", "split_exchange", "move", "emigrant_exchange", "patch", "halo_exchange", "finish"],
                                [round(x, 4) for x in seg]))
+        kt = (C.c_double * 12)()
+        lib.dsim_mg_kernel_times(sim.h, kt)
+        mg_kernels = dict(zip(["k_mg_split_ids", "k_mg_sort_out", "k_mg_pack", "k_mg_unpack", "k_mg_halo_pack", "k_mg_halo_unpack",
+                               "k_mg_finish", "k_lifecycle", "k_move", "k_children", "k_segments", "k_scatter"], [round(1e3 * x, 1) for x in kt]))
+        mg_segments["kernels_us"] = mg_kernels
         log(f"[bench] rank {rank}: multi-GPU step segments (ms): {mg_segments}")
     if args.profile_steps > 0 and world == 1:
         sim.profile_enable(True)

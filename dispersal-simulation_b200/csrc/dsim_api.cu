@@ -1702,6 +1702,11 @@ struct dsim_mg_state {
     double seg_ms[7] = {};
     uint64_t seg_steps = 0;
     uint64_t launches_per_step = 0;
+    /* per-kernel device times while profiling: event pairs around every launch of mg_launch_phase, read at step end */
+    std::vector<cudaEvent_t> kev;
+    std::vector<int> kev_id; /* >= 0: DSIM_K_*, < 0: -1 - DSIM_MGK_* */
+    size_t kev_used = 0;
+    double mgk_ms[DSIM_MGK_BUMP + 1] = {};
 };
 
 namespace {
@@ -1851,13 +1856,28 @@ enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_FINISH_HALO, MG_PHASE_FI
 static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
     const MgBuffers &mb = m->mb;
+    auto mark = [&](int id) { /* profiling: an event before and after the launch */
+        if (!h->profiling) return;
+        if (m->kev_used == m->kev.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            m->kev.push_back(e);
+            m->kev_id.push_back(0);
+        }
+        m->kev_id[m->kev_used] = id;
+        cudaEventRecord(m->kev[m->kev_used++], h->stream);
+    };
     auto K = [&](int k, const StepArgs &a) {
+        mark(k);
         dsim_launch_kernel(k, a, h->geom, h->stream);
+        mark(k);
         h->k_launches[k] += 1;
         h->total_launches += 1;
     };
     auto M = [&](int k, const StepArgs &a) {
+        mark(-1 - k);
         dsim_mg_launch(k, a, mb, h->geom, h->stream);
+        mark(-1 - k);
         h->total_launches += 1;
     };
     switch (phase) {
@@ -2136,6 +2156,16 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
             CK(cudaEventElapsedTime(&ms, m->seg_ev[k], m->seg_ev[k + 1]));
             m->seg_ms[k] += ms;
         }
+        for (size_t k = 0; k + 1 < m->kev_used; k += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, m->kev[k], m->kev[k + 1]) != cudaSuccess) continue;
+            const int id = m->kev_id[k];
+            if (id >= 0)
+                h->k_ms[id] += ms;
+            else
+                m->mgk_ms[-1 - id] += ms;
+        }
+        m->kev_used = 0;
         m->seg_steps += 1;
     } else if ((rc = mg_enqueue_step(h, m))) {
         return rc;
@@ -2152,6 +2182,19 @@ int dsim_mg_segment_times(dsim_handle *h, double *out7) {
     dsim_mg_state *m = h ? mg_of(h) : nullptr;
     if (!m || !out7) return DSIM_ERR_INVALID;
     for (int k = 0; k < 7; ++k) out7[k] = m->seg_steps ? m->seg_ms[k] / (double)m->seg_steps : 0.0;
+    return DSIM_OK;
+}
+
+/* diagnostics: mean device milliseconds per launch of the multi-GPU kernels measured while profiling was on, in the order
+ * k_mg_split_ids, k_mg_sort_out, k_mg_pack, k_mg_unpack, k_mg_halo_pack, k_mg_halo_unpack, k_mg_finish; then the step
+ * kernels k_lifecycle, k_move, k_children, k_segments, k_scatter (the patch kernels run concurrently and are not timed
+ * one by one) */
+int dsim_mg_kernel_times(dsim_handle *h, double *out12) {
+    dsim_mg_state *m = h ? mg_of(h) : nullptr;
+    if (!m || !out12) return DSIM_ERR_INVALID;
+    const double inv = m->seg_steps ? 1.0 / (double)m->seg_steps : 0.0;
+    for (int k = 0; k < 7; ++k) out12[k] = m->mgk_ms[k] * inv;
+    for (int k = 0; k < 5; ++k) out12[7 + k] = h->k_ms[k] * inv;
     return DSIM_OK;
 }
 
@@ -2221,6 +2264,7 @@ void dsim_mg_release(dsim_handle *h) {
     for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto &e : m->seg_ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : m->kev) cudaEventDestroy(e);
 #endif
     free_list(m->allocs);
     g_mg.erase(h);

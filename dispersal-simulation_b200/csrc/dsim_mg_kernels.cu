@@ -19,8 +19,8 @@
 
 /* The last block of a packing kernel to finish publishes the message: `publish` runs in one thread after every block's
  * stores have been fenced at system scope. */
-template <typename F> __device__ __forceinline__ void mg_last_block(uint32_t *ticket, F publish) {
-    mg_fence_sys();
+template <typename F> __device__ __forceinline__ void mg_last_block(uint32_t *ticket, bool wrote, F publish) {
+    if (wrote) mg_fence_sys(); /* system-scope fences are expensive: only the threads that stored part of the message */
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t prev = atomicAdd(ticket, 1u);
@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
     const uint32_t round = mb.p2p ? *mb.seq + 1u : 0u; /* read before any block can have taken the last ticket */
     const size_t stride = 1 + (size_t)mb.scap;
     const size_t slot = ((size_t)(round & 1u) * a.mg.world + a.mg.rank) * stride;
+    bool wrote = false;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t c = i >> 5, lt = (1u << (i & 31u)) - 1u;
         const uint32_t split_mask = a.sc.split_bits[c];
@@ -57,22 +58,26 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         if (crank < mb.scap) {
             const uint64_t id = a.cur.key[i].id;
             mb.split_send[1 + crank] = id;
-            if (mb.p2p)
+            if (mb.p2p) {
                 for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot + 1 + crank] = id;
+                wrote = true;
+            }
         } else {
             atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         mb.split_send[0] = ctl->n_children;
-        if (mb.p2p)
+        if (mb.p2p) {
             for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot] = ctl->n_children;
+            wrote = true;
+        }
     }
     if (!mb.p2p) return;
-    mg_last_block(&mb.done[DSIM_MG_CH_SPLIT], [&] {
+    mg_last_block(&mb.done[DSIM_MG_CH_SPLIT], wrote, [&] {
         *mb.seq = round; /* the exchange round of this step */
         for (uint32_t r = 0; r < a.mg.world; ++r)
-            mg_st_release_sys(mb.peer_flags[r] + MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + a.mg.rank, round);
+            mg_st_flag(mb.peer_flags[r] + MG_FLAG_SPLIT0 + (round & 1u) * DSIM_MG_MAX_WORLD + a.mg.rank, round);
     });
 }
 
@@ -116,140 +121,183 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
  * peer-memory transport straight into the neighbour's receive buffer (remote stores over NVLink: the transfer overlaps
  * the packing record by record), published by the last block to finish */
 __global__ void __launch_bounds__(128) k_mg_pack(StepArgs a, MgBuffers mb) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    /* a BLOCK per emigrant: its 7.8 KB (628-entry history ring) are read with every load of a pass in flight before the
+     * first store — a warp per emigrant walked the ring in 20 dependent load -> remote store steps (41 us per launch) */
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
-    for (uint32_t side = 0; side < 2u; ++side) {
-        uint32_t m = mb.counters[MG_N_EMIG0 + side];
-        if (m > mb.ecap) m = mb.ecap;
-        unsigned char *buf = (mb.p2p && mb.has_peer[side]) ? mb.peer_emig_recv[side] : mb.emig_send[side];
-        if (gw == 0 && lane == 0) {
-            *reinterpret_cast<uint64_t *>(buf) = m;
-            atomicMax(&mb.counters[MG_MAX_EMIG], mb.counters[MG_N_EMIG0 + side]);
+    uint32_t m0 = mb.counters[MG_N_EMIG0], m1 = mb.counters[MG_N_EMIG1];
+    if (blockIdx.x == 0 && tid == 0) atomicMax(&mb.counters[MG_MAX_EMIG], m0 > m1 ? m0 : m1);
+    if (m0 > mb.ecap) m0 = mb.ecap;
+    if (m1 > mb.ecap) m1 = mb.ecap;
+    unsigned char *const bufs[2] = {(mb.p2p && mb.has_peer[0]) ? mb.peer_emig_recv[0] : mb.emig_send[0],
+                                    (mb.p2p && mb.has_peer[1]) ? mb.peer_emig_recv[1] : mb.emig_send[1]};
+    bool wrote = false;
+    if (blockIdx.x == 0 && tid < 2u) {
+        *reinterpret_cast<uint64_t *>(bufs[tid]) = tid == 0u ? m0 : m1;
+        wrote = true;
+    }
+    for (uint32_t eg = blockIdx.x; eg < m0 + m1; eg += gridDim.x) {
+        const uint32_t side = eg < m0 ? 0u : 1u, e = eg - (side ? m0 : 0u);
+        unsigned char *buf = bufs[side];
+        wrote = true;
+        const uint32_t j = mb.emig_list[side * mb.ecap + e];
+        const FamPlace pl = a.next.place[j];
+        const uint32_t hs = pl.hs;
+        unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
+        const uint32_t cnt = a.hv.hist_cnt[hs];
+        const uint32_t valid = cnt < hcap ? cnt : hcap;
+        if (tid == 0) {
+            uint64_t *q = reinterpret_cast<uint64_t *>(rec);
+            const FamKey ky = a.next.key[j];
+            const FamStock sk = a.next.stock[j];
+            const FamClock ck = a.next.clock[j];
+            q[0] = ky.id;
+            q[1] = ky.culture;
+            q[2] = dsim_f64_to_bits(sk.stored);
+            q[3] = dsim_f64_to_bits(sk.last_harvest);
+            q[4] = a.hv.parent[hs];
+            uint32_t *w = reinterpret_cast<uint32_t *>(rec + 40);
+            w[0] = pl.loc;
+            w[1] = pl.size;
+            w[2] = ck.till_adult;
+            w[3] = ck.till_mut;
+            w[4] = pl.misc;
+            w[5] = valid;
+            w[6] = a.hv.decay[hs];
+            w[7] = a.hv.birth_index[hs];
+            /* the emigrant's heavy slot is free again: listed behind the slots of the dead */
+            mb.emig_hs[atomicAdd(&mb.counters[MG_N_FREED], 1u)] = hs;
         }
-        for (uint32_t e = gw; e < m; e += nw) {
-            const uint32_t j = mb.emig_list[side * mb.ecap + e];
-            const FamPlace pl = a.next.place[j];
-            const uint32_t hs = pl.hs;
-            unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
-            const uint32_t cnt = a.hv.hist_cnt[hs];
-            const uint32_t valid = cnt < hcap ? cnt : hcap;
-            if (lane == 0) {
-                uint64_t *q = reinterpret_cast<uint64_t *>(rec);
-                const FamKey ky = a.next.key[j];
-                const FamStock sk = a.next.stock[j];
-                const FamClock ck = a.next.clock[j];
-                q[0] = ky.id;
-                q[1] = ky.culture;
-                q[2] = dsim_f64_to_bits(sk.stored);
-                q[3] = dsim_f64_to_bits(sk.last_harvest);
-                q[4] = a.hv.parent[hs];
-                uint32_t *w = reinterpret_cast<uint32_t *>(rec + 40);
-                w[0] = pl.loc;
-                w[1] = pl.size;
-                w[2] = ck.till_adult;
-                w[3] = ck.till_mut;
-                w[4] = pl.misc;
-                w[5] = valid;
-                w[6] = a.hv.decay[hs];
-                w[7] = a.hv.birth_index[hs];
-                /* the emigrant's heavy slot is free again: listed behind the slots of the dead */
-                mb.emig_hs[atomicAdd(&mb.counters[MG_N_FREED], 1u)] = hs;
+        uint16_t *r_eco = reinterpret_cast<uint16_t *>(rec + MG_REC_HDR);
+        uint32_t *r_cnt = reinterpret_cast<uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
+        double *r_val = reinterpret_cast<double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
+        for (uint32_t k = tid; k < acap; k += nt) {
+            r_eco[k] = a.hv.a_eco[(size_t)hs * acap + k];
+            r_cnt[k] = a.hv.a_cnt[(size_t)hs * acap + k];
+            r_val[k] = a.hv.a_val[(size_t)hs * acap + k];
+        }
+        unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
+        uint32_t *r_hp = reinterpret_cast<uint32_t *>(hist);
+        double *r_hh = reinterpret_cast<double *>(hist + mg_pad8(hcap * 4u));
+        const size_t hb = (size_t)hs * hcap;
+        const uint32_t oldest = cnt - valid; /* chronological entry k sits at ring position (oldest + k) % hcap */
+        for (uint32_t k0 = tid; k0 < valid; k0 += 4u * nt) {
+            uint32_t hp[4];
+            double hh[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t k = k0 + u * nt;
+                hp[u] = 0u;
+                hh[u] = 0.0;
+                if (k < valid) {
+                    const uint32_t pos = (oldest + k) % hcap;
+                    hp[u] = a.hv.hist_patch[hb + pos];
+                    hh[u] = a.hv.hist_harv[hb + pos];
+                }
             }
-            uint16_t *r_eco = reinterpret_cast<uint16_t *>(rec + MG_REC_HDR);
-            uint32_t *r_cnt = reinterpret_cast<uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
-            double *r_val = reinterpret_cast<double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
-            for (uint32_t k = lane; k < acap; k += 32u) {
-                r_eco[k] = a.hv.a_eco[(size_t)hs * acap + k];
-                r_cnt[k] = a.hv.a_cnt[(size_t)hs * acap + k];
-                r_val[k] = a.hv.a_val[(size_t)hs * acap + k];
-            }
-            unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
-            uint32_t *r_hp = reinterpret_cast<uint32_t *>(hist);
-            double *r_hh = reinterpret_cast<double *>(hist + mg_pad8(hcap * 4u));
-            for (uint32_t k = lane; k < valid; k += 32u) { /* chronological k = newest-first valid-1-k */
-                const uint32_t pos = (cnt - 1u - (valid - 1u - k)) % hcap;
-                r_hp[k] = a.hv.hist_patch[(size_t)hs * hcap + pos];
-                r_hh[k] = a.hv.hist_harv[(size_t)hs * hcap + pos];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t k = k0 + u * nt;
+                if (k < valid) {
+                    r_hp[k] = hp[u];
+                    r_hh[k] = hh[u];
+                }
             }
         }
     }
     if (!mb.p2p) return;
-    mg_last_block(&mb.done[DSIM_MG_CH_EMIGRANTS], [&] {
+    mg_last_block(&mb.done[DSIM_MG_CH_EMIGRANTS], wrote, [&] {
         const uint32_t round = *mb.seq;
         /* what I send to my lower neighbour (side 0) arrives from ITS upper side (slot 1), and vice versa */
-        if (mb.has_peer[0]) mg_st_release_sys(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_EMIG0 + 1u, round);
-        if (mb.has_peer[1]) mg_st_release_sys(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_EMIG0 + 0u, round);
+        if (mb.has_peer[0]) mg_st_flag(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_EMIG0 + 1u, round);
+        if (mb.has_peer[1]) mg_st_flag(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_EMIG0 + 0u, round);
     });
 }
 
 /* one warp per immigrant: append to `cur`, take a heavy slot, count the arrival */
 __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
     DevCtl *ctl = a.ctl;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t gw = blockIdx.x, lane = tid; /* a block per immigrant; (gw, lane) == (0, 0) does the bookkeeping below */
     const uint32_t hcap = a.hv.hcap, acap = a.hv.acap;
     if (mb.p2p) mg_wait_flags(mb.flags, MG_FLAG_EMIG0, 2u, mb.has_peer[0] | (mb.has_peer[1] << 1), *mb.seq, &ctl->errors);
     const uint32_t n_stay = mb.counters[MG_N_STAY];
-    uint32_t base = 0;
-    for (uint32_t side = 0; side < 2u; ++side) {
-        const unsigned char *buf = mb.emig_recv[side];
-        const uint32_t m = mb.has_peer[side] ? (uint32_t)*reinterpret_cast<const uint64_t *>(buf) : 0u;
-        for (uint32_t e = gw; e < m; e += nw) {
-            const unsigned char *rec = buf + 16 + (size_t)e * mb.rec_bytes;
-            const uint32_t p = n_stay + base + e;
-            /* heavy slots: the children popped the first n_children, the immigrants continue */
-            const uint32_t pop = ctl->n_children + base + e, ft = ctl->free_top;
-            const uint32_t hs = (pop < ft) ? a.sc.free_hs[ft - 1u - pop] : ctl->hs_hwm + (pop - ft);
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(rec + 40);
-            const uint32_t loc = w[0], valid = w[5];
-            if (p >= ctl->cap || hs >= ctl->hs_cap || loc < a.mg.own_lo || loc >= a.mg.own_hi) {
-                if (lane == 0) atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
-                continue;
+    const uint32_t m0 = mb.has_peer[0] ? (uint32_t)*reinterpret_cast<const uint64_t *>(mb.emig_recv[0]) : 0u;
+    const uint32_t m1 = mb.has_peer[1] ? (uint32_t)*reinterpret_cast<const uint64_t *>(mb.emig_recv[1]) : 0u;
+    const uint32_t base = m0 + m1;
+    for (uint32_t eg = blockIdx.x; eg < base; eg += gridDim.x) {
+        const uint32_t side = eg < m0 ? 0u : 1u, e = eg - (side ? m0 : 0u);
+        const unsigned char *rec = mb.emig_recv[side] + 16 + (size_t)e * mb.rec_bytes;
+        const uint32_t p = n_stay + eg;
+        /* heavy slots: the children popped the first n_children, the immigrants continue */
+        const uint32_t pop = ctl->n_children + eg, ft = ctl->free_top;
+        const uint32_t hs = (pop < ft) ? a.sc.free_hs[ft - 1u - pop] : ctl->hs_hwm + (pop - ft);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(rec + 40);
+        const uint32_t loc = w[0], valid = w[5];
+        if (p >= ctl->cap || hs >= ctl->hs_cap || loc < a.mg.own_lo || loc >= a.mg.own_hi) {
+            if (tid == 0) atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+            continue;
+        }
+        const uint16_t *r_eco = reinterpret_cast<const uint16_t *>(rec + MG_REC_HDR);
+        const uint32_t *r_cnt = reinterpret_cast<const uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
+        const double *r_val = reinterpret_cast<const double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
+        for (uint32_t k = tid; k < acap; k += nt) {
+            a.hv.a_eco[(size_t)hs * acap + k] = r_eco[k];
+            a.hv.a_cnt[(size_t)hs * acap + k] = r_cnt[k];
+            a.hv.a_val[(size_t)hs * acap + k] = r_val[k];
+        }
+        const unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
+        const uint32_t *r_hp = reinterpret_cast<const uint32_t *>(hist);
+        const double *r_hh = reinterpret_cast<const double *>(hist + mg_pad8(hcap * 4u));
+        const size_t hb = (size_t)hs * hcap;
+        for (uint32_t k0 = tid; k0 < valid; k0 += 4u * nt) { /* every load of a pass in flight before the first store */
+            uint32_t hp[4];
+            double hh[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t k = k0 + u * nt;
+                hp[u] = 0u;
+                hh[u] = 0.0;
+                if (k < valid) {
+                    hp[u] = r_hp[k];
+                    hh[u] = r_hh[k];
+                }
             }
-            const uint16_t *r_eco = reinterpret_cast<const uint16_t *>(rec + MG_REC_HDR);
-            const uint32_t *r_cnt = reinterpret_cast<const uint32_t *>(rec + MG_REC_HDR + mg_pad8(acap * 2u));
-            const double *r_val = reinterpret_cast<const double *>(rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u));
-            for (uint32_t k = lane; k < acap; k += 32u) {
-                a.hv.a_eco[(size_t)hs * acap + k] = r_eco[k];
-                a.hv.a_cnt[(size_t)hs * acap + k] = r_cnt[k];
-                a.hv.a_val[(size_t)hs * acap + k] = r_val[k];
-            }
-            const unsigned char *hist = rec + MG_REC_HDR + mg_pad8(acap * 2u) + mg_pad8(acap * 4u) + acap * 8u;
-            const uint32_t *r_hp = reinterpret_cast<const uint32_t *>(hist);
-            const double *r_hh = reinterpret_cast<const double *>(hist + mg_pad8(hcap * 4u));
-            for (uint32_t k = lane; k < valid; k += 32u) {
-                a.hv.hist_patch[(size_t)hs * hcap + k] = r_hp[k];
-                a.hv.hist_harv[(size_t)hs * hcap + k] = r_hh[k];
-            }
-            if (lane == 0) {
-                const uint64_t *q = reinterpret_cast<const uint64_t *>(rec);
-                FamKey ky;
-                ky.id = q[0];
-                ky.culture = q[1];
-                FamStock sk;
-                sk.stored = dsim_bits_to_f64(q[2]);
-                sk.last_harvest = dsim_bits_to_f64(q[3]);
-                FamPlace pl;
-                pl.loc = loc;
-                pl.size = w[1];
-                pl.hs = hs;
-                pl.misc = w[4];
-                FamClock ck;
-                ck.till_adult = w[2];
-                ck.till_mut = w[3];
-                a.cur.key[p] = ky;
-                a.cur.stock[p] = sk;
-                a.cur.place[p] = pl;
-                a.cur.clock[p] = ck;
-                a.hv.parent[hs] = q[4];
-                a.hv.hist_cnt[hs] = valid;
-                a.hv.decay[hs] = w[6];
-                a.hv.birth_index[hs] = (uint16_t)w[7];
-                mb.fslot2[p] = atomicAdd(&a.ps.cnt[loc], 1u); /* rank 0 = first arrival: k_segments lists the node */
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t k = k0 + u * nt;
+                if (k < valid) {
+                    a.hv.hist_patch[hb + k] = hp[u];
+                    a.hv.hist_harv[hb + k] = hh[u];
+                }
             }
         }
-        base += m;
+        if (tid == 0) {
+            const uint64_t *q = reinterpret_cast<const uint64_t *>(rec);
+            FamKey ky;
+            ky.id = q[0];
+            ky.culture = q[1];
+            FamStock sk;
+            sk.stored = dsim_bits_to_f64(q[2]);
+            sk.last_harvest = dsim_bits_to_f64(q[3]);
+            FamPlace pl;
+            pl.loc = loc;
+            pl.size = w[1];
+            pl.hs = hs;
+            pl.misc = w[4];
+            FamClock ck;
+            ck.till_adult = w[2];
+            ck.till_mut = w[3];
+            a.cur.key[p] = ky;
+            a.cur.stock[p] = sk;
+            a.cur.place[p] = pl;
+            a.cur.clock[p] = ck;
+            a.hv.parent[hs] = q[4];
+            a.hv.hist_cnt[hs] = valid;
+            a.hv.decay[hs] = w[6];
+            a.hv.birth_index[hs] = (uint16_t)w[7];
+            mb.fslot2[p] = atomicAdd(&a.ps.cnt[loc], 1u); /* rank 0 = first arrival: k_segments lists the node */
+        }
     }
     if (gw == 0 && lane == 0) { /* the families of part 2 */
         ctl->n_next = n_stay + base;
@@ -287,10 +335,10 @@ __global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) 
         }
     }
     if (!mb.p2p) return;
-    mg_last_block(&mb.done[DSIM_MG_CH_HALO], [&] {
+    mg_last_block(&mb.done[DSIM_MG_CH_HALO], true, [&] {
         const uint32_t round = *mb.seq;
-        if (mb.has_peer[0]) mg_st_release_sys(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_HALO0 + 1u, round);
-        if (mb.has_peer[1]) mg_st_release_sys(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_HALO0 + 0u, round);
+        if (mb.has_peer[0]) mg_st_flag(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_HALO0 + 1u, round);
+        if (mb.has_peer[1]) mg_st_flag(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_HALO0 + 0u, round);
     });
 }
 
@@ -346,12 +394,12 @@ __global__ void k_mg_bump(StepArgs a, MgBuffers mb) {
 void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const LaunchGeom &g, cudaStream_t s) {
     const uint32_t sm = g.n_sm;
     switch (which) {
-    case DSIM_MGK_SPLIT_IDS: DSIM_LAUNCH(k_mg_split_ids, sm * 4, 256, 0, s, a, mb); break;
+    case DSIM_MGK_SPLIT_IDS: DSIM_LAUNCH(k_mg_split_ids, sm, 256, 0, s, a, mb); break;
     case DSIM_MGK_SORT_OUT: DSIM_LAUNCH(k_mg_sort_out, sm * 8, 256, 0, s, a, mb); break;
     case DSIM_MGK_PACK: DSIM_LAUNCH(k_mg_pack, sm * 4, 128, 0, s, a, mb); break;
     case DSIM_MGK_UNPACK: DSIM_LAUNCH(k_mg_unpack, sm * 4, 128, 0, s, a, mb); break;
-    case DSIM_MGK_HALO_PACK: DSIM_LAUNCH(k_mg_halo_pack, sm * 2, 256, 0, s, a, mb); break;
-    case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm * 2, 256, 0, s, a, mb); break;
+    case DSIM_MGK_HALO_PACK: DSIM_LAUNCH(k_mg_halo_pack, sm, 128, 0, s, a, mb); break;
+    case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm, 128, 0, s, a, mb); break;
     case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, 1, 256, 0, s, a, mb); break;
     case DSIM_MGK_BUMP: DSIM_LAUNCH(k_mg_bump, 1, 32, 0, s, a, mb); break;
     default: break;

@@ -3,7 +3,7 @@
  *
  * A message is written with plain remote stores into the receiver's buffer (NVLink peer memory mapped through CUDA IPC);
  * the LAST block of the writing kernel to finish then publishes the exchange round in the receiver's flag word
- * (st.release.sys after a system-scope fence); the consuming kernel starts by spinning on its own flag words
+ * (relaxed system-scope store after a system-scope fence); the consuming kernel starts by spinning on its own flag words
  * (ld.acquire.sys, bounded).  In the CPU debugging build of the test-suite these are plain accesses.
  */
 #ifndef DSIM_MG_SYNC_H
@@ -12,12 +12,15 @@
 #include "dsim_kernels.h"
 
 #if defined(DSIM_EMU)
-static inline void mg_st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
+static inline void mg_st_flag(uint32_t *p, uint32_t v) { *p = v; }
 static inline uint32_t mg_ld_acquire_sys(const uint32_t *p) { return *p; }
 static inline void mg_fence_sys() {}
 static inline void mg_backoff() {}
 #else
-__device__ __forceinline__ void mg_st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+/* a flag word is stored relaxed at system scope AFTER one system-scope fence of the publishing thread (mg_last_block):
+ * fence + relaxed store is the release pattern, and several flag words (both neighbours, or every rank for SPLIT) then
+ * cost one fence — a st.release.sys each would wait for the peer's acknowledgement once per flag */
+__device__ __forceinline__ void mg_st_flag(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t mg_ld_acquire_sys(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -42,8 +45,7 @@ __device__ __forceinline__ void mg_wait_flags(const uint32_t *flags, uint32_t sl
             }
         }
     }
-    mg_fence_sys();
-    __syncthreads();
+    __syncthreads(); /* the acquire of the waiting threads orders the whole block's later reads behind the message */
 }
 
 #endif

@@ -255,6 +255,8 @@ int dsim_mg_reduce_stats(dsim_handle *h, dsim_step_stats *stats);
 /* Diagnostics: internal per-step counters; out8[7] = most emigrants per neighbour and step seen so far. */
 int dsim_mg_debug_counters(dsim_handle *h, uint32_t *out8);
 int dsim_mg_segment_times(dsim_handle *h, double *out7); /* mean ms of lifecycle, SPLIT, move, EMIGRANTS, patch, HALO, finish while profiling */
+int dsim_mg_kernel_times(dsim_handle *h, double *out12); /* mean ms per launch while profiling: split_ids, sort_out, pack, unpack,
+                                                           * halo_pack, halo_unpack, finish, lifecycle, move, children, segments, scatter */
 int dsim_mg_halo_sync(dsim_handle *h); /* built-in transports: initial halo exchange after the state was set on every rank */
 
 /* Kernel-level timing for bench.py: device time in ms of each kernel class accumulated since the
