@@ -1729,6 +1729,8 @@ StepArgs mg_args(dsim_handle *h, bool part2) {
     a.mg.seq = m->mb.seq;
     a.mg.flags = m->mb.flags;
     a.mg.counters = m->mb.counters;
+    a.mg.emig_list = m->mb.emig_list;
+    a.mg.ecap = m->mb.ecap;
     a.mg.halo_cult[0] = m->mb.halo_cult[0];
     a.mg.halo_cult[1] = m->mb.halo_cult[1];
     if (part2) { /* part 2 runs in place on the re-packed buffer */
@@ -1851,7 +1853,7 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes) {
     return DSIM_OK;
 }
 
-enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
+enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_MOVE_FORKED, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
 
 static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
@@ -1889,6 +1891,16 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         break;
     case MG_PHASE_MOVE_A: K(DSIM_K_MOVE, a1); break;
     case MG_PHASE_MOVE_B: K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1); break;
+    case MG_PHASE_MOVE_FORKED: /* k_mg_sort_out (re-packs the stayers) on the second stream next to k_mg_pack (sends the emigrants) */
+        K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1);
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        dsim_mg_launch(DSIM_MGK_SORT_OUT, a1, mb, h->geom, h->stream2);
+        h->total_launches += 1;
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        M(DSIM_MGK_PACK, a1);
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        break;
     case MG_PHASE_FINISH_HALO: /* on the second stream, next to MG_PHASE_FINISH_BOOK */
         dsim_mg_launch(DSIM_MGK_HALO_UNPACK, a2, mb, h->geom, h->stream2);
         h->total_launches += 1;
@@ -2072,7 +2084,7 @@ static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
     int rc;
     if (m->p2p) { /* peer memory: the messages travel inside the packing kernels; 18 launches, 14 of them in sequence */
         if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
-        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_MOVE))) return rc;
+        if ((rc = mg_launch_phase(h, m, MG_PHASE_MOVE_FORKED))) return rc;
         if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
         CK(cudaEventRecord(h->fork_ev, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));

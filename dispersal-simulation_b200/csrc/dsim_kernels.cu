@@ -466,6 +466,16 @@ __device__ __forceinline__ void accept_scan_warp(Choice &ch, bool valid, double 
     }
 }
 
+/* several GPUs: a family whose new node belongs to a neighbour's band is listed for k_mg_pack right where it is written */
+__device__ __forceinline__ void mg_list_emigrant(const StepArgs &a, uint32_t pos, uint32_t newloc) {
+    const uint32_t side = newloc < a.mg.own_lo ? 0u : 1u;
+    const uint32_t e = atomicAdd(&a.mg.counters[MG_N_EMIG0 + side], 1u);
+    if (e < a.mg.ecap)
+        a.mg.emig_list[side * a.mg.ecap + e] = pos;
+    else
+        atomicOr(&a.ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
+}
+
 /* ------------------------------------------------------------------------------------------ *
  * part 1c: move, one WARP per tile of MOVE_WF families, work items spread over the lanes.
  *
@@ -1045,6 +1055,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 pend_pos = newpos;
             } else {
                 a.sc.fslot[newpos] = 0xFFFFFFFFu; /* emigrant: counted where it arrives (k_mg_unpack) */
+                mg_list_emigrant(a, newpos, newloc);
             }
         }
         __syncwarp();
@@ -1081,11 +1092,6 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             uint64_t total = 0;
             for (uint32_t r = 0; r < a.mg.world; ++r) total += split_lists[r * split_stride];
             ctl->next_id = ctl->child_id_base + total; /* k_lifecycle's tail had added the local count only */
-            a.mg.counters[MG_N_STAY] = 0;
-            a.mg.counters[MG_N_EMIG0] = 0;
-            a.mg.counters[MG_N_EMIG1] = 0;
-            a.mg.counters[MG_HALO_CULT0] = 0;
-            a.mg.counters[MG_HALO_CULT1] = 0;
         }
     }
 
@@ -1327,6 +1333,7 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
                 a.sc.fslot[cpos] = atomicAdd(&a.ps.cnt[cc.target], 1u);
             } else {
                 a.sc.fslot[cpos] = 0xFFFFFFFFu;
+                mg_list_emigrant(a, cpos, cc.target);
             }
         }
         __syncwarp();

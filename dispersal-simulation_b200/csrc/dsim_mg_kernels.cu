@@ -17,10 +17,14 @@
 #include "dsim_math.h"
 #include "dsim_mg_sync.h"
 
-/* The last block of a packing kernel to finish publishes the message: `publish` runs in one thread after every block's
- * stores have been fenced at system scope. */
+/* The last block of a packing kernel to finish publishes the message.  Every thread that stored part of it fences at
+ * device scope before its block takes a ticket (the pattern of a last-block reduction); the thread that takes the last
+ * ticket has thereby observed all of them, and its ONE system-scope fence, followed by relaxed system-scope stores of the
+ * flag words, releases the whole message to the receivers (fences are cumulative: causality order is transitive over
+ * the ticket's device-scope synchronisation and the flag's system-scope one).  A system-scope fence with peer stores in
+ * flight costs about 5 us on B200 — with one in every writing thread as well, a message cost 10 us instead of 5. */
 template <typename F> __device__ __forceinline__ void mg_last_block(uint32_t *ticket, bool wrote, F publish) {
-    if (wrote) mg_fence_sys(); /* system-scope fences are expensive: only the threads that stored part of the message */
+    if (wrote) __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t prev = atomicAdd(ticket, 1u);
@@ -67,6 +71,12 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        /* the step's counters: emigrants are listed by k_move / k_children, stayers counted by k_mg_sort_out */
+        mb.counters[MG_N_STAY] = 0;
+        mb.counters[MG_N_EMIG0] = 0;
+        mb.counters[MG_N_EMIG1] = 0;
+        mb.counters[MG_HALO_CULT0] = 0;
+        mb.counters[MG_HALO_CULT1] = 0;
         mb.split_send[0] = ctl->n_children;
         if (mb.p2p) {
             for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot] = ctl->n_children;
@@ -84,10 +94,10 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
 /* ---- EMIGRANTS -------------------------------------------------------------------------------- */
 /* After part 1 the step's families sit in `next` (survivors + children).  Those whose node is owned stay:
  * they are copied to `cur` (which part 1 no longer needs) at positions handed out by an atomic counter
- * — storage order never influences results.  The others are listed per side for k_mg_pack. */
+ * — storage order never influences results.  The others were listed per side by k_move / k_children when they wrote
+ * them (mg_list_emigrant), so k_mg_pack does not depend on this kernel and runs next to it. */
 __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
-    DevCtl *ctl = a.ctl;
-    const uint32_t n = ctl->n_next;
+    const uint32_t n = a.ctl->n_next;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_round = (n + 31u) & ~31u; /* whole warps take part in the ballots */
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
@@ -106,13 +116,6 @@ __global__ void __launch_bounds__(256) k_mg_sort_out(StepArgs a, MgBuffers mb) {
             a.cur.stock[p] = a.next.stock[j];
             a.cur.clock[p] = a.next.clock[j];
             mb.fslot2[p] = a.sc.fslot[j];
-        } else if (in) {
-            const uint32_t side = loc < a.mg.own_lo ? 0u : 1u;
-            const uint32_t e = atomicAdd(&mb.counters[MG_N_EMIG0 + side], 1u);
-            if (e < mb.ecap)
-                mb.emig_list[side * mb.ecap + e] = j;
-            else
-                atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_CAPACITY);
         }
     }
 }

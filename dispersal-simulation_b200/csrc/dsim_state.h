@@ -209,7 +209,9 @@ struct MgInfo {              /* part of StepArgs */
     uint32_t scap, p2p;
     const uint32_t *seq;          /* peer-memory transport: the exchange round                                     */
     const uint32_t *flags;        /* ... and this rank's flag words                                                */
-    uint32_t *counters;           /* MG_* counters, reset for the step by k_children                                */
+    uint32_t *counters;           /* MG_* counters (reset for the step by k_mg_split_ids)                           */
+    uint32_t *emig_list;          /* [2][ecap] positions (in `next`) of the emigrants per side, appended by k_move / k_children */
+    uint32_t ecap;
     const uint64_t *halo_cult[2]; /* band cultures of the halo views received from the lower / upper neighbour */
 };
 
