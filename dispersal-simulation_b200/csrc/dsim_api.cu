@@ -1699,6 +1699,8 @@ struct dsim_mg_state {
     bool nccl = false, graph_failed = false, p2p = false;
     std::vector<void *> ipc_opened;
     cudaEvent_t seg_ev[8] = {};
+    cudaEvent_t life_ev = nullptr, split_ev = nullptr; /* edges of the rotated step (mg_enqueue_step) */
+    bool halo_pending = false; /* the last step's halo messages have arrived (or will) but are not unpacked yet */
     double seg_ms[7] = {};
     uint64_t seg_steps = 0;
     uint64_t launches_per_step = 0;
@@ -1814,7 +1816,10 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
 #if !defined(DSIM_EMU)
     for (auto &e : m->seg_ev)
         if (!e) CK(cudaEventCreate(&e));
+    if (!m->life_ev) CK(cudaEventCreateWithFlags(&m->life_ev, cudaEventDisableTiming));
+    if (!m->split_ev) CK(cudaEventCreateWithFlags(&m->split_ev, cudaEventDisableTiming));
 #endif
+    m->halo_pending = false;
     h->mg_enabled = true;
     h->mg_lo = m->own_lo;
     h->mg_hi = m->own_hi;
@@ -1853,7 +1858,7 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes) {
     return DSIM_OK;
 }
 
-enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_MOVE_FORKED, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
+enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_MOVE_FORKED, MG_PHASE_ROTATED_HEAD, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
 
 static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
     const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
@@ -1891,6 +1896,31 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
         break;
     case MG_PHASE_MOVE_A: K(DSIM_K_MOVE, a1); break;
     case MG_PHASE_MOVE_B: K(DSIM_K_CHILDREN, a1); M(DSIM_MGK_SORT_OUT, a1); M(DSIM_MGK_PACK, a1); break;
+    case MG_PHASE_ROTATED_HEAD:
+        /* second stream: the halo of the PREVIOUS step is unpacked (after waiting for the neighbours' flags) next to
+         * k_lifecycle, then k_mg_split_ids sends the SPLIT lists next to k_move */
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        dsim_mg_launch(DSIM_MGK_HALO_UNPACK, a2, mb, h->geom, h->stream2);
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        K(DSIM_K_LIFECYCLE, a1);
+        CK(cudaEventRecord(m->life_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, m->life_ev, 0));
+        dsim_mg_launch(DSIM_MGK_SPLIT_IDS, a1, mb, h->geom, h->stream2);
+        CK(cudaEventRecord(m->split_ev, h->stream2));
+        h->total_launches += 2;
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0)); /* k_move reads the halo views */
+        K(DSIM_K_MOVE, a1);
+        CK(cudaStreamWaitEvent(h->stream, m->split_ev, 0)); /* k_children reads the SPLIT lists and the exchange round */
+        K(DSIM_K_CHILDREN, a1);
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        dsim_mg_launch(DSIM_MGK_SORT_OUT, a1, mb, h->geom, h->stream2);
+        h->total_launches += 1;
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        M(DSIM_MGK_PACK, a1);
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        break;
     case MG_PHASE_MOVE_FORKED: /* k_mg_sort_out (re-packs the stayers) on the second stream next to k_mg_pack (sends the emigrants) */
         K(DSIM_K_MOVE, a1); K(DSIM_K_CHILDREN, a1);
         CK(cudaEventRecord(h->fork_ev, h->stream));
@@ -2082,16 +2112,16 @@ static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
      * step's k_move) next to the allocator bookkeeping.  The communicator sees its operations in one order: every
      * exchange is joined back into the main stream before the next one is enqueued. */
     int rc;
-    if (m->p2p) { /* peer memory: the messages travel inside the packing kernels; 18 launches, 14 of them in sequence */
-        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
-        if ((rc = mg_launch_phase(h, m, MG_PHASE_MOVE_FORKED))) return rc;
+    if (m->p2p) {
+        /* Peer memory: the messages travel inside the packing kernels, and the step is ROTATED — it begins by unpacking
+         * the halo the previous step sent (k_move is its first reader) and ends right after k_mg_halo_pack has sent its
+         * own, so no rank waits for a neighbour at the end of a step:
+         *   main stream   k_lifecycle | k_move | k_children | k_mg_pack | k_mg_unpack ... patch kernels | k_mg_halo_pack | k_mg_finish
+         *   second stream k_mg_halo_unpack, k_mg_split_ids (next to k_move) | k_mg_sort_out (next to k_mg_pack)
+         * 18 launches, 12 of them in sequence. */
+        if ((rc = mg_launch_phase(h, m, MG_PHASE_ROTATED_HEAD))) return rc;
         if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
-        CK(cudaEventRecord(h->fork_ev, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
-        if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_HALO))) return rc; /* waits for the neighbours' halos next to the bookkeeping */
-        CK(cudaEventRecord(h->join_ev, h->stream2));
         if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_BOOK))) return rc;
-        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         return DSIM_OK;
     }
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;
@@ -2147,6 +2177,7 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
         }
         if (m->gexec[m->occ_par]) {
             CK(cudaGraphLaunch(m->gexec[m->occ_par], h->stream));
+            if (m->p2p) m->halo_pending = true;
             h->total_launches += m->launches_per_step;
             m->occ_par ^= 1u;
             h->mg_occ_prev = m->occ_par ^ 1u;
@@ -2154,6 +2185,10 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
         }
     }
     if (h->profiling) { /* per-segment device times (dsim_profile_enable): plain launches, one sync per step */
+        if (m->halo_pending) { /* a rotated step left its halo to the next one: this path unpacks at the END of a step */
+            if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
+            m->halo_pending = false;
+        }
         static const int seq[7] = {DSIM_MG_PHASE_LIFECYCLE, -1 - DSIM_MG_CH_SPLIT, DSIM_MG_PHASE_MOVE, -1 - DSIM_MG_CH_EMIGRANTS,
                                    DSIM_MG_PHASE_PATCH, -1 - DSIM_MG_CH_HALO, DSIM_MG_PHASE_FINISH};
         for (int k = 0; k < 7; ++k) {
@@ -2179,8 +2214,9 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
         }
         m->kev_used = 0;
         m->seg_steps += 1;
-    } else if ((rc = mg_enqueue_step(h, m))) {
-        return rc;
+    } else {
+        if ((rc = mg_enqueue_step(h, m))) return rc;
+        if (m->p2p) m->halo_pending = true;
     }
     m->occ_par ^= 1u;
     h->mg_occ_prev = m->occ_par ^ 1u;
@@ -2277,6 +2313,8 @@ void dsim_mg_release(dsim_handle *h) {
     for (auto &e : m->seg_ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : m->kev) cudaEventDestroy(e);
+    if (m->life_ev) cudaEventDestroy(m->life_ev);
+    if (m->split_ev) cudaEventDestroy(m->split_ev);
 #endif
     free_list(m->allocs);
     g_mg.erase(h);

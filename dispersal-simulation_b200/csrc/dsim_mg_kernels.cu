@@ -71,12 +71,6 @@ __global__ void __launch_bounds__(256) k_mg_split_ids(StepArgs a, MgBuffers mb) 
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        /* the step's counters: emigrants are listed by k_move / k_children, stayers counted by k_mg_sort_out */
-        mb.counters[MG_N_STAY] = 0;
-        mb.counters[MG_N_EMIG0] = 0;
-        mb.counters[MG_N_EMIG1] = 0;
-        mb.counters[MG_HALO_CULT0] = 0;
-        mb.counters[MG_HALO_CULT1] = 0;
         mb.split_send[0] = ctl->n_children;
         if (mb.p2p) {
             for (uint32_t r = 0; r < a.mg.world; ++r) mb.peer_split_recv[r][slot] = ctl->n_children;
@@ -383,6 +377,13 @@ __global__ void __launch_bounds__(256) k_mg_finish(StepArgs a, MgBuffers mb) {
     ctl->free_top = ft - popped + dead + freed;
     if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
     mb.counters[MG_N_FREED] = 0;
+    /* the next step's counters: emigrants are listed by k_move / k_children (next to which k_mg_split_ids runs),
+     * stayers are counted by k_mg_sort_out, halo cultures by k_mg_halo_pack */
+    mb.counters[MG_N_STAY] = 0;
+    mb.counters[MG_N_EMIG0] = 0;
+    mb.counters[MG_N_EMIG1] = 0;
+    mb.counters[MG_HALO_CULT0] = 0;
+    mb.counters[MG_HALO_CULT1] = 0;
     ctl->n_cur[a.parity] = ctl->n_next; /* part 2 ran in place on `cur`: the buffers do not swap */
     ctl->t += 1u;
 }
