@@ -69,6 +69,16 @@ struct dsim_handle {
     uint64_t n_near = 0, n_reach = 0, n_reach_padded = 0;
     uint32_t max_row = 0;
     uint32_t reach_span = 0; /* largest |node - reachable or 2-hop node|, in node ids */
+    /* device-built reach table: dsim_create runs the counting pass (row lengths, reach_span); the rows are laid out and
+     * filled when the table is first needed (ensure_reach) — for the nodes of the own band and its halo only when the
+     * handle has been configured for several GPUs by then */
+    bool reach_pending = false;
+    std::vector<void *> reach_tmp;      /* the graph on the device, kept for the fill pass */
+    std::vector<uint32_t> reach_lens;   /* [4 n] of the counting pass */
+    const uint64_t *rb_eoff = nullptr;
+    const uint32_t *rb_edst = nullptr;
+    const double *rb_esec = nullptr;
+    uint32_t reach_lo = 0, reach_hi = 0; /* start nodes whose rows exist */
     bool mg_enabled = false;
     uint32_t mg_lo = 0, mg_hi = 0, mg_occ_prev = 0;
 
@@ -427,96 +437,128 @@ int take_snapshot(dsim_handle *h, bool want_adapt);
 /* The reach table built by the device kernels of dsim_reach.cu (DSIM_OPT_REACH_ON_DEVICE).  *built stays false when a
  * node does not fit the per-warp tables; the caller then builds the table on the host. */
 int build_reach_device(dsim_handle *h, const dsim_graph *g, bool *built) {
+    /* counting pass over all nodes; the fill pass follows in ensure_reach */
     *built = false;
     const uint32_t n = g->n_nodes;
     const uint64_t n_edge = g->edge_off[n];
-    std::vector<void *> tmp;
+    std::vector<void *> &tmp = h->reach_tmp;
     uint64_t *d_eoff;
     uint32_t *d_edst, *d_lens, *d_stats;
     double *d_esec;
+    std::vector<void *> tmp2;
     int rc;
     if ((rc = dev_alloc(h, &d_eoff, (size_t)n + 1, tmp, false)) || (rc = dev_alloc(h, &d_edst, n_edge, tmp, false)) ||
-        (rc = dev_alloc(h, &d_esec, n_edge, tmp, false)) || (rc = dev_alloc(h, &d_lens, (size_t)n * 4, tmp)) ||
-        (rc = dev_alloc(h, &d_stats, 4, tmp)) || (rc = upload(h, d_eoff, g->edge_off, (size_t)n + 1)) ||
+        (rc = dev_alloc(h, &d_esec, n_edge, tmp, false)) || (rc = dev_alloc(h, &d_lens, (size_t)n * 4, tmp2)) ||
+        (rc = dev_alloc(h, &d_stats, 4, tmp2)) || (rc = upload(h, d_eoff, g->edge_off, (size_t)n + 1)) ||
         (rc = upload(h, d_edst, g->edge_dst, n_edge)) || (rc = upload(h, d_esec, g->edge_sec, n_edge))) {
         free_list(tmp);
+        free_list(tmp2);
         return rc;
     }
-    ReachDevGraph dg{d_eoff, d_edst, d_esec, n};
+    ReachDevGraph dg{d_eoff, d_edst, d_esec, n, 0u, n};
     ReachDevOut out{d_lens, d_stats, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     dsim_reach_device_pass(0, dg, out, h->geom.n_sm, (void *)h->stream);
-    std::vector<uint32_t> lens((size_t)n * 4);
+    h->reach_lens.assign((size_t)n * 4, 0u);
     uint32_t stats[4] = {0, 0, 0, 0};
-    if ((rc = download(h, lens.data(), d_lens, (size_t)n * 4)) || (rc = download(h, stats, d_stats, 4)) ||
+    if ((rc = download(h, h->reach_lens.data(), d_lens, (size_t)n * 4)) || (rc = download(h, stats, d_stats, 4)) ||
         cudaStreamSynchronize(h->stream) != cudaSuccess) {
         free_list(tmp);
+        free_list(tmp2);
         return rc ? rc : fail(h, DSIM_ERR_CUDA, "reach table: the counting pass failed");
     }
+    free_list(tmp2);
     if (stats[0] != 0u) { /* a reach set or 2-hop neighbourhood larger than the per-warp tables */
         free_list(tmp);
+        h->reach_lens.clear();
         return DSIM_OK;
     }
-    /* layout: rows padded to multiples of 8 entries (16-byte aligned starts for every column), as dsim_build_reach */
-    std::vector<HostRowHdr> hdr(n);
-    std::vector<uint32_t> near_off((size_t)n + 1);
-    uint64_t ro = 0, no = 0, n_reach = 0;
-    uint32_t max_row = 0;
-    for (uint32_t v = 0; v < n; ++v) {
-        const uint32_t r_len = lens[4 * (size_t)v], n_sensed = lens[4 * (size_t)v + 1], n_near = lens[4 * (size_t)v + 2];
-        if (n_near >= 0xFFFFu) {
+    for (uint32_t v = 0; v < n; ++v)
+        if (h->reach_lens[4 * (size_t)v + 2] >= 0xFFFFu) {
             free_list(tmp);
             return fail(h, DSIM_ERR_INVALID, "a node has 65535 or more nodes in its 2-hop neighbourhood");
         }
+    h->rb_eoff = d_eoff;
+    h->rb_edst = d_edst;
+    h->rb_esec = d_esec;
+    h->reach_span = std::max(h->reach_span, stats[1]);
+    h->reach_pending = true;
+    *built = true;
+    return DSIM_OK;
+}
+
+/* Lays out and fills the rows of the device-built reach table the first time it is needed: all of them, or — on a handle
+ * configured for several GPUs — those of the nodes [own_lo - halo, own_hi + halo), the only ones this rank reads
+ * (its families sit on owned nodes; a child's costs are looked up in the row of its parent's new node, at most one
+ * reach distance outside).  Memory and fill time per rank shrink with the number of bands. */
+int ensure_reach(dsim_handle *h) {
+    if (!h->reach_pending) return DSIM_OK;
+    const uint32_t n = h->n_nodes;
+    uint32_t lo = 0, hi = n;
+    if (h->mg_enabled) {
+        const uint32_t hw = 2u * h->reach_span;
+        lo = h->mg_lo > hw ? h->mg_lo - hw : 0u;
+        hi = h->mg_hi + hw < n ? h->mg_hi + hw : n;
+    }
+    const std::vector<uint32_t> &lens = h->reach_lens;
+    int rc;
+    /* layout: rows padded to multiples of 8 entries (16-byte aligned starts for every column), as dsim_build_reach */
+    std::vector<HostRowHdr> hdr(n, HostRowHdr{0u, 0u, 0u, 0u});
+    std::vector<uint32_t> near_off((size_t)n + 1, 0u);
+    uint64_t ro = 0, no = 0, n_reach = 0;
+    uint32_t max_row = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        near_off[v] = (uint32_t)no;
+        if (v < lo || v >= hi) continue;
+        const uint32_t r_len = lens[4 * (size_t)v], n_sensed = lens[4 * (size_t)v + 1], n_near = lens[4 * (size_t)v + 2];
         const uint32_t padded = (r_len + 7u) & ~7u;
         if (ro > 0xFFFFFFF0ull || no > 0xFFFFFFF0ull) break;
         hdr[v] = HostRowHdr{(uint32_t)ro, padded, n_sensed, n_near};
-        near_off[v] = (uint32_t)no;
         ro += padded;
         no += n_near;
         n_reach += r_len;
         max_row = std::max(max_row, padded);
     }
-    if (ro > 0xFFFFFFF0ull || no > 0xFFFFFFF0ull) {
-        free_list(tmp);
-        return fail(h, DSIM_ERR_CAPACITY, "reach table exceeds 2^32 entries");
-    }
+    if (ro > 0xFFFFFFF0ull || no > 0xFFFFFFF0ull) return fail(h, DSIM_ERR_CAPACITY, "reach table exceeds 2^32 entries");
     near_off[n] = (uint32_t)no;
     RowHdr *d_hdr;
     uint16_t *d_hash;
     uint32_t *d_dst, *d_noff, *d_ndst;
     double *d_cost;
     if ((rc = dev_alloc(h, &d_hdr, n, h->allocs, false)) || (rc = dev_alloc(h, &d_dst, ro + 8, h->allocs, false)) ||
-        (rc = dev_alloc(h, &d_cost, ro + 8, h->allocs, false)) || (rc = dev_alloc(h, &d_hash, (size_t)n * 256u, h->allocs, false)) ||
-        (rc = dev_alloc(h, &d_noff, (size_t)n + 1, h->allocs, false)) || (rc = dev_alloc(h, &d_ndst, no, h->allocs, false)) ||
-        (rc = upload(h, (HostRowHdr *)d_hdr, hdr.data(), n)) || (rc = upload(h, d_noff, near_off.data(), (size_t)n + 1))) {
-        free_list(tmp);
+        (rc = dev_alloc(h, &d_cost, ro + 8, h->allocs, false)) || (rc = dev_alloc(h, &d_hash, (size_t)(hi - lo) * 256u + 8, h->allocs, false)) ||
+        (rc = dev_alloc(h, &d_noff, (size_t)n + 1, h->allocs, false)) || (rc = dev_alloc(h, &d_ndst, no + 8, h->allocs, false)) ||
+        (rc = upload(h, (HostRowHdr *)d_hdr, hdr.data(), n)) || (rc = upload(h, d_noff, near_off.data(), (size_t)n + 1)))
         return rc;
-    }
-    out.hdr = (const HostRowHdr *)d_hdr;
-    out.dst = d_dst;
-    out.cost = d_cost;
-    out.hash = d_hash;
-    out.near_off = d_noff;
-    out.near_dst = d_ndst;
+    /* the bucket index is addressed by node id: the pointer is biased so that node `lo` maps to the first bucket row */
+    uint16_t *hash_biased = reinterpret_cast<uint16_t *>(reinterpret_cast<uintptr_t>(d_hash) - (uintptr_t)lo * 256u * sizeof(uint16_t));
+    ReachDevGraph dg{h->rb_eoff, h->rb_edst, h->rb_esec, n, lo, hi};
+    uint32_t *d_stats;
+    std::vector<void *> tmp2;
+    if ((rc = dev_alloc(h, &d_stats, 4, tmp2))) return rc;
+    ReachDevOut out{nullptr, d_stats, (const HostRowHdr *)d_hdr, d_dst, d_cost, hash_biased, d_noff, d_ndst};
     dsim_reach_device_pass(1, dg, out, h->geom.n_sm, (void *)h->stream);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
-        free_list(tmp);
+        free_list(tmp2);
         return fail(h, DSIM_ERR_CUDA, "reach table: the fill pass failed");
     }
-    free_list(tmp);
+    free_list(tmp2);
+    free_list(h->reach_tmp);
+    h->reach_lens.clear();
+    h->reach_lens.shrink_to_fit();
+    h->reach_pending = false;
+    h->reach_lo = lo;
+    h->reach_hi = hi;
     h->n_near = no;
     h->n_reach = n_reach;
     h->n_reach_padded = ro;
     h->max_row = max_row;
-    h->reach_span = std::max(h->reach_span, stats[1]);
-    h->rt.hash = d_hash;
+    h->rt.hash = hash_biased;
     h->rt.hdr = d_hdr;
     h->rt.dst = d_dst;
     h->rt.cost = d_cost;
     h->rt.near_off = d_noff;
     h->rt.near_dst = d_ndst;
-    *built = true;
-    if (std::getenv("DSIM_DEBUG")) std::fprintf(stderr, "[dsim] reach table built on the device: %llu entries, %llu nearby, span %u\n",
+    if (std::getenv("DSIM_DEBUG")) std::fprintf(stderr, "[dsim] reach table filled on the device for the nodes [%u, %u): %llu entries, %llu nearby, span %u\n", lo, hi,
                                                 (unsigned long long)n_reach, (unsigned long long)no, h->reach_span);
     return DSIM_OK;
 }
@@ -762,6 +804,7 @@ void dsim_destroy(dsim_handle *h) {
     if (h->join3_ev) cudaEventDestroy(h->join3_ev);
     if (h->join4_ev) cudaEventDestroy(h->join4_ev);
     if (h->stream4) cudaStreamDestroy(h->stream4);
+    free_list(h->reach_tmp);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -895,6 +938,8 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         TRY(upload(h, near_dst, hr.near_dst.data(), hr.near_dst.size()));
         TRYCUDA(cudaStreamSynchronize(h->stream));
         h->rt.hash = hash;
+        h->reach_lo = 0;
+        h->reach_hi = n;
         h->rt.hdr = hdr; h->rt.dst = dst; h->rt.cost = cost;
         h->rt.near_off = near_off; h->rt.near_dst = near_dst;
     }
@@ -1025,6 +1070,10 @@ int dsim_sync(dsim_handle *h) {
 }
 
 int dsim_set_patches(dsim_handle *h, const double *res, const double *max_res) {
+    if (h) {
+        int rc_ = ensure_reach(h);
+        if (rc_) return rc_;
+    }
     if (!h || !res || !max_res) return DSIM_ERR_INVALID;
     int rc;
     if ((rc = upload(h, h->ps.res, res, h->n_eco))) return rc;
@@ -1049,6 +1098,10 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     const uint64_t n = f->n;
     if (n && (!f->id || !f->culture || !f->location || !f->size || !f->stored)) return fail(h, DSIM_ERR_INVALID, "missing family array");
     if (n > 0xFFFFFF00ull) return fail(h, DSIM_ERR_CAPACITY, "too many families");
+    {
+        int rc_ = ensure_reach(h);
+        if (rc_) return rc_;
+    }
     for (uint64_t i = 0; i < n; ++i) {
         if (f->location[i] >= h->n_nodes) return fail(h, DSIM_ERR_INVALID, "family location out of range");
         if (i > 0 && f->id[i] <= f->id[i - 1]) return fail(h, DSIM_ERR_INVALID, "family ids must ascend");
@@ -1505,6 +1558,7 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
     if (!h) return DSIM_ERR_INVALID;
     if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "dsim_step between the two parts of a step");
     int rc;
+    if ((rc = ensure_reach(h))) return rc;
     h->snap_valid = false;
     h->obs_valid = false;
     uint64_t births0 = 0, deaths0 = 0, updates0 = 0;
@@ -1567,6 +1621,7 @@ int dsim_step_part(dsim_handle *h, int part) {
     if (!h) return DSIM_ERR_INVALID;
     if (h->mg_enabled) return fail(h, DSIM_ERR_INVALID, "use dsim_mg_phase on a multi-GPU handle");
     int rc;
+    if ((rc = ensure_reach(h))) return rc;
     h->snap_valid = false;
     if (part == 1) {
         if (h->mid_step) return fail(h, DSIM_ERR_INVALID, "part 1 twice");
@@ -1588,6 +1643,10 @@ int dsim_step_part(dsim_handle *h, int part) {
 
 int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach) {
     if (!h) return DSIM_ERR_INVALID;
+    {
+        int rc_ = ensure_reach(h);
+        if (rc_) return rc_;
+    }
     if (n_nearby) *n_nearby = h->n_near;
     if (n_reach) *n_reach = h->n_reach;
     return DSIM_OK;
@@ -1596,6 +1655,10 @@ int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach) {
 int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst, uint64_t *reach_off, uint32_t *reach_dst,
                    double *reach_cost) {
     if (!h) return DSIM_ERR_INVALID;
+    {
+        int rc_ = ensure_reach(h);
+        if (rc_) return rc_;
+    }
     const uint32_t n = h->n_nodes;
     std::vector<HostRowHdr> hdr(n);
     std::vector<uint32_t> noff(n + 1), dst(h->n_reach_padded);
@@ -1628,13 +1691,17 @@ int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst, uint6
 
 int dsim_reach_digest(dsim_handle *h, uint64_t out[5]) {
     if (!h || !out) return DSIM_ERR_INVALID;
+    {
+        int rc_ = ensure_reach(h);
+        if (rc_) return rc_;
+    }
     std::vector<void *> tmp;
     unsigned long long *acc = nullptr;
     int rc = dev_alloc(h, &acc, 5, tmp);
     if (rc) return rc;
     const struct { const void *p; uint64_t words; } part[5] = {
         {h->rt.hdr, (uint64_t)h->n_nodes * 4u},       {h->rt.dst, h->n_reach_padded},
-        {h->rt.cost, h->n_reach_padded * 2u},         {h->rt.hash, (uint64_t)h->n_nodes * 128u},
+        {h->rt.cost, h->n_reach_padded * 2u},         {h->rt.hash + (size_t)h->reach_lo * 256u, (uint64_t)(h->reach_hi - h->reach_lo) * 128u},
         {h->rt.near_dst, h->n_near}};
     for (int k = 0; k < 5; ++k)
         DSIM_LAUNCH(k_digest32, h->geom.n_sm * 8, 256, 0, h->stream, (const uint32_t *)part[k].p, part[k].words, acc + k);
@@ -1968,7 +2035,9 @@ int dsim_mg_phase(dsim_handle *h, int phase) {
     dsim_mg_state *m = h ? mg_of(h) : nullptr;
     if (!m) return DSIM_ERR_INVALID;
     h->snap_valid = false;
-    int rc = mg_launch_phase(h, m, phase);
+    int rc = ensure_reach(h);
+    if (rc) return rc;
+    rc = mg_launch_phase(h, m, phase);
     if (rc) return rc;
     if (phase == DSIM_MG_PHASE_FINISH) { /* the occupied-node lists swap roles */
         m->occ_par ^= 1u;

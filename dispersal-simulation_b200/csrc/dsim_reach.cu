@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_reach_build(ReachDevGraph g, 
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 
-    for (uint32_t v = gwarp; v < g.n; v += nwarps) {
+    for (uint32_t v = g.v_lo + gwarp; v < g.v_hi; v += nwarps) {
         for (uint32_t s = lane; s < RB_CAP; s += 32u) {
             M.key[s] = RB_EMPTY;
             M.dist[s] = RB_INF;

@@ -43,6 +43,7 @@ struct ReachDevGraph {
     const uint32_t *edge_dst;
     const double *edge_sec;
     uint32_t n;
+    uint32_t v_lo, v_hi; /* the pass runs for the start nodes [v_lo, v_hi) (a band of a multi-GPU run, or everything) */
 };
 struct ReachDevOut {
     uint32_t *lens;  /* [4 n] */

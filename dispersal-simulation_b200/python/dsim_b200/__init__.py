@@ -416,6 +416,13 @@ class Sim:
     def step_part(self, part: int):
         self._check(self._f("step_part")(self.h, part))
 
+    def reach_counts(self):
+        """(entries of the 2-hop lists, entries of the reach rows) this handle holds: everything, or on a multi-GPU handle
+        the rows of the own band and its halo."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._f("reach_counts")(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def get_reach(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._f("reach_counts")(self.h, C.byref(a), C.byref(b)))

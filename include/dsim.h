@@ -206,7 +206,10 @@ int dsim_step_part(dsim_handle *h, int part);
 
 /* Reach table read-back (parity tests of the precomputation against movementgraph.rs:64-115).
  * nearby: the 2-hop set of lib.rs:1158-1178 in ascending node order.
- * reach : (destination, cost in OYR) of lib.rs:1133-1154 in ascending destination order. */
+ * reach : (destination, cost in OYR) of lib.rs:1133-1154 in ascending destination order.
+ * The device builder counts every node's row at dsim_create and fills the rows when the table is first needed (state
+ * upload, a step, these calls): on a handle that dsim_mg_configure has split into bands by then, only the rows of the
+ * own band and its halo exist (per-rank memory and fill time ~ 1/ranks); the other rows read as empty. */
 int dsim_reach_counts(dsim_handle *h, uint64_t *n_nearby, uint64_t *n_reach);
 int dsim_get_reach(dsim_handle *h, uint64_t *near_off, uint32_t *near_dst,
                    uint64_t *reach_off, uint32_t *reach_dst, double *reach_cost);

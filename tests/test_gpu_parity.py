@@ -22,7 +22,7 @@ def test_reach_table_built_on_device(oracle, gpu_lib, synth, capfd, monkeypatch)
     for edit in (None, pc.sparse_edges_graph, pc.long_range_graph(16)):
         capfd.readouterr()
         o, d = pc.build_pair(oracle, gpu_lib, synth, 16, 20, 10, hist_cap=96, graph_edit=edit, flags=pc.D.OPT_REACH_ON_DEVICE)
-        assert "reach table built on the device" in capfd.readouterr().err, "the host builder must not have been used"
+        assert "reach table filled on the device" in capfd.readouterr().err, "the host builder must not have been used"
         pc.check_reach(o, d)
     o, d = pc.build_pair(oracle, gpu_lib, synth, 20, 30, 150, hist_cap=96, hist_fill=40, flags=pc.D.OPT_REACH_ON_DEVICE)
     pc.run_lockstep(o, d, 6, hist_cap=96)

@@ -111,5 +111,16 @@ def test_virtual_ranks_with_history(oracle, emu, synth):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
 def test_virtual_ranks_on_gpu(oracle, gpu_lib, synth, world):
-    moved, _ = run_partitioned(gpu_lib, oracle, synth, world, 24, 120, 900, 12, hist_fill=40)
+    moved, sims = run_partitioned(gpu_lib, oracle, synth, world, 24, 120, 900, 12, hist_fill=40)
     assert moved > 0
+    # the reach table of a rank holds the rows of its band and halo only (device builder: counting pass for all nodes,
+    # fill pass for [own_lo - halo, own_hi + halo)): bit-identical results above, a fraction of the entries here
+    full = D.Sim(gpu_lib, sims[0].graph, seed=7)
+    n_full = full.reach_counts()[1]
+    hw = sims[0].mg_halo_width()
+    for s in sims:
+        lo, hi = int(s.mg_bounds[s.mg_rank]), int(s.mg_bounds[s.mg_rank + 1])
+        n_band = s.reach_counts()[1]
+        assert n_band < n_full, "a band's table must be smaller than the full one"
+        assert n_band <= n_full * (hi - lo + 2 * hw) / s.graph.n_nodes * 1.25 + 1
+    full.close()
