@@ -1927,9 +1927,10 @@ int dsim_mg_memcpy(dsim_handle *h, void *dst, const void *src, uint64_t bytes) {
 
 enum { MG_PHASE_MOVE_A = 100, MG_PHASE_MOVE_B, MG_PHASE_MOVE_FORKED, MG_PHASE_ROTATED_HEAD, MG_PHASE_FINISH_HALO, MG_PHASE_FINISH_BOOK }; /* pieces of MOVE and FINISH for the overlapped schedule */
 
-static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase) {
+static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase, bool fuse_finish = false) {
     const StepArgs a1 = mg_args(h, false), a2 = mg_args(h, true);
-    const MgBuffers &mb = m->mb;
+    MgBuffers mb = m->mb;
+    mb.fuse_finish = fuse_finish ? 1u : 0u;
     auto mark = [&](int id) { /* profiling: an event before and after the launch */
         if (!h->profiling) return;
         if (m->kev_used == m->kev.size()) {
@@ -2185,12 +2186,11 @@ static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
         /* Peer memory: the messages travel inside the packing kernels, and the step is ROTATED — it begins by unpacking
          * the halo the previous step sent (k_move is its first reader) and ends right after k_mg_halo_pack has sent its
          * own, so no rank waits for a neighbour at the end of a step:
-         *   main stream   k_lifecycle | k_move | k_children | k_mg_pack | k_mg_unpack ... patch kernels | k_mg_halo_pack | k_mg_finish
+         *   main stream   k_lifecycle | k_move | k_children | k_mg_pack | k_mg_unpack ... patch kernels | k_mg_halo_pack (+ end-of-step bookkeeping)
          *   second stream k_mg_halo_unpack, k_mg_split_ids (next to k_move) | k_mg_sort_out (next to k_mg_pack)
-         * 18 launches, 12 of them in sequence. */
+         * 17 launches, 11 of them in sequence. */
         if ((rc = mg_launch_phase(h, m, MG_PHASE_ROTATED_HEAD))) return rc;
-        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH))) return rc;
-        if ((rc = mg_launch_phase(h, m, MG_PHASE_FINISH_BOOK))) return rc;
+        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH, true))) return rc; /* k_mg_halo_pack's last block ends the step */
         return DSIM_OK;
     }
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_LIFECYCLE))) return rc;

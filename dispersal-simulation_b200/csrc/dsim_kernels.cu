@@ -34,6 +34,9 @@
 #include <cstring>
 
 #define LIFE_BLOCK 256
+#ifndef LIFE_GRID_PER_SM
+#define LIFE_GRID_PER_SM 8 /* every block ends with a ticket on one counter */
+#endif
 #ifndef CHILD_HR
 #define CHILD_HR 3u /* k_children: rounds of 32 history entries handled together (3 x 32 >= the default child history of 91) */
 #endif
@@ -2161,7 +2164,7 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
             DSIM_LAUNCH(kernel, grid, block, smem, s, a);        \
     } while (0)
     switch (which) {
-    case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, 8), LIFE_BLOCK, 0, s, a); break; /* first of the step: a full dependency on what precedes */
+    case DSIM_K_LIFECYCLE: DSIM_LAUNCH(k_lifecycle, grid_for(g, LIFE_GRID_PER_SM), LIFE_BLOCK, 0, s, a); break; /* first of the step: a full dependency on what precedes */
     case DSIM_K_MOVE: STEP_LAUNCH(k_move, grid_for(g, MOVE_MIN_BLOCKS), MOVE_WARPS * 32, 0); break;
     case DSIM_K_CHILDREN: STEP_LAUNCH(k_children, grid_for(g, 2), 128, 0); break;
     case DSIM_K_SEGMENTS: STEP_LAUNCH(k_segments, grid_for(g, 8), 256, 0); break;

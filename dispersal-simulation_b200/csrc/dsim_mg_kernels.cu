@@ -303,6 +303,35 @@ __global__ void __launch_bounds__(128) k_mg_unpack(StepArgs a, MgBuffers mb) {
     }
 }
 
+/* ---- end of step ------------------------------------------------------------------------------ */
+/* one block: heavy-slot allocator (children and immigrants popped, the dead and the emigrants pushed), t += 1 */
+__device__ __forceinline__ void mg_finish_body(const StepArgs &a, const MgBuffers &mb) {
+    DevCtl *ctl = a.ctl;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
+    const uint32_t dead = ctl->n_dead, freed = mb.counters[MG_N_FREED];
+    const uint32_t popped = pops < ft ? pops : ft;
+    const uint32_t base = ft - popped;
+    for (uint32_t k = tid; k < dead; k += nth) a.sc.free_hs[base + k] = a.sc.dead_hs[k];
+    for (uint32_t k = tid; k < freed; k += nth) a.sc.free_hs[base + dead + k] = mb.emig_hs[k];
+    __syncthreads();
+    if (tid != 0) return;
+    ctl->hs_hwm += pops - popped;
+    ctl->free_top = ft - popped + dead + freed;
+    if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
+    mb.counters[MG_N_FREED] = 0;
+    /* the next step's counters: emigrants are listed by k_move / k_children (next to which k_mg_split_ids runs),
+     * stayers are counted by k_mg_sort_out, halo cultures by k_mg_halo_pack */
+    mb.counters[MG_N_STAY] = 0;
+    mb.counters[MG_N_EMIG0] = 0;
+    mb.counters[MG_N_EMIG1] = 0;
+    mb.counters[MG_HALO_CULT0] = 0;
+    mb.counters[MG_HALO_CULT1] = 0;
+    ctl->n_cur[a.parity] = ctl->n_next; /* part 2 ran in place on `cur`: the buffers do not swap */
+    ctl->t += 1u;
+}
+__global__ void __launch_bounds__(256) k_mg_finish(StepArgs a, MgBuffers mb) { mg_finish_body(a, mb); }
+
 /* ---- HALO ------------------------------------------------------------------------------------- */
 /* the views of my boundary strips, with the band cultures they point to packed behind them:
  * message = [header 16][views hw x 16][bands hw x 16][cultures ccap x 8] */
@@ -332,11 +361,24 @@ __global__ void __launch_bounds__(256) k_mg_halo_pack(StepArgs a, MgBuffers mb) 
         }
     }
     if (!mb.p2p) return;
-    mg_last_block(&mb.done[DSIM_MG_CH_HALO], true, [&] {
-        const uint32_t round = *mb.seq;
-        if (mb.has_peer[0]) mg_st_flag(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_HALO0 + 1u, round);
-        if (mb.has_peer[1]) mg_st_flag(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_HALO0 + 0u, round);
-    });
+    /* the last block to finish publishes the message (mg_last_block) and, in the library's own step (mb.fuse_finish),
+     * goes on to do the end-of-step bookkeeping: nothing else of the step is running any more */
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&mb.done[DSIM_MG_CH_HALO], 1u);
+        s_last = prev == gridDim.x - 1u ? 1u : 0u;
+        if (s_last) {
+            mb.done[DSIM_MG_CH_HALO] = 0u;
+            mg_fence_sys();
+            const uint32_t round = *mb.seq;
+            if (mb.has_peer[0]) mg_st_flag(mb.peer_flags[a.mg.rank - 1u] + MG_FLAG_HALO0 + 1u, round);
+            if (mb.has_peer[1]) mg_st_flag(mb.peer_flags[a.mg.rank + 1u] + MG_FLAG_HALO0 + 0u, round);
+        }
+    }
+    __syncthreads();
+    if (s_last && mb.fuse_finish) mg_finish_body(a, mb);
 }
 
 __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb) {
@@ -358,34 +400,6 @@ __global__ void __launch_bounds__(256) k_mg_halo_unpack(StepArgs a, MgBuffers mb
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < mb.ccap; k += gridDim.x * blockDim.x)
             mb.halo_cult[side][k] = cults[k];
     }
-}
-
-/* ---- end of step ------------------------------------------------------------------------------ */
-/* one block: heavy-slot allocator (children and immigrants popped, the dead and the emigrants pushed), t += 1 */
-__global__ void __launch_bounds__(256) k_mg_finish(StepArgs a, MgBuffers mb) {
-    DevCtl *ctl = a.ctl;
-    const uint32_t tid = threadIdx.x, nth = blockDim.x;
-    const uint32_t ft = ctl->free_top, pops = ctl->n_children + mb.counters[MG_N_IMMIG];
-    const uint32_t dead = ctl->n_dead, freed = mb.counters[MG_N_FREED];
-    const uint32_t popped = pops < ft ? pops : ft;
-    const uint32_t base = ft - popped;
-    for (uint32_t k = tid; k < dead; k += nth) a.sc.free_hs[base + k] = a.sc.dead_hs[k];
-    for (uint32_t k = tid; k < freed; k += nth) a.sc.free_hs[base + dead + k] = mb.emig_hs[k];
-    __syncthreads();
-    if (tid != 0) return;
-    ctl->hs_hwm += pops - popped;
-    ctl->free_top = ft - popped + dead + freed;
-    if (ctl->hs_hwm > ctl->hs_cap) ctl->errors |= DSIM_MODEL_CAPACITY;
-    mb.counters[MG_N_FREED] = 0;
-    /* the next step's counters: emigrants are listed by k_move / k_children (next to which k_mg_split_ids runs),
-     * stayers are counted by k_mg_sort_out, halo cultures by k_mg_halo_pack */
-    mb.counters[MG_N_STAY] = 0;
-    mb.counters[MG_N_EMIG0] = 0;
-    mb.counters[MG_N_EMIG1] = 0;
-    mb.counters[MG_HALO_CULT0] = 0;
-    mb.counters[MG_HALO_CULT1] = 0;
-    ctl->n_cur[a.parity] = ctl->n_next; /* part 2 ran in place on `cur`: the buffers do not swap */
-    ctl->t += 1u;
 }
 
 /* an exchange round outside the steps (the initial halo over peer memory): every rank calls it equally often */

@@ -243,6 +243,7 @@ struct MgBuffers {           /* device buffers of one rank; messages have a 16-b
     /* peer-memory transport (dsim_mg_ipc_connect): the exchanges are remote stores over NVLink into the neighbours'
      * receive buffers followed by a flag, instead of NCCL operations */
     uint32_t p2p;
+    uint32_t fuse_finish;               /* k_mg_halo_pack's last block also does k_mg_finish's work (the library's own step) */
     uint32_t *seq;                      /* [1] exchange round of this rank, bumped at the start of every step        */
     uint32_t *done;                     /* [3] blocks of a push kernel that have finished, per channel               */
     uint32_t *flags;                    /* [MG_FLAG_SPLIT0 + 2 x MAX_WORLD] round of the last complete message per source (SPLIT: per round parity) */
