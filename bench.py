@@ -385,7 +385,7 @@ def main():
     sampler = ClockSampler(local_rank)   # samples from the warm-up on: the timed region of a 20-step run lasts milliseconds
     sampler.start()
     st_w = sim.step(args.warmup, want_stats=True, allow_model_errors=True)
-    log(f"[bench] rank {rank}: {st_w.live_families} live families after {args.warmup} warm-up steps")
+    log(f"[bench] rank {rank}: {st_w.live_families} live families on {st_w.occupied_patches} patches after {args.warmup} warm-up steps")
     barrier()
     launches1 = sim.launch_count()
     t_timed0 = time.perf_counter()
