@@ -63,6 +63,9 @@ struct dsim_handle {
     uint64_t seed = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr, join4_ev = nullptr;
+#if !defined(DSIM_EMU)
+    cudaAccessPolicyWindow l2_window = {}; /* views + band records pinned in the persisting part of L2 (num_bytes 0 = off) */
+#endif
     LaunchGeom geom;
     uint32_t n_nodes = 0, n_eco = 0;
     std::vector<uint32_t> eco_off_h; /* [n+1] */
@@ -317,6 +320,22 @@ int ensure_capacity(dsim_handle *h, uint64_t n_now) {
 }
 
 #if !defined(DSIM_EMU)
+/* the persisting-L2 window of the handle on every kernel node of a captured step */
+void apply_l2_window(dsim_handle *h, cudaGraph_t g) {
+    if (h->l2_window.num_bytes == 0) return;
+    size_t n_nodes = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n_nodes) != cudaSuccess || n_nodes == 0) return;
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    if (cudaGraphGetNodes(g, nodes.data(), &n_nodes) != cudaSuccess) return;
+    cudaKernelNodeAttrValue av{};
+    av.accessPolicyWindow = h->l2_window;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+            if (cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+    }
+}
+
 /* The four patch kernels work on disjoint sets of nodes: they fork from the main stream onto three side streams and
  * join it again (also inside a stream capture, where the events become graph edges), so they run concurrently. */
 int launch_patch_kernels(dsim_handle *h, const StepArgs &a) {
@@ -354,6 +373,7 @@ int build_graphs(dsim_handle *h) {
         std::memcpy(h->k_launches, kl, sizeof kl);
         if (rc) return rc;
         CK(cudaStreamEndCapture(h->stream, &g));
+        apply_l2_window(h, g);
         CK(cudaGraphInstantiate(&h->gexec[par], g, 0));
         CK(cudaGraphDestroy(g));
     }
@@ -952,8 +972,50 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         uint32_t *eco_off;
         uint16_t *eco_id;
         double *mx;
-        TRY(dev_alloc(h, &h->ps.view, n, h->allocs));
-        TRY(dev_alloc(h, &h->ps.bands, n, h->allocs));
+        /* views and band records in ONE allocation: the window of the persisting-L2 policy below covers both */
+        {
+            static_assert(sizeof(PatchView) == 16 && sizeof(PatchBands) == 16, "16-byte patch records");
+            PatchView *vb = nullptr;
+            TRY(dev_alloc(h, &vb, 2 * (size_t)n, h->allocs));
+            h->ps.view = vb;
+            h->ps.bands = reinterpret_cast<PatchBands *>(vb + n);
+        }
+#if !defined(DSIM_EMU)
+        /* Developer knob DSIM_L2_PERSIST=1, off by default.  Every move decision gathers ~61 of these 16-byte records at
+         * random (a third of k_move's DRAM sectors), and between two steps more than an L2 worth of reach rows and
+         * history rings streams through the cache: with the knob the 32 n bytes of views and bands are pinned in the
+         * persisting carve-out of L2 (access policy window on every stream of the handle and on every kernel node of
+         * its graphs).  Measured on B200 (profiles/r02_k_move_ab.md): k_move does not get faster (115.4 vs 115.4 us at
+         * C2, 855 vs 867 at C3: the kernel is not bound by those sectors), and the 61 MB taken from the rest of L2
+         * slow the patch kernels down (C3: k_patch_small 75 -> 132 us). */
+        h->l2_window = {};
+        if (std::getenv("DSIM_L2_PERSIST")) {
+            cudaDeviceProp prop{};
+            int dev = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+                prop.accessPolicyMaxWindowSize > 0) {
+                const size_t want = 2 * (size_t)n * sizeof(PatchView);
+                const size_t window = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+                const size_t carve = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                    h->l2_window.base_ptr = h->ps.view;
+                    h->l2_window.num_bytes = window;
+                    h->l2_window.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+                    h->l2_window.hitProp = cudaAccessPropertyPersisting;
+                    h->l2_window.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamAttrValue av{};
+                    av.accessPolicyWindow = h->l2_window;
+                    for (cudaStream_t st : {h->stream, h->stream2, h->stream3, h->stream4})
+                        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+                    if (std::getenv("DSIM_DEBUG"))
+                        std::fprintf(stderr, "[dsim] persisting L2: window %zu MB, carve-out %zu MB (device maximum %d MB), hit ratio %.2f\n", window >> 20,
+                                     carve >> 20, prop.persistingL2CacheMaxSize >> 20, h->l2_window.hitRatio);
+                } else {
+                    (void)cudaGetLastError();
+                }
+            }
+        }
+#endif
         TRY(dev_alloc(h, &h->ps.cnt, n, h->allocs));
         TRY(dev_alloc(h, &h->ps.seg, n, h->allocs));
         TRY(dev_alloc(h, &eco_off, (size_t)n + 1, h->allocs, false));
@@ -2234,6 +2296,7 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
                 rc = mg_enqueue_step(h, m);
                 ok = cudaStreamEndCapture(h->stream, &g) == cudaSuccess && rc == DSIM_OK && g != nullptr;
             }
+            if (ok) apply_l2_window(h, g);
             if (ok) ok = cudaGraphInstantiate(&m->gexec[m->occ_par], g, 0) == cudaSuccess;
             if (g) cudaGraphDestroy(g);
             m->launches_per_step = h->total_launches - launches0;
