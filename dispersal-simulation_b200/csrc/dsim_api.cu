@@ -103,6 +103,7 @@ struct dsim_handle {
     uint32_t parity = 0;
     bool mid_step = false;
     uint32_t steps_since_check = 0;
+    uint32_t check_interval = 1; /* steps that may be enqueued before the live count is read again (host_check) */
     uint64_t n_known = 0; /* families at the last host check */
 
 #if !defined(DSIM_EMU)
@@ -1108,7 +1109,15 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
             dsim_destroy(h);
             return DSIM_ERR_CUDA;
         }
-        uint32_t hcap = o.history_capacity ? o.history_capacity : std::max(mc.n_mem, mc.adult_reset + 1u);
+        const uint32_t hcap_exact = std::max(mc.n_mem, mc.adult_reset + 1u);
+        if (o.history_capacity != 0 && o.history_capacity < hcap_exact && !(o.flags & DSIM_OPT_SHORT_HISTORY)) {
+            g_create_error = "dsim_options.history_capacity is shorter than what the memory loop of lib.rs:854-866 can sample and a child "
+                             "inherits (lib.rs:1841-1844): decisions would silently deviate from the reference once a history outgrows the "
+                             "ring; pass 0 (exact) or set DSIM_OPT_SHORT_HISTORY";
+            dsim_destroy(h);
+            return DSIM_ERR_INVALID;
+        }
+        uint32_t hcap = o.history_capacity ? o.history_capacity : hcap_exact;
         h->hcap = (hcap + 3u) & ~3u;
         h->acap = compute_acap(mc.min_adapt);
     }
@@ -1610,10 +1619,34 @@ int dsim_set_storage(dsim_handle *h, uint64_t n, const uint32_t *node, const uin
 static int host_check(dsim_handle *h) { /* read the live count, grow if the buffers are getting full */
     int rc = sync_ctl(h);
     if (rc) return rc;
+    const uint64_t n_prev = h->n_known;
+    const uint32_t steps = h->steps_since_check;
     h->steps_since_check = 0;
     h->n_known = h->ctl_h->n_cur[h->parity];
     if (h->ctl_h->errors & DSIM_MODEL_CAPACITY) return fail(h, DSIM_ERR_CAPACITY, "family capacity exceeded during a batch of steps");
-    return ensure_capacity(h, h->n_known);
+    if ((rc = ensure_capacity(h, h->n_known))) return rc;
+    /* How many steps may run before the next look at the live count: the growth per step seen since the last check,
+     * squared for safety (1.25 while nothing has been seen: a family splits at most once per step, the usual rate is a
+     * per cent), must not reach 90 % of the capacity.  A population that doubles per step is checked — and its buffers
+     * doubled — every step; a steady one every 8 steps as before. */
+    double g = 1.25;
+    if (steps > 0 && n_prev > 0) {
+        const double r = std::pow((double)std::max<uint64_t>(h->n_known, 1) / (double)n_prev, 1.0 / (double)steps);
+        g = std::max(1.02, r * r);
+    }
+    if (!h->mg_enabled && h->opt.family_capacity == 0 && (double)h->n_known * g * g > 0.9 * (double)h->cap) {
+        const uint64_t want = std::max<uint64_t>(2 * h->n_known + 1024, (uint64_t)((double)h->n_known * g * g * 1.5));
+        if (want > h->cap) {
+            if ((rc = alloc_families(h, want))) return rc;
+            h->ctl_h->cap = (uint32_t)h->cap;
+            h->ctl_h->hs_cap = (uint32_t)h->hs_cap;
+            if ((rc = push_ctl(h))) return rc;
+        }
+    }
+    uint32_t k = 1;
+    for (double x = (double)h->n_known * g * g; k < 8u && x * g <= 0.9 * (double)h->cap; x *= g) ++k;
+    h->check_interval = k;
+    return DSIM_OK;
 }
 
 int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
@@ -1629,7 +1662,7 @@ int dsim_step(dsim_handle *h, uint32_t n_steps, dsim_step_stats *stats) {
         births0 = h->ctl_h->births; deaths0 = h->ctl_h->deaths; updates0 = h->ctl_h->updates;
     }
     for (uint32_t s = 0; s < n_steps; ++s) {
-        if (h->steps_since_check >= 8 || h->n_known * 10 > h->cap * 7)
+        if (h->steps_since_check >= h->check_interval || h->n_known * 10 > h->cap * 7)
             if ((rc = host_check(h))) return rc;
         if (h->mg_enabled) {
             if ((rc = dsim_mg_step_enqueue(h))) return rc;

@@ -26,6 +26,8 @@ N_ECOREGIONS = 304
 OPT_PATCH_WARP_ONLY = 0x2
 OPT_REACH_ON_DEVICE = 0x4
 OPT_REACH_ON_HOST = 0x8
+OPT_NO_PDL = 0x10
+OPT_SHORT_HISTORY = 0x20  # accept a history ring shorter than the exact length (tests whose histories never outgrow it)
 NO_PARENT = 2**64 - 1
 MG_IPC_BYTES = 384
 

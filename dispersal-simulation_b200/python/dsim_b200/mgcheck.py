@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import (_FAM_FIELDS, Options, Sim, StepStats, mg_band_bounds, mg_unique_id, synth_families, synth_grid)
+from . import (_FAM_FIELDS, OPT_SHORT_HISTORY, Options, Sim, StepStats, mg_band_bounds, mg_unique_id, synth_families, synth_grid)
 
 CASE = dict(W=64, H=400, families=6000, steps=30, hist_fill=60, hist_cap=96)
 
@@ -27,6 +27,7 @@ def run_check(lib, synth, dist, rank: int, world: int, device: int, transport: s
         lib.dsim_default_options(C.byref(opt))
         opt.device = device
         opt.history_capacity = c["hist_cap"]
+        opt.flags |= OPT_SHORT_HISTORY
         opt.family_capacity = 4 * c["families"]
         s = Sim(lib, g, seed=7, options=opt)
         if mg:

@@ -125,7 +125,7 @@ typedef struct dsim_families {
 /* Optional knobs that are not model parameters. */
 typedef struct dsim_options {
     uint64_t family_capacity;  /* 0 = choose (2x the families set, at least 1024); grows on demand between steps */
-    uint32_t history_capacity; /* 0 = exact: every entry the memory loop of lib.rs:854-866 can still sample */
+    uint32_t history_capacity; /* 0 = exact: every entry the memory loop of lib.rs:854-866 can still sample; shorter rings need DSIM_OPT_SHORT_HISTORY */
     uint32_t device;           /* CUDA device ordinal */
     uint32_t use_graphs;       /* 1 = replay the step as a CUDA graph (default), 0 = plain launches */
     uint32_t flags;            /* DSIM_OPT_* test knobs, 0 by default */
@@ -135,6 +135,8 @@ typedef struct dsim_options {
                                         * to the host builder for graphs with reach sets of more than 384 or 2-hop sets of
                                         * more than 512 nodes); the flag is accepted and changes nothing */
 #define DSIM_OPT_REACH_ON_HOST 0x8u   /* build the reach table with the host (OpenMP) builder */
+#define DSIM_OPT_SHORT_HISTORY 0x20u   /* accept a history_capacity below the exact ring length (test knob: saves memory in cases whose
+                                        * histories never outgrow the ring; otherwise dsim_create rejects it) */
 #define DSIM_OPT_NO_PDL 0x10u         /* plain stream-ordered launches instead of programmatic dependent launches (A/B knob) */
 
 typedef struct dsim_step_stats {

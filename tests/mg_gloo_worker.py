@@ -46,6 +46,7 @@ def main():
     opt = D.Options()
     emu.dsim_default_options(C.byref(opt))
     opt.history_capacity = 96
+    opt.flags |= D.OPT_SHORT_HISTORY
     opt.family_capacity = 4 * NF + 1024
     sim = D.Sim(emu, g, seed=7, options=opt)
     bounds = D.mg_band_bounds(fam.location, g.n_nodes, world, sim.mg_halo_width())

@@ -30,7 +30,7 @@ def build_pair(oracle_lib, dev_lib, synth, W, H, n_fam, seed=1, sim_seed=7, n_oc
     getattr(dev_lib, dev_prefix + "default_options")(opt)
     opt.history_capacity = hist_cap
     opt.use_graphs = use_graphs
-    opt.flags = flags
+    opt.flags = flags | D.OPT_SHORT_HISTORY
     d = D.Sim(dev_lib, g, params=p, seed=sim_seed, options=opt, prefix=dev_prefix)
     for s in (o, d):
         s.set_patches(res, mx)

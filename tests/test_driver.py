@@ -24,6 +24,7 @@ def _sim(lib, synth, prefix, n_fam=150, params_edit=None):
     opt = D.Options()
     getattr(lib, prefix + "default_options")(C.byref(opt))
     opt.history_capacity = 96
+    opt.flags |= D.OPT_SHORT_HISTORY
     s = D.Sim(lib, g, params=p, seed=7, options=opt, prefix=prefix)
     s.set_patches(res, mx)
     s.set_families(fam)

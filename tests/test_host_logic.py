@@ -15,6 +15,7 @@ def _sim(emu, synth, W=12, H=14, n=60, hist_cap=64, cap=0, **kw):
     opt = D.Options()
     emu.dsim_default_options(C.byref(opt))
     opt.history_capacity = hist_cap
+    opt.flags |= D.OPT_SHORT_HISTORY
     opt.family_capacity = cap
     s = D.Sim(emu, g, seed=5, options=opt)
     s.set_patches(res, mx)
@@ -95,6 +96,7 @@ def test_capacity_grows_between_steps(oracle, emu, synth):
     opt = D.Options()
     emu.dsim_default_options(C.byref(opt))
     opt.history_capacity = 96
+    opt.flags |= D.OPT_SHORT_HISTORY
     opt.family_capacity = 128            # will have to grow: the population passes 180
     d = D.Sim(emu, g, params=p, seed=7, options=opt)
     o = helpers.oracle_sim(oracle, g, params=p, seed=7)

@@ -59,6 +59,7 @@ def run_partitioned(lib, oracle, synth, world, W, H, n_fam, steps, hist_fill=0, 
         opt = D.Options()
         lib.dsim_default_options(C.byref(opt))
         opt.history_capacity = hist_cap
+        opt.flags |= D.OPT_SHORT_HISTORY
         opt.family_capacity = 4 * n_fam + 1024
         s = D.Sim(lib, g, params=p, seed=7, options=opt)
         if r == 0:
