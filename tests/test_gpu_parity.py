@@ -342,3 +342,30 @@ def test_reach_table_device_vs_host_at_c2(gpu_lib, synth):
     assert digests[0] == digests[1], (digests, times)
     assert all(x != 0 for x in digests[0])
     assert times[0] < 4.0, times   # 2.1 s measured; the bound leaves room for a cold first CUDA context
+
+
+@pytest.mark.gpu
+def test_long_run_in_batches(oracle, gpu_lib, synth):
+    """400 seasons enqueued 25 at a time (no host look at the state inside a batch: the adaptive interval between the
+    library's own checks of the live count, capacity growth and the graph re-captures that follow it, the deferred
+    end-of-step bookkeeping), a growing population, histories that wrap the exact ring (300 + 400 > 628 entries):
+    bit-identical to the oracle after every batch."""
+    n0, n1 = _long_run(oracle, gpu_lib, synth, 16)
+    assert n1 > 2 * n0 + 1024, "scenario must exercise growth beyond the initial capacity"
+
+
+def _long_run(oracle, lib, synth, batches, steps_per_batch=25):
+    def peaceful(p):
+        p.cooperation_threshold = 65
+    o, d = pc.build_pair(oracle, lib, synth, 60, 80, 800, params_edit=peaceful, hist_fill=700, hist_cap=0)
+    f = d.get_families()
+    cap = int(f.hist_off[1] - f.hist_off[0])   # the exact ring: what the memory loop can sample (628 at the default season)
+    assert cap >= 625
+    n0 = o.family_counts()[0]
+    for batch in range(batches):
+        so = o.step(steps_per_batch, allow_model_errors=True)
+        sd = d.step(steps_per_batch, allow_model_errors=True)
+        assert so.as_dict() == sd.as_dict(), (batch, so.as_dict(), sd.as_dict())
+        msgs = helpers.compare_sims(o, d, hist_cap=cap, what=f"after batch {batch}")
+        assert not msgs, "\n".join(msgs)
+    return n0, o.family_counts()[0]
