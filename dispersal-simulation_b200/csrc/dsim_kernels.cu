@@ -1107,7 +1107,14 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
             for (uint32_t q = 0; q < a.mg.world; ++q) {
                 const uint64_t *list = split_lists + q * split_stride;
                 const uint32_t m = (uint32_t)list[0];
-                for (uint32_t k = lane; k < m; k += 32u) smaller += list[1 + k] < id ? 1u : 0u;
+                /* four independent loads per lane and round: the scan is a chain of L2 round trips otherwise */
+                for (uint32_t k0 = lane; k0 < m; k0 += 128u) {
+                    uint64_t v[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4u; ++u) v[u] = (k0 + 32u * u < m) ? list[1 + k0 + 32u * u] : ~0ull;
+#pragma unroll
+                    for (uint32_t u = 0; u < 4u; ++u) smaller += v[u] < id ? 1u : 0u;
+                }
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) smaller += __shfl_xor_sync(DSIM_FULL, smaller, d);

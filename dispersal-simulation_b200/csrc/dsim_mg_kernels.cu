@@ -414,8 +414,8 @@ void dsim_mg_launch(int which, const StepArgs &a, const MgBuffers &mb, const Lau
     switch (which) {
     case DSIM_MGK_SPLIT_IDS: DSIM_LAUNCH(k_mg_split_ids, sm, 256, 0, s, a, mb); break;
     case DSIM_MGK_SORT_OUT: DSIM_LAUNCH(k_mg_sort_out, sm * 8, 256, 0, s, a, mb); break;
-    case DSIM_MGK_PACK: DSIM_LAUNCH(k_mg_pack, sm * 4, 128, 0, s, a, mb); break;
-    case DSIM_MGK_UNPACK: DSIM_LAUNCH(k_mg_unpack, sm * 4, 128, 0, s, a, mb); break;
+    case DSIM_MGK_PACK: DSIM_LAUNCH(k_mg_pack, sm * 2, 128, 0, s, a, mb); break; /* a block per emigrant; every block ends with a ticket */
+    case DSIM_MGK_UNPACK: DSIM_LAUNCH(k_mg_unpack, sm * 2, 128, 0, s, a, mb); break;
     case DSIM_MGK_HALO_PACK: DSIM_LAUNCH(k_mg_halo_pack, sm, 128, 0, s, a, mb); break;
     case DSIM_MGK_HALO_UNPACK: DSIM_LAUNCH(k_mg_halo_unpack, sm, 128, 0, s, a, mb); break;
     case DSIM_MGK_FINISH: DSIM_LAUNCH(k_mg_finish, 1, 256, 0, s, a, mb); break;
