@@ -360,10 +360,13 @@ def main():
         opt.family_capacity = int(1.2 * cfg[2])
     t0 = time.time()
     sim = D.Sim(lib, g, seed=args.sim_seed, options=opt)
-    log(f"[bench] rank {rank}: handle + reach table in {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: handle + counting pass of the reach table in {time.time() - t0:.1f}s")
     if world > 1:
         bounds = D.mg_band_bounds(fam.location, g.n_nodes, world, sim.mg_halo_width())
         sim.mg_configure(rank, world, bounds)
+    t0 = time.time()
+    sim.reach_counts()                  # the rows of the reach table are filled on first use: all of them, or the band's
+    log(f"[bench] rank {rank}: reach rows filled in {time.time() - t0:.1f}s ({sim.reach_counts()[1]} entries on this rank)")
     sim.set_patches(res, mx)
     sim.set_families(fam)
     if world > 1:
