@@ -2133,6 +2133,10 @@ int dsim_mg_phase(dsim_handle *h, int phase) {
     h->snap_valid = false;
     int rc = ensure_reach(h);
     if (rc) return rc;
+    if (m->halo_pending) { /* a step of the library's own (rotated) schedule left its halo to the next one */
+        if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
+        m->halo_pending = false;
+    }
     rc = mg_launch_phase(h, m, phase);
     if (rc) return rc;
     if (phase == DSIM_MG_PHASE_FINISH) { /* the occupied-node lists swap roles */
@@ -2427,6 +2431,7 @@ int dsim_mg_halo_sync(dsim_handle *h) { /* initial halo, after the state was set
     rc = mg_exchange(h, m, DSIM_MG_CH_HALO);
     if (rc) return rc;
     if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_HALO_UNPACK))) return rc;
+    m->halo_pending = false;
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
 #endif
