@@ -136,6 +136,11 @@ struct dsim_handle {
     std::vector<uint64_t> obs_cult, obs_size;
     bool obs_valid = false;
     std::string err;
+    /* grow-only staging for state uploads and downloads (dsim_set_families, the snapshots of the getters): a device
+     * buffer for the caller's history / adaptation CSR arrays on their way into the rings, and page-locked host memory
+     * for the packed core records — no cudaMalloc / cudaFree and no pageable copies on a repeated upload or download */
+    void *stage_dev = nullptr, *stage_host = nullptr;
+    size_t stage_dev_bytes = 0, stage_host_bytes = 0;
 };
 
 namespace {
@@ -183,6 +188,36 @@ int push_ctl(dsim_handle *h) {
     CK(cudaStreamSynchronize(h->stream));
     return DSIM_OK;
 }
+
+int stage_reserve(dsim_handle *h, bool device, size_t bytes) {
+    void *&p = device ? h->stage_dev : h->stage_host;
+    size_t &have = device ? h->stage_dev_bytes : h->stage_host_bytes;
+    if (bytes <= have) return DSIM_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (p) {
+        if (device)
+            cudaFree(p);
+        else
+            cudaFreeHost(p);
+        p = nullptr;
+        have = 0;
+    }
+    bytes += bytes / 8 + 4096;
+    if (device) {
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(h, DSIM_ERR_CUDA, "out of device memory (staging)");
+    } else {
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) return fail(h, DSIM_ERR_CUDA, "out of page-locked host memory (staging)");
+    }
+    have = bytes;
+    return DSIM_OK;
+}
+/* carves `count` elements of T out of a staging buffer at `*off` (256-byte aligned) */
+template <typename T> T *stage_take(void *base, size_t *off, size_t count) {
+    T *p = reinterpret_cast<T *>(static_cast<char *>(base) + *off);
+    *off += (count * sizeof(T) + 255u) & ~(size_t)255u;
+    return p;
+}
+template <typename T> size_t stage_size(size_t count) { return (count * sizeof(T) + 255u) & ~(size_t)255u; }
 
 void free_list(std::vector<void *> &l) {
     for (void *p : l) cudaFree(p);
@@ -727,17 +762,24 @@ int take_snapshot(dsim_handle *h, bool want_adapt) {
         h->s_id.resize(n); h->s_culture.resize(n); h->s_stored.resize(n); h->s_lh.resize(n);
         h->s_loc.resize(n); h->s_size.resize(n); h->s_till_adult.resize(n); h->s_till_mut.resize(n);
         h->s_misc.resize(n); h->s_hs.resize(n); h->s_hist_len.resize(n); h->s_hist_cnt.resize(h->hs_cap);
-        /* the packed sub-records come down as they are and are split into the caller's columns here */
-        std::vector<FamKey> key(n);
-        std::vector<FamPlace> place(n);
-        std::vector<FamStock> stock(n);
-        std::vector<FamClock> clock(n);
-        if ((rc = download(h, key.data(), f.key, n))) return rc;
-        if ((rc = download(h, place.data(), f.place, n))) return rc;
-        if ((rc = download(h, stock.data(), f.stock, n))) return rc;
-        if ((rc = download(h, clock.data(), f.clock, n))) return rc;
-        if ((rc = download(h, h->s_hist_cnt.data(), h->hv.hist_cnt, h->hs_cap))) return rc; /* history lengths */
+        /* the packed sub-records come down as they are (into page-locked staging memory) and are split into the
+         * caller's columns here */
+        if ((rc = stage_reserve(h, false, stage_size<FamKey>(n) + stage_size<FamPlace>(n) + stage_size<FamStock>(n) + stage_size<FamClock>(n) +
+                                              stage_size<uint32_t>(h->hs_cap))))
+            return rc;
+        size_t so_ = 0;
+        FamKey *key = stage_take<FamKey>(h->stage_host, &so_, n);
+        FamPlace *place = stage_take<FamPlace>(h->stage_host, &so_, n);
+        FamStock *stock = stage_take<FamStock>(h->stage_host, &so_, n);
+        FamClock *clock = stage_take<FamClock>(h->stage_host, &so_, n);
+        uint32_t *hcnt = stage_take<uint32_t>(h->stage_host, &so_, h->hs_cap);
+        if ((rc = download(h, key, (const FamKey *)f.key, n))) return rc;
+        if ((rc = download(h, place, (const FamPlace *)f.place, n))) return rc;
+        if ((rc = download(h, stock, (const FamStock *)f.stock, n))) return rc;
+        if ((rc = download(h, clock, (const FamClock *)f.clock, n))) return rc;
+        if ((rc = download(h, hcnt, (const uint32_t *)h->hv.hist_cnt, h->hs_cap))) return rc; /* history lengths */
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, DSIM_ERR_CUDA, "synchronize failed in snapshot");
+        std::copy(hcnt, hcnt + h->hs_cap, h->s_hist_cnt.begin());
         for (uint32_t i = 0; i < n; ++i) {
             h->s_id[i] = key[i].id; h->s_culture[i] = key[i].culture;
             h->s_stored[i] = stock[i].stored; h->s_lh[i] = stock[i].last_harvest;
@@ -826,6 +868,8 @@ void dsim_destroy(dsim_handle *h) {
     if (h->join4_ev) cudaEventDestroy(h->join4_ev);
     if (h->stream4) cudaStreamDestroy(h->stream4);
     free_list(h->reach_tmp);
+    if (h->stage_dev) cudaFree(h->stage_dev);
+    if (h->stage_host) cudaFreeHost(h->stage_host);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1188,13 +1232,19 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
         if ((rc = alloc_families(h, want))) return rc;
     }
     const uint32_t acap = h->acap;
-    /* the caller's columns are packed into the four sub-records of the core record (dsim_state.h) */
-    std::vector<FamKey> key(n);
-    std::vector<FamPlace> place(n);
-    std::vector<FamStock> stock(n);
-    std::vector<FamClock> clk(n);
-    std::vector<uint64_t> parent(n);
-    std::vector<uint16_t> birth(n);
+    /* the caller's columns are packed into the four sub-records of the core record (dsim_state.h), in page-locked
+     * staging memory: the uploads below run at the rate of the link and overlap the unpacking of the histories */
+    const size_t host_bytes = stage_size<FamKey>(n) + stage_size<FamPlace>(n) + stage_size<FamStock>(n) + stage_size<FamClock>(n) +
+                              stage_size<uint64_t>(n) + stage_size<uint16_t>(n) + stage_size<uint32_t>(1);
+    if ((rc = stage_reserve(h, false, host_bytes))) return rc;
+    size_t hoff_ = 0;
+    FamKey *key = stage_take<FamKey>(h->stage_host, &hoff_, n);
+    FamPlace *place = stage_take<FamPlace>(h->stage_host, &hoff_, n);
+    FamStock *stock = stage_take<FamStock>(h->stage_host, &hoff_, n);
+    FamClock *clk = stage_take<FamClock>(h->stage_host, &hoff_, n);
+    uint64_t *parent = stage_take<uint64_t>(h->stage_host, &hoff_, n);
+    uint16_t *birth = stage_take<uint16_t>(h->stage_host, &hoff_, n);
+    uint32_t *bad_h = stage_take<uint32_t>(h->stage_host, &hoff_, 1);
     for (uint64_t i = 0; i < n; ++i) {
         const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
         key[i].id = f->id[i];
@@ -1214,42 +1264,48 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     h->mid_step = false;
     h->snap_valid = false;
     const FamCore &c = h->fam[0];
-    if ((rc = upload(h, c.key, key.data(), n)) || (rc = upload(h, c.place, place.data(), n)) || (rc = upload(h, c.stock, stock.data(), n)) ||
-        (rc = upload(h, c.clock, clk.data(), n)) ||
-        (rc = upload(h, h->hv.parent, parent.data(), n)) || (rc = upload(h, h->hv.birth_index, birth.data(), n)))
+    if ((rc = upload(h, c.key, (const FamKey *)key, n)) || (rc = upload(h, c.place, (const FamPlace *)place, n)) ||
+        (rc = upload(h, c.stock, (const FamStock *)stock, n)) || (rc = upload(h, c.clock, (const FamClock *)clk, n)) ||
+        (rc = upload(h, h->hv.parent, (const uint64_t *)parent, n)) || (rc = upload(h, h->hv.birth_index, (const uint16_t *)birth, n)))
         return rc;
-    CK(cudaStreamSynchronize(h->stream)); /* the staging vectors are local to this function */
     CK(cudaMemsetAsync(h->hv.hist_cnt, 0, h->hs_cap * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->hv.a_eco, 0xFF, h->hs_cap * acap * sizeof(uint16_t), h->stream));
     {
-        /* history and adaptation travel as the caller's CSR arrays and are unpacked on the device */
-        std::vector<void *> tmp;
-        uint32_t *d_bad = nullptr;
-        uint32_t bad = 0;
-        if ((rc = dev_alloc(h, &d_bad, 1, tmp))) { free_list(tmp); return rc; }
+        /* history and adaptation travel as the caller's CSR arrays (through the device staging buffer) and are unpacked
+         * on the device */
         const uint64_t nh = f->hist_off ? f->hist_off[n] : 0, na = f->adapt_off ? f->adapt_off[n] : 0;
+        const size_t dev_bytes = stage_size<uint32_t>(1) + (nh ? stage_size<uint64_t>(n + 1) + stage_size<uint32_t>(nh) + stage_size<double>(nh) : 0) +
+                                 (na ? stage_size<uint64_t>(n + 1) + stage_size<uint32_t>(na) + stage_size<double>(na) : 0);
+        if ((rc = stage_reserve(h, true, dev_bytes))) return rc;
+        size_t doff_ = 0;
+        uint32_t *d_bad = stage_take<uint32_t>(h->stage_dev, &doff_, 1);
+        CK(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), h->stream));
         if (n && nh) {
-            uint64_t *d_off; uint32_t *d_patch; double *d_harv;
-            if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_patch, nh, tmp, false)) ||
-                (rc = dev_alloc(h, &d_harv, nh, tmp, false)) || (rc = upload(h, d_off, f->hist_off, n + 1)) ||
-                (rc = upload(h, d_patch, f->hist_patch, nh)) || (rc = upload(h, d_harv, f->hist_harvest, nh))) { free_list(tmp); return rc; }
+            uint64_t *d_off = stage_take<uint64_t>(h->stage_dev, &doff_, n + 1);
+            uint32_t *d_patch = stage_take<uint32_t>(h->stage_dev, &doff_, nh);
+            double *d_harv = stage_take<double>(h->stage_dev, &doff_, nh);
+            if ((rc = upload(h, d_off, (const uint64_t *)f->hist_off, n + 1)) || (rc = upload(h, d_patch, (const uint32_t *)f->hist_patch, nh)) ||
+                (rc = upload(h, d_harv, (const double *)f->hist_harvest, nh)))
+                return rc;
             DSIM_LAUNCH(k_unpack_history, h->geom.n_sm * 8, 256, 0, h->stream, h->hv, (const uint64_t *)d_off, (const uint32_t *)d_patch,
                         (const double *)d_harv, (uint32_t)n, h->n_nodes, d_bad);
             h->total_launches += 1;
         }
         if (n && na) {
-            uint64_t *d_off; uint32_t *d_eco; double *d_val;
-            if ((rc = dev_alloc(h, &d_off, n + 1, tmp, false)) || (rc = dev_alloc(h, &d_eco, na, tmp, false)) ||
-                (rc = dev_alloc(h, &d_val, na, tmp, false)) || (rc = upload(h, d_off, f->adapt_off, n + 1)) ||
-                (rc = upload(h, d_eco, f->adapt_eco, na)) || (rc = upload(h, d_val, f->adapt_val, na))) { free_list(tmp); return rc; }
+            uint64_t *d_off = stage_take<uint64_t>(h->stage_dev, &doff_, n + 1);
+            uint32_t *d_eco = stage_take<uint32_t>(h->stage_dev, &doff_, na);
+            double *d_val = stage_take<double>(h->stage_dev, &doff_, na);
+            if ((rc = upload(h, d_off, (const uint64_t *)f->adapt_off, n + 1)) || (rc = upload(h, d_eco, (const uint32_t *)f->adapt_eco, na)) ||
+                (rc = upload(h, d_val, (const double *)f->adapt_val, na)))
+                return rc;
             DSIM_LAUNCH(k_unpack_adaptation, h->geom.n_sm * 4, 256, 0, h->stream, h->hv, (const uint64_t *)d_off, (const uint32_t *)d_eco,
                         (const double *)d_val, (uint32_t)n, h->p.minimum_adaptation, d_bad);
             h->total_launches += 1;
         }
-        rc = download(h, &bad, d_bad, 1);
+        rc = download(h, bad_h, (const uint32_t *)d_bad, 1);
         if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in set_families");
-        free_list(tmp);
         if (rc) return rc;
+        const uint32_t bad = *bad_h;
         if (bad & 1u) return fail(h, DSIM_ERR_INVALID, "history node out of range");
         if (bad & 2u) return fail(h, DSIM_ERR_INVALID, "adaptation ecoregion out of range");
         if (bad & 4u) return fail(h, DSIM_ERR_CAPACITY, "more adapted ecoregions than adaptation slots");
