@@ -502,11 +502,12 @@ def main():
                 upd += s1.family_updates
             t2 = time.perf_counter()
             out = sim2.get_families(history=False, adaptation=False)
+            t3 = time.perf_counter()
             r_out, _ = sim2.get_patches(maximum=False, out=res_out)  # the maxima are inputs and never change
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             log(f"[bench] rank {rank}: end to end #{rep}: {dt * 1e3:.1f} ms = upload {1e3 * (t1 - t0):.1f} + {n_steps_e2e} steps "
-                f"{1e3 * (t2 - t1):.1f} + download {1e3 * (t0 + dt - t2):.1f}")
+                f"{1e3 * (t2 - t1):.1f} + download {1e3 * (t0 + dt - t2):.1f} (families {1e3 * (t3 - t2):.1f}, patches {1e3 * (t0 + dt - t3):.1f})")
             reps.append((dt, upd))
         dt, upd = sorted(reps)[1]
         dt_best = min(r[0] for r in reps)

@@ -139,6 +139,7 @@ struct dsim_handle {
     /* grow-only staging for state uploads and downloads (dsim_set_families, the snapshots of the getters): a device
      * buffer for the caller's history / adaptation CSR arrays on their way into the rings, and page-locked host memory
      * for the packed core records — no cudaMalloc / cudaFree and no pageable copies on a repeated upload or download */
+    std::vector<uint64_t> s_hoff;
     void *stage_dev = nullptr, *stage_host = nullptr;
     size_t stage_dev_bytes = 0, stage_host_bytes = 0;
 };
@@ -1411,16 +1412,21 @@ int dsim_get_families(dsim_handle *h, dsim_families *f) {
     if (rc) return rc;
     const size_t n = h->s_id.size();
     f->n = n;
-    std::vector<uint64_t> parent;
-    std::vector<uint16_t> birth;
-    if (f->parent_id || f->birth_index) {
-        parent.resize(h->hs_cap);
-        birth.resize(h->hs_cap);
-        if ((rc = download(h, parent.data(), h->hv.parent, h->hs_cap)) || (rc = download(h, birth.data(), h->hv.birth_index, h->hs_cap)))
+    const uint64_t *parent = nullptr;
+    const uint16_t *birth = nullptr;
+    if (f->parent_id || f->birth_index) { /* lineage columns of the heavy slots, through the page-locked staging buffer */
+        if ((rc = stage_reserve(h, false, stage_size<uint64_t>(h->hs_cap) + stage_size<uint16_t>(h->hs_cap)))) return rc;
+        size_t so_ = 0;
+        uint64_t *pp = stage_take<uint64_t>(h->stage_host, &so_, h->hs_cap);
+        uint16_t *bb = stage_take<uint16_t>(h->stage_host, &so_, h->hs_cap);
+        if ((rc = download(h, pp, (const uint64_t *)h->hv.parent, h->hs_cap)) || (rc = download(h, bb, (const uint16_t *)h->hv.birth_index, h->hs_cap)))
             return rc;
         CK(cudaStreamSynchronize(h->stream));
+        parent = pp;
+        birth = bb;
     }
-    std::vector<uint64_t> hoff(n + 1, 0);
+    std::vector<uint64_t> &hoff = h->s_hoff;
+    hoff.assign(n + 1, 0);
     for (size_t i = 0; i < n; ++i) {
         if (f->id) f->id[i] = h->s_id[i];
         if (f->parent_id) f->parent_id[i] = parent[h->s_hs[i]];
