@@ -488,6 +488,9 @@ def main():
         for name in [n_ for n_, _ in D._FAM_FIELDS] + ["hist_off", "hist_patch", "hist_harvest", "adapt_off", "adapt_eco", "adapt_val"]:
             v, t_ = pinned(getattr(fam, name)); keep.append(t_)
             setattr(fam_p, name, v)
+        fam_out = D.Families.empty(2 * fam.n + 1024)  # the caller's buffers for the downloaded family columns, reused
+        for name, _ in D._FAM_FIELDS:                  # (touched once: first-use page faults are not part of a download)
+            getattr(fam_out, name)[:] = 0
         reps = []
         for rep in range(-1, 3):  # one untimed warm-up repetition (first-use costs of the getters: page-locked staging, host
             # pages), then three timed ones; the median is reported
@@ -502,7 +505,10 @@ def main():
                 s1 = sim2.step(1, allow_model_errors=True)      # stats read-back every step (cli.rs:138 extinction check)
                 upd += s1.family_updates
             t2 = time.perf_counter()
-            out = sim2.get_families(history=False, adaptation=False)
+            try:
+                out = sim2.get_families(history=False, adaptation=False, out=fam_out)
+            except ValueError:   # more live families than the reusable buffers hold
+                out = sim2.get_families(history=False, adaptation=False)
             t3 = time.perf_counter()
             r_out, _ = sim2.get_patches(maximum=False, out=res_out)  # the maxima are inputs and never change
             torch.cuda.synchronize()

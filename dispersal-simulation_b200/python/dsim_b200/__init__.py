@@ -358,8 +358,24 @@ class Sim:
                                              C.byref(na) if adaptation else None))
         return n.value, nh.value, na.value
 
-    def get_families(self, history: bool = True, adaptation: bool = True) -> Families:
+    def get_families(self, history: bool = True, adaptation: bool = True, out: "Families | None" = None) -> Families:
+        """`out` = caller-owned column arrays to fill (core columns only: history=False, adaptation=False), e.g. the
+        buffers of a checkpoint writer that downloads the state repeatedly; they must hold at least the live families."""
         n, nh, na = self.family_counts(history, adaptation)
+        if out is not None:
+            if history or adaptation:
+                raise ValueError("out= takes the core columns only")
+            if len(out.id) < n:
+                raise ValueError("out is too small")
+            f = Families(n)
+            for name, _ in _FAM_FIELDS:
+                setattr(f, name, getattr(out, name))
+            f.hist_off = f.hist_patch = f.hist_harvest = f.adapt_off = f.adapt_eco = f.adapt_val = None
+            c = f.as_c()
+            self._check(self._f("get_families")(self.h, C.byref(c)))
+            for name, _ in _FAM_FIELDS:
+                setattr(f, name, getattr(out, name)[:n])
+            return f
         f = Families.empty(n, nh if history else 0, na if adaptation else 0)
         if not history:
             f.hist_off = f.hist_patch = f.hist_harvest = None
