@@ -401,7 +401,17 @@ int build_graphs(dsim_handle *h) {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const StepArgs a = make_args(h, par);
-        for (int k = 0; k < DSIM_K_PATCH_ONE; ++k) dsim_launch_kernel(k, a, h->geom, h->stream);
+        /* k_children runs NEXT TO k_move (second stream): it waits, task by task, for the tag a parent's tile stores when
+         * it has decided, and fills the SM resources k_move's tail frees; both are joined before k_segments */
+        dsim_launch_kernel(DSIM_K_LIFECYCLE, a, h->geom, h->stream);
+        CK(cudaEventRecord(h->fork_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+        dsim_launch_kernel(DSIM_K_MOVE, a, h->geom, h->stream);
+        dsim_launch_kernel(DSIM_K_CHILDREN, a, h->geom, h->stream2);
+        CK(cudaEventRecord(h->join_ev, h->stream2));
+        CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        dsim_launch_kernel(DSIM_K_SEGMENTS, a, h->geom, h->stream);
+        dsim_launch_kernel(DSIM_K_SCATTER, a, h->geom, h->stream);
         const uint64_t tl = h->total_launches; /* counted per replay, not per capture */
         uint64_t kl[DSIM_K_COUNT];
         std::memcpy(kl, h->k_launches, sizeof kl);
@@ -944,7 +954,13 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
         return DSIM_ERR_CUDA;                                                             \
     }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    TRYCUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    {
+        /* the second stream carries kernels that run NEXT TO a bigger one on the main stream (k_children next to k_move):
+         * lowest priority, so that their blocks only take what the main stream's kernel leaves or frees */
+        int least = 0, greatest = 0;
+        TRYCUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        TRYCUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, least));
+    }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
     TRYCUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
@@ -1314,9 +1330,10 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     CK(cudaMemsetAsync(h->hv.decay, 0, h->hs_cap * sizeof(uint32_t), h->stream));
     if ((rc = sync_ctl(h))) return rc;
     DevCtl &ctl = *h->ctl_h;
-    const uint32_t t_keep = ctl.t;
+    const uint32_t t_keep = ctl.t, serial_keep = ctl.serial;
     std::memset(&ctl, 0, sizeof ctl);
     ctl.t = t_keep;
+    ctl.serial = serial_keep; /* never reset: stale ChildTask tags of earlier steps must not match a later step */
     ctl.n_cur[0] = (uint32_t)n;
     ctl.hs_hwm = (uint32_t)n;
     ctl.next_id = have_override ? next_id_override : (n ? f->id[n - 1] + 1 : 0);
@@ -2132,12 +2149,15 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase, bool fus
         CK(cudaEventRecord(m->life_ev, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, m->life_ev, 0));
         dsim_mg_launch(DSIM_MGK_SPLIT_IDS, a1, mb, h->geom, h->stream2);
+        /* k_children follows on the second stream, next to k_move: it waits for the SPLIT flags of all ranks and then,
+         * task by task, for the tag a parent's tile stores when it has decided (ChildTask.ready) */
+        dsim_launch_kernel(DSIM_K_CHILDREN, a1, h->geom, h->stream2);
+        h->k_launches[DSIM_K_CHILDREN] += 1;
         CK(cudaEventRecord(m->split_ev, h->stream2));
-        h->total_launches += 2;
+        h->total_launches += 3;
         CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0)); /* k_move reads the halo views */
         K(DSIM_K_MOVE, a1);
-        CK(cudaStreamWaitEvent(h->stream, m->split_ev, 0)); /* k_children reads the SPLIT lists and the exchange round */
-        K(DSIM_K_CHILDREN, a1);
+        CK(cudaStreamWaitEvent(h->stream, m->split_ev, 0)); /* the children are written: k_mg_sort_out / k_mg_pack see every family */
         CK(cudaEventRecord(h->fork_ev, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
         dsim_mg_launch(DSIM_MGK_SORT_OUT, a1, mb, h->geom, h->stream2);
@@ -2347,9 +2367,9 @@ static int mg_enqueue_step(dsim_handle *h, dsim_mg_state *m) {
         /* Peer memory: the messages travel inside the packing kernels, and the step is ROTATED — it begins by unpacking
          * the halo the previous step sent (k_move is its first reader) and ends right after k_mg_halo_pack has sent its
          * own, so no rank waits for a neighbour at the end of a step:
-         *   main stream   k_lifecycle | k_move | k_children | k_mg_pack | k_mg_unpack ... patch kernels | k_mg_halo_pack (+ end-of-step bookkeeping)
-         *   second stream k_mg_halo_unpack, k_mg_split_ids (next to k_move) | k_mg_sort_out (next to k_mg_pack)
-         * 17 launches, 11 of them in sequence. */
+         *   main stream   k_lifecycle | k_move | k_mg_pack | k_mg_unpack ... patch kernels | k_mg_halo_pack (+ end-of-step bookkeeping)
+         *   second stream k_mg_halo_unpack, k_mg_split_ids, k_children (next to k_move) | k_mg_sort_out (next to k_mg_pack)
+         * 17 launches, 10 of them in sequence. */
         if ((rc = mg_launch_phase(h, m, MG_PHASE_ROTATED_HEAD))) return rc;
         if ((rc = mg_launch_phase(h, m, DSIM_MG_PHASE_PATCH, true))) return rc; /* k_mg_halo_pack's last block ends the step */
         return DSIM_OK;

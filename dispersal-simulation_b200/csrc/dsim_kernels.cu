@@ -219,6 +219,7 @@ __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint
         }
         ctl->life_done = 0;
         ctl->move_next = 0; /* k_move hands its tiles out from here */
+        ctl->serial += 1u;  /* tags this step's ChildTasks */
     }
 }
 
@@ -557,6 +558,7 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
     dsim_pdl_wait();
     const uint32_t n = ctl->n_cur[a.parity];
     const uint32_t step = ctl->t;
+    const uint32_t serial = ctl->serial;
     const uint32_t cap = ctl->cap;
     const uint32_t hcap = a.hv.hcap;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1028,8 +1030,12 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, MOVE_MIN_BLOCKS) k_move(StepA
                 t.parent_hs = hs;
                 t.hist_cnt = hist_cnt + 1u;
                 t.n_off = n_off;
-                t.pad_ = 0u;
+                t.ready = 0u;
                 a.sc.child_task[S.crank[lane]] = t;
+                /* k_children runs next to this kernel: the task — and the history entry pushed above, which the child
+                 * inherits — become visible before the tag that says so */
+                __threadfence();
+                dsim_store_release_u32(&a.sc.child_task[S.crank[lane]].ready, serial);
             }
             FamKey ky;
             ky.id = fid;
@@ -1098,7 +1104,22 @@ __global__ void __launch_bounds__(128) k_children(StepArgs a) {
         }
     }
 
+    const uint32_t serial = ctl->serial;
     for (uint32_t r = gwarp; r < n_children; r += nwarps) {
+        /* the parent's k_move tile may still be running (this kernel is launched next to k_move and fills the SMs
+         * its tail frees): wait for the task's tag.  Bounded: a producer that never comes raises a model error
+         * instead of hanging the device. */
+        {
+            uint32_t spins = 0;
+            while (dsim_load_acquire_u32(&a.sc.child_task[r].ready) != serial) {
+                dsim_backoff();
+                if (++spins > (1u << 24)) {
+                    if (lane == 0) atomicOr(&ctl->errors, (uint32_t)DSIM_MODEL_COMM_TIMEOUT);
+                    break;
+                }
+            }
+            __syncwarp();
+        }
         const ChildTask t = a.sc.child_task[r];
         uint32_t grank = r;
         if (a.mg.enabled) { /* the lanes stride over the gathered lists */

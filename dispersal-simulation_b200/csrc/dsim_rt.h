@@ -8,6 +8,8 @@
 #ifndef DSIM_RT_H
 #define DSIM_RT_H
 
+#include <stdint.h>
+
 #if defined(DSIM_EMU)
 #include "cuda_emu.h"
 #define DSIM_LAUNCH(kernel, grid, block, smem, stream, ...) \
@@ -52,6 +54,21 @@ __device__ __forceinline__ void dsim_pdl_trigger() { asm volatile("griddepcontro
 #else
 #define DSIM_NOINLINE __noinline__
 #define DSIM_LDCG(p) __ldcg(p) /* read at L2: data another block of the same launch has just written */
+#endif
+
+/* release / acquire at device scope for hand-offs between kernels that run concurrently (ChildTask.ready) */
+#if defined(DSIM_EMU)
+static inline void dsim_store_release_u32(uint32_t *p, uint32_t v) { *p = v; }
+static inline uint32_t dsim_load_acquire_u32(const uint32_t *p) { return *p; }
+static inline void dsim_backoff() {}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void dsim_store_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t dsim_load_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsim_backoff() { __nanosleep(64); }
 #endif
 
 #define DSIM_FULL 0xffffffffu

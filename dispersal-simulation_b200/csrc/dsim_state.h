@@ -113,7 +113,9 @@ struct ChildTask { /* what k_children needs about a family that split (lib.rs:18
     double take;             /* resources_they_take */
     uint32_t old_loc, new_loc, parent_hs;
     uint32_t hist_cnt;       /* parent's history pushes incl. this step's */
-    uint32_t n_off, pad_;    /* the ":<k>" of lib.rs:1880 */
+    uint32_t n_off;          /* the ":<k>" of lib.rs:1880 */
+    uint32_t ready;          /* = DevCtl.serial of the step once the task is complete: k_children runs next to k_move and
+                                picks a task up as soon as its parent has decided (stored last, after a fence) */
 };
 
 struct StepScratch {
@@ -155,7 +157,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t life_done;      /* blocks of k_lifecycle that have finished (the last one scans and resets it) */
     uint32_t move_next;      /* next tile of k_move to hand out (reset by the tail of k_lifecycle)           */
     uint32_t advance_pending;/* the end-of-step bookkeeping of the last step is still due (dsim_apply_advance)      */
-    uint32_t pad_;
+    uint32_t serial;         /* steps begun on this handle, never reset: tags the ChildTasks of a step (ChildTask.ready) */
     uint64_t child_id_base, next_id;
     uint64_t births, deaths, updates;
 };
