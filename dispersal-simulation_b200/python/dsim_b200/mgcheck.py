@@ -15,7 +15,7 @@ CASE = dict(W=64, H=400, families=6000, steps=30, hist_fill=60, hist_cap=96)
 
 
 def run_check(lib, synth, dist, rank: int, world: int, device: int, transport: str = "peer", case: dict | None = None,
-              use_nccl: bool = True, log=None):
+              use_nccl: bool = True, log=None, lag_rank=None):
     """Returns (ok, detail) on every rank.  transport: "peer" (CUDA IPC remote stores; with use_nccl=False no
     communicator is created at all) or "nccl"."""
     c = dict(CASE, **(case or {}))
@@ -48,7 +48,25 @@ def run_check(lib, synth, dist, rank: int, world: int, device: int, transport: s
         if not use_nccl:
             dist.barrier()                   # every rank is connected before the first remote store
             sim.mg_halo_sync()               # initial halo over peer memory
-    st = sim.step(c["steps"], allow_model_errors=True)
+    if lag_rank is None:
+        st = sim.step(c["steps"], allow_model_errors=True)
+    else:
+        # steps issued one at a time, one rank's host sleeping before each: its device falls behind and the other ranks
+        # run ahead as far as the messages let them (a rank three bands away gets a whole SPLIT round ahead: the case
+        # the per-parity receive areas of the SPLIT channel exist for)
+        import time
+        st = None
+        for _ in range(c["steps"]):
+            if rank == lag_rank:
+                time.sleep(0.02)
+            s1 = sim.step(1, allow_model_errors=True)
+            if st is None:
+                st = s1
+            else:
+                st.births += s1.births
+                st.deaths += s1.deaths
+                st.model_errors |= s1.model_errors
+                st.live_families = s1.live_families
     f = sim.get_families()
     mine = {name: getattr(f, name) for name, _ in _FAM_FIELDS}
     mine["hist"] = [tuple(map(np.ndarray.tolist, f.history_of(i))) for i in range(f.n)]

@@ -19,8 +19,9 @@ def main():
     lib, synth = D.load(), helpers.load_synth()
     case = {"W": 48, "H": int(os.environ.get("MG_H", "240")), "families": 3000, "steps": int(os.environ.get("MG_STEPS", "12")),
             "hist_fill": 40}
+    lag = os.environ.get("MG_LAG_RANK")
     ok, detail = mgcheck.run_check(lib, synth, dist, rank, world, 0, transport="peer", case=case, use_nccl=False,
-                                   log=lambda m: print(m, flush=True))
+                                   log=lambda m: print(m, flush=True), lag_rank=int(lag) if lag else None)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -18,13 +18,17 @@ def _free_port():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_transport_processes_on_one_gpu(world):
+@pytest.mark.parametrize("world,lag", [(2, None), (4, None), (4, 3)])
+def test_peer_transport_processes_on_one_gpu(world, lag):
+    """lag = a rank whose host sleeps before every single step: the others run ahead as far as the messages allow (the
+    SPLIT channel's per-parity receive areas must keep a lagging far rank from reading the next round's lists)."""
     port = _free_port()
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="2", MG_H="240" if world == 2 else "400")
+        if lag is not None:
+            env["MG_LAG_RANK"] = str(lag)
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mg_ipc_worker.py")], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
