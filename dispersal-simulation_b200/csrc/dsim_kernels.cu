@@ -1,7 +1,7 @@
 /*
  * dsim_kernels.cu — the step loop of the dispersal model as sm_100a kernels.
  *
- * One season = `step` (lib.rs:477-496) = nine launches (the last four concurrent), replayed as a CUDA graph:
+ * One season = `step` (lib.rs:477-496) = nine launches (k_children next to k_move, the four patch kernels concurrent), replayed as a CUDA graph:
  *
  *   part 1, update_each_family_step (lib.rs:511-552)
  *     k_lifecycle   consume / shrink / grow per family (lib.rs:527-539, 1912-1937); survivor and
@@ -12,7 +12,8 @@
  *                   parent's half of maybe_procreate (lib.rs:1869-1897); writes the compacted next
  *                   family buffer; counts arrivals per node (histogram of the counting sort by patch)
  *     k_children    one warp per child: its record, history and adaptation, its own move
- *                   (lib.rs:1840-1855, 1877-1895)
+ *                   (lib.rs:1840-1855, 1877-1895); launched next to k_move, it picks a child up as soon as the parent's
+ *                   tile has tagged its ChildTask
  *   part 2, distribute_each_patch_resources_step (lib.rs:591-655)
  *     k_segments    one thread per occupied node: claim a segment of `members`
  *     k_scatter     one thread per family: counting-sort scatter; clears the views of vacated nodes
@@ -1461,7 +1462,7 @@ __global__ void __launch_bounds__(256) k_scatter(StepArgs a) {
     /* The end-of-step bookkeeping (heavy-slot allocator, `s.t += 1`, src/cli.rs:154) has no kernel of its own: it is
      * marked as due here — k_children, the last reader of the allocator fields, is done; the patch kernels still read
      * ctl->t, which does not change yet — and applied by the tail of the next k_lifecycle, or by the host when it
-     * reads the control block (sync_ctl).  The multi-GPU step keeps its own k_mg_finish2. */
+     * reads the control block (sync_ctl).  The multi-GPU step keeps its own k_mg_finish. */
     if (tid == 0 && !a.mg.enabled) ctl->advance_pending = 1u;
     /* nodes occupied last step and empty now: census 0, no band cultures (lib.rs:522-525, 614) */
     const uint32_t n_prev = ctl->n_occ[a.occ_par ^ 1u];

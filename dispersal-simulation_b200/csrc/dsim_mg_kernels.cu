@@ -11,7 +11,12 @@
  *   HALO       rank <-> rank +-1: the 32-byte views (census, quality, band cultures) of the 2S nodes on
  *              each side of a boundary, S = largest node-id distance in the reach table.
  * Nothing here depends on the order in which families are stored, so the partitioned run is
- * bit-identical to the single-GPU run (tests/test_multi_rank.py).
+ * bit-identical to the single-GPU run (tests/test_multi_rank.py, tests/test_multi_rank_ipc.py, bench.py at N > 1).
+ *
+ * A message is written by the kernel that produces it and read by the kernel that needs it.  With the peer-memory
+ * transport (mb.p2p) the producer stores straight into the receiver's buffer over NVLink and its last block publishes a
+ * flag (mg_last_block); the consumer starts by waiting for the flag (mg_wait_flags).  With NCCL or a caller-driven
+ * transport the same kernels write and read the local send / receive buffers and the copy happens between them.
  */
 #include "dsim_kernels.h"
 #include "dsim_math.h"

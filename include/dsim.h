@@ -249,7 +249,7 @@ int dsim_mg_init_nccl(dsim_handle *h, const void *unique_id);
 /* Peer-memory transport (all ranks on one NVLink node, one process per rank): every rank exports CUDA IPC handles of
  * its receive buffers (DSIM_MG_IPC_BYTES), the caller gathers them from all ranks (rank-major) and hands them back;
  * from then on dsim_mg_step_enqueue moves the three messages of a step by remote stores into the neighbours' buffers
- * plus a flag (k_mg_push / k_mg_wait) instead of NCCL operations.  Results are unchanged.  It works with or without
+ * plus a flag (written by the packing kernels themselves, awaited by the consuming ones) instead of NCCL operations.  Results are unchanged.  It works with or without
  * dsim_mg_init_nccl: without a communicator dsim_mg_halo_sync also goes through peer memory (call it on every rank
  * once all ranks have connected) and dsim_mg_reduce_stats is not available (the caller sums the per-rank stats). */
 #define DSIM_MG_IPC_BYTES 384 /* 6 handles of 64 bytes */
