@@ -1262,29 +1262,6 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
     uint64_t *parent = stage_take<uint64_t>(h->stage_host, &hoff_, n);
     uint16_t *birth = stage_take<uint16_t>(h->stage_host, &hoff_, n);
     uint32_t *bad_h = stage_take<uint32_t>(h->stage_host, &hoff_, 1);
-    for (uint64_t i = 0; i < n; ++i) {
-        const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
-        key[i].id = f->id[i];
-        key[i].culture = f->culture[i];
-        place[i].loc = f->location[i];
-        place[i].size = f->size[i];
-        place[i].hs = (uint32_t)i;
-        place[i].misc = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
-        stock[i].stored = f->stored[i];
-        stock[i].last_harvest = f->last_harvest ? f->last_harvest[i] : 0.0;
-        clk[i].till_adult = f->till_adult ? f->till_adult[i] : 0;
-        clk[i].till_mut = (clock && f->till_mutation) ? f->till_mutation[i] : 0;
-        parent[i] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
-        birth[i] = f->birth_index ? f->birth_index[i] : 0;
-    }
-    h->parity = 0;
-    h->mid_step = false;
-    h->snap_valid = false;
-    const FamCore &c = h->fam[0];
-    if ((rc = upload(h, c.key, (const FamKey *)key, n)) || (rc = upload(h, c.place, (const FamPlace *)place, n)) ||
-        (rc = upload(h, c.stock, (const FamStock *)stock, n)) || (rc = upload(h, c.clock, (const FamClock *)clk, n)) ||
-        (rc = upload(h, h->hv.parent, (const uint64_t *)parent, n)) || (rc = upload(h, h->hv.birth_index, (const uint16_t *)birth, n)))
-        return rc;
     CK(cudaMemsetAsync(h->hv.hist_cnt, 0, h->hs_cap * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->hv.a_eco, 0xFF, h->hs_cap * acap * sizeof(uint16_t), h->stream));
     {
@@ -1319,6 +1296,30 @@ static int set_families_impl(dsim_handle *h, const dsim_families *f, uint64_t ne
                         (const double *)d_val, (uint32_t)n, h->p.minimum_adaptation, d_bad);
             h->total_launches += 1;
         }
+        /* the packing of the core records runs on the host while the history arrays (95 % of the bytes) are on the link */
+        for (uint64_t i = 0; i < n; ++i) {
+            const bool clock = f->has_mutation_clock ? f->has_mutation_clock[i] != 0 : false;
+            key[i].id = f->id[i];
+            key[i].culture = f->culture[i];
+            place[i].loc = f->location[i];
+            place[i].size = f->size[i];
+            place[i].hs = (uint32_t)i;
+            place[i].misc = (uint32_t)(f->n_offspring ? f->n_offspring[i] : 0) | (clock ? DSIM_MISC_CLOCK : 0u);
+            stock[i].stored = f->stored[i];
+            stock[i].last_harvest = f->last_harvest ? f->last_harvest[i] : 0.0;
+            clk[i].till_adult = f->till_adult ? f->till_adult[i] : 0;
+            clk[i].till_mut = (clock && f->till_mutation) ? f->till_mutation[i] : 0;
+            parent[i] = f->parent_id ? f->parent_id[i] : DSIM_NO_PARENT;
+            birth[i] = f->birth_index ? f->birth_index[i] : 0;
+        }
+        h->parity = 0;
+        h->mid_step = false;
+        h->snap_valid = false;
+        const FamCore &c = h->fam[0];
+        if ((rc = upload(h, c.key, (const FamKey *)key, n)) || (rc = upload(h, c.place, (const FamPlace *)place, n)) ||
+            (rc = upload(h, c.stock, (const FamStock *)stock, n)) || (rc = upload(h, c.clock, (const FamClock *)clk, n)) ||
+            (rc = upload(h, h->hv.parent, (const uint64_t *)parent, n)) || (rc = upload(h, h->hv.birth_index, (const uint16_t *)birth, n)))
+            return rc;
         rc = download(h, bad_h, (const uint32_t *)d_bad, 1);
         if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, DSIM_ERR_CUDA, "synchronize failed in set_families");
         if (rc) return rc;
