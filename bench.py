@@ -193,7 +193,7 @@ def run_reference(args, cfg_name, cfg):
     if rank != 0:
         return 0
     world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)
-    if world > 1:
+    if world > 1 and not args.strong:
         cfg = (cfg[0], cfg[1], cfg[2] * world, cfg[3], cfg[4])
     synth = D.load_synth()
     g, res, mx, fam = build_workload(cfg, args.seed, synth)
@@ -236,7 +236,7 @@ def run_reference(args, cfg_name, cfg):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "family-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_of(cfg_name, cfg, args.seed, world),
         "note": "CPU arm: C++ port of the reference algorithm (reference-shaped: one bounded Dijkstra per family per "
@@ -303,6 +303,9 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--flags", type=int, default=0, help="dsim_options.flags (kernel variants, see include/dsim.h)")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: keep the configuration's total number of families (BASELINE configs[2]: --config c3 --strong) instead "
+                         "of the default weak scaling (the configuration's families per GPU)")
     args = ap.parse_args()
     cfg_name = args.config or "c2"
     cfg = CONFIGS[cfg_name]
@@ -345,7 +348,7 @@ def main():
                                              transport=os.environ.get("DSIM_MG_TRANSPORT", "peer"), log=log)
     # N > 1: weak scaling — 100k x N families on the same Americas-scale grid, split into N latitude bands of
     # about equal family counts; halo views and migrating families travel over NCCL.
-    if world > 1:
+    if world > 1 and not args.strong:
         cfg = (cfg[0], cfg[1], cfg[2] * world, cfg[3], cfg[4])
     g, res, mx, fam = build_workload(cfg, args.seed, synth)
     opt = D.Options()
@@ -561,7 +564,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "family-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_all / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": config_of(cfg_name, cfg, args.seed, world),
             "transport": transport,
             "cuda_graphs": not args.no_graphs,
