@@ -1539,9 +1539,19 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
 
 /* one node of k_patch, worked on by the whole block; inlined twice, once with the working arrays in shared memory
  * (fixed offsets) and once with them in HBM scratch, so that neither copy carries seventeen live pointers.
- * s_ctl: two shared words (number of bands, population). */
+ * s_ctl: two shared words (number of bands, population); X: shared scratch of the two steps that would otherwise cost
+ * O(n^2) on a node of hundreds or thousands of families (the long-run regime of the continental grid: nodes of 1 400
+ * families after 10^4 seasons) — the rank sort of the shuffle and the "hostile to an earlier member" test. */
+#define PATCH_DMAX 64u /* distinct cultures of a node listed in shared memory (beyond: the quadratic test) */
+struct PatchAux {
+    uint32_t bstart[257]; /* rank sort: keys bucketed by their top byte */
+    uint32_t bcur[256];
+    uint64_t dcult[PATCH_DMAX]; /* distinct cultures in order of first appearance in the shuffled order ... */
+    uint32_t dfirst[PATCH_DMAX]; /* ... and where they first appear */
+    uint32_t dn;
+};
 __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t tid,
-                                           uint32_t step, const dsim_stream rs, double season, uint32_t &errors, uint32_t *s_ctl) {
+                                           uint32_t step, const dsim_stream rs, double season, uint32_t &errors, uint32_t *s_ctl, PatchAux &X) {
     const uint32_t lane = tid & 31u, nthr = PATCH_WARPS * 32u;
     __syncthreads();
 
@@ -1554,12 +1564,44 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
         M.tfid[j] = id;
         M.key[j] = ((uint64_t)o.y << 32) | o.x;
     }
+    /* rank of (key, id): the keys are uniform 64-bit numbers, so they are first grouped by their top byte (a counting
+     * sort into M.bcnt, free until the bands are counted) and a family is then compared with the n / 256 families of
+     * its own group only — n^2 / 256 comparisons instead of n^2 */
+    for (uint32_t b = tid; b < 257u; b += nthr) X.bstart[b] = 0u;
+    __syncthreads();
+    for (uint32_t j = tid; j < n; j += nthr) atomicAdd(&X.bstart[1u + (uint32_t)(M.key[j] >> 56)], 1u);
+    __syncthreads();
+    if (tid < 32u) { /* exclusive scan of the 256 counts by the first warp: eight per lane */
+        uint32_t v[8], sum = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            v[k] = X.bstart[1u + 8u * lane + k];
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(DSIM_FULL, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            X.bcur[8u * lane + k] = run;
+            run += v[k];
+            X.bstart[1u + 8u * lane + k] = run; /* bstart[b + 1] = end of group b, bstart[0] stays 0 */
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < n; j += nthr) M.bcnt[atomicAdd(&X.bcur[(uint32_t)(M.key[j] >> 56)], 1u)] = j;
     __syncthreads();
     for (uint32_t j = tid; j < n; j += nthr) {
         const uint64_t kj = M.key[j], ij = M.tfid[j];
-        uint32_t r = 0;
-        for (uint32_t k = 0; k < n; ++k) {
-            const uint64_t kk = M.key[k], ik = M.tfid[k];
+        const uint32_t b = (uint32_t)(kj >> 56);
+        uint32_t r = X.bstart[b];
+        for (uint32_t k = X.bstart[b]; k < X.bstart[b + 1u]; ++k) {
+            const uint32_t o = M.bcnt[k];
+            const uint64_t kk = M.key[o], ik = M.tfid[o];
             r += (kk < kj || (kk == kj && ik < ij)) ? 1u : 0u;
         }
         M.idx[r] = M.tidx[j];
@@ -1577,11 +1619,45 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     /* ---- cooperate_or_fight, lib.rs:1380-1399; encounter_maybe_join, lib.rs:1209-1232 --------
      * A newcomer that is hostile to none of the members before it finds no hostile member in the first band, joins
      * it and changes nothing else: those are settled here, all at once.  Only the others walk the bands. */
-    for (uint32_t r = tid; r < n; r += nthr) {
-        const uint64_t c = M.cult[r];
-        bool h = false;
-        for (uint32_t j = 0; j < r; ++j) h |= !dsim_will_cooperate(c, M.cult[j], a.mc.threshold, a.mc.inclusive);
-        M.band[r] = h ? PATCH_TODO : 0u;
+    /* "hostile to a member before it" = hostile to a culture that FIRST appears before it.  Band members take their band's
+     * culture every step, so a node of a thousand families holds a handful of distinct cultures: the first warp lists
+     * them with their first positions (32 members per round), and every member is then tested against the list — n d
+     * tests instead of n^2 / 2.  A node with more than PATCH_DMAX cultures takes the quadratic test. */
+    if (tid < 32u) {
+        uint32_t d = 0;
+        for (uint32_t i0 = 0; i0 < n && d <= PATCH_DMAX; i0 += 32u) {
+            const bool in = i0 + lane < n;
+            const uint64_t c = in ? M.cult[i0 + lane] : 0ull;
+            bool fresh = in;
+            for (uint32_t k = 0; k < d && k < PATCH_DMAX; ++k) fresh = fresh && X.dcult[k] != c;
+            uint32_t m = __ballot_sync(DSIM_FULL, fresh);
+            while (m != 0u) { /* the new cultures of this round, in member order; equal ones collapse onto the first */
+                const int L = __ffs((int)m) - 1;
+                const uint64_t cL = __shfl_sync(DSIM_FULL, c, L);
+                if (d < PATCH_DMAX && lane == 0u) {
+                    X.dcult[d] = cL;
+                    X.dfirst[d] = i0 + (uint32_t)L;
+                }
+                ++d;
+                m &= ~__ballot_sync(DSIM_FULL, fresh && c == cL);
+            }
+            __syncwarp();
+        }
+        if (lane == 0u) X.dn = d;
+    }
+    __syncthreads();
+    {
+        const uint32_t d = X.dn;
+        for (uint32_t r = tid; r < n; r += nthr) {
+            const uint64_t c = M.cult[r];
+            bool h = false;
+            if (d <= PATCH_DMAX) {
+                for (uint32_t k = 0; k < d; ++k) h |= X.dfirst[k] < r && !dsim_will_cooperate(c, X.dcult[k], a.mc.threshold, a.mc.inclusive);
+            } else {
+                for (uint32_t j = 0; j < r; ++j) h |= !dsim_will_cooperate(c, M.cult[j], a.mc.threshold, a.mc.inclusive);
+            }
+            M.band[r] = h ? PATCH_TODO : 0u;
+        }
     }
     if (tid == 0) s_ctl[1] = 0u;
     __syncthreads();
@@ -1819,6 +1895,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
      * (every newcomer meets every member, lib.rs:1380-1399) — from shared memory, not from HBM scratch */
     DSIM_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_ctl[2];
+    __shared__ PatchAux s_aux;
     uint64_t *const s_u64 = reinterpret_cast<uint64_t *>(smem_raw);
     double *const s_f64 = reinterpret_cast<double *>(smem_raw + 5u * 8u * PATCH_M);
     uint32_t *const s_u32 = reinterpret_cast<uint32_t *>(smem_raw + 10u * 8u * PATCH_M);
@@ -1847,7 +1924,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
             M.stored = s_f64; M.contrib = s_f64 + PATCH_M; M.lh = s_f64 + 2u * PATCH_M; M.beff = s_f64 + 3u * PATCH_M;
             M.bcoef = s_f64 + 4u * PATCH_M;
             M.balive = s_u8;
-            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl);
+            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
         } else {
             M.idx = a.sc.x_idx + s0; M.tidx = a.sc.x_tidx + s0; M.size = a.sc.x_size + s0; M.band = a.sc.x_band + s0;
             M.bcnt = a.sc.x_bcnt + s0; M.btot = a.sc.x_btot + s0;
@@ -1856,7 +1933,7 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
             M.stored = a.sc.x_stored + s0; M.contrib = a.sc.x_contrib + s0; M.lh = a.sc.x_lh + s0;
             M.beff = a.sc.x_beff + s0; M.bcoef = a.sc.x_bcoef + s0;
             M.balive = a.sc.x_balive + s0;
-            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl);
+            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
         }
     }
     if (errors) atomicOr(&ctl->errors, errors);

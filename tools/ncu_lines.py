@@ -20,7 +20,8 @@ for b in blocks:
         r = list(r); r[1] = b["file"] + ": " + r[1]; m["rows"].append(r)
 for b in merged.values():
     h = b["hdr"]; isamp = h.index("# Samples"); iinst = h.index("Instructions Executed")
-    cols = {k: h.index(k) for k in ("stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_lg", "stall_math", "stall_no_inst", "stall_not_selected")}
+    cols = {k: h.index(k) for k in ("stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_lg", "stall_math", "stall_no_inst", "stall_not_selected",
+                                    "stall_barrier", "stall_membar", "stall_mio", "stall_dispatch", "stall_drain", "stall_sleep", "stall_selected", "stall_misc") if k in h}
     lines = []
     for r in b["rows"]:
         if r[0] == "": continue
