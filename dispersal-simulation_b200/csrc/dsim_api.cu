@@ -61,8 +61,8 @@ struct dsim_handle {
     dsim_params p;
     dsim_options opt;
     uint64_t seed = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr, join4_ev = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream5 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join3_ev = nullptr, join4_ev = nullptr, join5_ev = nullptr;
 #if !defined(DSIM_EMU)
     cudaAccessPolicyWindow l2_window = {}; /* views + band records pinned in the persisting part of L2 (num_bytes 0 = off) */
 #endif
@@ -103,7 +103,10 @@ struct dsim_handle {
     uint32_t parity = 0;
     bool mid_step = false;
     uint32_t steps_since_check = 0;
-    uint32_t check_interval = 1; /* steps that may be enqueued before the live count is read again (host_check) */
+    uint32_t check_interval = 1;
+    /* k_patch_huge (a whole SM's shared memory per block) joins the step when the host has seen a node of more than 512
+     * families at one of its looks at the control block; until then the step has one launch less */
+    bool huge_enabled = false; /* steps that may be enqueued before the live count is read again (host_check) */
     uint64_t n_known = 0; /* families at the last host check */
 
 #if !defined(DSIM_EMU)
@@ -251,6 +254,8 @@ StepArgs make_args(dsim_handle *h, uint32_t parity) {
     std::memset(&a.mg, 0, sizeof a.mg);
     a.small_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 8u;
     a.mid_max = (h->opt.flags & DSIM_OPT_PATCH_WARP_ONLY) ? 0u : 32u;
+    /* k_patch's shared-memory capacity (PATCH_M); larger nodes take k_patch_huge once the step includes it */
+    a.big_max = h->huge_enabled ? 512u : 0xFFFFFFFFu;
     return a;
 }
 
@@ -282,7 +287,7 @@ int alloc_families(dsim_handle *h, uint64_t new_cap) {
     A(ns.alive_bits, new_cap / 32 + 8) A(ns.split_bits, new_cap / 32 + 8) A(ns.word_pre, new_cap / 32 + 8)
     A(ns.blk_alive, new_cap / 256 + 1) A(ns.blk_split, new_cap / 256 + 1)
     A(ns.dead_hs, new_cap) A(ns.free_hs, hs_cap) A(ns.fslot, new_cap) A(ns.members, new_cap)
-    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_one, new_cap) A(ns.plist_small, new_cap) A(ns.plist_mid, new_cap) A(ns.plist_big, new_cap)
+    A(ns.occ[0], new_cap) A(ns.occ[1], new_cap) A(ns.plist_one, new_cap) A(ns.plist_small, new_cap) A(ns.plist_mid, new_cap) A(ns.plist_big, new_cap) A(ns.plist_huge, new_cap)
     A(ns.child_task, new_cap)
     A(ns.x_idx, new_cap) A(ns.x_tidx, new_cap) A(ns.x_size, new_cap) A(ns.x_band, new_cap)
     A(ns.x_bcnt, new_cap) A(ns.x_btot, new_cap)
@@ -380,6 +385,8 @@ int launch_patch_kernels(dsim_handle *h, const StepArgs &a) {
     CK(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
     CK(cudaStreamWaitEvent(h->stream3, h->fork_ev, 0));
     CK(cudaStreamWaitEvent(h->stream4, h->fork_ev, 0));
+    CK(cudaStreamWaitEvent(h->stream5, h->fork_ev, 0));
+    if (h->huge_enabled) dsim_launch_kernel(DSIM_K_PATCH_HUGE, a, h->geom, h->stream5); /* the few largest nodes are the longest pole: first */
     dsim_launch_kernel(DSIM_K_PATCH_SMALL, a, h->geom, h->stream);
     dsim_launch_kernel(DSIM_K_PATCH_ONE, a, h->geom, h->stream4);
     dsim_launch_kernel(DSIM_K_PATCH_MID, a, h->geom, h->stream3);
@@ -387,11 +394,13 @@ int launch_patch_kernels(dsim_handle *h, const StepArgs &a) {
     CK(cudaEventRecord(h->join_ev, h->stream2));
     CK(cudaEventRecord(h->join3_ev, h->stream3));
     CK(cudaEventRecord(h->join4_ev, h->stream4));
+    CK(cudaEventRecord(h->join5_ev, h->stream5));
+    CK(cudaStreamWaitEvent(h->stream, h->join5_ev, 0));
     CK(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
     CK(cudaStreamWaitEvent(h->stream, h->join3_ev, 0));
     CK(cudaStreamWaitEvent(h->stream, h->join4_ev, 0));
-    for (int k = DSIM_K_PATCH_ONE; k <= DSIM_K_PATCH; ++k) h->k_launches[k] += 1;
-    h->total_launches += 4;
+    for (int k = DSIM_K_PATCH_ONE; k <= (h->huge_enabled ? DSIM_K_PATCH_HUGE : DSIM_K_PATCH); ++k) h->k_launches[k] += 1;
+    h->total_launches += h->huge_enabled ? 5 : 4;
     return DSIM_OK;
 }
 
@@ -433,6 +442,7 @@ int launch_range(dsim_handle *h, int k0, int k1) { /* kernels [k0, k1) of one st
     const StepArgs a = make_args(h, h->parity);
     for (int k = k0; k < k1; ++k) {
         if (h->profiling) CK(cudaEventRecord(h->ev[k], h->stream));
+        if (k == DSIM_K_PATCH_HUGE && !h->huge_enabled) continue; /* not part of the step yet (see dsim_handle::huge_enabled) */
         dsim_launch_kernel(k, a, h->geom, h->stream);
         h->k_launches[k] += 1;
         h->total_launches += 1;
@@ -458,8 +468,9 @@ int launch_step(dsim_handle *h) {
             if (rc) return rc;
         }
         CK(cudaGraphLaunch(h->gexec[h->parity], h->stream));
-        for (int k = 0; k < DSIM_K_COUNT; ++k) h->k_launches[k] += 1;
-        h->total_launches += DSIM_K_COUNT;
+        const int n_k = h->huge_enabled ? DSIM_K_COUNT : DSIM_K_COUNT - 1; /* k_patch_huge is the last one */
+        for (int k = 0; k < n_k; ++k) h->k_launches[k] += 1;
+        h->total_launches += n_k;
         h->parity ^= 1u;
         return DSIM_OK;
     }
@@ -878,6 +889,8 @@ void dsim_destroy(dsim_handle *h) {
     if (h->join3_ev) cudaEventDestroy(h->join3_ev);
     if (h->join4_ev) cudaEventDestroy(h->join4_ev);
     if (h->stream4) cudaStreamDestroy(h->stream4);
+    if (h->join5_ev) cudaEventDestroy(h->join5_ev);
+    if (h->stream5) cudaStreamDestroy(h->stream5);
     free_list(h->reach_tmp);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_host) cudaFreeHost(h->stage_host);
@@ -963,10 +976,12 @@ int dsim_create(const dsim_params *p, const dsim_graph *g, uint64_t seed, const 
     }
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
     TRYCUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join3_ev, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&h->join4_ev, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&h->join5_ev, cudaEventDisableTiming));
     for (auto &e : h->ev) TRYCUDA(cudaEventCreate(&e));
     for (auto &e : h->tev) TRYCUDA(cudaEventCreate(&e));
     TRYCUDA(cudaMallocHost(&h->ctl_h, sizeof(DevCtl)));
@@ -1704,6 +1719,10 @@ static int host_check(dsim_handle *h) { /* read the live count, grow if the buff
     h->steps_since_check = 0;
     h->n_known = h->ctl_h->n_cur[h->parity];
     if (h->ctl_h->errors & DSIM_MODEL_CAPACITY) return fail(h, DSIM_ERR_CAPACITY, "family capacity exceeded during a batch of steps");
+    if (!h->huge_enabled && h->ctl_h->n_over > 0) { /* a node has outgrown k_patch's shared memory: add k_patch_huge to the step */
+        h->huge_enabled = true;
+        destroy_graphs(h);
+    }
     if ((rc = ensure_capacity(h, h->n_known))) return rc;
     /* How many steps may run before the next look at the live count: the growth per step seen since the last check,
      * squared for safety (1.25 while nothing has been seen: a family splits at most once per step, the usual rate is a
@@ -2063,6 +2082,7 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
 #endif
     m->halo_pending = false;
     h->mg_enabled = true;
+    h->huge_enabled = true; /* bands of a multi-GPU run are dense, and their step graphs are captured once */
     h->mg_lo = m->own_lo;
     h->mg_hi = m->own_hi;
     destroy_graphs(h);
@@ -2185,7 +2205,7 @@ static int mg_launch_phase(dsim_handle *h, dsim_mg_state *m, int phase, bool fus
     case DSIM_MG_PHASE_PATCH:
         M(DSIM_MGK_UNPACK, a2); K(DSIM_K_SEGMENTS, a2); K(DSIM_K_SCATTER, a2);
 #if defined(DSIM_EMU)
-        for (int k = DSIM_K_PATCH_ONE; k <= DSIM_K_PATCH; ++k) K(k, a2);
+        for (int k = DSIM_K_PATCH_ONE; k <= DSIM_K_PATCH_HUGE; ++k) K(k, a2);
 #else
         {
             int rc = launch_patch_kernels(h, a2);

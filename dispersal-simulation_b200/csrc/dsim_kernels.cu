@@ -210,6 +210,8 @@ __device__ __forceinline__ void control_tail(const StepArgs &a, uint32_t n, uint
         ctl->n_one = 0;
         ctl->n_mid = 0;
         ctl->n_big = 0;
+        ctl->n_huge = 0;
+        ctl->n_over = 0;
         ctl->births += n_children;
         ctl->deaths += n - n_alive;
         ctl->updates += n;
@@ -1392,7 +1394,7 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
      * atomics (profiles/r02_small_kernels.md). */
     DevCtl *ctl = a.ctl;
     dsim_pdl_wait();
-    __shared__ uint32_t s_tot[8][6], s_base[8][6];
+    __shared__ uint32_t s_tot[8][7], s_base[8][7];
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t n = ctl->n_next;
     const uint32_t n_round = (n + 255u) & ~255u; /* whole blocks take part in the barriers */
@@ -1408,11 +1410,16 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         const bool one = first && c == 1u && a.small_max >= 1u;
         const bool small = first && !one && c <= a.small_max;
         const bool mid = first && !one && !small && c <= a.mid_max;
-        const bool big = first && !one && !small && !mid;
+        /* nodes beyond k_patch's shared-memory capacity are counted for the host, which adds k_patch_huge to the step
+         * once it has seen one (a.big_max = PATCH_M from then on; until then they stay with k_patch and its HBM scratch) */
+        if (first && c > PATCH_M) atomicAdd(&ctl->n_over, 1u);
+        const bool huge = first && !one && !small && !mid && c > a.big_max;
+        const bool big = first && !one && !small && !mid && !huge;
         /* segment starts: exclusive scan of the counts; positions in the five lists: rank among the block's threads */
         const uint32_t incl = warp_incl_scan_u32(c, lane);
         const uint32_t m_first = __ballot_sync(DSIM_FULL, first), m_one = __ballot_sync(DSIM_FULL, one);
         const uint32_t m_small = __ballot_sync(DSIM_FULL, small), m_mid = __ballot_sync(DSIM_FULL, mid), m_big = __ballot_sync(DSIM_FULL, big);
+        const uint32_t m_huge = __ballot_sync(DSIM_FULL, huge);
         if (lane == 31u) {
             s_tot[w][0] = incl;
             s_tot[w][1] = (uint32_t)__popc(m_first);
@@ -1420,11 +1427,12 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
             s_tot[w][3] = (uint32_t)__popc(m_small);
             s_tot[w][4] = (uint32_t)__popc(m_mid);
             s_tot[w][5] = (uint32_t)__popc(m_big);
+            s_tot[w][6] = (uint32_t)__popc(m_huge);
         }
         __syncthreads();
-        if (threadIdx.x < 6u) { /* thread k: counter k — six atomics in flight together, one memory round trip per block */
+        if (threadIdx.x < 7u) { /* thread k: counter k — seven atomics in flight together, one memory round trip per block */
             uint32_t *counter = threadIdx.x == 0u ? &ctl->seg_cursor : threadIdx.x == 1u ? &ctl->n_occ[a.occ_par] : threadIdx.x == 2u ? &ctl->n_one
-                                : threadIdx.x == 3u ? &ctl->n_small : threadIdx.x == 4u ? &ctl->n_mid : &ctl->n_big;
+                                : threadIdx.x == 3u ? &ctl->n_small : threadIdx.x == 4u ? &ctl->n_mid : threadIdx.x == 5u ? &ctl->n_big : &ctl->n_huge;
             uint32_t tot = 0;
             for (uint32_t k = 0; k < 8u; ++k) tot += s_tot[k][threadIdx.x];
             uint32_t base = tot ? atomicAdd(counter, tot) : 0u;
@@ -1443,6 +1451,7 @@ __global__ void __launch_bounds__(256) k_segments(StepArgs a) {
         if (small) a.sc.plist_small[s_base[w][3] + (uint32_t)__popc(m_small & below)] = p;
         if (mid) a.sc.plist_mid[s_base[w][4] + (uint32_t)__popc(m_mid & below)] = p;
         if (big) a.sc.plist_big[s_base[w][5] + (uint32_t)__popc(m_big & below)] = p;
+        if (huge) a.sc.plist_huge[s_base[w][6] + (uint32_t)__popc(m_huge & below)] = p;
     }
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (a.mg.enabled) return; /* the multi-GPU step recycles heavy slots in k_mg_finish (emigrants, immigrants) */
@@ -1550,9 +1559,10 @@ struct PatchAux {
     uint32_t dfirst[PATCH_DMAX]; /* ... and where they first appear */
     uint32_t dn;
 };
+template <uint32_t NW> /* warps of the block that works on the node */
 __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t tid,
                                            uint32_t step, const dsim_stream rs, double season, uint32_t &errors, uint32_t *s_ctl, PatchAux &X) {
-    const uint32_t lane = tid & 31u, nthr = PATCH_WARPS * 32u;
+    const uint32_t lane = tid & 31u, nthr = NW * 32u;
     __syncthreads();
 
     /* ---- stochasticity::shuffle (lib.rs:1376): order by (keyed random number, id) ----------- */
@@ -1694,7 +1704,19 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                             dy = o.y < a.mc.deadliness; /* lib.rs:1226 */
                         }
                         const uint32_t mdx = __ballot_sync(DSIM_FULL, dx), mdy = __ballot_sync(DSIM_FULL, dy);
+                        /* Fights that cannot change anything are not replayed: neither draw deadly; or only the newcomer's
+                         * side deadly against a member of size 0 (reduction 0).  Once the newcomer itself is down to size 0
+                         * every reduction is 0, and only a deadly draw against a size-0 member (whose stores then pass to the
+                         * newcomer) still has an effect.  On a node of a thousand families most fights are of these kinds. */
+                        const uint32_t mz0 = __ballot_sync(DSIM_FULL, hostile && so_mine == 0u);
+                        mask &= mdx | (mdy & ~mz0);
+                        bool pruned = false;
                         while (mask != 0u) {
+                            if (sz == 0u && !pruned) {
+                                mask &= mdx & __ballot_sync(DSIM_FULL, hostile && so_mine == 0u);
+                                pruned = true;
+                                if (mask == 0u) break;
+                            }
                             const uint32_t l = (uint32_t)(__ffs((int)mask) - 1);
                             mask &= mask - 1u;
                             const uint32_t so = __shfl_sync(DSIM_FULL, so_mine, l);
@@ -1731,29 +1753,40 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     const uint32_t nb = s_ctl[0];
 
     /* ---- band culture = culture of a random member; drop empty bands, lib.rs:1400-1416 -------- */
-    for (uint32_t B = tid; B < nb; B += nthr) {
+    /* a WARP per band (a thread per band walked all n members twice while the rest of the block waited): the lanes take
+     * 32 members at a time, ballots count the band's members and find the pick-th one in join order */
+    for (uint32_t B = tid >> 5; B < nb; B += nthr >> 5) {
         uint32_t cnt = 0, tot = 0;
-        for (uint32_t j = 0; j < n; ++j)
-            if (M.band[j] == B) {
-                cnt += 1u;
-                tot += M.size[j];
-            }
+        for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
+            const uint32_t j = j0 + lane;
+            const bool in = j < n && M.band[j] == B;
+            cnt += (uint32_t)__popc(__ballot_sync(DSIM_FULL, in));
+            tot += in ? M.size[j] : 0u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(DSIM_FULL, tot, d);
         const dsim_u4 o = dsim_draw(rs, step, (uint64_t)p, DSIM_P_PIVOT, B);
         const uint32_t pick = (uint32_t)__umul64hi(((uint64_t)o.y << 32) | o.x, (uint64_t)cnt);
         uint64_t c = 0;
         uint32_t seen = 0;
-        for (uint32_t j = 0; j < n; ++j)
-            if (M.band[j] == B) {
-                if (seen == pick) {
-                    c = M.cult[j];
-                    break;
-                }
-                ++seen;
+        for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
+            const uint32_t j = j0 + lane;
+            const bool in = j < n && M.band[j] == B;
+            uint32_t m = __ballot_sync(DSIM_FULL, in);
+            const uint32_t k = (uint32_t)__popc(m);
+            if (seen + k > pick) { /* the (pick - seen)-th member of this round */
+                for (uint32_t skip = pick - seen; skip > 0u; --skip) m &= m - 1u;
+                c = __shfl_sync(DSIM_FULL, in ? M.cult[j] : 0ull, __ffs((int)m) - 1);
+                break;
             }
-        M.bcult[B] = c;
-        M.bcnt[B] = cnt;
-        M.btot[B] = tot;
-        M.balive[B] = tot > 0u ? 1 : 0;
+            seen += k;
+        }
+        if (lane == 0u) {
+            M.bcult[B] = c;
+            M.bcnt[B] = cnt;
+            M.btot[B] = tot;
+            M.balive[B] = tot > 0u ? 1 : 0;
+        }
     }
     __syncthreads();
 
@@ -1811,12 +1844,21 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             M.contrib[r] = c;
         }
         __syncthreads();
-        for (uint32_t B = tid; B < nb; B += nthr) { /* sum_effort in join order */
+        for (uint32_t B = tid >> 5; B < nb; B += nthr >> 5) { /* sum_effort in join order, a warp per band */
             double eff = 0.0;
             if (M.balive[B])
-                for (uint32_t j = 0; j < n; ++j)
-                    if (M.band[j] == B) eff = eff + M.contrib[j];
-            M.beff[B] = eff;
+                for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
+                    const uint32_t j = j0 + lane;
+                    const bool in = j < n && M.band[j] == B;
+                    const double cj = in ? M.contrib[j] : 0.0;
+                    uint32_t m = __ballot_sync(DSIM_FULL, in);
+                    while (m != 0u) { /* the band's members of this round, one sequential add each (lib.rs:2040-2047) */
+                        const int l = __ffs((int)m) - 1;
+                        m &= m - 1u;
+                        eff = eff + __shfl_sync(DSIM_FULL, cj, l);
+                    }
+                }
+            if (lane == 0u) M.beff[B] = eff;
         }
         __syncthreads();
         double total_squared = 1.0;
@@ -1887,44 +1929,56 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
     }
 }
 
-/* shared-memory working set of one node of up to PATCH_M families: 105 bytes per family */
-#define PATCH_SMEM_BYTES (PATCH_M * (6u * 4u + 5u * 8u + 5u * 8u + 1u))
+/* shared-memory working set of one node of up to MC families: 105 bytes per family */
+#define PATCH_SMEM_BYTES_OF(MC) ((MC) * (6u * 4u + 5u * 8u + 5u * 8u + 1u))
+#define PATCH_SMEM_BYTES PATCH_SMEM_BYTES_OF(PATCH_M)
+#ifndef PATCH_HUGE_WARPS
+#define PATCH_HUGE_WARPS 16u /* k_patch_huge: a block of sixteen warps per node with more than PATCH_M families ... */
+#endif
+#ifndef PATCH_HUGE_BLOCKS
+#define PATCH_HUGE_BLOCKS 32u
+#endif
+#ifndef PATCH_HUGE_M
+#define PATCH_HUGE_M 2048u   /* ... its working arrays in 210 KB of shared memory (one block per SM); HBM scratch beyond */
+#endif
 
-__global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(StepArgs a) {
-    /* one block per node: crowded nodes are few, and a node of hundreds of families walks its member arrays n times
-     * (every newcomer meets every member, lib.rs:1380-1399) — from shared memory, not from HBM scratch */
+/* One block of NW warps per node of the list: crowded nodes are few, and a node of hundreds of families walks its member
+ * arrays many times (every hostile newcomer meets every member, lib.rs:1380-1399) — from shared memory (up to MC
+ * families), not from HBM scratch.  Two instances: k_patch (4 warps, 512 families, four blocks per SM) for nodes of
+ * 33..512 families, k_patch_huge (16 warps, 2048 families, one block per SM) for the few nodes beyond — after 10^4 seasons
+ * of the continental configuration 28 nodes hold 500..1 400 families each, and a block of four warps spent a millisecond
+ * per step on the largest of them. */
+template <uint32_t NW, uint32_t MC>
+__device__ __forceinline__ void patch_block(const StepArgs &a, const uint32_t *plist, uint32_t n_list) {
     DSIM_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_ctl[2];
     __shared__ PatchAux s_aux;
     uint64_t *const s_u64 = reinterpret_cast<uint64_t *>(smem_raw);
-    double *const s_f64 = reinterpret_cast<double *>(smem_raw + 5u * 8u * PATCH_M);
-    uint32_t *const s_u32 = reinterpret_cast<uint32_t *>(smem_raw + 10u * 8u * PATCH_M);
-    uint8_t *const s_u8 = smem_raw + 10u * 8u * PATCH_M + 6u * 4u * PATCH_M;
+    double *const s_f64 = reinterpret_cast<double *>(smem_raw + 5u * 8u * MC);
+    uint32_t *const s_u32 = reinterpret_cast<uint32_t *>(smem_raw + 10u * 8u * MC);
+    uint8_t *const s_u8 = smem_raw + 10u * 8u * MC + 6u * 4u * MC;
 
     DevCtl *ctl = a.ctl;
-    dsim_pdl_wait();
     const uint32_t step = ctl->t;
     const uint32_t tid = threadIdx.x;
-    const uint32_t gwarp = blockIdx.x, nwarps = gridDim.x;
-    const uint32_t n_big = ctl->n_big;
     const dsim_stream rs = stream_of(a.mc);
     const double season = a.mc.season;
     uint32_t errors = 0;
 
-    for (uint32_t vw = gwarp; vw < n_big; vw += nwarps) {
-        const uint32_t p = a.sc.plist_big[vw];
+    for (uint32_t vw = blockIdx.x; vw < n_list; vw += gridDim.x) {
+        const uint32_t p = plist[vw];
         const uint32_t n = a.ps.cnt[p];
         const uint32_t s0 = a.ps.seg[p];
         PatchMem M;
-        if (n <= PATCH_M) {
-            M.idx = s_u32; M.tidx = s_u32 + PATCH_M; M.size = s_u32 + 2u * PATCH_M; M.band = s_u32 + 3u * PATCH_M;
-            M.bcnt = s_u32 + 4u * PATCH_M; M.btot = s_u32 + 5u * PATCH_M;
-            M.key = s_u64; M.fid = s_u64 + PATCH_M; M.tfid = s_u64 + 2u * PATCH_M; M.cult = s_u64 + 3u * PATCH_M;
-            M.bcult = s_u64 + 4u * PATCH_M;
-            M.stored = s_f64; M.contrib = s_f64 + PATCH_M; M.lh = s_f64 + 2u * PATCH_M; M.beff = s_f64 + 3u * PATCH_M;
-            M.bcoef = s_f64 + 4u * PATCH_M;
+        if (n <= MC) {
+            M.idx = s_u32; M.tidx = s_u32 + MC; M.size = s_u32 + 2u * MC; M.band = s_u32 + 3u * MC;
+            M.bcnt = s_u32 + 4u * MC; M.btot = s_u32 + 5u * MC;
+            M.key = s_u64; M.fid = s_u64 + MC; M.tfid = s_u64 + 2u * MC; M.cult = s_u64 + 3u * MC;
+            M.bcult = s_u64 + 4u * MC;
+            M.stored = s_f64; M.contrib = s_f64 + MC; M.lh = s_f64 + 2u * MC; M.beff = s_f64 + 3u * MC;
+            M.bcoef = s_f64 + 4u * MC;
             M.balive = s_u8;
-            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
+            patch_node<NW>(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
         } else {
             M.idx = a.sc.x_idx + s0; M.tidx = a.sc.x_tidx + s0; M.size = a.sc.x_size + s0; M.band = a.sc.x_band + s0;
             M.bcnt = a.sc.x_bcnt + s0; M.btot = a.sc.x_btot + s0;
@@ -1933,10 +1987,19 @@ __global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(St
             M.stored = a.sc.x_stored + s0; M.contrib = a.sc.x_contrib + s0; M.lh = a.sc.x_lh + s0;
             M.beff = a.sc.x_beff + s0; M.bcoef = a.sc.x_bcoef + s0;
             M.balive = a.sc.x_balive + s0;
-            patch_node(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
+            patch_node<NW>(a, M, p, n, s0, tid, step, rs, season, errors, s_ctl, s_aux);
         }
     }
     if (errors) atomicOr(&ctl->errors, errors);
+}
+
+__global__ void __launch_bounds__(PATCH_WARPS * 32, PATCH_MIN_BLOCKS) k_patch(StepArgs a) {
+    dsim_pdl_wait();
+    patch_block<PATCH_WARPS, PATCH_M>(a, a.sc.plist_big, a.ctl->n_big);
+}
+__global__ void __launch_bounds__(PATCH_HUGE_WARPS * 32, 1) k_patch_huge(StepArgs a) {
+    dsim_pdl_wait();
+    patch_block<PATCH_HUGE_WARPS, PATCH_HUGE_M>(a, a.sc.plist_huge, a.ctl->n_huge);
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -2279,6 +2342,10 @@ void dsim_launch_kernel(int which, const StepArgs &a, const LaunchGeom &g, cudaS
     case DSIM_K_PATCH_SMALL: STEP_LAUNCH(k_patch_small, grid_for(g, 2 * PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
     case DSIM_K_PATCH_MID: STEP_LAUNCH(k_patch_mid, grid_for(g, PATCH_SMALL_MIN_BLOCKS), 128, 0); break;
     case DSIM_K_PATCH: STEP_LAUNCH(k_patch, grid_for(g, PATCH_MIN_BLOCKS), PATCH_WARPS * 32, PATCH_SMEM_BYTES); break;
+    case DSIM_K_PATCH_HUGE: /* a block takes a whole SM's shared memory: few blocks (the nodes of this class are few), so that the other patch
+                             * kernels keep most SMs while this one finds out whether it has anything to do */
+        STEP_LAUNCH(k_patch_huge, PATCH_HUGE_BLOCKS, PATCH_HUGE_WARPS * 32, PATCH_SMEM_BYTES_OF(PATCH_HUGE_M));
+        break;
     default: break;
     }
 #undef STEP_LAUNCH
@@ -2303,6 +2370,8 @@ int dsim_configure_kernels(LaunchGeom *g) {
     (void)g;
 #if !defined(DSIM_EMU)
     cudaError_t e = cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_patch_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_SMEM_BYTES_OF(PATCH_HUGE_M));
     if (e != cudaSuccess) return (int)e;
 #endif
     return 0;

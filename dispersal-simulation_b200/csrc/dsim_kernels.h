@@ -21,6 +21,7 @@ struct StepArgs {
     MgInfo mg;
     uint32_t mid_max;   /* nodes with small_max < n <= mid_max families take k_patch_mid (a warp per node) */
     uint32_t small_max; /* nodes with <= small_max families take the thread-per-node kernel (<= PATCH_SMALL_MAX) */
+    uint32_t big_max;   /* nodes with mid_max < n <= big_max families take k_patch, larger ones k_patch_huge */
 };
 
 struct LaunchGeom {
@@ -47,11 +48,12 @@ enum {
     DSIM_K_PATCH_SMALL,
     DSIM_K_PATCH_MID,
     DSIM_K_PATCH,
+    DSIM_K_PATCH_HUGE,
     DSIM_K_COUNT
 };
 
 static const char *const dsim_kernel_names[DSIM_K_COUNT] = {"k_lifecycle", "k_move",  "k_children", "k_segments",
-                                                            "k_scatter",   "k_patch_one", "k_patch_small", "k_patch_mid", "k_patch"};
+                                                            "k_scatter",   "k_patch_one", "k_patch_small", "k_patch_mid", "k_patch", "k_patch_huge"};
 
 enum { DSIM_MGK_SPLIT_IDS = 0, DSIM_MGK_SORT_OUT, DSIM_MGK_PACK, DSIM_MGK_UNPACK, DSIM_MGK_HALO_PACK, DSIM_MGK_HALO_UNPACK, DSIM_MGK_FINISH,
        DSIM_MGK_BUMP };

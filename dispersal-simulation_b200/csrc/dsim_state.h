@@ -133,7 +133,8 @@ struct StepScratch {
     uint32_t *plist_one;    /* [cap] occupied nodes with exactly one family (a thread per node)              */
     uint32_t *plist_small;  /* [cap] occupied nodes with 2..8 families (eight lanes per node)                 */
     uint32_t *plist_mid;    /* [cap] occupied nodes with 9..32 families (a warp per node, registers only)    */
-    uint32_t *plist_big;    /* [cap] the others (a block per node, shared memory / HBM scratch)             */
+    uint32_t *plist_big;    /* [cap] nodes with 33..512 families (a block of four warps per node, shared memory)   */
+    uint32_t *plist_huge;   /* [cap] the others (a block of sixteen warps per node, shared memory / HBM scratch)   */
     ChildTask *child_task;  /* [cap] indexed by child rank                                          */
     /* patch-kernel spill arrays for nodes with more families than fit in shared memory, indexed
      * by segment position */
@@ -157,6 +158,7 @@ struct DevCtl {              /* one instance in device memory */
     uint32_t life_done;      /* blocks of k_lifecycle that have finished (the last one scans and resets it) */
     uint32_t move_next;      /* next tile of k_move to hand out (reset by the tail of k_lifecycle)           */
     uint32_t advance_pending;/* the end-of-step bookkeeping of the last step is still due (dsim_apply_advance)      */
+    uint32_t n_huge, n_over; /* length of plist_huge; nodes with more families than k_patch holds in shared memory (this step) */
     uint32_t serial;         /* steps begun on this handle, never reset: tags the ChildTasks of a step (ChildTask.ready) */
     uint64_t child_id_base, next_id;
     uint64_t births, deaths, updates;

@@ -46,7 +46,8 @@ def test_growth_and_splits(oracle, emu, synth):
 
 
 def test_dense_coresidence_spill_path(oracle, emu, synth):
-    """Nodes with more families than k_patch holds in shared memory (512): the HBM scratch path."""
+    """Nodes with more families than k_patch holds in shared memory (512): k_patch_huge, a block of sixteen warps per node
+    (its HBM scratch path, beyond 2048 families, is exercised by the tiny-capacity build below)."""
     o, d = pc.build_pair(oracle, emu, synth, 30, 40, 3600, n_occupied=5, hist_cap=96)
     f = o.get_families(history=False, adaptation=False)
     assert np.unique(f.location, return_counts=True)[1].max() > 512, "scenario must exceed the shared-memory path"
@@ -186,6 +187,9 @@ def peaceful(p):
     p.cooperation_threshold = 65
 o, d = pc.build_pair(oracle, emu_small, synth, 24, 30, 120, params_edit=peaceful, hist_cap=96)
 pc.run_lockstep(o, d, 30, by_parts=False, hist_cap=96, check_every=5)
+# nodes of ~720 families: beyond this build's shared-memory capacity of k_patch_huge (600): its HBM scratch path
+o, d = pc.build_pair(oracle, emu_small, synth, 30, 40, 3600, n_occupied=5, hist_cap=96)
+pc.run_lockstep(o, d, 2, hist_cap=96)
 print("tiny capacities ok")
 """ % os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
