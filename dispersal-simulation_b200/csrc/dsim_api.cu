@@ -1958,6 +1958,7 @@ struct dsim_mg_state {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 #endif
     bool nccl = false, graph_failed = false, p2p = false;
+    bool graph_huge = false; /* the captured steps include k_patch_huge (dsim_handle::huge_enabled at capture time) */
     std::vector<void *> ipc_opened;
     cudaEvent_t seg_ev[8] = {};
     cudaEvent_t life_ev = nullptr, split_ev = nullptr; /* edges of the rotated step (mg_enqueue_step) */
@@ -2082,7 +2083,6 @@ int dsim_mg_configure(dsim_handle *h, uint32_t rank, uint32_t world, const uint3
 #endif
     m->halo_pending = false;
     h->mg_enabled = true;
-    h->huge_enabled = true; /* bands of a multi-GPU run are dense, and their step graphs are captured once */
     h->mg_lo = m->own_lo;
     h->mg_hi = m->own_hi;
     destroy_graphs(h);
@@ -2428,6 +2428,14 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
         return fail(h, DSIM_ERR_COMM, "no transport: call dsim_mg_init_nccl or dsim_mg_ipc_connect, or drive dsim_mg_phase yourself");
     int rc = DSIM_OK;
     if (h->opt.use_graphs && !m->graph_failed && !h->profiling) {
+        if (m->graph_huge != h->huge_enabled) { /* k_patch_huge has joined the step: capture again */
+            for (auto &g : m->gexec)
+                if (g) {
+                    cudaGraphExecDestroy(g);
+                    g = nullptr;
+                }
+            m->graph_huge = h->huge_enabled;
+        }
         if (!m->gexec[m->occ_par]) {
             cudaGraph_t g = nullptr;
             const uint64_t launches0 = h->total_launches;
