@@ -46,3 +46,26 @@ for k in want:
                 n = sum(c for o, c in ops.items() if any(o.startswith(p) for p in pats))
                 print(f"* {label}: {n}")
             print()
+
+# ---- excerpts of k_move: the instructions that show what the kernel is built from ------------------------------------
+def clean(l):
+    return re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip()
+km = next((lines for f, lines in funcs.items() if re.fullmatch(r"_Z\d+k_move8StepArgs.*", f)), None)
+if km:
+    def at(pred, before=0, after=1, which=0):
+        ks = [n for n, l in enumerate(km) if pred(l)]
+        if not ks:
+            return ["(not found in this build)"]
+        k = ks[min(which, len(ks) - 1)]
+        return [clean(l) for l in km[max(0, k - before):k + after]]
+    best = max(range(max(1, len(km) - 14)), key=lambda k: sum(("-0x2daee0ad" in l or "-0x326172a9" in l) for l in km[k:k + 14]))
+    print("## `k_move` excerpts (`cuobjdump -sass`)\n")
+    print("Prologue: the packed family record (128-bit loads):\n\n```\n" + "\n".join(at(lambda l: "LDG.E.128" in l, 0, 1) + at(lambda l: "LDG.E.128" in l, 0, 1, 1)) + "\n```\n")
+    print("TMA bulk copy of a reach-row column into shared memory (one elected lane per column), completion on the warp's mbarrier:\n\n```\n"
+          + "\n".join(at(lambda l: "UBLKCP" in l, 6, 2)) + "\n```\n")
+    print("Waiting for it:\n\n```\n" + "\n".join(at(lambda l: "SYNCS" in l and "TRYWAIT" in l)) + "\n```\n")
+    print("Philox rounds (per round two 32x32->64 multiplies `IMAD.WIDE.U32` by the Philox multipliers 0xD2511F53 / 0xCD9E8D57 and two "
+          "3-input XORs `LOP3.LUT ... 0x96` with the round key: 40 instructions per block of four words):\n\n```\n"
+          + "\n".join(clean(l) for l in km[best:best + 14]) + "\n```\n")
+    print("A 16-byte candidate view gathered straight into shared memory (cp.async = `LDGSTS`, with the L2 eviction-priority descriptor):\n\n```\n"
+          + "\n".join(at(lambda l: "LDGSTS.E.128" in l)) + "\n```")
