@@ -1722,6 +1722,7 @@ static int host_check(dsim_handle *h) { /* read the live count, grow if the buff
     if (!h->huge_enabled && h->ctl_h->n_over > 0) { /* a node has outgrown k_patch's shared memory: add k_patch_huge to the step */
         h->huge_enabled = true;
         destroy_graphs(h);
+        if (std::getenv("DSIM_DEBUG")) std::fprintf(stderr, "[dsim] a node holds more than 512 families: k_patch_huge joins the step (t = %u)\n", h->ctl_h->t);
     }
     if ((rc = ensure_capacity(h, h->n_known))) return rc;
     /* How many steps may run before the next look at the live count: the growth per step seen since the last check,
@@ -2437,6 +2438,7 @@ int dsim_mg_step_enqueue(dsim_handle *h) {
             m->graph_huge = h->huge_enabled;
         }
         if (!m->gexec[m->occ_par]) {
+            if (std::getenv("DSIM_DEBUG")) std::fprintf(stderr, "[dsim] rank %u: capturing the multi-GPU step (parity %u)\n", m->rank, m->occ_par);
             cudaGraph_t g = nullptr;
             const uint64_t launches0 = h->total_launches;
             bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
