@@ -73,6 +73,24 @@ def test_crowded_nodes_many_hostile_bands(oracle, emu, synth):
     pc.run_lockstep(o, d, 3, hist_cap=96)
 
 
+@pytest.mark.parametrize("n_cultures", [63, 64, 65, 70])
+def test_crowded_nodes_around_the_culture_list_limit(oracle, emu, synth, n_cultures):
+    """k_patch tests a newcomer against the node's DISTINCT cultures, listed in shared memory up to 64 of them; one more and
+    the node takes the quadratic test against every earlier member.  Both sides of the limit, on nodes of ~250 families
+    that hold every culture."""
+    def round_robin(fam):
+        rng = np.random.default_rng(11)
+        pool = rng.integers(0, 1 << 63, n_cultures, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n_cultures, dtype=np.uint64)
+        for node in np.unique(fam.location):
+            members = np.nonzero(fam.location == node)[0]
+            fam.culture[members] = pool[np.arange(len(members)) % n_cultures]
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=round_robin)
+    f = o.get_families(history=False, adaptation=False)
+    top = np.bincount(f.location).argmax()
+    assert len(np.unique(f.culture[f.location == top])) == n_cultures, "the largest node must hold exactly that many cultures"
+    pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)
+
+
 def test_mid_sized_nodes(oracle, emu, synth):
     """Nodes with 9..32 families (k_patch_mid: a warp per node, lane per family), hostile neighbours included."""
     o, d = pc.build_pair(oracle, emu, synth, 20, 24, 1500, n_occupied=80, hist_cap=96)
