@@ -164,3 +164,39 @@ def test_step_timed_counts_only_its_own_steps(oracle, emu, synth):
     so2 = o.step(3)                                   # and again, after a stats-carrying call
     sd2, _ = d.step_timed(3)
     assert (sd2.family_updates, sd2.births, sd2.deaths) == (so2.family_updates, so2.births, so2.deaths)
+
+
+def test_get_families_into_caller_buffers(emu, synth):
+    """get_families(out=): the core columns land in caller-owned arrays (a checkpoint writer's reusable buffers) and equal
+    a fresh download; too small a buffer and a request for histories are refused."""
+    s, g, *_ = _sim(emu, synth)
+    s.set_families(D.synth_families(12, 14, 50, 2, hist_fill=3, lib=synth))
+    s.step(3, allow_model_errors=True)
+    a = s.get_families(history=False, adaptation=False)
+    buf = D.Families.empty(200)
+    b = s.get_families(history=False, adaptation=False, out=buf)
+    assert b.n == a.n and len(b.id) == a.n
+    for name, _ in D._FAM_FIELDS:
+        assert (getattr(a, name) == getattr(b, name)).all(), name
+        assert np.shares_memory(getattr(b, name), getattr(buf, name))
+    with pytest.raises(ValueError):
+        s.get_families(history=False, adaptation=False, out=D.Families.empty(max(1, a.n - 1)))
+    with pytest.raises(ValueError):
+        s.get_families(history=True, adaptation=False, out=buf)
+
+
+def test_short_history_ring_needs_the_flag(emu, synth):
+    """A history ring shorter than what the memory loop of lib.rs:854-866 can sample changes decisions silently once a
+    history outgrows it: dsim_create refuses it unless DSIM_OPT_SHORT_HISTORY says the caller knows."""
+    g, _, _ = D.synth_grid(8, 8, 1, lib=synth)
+    opt = D.Options()
+    emu.dsim_default_options(C.byref(opt))
+    opt.history_capacity = 96
+    with pytest.raises(D.DsimError) as e:
+        D.Sim(emu, g, seed=1, options=opt)
+    assert e.value.code == -1
+    opt.flags |= D.OPT_SHORT_HISTORY
+    D.Sim(emu, g, seed=1, options=opt).close()
+    opt.flags = 0
+    opt.history_capacity = 0              # exact
+    D.Sim(emu, g, seed=1, options=opt).close()
