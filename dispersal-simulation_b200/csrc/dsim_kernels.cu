@@ -1552,12 +1552,31 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
  * O(n^2) on a node of hundreds or thousands of families (the long-run regime of the continental grid: nodes of 1 400
  * families after 10^4 seasons) — the rank sort of the shuffle and the "hostile to an earlier member" test. */
 #define PATCH_DMAX 64u /* distinct cultures of a node listed in shared memory (beyond: the quadratic test) */
+#ifndef PATCH_ECAP
+/* (band, culture) pairs of a node listed for the walk.  While a culture cooperates with itself, its members all end up in
+ * one band (a later member finds the bands before it as hostile as the earlier one did, and that one's band still without
+ * a hostile member, since whoever joined it since cooperates with the culture), so there are as many pairs as cultures;
+ * only cooperation_threshold 0, exclusive, spreads a culture over bands: then the list overflows and every band is scanned. */
+#define PATCH_ECAP 64u
+#endif
+#if defined(DSIM_EMU) /* the CPU debugging build counts the shortcuts of the walk, so that its tests can tell they were taken */
+extern "C" unsigned long long dsim_walk_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define WALK_STAT(k) do { if (lane == 0u) __atomic_fetch_add(&dsim_walk_stats[k], 1ull, __ATOMIC_RELAXED); } while (0)
+#else
+#define WALK_STAT(k) do { } while (0)
+#endif
 struct PatchAux {
     uint32_t bstart[257]; /* rank sort: keys bucketed by their top byte */
     uint32_t bcur[256];
     uint64_t dcult[PATCH_DMAX]; /* distinct cultures in order of first appearance in the shuffled order ... */
     uint32_t dfirst[PATCH_DMAX]; /* ... and where they first appear */
     uint32_t dn;
+    /* the walk of the hostile newcomers: (band, culture) pairs met so far with the position of the first such member,
+     * and per band the number of members of size 0 whose stores are not +0.0 (a deadly draw still moves those) */
+    uint64_t ecult[PATCH_ECAP];
+    uint32_t eband[PATCH_ECAP];
+    uint32_t efirst[PATCH_ECAP];
+    uint32_t deadnz[PATCH_ECAP];
 };
 template <uint32_t NW> /* warps of the block that works on the node */
 __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M, uint32_t p, uint32_t n, uint32_t s0, uint32_t tid,
@@ -1654,6 +1673,7 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             __syncwarp();
         }
         if (lane == 0u) X.dn = d;
+        for (uint32_t k = lane; k < PATCH_ECAP; k += 32u) X.deadnz[k] = 0u;
     }
     __syncthreads();
     {
@@ -1667,12 +1687,38 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                 for (uint32_t j = 0; j < r; ++j) h |= !dsim_will_cooperate(c, M.cult[j], a.mc.threshold, a.mc.inclusive);
             }
             M.band[r] = h ? PATCH_TODO : 0u;
+            if (!h && M.size[r] == 0u && dsim_f64_to_bits(M.stored[r]) != 0ull) atomicAdd(&X.deadnz[0], 1u);
         }
     }
     if (tid == 0) s_ctl[1] = 0u;
     __syncthreads();
     if (tid < 32u) { /* the first warp: hostile newcomers one after the other */
-        uint32_t nb = 1;
+        /* A newcomer walks the bands in creation order and fights every hostile member of a band before it moves on
+         * (lib.rs:1380-1399).  On a node of a thousand families that was a scan of all earlier members per band and
+         * newcomer.  Two facts shorten it without changing a result: (1) whether a band holds a hostile member follows
+         * from the (band, culture) pairs met so far — a few dozen, tested by the lanes in one round; a band without one
+         * is joined without a scan; (2) a newcomer that is down to size 0 changes nothing in a fight (every reduction
+         * is 0) unless the member is itself of size 0 and still holds stores, which deadnz counts per band: a hostile
+         * band without such a member is passed without a scan, and a scan stops at the chunk where the newcomer died.
+         * sm: the pair list is complete (it is given up, for the rest of the node, if it outgrows PATCH_ECAP). */
+        uint32_t nb = 1, en = 0;
+        bool sm = X.dn <= PATCH_DMAX && X.dn <= PATCH_ECAP;
+        if (sm) { /* band 0 so far: the settled members; a culture has settled members iff its first member is settled */
+            const uint32_t d = X.dn;
+            for (uint32_t k0 = 0; k0 < d; k0 += 32u) {
+                const uint32_t k = k0 + lane;
+                const bool in0 = k < d && M.band[X.dfirst[k]] == 0u;
+                const uint32_t m = __ballot_sync(DSIM_FULL, in0);
+                if (in0) {
+                    const uint32_t e = en + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    X.ecult[e] = X.dcult[k];
+                    X.eband[e] = 0u;
+                    X.efirst[e] = X.dfirst[k];
+                }
+                en += (uint32_t)__popc(m);
+            }
+            __syncwarp();
+        }
         for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
             uint32_t todo = __ballot_sync(DSIM_FULL, i0 + lane < n && M.band[i0 + lane] == PATCH_TODO);
             while (todo != 0u) {
@@ -1682,8 +1728,35 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                 uint32_t sz = M.size[i];
                 double st = M.stored[i];
                 int joined = -1;
+                /* the bands of the listed pairs this newcomer is hostile to, two pairs per lane (a settled member of
+                 * band 0 that comes after the newcomer is not there yet for it: efirst) */
+                uint32_t hband[PATCH_ECAP / 32u];
+#pragma unroll
+                for (uint32_t k = 0; k < PATCH_ECAP / 32u; ++k) {
+                    const uint32_t e = lane + 32u * k;
+                    hband[k] = 0xFFFFFFFFu;
+                    if (sm && e < en && X.efirst[e] < i && !dsim_will_cooperate(cf, X.ecult[e], a.mc.threshold, a.mc.inclusive))
+                        hband[k] = X.eband[e];
+                }
                 for (uint32_t B = 0; B < nb && joined < 0; ++B) {
                     bool any_hostile = false;
+                    uint32_t dz = 1u;
+                    if (sm) {
+                        bool mine = false;
+#pragma unroll
+                        for (uint32_t k = 0; k < PATCH_ECAP / 32u; ++k) mine = mine || hband[k] == B;
+                        if (!__any_sync(DSIM_FULL, mine)) {
+                            WALK_STAT(0);
+                            joined = (int)B;
+                            break;
+                        }
+                        dz = X.deadnz[B];
+                        if (sz == 0u && dz == 0u && dsim_f64_to_bits(st) != 0x8000000000000000ull) {
+                            WALK_STAT(1);
+                            continue;
+                        }
+                        WALK_STAT(2);
+                    }
                     for (uint32_t j0 = 0; j0 < i; j0 += 32u) {
                         const uint32_t j = j0 + lane;
                         bool hostile = false;
@@ -1724,8 +1797,13 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                             if ((mdx >> l) & 1u) {
                                 if (lane == l) so_mine = so - reduction;
                                 if (so == reduction) { /* the member is wiped out: its stores go to the newcomer */
-                                    st = st + __shfl_sync(DSIM_FULL, sto_mine, l);
+                                    const double got = __shfl_sync(DSIM_FULL, sto_mine, l);
+                                    st = st + got;
                                     if (lane == l) sto_mine = 0.0;
+                                    if (so == 0u && dsim_f64_to_bits(got) != 0ull) { /* one dead member with stores less */
+                                        --dz;
+                                        WALK_STAT(3);
+                                    }
                                 }
                             }
                             if ((mdy >> l) & 1u) sz -= reduction;
@@ -1735,10 +1813,44 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                             M.stored[j] = sto_mine;
                         }
                         __syncwarp();
+                        if (sm && sz == 0u && dz == 0u && dsim_f64_to_bits(st) != 0x8000000000000000ull) { /* the rest are no-ops */
+                            if (j0 + 32u < i) WALK_STAT(4);
+                            break;
+                        }
                     }
-                    if (!any_hostile) joined = (int)B;
+                    if (sm) {
+                        if (lane == 0u) X.deadnz[B] = dz;
+                        __syncwarp();
+                    } else if (!any_hostile) {
+                        joined = (int)B;
+                    }
                 }
                 if (joined < 0) joined = (int)nb++;
+                if (sm) { /* the newcomer's pair, if it is a new one; its own remains, if it came through dead */
+                    bool mine = false;
+#pragma unroll
+                    for (uint32_t k = 0; k < PATCH_ECAP / 32u; ++k) {
+                        const uint32_t e = lane + 32u * k;
+                        mine = mine || (e < en && X.eband[e] == (uint32_t)joined && X.ecult[e] == cf);
+                    }
+                    if (!__any_sync(DSIM_FULL, mine)) {
+                        if (en < PATCH_ECAP) {
+                            if (lane == 0u) {
+                                X.ecult[en] = cf;
+                                X.eband[en] = (uint32_t)joined;
+                                X.efirst[en] = i;
+                            }
+                            ++en;
+                        } else {
+                            WALK_STAT(5);
+                            sm = false;
+                        }
+                    }
+                    if (sm && sz == 0u && dsim_f64_to_bits(st) != 0ull) {
+                        WALK_STAT(6);
+                        if (lane == 0u) X.deadnz[joined] += 1u;
+                    }
+                }
                 if (lane == 0) {
                     M.band[i] = (uint32_t)joined;
                     M.size[i] = sz;

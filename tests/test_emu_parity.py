@@ -91,6 +91,42 @@ def test_crowded_nodes_around_the_culture_list_limit(oracle, emu, synth, n_cultu
     pc.run_lockstep(o, d, 2, by_parts=False, hist_cap=96)
 
 
+def _walk_stats(lib):
+    import ctypes as C
+    return list((C.c_ulonglong * 8).in_dll(lib, "dsim_walk_stats"))
+
+
+def test_walk_shortcuts_are_taken_and_exact(oracle, emu, synth):
+    """The walk of the hostile newcomers (patch_node) joins a band without hostile (band, culture) pair unscanned, passes
+    a hostile band unscanned once the newcomer is dead and the band holds no dead member with stores, stops a scan where
+    the newcomer died, and counts dead members with stores per band.  The CPU build counts each shortcut
+    (dsim_walk_stats): the scenario must take every one of them and still equal the oracle bit for bit.  Families with
+    stores of -0.0 are in it: for them `stores + 0.0` is not a no-op and the shortcuts must stand back."""
+    def edit(fam):
+        pc.hostile_cultures(6)(fam)
+        fam.stored[::7] = -0.0
+    before = _walk_stats(emu)
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=edit)
+    pc.run_lockstep(o, d, 4, hist_cap=96)
+    joined, passed, scanned, took_stores, stopped, overflow, died = [b - a for a, b in zip(before, _walk_stats(emu))][:7]
+    assert joined > 50 and passed > 50 and scanned > 50 and stopped > 10 and died > 50, (joined, passed, scanned, stopped, died)
+    assert took_stores > 0, "a dead member's stores must have been taken by a later newcomer"
+    assert overflow == 0
+
+
+def test_cultures_hostile_to_themselves(oracle, emu, synth):
+    """cooperation_threshold 0, exclusive: nobody cooperates, not even with its own culture, so every member is a band
+    of its own and a culture sits in as many bands as it has members: the (band, culture) list of the walk outgrows its
+    64 pairs on the crowded nodes and the walk falls back to scanning every band."""
+    def edit(p):
+        p.cooperation_threshold = 0
+        p.cooperation_inclusive = 0
+    before = _walk_stats(emu)[5]
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 1600, n_occupied=8, hist_cap=96, params_edit=edit, families_edit=pc.hostile_cultures(5))
+    pc.run_lockstep(o, d, 2, hist_cap=96)
+    assert _walk_stats(emu)[5] > before, "the pair list must have overflowed"
+
+
 def test_mid_sized_nodes(oracle, emu, synth):
     """Nodes with 9..32 families (k_patch_mid: a warp per node, lane per family), hostile neighbours included."""
     o, d = pc.build_pair(oracle, emu, synth, 20, 24, 1500, n_occupied=80, hist_cap=96)
@@ -207,6 +243,9 @@ o, d = pc.build_pair(oracle, emu_small, synth, 24, 30, 120, params_edit=peaceful
 pc.run_lockstep(o, d, 30, by_parts=False, hist_cap=96, check_every=5)
 # nodes of ~720 families: beyond this build's shared-memory capacity of k_patch_huge (600): its HBM scratch path
 o, d = pc.build_pair(oracle, emu_small, synth, 30, 40, 3600, n_occupied=5, hist_cap=96)
+pc.run_lockstep(o, d, 2, hist_cap=96)
+# the same with four mutually hostile cultures: the walk of the newcomers over working arrays in HBM scratch
+o, d = pc.build_pair(oracle, emu_small, synth, 30, 40, 3600, n_occupied=5, hist_cap=96, families_edit=pc.hostile_cultures(4))
 pc.run_lockstep(o, d, 2, hist_cap=96)
 print("tiny capacities ok")
 """ % os.path.dirname(os.path.abspath(__file__))
