@@ -1561,10 +1561,11 @@ __device__ __forceinline__ double adapt_touch(const StepArgs &a, uint32_t hs, ui
 #endif
 #if defined(DSIM_EMU) /* the CPU debugging build counts the shortcuts of the walk, so that its tests can tell they were taken */
 extern "C" unsigned long long dsim_walk_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define WALK_STAT(k) do { if (lane == 0u) __atomic_fetch_add(&dsim_walk_stats[k], 1ull, __ATOMIC_RELAXED); } while (0)
+#define WALK_STAT_N(k, cnt) do { if (lane == 0u) __atomic_fetch_add(&dsim_walk_stats[k], (unsigned long long)(cnt), __ATOMIC_RELAXED); } while (0)
 #else
-#define WALK_STAT(k) do { } while (0)
+#define WALK_STAT_N(k, cnt) do { } while (0)
 #endif
+#define WALK_STAT(k) WALK_STAT_N(k, 1)
 struct PatchAux {
     uint32_t bstart[257]; /* rank sort: keys bucketed by their top byte */
     uint32_t bcur[256];
@@ -1719,8 +1720,29 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
             }
             __syncwarp();
         }
+        const bool reflexive = dsim_will_cooperate(0ull, 0ull, a.mc.threshold, a.mc.inclusive); /* a culture with itself */
         for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
-            uint32_t todo = __ballot_sync(DSIM_FULL, i0 + lane < n && M.band[i0 + lane] == PATCH_TODO);
+            bool mine_todo = i0 + lane < n && M.band[i0 + lane] == PATCH_TODO;
+            if (sm && reflexive && __any_sync(DSIM_FULL, mine_todo)) {
+                /* A newcomer whose culture band 0 already holds finds no hostile member there (whoever is in band 0 got
+                 * in next to that culture), joins it without a fight and adds no pair: the 32 newcomers of a round are
+                 * tested against the list at once, and only the others take their turns below.  Once a hostile culture
+                 * has turned up on a node, every later member of the node's main culture is such a newcomer. */
+                const uint64_t c = mine_todo ? M.cult[i0 + lane] : 0ull;
+                bool home0 = false;
+                for (uint32_t e = 0; e < en; ++e) home0 = home0 || (X.eband[e] == 0u && X.ecult[e] == c);
+                home0 = home0 && mine_todo;
+                if (home0) {
+                    M.band[i0 + lane] = 0u;
+                    if (M.size[i0 + lane] == 0u && dsim_f64_to_bits(M.stored[i0 + lane]) != 0ull) atomicAdd(&X.deadnz[0], 1u);
+                }
+                const uint32_t homed = __ballot_sync(DSIM_FULL, home0);
+                WALK_STAT_N(7, __popc(homed));
+                (void)homed;
+                mine_todo = mine_todo && !home0;
+                __syncwarp(); /* the band writes are visible to the turns below */
+            }
+            uint32_t todo = __ballot_sync(DSIM_FULL, mine_todo);
             while (todo != 0u) {
                 const uint32_t i = i0 + (uint32_t)(__ffs((int)todo) - 1);
                 todo &= todo - 1u;
@@ -1964,10 +1986,22 @@ __device__ __forceinline__ void patch_node(const StepArgs &a, const PatchMem &M,
                     const bool in = j < n && M.band[j] == B;
                     const double cj = in ? M.contrib[j] : 0.0;
                     uint32_t m = __ballot_sync(DSIM_FULL, in);
-                    while (m != 0u) { /* the band's members of this round, one sequential add each (lib.rs:2040-2047) */
-                        const int l = __ffs((int)m) - 1;
-                        m &= m - 1u;
-                        eff = eff + __shfl_sync(DSIM_FULL, cj, l);
+                    /* the band's members of this round, one sequential add each (lib.rs:2040-2047).  The adds are a chain
+                     * whatever is done; what can be taken off the chain is the fetch of the next term: a round that is
+                     * mostly this band's (the main band of a node of a thousand families) issues its 32 shuffles back to
+                     * back and skips the terms of other bands by predicate */
+                    if (__popc(m) >= 16) {
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) {
+                            const double v = __shfl_sync(DSIM_FULL, cj, l);
+                            if ((m >> l) & 1u) eff = eff + v;
+                        }
+                    } else {
+                        while (m != 0u) {
+                            const int l = __ffs((int)m) - 1;
+                            m &= m - 1u;
+                            eff = eff + __shfl_sync(DSIM_FULL, cj, l);
+                        }
                     }
                 }
             if (lane == 0u) M.beff[B] = eff;

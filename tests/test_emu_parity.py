@@ -99,7 +99,8 @@ def _walk_stats(lib):
 def test_walk_shortcuts_are_taken_and_exact(oracle, emu, synth):
     """The walk of the hostile newcomers (patch_node) joins a band without hostile (band, culture) pair unscanned, passes
     a hostile band unscanned once the newcomer is dead and the band holds no dead member with stores, stops a scan where
-    the newcomer died, and counts dead members with stores per band.  The CPU build counts each shortcut
+    the newcomer died, counts dead members with stores per band, and settles the newcomers of a culture that band 0
+    already holds 32 at a time.  The CPU build counts each shortcut
     (dsim_walk_stats): the scenario must take every one of them and still equal the oracle bit for bit.  Families with
     stores of -0.0 are in it: for them `stores + 0.0` is not a no-op and the shortcuts must stand back."""
     def edit(fam):
@@ -108,8 +109,9 @@ def test_walk_shortcuts_are_taken_and_exact(oracle, emu, synth):
     before = _walk_stats(emu)
     o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=edit)
     pc.run_lockstep(o, d, 4, hist_cap=96)
-    joined, passed, scanned, took_stores, stopped, overflow, died = [b - a for a, b in zip(before, _walk_stats(emu))][:7]
+    joined, passed, scanned, took_stores, stopped, overflow, died, homed = [b - a for a, b in zip(before, _walk_stats(emu))]
     assert joined > 50 and passed > 50 and scanned > 50 and stopped > 10 and died > 50, (joined, passed, scanned, stopped, died)
+    assert homed > 50, "newcomers of a culture band 0 holds must have been settled a round at a time"
     assert took_stores > 0, "a dead member's stores must have been taken by a later newcomer"
     assert overflow == 0
 
