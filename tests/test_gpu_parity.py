@@ -345,6 +345,30 @@ def test_reach_table_device_vs_host_at_c2(gpu_lib, synth):
 
 
 @pytest.mark.gpu
+def test_walk_shortcuts_with_negative_zero_stores(oracle, gpu_lib, synth):
+    """The walk of the hostile newcomers passes bands unscanned and settles band 0's own culture 32 at a time
+    (tests/test_emu_parity.py::test_walk_shortcuts_are_taken_and_exact counts the shortcuts on the CPU build); here the
+    same scenario on the device, stores of -0.0 included (for those `stores + 0.0` is not a no-op)."""
+    def edit(fam):
+        pc.hostile_cultures(6)(fam)
+        fam.stored[::7] = -0.0
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=edit)
+    pc.run_lockstep(o, d, 4, hist_cap=96)
+
+
+@pytest.mark.gpu
+def test_cultures_hostile_to_themselves(oracle, gpu_lib, synth):
+    """cooperation_threshold 0, exclusive: every member a band of its own; the (band, culture) list of the walk
+    overflows and every band is scanned."""
+    def edit(p):
+        p.cooperation_threshold = 0
+        p.cooperation_inclusive = 0
+    o, d = pc.build_pair(oracle, gpu_lib, synth, 30, 40, 1600, n_occupied=8, hist_cap=96, params_edit=edit,
+                         families_edit=pc.hostile_cultures(5))
+    pc.run_lockstep(o, d, 2, hist_cap=96)
+
+
+@pytest.mark.gpu
 def test_long_run_in_batches(oracle, gpu_lib, synth):
     """400 seasons enqueued 25 at a time (no host look at the state inside a batch: the adaptive interval between the
     library's own checks of the live count, capacity growth and the graph re-captures that follow it, the deferred
