@@ -17,5 +17,5 @@ python tools/ncu_sectors.py gpurun_out/r02_k_move.ncu-rep k_move "$fam" 24 > pro
 cp gpurun_out/r02_launches.csv profiles/r02_launches.csv
 python tools/launch_table.py profiles/r02_launches.csv "python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 --no-graphs" > profiles/r02_launches.md
 cp gpurun_out/r02_bench_n1.json gpurun_out/r02_bench_n1_20.json gpurun_out/r02_bench_reference.json profiles/
-python tools/sass_summary.py > profiles/r02_sass.md
+python tools/sass_summary.py k_move k_patch_small k_patch_one k_children k_patch_mid k_patch k_patch_huge k_lifecycle k_segments k_scatter > profiles/r02_sass.md
 echo "profiles refreshed: $fam families on $occ patches"
