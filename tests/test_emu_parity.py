@@ -129,6 +129,25 @@ def test_cultures_hostile_to_themselves(oracle, emu, synth):
     assert _walk_stats(emu)[5] > before, "the pair list must have overflowed"
 
 
+@pytest.mark.parametrize("bits,threshold,inclusive", [(5, 2, 0), (6, 3, 0), (4, 1, 0), (5, 1, 1), (3, 2, 1)])
+def test_partially_cooperating_cultures(oracle, emu, synth, bits, threshold, inclusive):
+    """Cultures of a few bits with a threshold inside their range: cooperation is not transitive, bands are cliques of
+    cultures close to one another, band 0 holds several cultures and turns hostile to some newcomers and not to others
+    — the (band, culture) list of the walk decides joins and passes on more than "same culture or not"."""
+    def cultures(fam):
+        fam.culture[:] = np.random.default_rng(bits * 10 + threshold).integers(0, 1 << bits, len(fam.culture)).astype(np.uint64)
+    def params(p):
+        p.cooperation_threshold = threshold
+        p.cooperation_inclusive = inclusive
+    before = _walk_stats(emu)
+    o, d = pc.build_pair(oracle, emu, synth, 30, 40, 2000, n_occupied=8, hist_cap=96, families_edit=cultures, params_edit=params)
+    pc.run_lockstep(o, d, 3, by_parts=False, hist_cap=96)
+    o, d = pc.build_pair(oracle, emu, synth, 20, 24, 1500, n_occupied=60, hist_cap=96, families_edit=cultures, params_edit=params)
+    pc.run_lockstep(o, d, 3, by_parts=False, hist_cap=96)
+    joined, passed, scanned = [b - a for a, b in zip(before, _walk_stats(emu))][:3]
+    assert joined > 0 and scanned > 0, (joined, passed, scanned)
+
+
 def test_mid_sized_nodes(oracle, emu, synth):
     """Nodes with 9..32 families (k_patch_mid: a warp per node, lane per family), hostile neighbours included."""
     o, d = pc.build_pair(oracle, emu, synth, 20, 24, 1500, n_occupied=80, hist_cap=96)
